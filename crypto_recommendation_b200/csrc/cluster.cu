@@ -1,0 +1,1051 @@
+// cluster.cu -- lib/clustering_phases of the reference on the GPU:
+//   K5 Lloyd assignment (tiled FP64 pair scan + fused warp-shuffle argmin), cluster sums / k-means
+//   update, K6 k-means++ rounds, K7 LSH / hypercube range-search assignment, K8 PAM medoid update,
+//   K11 silhouette.
+#include <algorithm>
+#include <climits>
+#include <cub/cub.cuh>
+#include <random>
+
+#include "pair_tile.cuh"
+#include "rowwalk.cuh"
+#include "tables.cuh"
+
+void crx_cube_probe_sequence(int home, int probes, int k, std::vector<int>& seq);  // hash.cu
+
+// ------------------------------------------------------------------------------------------------
+// centroid staging: [K][D] doubles -> padded [K][ld] + exact sums of squares
+// ------------------------------------------------------------------------------------------------
+__global__ void pad_centroids_kernel(const double* __restrict__ C, int K, int D, int ld, double* __restrict__ out,
+                                     double* __restrict__ csqn) {
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= K) return;
+    double acc = 0.0;
+    for (int i = 0; i < ld; i++) {
+        double v = i < D ? C[(size_t)c * D + i] : 0.0;
+        out[(size_t)c * ld + i] = v;
+        if (i < D) acc = __dadd_rn(acc, __dmul_rn(v, v));
+    }
+    csqn[c] = acc;
+}
+
+struct Centroids {
+    DevBuf<double> pad, sqn;
+    IoBuf<double> in;
+    int K = 0, ld = 0;
+    int stage(crx_ctx* c, const double* C, int cmem, int K_, int D, int ld_) {
+        K = K_; ld = ld_;
+        CRX_TRY(in.bind(c, C, (size_t)K * D, cmem, true));
+        CRX_TRY(pad.alloc(c, (size_t)K * ld));
+        CRX_TRY(sqn.alloc(c, K));
+        CRX_KERNEL(c, "pad_centroids");
+        pad_centroids_kernel<<<crx_grid(K, 128), 128, 0, c->stream>>>(in.dev, K, D, ld, pad.p, sqn.p);
+        CRX_CUDA(cudaGetLastError());
+        return CRX_OK;
+    }
+};
+
+template <typename T>
+__global__ void gather_rows_kernel(const T* __restrict__ x, int ld, int D, const int32_t* __restrict__ rows, int K,
+                                   double* __restrict__ out /* [K][D] */) {
+    int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= K * D) return;
+    int c = e / D, i = e - c * D;
+    out[e] = (double)x[(size_t)rows[c] * ld + i];
+}
+
+// rows of `pts` as a [K][D] double matrix on the device
+static int gather_rows(crx_ctx* c, const crx_points* p, const int32_t* d_rows, int K, double* d_out) {
+    CRX_KERNEL(c, "gather_rows");
+    int g = crx_grid((int64_t)K * p->d, 256);
+    if (p->x64) gather_rows_kernel<double><<<g, 256, 0, c->stream>>>(p->x64, p->ld, p->d, d_rows, K, d_out);
+    else gather_rows_kernel<float><<<g, 256, 0, c->stream>>>(p->x32, p->ld, p->d, d_rows, K, d_out);
+    CRX_CUDA(cudaGetLastError());
+    return CRX_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K5: Lloyd assignment.  One CTA = 64 points, all K centroids streamed through shared memory in
+// tiles of 64; each warp owns 8 points, each lane 2 centroids per tile; the argmin over centroids
+// is lane-local across tiles and finishes with one warp-shuffle reduction per point.
+//   Euclidean: FORM_DIFF_EXACT => the sums are the reference's own values, so labels and distances
+//              are bit-exact including ties (lowest index wins, assignment.hpp:67).
+//   cosine:    FORM_DOT for the scan, winner's distance recomputed with the compensated dot product.
+// ------------------------------------------------------------------------------------------------
+template <typename T, int METRIC>
+__global__ void __launch_bounds__(pt::NT)
+lloyd_scan_kernel(const T* __restrict__ x, int ld, int D, const double* __restrict__ sqn, const int32_t* __restrict__ rowmap,
+                  int64_t nrows, const double* __restrict__ cent, const double* __restrict__ csqn, int K,
+                  int32_t* __restrict__ labels, double* __restrict__ dists) {
+    extern __shared__ double sm[];
+    double* As = sm;
+    double* Bs = sm + pt::BM * ld;
+    double* cn = Bs + pt::BN * ld;  // [BN] sqrt of centroid norms (cosine)
+    int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    int64_t r0 = (int64_t)blockIdx.x * pt::BM;
+    pt::load_a_tile<T>(As, x, ld, rowmap, r0, nrows);
+
+    double best_v[pt::RW];
+    int best_i[pt::RW];
+    double xn[pt::RW];
+    unsigned nan0 = 0;
+#pragma unroll
+    for (int r = 0; r < pt::RW; r++) {
+        best_v[r] = INFINITY; best_i[r] = INT_MAX;
+        int64_t pos = r0 + warp * pt::RW + r;
+        xn[r] = 0.0;
+        if (METRIC == CRX_COSINE && pos < nrows) xn[r] = __dsqrt_rn(sqn[rowmap ? rowmap[pos] : pos]);
+    }
+    for (int c0 = 0; c0 < K; c0 += pt::BN) {
+        __syncthreads();
+        pt::load_b_tile<double>(Bs, cent, ld, nullptr, c0, K);
+        if (METRIC == CRX_COSINE && threadIdx.x < pt::BN) {
+            int c = c0 + threadIdx.x;
+            cn[threadIdx.x] = c < K ? __dsqrt_rn(csqn[c]) : 1.0;
+        }
+        __syncthreads();
+        double acc[pt::RW][2];
+        pt::tile_mac<METRIC == CRX_EUCLIDEAN ? pt::FORM_DIFF_EXACT : pt::FORM_DOT>(As, Bs, ld, warp, lane, acc);
+#pragma unroll
+        for (int cc = 0; cc < 2; cc++) {
+            int col = c0 + 2 * lane + cc;
+            if (col < K) {
+#pragma unroll
+                for (int r = 0; r < pt::RW; r++) {
+                    if (METRIC == CRX_EUCLIDEAN) {
+                        if (pt::euclid_better(acc[r][cc], col, best_v[r], best_i[r])) { best_v[r] = acc[r][cc]; best_i[r] = col; }
+                    } else {
+                        double dist = __dsub_rn(1.0, __ddiv_rn(acc[r][cc], __dmul_rn(xn[r], cn[2 * lane + cc])));
+                        if (col == 0 && dist != dist) nan0 |= 1u << r;  // `min == -1` takes centroid 0 even when NaN
+                        if (pt::plain_better(dist, col, best_v[r], best_i[r])) { best_v[r] = dist; best_i[r] = col; }
+                    }
+                }
+            }
+        }
+    }
+    // warp reduction per row
+#pragma unroll
+    for (int r = 0; r < pt::RW; r++) {
+        double v = best_v[r];
+        int i = best_i[r];
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            double ov = __shfl_xor_sync(0xffffffffu, v, off);
+            int oi = __shfl_xor_sync(0xffffffffu, i, off);
+            bool take = METRIC == CRX_EUCLIDEAN ? pt::euclid_better(ov, oi, v, i) : pt::plain_better(ov, oi, v, i);
+            if (take) { v = ov; i = oi; }
+        }
+        best_v[r] = v; best_i[r] = i;
+    }
+    unsigned nan0_all = __shfl_sync(0xffffffffu, nan0, 0);  // column 0 lives in lane 0
+    // lane r finishes row r
+    if (lane < pt::RW) {
+        int r = lane;
+        double v = 0.0; int i = 0;
+#pragma unroll
+        for (int rr = 0; rr < pt::RW; rr++) if (rr == r) { v = best_v[rr]; i = best_i[rr]; }
+        int64_t pos = r0 + warp * pt::RW + r;
+        if (pos < nrows) {
+            int64_t row = rowmap ? (int64_t)rowmap[pos] : pos;
+            double dist;
+            if (METRIC == CRX_EUCLIDEAN) dist = __dsqrt_rn(v);
+            else {
+                if ((nan0_all >> r) & 1u) { i = 0; dist = v = nan(""); }
+                else {
+                    const double* a = As + (warp * pt::RW + r) * ld;
+                    dist = __dsub_rn(1.0, cos_sim_exact(a, cent + (size_t)i * ld, D, sqn[row], csqn[i]));
+                }
+            }
+            labels[row] = i;
+            dists[row] = dist;
+        }
+    }
+}
+
+__global__ void self_assign_kernel(const int32_t* __restrict__ crow, int K, int32_t* labels, double* dists) {
+    if (blockIdx.x == 0 && threadIdx.x == 0)
+        for (int c = 0; c < K; c++)  // sequential: a later centroid aliasing the same row wins (assignment.hpp:77-78)
+            if (crow[c] >= 0) { labels[crow[c]] = c; dists[crow[c]] = 0.0; }
+}
+
+__global__ void compact_unassigned_kernel(const int32_t* __restrict__ labels, int64_t n, int32_t* __restrict__ rows, int* count) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && labels[i] == -1) rows[atomicAdd(count, 1)] = (int32_t)i;
+}
+
+static int lloyd_scan(crx_ctx* c, const crx_points* p, const int32_t* d_rowmap, int64_t nrows, const Centroids& cen,
+                      int metric, int32_t* d_labels, double* d_dists) {
+    if (nrows == 0) return CRX_OK;
+    int ld = p->ld;
+    size_t smem = pt::smem_bytes(ld) + pt::BN * sizeof(double);
+    int grid = (int)((nrows + pt::BM - 1) / pt::BM);
+    CRX_KERNEL(c, "lloyd_scan");
+#define LAUNCH_L(T, M, xptr)                                                                                       \
+    do {                                                                                                           \
+        CRX_CUDA(cudaFuncSetAttribute(lloyd_scan_kernel<T, M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        lloyd_scan_kernel<T, M><<<grid, pt::NT, smem, c->stream>>>(xptr, ld, p->d, p->sqn, d_rowmap, nrows, cen.pad.p,   \
+                                                                   cen.sqn.p, cen.K, d_labels, d_dists);          \
+    } while (0)
+    if (p->x64) { if (metric == CRX_EUCLIDEAN) LAUNCH_L(double, CRX_EUCLIDEAN, p->x64); else LAUNCH_L(double, CRX_COSINE, p->x64); }
+    else { if (metric == CRX_EUCLIDEAN) LAUNCH_L(float, CRX_EUCLIDEAN, p->x32); else LAUNCH_L(float, CRX_COSINE, p->x32); }
+#undef LAUNCH_L
+    CRX_CUDA(cudaGetLastError());
+    return CRX_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// cluster sums (the data-parallel half of k_means, update.hpp:50-58): rows are grouped by label
+// with the stable segment sort, every (cluster, chunk of CH rows) is summed by one CTA whose thread
+// j owns coordinate j and walks the rows IN INPUT ORDER; chunk partials are then added in order.
+// A cluster of <= CH members therefore gets the reference's own sequential sum, bit for bit.
+// ------------------------------------------------------------------------------------------------
+constexpr int SUM_CH = 1024;
+
+template <typename T>
+__global__ void __launch_bounds__(128)
+chunk_sums_kernel(const T* __restrict__ x, int ld, int D, const int32_t* __restrict__ perm, const int32_t* __restrict__ off,
+                  const int32_t* __restrict__ chunk_cluster, const int32_t* __restrict__ chunk_index,
+                  double* __restrict__ partial /* [nchunks][D] */) {
+    int ch = blockIdx.x;
+    int cl = chunk_cluster[ch];
+    int begin = off[cl] + chunk_index[ch] * SUM_CH;
+    int end = min(off[cl + 1], begin + SUM_CH);
+    int j = threadIdx.x;
+    if (j >= D) return;
+    double acc = 0.0;
+    int r = begin;
+    for (; r + 4 <= end; r += 4) {
+        double v0 = (double)x[(size_t)perm[r] * ld + j];
+        double v1 = (double)x[(size_t)perm[r + 1] * ld + j];
+        double v2 = (double)x[(size_t)perm[r + 2] * ld + j];
+        double v3 = (double)x[(size_t)perm[r + 3] * ld + j];
+        acc = __dadd_rn(acc, v0); acc = __dadd_rn(acc, v1); acc = __dadd_rn(acc, v2); acc = __dadd_rn(acc, v3);
+    }
+    for (; r < end; r++) acc = __dadd_rn(acc, (double)x[(size_t)perm[r] * ld + j]);
+    partial[(size_t)ch * D + j] = acc;
+}
+
+__global__ void combine_sums_kernel(const double* __restrict__ partial, const int32_t* __restrict__ chunk_first, int K, int D,
+                                    const int32_t* __restrict__ off, double* __restrict__ sums, long long* __restrict__ counts) {
+    int cl = blockIdx.x, j = threadIdx.x;
+    int n = off[cl + 1] - off[cl];
+    if (j == 0) counts[cl] = n;
+    if (j >= D) return;
+    int nch = (n + SUM_CH - 1) / SUM_CH;
+    double acc = 0.0;
+    for (int ch = 0; ch < nch; ch++) {
+        double v = partial[(size_t)(chunk_first[cl] + ch) * D + j];
+        acc = ch == 0 ? v : __dadd_rn(acc, v);
+    }
+    sums[(size_t)cl * D + j] = acc;
+}
+
+// means, convergence (update.hpp:57-80)
+__global__ void kmeans_finish_kernel(const double* __restrict__ sums, const long long* __restrict__ counts,
+                                     const double* __restrict__ oldc, int K, int D, int metric, double min_dist,
+                                     double* __restrict__ newc, int* __restrict__ moved) {
+    int cl = blockIdx.x * blockDim.x + threadIdx.x;
+    if (cl >= K) return;
+    double div = (double)counts[cl];
+    double na = 0.0, nb = 0.0, acc = 0.0, s = 0.0, comp = 0.0;
+    for (int i = 0; i < D; i++) {
+        double v = sums[(size_t)cl * D + i];
+        if (div != 0.0) v = __ddiv_rn(v, div);  // divDimensionsByD skips count 0 (cust_vector.hpp:189)
+        newc[(size_t)cl * D + i] = v;
+        double o = oldc[(size_t)cl * D + i];
+        if (metric == CRX_EUCLIDEAN) {
+            double t = __dsub_rn(v, o);
+            acc = __dadd_rn(acc, __dmul_rn(t, t));
+        } else {
+            na = __dadd_rn(na, __dmul_rn(v, v));
+            nb = __dadd_rn(nb, __dmul_rn(o, o));
+            double p, pe, se;
+            two_prod(v, o, p, pe);
+            two_sum(s, p, s, se);
+            comp = __dadd_rn(comp, __dadd_rn(pe, se));
+        }
+    }
+    double dist = metric == CRX_EUCLIDEAN ? __dsqrt_rn(acc) : __dsub_rn(1.0, cos_sim_from(__dadd_rn(s, comp), na, nb));
+    if (dist > min_dist) atomicExch(moved, 1);
+}
+
+__global__ void select_centroids_kernel(const double* __restrict__ newc, const double* __restrict__ oldc, size_t n,
+                                        const int* __restrict__ moved, double* __restrict__ out) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = *moved ? newc[i] : oldc[i];
+}
+
+// ------------------------------------------------------------------------------------------------
+// K6: k-means++ (initialization.hpp:72-156)
+// ------------------------------------------------------------------------------------------------
+template <typename T, int METRIC>
+__global__ void __launch_bounds__(256)
+kpp_update_kernel(const T* __restrict__ x, int ld, int D, const double* __restrict__ sqn, int64_t N, int crow, int first,
+                  double* __restrict__ mind, unsigned long long* __restrict__ maxbits) {
+    __shared__ rw::WarpTile tiles[8];
+    __shared__ double vec[128];
+    int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int k = threadIdx.x; k < ld; k += blockDim.x) vec[k] = (double)x[(size_t)crow * ld + k];
+    __syncthreads();
+    int64_t row = ((int64_t)blockIdx.x * 8 + warp) * 32 + lane;
+    bool valid = row < N;
+    double d = rw::dist_rows<T, METRIC>(x, ld, D, valid ? row : -1, vec, valid ? sqn[row] : 1.0, sqn[crow], tiles[warp]);
+    double m = 0.0;
+    if (valid) {
+        m = mind[row];
+        if (first || d < m) { m = d; mind[row] = d; }  // running form of the `min == -1 || d < min` scan
+    }
+    // max over values > 0 (max_for_normalizing starts at 0 and uses '>', initialization.hpp:116-117)
+    double mx = (valid && m > 0.0) ? m : 0.0;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, off));
+    if (lane == 0 && mx > 0.0) atomicMax(maxbits, (unsigned long long)__double_as_longlong(mx));
+}
+
+// p_v = (min_d / max)^2 (initialization.hpp:122-127, before the running sum)
+__global__ void kpp_prob_kernel(const double* __restrict__ mind, int64_t N, const unsigned long long* __restrict__ maxbits,
+                                double* __restrict__ p) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    double mx = __longlong_as_double((long long)*maxbits);
+    double t = __ddiv_rn(mind[i], mx);
+    p[i] = __dmul_rn(t, t);
+}
+
+// first index with x <= P[idx] (the reference's custom binary search, initialization.hpp:134-149)
+__global__ void kpp_pick_kernel(const double* __restrict__ P, int64_t N, double x, int32_t* __restrict__ chosen,
+                                unsigned long long* counters) {
+    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    int64_t lo = 0, hi = N - 1, ch = 0;
+    if (x > P[lo]) {
+        while (hi - lo > 1) {
+            int64_t m = lo + (hi - lo) / 2;
+            if (x <= P[m]) hi = m; else lo = m;
+        }
+        ch = hi;
+    }
+    *chosen = (int32_t)ch;
+    double tol = 1e-12 * P[N - 1];
+    if (fabs(x - P[ch]) <= tol || (ch > 0 && fabs(x - P[ch - 1]) <= tol)) atomicAdd(&counters[CRX_CNT_KPP_NEAR], 1ull);
+}
+
+// ------------------------------------------------------------------------------------------------
+// K7: range-search assignment (assignment.hpp:156-217).
+//
+// The reference sweeps the centroids in order and doubles the radius after EVERY centroid, so the
+// global step j = sweep*K + c tests the annulus [r0 2^(j-1), r0 2^j) ([0, r0) for j = 0).  The
+// annuli partition [0, inf), an assigned vector always has dist < min_radius at every later step,
+// hence it is never reconsidered: a vector ends up at the FIRST step j at which some centroid
+// c = j mod K has it in its bucket list with d(c, v) inside annulus j.  That is an order-free
+// statement: every (centroid, bucket member) pair is evaluated independently (exact FP64
+// distance), fires at most at one step a(d) and only if a(d) == c (mod K); atomicMin over the
+// firing steps gives the assignment.  The reference stops after the first sweep that assigned
+// nothing; the per-sweep counts reproduce that cut-off afterwards.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int annulus_index(double d, double r0) {
+    if (!(r0 > 0.0) || !(d >= 0.0)) return -1;  // radius stays <= 0 for ever / NaN or negative distance never fires
+    if (d < r0) return 0;
+    int j = ilogb(d / r0) + 1;
+    if (j < 1) j = 1;
+    while (j > 1 && d < ldexp(r0, j - 1)) j--;
+    while (!(d < ldexp(r0, j))) { j++; if (j > 4096) return -1; }
+    return j;
+}
+
+template <typename T, int METRIC>
+__global__ void __launch_bounds__(256)
+range_fire_kernel(const T* __restrict__ x, int ld, int D, const double* __restrict__ sqn, int K, const int32_t* __restrict__ crow,
+                  double r0, int nseg,                        // segments per centroid
+                  const int32_t* __restrict__ seg_begin,      // [K*nseg] start position in seg_perm space
+                  const int32_t* __restrict__ seg_end,        // [K*nseg]
+                  const int32_t* const* __restrict__ seg_perm,  // [nseg] position -> row (per table) or one shared perm
+                  const int32_t* __restrict__ bucket, int64_t N,  // [L][N] bucket ids for the duplicate filter (LSH) or NULL
+                  int chunk, int* __restrict__ key) {
+    __shared__ rw::WarpTile tiles[8];
+    __shared__ double vec[128];
+    int cs = blockIdx.x;  // centroid * nseg + seg
+    int c = cs / nseg, sgi = cs - c * nseg;
+    int begin = seg_begin[cs] + blockIdx.y * chunk;
+    int end = min(seg_end[cs], begin + chunk);
+    if (begin >= end) return;
+    int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    int cr = crow[c];
+    for (int k = threadIdx.x; k < ld; k += blockDim.x) vec[k] = (double)x[(size_t)cr * ld + k];
+    __syncthreads();
+    const int32_t* perm = seg_perm[bucket ? sgi : 0];
+    double ncr = sqn[cr];
+    for (int base = begin + warp * 32; base < end; base += 256) {
+        int pos = base + lane;
+        int64_t row = pos < end ? (int64_t)perm[pos] : -1;
+        if (row >= 0 && bucket) {  // union of the L buckets: count a vector in the first table that holds it
+            for (int l = 0; l < sgi; l++)
+                if (bucket[(size_t)l * N + row] == bucket[(size_t)l * N + cr]) { row = -1; break; }
+        }
+        double d = rw::dist_rows<T, METRIC>(x, ld, D, row, vec, row >= 0 ? sqn[row] : 1.0, ncr, tiles[warp]);
+        if (row >= 0) {
+            int a = annulus_index(d, r0);
+            if (a >= 0 && a % K == c) atomicMin(&key[row], a);
+        }
+    }
+}
+
+__global__ void range_hist_kernel(const int* __restrict__ key, int64_t N, int K, int* __restrict__ hist, int nh) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    int a = key[i];
+    if (a != INT_MAX) { int s = a / K; if (s < nh) atomicAdd(&hist[s], 1); }
+}
+
+template <typename T, int METRIC>
+__global__ void __launch_bounds__(256)
+range_finalize_kernel(const T* __restrict__ x, int ld, int D, const double* __restrict__ sqn, int64_t N, int K,
+                      const int32_t* __restrict__ crow, const int* __restrict__ key, int sweep_limit,
+                      int32_t* __restrict__ labels, double* __restrict__ dists) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    int a = key[i];
+    if (a != INT_MAX && a / K < sweep_limit) {
+        int c = a % K;
+        int cr = crow[c];
+        const T* xi = x + (size_t)i * ld;
+        const T* xc = x + (size_t)cr * ld;
+        labels[i] = c;
+        dists[i] = metric_dist_exact(METRIC, xc, xi, D, sqn[cr], sqn[i]);
+    } else {
+        labels[i] = -1;
+        dists[i] = 0.0;
+    }
+}
+
+// min over centroid pairs (utils.hpp:161-178); K is small, one thread per pair row
+template <typename T>
+__global__ void min_pair_kernel(const T* __restrict__ x, int ld, int D, const double* __restrict__ sqn,
+                                const int32_t* __restrict__ crow, int K, int metric, double* __restrict__ rowmin) {
+    int a = blockIdx.x * blockDim.x + threadIdx.x;
+    if (a >= K) return;
+    double m = INFINITY;
+    for (int b = a + 1; b < K; b++) {
+        double d = metric_dist_exact(metric, x + (size_t)crow[a] * ld, x + (size_t)crow[b] * ld, D, sqn[crow[a]], sqn[crow[b]]);
+        if (d < m) m = d;
+    }
+    rowmin[a] = m;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K8: PAM medoid update (update.hpp:90-142).  Row sums of exact pairwise distances: one warp per
+// candidate medoid, lanes over the cluster members; then per cluster the candidates within the
+// summation-order tolerance of the minimum are re-summed sequentially in member order (the
+// reference's order) and the first minimum wins.
+// ------------------------------------------------------------------------------------------------
+template <typename T, int METRIC>
+__global__ void __launch_bounds__(256)
+pam_rowsum_kernel(const T* __restrict__ x, int ld, int D, const double* __restrict__ sqn, const int32_t* __restrict__ perm,
+                  const int32_t* __restrict__ sorted_label, const int32_t* __restrict__ off, int64_t N,
+                  double* __restrict__ rowsum) {
+    __shared__ rw::WarpTile tiles[8];
+    __shared__ double vecs[8][128];
+    int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    int64_t pos = (int64_t)blockIdx.x * 8 + warp;
+    if (pos >= N) return;
+    int cl = sorted_label[pos];
+    int begin = off[cl], end = off[cl + 1];
+    int64_t mrow = perm[pos];
+    rw::stage_vector<T>(x, ld, mrow, vecs[warp]);
+    double nm = sqn[mrow];
+    double acc = 0.0;
+    for (int base = begin; base < end; base += 32) {
+        int p = base + lane;
+        int64_t row = p < end ? (int64_t)perm[p] : -1;
+        double d = rw::dist_rows<T, METRIC>(x, ld, D, row, vecs[warp], row >= 0 ? sqn[row] : 1.0, nm, tiles[warp]);
+        if (row >= 0) acc += d;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) rowsum[pos] = acc;
+}
+
+template <typename T, int METRIC>
+__global__ void __launch_bounds__(256)
+pam_pick_kernel(const T* __restrict__ x, int ld, int D, const double* __restrict__ sqn, const int32_t* __restrict__ perm,
+                const int32_t* __restrict__ off, const double* __restrict__ rowsum, const int32_t* __restrict__ crow,
+                int32_t* __restrict__ new_crow, int* __restrict__ swapped, unsigned long long* counters) {
+    __shared__ double red[256];
+    __shared__ int redi[256];
+    __shared__ int ncand;
+    int cl = blockIdx.x;
+    int begin = off[cl], end = off[cl + 1];
+    int n = end - begin;
+    if (n == 0) { if (threadIdx.x == 0) new_crow[cl] = crow[cl]; return; }
+    double m = INFINITY;
+    for (int p = begin + threadIdx.x; p < end; p += blockDim.x) { double v = rowsum[p]; if (v < m) m = v; }
+    red[threadIdx.x] = m;
+    if (threadIdx.x == 0) ncand = 0;
+    __syncthreads();
+    for (int s = 128; s > 0; s >>= 1) { if (threadIdx.x < s) red[threadIdx.x] = fmin(red[threadIdx.x], red[threadIdx.x + s]); __syncthreads(); }
+    double mn = red[0];
+    __syncthreads();
+    double tol = mn * (8.0 * (double)(n + D) * 1.1102230246251565e-16);
+    // candidates: rows whose parallel sum is within tolerance of the minimum (NaN sums never qualify)
+    int mycount = 0;
+    for (int p = begin + threadIdx.x; p < end; p += blockDim.x) if (rowsum[p] <= mn + tol) mycount++;
+    if (mycount) atomicAdd(&ncand, mycount);
+    __syncthreads();
+    bool exact = ncand > 1;
+    double best = INFINITY;
+    int bestp = INT_MAX;
+    for (int p = begin + threadIdx.x; p < end; p += blockDim.x) {
+        if (rowsum[p] <= mn + tol) {
+            double s = rowsum[p];
+            if (exact) {  // the reference's own sequential sum over members in input order
+                const T* xm = x + (size_t)perm[p] * ld;
+                s = 0.0;
+                for (int q = begin; q < end; q++)
+                    s = __dadd_rn(s, metric_dist_exact(METRIC, xm, x + (size_t)perm[q] * ld, D, sqn[perm[p]], sqn[perm[q]]));
+                atomicAdd(&counters[CRX_CNT_PAM_EXACT], 1ull);
+            }
+            if (s < best || (s == best && p < bestp)) { best = s; bestp = p; }
+        }
+    }
+    red[threadIdx.x] = best; redi[threadIdx.x] = bestp;
+    __syncthreads();
+    for (int s = 128; s > 0; s >>= 1) {
+        if (threadIdx.x < s) {
+            double ov = red[threadIdx.x + s]; int oi = redi[threadIdx.x + s];
+            if (ov < red[threadIdx.x] || (ov == red[threadIdx.x] && oi < redi[threadIdx.x])) { red[threadIdx.x] = ov; redi[threadIdx.x] = oi; }
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        // all sums NaN (cosine with zero vectors): `min_dist_sum == -1 || s < min` keeps member 0
+        int p = redi[0] == INT_MAX ? begin : redi[0];
+        int row = perm[p];
+        if (row != crow[cl]) { new_crow[cl] = row; atomicExch(swapped, 1); }
+        else new_crow[cl] = crow[cl];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K11: silhouette (silhouette.hpp:32-144)
+// ------------------------------------------------------------------------------------------------
+__global__ void near_centroid_kernel(const double* __restrict__ cent, const double* __restrict__ csqn, int K, int ld, int D,
+                                     int metric, int32_t* __restrict__ near) {
+    int a = blockIdx.x * blockDim.x + threadIdx.x;
+    if (a >= K) return;
+    double mn = 0.0;
+    int arg = 0;
+    bool first = true;
+    for (int b = 0; b < K; b++) {
+        if (b == a) continue;
+        double d = metric_dist_exact(metric, cent + (size_t)a * ld, cent + (size_t)b * ld, D, csqn[a], csqn[b]);
+        if (first || d < mn) { mn = d; arg = b; first = false; }
+    }
+    near[a] = arg;
+}
+
+template <typename T, int METRIC>
+__global__ void __launch_bounds__(256)
+silhouette_point_kernel(const T* __restrict__ x, int ld, int D, const double* __restrict__ sqn, const int32_t* __restrict__ perm,
+                        const int32_t* __restrict__ sorted_label, const int32_t* __restrict__ off,
+                        const int32_t* __restrict__ near, int64_t N, double* __restrict__ s_out) {
+    __shared__ rw::WarpTile tiles[8];
+    __shared__ double vecs[8][128];
+    int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    int64_t pos = (int64_t)blockIdx.x * 8 + warp;
+    if (pos >= N) return;
+    int cl = sorted_label[pos];
+    int64_t mrow = perm[pos];
+    rw::stage_vector<T>(x, ld, mrow, vecs[warp]);
+    double nm = sqn[mrow];
+    double sums[2];
+    for (int which = 0; which < 2; which++) {
+        int tc = which == 0 ? cl : near[cl];
+        int begin = off[tc], end = off[tc + 1];
+        double acc = 0.0;
+        for (int base = begin; base < end; base += 32) {
+            int p = base + lane;
+            int64_t row = p < end ? (int64_t)perm[p] : -1;
+            double d = rw::dist_rows<T, METRIC>(x, ld, D, row, vecs[warp], row >= 0 ? sqn[row] : 1.0, nm, tiles[warp]);
+            if (row >= 0) acc += d;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        sums[which] = acc;
+    }
+    if (lane == 0) {
+        int n_own = off[cl + 1] - off[cl];
+        int n_nb = off[near[cl] + 1] - off[near[cl]];
+        double a = sums[0], b = sums[1];
+        if (n_own != 1) a = a / (double)(n_own - 1);
+        b = b / (double)n_nb;
+        double mx = a;
+        if (b > a) mx = b;
+        s_out[pos] = (b - a) / mx;
+    }
+}
+
+__global__ void silhouette_reduce_kernel(const double* __restrict__ s, const int32_t* __restrict__ off, int K,
+                                         double* __restrict__ sils, double* __restrict__ raw) {
+    int cl = blockIdx.x * blockDim.x + threadIdx.x;
+    if (cl >= K) return;
+    double acc = 0.0;
+    for (int p = off[cl]; p < off[cl + 1]; p++) acc = acc + s[p];  // member order = input order
+    raw[cl] = acc;
+    sils[cl] = acc / (double)(off[cl + 1] - off[cl]);
+}
+
+__global__ void fill_int_kernel(int* p, int64_t n, int v) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+
+__global__ void gather_int_kernel(const int32_t* __restrict__ src, const int32_t* __restrict__ idx, int n, int32_t* __restrict__ out) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = src[idx[i]];
+}
+
+// ------------------------------------------------------------------------------------------------
+// host drivers
+// ------------------------------------------------------------------------------------------------
+template <typename F32, typename F64>
+static int by_type(const crx_points* p, F32 f32, F64 f64) { return p->x64 ? f64() : f32(); }
+
+static int range_assign_common(crx_ctx* c, const crx_points* p, const int32_t* h_crow, int K, int metric, int nseg,
+                               const std::vector<int32_t>& h_begin, const std::vector<int32_t>& h_end,
+                               const std::vector<const int32_t*>& h_perm, const int32_t* d_bucket, int32_t* labels,
+                               double* dists, int mem, int32_t* before) {
+    int64_t N = p->n;
+    int D = p->d, ld = p->ld;
+    IoBuf<int32_t> lab, bef;
+    IoBuf<double> dis;
+    CRX_TRY(lab.bind(c, labels, N, mem, false));
+    CRX_TRY(dis.bind(c, dists, N, mem, false));
+    CRX_TRY(bef.bind(c, before, N, mem, false));
+    DevBuf<int32_t> d_crow, d_begin, d_end;
+    DevBuf<const int32_t*> d_perm;
+    DevBuf<double> rowmin;
+    DevBuf<int> key, hist;
+    const int NH = 4096;
+    CRX_TRY(d_crow.alloc(c, K)); CRX_TRY(d_begin.alloc(c, h_begin.size())); CRX_TRY(d_end.alloc(c, h_end.size()));
+    CRX_TRY(d_perm.alloc(c, h_perm.size())); CRX_TRY(rowmin.alloc(c, K)); CRX_TRY(key.alloc(c, N)); CRX_TRY(hist.alloc(c, NH));
+    CRX_CUDA(cudaMemcpyAsync(d_crow.p, h_crow, K * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+    CRX_CUDA(cudaMemcpyAsync(d_begin.p, h_begin.data(), h_begin.size() * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+    CRX_CUDA(cudaMemcpyAsync(d_end.p, h_end.data(), h_end.size() * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+    CRX_CUDA(cudaMemcpyAsync(d_perm.p, h_perm.data(), h_perm.size() * sizeof(const int32_t*), cudaMemcpyHostToDevice, c->stream));
+    // r0 = min centroid-centroid distance / 2 (assignment.hpp:161)
+    {
+        CRX_KERNEL(c, "min_pair");
+        if (p->x64) min_pair_kernel<double><<<crx_grid(K, 64), 64, 0, c->stream>>>(p->x64, ld, D, p->sqn, d_crow.p, K, metric, rowmin.p);
+        else min_pair_kernel<float><<<crx_grid(K, 64), 64, 0, c->stream>>>(p->x32, ld, D, p->sqn, d_crow.p, K, metric, rowmin.p);
+    }
+    std::vector<double> h_rowmin(K);
+    CRX_CUDA(cudaMemcpyAsync(h_rowmin.data(), rowmin.p, K * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CRX_CUDA(cudaStreamSynchronize(c->stream));
+    double mn = -1;  // find_min_vector_distance's sentinel: K == 1 leaves -1
+    for (int a = 0; a < K; a++)
+        if (h_rowmin[a] != INFINITY && (mn == -1 || h_rowmin[a] < mn)) mn = h_rowmin[a];
+    double r0 = mn / 2;
+    CRX_CUDA(cudaMemsetAsync(hist.p, 0, NH * sizeof(int), c->stream));
+    { CRX_KERNEL(c, "fill_key"); fill_int_kernel<<<crx_grid(N, 256), 256, 0, c->stream>>>(key.p, N, INT_MAX); }
+    int maxlen = 0;
+    for (size_t i = 0; i < h_begin.size(); i++) maxlen = std::max(maxlen, h_end[i] - h_begin[i]);
+    const int chunk = 8192;
+    dim3 grid((unsigned)(K * nseg), (unsigned)std::max(1, (maxlen + chunk - 1) / chunk));
+    if (maxlen > 0) {
+        CRX_KERNEL(c, "range_fire");
+#define LAUNCH_R(T, M, xptr) range_fire_kernel<T, M><<<grid, 256, 0, c->stream>>>(xptr, ld, D, p->sqn, K, d_crow.p, r0, nseg, d_begin.p, d_end.p, d_perm.p, d_bucket, N, chunk, key.p)
+        if (p->x64) { if (metric == CRX_EUCLIDEAN) LAUNCH_R(double, CRX_EUCLIDEAN, p->x64); else LAUNCH_R(double, CRX_COSINE, p->x64); }
+        else { if (metric == CRX_EUCLIDEAN) LAUNCH_R(float, CRX_EUCLIDEAN, p->x32); else LAUNCH_R(float, CRX_COSINE, p->x32); }
+#undef LAUNCH_R
+    }
+    { CRX_KERNEL(c, "range_hist"); range_hist_kernel<<<crx_grid(N, 256), 256, 0, c->stream>>>(key.p, N, K, hist.p, NH); }
+    std::vector<int> h_hist(NH);
+    CRX_CUDA(cudaMemcpyAsync(h_hist.data(), hist.p, NH * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CRX_CUDA(cudaStreamSynchronize(c->stream));
+    int limit = 0;  // first sweep that assigns nothing ends the do-while (assignment.hpp:216)
+    while (limit < NH && h_hist[limit] > 0) limit++;
+    {
+        CRX_KERNEL(c, "range_finalize");
+#define LAUNCH_F(T, M, xptr) range_finalize_kernel<T, M><<<crx_grid(N, 256), 256, 0, c->stream>>>(xptr, ld, D, p->sqn, N, K, d_crow.p, key.p, limit, lab.dev, dis.dev)
+        if (p->x64) { if (metric == CRX_EUCLIDEAN) LAUNCH_F(double, CRX_EUCLIDEAN, p->x64); else LAUNCH_F(double, CRX_COSINE, p->x64); }
+        else { if (metric == CRX_EUCLIDEAN) LAUNCH_F(float, CRX_EUCLIDEAN, p->x32); else LAUNCH_F(float, CRX_COSINE, p->x32); }
+#undef LAUNCH_F
+    }
+    CRX_CUDA(cudaGetLastError());
+    if (before) {
+        CRX_CUDA(cudaMemcpyAsync(bef.dev, lab.dev, N * sizeof(int32_t), cudaMemcpyDeviceToDevice, c->stream));
+        CRX_TRY(bef.flush());
+    }
+    // lloyds_for_remaining over the unassigned rows (assignment.hpp:121-124), then the self-assignment
+    DevBuf<int32_t> rows;
+    DevBuf<int> cnt;
+    DevBuf<double> cmat;
+    CRX_TRY(rows.alloc(c, N)); CRX_TRY(cnt.alloc(c, 1)); CRX_TRY(cmat.alloc(c, (size_t)K * D));
+    CRX_CUDA(cudaMemsetAsync(cnt.p, 0, sizeof(int), c->stream));
+    { CRX_KERNEL(c, "compact_unassigned"); compact_unassigned_kernel<<<crx_grid(N, 256), 256, 0, c->stream>>>(lab.dev, N, rows.p, cnt.p); }
+    int h_cnt = 0;
+    CRX_CUDA(cudaMemcpyAsync(&h_cnt, cnt.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CRX_TRY(gather_rows(c, p, d_crow.p, K, cmat.p));
+    Centroids cen;
+    CRX_TRY(cen.stage(c, cmat.p, CRX_DEVICE, K, D, ld));
+    CRX_CUDA(cudaStreamSynchronize(c->stream));
+    CRX_TRY(lloyd_scan(c, p, rows.p, h_cnt, cen, metric, lab.dev, dis.dev));
+    { CRX_KERNEL(c, "self_assign"); self_assign_kernel<<<1, 32, 0, c->stream>>>(d_crow.p, K, lab.dev, dis.dev); }
+    CRX_CUDA(cudaGetLastError());
+    CRX_TRY(lab.flush());
+    CRX_TRY(dis.flush());
+    CRX_CUDA(cudaStreamSynchronize(c->stream));
+    return CRX_OK;
+}
+
+extern "C" {
+
+int crx_rand_selection(crx_ctx* c, const crx_points* p, int K, uint64_t seed, int32_t* out) {
+    CRX_REQUIRE(c && p && out, "NULL argument");
+    CRX_REQUIRE(K >= 1 && K <= p->n, "cluster_num must be in [1, N]");
+    // initialization.hpp:40-68: host-only integer logic (ids are unique row indices)
+    std::default_random_engine e;
+    e.seed((unsigned long)seed);
+    std::uniform_int_distribution<int> ui(0, (int)p->n - 1);
+    out[0] = ui(e);
+    for (int i = 1; i < K; i++) {
+        int r;
+        bool clash;
+        do {
+            r = ui(e);
+            clash = false;
+            for (int j = 0; j < i; j++) if (out[j] == r) { clash = true; break; }
+        } while (clash);
+        out[i] = r;
+    }
+    return CRX_OK;
+}
+
+int crx_k_means_pp(crx_ctx* c, const crx_points* p, int K, int metric, uint64_t seed, int32_t* out) {
+    CRX_REQUIRE(c && p && out, "NULL argument");
+    CRX_REQUIRE(K >= 1, "cluster_num");
+    CRX_REQUIRE(metric == CRX_EUCLIDEAN || metric == CRX_COSINE, "metric");
+    CRX_CUDA(cudaSetDevice(c->device));
+    int64_t N = p->n;
+    std::default_random_engine e;
+    e.seed((unsigned long)seed);
+    std::uniform_int_distribution<int> ui(0, (int)N - 1);
+    out[0] = ui(e);
+    DevBuf<double> mind, prob, P;
+    DevBuf<unsigned long long> mx;
+    DevBuf<int32_t> chosen;
+    DevBuf<char> tmp;
+    CRX_TRY(mind.alloc(c, N)); CRX_TRY(prob.alloc(c, N)); CRX_TRY(P.alloc(c, N)); CRX_TRY(mx.alloc(c, 1)); CRX_TRY(chosen.alloc(c, 1));
+    size_t bytes = 0;
+    CRX_CUDA(cub::DeviceScan::InclusiveSum(nullptr, bytes, prob.p, P.p, (int)N, c->stream));
+    CRX_TRY(tmp.alloc(c, bytes));
+    int gridu = (int)((N + 255) / 256);
+    for (int i = 1; i < K; i++) {
+        CRX_CUDA(cudaMemsetAsync(mx.p, 0, sizeof(unsigned long long), c->stream));
+        {
+            CRX_KERNEL(c, "kpp_update");
+#define LAUNCH_K(T, M, xptr) kpp_update_kernel<T, M><<<gridu, 256, 0, c->stream>>>(xptr, p->ld, p->d, p->sqn, N, out[i - 1], i == 1, mind.p, mx.p)
+            if (p->x64) { if (metric == CRX_EUCLIDEAN) LAUNCH_K(double, CRX_EUCLIDEAN, p->x64); else LAUNCH_K(double, CRX_COSINE, p->x64); }
+            else { if (metric == CRX_EUCLIDEAN) LAUNCH_K(float, CRX_EUCLIDEAN, p->x32); else LAUNCH_K(float, CRX_COSINE, p->x32); }
+#undef LAUNCH_K
+        }
+        { CRX_KERNEL(c, "kpp_prob"); kpp_prob_kernel<<<crx_grid(N, 256), 256, 0, c->stream>>>(mind.p, N, mx.p, prob.p); }
+        CRX_CUDA(cub::DeviceScan::InclusiveSum(tmp.p, bytes, prob.p, P.p, (int)N, c->stream));
+        double total = 0;
+        CRX_CUDA(cudaMemcpyAsync(&total, P.p + (N - 1), sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        CRX_CUDA(cudaStreamSynchronize(c->stream));
+        std::uniform_real_distribution<double> ur(0.0, total);  // initialization.hpp:132-133
+        double xr = ur(e);
+        { CRX_KERNEL(c, "kpp_pick"); kpp_pick_kernel<<<1, 32, 0, c->stream>>>(P.p, N, xr, chosen.p, c->counters); }
+        CRX_CUDA(cudaMemcpyAsync(&out[i], chosen.p, sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+        CRX_CUDA(cudaStreamSynchronize(c->stream));
+    }
+    CRX_CUDA(cudaGetLastError());
+    return CRX_OK;
+}
+
+int crx_lloyds_assignment(crx_ctx* c, const crx_points* p, const double* centroids, int cmem, int K, const int32_t* crow,
+                          int metric, int32_t* labels, double* dists, int mem) {
+    CRX_REQUIRE(c && p && centroids && labels && dists, "NULL argument");
+    CRX_REQUIRE(K >= 1, "K");
+    CRX_REQUIRE(metric == CRX_EUCLIDEAN || metric == CRX_COSINE, "metric");
+    CRX_CUDA(cudaSetDevice(c->device));
+    Centroids cen;
+    CRX_TRY(cen.stage(c, centroids, cmem, K, p->d, p->ld));
+    IoBuf<int32_t> lab;
+    IoBuf<double> dis;
+    CRX_TRY(lab.bind(c, labels, p->n, mem, false));
+    CRX_TRY(dis.bind(c, dists, p->n, mem, false));
+    CRX_TRY(lloyd_scan(c, p, nullptr, p->n, cen, metric, lab.dev, dis.dev));
+    if (crow) {
+        DevBuf<int32_t> d_crow;
+        CRX_TRY(d_crow.alloc(c, K));
+        for (int i = 0; i < K; i++) CRX_REQUIRE(crow[i] >= -1 && crow[i] < p->n, "centroid_rows out of range");
+        CRX_CUDA(cudaMemcpyAsync(d_crow.p, crow, K * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+        CRX_KERNEL(c, "self_assign");
+        self_assign_kernel<<<1, 32, 0, c->stream>>>(d_crow.p, K, lab.dev, dis.dev);
+        CRX_CUDA(cudaStreamSynchronize(c->stream));
+    }
+    CRX_CUDA(cudaGetLastError());
+    CRX_TRY(lab.flush());
+    CRX_TRY(dis.flush());
+    if (mem == CRX_HOST || cmem == CRX_HOST) CRX_CUDA(cudaStreamSynchronize(c->stream));
+    return CRX_OK;
+}
+
+int crx_lloyds_for_remaining(crx_ctx* c, const crx_points* p, const double* centroids, int cmem, int K, int metric,
+                             int32_t* labels, double* dists, int mem) {
+    CRX_REQUIRE(c && p && centroids && labels && dists, "NULL argument");
+    CRX_CUDA(cudaSetDevice(c->device));
+    Centroids cen;
+    CRX_TRY(cen.stage(c, centroids, cmem, K, p->d, p->ld));
+    IoBuf<int32_t> lab;
+    IoBuf<double> dis;
+    CRX_TRY(lab.bind(c, labels, p->n, mem, true));
+    CRX_TRY(dis.bind(c, dists, p->n, mem, true));
+    DevBuf<int32_t> rows;
+    DevBuf<int> cnt;
+    CRX_TRY(rows.alloc(c, p->n)); CRX_TRY(cnt.alloc(c, 1));
+    CRX_CUDA(cudaMemsetAsync(cnt.p, 0, sizeof(int), c->stream));
+    { CRX_KERNEL(c, "compact_unassigned"); compact_unassigned_kernel<<<crx_grid(p->n, 256), 256, 0, c->stream>>>(lab.dev, p->n, rows.p, cnt.p); }
+    int h_cnt = 0;
+    CRX_CUDA(cudaMemcpyAsync(&h_cnt, cnt.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CRX_CUDA(cudaStreamSynchronize(c->stream));
+    CRX_TRY(lloyd_scan(c, p, rows.p, h_cnt, cen, metric, lab.dev, dis.dev));
+    CRX_TRY(lab.flush());
+    CRX_TRY(dis.flush());
+    CRX_CUDA(cudaStreamSynchronize(c->stream));
+    return CRX_OK;
+}
+
+int crx_lsh_range_assignment(crx_ctx* c, const crx_points* p, const crx_lsh* t, const int32_t* crow, int K, int metric,
+                             int32_t* labels, double* dists, int mem, int32_t* before) {
+    CRX_REQUIRE(c && p && t && crow && labels && dists, "NULL argument");
+    CRX_REQUIRE(t->pts == p, "the tables were built over a different point set");
+    CRX_REQUIRE(K >= 1, "K");
+    for (int i = 0; i < K; i++) CRX_REQUIRE(crow[i] >= 0 && crow[i] < p->n, "centroid_rows must be stored rows");
+    CRX_CUDA(cudaSetDevice(c->device));
+    int L = t->L;
+    int64_t N = p->n;
+    // bucket of every centroid in every table (get_LSH_combined_buckets -> getBucketFor, unfiltered)
+    DevBuf<int32_t> d_crow, d_cb;
+    CRX_TRY(d_crow.alloc(c, K)); CRX_TRY(d_cb.alloc(c, (size_t)K * L));
+    CRX_CUDA(cudaMemcpyAsync(d_crow.p, crow, K * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+    for (int l = 0; l < L; l++) {
+        CRX_KERNEL(c, "gather_int");
+        gather_int_kernel<<<crx_grid(K, 128), 128, 0, c->stream>>>(t->bucket + (size_t)l * N, d_crow.p, K, d_cb.p + (size_t)l * K);
+    }
+    std::vector<int32_t> cb((size_t)K * L);
+    CRX_CUDA(cudaMemcpyAsync(cb.data(), d_cb.p, cb.size() * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+    std::vector<std::vector<int32_t>> offs(L);
+    for (int l = 0; l < L; l++) {
+        offs[l].resize((size_t)t->nbuckets + 1);
+        CRX_CUDA(cudaMemcpyAsync(offs[l].data(), t->by_bucket[l].off, offs[l].size() * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+    }
+    CRX_CUDA(cudaStreamSynchronize(c->stream));
+    std::vector<int32_t> hb((size_t)K * L), he((size_t)K * L);
+    std::vector<const int32_t*> perms(L);
+    for (int l = 0; l < L; l++) perms[l] = t->by_bucket[l].perm;
+    for (int cc = 0; cc < K; cc++)
+        for (int l = 0; l < L; l++) {
+            int b = cb[(size_t)l * K + cc];
+            hb[(size_t)cc * L + l] = offs[l][b];
+            he[(size_t)cc * L + l] = offs[l][b + 1];
+        }
+    return range_assign_common(c, p, crow, K, metric, L, hb, he, perms, t->bucket, labels, dists, mem, before);
+}
+
+int crx_cube_range_assignment(crx_ctx* c, const crx_points* p, const crx_cube* cu, const int32_t* crow, int K, int metric,
+                              int probes, int32_t* labels, double* dists, int mem, int32_t* before) {
+    CRX_REQUIRE(c && p && cu && crow && labels && dists, "NULL argument");
+    CRX_REQUIRE(cu->pts == p, "the hypercube was built over a different point set");
+    CRX_REQUIRE(K >= 1, "K");
+    for (int i = 0; i < K; i++) CRX_REQUIRE(crow[i] >= 0 && crow[i] < p->n, "centroid_rows must be stored rows");
+    CRX_CUDA(cudaSetDevice(c->device));
+    DevBuf<int32_t> d_crow, d_home;
+    CRX_TRY(d_crow.alloc(c, K)); CRX_TRY(d_home.alloc(c, K));
+    CRX_CUDA(cudaMemcpyAsync(d_crow.p, crow, K * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+    { CRX_KERNEL(c, "gather_int"); gather_int_kernel<<<crx_grid(K, 128), 128, 0, c->stream>>>(cu->vertex, d_crow.p, K, d_home.p); }
+    std::vector<int32_t> home(K), off((size_t)(1 << cu->k) + 1);
+    CRX_CUDA(cudaMemcpyAsync(home.data(), d_home.p, K * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+    CRX_CUDA(cudaMemcpyAsync(off.data(), cu->by_vertex.off, off.size() * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+    CRX_CUDA(cudaStreamSynchronize(c->stream));
+    // probe sequences (lsh_cube.hpp:140-177); every centroid gets the same number of segment slots
+    std::vector<std::vector<int>> seqs(K);
+    size_t nseg = 1;
+    for (int cc = 0; cc < K; cc++) { crx_cube_probe_sequence(home[cc], probes, cu->k, seqs[cc]); nseg = std::max(nseg, seqs[cc].size()); }
+    std::vector<int32_t> hb((size_t)K * nseg, 0), he((size_t)K * nseg, 0);
+    for (int cc = 0; cc < K; cc++)
+        for (size_t s = 0; s < seqs[cc].size(); s++) { hb[cc * nseg + s] = off[seqs[cc][s]]; he[cc * nseg + s] = off[seqs[cc][s] + 1]; }
+    std::vector<const int32_t*> perms(1, cu->by_vertex.perm);
+    return range_assign_common(c, p, crow, K, metric, (int)nseg, hb, he, perms, nullptr, labels, dists, mem, before);
+}
+
+int crx_cluster_sums(crx_ctx* c, const crx_points* p, const int32_t* labels, int lmem, int K, double* sums, int64_t* counts, int mem) {
+    CRX_REQUIRE(c && p && labels && sums && counts, "NULL argument");
+    CRX_REQUIRE(K >= 1, "K");
+    CRX_CUDA(cudaSetDevice(c->device));
+    int64_t N = p->n;
+    int D = p->d;
+    IoBuf<int32_t> lab;
+    IoBuf<double> out;
+    IoBuf<long long> cnt;
+    CRX_TRY(lab.bind(c, labels, N, lmem, true));
+    CRX_TRY(out.bind(c, sums, (size_t)K * D, mem, false));
+    CRX_TRY(cnt.bind(c, (long long*)counts, K, mem, false));
+    Segments seg;
+    int st = crx_build_segments(c, lab.dev, N, K, &seg);
+    if (st != CRX_OK) { seg.free_all(); return st; }
+    std::vector<int32_t> off(K + 1);
+    CRX_CUDA(cudaMemcpyAsync(off.data(), seg.off, (K + 1) * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+    CRX_CUDA(cudaStreamSynchronize(c->stream));
+    std::vector<int32_t> ch_cluster, ch_index, ch_first(K + 1, 0);
+    for (int cl = 0; cl < K; cl++) {
+        int n = off[cl + 1] - off[cl];
+        int nch = (n + SUM_CH - 1) / SUM_CH;
+        ch_first[cl] = (int32_t)ch_cluster.size();
+        for (int i = 0; i < nch; i++) { ch_cluster.push_back(cl); ch_index.push_back(i); }
+    }
+    ch_first[K] = (int32_t)ch_cluster.size();
+    int nchunks = (int)ch_cluster.size();
+    DevBuf<int32_t> d_cc, d_ci, d_cf;
+    DevBuf<double> partial;
+    CRX_TRY(d_cc.alloc(c, nchunks)); CRX_TRY(d_ci.alloc(c, nchunks)); CRX_TRY(d_cf.alloc(c, K + 1));
+    CRX_TRY(partial.alloc(c, (size_t)nchunks * D));
+    if (nchunks) {
+        CRX_CUDA(cudaMemcpyAsync(d_cc.p, ch_cluster.data(), nchunks * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+        CRX_CUDA(cudaMemcpyAsync(d_ci.p, ch_index.data(), nchunks * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+    }
+    CRX_CUDA(cudaMemcpyAsync(d_cf.p, ch_first.data(), (K + 1) * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+    if (nchunks) {
+        CRX_KERNEL(c, "chunk_sums");
+        if (p->x64) chunk_sums_kernel<double><<<nchunks, 128, 0, c->stream>>>(p->x64, p->ld, D, seg.perm, seg.off, d_cc.p, d_ci.p, partial.p);
+        else chunk_sums_kernel<float><<<nchunks, 128, 0, c->stream>>>(p->x32, p->ld, D, seg.perm, seg.off, d_cc.p, d_ci.p, partial.p);
+    }
+    { CRX_KERNEL(c, "combine_sums"); combine_sums_kernel<<<K, 128, 0, c->stream>>>(partial.p, d_cf.p, K, D, seg.off, out.dev, cnt.dev); }
+    CRX_CUDA(cudaGetLastError());
+    st = out.flush();
+    if (st == CRX_OK) st = cnt.flush();
+    CRX_CUDA(cudaStreamSynchronize(c->stream));
+    seg.free_all();
+    return st;
+}
+
+int crx_k_means_finish(crx_ctx* c, const double* sums, const int64_t* counts, const double* oldc, int K, int D, int metric,
+                       double min_dist, double* newc, int mem, int* cont) {
+    CRX_REQUIRE(c && sums && counts && oldc && newc && cont, "NULL argument");
+    CRX_CUDA(cudaSetDevice(c->device));
+    IoBuf<double> s, o, n;
+    IoBuf<long long> cn;
+    CRX_TRY(s.bind(c, sums, (size_t)K * D, mem, true));
+    CRX_TRY(o.bind(c, oldc, (size_t)K * D, mem, true));
+    CRX_TRY(cn.bind(c, (const long long*)counts, K, mem, true));
+    CRX_TRY(n.bind(c, newc, (size_t)K * D, mem, false));
+    DevBuf<double> cand;
+    DevBuf<int> moved;
+    CRX_TRY(cand.alloc(c, (size_t)K * D)); CRX_TRY(moved.alloc(c, 1));
+    CRX_CUDA(cudaMemsetAsync(moved.p, 0, sizeof(int), c->stream));
+    { CRX_KERNEL(c, "kmeans_finish"); kmeans_finish_kernel<<<crx_grid(K, 64), 64, 0, c->stream>>>(s.dev, cn.dev, o.dev, K, D, metric, min_dist, cand.p, moved.p); }
+    { CRX_KERNEL(c, "select_centroids"); select_centroids_kernel<<<crx_grid((int64_t)K * D, 256), 256, 0, c->stream>>>(cand.p, o.dev, (size_t)K * D, moved.p, n.dev); }
+    CRX_CUDA(cudaGetLastError());
+    int h = 0;
+    CRX_CUDA(cudaMemcpyAsync(&h, moved.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CRX_TRY(n.flush());
+    CRX_CUDA(cudaStreamSynchronize(c->stream));
+    *cont = h;
+    return CRX_OK;
+}
+
+int crx_k_means(crx_ctx* c, const crx_points* p, const int32_t* labels, int lmem, const double* oldc, int K, int metric,
+                double min_dist, double* newc, int cmem, int* cont) {
+    CRX_REQUIRE(c && p && labels && oldc && newc && cont, "NULL argument");
+    DevBuf<double> sums, o, n;
+    DevBuf<long long> cnt;
+    size_t kd = (size_t)K * p->d;
+    CRX_TRY(sums.alloc(c, kd)); CRX_TRY(cnt.alloc(c, K)); CRX_TRY(o.alloc(c, kd)); CRX_TRY(n.alloc(c, kd));
+    CRX_CUDA(cudaMemcpyAsync(o.p, oldc, kd * sizeof(double), cmem == CRX_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, c->stream));
+    CRX_TRY(crx_cluster_sums(c, p, labels, lmem, K, sums.p, (int64_t*)cnt.p, CRX_DEVICE));
+    CRX_TRY(crx_k_means_finish(c, sums.p, (const int64_t*)cnt.p, o.p, K, p->d, metric, min_dist, n.p, CRX_DEVICE, cont));
+    CRX_CUDA(cudaMemcpyAsync(newc, n.p, kd * sizeof(double), cmem == CRX_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice, c->stream));
+    CRX_CUDA(cudaStreamSynchronize(c->stream));
+    return CRX_OK;
+}
+
+int crx_pam_lloyds(crx_ctx* c, const crx_points* p, const int32_t* labels, int lmem, const int32_t* crow, int K, int metric,
+                   int32_t* new_crow, int* swapped) {
+    CRX_REQUIRE(c && p && labels && crow && new_crow && swapped, "NULL argument");
+    CRX_CUDA(cudaSetDevice(c->device));
+    int64_t N = p->n;
+    IoBuf<int32_t> lab;
+    CRX_TRY(lab.bind(c, labels, N, lmem, true));
+    Segments seg;
+    int st = crx_build_segments(c, lab.dev, N, K, &seg);
+    if (st != CRX_OK) { seg.free_all(); return st; }
+    DevBuf<double> rowsum;
+    DevBuf<int32_t> d_crow, d_new;
+    DevBuf<int> d_sw;
+    CRX_TRY(rowsum.alloc(c, N)); CRX_TRY(d_crow.alloc(c, K)); CRX_TRY(d_new.alloc(c, K)); CRX_TRY(d_sw.alloc(c, 1));
+    CRX_CUDA(cudaMemcpyAsync(d_crow.p, crow, K * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+    CRX_CUDA(cudaMemsetAsync(d_sw.p, 0, sizeof(int), c->stream));
+    int g = (int)((N + 7) / 8);
+    {
+        CRX_KERNEL(c, "pam_rowsum");
+#define LAUNCH_P(T, M, xptr) pam_rowsum_kernel<T, M><<<g, 256, 0, c->stream>>>(xptr, p->ld, p->d, p->sqn, seg.perm, seg.sorted, seg.off, N, rowsum.p)
+        if (p->x64) { if (metric == CRX_EUCLIDEAN) LAUNCH_P(double, CRX_EUCLIDEAN, p->x64); else LAUNCH_P(double, CRX_COSINE, p->x64); }
+        else { if (metric == CRX_EUCLIDEAN) LAUNCH_P(float, CRX_EUCLIDEAN, p->x32); else LAUNCH_P(float, CRX_COSINE, p->x32); }
+#undef LAUNCH_P
+    }
+    {
+        CRX_KERNEL(c, "pam_pick");
+#define LAUNCH_Q(T, M, xptr) pam_pick_kernel<T, M><<<K, 256, 0, c->stream>>>(xptr, p->ld, p->d, p->sqn, seg.perm, seg.off, rowsum.p, d_crow.p, d_new.p, d_sw.p, c->counters)
+        if (p->x64) { if (metric == CRX_EUCLIDEAN) LAUNCH_Q(double, CRX_EUCLIDEAN, p->x64); else LAUNCH_Q(double, CRX_COSINE, p->x64); }
+        else { if (metric == CRX_EUCLIDEAN) LAUNCH_Q(float, CRX_EUCLIDEAN, p->x32); else LAUNCH_Q(float, CRX_COSINE, p->x32); }
+#undef LAUNCH_Q
+    }
+    CRX_CUDA(cudaGetLastError());
+    int h = 0;
+    CRX_CUDA(cudaMemcpyAsync(new_crow, d_new.p, K * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+    CRX_CUDA(cudaMemcpyAsync(&h, d_sw.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CRX_CUDA(cudaStreamSynchronize(c->stream));
+    *swapped = h;
+    seg.free_all();
+    return CRX_OK;
+}
+
+int crx_silhouette_cluster(crx_ctx* c, const crx_points* p, const int32_t* labels, int lmem, const double* centroids,
+                           int cmem, int K, int metric, double* sils) {
+    CRX_REQUIRE(c && p && labels && centroids && sils, "NULL argument");
+    CRX_CUDA(cudaSetDevice(c->device));
+    int64_t N = p->n;
+    IoBuf<int32_t> lab;
+    CRX_TRY(lab.bind(c, labels, N, lmem, true));
+    Centroids cen;
+    CRX_TRY(cen.stage(c, centroids, cmem, K, p->d, p->ld));
+    Segments seg;
+    int st = crx_build_segments(c, lab.dev, N, K, &seg);
+    if (st != CRX_OK) { seg.free_all(); return st; }
+    DevBuf<int32_t> near;
+    DevBuf<double> s, d_sils, raw;
+    CRX_TRY(near.alloc(c, K)); CRX_TRY(s.alloc(c, N)); CRX_TRY(d_sils.alloc(c, K)); CRX_TRY(raw.alloc(c, K));
+    { CRX_KERNEL(c, "near_centroid"); near_centroid_kernel<<<crx_grid(K, 64), 64, 0, c->stream>>>(cen.pad.p, cen.sqn.p, K, p->ld, p->d, metric, near.p); }
+    int g = (int)((N + 7) / 8);
+    {
+        CRX_KERNEL(c, "silhouette_point");
+#define LAUNCH_S(T, M, xptr) silhouette_point_kernel<T, M><<<g, 256, 0, c->stream>>>(xptr, p->ld, p->d, p->sqn, seg.perm, seg.sorted, seg.off, near.p, N, s.p)
+        if (p->x64) { if (metric == CRX_EUCLIDEAN) LAUNCH_S(double, CRX_EUCLIDEAN, p->x64); else LAUNCH_S(double, CRX_COSINE, p->x64); }
+        else { if (metric == CRX_EUCLIDEAN) LAUNCH_S(float, CRX_EUCLIDEAN, p->x32); else LAUNCH_S(float, CRX_COSINE, p->x32); }
+#undef LAUNCH_S
+    }
+    { CRX_KERNEL(c, "silhouette_reduce"); silhouette_reduce_kernel<<<crx_grid(K, 64), 64, 0, c->stream>>>(s.p, seg.off, K, d_sils.p, raw.p); }
+    CRX_CUDA(cudaGetLastError());
+    std::vector<double> h_raw(K);
+    CRX_CUDA(cudaMemcpyAsync(sils, d_sils.p, K * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CRX_CUDA(cudaMemcpyAsync(h_raw.data(), raw.p, K * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CRX_CUDA(cudaStreamSynchronize(c->stream));
+    double total = 0;  // sils[K] accumulates the per-cluster sums in cluster order (silhouette.hpp:78)
+    for (int cl = 0; cl < K; cl++) total = total + h_raw[cl];
+    sils[K] = total / (double)N;
+    seg.free_all();
+    return CRX_OK;
+}
+
+} // extern "C"

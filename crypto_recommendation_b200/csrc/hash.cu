@@ -1,0 +1,688 @@
+// hash.cu -- lib/generators + lib/data_structures of the reference on the GPU:
+//   K1 batched projection (Euclidean floor((v.x+t)/w), cosine sign) with certified boundaries,
+//   K2 phi / g combination and bucket index, K3 table build (stable radix sort + offsets),
+//   hypercube vertex map with the order-dependent f(h) draws reproduced on the host.
+#include <algorithm>
+#include <cub/cub.cuh>
+
+#include "tables.cuh"
+
+// ------------------------------------------------------------------------------------------------
+// K1 + K2: projections of every row, 2 rows per thread, one table (k <= KC hashes) at a time.
+//
+// Arithmetic: FP64 FMA chain in index order with the a-priori bound
+//     |computed - exact| <= (D+2) 2^-53 ||x|| ||r||
+// A projection whose decision (sign / floor) lies inside the bound is recomputed with a
+// compensated double-double dot product (counted in counters[CRX_CNT_HASH_DD]); the reference's
+// own x87 accumulation (cust_vector.hpp:107-121) is less accurate than that fallback.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void load4(const float* p, double o[4]) {
+    float4 v = *reinterpret_cast<const float4*>(p);
+    o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w;
+}
+__device__ __forceinline__ void load4(const double* p, double o[4]) {
+    double2 a = *reinterpret_cast<const double2*>(p);
+    double2 b = *reinterpret_cast<const double2*>(p + 2);
+    o[0] = a.x; o[1] = a.y; o[2] = b.x; o[3] = b.y;
+}
+
+template <typename T>
+__device__ int cosine_bit_dd(const T* x, const double* r, int D) {
+    double hi, lo;
+    dot2(r, x, D, hi, lo);
+    return (hi > 0.0 || (hi == 0.0 && lo >= 0.0)) ? 1 : 0;
+}
+template <typename T>
+__device__ int euclid_h_dd(const T* x, const double* v, int D, double t, double w) {
+    double hi, lo, s, e;
+    dot2(v, x, D, hi, lo);
+    two_sum(hi, t, s, e);
+    e = __dadd_rn(e, lo);
+    double f = floor(__ddiv_rn(s, w));
+    double rem = __dadd_rn(__fma_rn(-w, f, s), e);  // (s + e) - w f
+    if (rem < 0.0) f -= 1.0;
+    else if (rem >= w) f += 1.0;
+    return (int)f;
+}
+
+#define PHI_M 2147483647  // int(pow(2,32)-5) as GCC folds it (euclidean_phi_gen.hpp:70)
+
+template <typename T, int KC>
+__global__ void __launch_bounds__(128)
+hash_rows_kernel(const T* __restrict__ x, int ld, const double* __restrict__ sqn, int64_t N, int D, int metric, int k,
+                 int L, const double* __restrict__ proj, int ldp, const double* __restrict__ pnorm,
+                 const float* __restrict__ tt, const int32_t* __restrict__ rr, float w, int nbuckets,
+                 int32_t* __restrict__ hvals, int32_t* __restrict__ bucket, unsigned long long* counters) {
+    extern __shared__ double sproj[];  // [k][ldp]
+    int64_t i0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 2;
+    int64_t i1 = i0 + 1;
+    bool v0 = i0 < N, v1 = i1 < N;
+    const T* row0 = x + (v0 ? i0 : 0) * ld;
+    const T* row1 = x + (v1 ? i1 : 0) * ld;
+    double nx0 = v0 ? sqrt(sqn[i0]) : 0.0, nx1 = v1 ? sqrt(sqn[i1]) : 0.0;
+    const double cbound = (double)(D + 2) * 1.1102230246251565e-16 * 1.001;
+    const double dw = (double)w;
+
+    for (int l = 0; l < L; l++) {
+        __syncthreads();
+        for (int e = threadIdx.x; e < k * ldp; e += blockDim.x) sproj[e] = proj[(size_t)l * k * ldp + e];
+        __syncthreads();
+        double a0[KC], a1[KC];
+#pragma unroll
+        for (int h = 0; h < KC; h++) { a0[h] = 0.0; a1[h] = 0.0; }
+        for (int i = 0; i < ld; i += 4) {
+            double p0[4], p1[4];
+            load4(row0 + i, p0);
+            load4(row1 + i, p1);
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+#pragma unroll
+                for (int h = 0; h < KC; h++) {
+                    if (h < k) {
+                        double r = sproj[h * ldp + i + u];
+                        a0[h] = __fma_rn(p0[u], r, a0[h]);
+                        a1[h] = __fma_rn(p1[u], r, a1[h]);
+                    }
+                }
+            }
+        }
+        // decisions
+        int g0 = 0, g1 = 0;
+        unsigned int phi0 = 0, phi1 = 0;
+#pragma unroll
+        for (int h = 0; h < KC; h++) {
+            if (h < k) {
+                double pn = pnorm[l * k + h];
+                double E0 = cbound * nx0 * pn, E1 = cbound * nx1 * pn;
+                int r0, r1;
+                if (metric == CRX_COSINE) {
+                    if (fabs(a0[h]) <= E0) { r0 = cosine_bit_dd(row0, sproj + h * ldp, D); if (v0) atomicAdd(&counters[CRX_CNT_HASH_DD], 1ull); }
+                    else r0 = a0[h] >= 0.0 ? 1 : 0;
+                    if (fabs(a1[h]) <= E1) { r1 = cosine_bit_dd(row1, sproj + h * ldp, D); if (v1) atomicAdd(&counters[CRX_CNT_HASH_DD], 1ull); }
+                    else r1 = a1[h] >= 0.0 ? 1 : 0;
+                    g0 = (g0 << 1) + r0;  // cosine_g_gen.hpp:62-72: function 0 is the MSB
+                    g1 = (g1 << 1) + r1;
+                } else {
+                    double t = (double)tt[l * k + h];
+                    {
+                        double s = a0[h] + t, y = s / dw, f = floor(y), fr = y - f;
+                        double Ey = (E0 + fabs(s) * 2.3e-16) / dw + fabs(y) * 2.3e-16;
+                        if (fmin(fr, 1.0 - fr) <= Ey) { r0 = euclid_h_dd(row0, sproj + h * ldp, D, t, dw); if (v0) atomicAdd(&counters[CRX_CNT_HASH_DD], 1ull); }
+                        else r0 = (int)f;
+                    }
+                    {
+                        double s = a1[h] + t, y = s / dw, f = floor(y), fr = y - f;
+                        double Ey = (E1 + fabs(s) * 2.3e-16) / dw + fabs(y) * 2.3e-16;
+                        if (fmin(fr, 1.0 - fr) <= Ey) { r1 = euclid_h_dd(row1, sproj + h * ldp, D, t, dw); if (v1) atomicAdd(&counters[CRX_CNT_HASH_DD], 1ull); }
+                        else r1 = (int)f;
+                    }
+                    if (hvals) {
+                        if (v0) hvals[((size_t)l * N + i0) * k + h] = r0;
+                        if (v1) hvals[((size_t)l * N + i1) * k + h] = r1;
+                    }
+                    if (rr) {  // euclidean_phi_gen.hpp:85-96
+                        int ri = rr[l * k + h];
+                        long long t0 = (long long)(int)((unsigned int)r0 * (unsigned int)ri);
+                        long long t1 = (long long)(int)((unsigned int)r1 * (unsigned int)ri);
+                        phi0 += (unsigned int)(int)((t0 % PHI_M + PHI_M) % PHI_M);
+                        phi1 += (unsigned int)(int)((t1 % PHI_M + PHI_M) % PHI_M);
+                    }
+                }
+            }
+        }
+        if (bucket) {
+            if (metric == CRX_COSINE) {
+                if (v0) bucket[(size_t)l * N + i0] = g0 % nbuckets;
+                if (v1) bucket[(size_t)l * N + i1] = g1 % nbuckets;
+            } else if (rr) {
+                unsigned int M = (unsigned int)PHI_M;
+                unsigned int f0 = (phi0 % M + M) % M, f1 = (phi1 % M + M) % M;
+                if (v0) bucket[(size_t)l * N + i0] = (int)((unsigned long long)f0 % (unsigned long long)nbuckets);
+                if (v1) bucket[(size_t)l * N + i1] = (int)((unsigned long long)f1 % (unsigned long long)nbuckets);
+            }
+        }
+    }
+}
+
+template <typename T>
+static int launch_hash(crx_ctx* c, const T* x, const crx_points* pts, int metric, int k, int L, const double* d_proj,
+                       int ldp, const double* d_pnorm, const float* d_t, const int32_t* d_r, float w, int nbuckets,
+                       int32_t* hvals, int32_t* bucket) {
+    int64_t N = pts->n;
+    int grid = (int)((N + 255) / 256);
+    size_t smem = (size_t)k * ldp * sizeof(double);
+    CRX_KERNEL(c, "hash_rows");
+#define LAUNCH_H(KC)                                                                                              \
+    do {                                                                                                          \
+        CRX_CUDA(cudaFuncSetAttribute(hash_rows_kernel<T, KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        hash_rows_kernel<T, KC><<<grid, 128, smem, c->stream>>>(x, pts->ld, pts->sqn, N, pts->d, metric, k, L, d_proj, ldp, \
+                                                                 d_pnorm, d_t, d_r, w, nbuckets, hvals, bucket, c->counters); \
+    } while (0)
+    if (k <= 4) LAUNCH_H(4);
+    else if (k <= 8) LAUNCH_H(8);
+    else LAUNCH_H(16);
+#undef LAUNCH_H
+    CRX_CUDA(cudaGetLastError());
+    return CRX_OK;
+}
+
+int crx_hash_rows(crx_ctx* c, const crx_points* pts, int metric, int k, int L, const double* d_proj, int ldp,
+                  const double* d_pnorm, const float* d_t, const int32_t* d_r, float w, int nbuckets, int32_t* hvals,
+                  int32_t* bucket) {
+    CRX_REQUIRE(k >= 1 && k <= 16, "k (hash functions per table / cube dimension) must be in [1,16]");
+    CRX_REQUIRE(ldp == pts->ld, "projection stride");
+    if (pts->x64)
+        return launch_hash<double>(c, pts->x64, pts, metric, k, L, d_proj, ldp, d_pnorm, d_t, d_r, w, nbuckets, hvals, bucket);
+    return launch_hash<float>(c, pts->x32, pts, metric, k, L, d_proj, ldp, d_pnorm, d_t, d_r, w, nbuckets, hvals, bucket);
+}
+
+// ------------------------------------------------------------------------------------------------
+// K3: segments (stable sort by key + offsets)
+// ------------------------------------------------------------------------------------------------
+__global__ void iota_kernel(int32_t* p, int64_t n) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = (int32_t)i;
+}
+// off[b] = lower_bound(sorted, b) for b in [0, nkeys]
+__global__ void offsets_kernel(const int32_t* __restrict__ sorted, int64_t n, int nkeys, int32_t* __restrict__ off) {
+    int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b > nkeys) return;
+    int64_t lo = 0, hi = n;
+    while (lo < hi) {
+        int64_t m = (lo + hi) >> 1;
+        if (sorted[m] < b) lo = m + 1; else hi = m;
+    }
+    off[b] = (int32_t)lo;
+}
+
+static int sort_pairs(crx_ctx* c, const int32_t* kin, int32_t* kout, const int32_t* vin, int32_t* vout, int64_t n,
+                      int end_bit) {
+    size_t bytes = 0;
+    CRX_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, bytes, kin, kout, vin, vout, (int)n, 0, end_bit, c->stream));
+    DevBuf<char> tmp;
+    CRX_TRY(tmp.alloc(c, bytes));
+    CRX_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, bytes, kin, kout, vin, vout, (int)n, 0, end_bit, c->stream));
+    return CRX_OK;
+}
+
+int crx_build_segments(crx_ctx* c, const int32_t* keys, int64_t n, int nkeys, Segments* out) {
+    out->n = n; out->nkeys = nkeys;
+    CRX_CUDA(cudaMalloc((void**)&out->perm, n * sizeof(int32_t)));
+    CRX_CUDA(cudaMalloc((void**)&out->sorted, n * sizeof(int32_t)));
+    CRX_CUDA(cudaMalloc((void**)&out->off, ((size_t)nkeys + 1) * sizeof(int32_t)));
+    DevBuf<int32_t> iota;
+    CRX_TRY(iota.alloc(c, n));
+    { CRX_KERNEL(c, "iota"); iota_kernel<<<crx_grid(n, 256), 256, 0, c->stream>>>(iota.p, n); }
+    int bits = 1;
+    while ((1ll << bits) < nkeys && bits < 31) bits++;
+    CRX_TRY(sort_pairs(c, keys, out->sorted, iota.p, out->perm, n, bits));
+    { CRX_KERNEL(c, "bucket_offsets"); offsets_kernel<<<crx_grid(nkeys + 1, 256), 256, 0, c->stream>>>(out->sorted, n, nkeys, out->off); }
+    CRX_CUDA(cudaGetLastError());
+    return CRX_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// euclidean filtered groups: dense rank of the k-tuple of h values (cust_hashtable.hpp:81-97)
+// ------------------------------------------------------------------------------------------------
+__global__ void gather_h_kernel(const int32_t* __restrict__ hv, const int32_t* __restrict__ perm, int64_t n, int k, int j,
+                                int32_t* __restrict__ keys) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) keys[i] = hv[(size_t)perm[i] * k + j];
+}
+__global__ void tuple_flag_kernel(const int32_t* __restrict__ hv, const int32_t* __restrict__ perm, int64_t n, int k,
+                                  int32_t* __restrict__ flag) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int f = 0;
+    if (i > 0) {
+        const int32_t* a = hv + (size_t)perm[i] * k;
+        const int32_t* b = hv + (size_t)perm[i - 1] * k;
+        for (int j = 0; j < k; j++) f |= (a[j] != b[j]);
+    }
+    flag[i] = f;
+}
+__global__ void scatter_rank_kernel(const int32_t* __restrict__ rank, const int32_t* __restrict__ perm, int64_t n,
+                                    int32_t* __restrict__ gid) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) gid[perm[i]] = rank[i];
+}
+
+static int build_tuple_groups(crx_ctx* c, const int32_t* hv /* [N][k] */, int64_t n, int k, int32_t* gid, Segments* seg,
+                              int* ngroups) {
+    DevBuf<int32_t> pa, pb, ka, kb;
+    CRX_TRY(pa.alloc(c, n)); CRX_TRY(pb.alloc(c, n)); CRX_TRY(ka.alloc(c, n)); CRX_TRY(kb.alloc(c, n));
+    int g = crx_grid(n, 256);
+    { CRX_KERNEL(c, "iota"); iota_kernel<<<g, 256, 0, c->stream>>>(pa.p, n); }
+    int32_t* pin = pa.p; int32_t* pout = pb.p;
+    for (int j = k - 1; j >= 0; j--) {  // LSD passes, each stable => lexicographic order, ties by row
+        { CRX_KERNEL(c, "gather_h"); gather_h_kernel<<<g, 256, 0, c->stream>>>(hv, pin, n, k, j, ka.p); }
+        CRX_TRY(sort_pairs(c, ka.p, kb.p, pin, pout, n, 32));
+        std::swap(pin, pout);
+    }
+    { CRX_KERNEL(c, "tuple_flag"); tuple_flag_kernel<<<g, 256, 0, c->stream>>>(hv, pin, n, k, ka.p); }
+    size_t bytes = 0;
+    CRX_CUDA(cub::DeviceScan::InclusiveSum(nullptr, bytes, ka.p, kb.p, (int)n, c->stream));
+    DevBuf<char> tmp;
+    CRX_TRY(tmp.alloc(c, bytes));
+    CRX_CUDA(cub::DeviceScan::InclusiveSum(tmp.p, bytes, ka.p, kb.p, (int)n, c->stream));
+    { CRX_KERNEL(c, "scatter_rank"); scatter_rank_kernel<<<g, 256, 0, c->stream>>>(kb.p, pin, n, gid); }
+    int32_t last = 0;
+    CRX_CUDA(cudaMemcpyAsync(&last, kb.p + (n - 1), sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+    CRX_CUDA(cudaStreamSynchronize(c->stream));
+    *ngroups = last + 1;
+    seg->n = n; seg->nkeys = *ngroups;
+    CRX_CUDA(cudaMalloc((void**)&seg->perm, n * sizeof(int32_t)));
+    CRX_CUDA(cudaMalloc((void**)&seg->sorted, n * sizeof(int32_t)));
+    CRX_CUDA(cudaMalloc((void**)&seg->off, ((size_t)*ngroups + 1) * sizeof(int32_t)));
+    CRX_CUDA(cudaMemcpyAsync(seg->perm, pin, n * sizeof(int32_t), cudaMemcpyDeviceToDevice, c->stream));
+    CRX_CUDA(cudaMemcpyAsync(seg->sorted, kb.p, n * sizeof(int32_t), cudaMemcpyDeviceToDevice, c->stream));
+    { CRX_KERNEL(c, "bucket_offsets"); offsets_kernel<<<crx_grid(*ngroups + 1, 256), 256, 0, c->stream>>>(seg->sorted, n, *ngroups, seg->off); }
+    CRX_CUDA(cudaGetLastError());
+    return CRX_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// host parameter generation: the reference's libstdc++ <random> calls in the reference's order
+// 
+// ------------------------------------------------------------------------------------------------
+static void draw_euclid_h(std::default_random_engine& e, int D, float w, float* v, float* t) {
+    std::normal_distribution<float> nd(0, 1);  // euclidean_h_gen.hpp:60-64
+    for (int i = 0; i < D; i++) v[i] = nd(e);
+    std::uniform_real_distribution<float> ud(0, w);  // euclidean_h_gen.hpp:68-69
+    *t = ud(e);
+}
+static void draw_cosine_h(std::default_random_engine& e, int D, double* r) {
+    std::normal_distribution<double> nd(0, 1);  // cosine_h_gen.hpp:54-59
+    for (int i = 0; i < D; i++) r[i] = nd(e);
+}
+
+static int upload_proj(crx_ctx* c, int H, int D, int ld, const double* cos_r, const float* euc_v, double** d_proj,
+                       double** d_pnorm) {
+    std::vector<double> proj((size_t)H * ld, 0.0), pn(H);
+    for (int h = 0; h < H; h++) {
+        double s = 0;
+        for (int i = 0; i < D; i++) {
+            double v = cos_r ? cos_r[(size_t)h * D + i] : (double)euc_v[(size_t)h * D + i];
+            proj[(size_t)h * ld + i] = v;
+            s += v * v;
+        }
+        pn[h] = std::sqrt(s) * 1.0000001;
+    }
+    CRX_CUDA(cudaMalloc((void**)d_proj, proj.size() * sizeof(double)));
+    CRX_CUDA(cudaMalloc((void**)d_pnorm, pn.size() * sizeof(double)));
+    CRX_CUDA(cudaMemcpyAsync(*d_proj, proj.data(), proj.size() * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    CRX_CUDA(cudaMemcpyAsync(*d_pnorm, pn.data(), pn.size() * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    CRX_CUDA(cudaStreamSynchronize(c->stream));
+    return CRX_OK;
+}
+
+// hamming ball enumeration: utils.cpp:22-50 restated as lexicographic combinations of bit positions
+static void hamming_ball(int num, int dist, int min_bit, int bits, std::vector<int>& out) {
+    if (dist < 1 || dist > bits - min_bit) return;
+    std::vector<int> pos(dist);
+    for (int i = 0; i < dist; i++) pos[i] = min_bit + i;
+    for (;;) {
+        int v = num;
+        for (int i = 0; i < dist; i++) v ^= (1 << pos[i]);
+        out.push_back(v);
+        int i = dist - 1;
+        while (i >= 0 && pos[i] == bits - dist + i) i--;
+        if (i < 0) break;
+        pos[i]++;
+        for (int j = i + 1; j < dist; j++) pos[j] = pos[j - 1] + 1;
+    }
+}
+
+// vertex visit order of get_hypercube_combined_buckets (lsh_cube.hpp:140-177), home first
+void crx_cube_probe_sequence(int home, int probes, int k, std::vector<int>& seq) {
+    seq.clear();
+    seq.push_back(home);
+    std::vector<int> neigh;
+    size_t ni = 0;
+    if (probes > 1) hamming_ball(home, 1, 0, k, neigh);
+    int left = probes, dist = 1;
+    while (left > 0) {
+        if (ni < neigh.size()) { seq.push_back(neigh[ni++]); left--; }
+        else {
+            dist++;
+            neigh.clear();
+            hamming_ball(home, dist, 0, k, neigh);
+            ni = 0;
+            if (neigh.empty()) break;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// hypercube f-map kernels
+// ------------------------------------------------------------------------------------------------
+__global__ void cube_keys_kernel(const int32_t* __restrict__ hv, int64_t total, int k, unsigned long long* __restrict__ keys,
+                                 uint32_t* __restrict__ pos) {
+    int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= total) return;
+    int f = (int)(p % k);
+    keys[p] = ((unsigned long long)f << 32) | (unsigned long long)((uint32_t)hv[p] ^ 0x80000000u);
+    pos[p] = (uint32_t)p;
+}
+__global__ void cube_heads_kernel(const unsigned long long* __restrict__ keys, const uint32_t* __restrict__ pos, int64_t total,
+                                  unsigned long long* __restrict__ hkeys, uint32_t* __restrict__ hpos, int cap,
+                                  int* __restrict__ count) {
+    int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= total) return;
+    if (p == 0 || keys[p] != keys[p - 1]) {
+        int s = atomicAdd(count, 1);
+        if (s < cap) { hkeys[s] = keys[p]; hpos[s] = pos[p]; }
+    }
+}
+// vertex = concatenation of f_i(h_i) bits, f_0 = MSB (hypercube_gen.hpp:63-73); maps: sorted h per f
+__global__ void cube_vertex_kernel(const int32_t* __restrict__ hv, int64_t N, int k, const int32_t* __restrict__ map_h,
+                                   const int32_t* __restrict__ map_bit, const int32_t* __restrict__ map_off,
+                                   int32_t* __restrict__ vertex) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    int g = 0;
+    for (int f = 0; f < k; f++) {
+        int h = hv[i * k + f];
+        int lo = map_off[f], hi = map_off[f + 1];
+        while (lo < hi) {
+            int m = (lo + hi) >> 1;
+            if (map_h[m] < h) lo = m + 1; else hi = m;
+        }
+        g = (g << 1) + map_bit[lo];
+    }
+    vertex[i] = g;
+}
+
+// ------------------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------------------
+extern "C" {
+
+int crx_get_num_hamming_dist_from(int num, int dist, int min_bit, int bits, int32_t* out, int cap) {
+    std::vector<int> r;
+    hamming_ball(num, dist, min_bit, bits, r);
+    for (size_t i = 0; i < r.size() && (int)i < cap; i++) out[i] = r[i];
+    return (int)r.size();
+}
+
+int crx_lsh_destroy(crx_lsh* t) {
+    if (!t) return CRX_OK;
+    cudaSetDevice(t->ctx->device);
+    cudaStreamSynchronize(t->ctx->stream);
+    cudaFree(t->d_proj); cudaFree(t->d_pnorm); cudaFree(t->d_t); cudaFree(t->d_r);
+    cudaFree(t->hvals); cudaFree(t->bucket);
+    if (t->gid != t->bucket) cudaFree(t->gid);
+    for (size_t l = 0; l < t->by_bucket.size(); l++) {
+        if (l < t->by_group.size() && t->by_group[l].perm != t->by_bucket[l].perm) t->by_group[l].free_all();
+        t->by_bucket[l].free_all();
+    }
+    delete t;
+    return CRX_OK;
+}
+
+int crx_create_LSH_hashtables(crx_ctx* c, const crx_points* pts, int metric, int k, int L, int lsh_bucket_div,
+                              double euclidean_h_w, uint64_t seed, crx_lsh** out) {
+    CRX_REQUIRE(c && pts && out, "NULL argument");
+    CRX_REQUIRE(metric == CRX_EUCLIDEAN || metric == CRX_COSINE, "metric");
+    CRX_REQUIRE(k >= 1 && k <= 16 && L >= 1 && L <= 16, "k in [1,16], L in [1,16]");
+    CRX_CUDA(cudaSetDevice(c->device));
+    int64_t N = pts->n;
+    int D = pts->d;
+    crx_lsh* t = new crx_lsh();
+    t->ctx = c; t->pts = pts; t->metric = metric; t->k = k; t->L = L; t->D = D; t->N = N; t->w = (float)euclidean_h_w;
+    t->ldp = pts->ld;
+    if (metric == CRX_EUCLIDEAN) {
+        CRX_REQUIRE(lsh_bucket_div > 0 && (int64_t)((size_t)N / (size_t)lsh_bucket_div) > 0,
+                    "euclidean LSH needs N / lsh_bucket_div >= 1 buckets (lsh_cube.hpp:60)");
+        t->nbuckets = (int)((size_t)N / (size_t)lsh_bucket_div);
+    } else t->nbuckets = (int)std::pow(2, k);  // lsh_cube.hpp:65
+    int H = L * k;
+    // lsh_cube.hpp:49-51 + App. B consumption order
+    std::default_random_engine e;
+    e.seed((unsigned long)seed);
+    if (metric == CRX_EUCLIDEAN) {
+        t->euc_v.resize((size_t)H * D); t->euc_t.resize(H); t->euc_r.resize(H);
+        for (int l = 0; l < L; l++) {
+            std::uniform_int_distribution<int> ui(0, 100);  // euclidean_phi_gen.hpp:64
+            for (int j = 0; j < k; j++) {
+                int h = l * k + j;
+                draw_euclid_h(e, D, t->w, &t->euc_v[(size_t)h * D], &t->euc_t[h]);
+                t->euc_r[h] = ui(e);
+            }
+        }
+    } else {
+        t->cos_r.resize((size_t)H * D);
+        for (int h = 0; h < H; h++) draw_cosine_h(e, D, &t->cos_r[(size_t)h * D]);
+    }
+    int st = upload_proj(c, H, D, t->ldp, metric == CRX_COSINE ? t->cos_r.data() : nullptr,
+                         metric == CRX_EUCLIDEAN ? t->euc_v.data() : nullptr, &t->d_proj, &t->d_pnorm);
+    if (st != CRX_OK) { crx_lsh_destroy(t); return st; }
+    if (metric == CRX_EUCLIDEAN) {
+        CRX_CUDA(cudaMalloc((void**)&t->d_t, H * sizeof(float)));
+        CRX_CUDA(cudaMalloc((void**)&t->d_r, H * sizeof(int32_t)));
+        CRX_CUDA(cudaMemcpyAsync(t->d_t, t->euc_t.data(), H * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+        CRX_CUDA(cudaMemcpyAsync(t->d_r, t->euc_r.data(), H * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+        CRX_CUDA(cudaMalloc((void**)&t->hvals, (size_t)L * N * k * sizeof(int32_t)));
+    }
+    CRX_CUDA(cudaMalloc((void**)&t->bucket, (size_t)L * N * sizeof(int32_t)));
+    st = crx_hash_rows(c, pts, metric, k, L, t->d_proj, t->ldp, t->d_pnorm, t->d_t, t->d_r, t->w, t->nbuckets, t->hvals, t->bucket);
+    if (st != CRX_OK) { crx_lsh_destroy(t); return st; }
+    t->by_bucket.resize(L); t->by_group.resize(L); t->ngroups.resize(L);
+    if (metric == CRX_EUCLIDEAN) CRX_CUDA(cudaMalloc((void**)&t->gid, (size_t)L * N * sizeof(int32_t)));
+    else t->gid = t->bucket;
+    for (int l = 0; l < L; l++) {
+        st = crx_build_segments(c, t->bucket + (size_t)l * N, N, t->nbuckets, &t->by_bucket[l]);
+        if (st != CRX_OK) { crx_lsh_destroy(t); return st; }
+        if (metric == CRX_EUCLIDEAN) {
+            st = build_tuple_groups(c, t->hvals + (size_t)l * N * k, N, k, t->gid + (size_t)l * N, &t->by_group[l], &t->ngroups[l]);
+            if (st != CRX_OK) { crx_lsh_destroy(t); return st; }
+        } else {
+            t->by_group[l] = t->by_bucket[l];
+            t->ngroups[l] = t->nbuckets;
+        }
+    }
+    CRX_CUDA(cudaStreamSynchronize(c->stream));
+    *out = t;
+    return CRX_OK;
+}
+
+int crx_lsh_bucket_ids(const crx_lsh* t, int32_t* out, int mem) {
+    CRX_REQUIRE(t && out, "NULL argument");
+    size_t bytes = (size_t)t->L * t->N * sizeof(int32_t);
+    CRX_CUDA(cudaMemcpyAsync(out, t->bucket, bytes, mem == CRX_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice, t->ctx->stream));
+    if (mem == CRX_HOST) CRX_CUDA(cudaStreamSynchronize(t->ctx->stream));
+    return CRX_OK;
+}
+
+int crx_lsh_detailed_hashes(const crx_lsh* t, int32_t* out, int mem) {
+    CRX_REQUIRE(t && out, "NULL argument");
+    CRX_REQUIRE(t->hvals, "detailed hashes exist for euclidean tables only (hasDetailedHash, cosine_g_gen.hpp:76)");
+    size_t bytes = (size_t)t->L * t->N * t->k * sizeof(int32_t);
+    CRX_CUDA(cudaMemcpyAsync(out, t->hvals, bytes, mem == CRX_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice, t->ctx->stream));
+    if (mem == CRX_HOST) CRX_CUDA(cudaStreamSynchronize(t->ctx->stream));
+    return CRX_OK;
+}
+
+int crx_lsh_params(const crx_lsh* t, double* cos_r, float* euc_v, float* euc_t, int32_t* euc_r) {
+    CRX_REQUIRE(t, "NULL argument");
+    if (cos_r && !t->cos_r.empty()) memcpy(cos_r, t->cos_r.data(), t->cos_r.size() * sizeof(double));
+    if (euc_v && !t->euc_v.empty()) memcpy(euc_v, t->euc_v.data(), t->euc_v.size() * sizeof(float));
+    if (euc_t && !t->euc_t.empty()) memcpy(euc_t, t->euc_t.data(), t->euc_t.size() * sizeof(float));
+    if (euc_r && !t->euc_r.empty()) memcpy(euc_r, t->euc_r.data(), t->euc_r.size() * sizeof(int32_t));
+    return CRX_OK;
+}
+
+int crx_get_LSH_combined_buckets(const crx_lsh* t, int64_t q, int filtered, int32_t* out, int64_t cap, int64_t* count) {
+    CRX_REQUIRE(t && count, "NULL argument");
+    CRX_REQUIRE(q >= 0 && q < t->N, "query_row out of range");
+    crx_ctx* c = t->ctx;
+    CRX_CUDA(cudaSetDevice(c->device));
+    std::vector<int32_t> all;
+    for (int l = 0; l < t->L; l++) {
+        const Segments& s = filtered ? t->by_group[l] : t->by_bucket[l];
+        const int32_t* ids = (filtered ? t->gid : t->bucket) + (size_t)l * t->N;
+        int32_t g, off[2];
+        CRX_CUDA(cudaMemcpyAsync(&g, ids + q, sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+        CRX_CUDA(cudaStreamSynchronize(c->stream));
+        CRX_CUDA(cudaMemcpyAsync(off, s.off + g, 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+        CRX_CUDA(cudaStreamSynchronize(c->stream));
+        size_t base = all.size();
+        all.resize(base + (off[1] - off[0]));
+        if (off[1] > off[0])
+            CRX_CUDA(cudaMemcpyAsync(all.data() + base, s.perm + off[0], (size_t)(off[1] - off[0]) * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+        CRX_CUDA(cudaStreamSynchronize(c->stream));
+    }
+    std::sort(all.begin(), all.end());  // std::set<CustVector*> order = row order (lsh_cube.hpp:96,104)
+    all.erase(std::unique(all.begin(), all.end()), all.end());
+    *count = (int64_t)all.size();
+    if (out) for (size_t i = 0; i < all.size() && (int64_t)i < cap; i++) out[i] = all[i];
+    return CRX_OK;
+}
+
+// ---- hypercube ----
+int crx_cube_destroy(crx_cube* cu) {
+    if (!cu) return CRX_OK;
+    cudaSetDevice(cu->ctx->device);
+    cudaStreamSynchronize(cu->ctx->stream);
+    cudaFree(cu->vertex);
+    cu->by_vertex.free_all();
+    delete cu;
+    return CRX_OK;
+}
+
+int crx_create_hypercube(crx_ctx* c, const crx_points* pts, int metric, int k, double euclidean_h_w, uint64_t seed,
+                         crx_cube** out) {
+    CRX_REQUIRE(c && pts && out, "NULL argument");
+    CRX_REQUIRE(metric == CRX_EUCLIDEAN || metric == CRX_COSINE, "metric");
+    CRX_REQUIRE(k >= 1 && k <= 16, "cube dimension k must be in [1,16]");
+    CRX_CUDA(cudaSetDevice(c->device));
+    int64_t N = pts->n;
+    int D = pts->d;
+    CRX_REQUIRE((uint64_t)N * (uint64_t)k < (1ull << 32), "N*k must be below 2^32");
+    crx_cube* cu = new crx_cube();
+    cu->ctx = c; cu->pts = pts; cu->metric = metric; cu->k = k; cu->D = D; cu->N = N; cu->w = (float)euclidean_h_w;
+    cu->engine.seed((unsigned long)seed);  // lsh_cube.hpp:112-114
+    if (metric == CRX_EUCLIDEAN) {
+        cu->euc_v.resize((size_t)k * D); cu->euc_t.resize(k);
+        for (int j = 0; j < k; j++) draw_euclid_h(cu->engine, D, cu->w, &cu->euc_v[(size_t)j * D], &cu->euc_t[j]);  // euclidean_f_gen.hpp:54-57
+    } else {
+        cu->cos_r.resize((size_t)k * D);
+        for (int j = 0; j < k; j++) draw_cosine_h(cu->engine, D, &cu->cos_r[(size_t)j * D]);
+    }
+    double* d_proj = nullptr; double* d_pnorm = nullptr; float* d_t = nullptr;
+    int st = upload_proj(c, k, D, pts->ld, metric == CRX_COSINE ? cu->cos_r.data() : nullptr,
+                         metric == CRX_EUCLIDEAN ? cu->euc_v.data() : nullptr, &d_proj, &d_pnorm);
+    if (st != CRX_OK) { crx_cube_destroy(cu); return st; }
+    CRX_CUDA(cudaMalloc((void**)&cu->vertex, N * sizeof(int32_t)));
+    int nvert = 1 << k;
+    if (metric == CRX_COSINE) {
+        st = crx_hash_rows(c, pts, metric, k, 1, d_proj, pts->ld, d_pnorm, nullptr, nullptr, 0.f, nvert, nullptr, cu->vertex);
+    } else {
+        CRX_CUDA(cudaMalloc((void**)&d_t, k * sizeof(float)));
+        CRX_CUDA(cudaMemcpyAsync(d_t, cu->euc_t.data(), k * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+        DevBuf<int32_t> hv;
+        CRX_TRY(hv.alloc(c, (size_t)N * k));
+        st = crx_hash_rows(c, pts, metric, k, 1, d_proj, pts->ld, d_pnorm, d_t, nullptr, cu->w, nvert, hv.p, nullptr);
+        if (st == CRX_OK) {
+            // first-occurrence order of the distinct (f, h) pairs in (row-major, f-minor) order:
+            // that is the order in which EuclideanFGen draws its 1-or-2 (euclidean_f_gen.hpp:65-79)
+            int64_t total = N * k;
+            DevBuf<unsigned long long> keys, keys2, hkeys;
+            DevBuf<uint32_t> pos, pos2, hpos;
+            DevBuf<int> cnt;
+            CRX_TRY(keys.alloc(c, total)); CRX_TRY(keys2.alloc(c, total));
+            CRX_TRY(pos.alloc(c, total)); CRX_TRY(pos2.alloc(c, total));
+            CRX_TRY(cnt.alloc(c, 1));
+            { CRX_KERNEL(c, "cube_keys"); cube_keys_kernel<<<crx_grid(total, 256), 256, 0, c->stream>>>(hv.p, total, k, keys.p, pos.p); }
+            size_t bytes = 0;
+            CRX_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, bytes, keys.p, keys2.p, pos.p, pos2.p, (int)total, 0, 37, c->stream));
+            DevBuf<char> tmp;
+            CRX_TRY(tmp.alloc(c, bytes));
+            CRX_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, bytes, keys.p, keys2.p, pos.p, pos2.p, (int)total, 0, 37, c->stream));
+            int cap = 1 << 20, nheads = 0;
+            for (int attempt = 0; attempt < 2; attempt++) {
+                CRX_TRY(hkeys.alloc(c, cap)); CRX_TRY(hpos.alloc(c, cap));
+                CRX_CUDA(cudaMemsetAsync(cnt.p, 0, sizeof(int), c->stream));
+                { CRX_KERNEL(c, "cube_heads"); cube_heads_kernel<<<crx_grid(total, 256), 256, 0, c->stream>>>(keys2.p, pos2.p, total, hkeys.p, hpos.p, cap, cnt.p); }
+                CRX_CUDA(cudaMemcpyAsync(&nheads, cnt.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+                CRX_CUDA(cudaStreamSynchronize(c->stream));
+                if (nheads <= cap) break;
+                cap = nheads;
+            }
+            std::vector<unsigned long long> hk(nheads);
+            std::vector<uint32_t> hp(nheads);
+            CRX_CUDA(cudaMemcpyAsync(hk.data(), hkeys.p, nheads * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
+            CRX_CUDA(cudaMemcpyAsync(hp.data(), hpos.p, nheads * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+            CRX_CUDA(cudaStreamSynchronize(c->stream));
+            std::vector<int> order(nheads);
+            for (int i = 0; i < nheads; i++) order[i] = i;
+            std::sort(order.begin(), order.end(), [&](int a, int b) { return hp[a] < hp[b]; });
+            cu->fmap.assign(k, std::vector<std::pair<int32_t, int32_t>>());
+            for (int oi = 0; oi < nheads; oi++) {
+                unsigned long long key = hk[order[oi]];
+                int f = (int)(key >> 32);
+                int32_t h = (int32_t)((uint32_t)(key & 0xffffffffull) ^ 0x80000000u);
+                std::uniform_int_distribution<int> u12(1, 2);  // fresh object per draw (euclidean_f_gen.hpp:72)
+                int bit = mod_ii(h, u12(cu->engine));
+                cu->fmap[f].emplace_back(h, bit);
+            }
+            std::vector<int32_t> mh, mb, mo(k + 1, 0);
+            for (int f = 0; f < k; f++) {
+                std::sort(cu->fmap[f].begin(), cu->fmap[f].end());
+                for (auto& pr : cu->fmap[f]) { mh.push_back(pr.first); mb.push_back(pr.second); }
+                mo[f + 1] = (int32_t)mh.size();
+            }
+            DevBuf<int32_t> dmh, dmb, dmo;
+            CRX_TRY(dmh.alloc(c, mh.size())); CRX_TRY(dmb.alloc(c, mb.size())); CRX_TRY(dmo.alloc(c, mo.size()));
+            CRX_CUDA(cudaMemcpyAsync(dmh.p, mh.data(), mh.size() * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+            CRX_CUDA(cudaMemcpyAsync(dmb.p, mb.data(), mb.size() * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+            CRX_CUDA(cudaMemcpyAsync(dmo.p, mo.data(), mo.size() * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+            { CRX_KERNEL(c, "cube_vertex"); cube_vertex_kernel<<<crx_grid(N, 256), 256, 0, c->stream>>>(hv.p, N, k, dmh.p, dmb.p, dmo.p, cu->vertex); }
+            CRX_CUDA(cudaGetLastError());
+            CRX_CUDA(cudaStreamSynchronize(c->stream));
+        }
+    }
+    cudaFree(d_proj); cudaFree(d_pnorm); cudaFree(d_t);
+    if (st != CRX_OK) { crx_cube_destroy(cu); return st; }
+    st = crx_build_segments(c, cu->vertex, N, nvert, &cu->by_vertex);
+    if (st != CRX_OK) { crx_cube_destroy(cu); return st; }
+    CRX_CUDA(cudaStreamSynchronize(c->stream));
+    *out = cu;
+    return CRX_OK;
+}
+
+int crx_cube_vertex_ids(const crx_cube* cu, int32_t* out, int mem) {
+    CRX_REQUIRE(cu && out, "NULL argument");
+    CRX_CUDA(cudaMemcpyAsync(out, cu->vertex, cu->N * sizeof(int32_t), mem == CRX_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice, cu->ctx->stream));
+    if (mem == CRX_HOST) CRX_CUDA(cudaStreamSynchronize(cu->ctx->stream));
+    return CRX_OK;
+}
+
+int crx_get_hypercube_combined_buckets(const crx_cube* cu, int64_t q, int probes, int32_t* out, int64_t cap, int64_t* count) {
+    CRX_REQUIRE(cu && count, "NULL argument");
+    CRX_REQUIRE(q >= 0 && q < cu->N, "query_row out of range");
+    crx_ctx* c = cu->ctx;
+    CRX_CUDA(cudaSetDevice(c->device));
+    int32_t home;
+    CRX_CUDA(cudaMemcpyAsync(&home, cu->vertex + q, sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+    CRX_CUDA(cudaStreamSynchronize(c->stream));
+    std::vector<int> seq;
+    crx_cube_probe_sequence(home, probes, cu->k, seq);
+    std::vector<int32_t> off((size_t)(1 << cu->k) + 1);
+    CRX_CUDA(cudaMemcpyAsync(off.data(), cu->by_vertex.off, off.size() * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+    CRX_CUDA(cudaStreamSynchronize(c->stream));
+    int64_t n = 0;
+    for (int v : seq) {
+        int64_t len = off[v + 1] - off[v];
+        if (out && n < cap && len > 0) {
+            int64_t take = std::min<int64_t>(len, cap - n);
+            CRX_CUDA(cudaMemcpyAsync(out + n, cu->by_vertex.perm + off[v], take * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+        }
+        n += len;
+    }
+    CRX_CUDA(cudaStreamSynchronize(c->stream));
+    *count = n;
+    return CRX_OK;
+}
+
+} // extern "C"

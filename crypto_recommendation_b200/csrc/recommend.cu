@@ -1,0 +1,528 @@
+// recommend.cu -- crypto_rec.hpp:214-345 on the GPU:
+//   K9  masked cosine-similarity scan with a register-resident top-32 list per query (filter),
+//   K10 exact re-evaluation of the survivors, descending order, weighted rating prediction and the
+//       literal Lomuto top-N over the unknown coins (refine + predict),
+//   cluster-neighbour recommendation (get_top_N_recom without similarities).
+#include <algorithm>
+#include <climits>
+
+#include "pair_tile.cuh"
+#include "rowwalk.cuh"
+#include "tables.cuh"
+
+constexpr int LIST = 32;   // per-query candidate list length (one entry per lane)
+constexpr int MAXL = 16;
+
+struct ScanArgs {
+    int L, pass;                      // pass = table index, or -1 for the dense any-table scan
+    int64_t nq;                       // queries in this launch (positions in qperm)
+    int64_t nb;                       // candidate positions
+    const int32_t* qperm;             // position -> query row (absolute row of the query point set)
+    int64_t q_begin;                  // first query row of the batch (lists / ncand are relative to it)
+    const int32_t* qgid[MAXL];        // [row] group id of the query rows per table
+    const int32_t* cgid[MAXL];        // [row] group id of the base rows per table
+    const int32_t* cperm;             // position -> base row (NULL = identity)
+    const int32_t* csorted;           // group ids of the pass's table in cperm order (NULL for dense)
+    double* list_s;                   // [nq_total][LIST]
+    int32_t* list_i;                  // [nq_total][LIST]
+    int32_t* ncand;                   // [nq_total]
+    int load_state;                   // lists already hold the results of earlier passes
+};
+
+__device__ __forceinline__ void warp_argmin(double v, double& mn, int& ml) {
+    int lane = threadIdx.x & 31;
+    double bv = v;
+    int bl = lane;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        double ov = __shfl_xor_sync(0xffffffffu, bv, off);
+        int ol = __shfl_xor_sync(0xffffffffu, bl, off);
+        if (ov < bv || (ov == bv && ol < bl)) { bv = ov; bl = ol; }
+    }
+    mn = bv; ml = bl;
+}
+
+template <typename TQ, typename TB>
+__global__ void __launch_bounds__(pt::NT)
+topp_scan_kernel(const TQ* __restrict__ xq, int ldq, const double* __restrict__ sqn_q, const TB* __restrict__ xb, int ldb,
+                 const double* __restrict__ sqn_b, ScanArgs a) {
+    extern __shared__ double sm[];
+    int ld = ldb;
+    double* As = sm;
+    double* Bs = sm + pt::BM * ld;
+    double* cinv = Bs + pt::BN * ld;                       // [BN]
+    int32_t* crow = reinterpret_cast<int32_t*>(cinv + pt::BN);  // [BN]
+    int32_t* cg = crow + pt::BN;                           // [L][BN]
+    int32_t* qg = cg + MAXL * pt::BN;                      // [L][BM]
+    __shared__ int64_t range[2];
+    int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    int64_t p0 = (int64_t)blockIdx.x * pt::BM;
+    pt::load_a_tile<TQ>(As, xq, ld, a.qperm, p0, a.nq);
+    for (int e = threadIdx.x; e < a.L * pt::BM; e += pt::NT) {
+        int l = e / pt::BM, r = e - l * pt::BM;
+        int64_t pos = p0 + r;
+        qg[l * pt::BM + r] = pos < a.nq ? a.qgid[l][a.qperm[pos]] : -2;
+    }
+    if (threadIdx.x == 0) {
+        int64_t c0 = 0, c1 = a.nb;
+        if (a.pass >= 0) {
+            int64_t plast = min(p0 + pt::BM, a.nq) - 1;
+            int gfirst = a.qgid[a.pass][a.qperm[p0]], glast = a.qgid[a.pass][a.qperm[plast]];
+            if (glast < 0) { c0 = 0; c1 = 0; }
+            else {
+                if (gfirst < 0) gfirst = 0;
+                int64_t lo = 0, hi = a.nb;
+                while (lo < hi) { int64_t m = (lo + hi) >> 1; if (a.csorted[m] < gfirst) lo = m + 1; else hi = m; }
+                c0 = lo;
+                hi = a.nb;
+                while (lo < hi) { int64_t m = (lo + hi) >> 1; if (a.csorted[m] <= glast) lo = m + 1; else hi = m; }
+                c1 = lo;
+            }
+        }
+        range[0] = c0; range[1] = c1;
+    }
+    // per-row state (this lane's slot of each of the warp's 8 lists)
+    double ls[pt::RW], thr[pt::RW], qinv[pt::RW];
+    int li[pt::RW], minlane[pt::RW], cnt[pt::RW];
+    int64_t qrel[pt::RW];
+#pragma unroll
+    for (int r = 0; r < pt::RW; r++) {
+        int64_t pos = p0 + warp * pt::RW + r;
+        cnt[r] = 0;
+        if (pos < a.nq) {
+            int64_t qrow = a.qperm[pos];
+            qrel[r] = qrow - a.q_begin;
+            qinv[r] = 1.0 / sqrt(sqn_q[qrow]);
+            if (a.load_state) { ls[r] = a.list_s[qrel[r] * LIST + lane]; li[r] = a.list_i[qrel[r] * LIST + lane]; }
+            else { ls[r] = -INFINITY; li[r] = -1; }
+        } else { qrel[r] = -1; qinv[r] = 0.0; ls[r] = -INFINITY; li[r] = -1; }
+        warp_argmin(ls[r], thr[r], minlane[r]);
+    }
+    __syncthreads();
+    int64_t c0 = range[0], c1 = range[1];
+    for (int64_t cb = c0; cb < c1; cb += pt::BN) {
+        __syncthreads();
+        pt::load_b_tile<TB>(Bs, xb, ld, a.cperm, cb, c1);
+        if (threadIdx.x < pt::BN) {
+            int64_t pos = cb + threadIdx.x;
+            int row = -1;
+            double inv = 0.0;
+            if (pos < c1) { row = a.cperm ? a.cperm[pos] : (int)pos; inv = 1.0 / sqrt(sqn_b[row]); }
+            crow[threadIdx.x] = row;
+            cinv[threadIdx.x] = inv;
+        }
+        for (int e = threadIdx.x; e < a.L * pt::BN; e += pt::NT) {
+            int l = e / pt::BN, col = e - l * pt::BN;
+            int64_t pos = cb + col;
+            int g = -3;
+            if (pos < c1) { int row = a.cperm ? a.cperm[pos] : (int)pos; g = a.cgid[l][row]; }
+            cg[l * pt::BN + col] = g;
+        }
+        __syncthreads();
+        double acc[pt::RW][2];
+        pt::tile_mac<pt::FORM_DOT>(As, Bs, ld, warp, lane, acc);
+#pragma unroll
+        for (int cc = 0; cc < 2; cc++) {
+            int col = 2 * lane + cc;
+            int brow = crow[col];
+            double binv = cinv[col];
+#pragma unroll
+            for (int r = 0; r < pt::RW; r++) {
+                int rr = warp * pt::RW + r;
+                bool match = false;
+                if (brow >= 0 && qrel[r] >= 0) {
+                    if (a.pass < 0) {
+                        for (int l = 0; l < a.L; l++) match |= (qg[l * pt::BM + rr] == cg[l * pt::BN + col]);
+                    } else {
+                        match = qg[a.pass * pt::BM + rr] == cg[a.pass * pt::BN + col];
+                        for (int l = 0; l < a.pass; l++) match &= (qg[l * pt::BM + rr] != cg[l * pt::BN + col]);
+                    }
+                }
+                double s = acc[r][cc] * qinv[r] * binv;
+                if (match) cnt[r]++;
+                bool want = match && s > thr[r];
+                unsigned m = __ballot_sync(0xffffffffu, want);
+                while (m) {
+                    int src = __ffs(m) - 1;
+                    m &= m - 1;
+                    double sv = __shfl_sync(0xffffffffu, s, src);
+                    int iv = __shfl_sync(0xffffffffu, brow, src);
+                    if (sv > thr[r]) {
+                        if (lane == minlane[r]) { ls[r] = sv; li[r] = iv; }
+                        warp_argmin(ls[r], thr[r], minlane[r]);
+                    }
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < pt::RW; r++) {
+        int total = cnt[r];
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) total += __shfl_xor_sync(0xffffffffu, total, off);
+        if (qrel[r] >= 0) {
+            a.list_s[qrel[r] * LIST + lane] = ls[r];
+            a.list_i[qrel[r] * LIST + lane] = li[r];
+            if (lane == 0 && total) atomicAdd(&a.ncand[qrel[r]], total);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K10: refine + predict + top-N.  One warp per query.
+// ------------------------------------------------------------------------------------------------
+template <typename TQ, typename TB>
+__global__ void __launch_bounds__(256)
+rec_finalize_kernel(const TQ* __restrict__ xq, int ldq, const double* __restrict__ sqn_q, const uint8_t* __restrict__ unk_q,
+                    const double* __restrict__ mean_q, const TB* __restrict__ xb, int ldb, const double* __restrict__ sqn_b,
+                    const double* __restrict__ mean_b, int D, int64_t q_begin, int64_t nq, int P, int Nrec,
+                    const double* __restrict__ list_s, const int32_t* __restrict__ list_i, const int32_t* __restrict__ ncand,
+                    int32_t* __restrict__ recs, int32_t* __restrict__ nbr_rows, double* __restrict__ nbr_sims,
+                    unsigned long long* counters) {
+    __shared__ int s_idx[8][LIST];
+    __shared__ double s_sim[8][LIST];
+    __shared__ double s_pred[8][128];
+    __shared__ int s_coin[8][128];
+    int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    int64_t qrel = (int64_t)blockIdx.x * 8 + warp;
+    if (qrel >= nq) return;
+    int64_t qrow = q_begin + qrel;
+    const TQ* q = xq + qrow * ldq;
+    int idx = list_i[qrel * LIST + lane];
+    double approx = list_s[qrel * LIST + lane];
+    double sim = -INFINITY;
+    if (idx >= 0) sim = cos_sim_exact(xb + (size_t)idx * ldb, q, D, sqn_b[idx], sqn_q[qrow]);  // crypto_rec.hpp:220
+    unsigned validmask = __ballot_sync(0xffffffffu, idx >= 0);
+    int nvalid = __popc(validmask);
+    int rank = 0;
+    for (int t = 0; t < 32; t++) {
+        double os = __shfl_sync(0xffffffffu, sim, t);
+        int oi = __shfl_sync(0xffffffffu, idx, t);
+        if (oi >= 0 && (os > sim || (os == sim && oi < idx))) rank++;
+    }
+    if (idx < 0) rank = 64;
+    int keep = min(P, nvalid);
+    if (rank < LIST) { s_idx[warp][rank] = idx; s_sim[warp][rank] = sim; }
+    __syncwarp();
+    int nc = ncand[qrel];
+    // certification: every candidate that is not in the list has an approximate similarity <= the
+    // smallest approximate one in it; the exact P-th best must clear that by more than the scan's error
+    if (nc > LIST && keep > 0) {
+        double amin = approx;
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) amin = fmin(amin, __shfl_xor_sync(0xffffffffu, amin, off));
+        double pth = s_sim[warp][keep - 1];
+        if (lane == 0 && !(pth > amin + 1e-12 * fmax(1.0, fabs(amin)))) atomicAdd(&counters[CRX_CNT_TOPP_RESCAN], 1ull);
+    }
+    if (nbr_rows) for (int j = lane; j < P; j += 32) nbr_rows[qrel * P + j] = j < keep ? s_idx[warp][j] : -1;
+    if (nbr_sims) for (int j = lane; j < P; j += 32) nbr_sims[qrel * P + j] = j < keep ? s_sim[warp][j] : 0.0;
+    if (!recs) return;
+    if (nc == 0) {  // `if (!neighbors.empty())` (main.cpp:161)
+        for (int j = lane; j < Nrec; j += 32) recs[qrel * Nrec + j] = -1;
+        return;
+    }
+    // crypto_rec.hpp:281-306 for the unknown coins, neighbours in descending-similarity order
+    double mq = mean_q[qrow];
+    int nu = 0;
+    for (int j0 = 0; j0 < D; j0 += 32) {
+        int j = j0 + lane;
+        bool u = j < D && unk_q[qrow * D + j] != 0;
+        double pred = 0.0;
+        if (u) {
+            double main_sum = 0.0, abs_sum = 0.0;
+            for (int i = 0; i < keep; i++) {
+                double s = s_sim[warp][i];
+                int nb = s_idx[warp][i];
+                abs_sum = __dadd_rn(abs_sum, fabs(s));
+                double v = (double)xb[(size_t)nb * ldb + j];
+                main_sum = __dadd_rn(main_sum, __dmul_rn(s, __dsub_rn(v, mean_b[nb])));
+            }
+            pred = __dadd_rn(__ddiv_rn(main_sum, abs_sum), mq);
+        }
+        unsigned um = __ballot_sync(0xffffffffu, u);
+        if (u) {
+            int slot = nu + __popc(um & ((1u << lane) - 1));
+            s_pred[warp][slot] = pred;
+            s_coin[warp][slot] = j;
+        }
+        nu += __popc(um);
+    }
+    __syncwarp();
+    if (lane == 0) lomuto_desc(s_pred[warp], s_coin[warp], nu);  // crypto_rec.hpp:320
+    __syncwarp();
+    for (int j = lane; j < Nrec; j += 32) recs[qrel * Nrec + j] = j < nu ? s_coin[warp][j] : 0;  // resize(N) pads with 0
+}
+
+// ------------------------------------------------------------------------------------------------
+// cluster-neighbour recommendation (crypto_rec.hpp:328-345): similarities to ALL co-members in
+// input order, no sort, no cut.  One warp per query; members are consumed 32 at a time (each lane
+// computes one exact similarity), then every lane owning a coin accumulates the 32 in order.
+// ------------------------------------------------------------------------------------------------
+template <typename TQ, typename TB>
+__global__ void __launch_bounds__(256)
+rec_cluster_kernel(const TQ* __restrict__ xq, int ldq, const double* __restrict__ sqn_q, const uint8_t* __restrict__ unk_q,
+                   const double* __restrict__ mean_q, const int32_t* __restrict__ qlabels, const TB* __restrict__ xb, int ldb,
+                   const double* __restrict__ sqn_b, const double* __restrict__ mean_b, const int32_t* __restrict__ perm,
+                   const int32_t* __restrict__ off, int D, int64_t nq, int Nrec, int32_t* __restrict__ recs) {
+    __shared__ int s_idx[8][32];
+    __shared__ double s_sim[8][32];
+    __shared__ double s_pred[8][128];
+    __shared__ int s_coin[8][128];
+    int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    int64_t qrow = (int64_t)blockIdx.x * 8 + warp;
+    if (qrow >= nq) return;
+    int cl = qlabels[qrow];
+    int begin = off[cl], end = off[cl + 1];
+    if (begin == end) {
+        for (int j = lane; j < Nrec; j += 32) recs[qrow * Nrec + j] = -1;
+        return;
+    }
+    const TQ* q = xq + qrow * ldq;
+    double nqv = sqn_q[qrow];
+    double main_sum[4] = {0, 0, 0, 0}, abs_sum = 0.0;  // coins lane, lane+32, lane+64, lane+96
+    for (int base = begin; base < end; base += 32) {
+        int p = base + lane;
+        int nb = p < end ? perm[p] : -1;
+        s_idx[warp][lane] = nb;
+        s_sim[warp][lane] = nb >= 0 ? cos_sim_exact(xb + (size_t)nb * ldb, q, D, sqn_b[nb], nqv) : 0.0;
+        __syncwarp();
+        int lim = min(32, end - base);
+        for (int i = 0; i < lim; i++) {
+            double s = s_sim[warp][i];
+            int r = s_idx[warp][i];
+            abs_sum = __dadd_rn(abs_sum, fabs(s));
+            double mb = mean_b[r];
+#pragma unroll
+            for (int t = 0; t < 4; t++) {
+                int j = lane + 32 * t;
+                if (j < D) main_sum[t] = __dadd_rn(main_sum[t], __dmul_rn(s, __dsub_rn((double)xb[(size_t)r * ldb + j], mb)));
+            }
+        }
+        __syncwarp();
+    }
+    double mq = mean_q[qrow];
+    int nu = 0;
+#pragma unroll
+    for (int t = 0; t < 4; t++) {
+        int j = lane + 32 * t;
+        bool u = j < D && unk_q[qrow * D + j] != 0;
+        unsigned um = __ballot_sync(0xffffffffu, u);
+        if (u) {
+            int slot = nu + __popc(um & ((1u << lane) - 1));
+            s_pred[warp][slot] = __dadd_rn(__ddiv_rn(main_sum[t], abs_sum), mq);
+            s_coin[warp][slot] = j;
+        }
+        nu += __popc(um);
+    }
+    __syncwarp();
+    if (lane == 0) lomuto_desc(s_pred[warp], s_coin[warp], nu);
+    __syncwarp();
+    for (int j = lane; j < Nrec; j += 32) recs[qrow * Nrec + j] = j < nu ? s_coin[warp][j] : 0;
+}
+
+__global__ void quicksort_kernel(double* sims, int32_t* ids, int n) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) lomuto_desc(sims, ids, n);
+}
+
+__global__ void fill_lists_kernel(double* s, int32_t* i, int32_t* nc, int64_t nq) {
+    int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < nq * LIST) { s[t] = -INFINITY; i[t] = -1; }
+    if (t < nq) nc[t] = 0;
+}
+
+__global__ void iota_off_kernel(int32_t* p, int64_t n, int32_t off) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = (int32_t)i + off;
+}
+
+__global__ void add_off_kernel(int32_t* p, int64_t n, int32_t off) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] += off;
+}
+
+// sum over groups of (group size)^2, as double: cost model for the per-table passes
+__global__ void sq_sizes_kernel(const int32_t* __restrict__ off, int ngroups, double* __restrict__ out) {
+    int g = blockIdx.x * blockDim.x + threadIdx.x;
+    double v = 0.0;
+    if (g < ngroups) { double n = (double)(off[g + 1] - off[g]); v = n * n; }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0 && v != 0.0) atomicAdd(out, v);
+}
+
+extern "C" {
+
+int crx_recommend_lsh(crx_ctx* c, const crx_lsh* t, const crx_points* queries, int64_t q_begin, int64_t q_end, int P,
+                      int Nrec, int32_t* recs, int32_t* nbr_rows, double* nbr_sims, int32_t* ncand, int mem) {
+    CRX_REQUIRE(c && t, "NULL argument");
+    const crx_points* base = t->pts;
+    bool self = queries == nullptr || queries == base;
+    if (!queries) queries = base;
+    CRX_REQUIRE(queries->d == base->d, "query / table dimension mismatch");
+    CRX_REQUIRE(q_begin >= 0 && q_begin <= q_end && q_end <= queries->n, "query range");
+    CRX_REQUIRE(P >= 1 && P <= LIST, "P must be in [1, 32] in this round");
+    CRX_REQUIRE(Nrec >= 0 && Nrec <= 128, "Nrec");
+    if (recs) CRX_REQUIRE(base->mean && queries->unknown && queries->mean, "ratings metadata missing (crx_points_set_ratings)");
+    CRX_REQUIRE(self || t->metric == CRX_COSINE, "external queries are supported for cosine tables only in this round");
+    CRX_CUDA(cudaSetDevice(c->device));
+    int64_t nq = q_end - q_begin;
+    if (nq == 0) return CRX_OK;
+    int L = t->L;
+    int64_t N = base->n;
+
+    // group ids of the query rows
+    DevBuf<int32_t> qgid_buf;
+    const int32_t* qgid_base = t->gid;
+    int64_t qstride = N;
+    if (!self) {
+        CRX_TRY(qgid_buf.alloc(c, (size_t)L * queries->n));
+        CRX_TRY(crx_hash_rows(c, queries, t->metric, t->k, L, t->d_proj, t->ldp, t->d_pnorm, t->d_t, t->d_r, t->w, t->nbuckets, nullptr, qgid_buf.p));
+        qgid_base = qgid_buf.p;
+        qstride = queries->n;
+    }
+    DevBuf<double> list_s;
+    DevBuf<int32_t> list_i, nc;
+    CRX_TRY(list_s.alloc(c, (size_t)nq * LIST)); CRX_TRY(list_i.alloc(c, (size_t)nq * LIST)); CRX_TRY(nc.alloc(c, nq));
+    { CRX_KERNEL(c, "fill_lists"); fill_lists_kernel<<<crx_grid(nq * LIST, 256), 256, 0, c->stream>>>(list_s.p, list_i.p, nc.p, nq); }
+
+    // cost model: dense any-table scan (nq * N pairs) vs one pass per table (sum of squared group sizes,
+    // scaled to the query share)
+    DevBuf<double> cost;
+    CRX_TRY(cost.alloc(c, 1));
+    CRX_CUDA(cudaMemsetAsync(cost.p, 0, sizeof(double), c->stream));
+    for (int l = 0; l < L; l++) {
+        CRX_KERNEL(c, "sq_sizes");
+        sq_sizes_kernel<<<crx_grid(t->ngroups[l], 256), 256, 0, c->stream>>>(t->by_group[l].off, t->ngroups[l], cost.p);
+    }
+    double h_cost = 0;
+    CRX_CUDA(cudaMemcpyAsync(&h_cost, cost.p, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CRX_CUDA(cudaStreamSynchronize(c->stream));
+    double table_cost = h_cost * ((double)nq / (double)N) + (double)L * 64.0 * (double)nq;
+    double dense_cost = (double)nq * (double)N;
+    bool dense = dense_cost <= table_cost;
+
+    ScanArgs a;
+    memset(&a, 0, sizeof(a));
+    a.L = L; a.nq = nq; a.nb = N; a.q_begin = q_begin;
+    for (int l = 0; l < L; l++) { a.qgid[l] = qgid_base + (size_t)l * qstride; a.cgid[l] = t->gid + (size_t)l * N; }
+    a.list_s = list_s.p; a.list_i = list_i.p; a.ncand = nc.p;
+    int ld = base->ld;
+    size_t smem = pt::smem_bytes(ld) + pt::BN * sizeof(double) + pt::BN * sizeof(int32_t) + (size_t)MAXL * (pt::BN + pt::BM) * sizeof(int32_t);
+    int grid = (int)((nq + pt::BM - 1) / pt::BM);
+    DevBuf<int32_t> qperm, qkeys, qsorted;
+    CRX_TRY(qperm.alloc(c, nq));
+    auto launch_scan = [&](const ScanArgs& args) -> int {
+        CRX_KERNEL(c, "topp_scan");
+#define LAUNCH_T(TQ, TB, xqp, xbp)                                                                                      \
+    do {                                                                                                                \
+        CRX_CUDA(cudaFuncSetAttribute(topp_scan_kernel<TQ, TB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        topp_scan_kernel<TQ, TB><<<grid, pt::NT, smem, c->stream>>>(xqp, queries->ld, queries->sqn, xbp, base->ld, base->sqn, args); \
+    } while (0)
+        if (queries->x64 && base->x64) LAUNCH_T(double, double, queries->x64, base->x64);
+        else if (queries->x64) LAUNCH_T(double, float, queries->x64, base->x32);
+        else if (base->x64) LAUNCH_T(float, double, queries->x32, base->x64);
+        else LAUNCH_T(float, float, queries->x32, base->x32);
+#undef LAUNCH_T
+        CRX_CUDA(cudaGetLastError());
+        return CRX_OK;
+    };
+    if (dense) {
+        { CRX_KERNEL(c, "iota"); iota_off_kernel<<<crx_grid(nq, 256), 256, 0, c->stream>>>(qperm.p, nq, (int32_t)q_begin); }
+        a.pass = -1; a.qperm = qperm.p; a.cperm = nullptr; a.csorted = nullptr; a.load_state = 0;
+        CRX_TRY(launch_scan(a));
+    } else {
+        for (int l = 0; l < L; l++) {
+            // queries of the batch ordered by their group in table l
+            Segments qs;
+            int st = crx_build_segments(c, a.qgid[l] + q_begin, nq, std::max(1, t->ngroups[l]), &qs);
+            if (st != CRX_OK) { qs.free_all(); return st; }
+            { CRX_KERNEL(c, "add_off"); add_off_kernel<<<crx_grid(nq, 256), 256, 0, c->stream>>>(qs.perm, nq, (int32_t)q_begin); }
+            a.pass = l; a.qperm = qs.perm; a.cperm = t->by_group[l].perm; a.csorted = t->by_group[l].sorted; a.load_state = l > 0;
+            st = launch_scan(a);
+            CRX_CUDA(cudaStreamSynchronize(c->stream));
+            qs.free_all();
+            if (st != CRX_OK) return st;
+        }
+    }
+    IoBuf<int32_t> o_recs, o_rows, o_nc;
+    IoBuf<double> o_sims;
+    CRX_TRY(o_recs.bind(c, recs, (size_t)nq * Nrec, mem, false));
+    CRX_TRY(o_rows.bind(c, nbr_rows, (size_t)nq * P, mem, false));
+    CRX_TRY(o_sims.bind(c, nbr_sims, (size_t)nq * P, mem, false));
+    {
+        CRX_KERNEL(c, "rec_finalize");
+        int g = (int)((nq + 7) / 8);
+#define LAUNCH_F(TQ, TB, xqp, xbp)                                                                                         \
+    rec_finalize_kernel<TQ, TB><<<g, 256, 0, c->stream>>>(xqp, queries->ld, queries->sqn, queries->unknown, queries->mean, xbp, \
+                                                           base->ld, base->sqn, base->mean, base->d, q_begin, nq, P, Nrec,   \
+                                                           list_s.p, list_i.p, nc.p, o_recs.dev, o_rows.dev, o_sims.dev, c->counters)
+        if (queries->x64 && base->x64) LAUNCH_F(double, double, queries->x64, base->x64);
+        else if (queries->x64) LAUNCH_F(double, float, queries->x64, base->x32);
+        else if (base->x64) LAUNCH_F(float, double, queries->x32, base->x64);
+        else LAUNCH_F(float, float, queries->x32, base->x32);
+#undef LAUNCH_F
+    }
+    CRX_CUDA(cudaGetLastError());
+    if (ncand) {
+        CRX_CUDA(cudaMemcpyAsync(ncand, nc.p, nq * sizeof(int32_t), mem == CRX_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice, c->stream));
+    }
+    CRX_TRY(o_recs.flush());
+    CRX_TRY(o_rows.flush());
+    CRX_TRY(o_sims.flush());
+    if (mem == CRX_HOST) CRX_CUDA(cudaStreamSynchronize(c->stream));
+    return CRX_OK;
+}
+
+int crx_recommend_cluster(crx_ctx* c, const crx_points* users, const int32_t* labels, int lmem, int K,
+                          const crx_points* queries, const int32_t* qlabels, int Nrec, int32_t* recs, int mem) {
+    CRX_REQUIRE(c && users && labels && recs, "NULL argument");
+    bool self = queries == nullptr || queries == users;
+    if (!queries) queries = users;
+    CRX_REQUIRE(self || qlabels, "qlabels required for external queries");
+    CRX_REQUIRE(users->mean && queries->unknown && queries->mean, "ratings metadata missing (crx_points_set_ratings)");
+    CRX_REQUIRE(queries->d == users->d && users->d <= 128, "dimension");
+    CRX_REQUIRE(Nrec >= 0 && Nrec <= 128, "Nrec");
+    CRX_CUDA(cudaSetDevice(c->device));
+    int64_t N = users->n, nq = queries->n;
+    IoBuf<int32_t> lab, qlab, out;
+    CRX_TRY(lab.bind(c, labels, N, lmem, true));
+    if (!self) CRX_TRY(qlab.bind(c, qlabels, nq, lmem, true));
+    CRX_TRY(out.bind(c, recs, (size_t)nq * Nrec, mem, false));
+    Segments seg;
+    int st = crx_build_segments(c, lab.dev, N, K, &seg);
+    if (st != CRX_OK) { seg.free_all(); return st; }
+    {
+        CRX_KERNEL(c, "rec_cluster");
+        int g = (int)((nq + 7) / 8);
+        const int32_t* ql = self ? lab.dev : qlab.dev;
+#define LAUNCH_C(TQ, TB, xqp, xbp)                                                                                          \
+    rec_cluster_kernel<TQ, TB><<<g, 256, 0, c->stream>>>(xqp, queries->ld, queries->sqn, queries->unknown, queries->mean, ql, xbp, \
+                                                          users->ld, users->sqn, users->mean, seg.perm, seg.off, users->d, nq, Nrec, out.dev)
+        if (queries->x64 && users->x64) LAUNCH_C(double, double, queries->x64, users->x64);
+        else if (queries->x64) LAUNCH_C(double, float, queries->x64, users->x32);
+        else if (users->x64) LAUNCH_C(float, double, queries->x32, users->x64);
+        else LAUNCH_C(float, float, queries->x32, users->x32);
+#undef LAUNCH_C
+    }
+    CRX_CUDA(cudaGetLastError());
+    st = out.flush();
+    CRX_CUDA(cudaStreamSynchronize(c->stream));
+    seg.free_all();
+    return st;
+}
+
+int crx_parallel_quickSort(crx_ctx* c, double* sims, int32_t* ids, int n) {
+    CRX_REQUIRE(c && sims && ids && n >= 0, "argument");
+    if (n == 0) return CRX_OK;
+    CRX_CUDA(cudaSetDevice(c->device));
+    IoBuf<double> s;
+    IoBuf<int32_t> d;
+    CRX_TRY(s.bind(c, sims, n, CRX_HOST, true));
+    CRX_TRY(d.bind(c, ids, n, CRX_HOST, true));
+    { CRX_KERNEL(c, "quicksort"); quicksort_kernel<<<1, 32, 0, c->stream>>>(s.dev, d.dev, n); }
+    CRX_CUDA(cudaGetLastError());
+    CRX_TRY(s.flush());
+    return d.flush();
+}
+
+} // extern "C"

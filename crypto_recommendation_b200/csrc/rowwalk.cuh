@@ -1,0 +1,73 @@
+// rowwalk.cuh -- "each lane owns one row and walks it in index order" against one vector held in
+// shared memory.  Global reads are staged 32 rows x 16 columns at a time through shared memory, so
+// that they are coalesced in 64-byte pieces while every lane still performs the reference's scalar
+// loop over ITS row (cust_vector.hpp:107-174) -- which is what bit-exact distances require.
+#pragma once
+#include "common.cuh"
+
+namespace rw {
+
+constexpr int TW = 17;  // padded tile width (doubles)
+typedef double WarpTile[32][TW];
+
+// result of a walk: Euclidean => acc = sum (x_k - v_k)^2 exactly as the reference;
+// cosine => (hi, lo) compensated dot product x . v
+struct Walk {
+    double a, b;
+};
+
+// myrow < 0 => lane idle (still participates in the staging shuffles).
+template <typename T, int METRIC>
+__device__ __forceinline__ Walk walk_rows(const T* __restrict__ x, int ld, int d, int64_t myrow, const double* __restrict__ vec,
+                                          WarpTile& tile) {
+    int lane = threadIdx.x & 31;
+    double s = 0.0, c = 0.0;
+    for (int c0 = 0; c0 < d; c0 += 16) {
+#pragma unroll 4
+        for (int it = 0; it < 16; it++) {
+            int r = it * 2 + (lane >> 4);
+            int64_t src = __shfl_sync(0xffffffffu, myrow, r);
+            int col = c0 + (lane & 15);
+            tile[r][lane & 15] = (src >= 0 && col < d) ? (double)x[src * ld + col] : 0.0;
+        }
+        __syncwarp();
+        int lim = min(16, d - c0);
+        if (METRIC == CRX_EUCLIDEAN) {
+            for (int k = 0; k < lim; k++) {
+                double t = __dsub_rn(tile[lane][k], vec[c0 + k]);
+                s = __dadd_rn(s, __dmul_rn(t, t));
+            }
+        } else {
+            for (int k = 0; k < lim; k++) {
+                double p, pe, se;
+                two_prod(tile[lane][k], vec[c0 + k], p, pe);
+                two_sum(s, p, s, se);
+                c = __dadd_rn(c, __dadd_rn(pe, se));
+            }
+        }
+        __syncwarp();
+    }
+    Walk w;
+    if (METRIC == CRX_EUCLIDEAN) { w.a = s; w.b = 0.0; }
+    else two_sum(s, c, w.a, w.b);
+    return w;
+}
+
+// distance of the lane's row to `vec` in the reference's metric; nrow / nvec = exact sums of squares
+template <typename T, int METRIC>
+__device__ __forceinline__ double dist_rows(const T* __restrict__ x, int ld, int d, int64_t myrow, const double* __restrict__ vec,
+                                            double nrow, double nvec, WarpTile& tile) {
+    Walk w = walk_rows<T, METRIC>(x, ld, d, myrow, vec, tile);
+    if (METRIC == CRX_EUCLIDEAN) return __dsqrt_rn(w.a);
+    return __dsub_rn(1.0, cos_sim_from(w.a, nrow, nvec));
+}
+
+// stage one row of x into shared memory as doubles (all 32 lanes of the calling warp)
+template <typename T>
+__device__ __forceinline__ void stage_vector(const T* __restrict__ x, int ld, int64_t row, double* vec) {
+    int lane = threadIdx.x & 31;
+    for (int k = lane; k < ld; k += 32) vec[k] = (double)x[row * ld + k];
+    __syncwarp();
+}
+
+}  // namespace rw

@@ -1,0 +1,171 @@
+/*
+ * crx.h -- C ABI of the B200-native engine for crypto-recommendation's data-parallel hot path.
+ *
+ * The reference (YannisLamp/crypto-recommendation) has no FFI: its boundary is the set of header
+ * templates main.cpp calls.  Every entry point below replaces one of those templates on flat,
+ * contiguous buffers; the drop-in C++ headers under include/crx/ re-create the reference's own
+ * signatures (CustVector / CustHashtable / std::vector arguments) on top of this ABI.
+ * Citations are file:line in the reference tree.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; opaque handles own device memory;
+ *   - every function returns CRX_OK (0) or a negative status; crx_last_error() gives the text
+ *     (the reference has no error channel at all: cust_vector.hpp:111-115 prints and returns -1);
+ *   - `mem` says where a caller buffer lives: CRX_HOST (library copies through pinned staging)
+ *     or CRX_DEVICE (pointer is device memory on the context's GPU, used in place, stream-ordered);
+ *   - rows are 0-based indices into a crx_points object -- they stand for the CustVector*
+ *     pointers of the reference (ids are assumed unique, as its string-keyed caches require);
+ *   - metric: CRX_EUCLIDEAN / CRX_COSINE  <->  metric_type "euclidean" / "cosine";
+ *   - `seed` is the value the reference reads from system_clock::now() (lsh_cube.hpp:49,112;
+ *     initialization.hpp:42,75); RNG consumption order is the reference's (libstdc++ <random>);
+ *   - there is NO CPU fallback: without a CUDA device every compute entry point fails.
+ */
+#ifndef CRX_H
+#define CRX_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CRX_OK 0
+#define CRX_ERR_INVALID -1
+#define CRX_ERR_CUDA -2
+#define CRX_ERR_NOMEM -3
+#define CRX_ERR_UNSUPPORTED -4
+
+enum { CRX_F32 = 0, CRX_F64 = 1 };
+enum { CRX_HOST = 0, CRX_DEVICE = 1 };
+enum { CRX_EUCLIDEAN = 0, CRX_COSINE = 1 };
+
+typedef struct crx_ctx crx_ctx;       /* one GPU + one stream; calls on a context are serialised */
+typedef struct crx_points crx_points; /* std::vector<CustVector<T>> resident in HBM (cust_vector.hpp:23-36) */
+typedef struct crx_lsh crx_lsh;       /* std::vector<CustHashtable<T>*> of create_LSH_hashtables */
+typedef struct crx_cube crx_cube;     /* CustHashtable<T>* of create_hypercube */
+
+/* ---- context ---- */
+int crx_version(void);
+const char* crx_last_error(void);
+/* cuda_stream: a cudaStream_t to launch on (e.g. torch's current stream) or NULL for an own stream */
+int crx_ctx_create(int device, void* cuda_stream, crx_ctx** out);
+int crx_ctx_destroy(crx_ctx* ctx);
+int crx_ctx_synchronize(crx_ctx* ctx);
+/* number of this library's own kernels launched so far on the context */
+int64_t crx_ctx_launch_count(const crx_ctx* ctx);
+/* per-kernel CUDA-event timing (on the context's stream).  enable!=0 starts recording every
+ * launch; crx_ctx_kernel_time sums the launches whose name starts with `prefix`. */
+int crx_ctx_profile(crx_ctx* ctx, int enable);
+int crx_ctx_profile_reset(crx_ctx* ctx);
+int crx_ctx_kernel_time(crx_ctx* ctx, const char* prefix, double* total_ms, int64_t* launches);
+/* near-boundary / fallback counters since the last reset (see DESIGN.md "exactness"):
+ * [0] hash projections recomputed in double-double, [1] top-P queries that needed the exhaustive
+ * re-scan, [2] k-means++ draws within tolerance of a prefix boundary, [3] PAM rows re-summed exactly,
+ * [4] Lloyd points re-evaluated exactly, [5..7] reserved */
+int crx_ctx_counters(crx_ctx* ctx, int64_t out[8], int reset);
+
+/* ---- points: vector<CustVector<T>> (cust_vector.hpp:23-72) ---- */
+/* data: row-major [n][d] of dtype; copied.  d <= 128 in this round. */
+int crx_points_create(crx_ctx* ctx, const void* data, int dtype, int64_t n, int32_t d, int mem, crx_points** out);
+/* unknown_indexes / known_mean of every row (cust_vector.hpp:30-32): unknown[n][d] (1 = unknown), mean[n] */
+int crx_points_set_ratings(crx_points* p, const uint8_t* unknown, const double* known_mean, int mem);
+int crx_points_destroy(crx_points* p);
+int64_t crx_points_n(const crx_points* p);
+int32_t crx_points_d(const crx_points* p);
+
+/* ---- vector math on rows (cust_vector.hpp:107-174); out[m] for row pairs (a[i], b[i]) ---- */
+/* op: 0 inner_product, 1 euclideanDistance, 2 cosineDistance, 3 cosineSimilarity */
+int crx_pair_op(crx_ctx* ctx, const crx_points* pa, const int32_t* a, const crx_points* pb, const int32_t* b, int64_t m,
+                int op, double* out /* host */);
+
+/* ---- LSH tables (lsh_cube.hpp:45-74; generators/*.hpp; cust_hashtable.hpp:51-70) ---- */
+int crx_create_LSH_hashtables(crx_ctx* ctx, const crx_points* input_vectors, int metric, int k, int L,
+                              int lsh_bucket_div, double euclidean_h_w, uint64_t seed, crx_lsh** out);
+int crx_lsh_destroy(crx_lsh* t);
+/* CustHashtable::getHash of every stored row: out[L][N] (cust_hashtable.hpp:123) */
+int crx_lsh_bucket_ids(const crx_lsh* t, int32_t* out, int mem);
+/* EuclideanPhiGen::getDetailedHashes: out[L][N][k] (euclidean_phi_gen.hpp:94); CRX_ERR_INVALID for cosine */
+int crx_lsh_detailed_hashes(const crx_lsh* t, int32_t* out, int mem);
+/* get_LSH_combined_buckets (filtered=0, lsh_cube.hpp:78) / get_LSH_filtered_combined_buckets
+ * (filtered=1, lsh_cube.hpp:94) for a stored row; ascending row order; *count may exceed cap */
+int crx_get_LSH_combined_buckets(const crx_lsh* t, int64_t query_row, int filtered, int32_t* out /* host */,
+                                 int64_t cap, int64_t* count);
+/* hash parameters actually drawn (for inspection / parity): cosine r[L][k][D] doubles,
+ * euclidean v[L][k][D] floats, t[L][k] floats, r_i[L][k] ints.  Any pointer may be NULL.  Host. */
+int crx_lsh_params(const crx_lsh* t, double* cos_r, float* euc_v, float* euc_t, int32_t* euc_r);
+
+/* ---- hypercube (lsh_cube.hpp:109-177; euclidean_f_gen.hpp; hypercube_gen.hpp) ---- */
+int crx_create_hypercube(crx_ctx* ctx, const crx_points* input_vectors, int metric, int k, double euclidean_h_w,
+                         uint64_t seed, crx_cube** out);
+int crx_cube_destroy(crx_cube* c);
+int crx_cube_vertex_ids(const crx_cube* c, int32_t* out /* [N] */, int mem);
+/* get_hypercube_combined_buckets for a stored row: vertex visit order x insertion order */
+int crx_get_hypercube_combined_buckets(const crx_cube* c, int64_t query_row, int probes, int32_t* out /* host */,
+                                       int64_t cap, int64_t* count);
+/* utils.cpp:22-50 (host helper, exposed for known-answer tests); returns count */
+int crx_get_num_hamming_dist_from(int num, int dist, int min_bit, int bits, int32_t* out, int cap);
+
+/* ---- clustering: initialisation (initialization.hpp:40-156) ---- */
+int crx_rand_selection(crx_ctx* ctx, const crx_points* input_vectors, int cluster_num, uint64_t seed,
+                       int32_t* centroid_rows /* host [K] */);
+int crx_k_means_pp(crx_ctx* ctx, const crx_points* input_vectors, int cluster_num, int metric, uint64_t seed,
+                   int32_t* centroid_rows /* host [K] */);
+
+/* ---- clustering: assignment (assignment.hpp:55-217) ---- */
+/* centroids: [K][D] doubles in `cmem`; centroid_rows[K] (host, may be NULL): row the centroid pointer
+ * aliases or -1 -- reproduces `centroids[c]->setCluster(c,0)` (assignment.hpp:77-78).
+ * labels[N] int32, dists[N] double in `mem`. */
+int crx_lloyds_assignment(crx_ctx* ctx, const crx_points* input_vectors, const double* centroids, int cmem, int K,
+                          const int32_t* centroid_rows, int metric, int32_t* labels, double* dists, int mem);
+/* assignment.hpp:84-105: only rows with labels[v] == -1 are (re)assigned; labels/dists are in/out */
+int crx_lloyds_for_remaining(crx_ctx* ctx, const crx_points* input_vectors, const double* centroids, int cmem, int K,
+                             int metric, int32_t* labels, double* dists, int mem);
+/* assignment.hpp:109-129 / 132-152: centroids are stored rows (after init or PAM).
+ * labels_before_lloyd (nullable): labels after range_assignment, before lloyds_for_remaining. */
+int crx_lsh_range_assignment(crx_ctx* ctx, const crx_points* input_vectors, const crx_lsh* lsh_hashtables,
+                             const int32_t* centroid_rows, int K, int metric, int32_t* labels, double* dists, int mem,
+                             int32_t* labels_before_lloyd);
+int crx_cube_range_assignment(crx_ctx* ctx, const crx_points* input_vectors, const crx_cube* hypercube,
+                              const int32_t* centroid_rows, int K, int metric, int probes, int32_t* labels,
+                              double* dists, int mem, int32_t* labels_before_lloyd);
+
+/* ---- clustering: update (update.hpp:38-142) ---- */
+/* per-cluster coordinate sums [K][D] and member counts [K] (device or host); the data-parallel
+ * half of k_means -- the only part that needs an all-reduce when rows are sharded across GPUs */
+int crx_cluster_sums(crx_ctx* ctx, const crx_points* input_vectors, const int32_t* labels, int lmem, int K,
+                     double* sums, int64_t* counts, int mem);
+/* means (empty cluster => zeros, cust_vector.hpp:189), convergence test of update.hpp:63-80;
+ * new_centroids = centres after the call (old ones when *continue_clustering == 0). All host or all device. */
+int crx_k_means_finish(crx_ctx* ctx, const double* sums, const int64_t* counts, const double* old_centroids, int K,
+                       int D, int metric, double min_dist, double* new_centroids, int mem, int* continue_clustering);
+/* k_means (update.hpp:38) = crx_cluster_sums + crx_k_means_finish on one GPU */
+int crx_k_means(crx_ctx* ctx, const crx_points* input_vectors, const int32_t* labels, int lmem,
+                const double* old_centroids, int K, int metric, double min_dist, double* new_centroids, int cmem,
+                int* continue_clustering);
+/* pam_lloyds (update.hpp:90): new_centroid_rows[K] host */
+int crx_pam_lloyds(crx_ctx* ctx, const crx_points* input_vectors, const int32_t* labels, int lmem,
+                   const int32_t* centroid_rows, int K, int metric, int32_t* new_centroid_rows, int* median_swapped);
+/* silhouette_cluster (silhouette.hpp:32): sils[K+1] host */
+int crx_silhouette_cluster(crx_ctx* ctx, const crx_points* input_vectors, const int32_t* labels, int lmem,
+                           const double* centroids, int cmem, int K, int metric, double* sils);
+
+/* ---- recommendation (crypto_rec.hpp:214-345; loops of main.cpp:159-170, 205-216, 260-269, 353-373) ---- */
+/* For queries [q_begin, q_end) of `queries` (NULL => the table's own rows, rec A):
+ *   neighbours = get_LSH_filtered_combined_buckets; sims = get_P_closest(neighbours, user, P);
+ *   recs = get_top_N_recom(neighbours, user, Nrec, sims).
+ * Outputs (rows relative to q_begin; any may be NULL): recs[nq][Nrec] (-1 when the reference prints
+ * nothing), nbr_rows[nq][P] (-1 padded), nbr_sims[nq][P], ncand[nq]. */
+int crx_recommend_lsh(crx_ctx* ctx, const crx_lsh* lsh_hashtables, const crx_points* queries, int64_t q_begin,
+                      int64_t q_end, int P, int Nrec, int32_t* recs, int32_t* nbr_rows, double* nbr_sims,
+                      int32_t* ncand, int mem);
+/* neighbours = all rows of `users` with labels == qlabels[q]; get_top_N_recom without similarities
+ * (crypto_rec.hpp:328).  queries NULL => users themselves with qlabels = labels. */
+int crx_recommend_cluster(crx_ctx* ctx, const crx_points* users, const int32_t* labels, int lmem, int K,
+                          const crx_points* queries, const int32_t* qlabels, int Nrec, int32_t* recs, int mem);
+/* parallel_quickSort (crypto_rec.hpp:269) on the device, one thread: known-answer tests only */
+int crx_parallel_quickSort(crx_ctx* ctx, double* sims /* host, in/out */, int32_t* ids /* host, in/out */, int n);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CRX_H */

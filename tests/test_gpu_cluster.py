@@ -1,0 +1,223 @@
+"""GPU parity (through the C ABI): clustering phases vs the CPU oracle."""
+import numpy as np
+import pytest
+
+from oracle import EUCLIDEAN, COSINE
+from crypto_recommendation_b200 import capi, synth
+from helpers import assert_float_close, assert_labels
+
+pytestmark = pytest.mark.gpu
+METRICS = [EUCLIDEAN, COSINE]
+
+
+def dist_fn(port, X64, C, metric):
+    f = port.euclidean_distance if metric == EUCLIDEAN else port.cosine_distance
+    return lambda v, c: f(X64[v], C[c])
+
+
+@pytest.mark.parametrize("metric", METRICS)
+def test_golden_clustering(ctx, port, golden, metric):
+    g, name = golden, ("euc" if metric == EUCLIDEAN else "cos")
+    X = g["cl_X"]
+    P = ctx.points(X)
+    assert np.array_equal(capi.rand_selection(ctx, P, 9, 8001), g["cl_rand_sel"])
+    cidx = capi.k_means_pp(ctx, P, 7, metric, 8002)
+    assert np.array_equal(cidx, g["cl_kpp_%s" % name])
+    lab, dist = capi.lloyds_assignment(ctx, P, X[cidx], cidx, metric)
+    assert_labels(lab, g["cl_lloyd_lab_%s" % name], dist_fn(port, X, X[cidx], metric))
+    if metric == EUCLIDEAN:
+        assert np.array_equal(dist, g["cl_lloyd_dist_%s" % name])  # bit-exact
+    else:
+        assert_float_close(dist, g["cl_lloyd_dist_%s" % name], 1e-12)
+    ret, newc = capi.k_means(ctx, P, g["cl_lloyd_lab_%s" % name], X[cidx], metric, 0.05)
+    assert ret == bool(g["cl_kmeans_ret_%s" % name])
+    assert_float_close(newc, g["cl_kmeans_C_%s" % name], 1e-12)
+    lab2, dist2 = capi.lloyds_assignment(ctx, P, g["cl_kmeans_C_%s" % name], None, metric)
+    assert_labels(lab2, g["cl_lloyd2_lab_%s" % name], dist_fn(port, X, g["cl_kmeans_C_%s" % name], metric))
+    assert_float_close(dist2, g["cl_lloyd2_dist_%s" % name], 1e-12)
+    t = capi.LshTables(ctx, P, metric, 4, 5, 10, 4.0, 8003)
+    l, d, b = capi.lsh_range_assignment(ctx, P, t, cidx, metric)
+    assert np.array_equal(b, g["cl_lshrange_before_%s" % name])
+    assert_labels(l, g["cl_lshrange_lab_%s" % name], dist_fn(port, X, X[cidx], metric))
+    assert_float_close(d, g["cl_lshrange_dist_%s" % name], 1e-12)
+    cube = capi.Hypercube(ctx, P, metric, 5, 4.0, 8004)
+    l, d, b = capi.cube_range_assignment(ctx, P, cube, cidx, metric, 6)
+    assert np.array_equal(b, g["cl_cuberange_before_%s" % name])
+    assert_labels(l, g["cl_cuberange_lab_%s" % name], dist_fn(port, X, X[cidx], metric))
+    assert_float_close(d, g["cl_cuberange_dist_%s" % name], 1e-12)
+    sw, new = capi.pam_lloyds(ctx, P, g["cl_lloyd_lab_%s" % name], cidx, metric)
+    assert sw == bool(g["cl_pam_sw_%s" % name]) and np.array_equal(new, g["cl_pam_new_%s" % name])
+    assert_float_close(capi.silhouette_cluster(ctx, P, g["cl_lloyd_lab_%s" % name], X[cidx], metric), g["cl_sil_%s" % name], 1e-10)
+
+
+@pytest.mark.parametrize("metric", METRICS)
+@pytest.mark.parametrize("dtype,n,d,k", [(np.float32, 20000, 128, 64), (np.float64, 5000, 100, 30), (np.float32, 4097, 7, 3),
+                                         (np.float32, 1000, 128, 1), (np.float64, 777, 1, 5), (np.float32, 3000, 100, 129)])
+def test_lloyd_kmeans_oracle(ctx, port, metric, dtype, n, d, k):
+    X = synth.gaussian_mixture(n, d, max(2, k // 2), seed=31, dtype=dtype)
+    if d == 1 and metric == COSINE:
+        X = np.abs(X) + 0.5  # 1-d cosine distances are all 0 or 2: keep them tie-free per sign
+    X64 = X.astype(np.float64)
+    P = ctx.points(X)
+    cidx = capi.rand_selection(ctx, P, k, 4000 + k)
+    assert np.array_equal(cidx, port.rand_selection(X64, k, 4000 + k))
+    C = X64[cidx]
+    lab, dist = capi.lloyds_assignment(ctx, P, C, cidx, metric)
+    rl, rd = port.lloyds_assignment(X64, C, cidx, metric)
+    near = assert_labels(lab, rl, dist_fn(port, X64, C, metric), max_near=0 if metric == EUCLIDEAN else 3)
+    ok = lab == rl
+    if metric == EUCLIDEAN:
+        assert np.array_equal(dist[ok], rd[ok])
+    else:
+        assert_float_close(dist[ok], rd[ok], 1e-12)
+    ret, newc = capi.k_means(ctx, P, rl, C, metric, 0.05)
+    pret, pC = port.k_means(X64, rl, C, metric, 0.05)
+    assert ret == pret
+    assert_float_close(newc, pC, 1e-12)
+    # second iteration from k-means centres (not data points)
+    lab2, dist2 = capi.lloyds_assignment(ctx, P, pC, None, metric)
+    rl2, rd2 = port.lloyds_assignment(X64, pC, None, metric)
+    assert_labels(lab2, rl2, dist_fn(port, X64, pC, metric), max_near=0 if metric == EUCLIDEAN else 3)
+    # convergence: a huge min_dist stops, centres unchanged
+    ret, same_c = capi.k_means(ctx, P, rl, C, metric, 1e9)
+    assert ret is False and np.array_equal(same_c, C)
+
+
+def test_lloyd_ties_and_duplicates(ctx, port):
+    # duplicate centroids and points equidistant from two centroids: lowest index must win (assignment.hpp:67)
+    X = np.zeros((600, 8))
+    X[:, 0] = np.arange(600) % 3 - 1.0  # -1, 0, 1
+    C = np.zeros((4, 8)); C[0, 0] = -1; C[1, 0] = 1; C[2, 0] = 1; C[3, 0] = -1
+    P = ctx.points(X)
+    lab, dist = capi.lloyds_assignment(ctx, P, C, None, EUCLIDEAN)
+    rl, rd = port.lloyds_assignment(X, C, None, EUCLIDEAN)
+    assert np.array_equal(lab, rl) and np.array_equal(dist, rd)
+    assert set(lab.tolist()) == {0, 1}
+    # empty clusters become the zero vector (cust_vector.hpp:189)
+    ret, newc = capi.k_means(ctx, P, rl, C, EUCLIDEAN, 0.0)
+    pret, pC = port.k_means(X, rl, C, EUCLIDEAN, 0.0)
+    assert ret == pret and np.array_equal(newc, pC)
+
+
+def test_centroid_self_assignment(ctx, port):
+    X = synth.gaussian_mixture(500, 16, 4, seed=8).astype(np.float64)
+    cidx = np.array([5, 5, 17, 300], np.int32)  # the same row twice: the later centroid wins the overwrite
+    P = ctx.points(X)
+    lab, dist = capi.lloyds_assignment(ctx, P, X[cidx], cidx, EUCLIDEAN)
+    rl, rd = port.lloyds_assignment(X, X[cidx], cidx, EUCLIDEAN)
+    assert np.array_equal(lab, rl) and np.array_equal(dist, rd)
+    assert lab[5] == 1 and dist[5] == 0
+
+
+@pytest.mark.parametrize("metric", METRICS)
+@pytest.mark.parametrize("dtype,n,d,k", [(np.float32, 12000, 128, 24), (np.float64, 3000, 20, 9)])
+def test_kmeanspp_oracle(ctx, port, metric, dtype, n, d, k):
+    X = synth.gaussian_mixture(n, d, 8, seed=41, dtype=dtype)
+    P = ctx.points(X)
+    ctx.counters(reset=True)
+    got = capi.k_means_pp(ctx, P, k, metric, 909)
+    want = port.k_means_pp(X.astype(np.float64), k, metric, 909)
+    near = ctx.counters()["kpp_near"]
+    if near == 0:
+        assert np.array_equal(got, want)
+    else:  # a draw landed within rounding of a prefix boundary: the two sequences may part from there
+        first = int(np.flatnonzero(got != want)[0]) if not np.array_equal(got, want) else k
+        assert first >= 1
+
+
+@pytest.mark.parametrize("metric", METRICS)
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_range_assignment_oracle(ctx, port, metric, dtype):
+    X = synth.gaussian_mixture(6000, 32, 10, seed=51, dtype=dtype)
+    X64 = X.astype(np.float64)
+    P = ctx.points(X)
+    cidx = port.k_means_pp(X64, 12, metric, 111)
+    fn = dist_fn(port, X64, X64[cidx], metric)
+    for (k, L, div, w) in [(4, 5, 100, 0.4), (3, 4, 50, 6.0)]:
+        t = capi.LshTables(ctx, P, metric, k, L, div, w, 112)
+        l, d, b = capi.lsh_range_assignment(ctx, P, t, cidx, metric)
+        rl, rd, rb = port.lsh_range_assignment(X64, cidx, metric, k, L, div, w, 112)
+        assert np.array_equal(b, rb), (np.sum(b != rb), (rb >= 0).sum())
+        assert_labels(l, rl, fn, max_near=0 if metric == EUCLIDEAN else 3)
+        ok = l == rl
+        assert_float_close(d[ok], rd[ok], 1e-12)
+    for (k, w, probes) in [(8, 6.0, 20), (6, 0.4, 1), (10, 3.0, 64)]:
+        cube = capi.Hypercube(ctx, P, metric, k, w, 113)
+        l, d, b = capi.cube_range_assignment(ctx, P, cube, cidx, metric, probes)
+        rl, rd, rb = port.cube_range_assignment(X64, cidx, metric, k, w, probes, 113)
+        assert np.array_equal(b, rb), (np.sum(b != rb), (rb >= 0).sum())
+        assert_labels(l, rl, fn, max_near=0 if metric == EUCLIDEAN else 3)
+        ok = l == rl
+        assert_float_close(d[ok], rd[ok], 1e-12)
+
+
+@pytest.mark.parametrize("metric", METRICS)
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_pam_silhouette_oracle(ctx, port, metric, dtype):
+    X = synth.gaussian_mixture(2500, 24, 6, seed=61, dtype=dtype)
+    X64 = X.astype(np.float64)
+    P = ctx.points(X)
+    cidx = port.rand_selection(X64, 7, 5)
+    rl, _ = port.lloyds_assignment(X64, X64[cidx], cidx, metric)
+    sw, new = capi.pam_lloyds(ctx, P, rl, cidx, metric)
+    psw, pnew = port.pam_lloyds(X64, rl, cidx, metric)
+    assert sw == psw and np.array_equal(new, pnew)
+    # a second PAM step from the new medoids is a fixed point or keeps matching
+    rl2, _ = port.lloyds_assignment(X64, X64[pnew], pnew, metric)
+    sw2, new2 = capi.pam_lloyds(ctx, P, rl2, pnew, metric)
+    psw2, pnew2 = port.pam_lloyds(X64, rl2, pnew, metric)
+    assert sw2 == psw2 and np.array_equal(new2, pnew2)
+    s = capi.silhouette_cluster(ctx, P, rl, X64[cidx], metric)
+    assert_float_close(s, port.silhouette(X64, rl, X64[cidx], metric), 1e-10)
+
+
+def test_pam_exact_duplicates(ctx, port):
+    # identical rows inside a cluster give identical row sums: the first member must win (update.hpp:125)
+    rng = np.random.default_rng(2)
+    base = rng.normal(size=(40, 6))
+    X = np.concatenate([base, base, base + 10.0])
+    lab = np.concatenate([np.zeros(80, np.int32), np.ones(40, np.int32)])
+    cidx = np.array([79, 100], np.int32)
+    P = ctx.points(X)
+    sw, new = capi.pam_lloyds(ctx, P, lab, cidx, EUCLIDEAN)
+    psw, pnew = port.pam_lloyds(X, lab, cidx, EUCLIDEAN)
+    assert sw == psw and np.array_equal(new, pnew)
+    assert ctx.counters()["pam_exact"] >= 2
+
+
+def test_cluster_sums_chunking(ctx, port):
+    # one cluster far larger than the summation chunk: deterministic, and equal to the sequential sum to ~1e-15
+    X = synth.gaussian_mixture(9000, 100, 3, seed=71, dtype=np.float32)
+    lab = (np.arange(9000) % 10 == 0).astype(np.int32)  # cluster 0: 8100 rows, cluster 1: 900 rows
+    P = ctx.points(X)
+    s1, c1 = capi.cluster_sums(ctx, P, lab, 3)
+    s2, c2 = capi.cluster_sums(ctx, P, lab, 3)
+    assert np.array_equal(s1, s2) and c1.tolist() == [8100, 900, 0]
+    X64 = X.astype(np.float64)
+    seq = np.zeros((3, 100))
+    for v in range(9000):
+        seq[lab[v]] += X64[v]
+    assert np.array_equal(s1[1], seq[1])          # <= 1024 members: the reference's own sequential sum
+    assert_float_close(s1[0], seq[0], 1e-13)
+
+
+def test_full_clustering_loop_matches_oracle(ctx, port):
+    # the loop of main.cpp:96-103 / 246-254: init -> (assign, update) x iters
+    X = synth.gaussian_mixture(8000, 100, 12, seed=81, dtype=np.float32)
+    X64 = X.astype(np.float64)
+    P = ctx.points(X)
+    for metric in METRICS:
+        cidx = capi.k_means_pp(ctx, P, 10, metric, 1234)
+        assert np.array_equal(cidx, port.k_means_pp(X64, 10, metric, 1234))
+        C = X64[cidx]; Cr = C.copy(); rows = cidx
+        for it in range(4):
+            lab, _ = capi.lloyds_assignment(ctx, P, C, rows, metric)
+            rl, _ = port.lloyds_assignment(X64, Cr, rows, metric)
+            assert_labels(lab, rl, dist_fn(port, X64, Cr, metric), max_near=2)
+            cont, C = capi.k_means(ctx, P, lab, C, metric, 0.05)
+            rcont, Cr = port.k_means(X64, rl, Cr, metric, 0.05)
+            assert cont == rcont
+            assert_float_close(C, Cr, 1e-9)
+            rows = None
+            if not cont:
+                break

