@@ -7,6 +7,7 @@ Nothing in this module imports or calls oracle/.
 """
 import ctypes
 import os
+import weakref
 
 import numpy as np
 
@@ -83,12 +84,18 @@ class Context:
     """One GPU + one stream (crx_ctx).  stream: a raw cudaStream_t (int) or None for an own stream."""
 
     def __init__(self, device=0, stream=None):
+        """stream=None: the context creates its own stream.  stream=0 (torch's default stream) selects the
+        legacy default stream (cudaStreamLegacy, handle 0x1); any other int is a cudaStream_t."""
         self.h = ctypes.c_void_p()
-        _check(lib().crx_ctx_create(int(device), ctypes.c_void_p(stream) if stream else None, ctypes.byref(self.h)))
+        sp = None if stream is None else ctypes.c_void_p(stream if stream != 0 else 1)
+        _check(lib().crx_ctx_create(int(device), sp, ctypes.byref(self.h)))
         self.device = device
+        self._children = weakref.WeakSet()  # handles that must be destroyed before the context
 
     def close(self):
         if self.h:
+            for ch in list(self._children):
+                ch.close()
             lib().crx_ctx_destroy(self.h)
             self.h = ctypes.c_void_p()
 
@@ -157,6 +164,7 @@ class Points:
         p, mem = _ptr(X)
         _check(lib().crx_points_create(ctx.h, p, dt, ctypes.c_int64(n), int(d), mem, ctypes.byref(self.h)))
         self.n, self.d = int(n), int(d)
+        ctx._children.add(self)
         if unknown is not None:
             self.set_ratings(unknown, known_mean)
 
@@ -197,6 +205,7 @@ class LshTables:
         self.h = ctypes.c_void_p()
         _check(lib().crx_create_LSH_hashtables(ctx.h, input_vectors.h, self.metric, k, L, int(lsh_bucket_div),
                                                ctypes.c_double(euclidean_h_w), ctypes.c_uint64(seed), ctypes.byref(self.h)))
+        ctx._children.add(self)
 
     def close(self):
         if self.h:
@@ -246,6 +255,7 @@ class Hypercube:
         self.h = ctypes.c_void_p()
         _check(lib().crx_create_hypercube(ctx.h, input_vectors.h, METRICS[metric_type], k, ctypes.c_double(euclidean_h_w),
                                           ctypes.c_uint64(seed), ctypes.byref(self.h)))
+        ctx._children.add(self)
 
     def close(self):
         if self.h:

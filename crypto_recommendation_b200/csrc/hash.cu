@@ -3,6 +3,7 @@
 //   K2 phi / g combination and bucket index, K3 table build (stable radix sort + offsets),
 //   hypercube vertex map with the order-dependent f(h) draws reproduced on the host.
 #include <algorithm>
+#include <climits>
 #include <cub/cub.cuh>
 
 #include "tables.cuh"
@@ -26,6 +27,12 @@ __device__ __forceinline__ void load4(const double* p, double o[4]) {
     o[0] = a.x; o[1] = a.y; o[2] = b.x; o[3] = b.y;
 }
 
+// int(floor(long double)) on x86-64 is an x87 FISTP: out-of-range values give the "integer indefinite"
+// 0x80000000 for either sign (euclidean_h_gen.hpp:81 relies on it for |h| >= 2^31); a CUDA cast saturates.
+__device__ __forceinline__ int f2i_x87(double f) {
+    return (f >= -2147483648.0 && f < 2147483648.0) ? (int)f : INT_MIN;
+}
+
 template <typename T>
 __device__ int cosine_bit_dd(const T* x, const double* r, int D) {
     double hi, lo;
@@ -42,7 +49,7 @@ __device__ int euclid_h_dd(const T* x, const double* v, int D, double t, double 
     double rem = __dadd_rn(__fma_rn(-w, f, s), e);  // (s + e) - w f
     if (rem < 0.0) f -= 1.0;
     else if (rem >= w) f += 1.0;
-    return (int)f;
+    return f2i_x87(f);
 }
 
 #define PHI_M 2147483647  // int(pow(2,32)-5) as GCC folds it (euclidean_phi_gen.hpp:70)
@@ -108,13 +115,13 @@ hash_rows_kernel(const T* __restrict__ x, int ld, const double* __restrict__ sqn
                         double s = a0[h] + t, y = s / dw, f = floor(y), fr = y - f;
                         double Ey = (E0 + fabs(s) * 2.3e-16) / dw + fabs(y) * 2.3e-16;
                         if (fmin(fr, 1.0 - fr) <= Ey) { r0 = euclid_h_dd(row0, sproj + h * ldp, D, t, dw); if (v0) atomicAdd(&counters[CRX_CNT_HASH_DD], 1ull); }
-                        else r0 = (int)f;
+                        else r0 = f2i_x87(f);
                     }
                     {
                         double s = a1[h] + t, y = s / dw, f = floor(y), fr = y - f;
                         double Ey = (E1 + fabs(s) * 2.3e-16) / dw + fabs(y) * 2.3e-16;
                         if (fmin(fr, 1.0 - fr) <= Ey) { r1 = euclid_h_dd(row1, sproj + h * ldp, D, t, dw); if (v1) atomicAdd(&counters[CRX_CNT_HASH_DD], 1ull); }
-                        else r1 = (int)f;
+                        else r1 = f2i_x87(f);
                     }
                     if (hvals) {
                         if (v0) hvals[((size_t)l * N + i0) * k + h] = r0;

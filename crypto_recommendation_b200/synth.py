@@ -67,22 +67,25 @@ def rating_users(n, d, seed, min_known=2, max_known=9, dtype=np.float64):
     return X.astype(dtype), (~known).astype(np.uint8), mean
 
 
-def rating_users_fast(n, d, seed, min_known=2, max_known=9, dtype=np.float32):
-    """Vectorised variant of rating_users for bench-scale n (1M): same distribution family,
-    different stream (so not bit-identical to rating_users)."""
-    g = _rng(seed, 4)
-    nk = g.integers(min_known, max_known + 1, size=n)
-    order = np.argsort(g.random((n, d)), axis=1)
-    rank = np.empty_like(order)
-    np.put_along_axis(rank, order, np.arange(d)[None, :].repeat(n, 0), axis=1)
-    known = rank < nk[:, None]
-    t = g.normal(0.0, 2.0, size=(n, d, 2))
-    s = t / np.sqrt(t * t + 15.0)
-    r = np.where(s > 0, s, 0.0).sum(axis=2)
-    X = np.where(known, r, 0.0)
-    keep = (X != 0).any(axis=1)
-    X, known = X[keep], known[keep]
-    X = X.astype(dtype).astype(np.float64)
-    mean = ((X * known).sum(axis=1) / known.sum(axis=1)).astype(dtype).astype(np.float64)
-    X = np.where(known, X, mean[:, None])
-    return X.astype(dtype), (~known).astype(np.uint8), mean
+def rating_users_fast(n, d, seed, min_known=2, max_known=9, dtype=np.float32, chunk=100_000):
+    """Vectorised variant of rating_users for bench-scale n (1M users): same distribution family
+    (each coin known with probability nk/d, nk ~ U{min_known..max_known}; a known coin's rating is the
+    sum of the positive scores of two tweets), generated in chunks.  Not bit-identical to rating_users."""
+    Xs, Us, Ms = [], [], []
+    for c0 in range(0, n, chunk):
+        m = min(chunk, n - c0)
+        g = _rng(seed, 4000 + c0 // chunk)
+        nk = g.integers(min_known, max_known + 1, size=m)
+        known = g.random((m, d), dtype=np.float32) < (nk[:, None] / np.float32(d))
+        t = g.standard_normal((m, d, 2), dtype=np.float32) * np.float32(2.0)
+        s = t / np.sqrt(t * t + np.float32(15.0))
+        r = np.where(s > 0, s, np.float32(0)).sum(axis=2)
+        X = np.where(known, r, np.float32(0)).astype(np.float32)
+        keep = (X != 0).any(axis=1)
+        X, known = X[keep], known[keep]
+        X64 = X.astype(np.float64)
+        mean = ((X64 * known).sum(axis=1) / known.sum(axis=1)).astype(np.float32)
+        X = np.where(known, X, mean[:, None]).astype(np.float32)
+        Xs.append(X); Us.append((~known).astype(np.uint8)); Ms.append(mean.astype(np.float64))
+    X = np.ascontiguousarray(np.concatenate(Xs)).astype(dtype)
+    return X, np.ascontiguousarray(np.concatenate(Us)), np.ascontiguousarray(np.concatenate(Ms))

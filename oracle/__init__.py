@@ -56,6 +56,7 @@ class Oracle:
             getattr(L, n).restype = ctypes.c_double
         L.orc_lsh_candidates.restype = ctypes.c_int64
         L.orc_cube_candidates.restype = ctypes.c_int64
+        L.orc_rec_handle_create.restype = ctypes.c_void_p
         self.kind = L.orc_kind().decode()
 
     # ---- KATs
@@ -195,6 +196,29 @@ class Oracle:
         self.lib.orc_recommend_cluster(_p(X), _p(unknown), _p(mean), _p(labels), ctypes.c_int64(N), D, K, _p(Xq),
                                        _p(unknown_q), _p(mean_q), _p(qlabels), ctypes.c_int64(Nq), Nrec, _p(recs))
         return recs
+
+
+class RecHandle:
+    """Tables built once (rec A of main.cpp:155), then slices of the per-user loop (main.cpp:159-170);
+    query() releases the GIL, so several threads can share one handle (cosine tables are read-only)."""
+
+    def __init__(self, oracle, X, unknown, mean, metric, k, L, div, w, seed):
+        self.o = oracle
+        self.X = _f64(X); self.unknown = _u8(unknown); self.mean = _f64(mean)  # kept alive for the port
+        N, D = self.X.shape
+        self.h = ctypes.c_void_p(oracle.lib.orc_rec_handle_create(_p(self.X), _p(self.unknown), _p(self.mean), ctypes.c_int64(N), D,
+                                                                  metric, k, L, div, ctypes.c_double(w), ctypes.c_uint64(seed)))
+
+    def query(self, q_begin, q_end, P, Nrec):
+        nq = q_end - q_begin
+        recs = np.zeros((nq, Nrec), np.int32); ncand = np.zeros(nq, np.int32)
+        self.o.lib.orc_rec_handle_query(self.h, ctypes.c_int64(q_begin), ctypes.c_int64(q_end), P, Nrec, _p(recs), _p(ncand))
+        return recs, ncand
+
+    def close(self):
+        if self.h:
+            self.o.lib.orc_rec_handle_destroy(self.h)
+            self.h = None
 
 
 _cache = {}

@@ -734,4 +734,44 @@ int orc_recommend_cluster(const double* X, const uint8_t* unknown, const double*
     return 0;
 }
 
+struct PortRecHandle {
+    Lsh lsh;
+    const double* X; const uint8_t* unknown; const double* mean;
+    std::vector<double> nrm;
+    int D;
+};
+
+void* orc_rec_handle_create(const double* X, const uint8_t* unknown, const double* mean, int64_t N, int D, int metric,
+                            int k, int L, int div, double w, uint64_t seed) {
+    PortRecHandle* h = new PortRecHandle();
+    h->X = X; h->unknown = unknown; h->mean = mean; h->D = D;  /* caller keeps the arrays alive */
+    h->lsh.build(X, N, D, metric, k, L, div, w, seed);
+    h->nrm.resize(N);
+    for (int64_t i = 0; i < N; i++) h->nrm[i] = sqnorm(X + i * D, D);
+    return h;
+}
+
+int orc_rec_handle_query(void* hv, int64_t q_begin, int64_t q_end, int P, int Nrec, int32_t* recs, int32_t* ncand) {
+    PortRecHandle* h = (PortRecHandle*)hv;
+    int D = h->D;
+    std::vector<int32_t> cand;
+    std::vector<double> sims;
+    for (int64_t u = q_begin; u < q_end; u++) {
+        const double* q = h->X + u * D;
+        h->lsh.candidates(q, 1, cand);
+        ncand[u - q_begin] = (int32_t)cand.size();
+        for (int j = 0; j < Nrec; j++) recs[(u - q_begin) * Nrec + j] = -1;
+        if (cand.empty()) continue;
+        sims.resize(cand.size());
+        for (size_t i = 0; i < cand.size(); i++) sims[i] = cos_sim_n(h->X + (size_t)cand[i] * D, q, D, h->nrm[cand[i]], h->nrm[u]);
+        lomuto_desc(sims.data(), cand.data(), 0, (int)cand.size() - 1);
+        int keep = (int)std::min<size_t>(cand.size(), (size_t)P);
+        top_n_from_neighbours(h->X, h->mean, D, cand.data(), sims.data(), keep, h->unknown + u * D, h->mean[u], Nrec,
+                              recs + (u - q_begin) * Nrec);
+    }
+    return 0;
+}
+
+void orc_rec_handle_destroy(void* hv) { delete (PortRecHandle*)hv; }
+
 } /* extern "C" */

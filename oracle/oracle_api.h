@@ -90,6 +90,14 @@ int orc_recommend_cluster(const double* X, const uint8_t* unknown, const double*
                           const double* Xq, const uint8_t* unknown_q, const double* mean_q, const int32_t* qlabels,
                           int64_t Nq, int Nrec, int32_t* recs);
 
+/* ---- persistent handles for the timed CPU baseline (bench.py): tables built once, then slices of the
+ * rec-A query loop (main.cpp:159-170) and of lloyds_assignment run on them, possibly from several threads
+ * (read-only after the build for cosine tables). ---- */
+void* orc_rec_handle_create(const double* X, const uint8_t* unknown, const double* mean, int64_t N, int D, int metric,
+                            int k, int L, int lsh_bucket_div, double w, uint64_t seed);
+int orc_rec_handle_query(void* h, int64_t q_begin, int64_t q_end, int P, int Nrec, int32_t* recs, int32_t* ncand);
+void orc_rec_handle_destroy(void* h);
+
 #ifdef __cplusplus
 }
 #endif

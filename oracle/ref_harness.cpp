@@ -392,4 +392,40 @@ int orc_recommend_cluster(const double* X, const uint8_t* unknown, const double*
     return 0;
 }
 
+struct RefRecHandle {
+    vector<CV> base;
+    vector<CustHashtable<double>*> tabs;
+};
+
+void* orc_rec_handle_create(const double* X, const uint8_t* unknown, const double* mean, int64_t N, int D, int metric,
+                            int k, int L, int div, double w, uint64_t seed) {
+    g_seed = seed;
+    RefRecHandle* h = new RefRecHandle();
+    h->base = make_users(X, unknown, mean, N, D);
+    h->tabs = create_LSH_hashtables<double>(h->base, metric_name(metric), k, L, div, w);
+    return h;
+}
+
+int orc_rec_handle_query(void* hv, int64_t q_begin, int64_t q_end, int P, int Nrec, int32_t* recs, int32_t* ncand) {
+    RefRecHandle* h = (RefRecHandle*)hv;
+    for (int64_t u = q_begin; u < q_end; u++) {
+        CV& user = h->base[u];
+        vector<CV*> neighbors = get_LSH_filtered_combined_buckets(h->tabs, &user);
+        ncand[u - q_begin] = (int32_t)neighbors.size();
+        for (int j = 0; j < Nrec; j++) recs[(u - q_begin) * Nrec + j] = -1;
+        if (!neighbors.empty()) {
+            vector<double> sims = get_P_closest(neighbors, user, P);
+            vector<int> r = get_top_N_recom(neighbors, user, Nrec, sims);
+            for (int j = 0; j < Nrec; j++) recs[(u - q_begin) * Nrec + j] = r[j];
+        }
+    }
+    return 0;
+}
+
+void orc_rec_handle_destroy(void* hv) {
+    RefRecHandle* h = (RefRecHandle*)hv;
+    for (auto t : h->tabs) delete t;
+    delete h;
+}
+
 } /* extern "C" */
