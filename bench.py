@@ -239,16 +239,24 @@ def run_crx(args):
         return cdist.max_over_ranks(ms) / steps, launches, clocks
 
     ms_step, launches, clocks = timed(step_resident, args.steps, max(args.min_warmup, args.warmup), sample_clocks=True, profile=True)
-    scan_ms, scan_launches = ctx.kernel_time("topp_scan")
+    scan_name = "tc_topp_scan" if ctx.kernel_time("tc_topp_scan")[1] > 0 else "topp_scan"
+    scan_ms, scan_launches = ctx.kernel_time(scan_name)
+    kernel_ms = {k: round(ctx.kernel_time(k)[0] / args.steps, 3) for k in (
+        "tc_topp_scan", "topp_scan", "rec_finalize", "hash_rows", "tc_prep", "pack_codes", "subset_hist", "subset_count",
+        "iota", "bucket_offsets", "fill_lists", "sq_sizes")}
     ncand_total = float(out_dev["ncand"].to(torch.float64).sum().item())
     counters = ctx.counters()
     value = world * n / (ms_step / 1e3)
     flops_per_launch = 2.0 * d * ncand_total * args.steps / max(1, scan_launches)
     achieved_tf = flops_per_launch / (scan_ms / max(1, scan_launches) * 1e-3) / 1e12 if scan_ms > 0 else 0.0
-    roofline = {"kernel": "topp_scan_kernel (masked cosine-similarity scan + per-query top-32 list)", "bound": "tensor",
+    tc = scan_name == "tc_topp_scan"
+    # tensor path: 3 fp16 products (hi*hi, lo*hi, hi*lo) over the D padded to 128 columns => 3*128/D tensor flops per algorithmic flop
+    roofline = {"kernel": ("tc_scan_kernel<TOPP> (tcgen05 split-fp16 cosine scan, per-row top-64 in the epilogue)" if tc else
+                           "topp_scan_kernel (FP64 SIMT masked cosine scan + per-query top-32 list)"), "bound": "tensor",
                 "achieved": achieved_tf, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s", "frac": achieved_tf / peaks["bf16_tflops"],
                 "traffic": None, "peak_source": peaks["which"] + " bf16 dense GEMM (burst)",
-                "pipe": "FP64 SIMT FMA in this round (no tensor-core path yet); algorithmic flops = 2*D*sum|cand(u)|",
+                "pipe": ("tcgen05.mma kind::f16, fp32 accumulate in TMEM; executed tensor flops = %.2fx algorithmic (3 split products, D padded to 128)" % (3 * 128.0 / d)) if tc else "FP64 SIMT FMA",
+                "algorithmic_flops": "2*D*sum|cand(u)|", "kernel_ms_all": kernel_ms,
                 "kernel_ms_per_step": scan_ms / args.steps, "share_of_step": scan_ms / args.steps / ms_step}
 
     e2e_ms, _, _ = timed(step_e2e, max(1, min(2, args.steps)), 1)

@@ -9,6 +9,7 @@
 #include "pair_tile.cuh"
 #include "rowwalk.cuh"
 #include "tables.cuh"
+#include "tc_scan.cuh"
 
 constexpr int LIST = 32;   // per-query candidate list length (one entry per lane)
 constexpr int MAXL = 16;
@@ -169,18 +170,22 @@ topp_scan_kernel(const TQ* __restrict__ xq, int ldq, const double* __restrict__ 
 }
 
 // ------------------------------------------------------------------------------------------------
-// K10: refine + predict + top-N.  One warp per query.
+// K10: refine + predict + top-N.  One warp per query.  LISTN = 32 (FP64 scan, double scores) or
+// 64 (tensor-core filter, float scores scaled by `approx_scale`, filter error `approx_eps`).
 // ------------------------------------------------------------------------------------------------
-template <typename TQ, typename TB>
+template <typename TQ, typename TB, int LISTN, typename TS>
 __global__ void __launch_bounds__(256)
 rec_finalize_kernel(const TQ* __restrict__ xq, int ldq, const double* __restrict__ sqn_q, const uint8_t* __restrict__ unk_q,
                     const double* __restrict__ mean_q, const TB* __restrict__ xb, int ldb, const double* __restrict__ sqn_b,
                     const double* __restrict__ mean_b, int D, int64_t q_begin, int64_t nq, int P, int Nrec,
-                    const double* __restrict__ list_s, const int32_t* __restrict__ list_i, const int32_t* __restrict__ ncand,
-                    int32_t* __restrict__ recs, int32_t* __restrict__ nbr_rows, double* __restrict__ nbr_sims,
-                    unsigned long long* counters) {
-    __shared__ int s_idx[8][LIST];
-    __shared__ double s_sim[8][LIST];
+                    const TS* __restrict__ list_s, const int32_t* __restrict__ list_i, const int32_t* __restrict__ ncand,
+                    double approx_scale, double approx_eps, int32_t* __restrict__ recs, int32_t* __restrict__ nbr_rows,
+                    double* __restrict__ nbr_sims, unsigned long long* counters) {
+    constexpr int EPL = LISTN / 32;  // list entries per lane
+    __shared__ int a_idx[8][LISTN];
+    __shared__ double a_sim[8][LISTN];
+    __shared__ int s_idx[8][32];
+    __shared__ double s_sim[8][32];
     __shared__ double s_pred[8][128];
     __shared__ int s_coin[8][128];
     int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -188,31 +193,54 @@ rec_finalize_kernel(const TQ* __restrict__ xq, int ldq, const double* __restrict
     if (qrel >= nq) return;
     int64_t qrow = q_begin + qrel;
     const TQ* q = xq + qrow * ldq;
-    int idx = list_i[qrel * LIST + lane];
-    double approx = list_s[qrel * LIST + lane];
-    double sim = -INFINITY;
-    if (idx >= 0) sim = cos_sim_exact(xb + (size_t)idx * ldb, q, D, sqn_b[idx], sqn_q[qrow]);  // crypto_rec.hpp:220
-    unsigned validmask = __ballot_sync(0xffffffffu, idx >= 0);
-    int nvalid = __popc(validmask);
-    int rank = 0;
-    for (int t = 0; t < 32; t++) {
-        double os = __shfl_sync(0xffffffffu, sim, t);
-        int oi = __shfl_sync(0xffffffffu, idx, t);
-        if (oi >= 0 && (os > sim || (os == sim && oi < idx))) rank++;
+    // every 32-slot group of the list is an independent "best 32 of its share of the columns" list
+    // (the FP64 scan has one, the tensor-core filter one per column half): a candidate outside the lists
+    // scores at most max over FULL groups of (smallest approximate score of the group)
+    double floor_s = -INFINITY;
+    int nvalid = 0;
+#pragma unroll
+    for (int e = 0; e < EPL; e++) {
+        int slot = e * 32 + lane;
+        int idx = list_i[qrel * LISTN + slot];
+        double sim = -INFINITY, ap = INFINITY;
+        if (idx >= 0) {
+            sim = cos_sim_exact(xb + (size_t)idx * ldb, q, D, sqn_b[idx], sqn_q[qrow]);  // crypto_rec.hpp:220
+            ap = (double)list_s[qrel * LISTN + slot];
+        }
+        a_idx[warp][slot] = idx;
+        a_sim[warp][slot] = sim;
+        int gcount = __popc(__ballot_sync(0xffffffffu, idx >= 0));
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) ap = fmin(ap, __shfl_xor_sync(0xffffffffu, ap, off));
+        nvalid += gcount;
+        if (gcount == 32) floor_s = fmax(floor_s, ap);
     }
-    if (idx < 0) rank = 64;
+    __syncwarp();
     int keep = min(P, nvalid);
-    if (rank < LIST) { s_idx[warp][rank] = idx; s_sim[warp][rank] = sim; }
+    // descending similarity, ties by ascending row
+#pragma unroll
+    for (int e = 0; e < EPL; e++) {
+        int slot = e * 32 + lane;
+        int idx = a_idx[warp][slot];
+        double sim = a_sim[warp][slot];
+        if (idx >= 0) {
+            int rank = 0;
+            for (int t = 0; t < LISTN; t++) {
+                int oi = a_idx[warp][t];
+                double os = a_sim[warp][t];
+                if (oi >= 0 && (os > sim || (os == sim && oi < idx))) rank++;
+            }
+            if (rank < 32) { s_idx[warp][rank] = idx; s_sim[warp][rank] = sim; }
+        }
+    }
     __syncwarp();
     int nc = ncand[qrel];
-    // certification: every candidate that is not in the list has an approximate similarity <= the
-    // smallest approximate one in it; the exact P-th best must clear that by more than the scan's error
-    if (nc > LIST && keep > 0) {
-        double amin = approx;
-#pragma unroll
-        for (int off = 16; off > 0; off >>= 1) amin = fmin(amin, __shfl_xor_sync(0xffffffffu, amin, off));
+    // certification: every candidate outside the list has an approximate similarity <= the smallest
+    // approximate one in it; the exact P-th best must clear that by more than the filter's error
+    if (floor_s > -INFINITY && keep > 0 && lane == 0) {
+        double floor_ = floor_s * approx_scale;
         double pth = s_sim[warp][keep - 1];
-        if (lane == 0 && !(pth > amin + 1e-12 * fmax(1.0, fabs(amin)))) atomicAdd(&counters[CRX_CNT_TOPP_RESCAN], 1ull);
+        if (!(pth > floor_ + approx_eps * fmax(1.0, fabs(floor_)))) atomicAdd(&counters[CRX_CNT_TOPP_RESCAN], 1ull);
     }
     if (nbr_rows) for (int j = lane; j < P; j += 32) nbr_rows[qrel * P + j] = j < keep ? s_idx[warp][j] : -1;
     if (nbr_sims) for (int j = lane; j < P; j += 32) nbr_sims[qrel * P + j] = j < keep ? s_sim[warp][j] : 0.0;
@@ -251,6 +279,47 @@ rec_finalize_kernel(const TQ* __restrict__ xq, int ldq, const double* __restrict
     if (lane == 0) lomuto_desc(s_pred[warp], s_coin[warp], nu);  // crypto_rec.hpp:320
     __syncwarp();
     for (int j = lane; j < Nrec; j += 32) recs[qrel * Nrec + j] = j < nu ? s_coin[warp][j] : 0;  // resize(N) pads with 0
+}
+
+// ------------------------------------------------------------------------------------------------
+// packed table codes and exact candidate counts for the tensor-core path.
+// code(row) = concatenation of the L k-bit bucket ids.  |union_l bucket_l(q)| by inclusion-exclusion over
+// the 2^L - 1 non-empty table subsets S: sum (-1)^(|S|+1) #{rows agreeing with q on every table of S};
+// the agreement counts are histograms over the sub-codes (sizes 2^(k|S|), (1+2^k)^L - 1 bins in total).
+// ------------------------------------------------------------------------------------------------
+__global__ void pack_codes_kernel(const int32_t* __restrict__ bucket, int64_t stride, int64_t n, int k, int L, uint32_t* __restrict__ code) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t c = 0;
+    for (int l = 0; l < L; l++) c |= (uint32_t)bucket[(size_t)l * stride + i] << (l * k);
+    code[i] = c;
+}
+__device__ __forceinline__ uint32_t subcode(uint32_t code, int S, int k, int L) {
+    uint32_t key = 0;
+    int pos = 0;
+    uint32_t fm = (1u << k) - 1u;
+    for (int l = 0; l < L; l++)
+        if ((S >> l) & 1) { key |= ((code >> (l * k)) & fm) << pos; pos += k; }
+    return key;
+}
+__global__ void subset_hist_kernel(const uint32_t* __restrict__ code, int64_t n, int k, int L, const int64_t* __restrict__ hoff,
+                                   int* __restrict__ hist) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t c = code[i];
+    for (int S = 1; S < (1 << L); S++) atomicAdd(&hist[hoff[S] + subcode(c, S, k, L)], 1);
+}
+__global__ void subset_count_kernel(const uint32_t* __restrict__ qcode, int64_t q_begin, int64_t nq, int k, int L,
+                                    const int64_t* __restrict__ hoff, const int* __restrict__ hist, int32_t* __restrict__ ncand) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nq) return;
+    uint32_t c = qcode[q_begin + i];
+    long long total = 0;
+    for (int S = 1; S < (1 << L); S++) {
+        int h = hist[hoff[S] + subcode(c, S, k, L)];
+        total += (__popc(S) & 1) ? h : -h;
+    }
+    ncand[i] = (int32_t)total;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -382,66 +451,111 @@ int crx_recommend_lsh(crx_ctx* c, const crx_lsh* t, const crx_points* queries, i
     }
     DevBuf<double> list_s;
     DevBuf<int32_t> list_i, nc;
-    CRX_TRY(list_s.alloc(c, (size_t)nq * LIST)); CRX_TRY(list_i.alloc(c, (size_t)nq * LIST)); CRX_TRY(nc.alloc(c, nq));
-    { CRX_KERNEL(c, "fill_lists"); fill_lists_kernel<<<crx_grid(nq * LIST, 256), 256, 0, c->stream>>>(list_s.p, list_i.p, nc.p, nq); }
-
-    // cost model: dense any-table scan (nq * N pairs) vs one pass per table (sum of squared group sizes,
-    // scaled to the query share)
-    DevBuf<double> cost;
-    CRX_TRY(cost.alloc(c, 1));
-    CRX_CUDA(cudaMemsetAsync(cost.p, 0, sizeof(double), c->stream));
-    for (int l = 0; l < L; l++) {
-        CRX_KERNEL(c, "sq_sizes");
-        sq_sizes_kernel<<<crx_grid(t->ngroups[l], 256), 256, 0, c->stream>>>(t->by_group[l].off, t->ngroups[l], cost.p);
-    }
-    double h_cost = 0;
-    CRX_CUDA(cudaMemcpyAsync(&h_cost, cost.p, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
-    CRX_CUDA(cudaStreamSynchronize(c->stream));
-    double table_cost = h_cost * ((double)nq / (double)N) + (double)L * 64.0 * (double)nq;
-    double dense_cost = (double)nq * (double)N;
-    bool dense = dense_cost <= table_cost;
-
-    ScanArgs a;
-    memset(&a, 0, sizeof(a));
-    a.L = L; a.nq = nq; a.nb = N; a.q_begin = q_begin;
-    for (int l = 0; l < L; l++) { a.qgid[l] = qgid_base + (size_t)l * qstride; a.cgid[l] = t->gid + (size_t)l * N; }
-    a.list_s = list_s.p; a.list_i = list_i.p; a.ncand = nc.p;
-    int ld = base->ld;
-    size_t smem = pt::smem_bytes(ld) + pt::BN * sizeof(double) + pt::BN * sizeof(int32_t) + (size_t)MAXL * (pt::BN + pt::BM) * sizeof(int32_t);
-    int grid = (int)((nq + pt::BM - 1) / pt::BM);
-    DevBuf<int32_t> qperm, qkeys, qsorted;
-    CRX_TRY(qperm.alloc(c, nq));
-    auto launch_scan = [&](const ScanArgs& args) -> int {
-        CRX_KERNEL(c, "topp_scan");
-#define LAUNCH_T(TQ, TB, xqp, xbp)                                                                                      \
-    do {                                                                                                                \
-        CRX_CUDA(cudaFuncSetAttribute(topp_scan_kernel<TQ, TB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-        topp_scan_kernel<TQ, TB><<<grid, pt::NT, smem, c->stream>>>(xqp, queries->ld, queries->sqn, xbp, base->ld, base->sqn, args); \
-    } while (0)
-        if (queries->x64 && base->x64) LAUNCH_T(double, double, queries->x64, base->x64);
-        else if (queries->x64) LAUNCH_T(double, float, queries->x64, base->x32);
-        else if (base->x64) LAUNCH_T(float, double, queries->x32, base->x64);
-        else LAUNCH_T(float, float, queries->x32, base->x32);
-#undef LAUNCH_T
+    DevBuf<float> tl_s;
+    DevBuf<int32_t> tl_i;
+    double tc_unscale = 1.0;
+    CRX_TRY(nc.alloc(c, nq));
+    // Tensor-core filter (tcgen05, tc_scan.cu): cosine tables whose L k-bit bucket ids pack into 32 bits and
+    // whose sub-code histograms stay small.  CRX_NO_TC=1 forces the FP64 scan (tests compare the two paths).
+    static const bool tc_off = getenv("CRX_NO_TC") != nullptr && getenv("CRX_NO_TC")[0] == '1';
+    const bool use_tc = !tc_off && t->metric == CRX_COSINE && t->k * L <= 32 && L <= 8 &&
+                        pow(1.0 + (double)(1 << t->k), (double)L) <= (double)(1 << 24);
+    if (use_tc) {
+        int k = t->k;
+        CRX_TRY(tl_s.alloc(c, (size_t)nq * TC_LIST)); CRX_TRY(tl_i.alloc(c, (size_t)nq * TC_LIST));
+        DevBuf<uint32_t> ccode, qcode_buf;
+        CRX_TRY(ccode.alloc(c, N));
+        { CRX_KERNEL(c, "pack_codes"); pack_codes_kernel<<<crx_grid(N, 256), 256, 0, c->stream>>>(t->bucket, N, N, k, L, ccode.p); }
+        const uint32_t* qcode = ccode.p;
+        if (!self) {
+            CRX_TRY(qcode_buf.alloc(c, queries->n));
+            { CRX_KERNEL(c, "pack_codes"); pack_codes_kernel<<<crx_grid(queries->n, 256), 256, 0, c->stream>>>(qgid_base, qstride, queries->n, k, L, qcode_buf.p); }
+            qcode = qcode_buf.p;
+        }
+        // exact |candidates| per query by inclusion-exclusion over table subsets
+        std::vector<int64_t> hoff((size_t)1 << L, 0);
+        int64_t bins = 0;
+        for (int S = 1; S < (1 << L); S++) { hoff[S] = bins; bins += (int64_t)1 << (k * __builtin_popcount(S)); }
+        DevBuf<int64_t> d_hoff;
+        DevBuf<int> hist;
+        CRX_TRY(d_hoff.alloc(c, hoff.size())); CRX_TRY(hist.alloc(c, bins));
+        CRX_CUDA(cudaMemcpyAsync(d_hoff.p, hoff.data(), hoff.size() * sizeof(int64_t), cudaMemcpyHostToDevice, c->stream));
+        CRX_CUDA(cudaMemsetAsync(hist.p, 0, bins * sizeof(int), c->stream));
+        { CRX_KERNEL(c, "subset_hist"); subset_hist_kernel<<<crx_grid(N, 256), 256, 0, c->stream>>>(ccode.p, N, k, L, d_hoff.p, hist.p); }
+        { CRX_KERNEL(c, "subset_count"); subset_count_kernel<<<crx_grid(nq, 256), 256, 0, c->stream>>>(qcode, q_begin, nq, k, L, d_hoff.p, hist.p, nc.p); }
         CRX_CUDA(cudaGetLastError());
-        return CRX_OK;
-    };
-    if (dense) {
-        { CRX_KERNEL(c, "iota"); iota_off_kernel<<<crx_grid(nq, 256), 256, 0, c->stream>>>(qperm.p, nq, (int32_t)q_begin); }
-        a.pass = -1; a.qperm = qperm.p; a.cperm = nullptr; a.csorted = nullptr; a.load_state = 0;
-        CRX_TRY(launch_scan(a));
+        // split-fp16 operands: unit rows times 2^10, so the accumulators hold 2^20 * cosine
+        TcOperand opB, opA;
+        int st = crx_tc_prepare(c, base, 0, 10.0, &opB);
+        if (st == CRX_OK && !self) st = crx_tc_prepare(c, queries, 0, 10.0, &opA);
+        if (st == CRX_OK) st = crx_tc_topp(c, self ? opB : opA, q_begin, nq, opB, qcode, ccode.p, k, L, tl_s.p, tl_i.p);
+        tc_unscale = ldexp(1.0, -20);
+        cudaStreamSynchronize(c->stream);
+        opB.free_all();
+        opA.free_all();
+        if (st != CRX_OK) return st;
     } else {
+        CRX_TRY(list_s.alloc(c, (size_t)nq * LIST)); CRX_TRY(list_i.alloc(c, (size_t)nq * LIST));
+        { CRX_KERNEL(c, "fill_lists"); fill_lists_kernel<<<crx_grid(nq * LIST, 256), 256, 0, c->stream>>>(list_s.p, list_i.p, nc.p, nq); }
+
+        // cost model: dense any-table scan (nq * N pairs) vs one pass per table (sum of squared group sizes,
+        // scaled to the query share)
+        DevBuf<double> cost;
+        CRX_TRY(cost.alloc(c, 1));
+        CRX_CUDA(cudaMemsetAsync(cost.p, 0, sizeof(double), c->stream));
         for (int l = 0; l < L; l++) {
-            // queries of the batch ordered by their group in table l
-            Segments qs;
-            int st = crx_build_segments(c, a.qgid[l] + q_begin, nq, std::max(1, t->ngroups[l]), &qs);
-            if (st != CRX_OK) { qs.free_all(); return st; }
-            { CRX_KERNEL(c, "add_off"); add_off_kernel<<<crx_grid(nq, 256), 256, 0, c->stream>>>(qs.perm, nq, (int32_t)q_begin); }
-            a.pass = l; a.qperm = qs.perm; a.cperm = t->by_group[l].perm; a.csorted = t->by_group[l].sorted; a.load_state = l > 0;
-            st = launch_scan(a);
-            CRX_CUDA(cudaStreamSynchronize(c->stream));
-            qs.free_all();
-            if (st != CRX_OK) return st;
+            CRX_KERNEL(c, "sq_sizes");
+            sq_sizes_kernel<<<crx_grid(t->ngroups[l], 256), 256, 0, c->stream>>>(t->by_group[l].off, t->ngroups[l], cost.p);
+        }
+        double h_cost = 0;
+        CRX_CUDA(cudaMemcpyAsync(&h_cost, cost.p, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        CRX_CUDA(cudaStreamSynchronize(c->stream));
+        double table_cost = h_cost * ((double)nq / (double)N) + (double)L * 64.0 * (double)nq;
+        double dense_cost = (double)nq * (double)N;
+        bool dense = dense_cost <= table_cost;
+
+        ScanArgs a;
+        memset(&a, 0, sizeof(a));
+        a.L = L; a.nq = nq; a.nb = N; a.q_begin = q_begin;
+        for (int l = 0; l < L; l++) { a.qgid[l] = qgid_base + (size_t)l * qstride; a.cgid[l] = t->gid + (size_t)l * N; }
+        a.list_s = list_s.p; a.list_i = list_i.p; a.ncand = nc.p;
+        int ld = base->ld;
+        size_t smem = pt::smem_bytes(ld) + pt::BN * sizeof(double) + pt::BN * sizeof(int32_t) + (size_t)MAXL * (pt::BN + pt::BM) * sizeof(int32_t);
+        int grid = (int)((nq + pt::BM - 1) / pt::BM);
+        DevBuf<int32_t> qperm, qkeys, qsorted;
+        CRX_TRY(qperm.alloc(c, nq));
+        auto launch_scan = [&](const ScanArgs& args) -> int {
+            CRX_KERNEL(c, "topp_scan");
+#define LAUNCH_T(TQ, TB, xqp, xbp)                                                                                      \
+        do {                                                                                                                \
+            CRX_CUDA(cudaFuncSetAttribute(topp_scan_kernel<TQ, TB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+            topp_scan_kernel<TQ, TB><<<grid, pt::NT, smem, c->stream>>>(xqp, queries->ld, queries->sqn, xbp, base->ld, base->sqn, args); \
+        } while (0)
+            if (queries->x64 && base->x64) LAUNCH_T(double, double, queries->x64, base->x64);
+            else if (queries->x64) LAUNCH_T(double, float, queries->x64, base->x32);
+            else if (base->x64) LAUNCH_T(float, double, queries->x32, base->x64);
+            else LAUNCH_T(float, float, queries->x32, base->x32);
+#undef LAUNCH_T
+            CRX_CUDA(cudaGetLastError());
+            return CRX_OK;
+        };
+        if (dense) {
+            { CRX_KERNEL(c, "iota"); iota_off_kernel<<<crx_grid(nq, 256), 256, 0, c->stream>>>(qperm.p, nq, (int32_t)q_begin); }
+            a.pass = -1; a.qperm = qperm.p; a.cperm = nullptr; a.csorted = nullptr; a.load_state = 0;
+            CRX_TRY(launch_scan(a));
+        } else {
+            for (int l = 0; l < L; l++) {
+                // queries of the batch ordered by their group in table l
+                Segments qs;
+                int st = crx_build_segments(c, a.qgid[l] + q_begin, nq, std::max(1, t->ngroups[l]), &qs);
+                if (st != CRX_OK) { qs.free_all(); return st; }
+                { CRX_KERNEL(c, "add_off"); add_off_kernel<<<crx_grid(nq, 256), 256, 0, c->stream>>>(qs.perm, nq, (int32_t)q_begin); }
+                a.pass = l; a.qperm = qs.perm; a.cperm = t->by_group[l].perm; a.csorted = t->by_group[l].sorted; a.load_state = l > 0;
+                st = launch_scan(a);
+                CRX_CUDA(cudaStreamSynchronize(c->stream));
+                qs.free_all();
+                if (st != CRX_OK) return st;
+            }
         }
     }
     IoBuf<int32_t> o_recs, o_rows, o_nc;
@@ -453,9 +567,14 @@ int crx_recommend_lsh(crx_ctx* c, const crx_lsh* t, const crx_points* queries, i
         CRX_KERNEL(c, "rec_finalize");
         int g = (int)((nq + 7) / 8);
 #define LAUNCH_F(TQ, TB, xqp, xbp)                                                                                         \
-    rec_finalize_kernel<TQ, TB><<<g, 256, 0, c->stream>>>(xqp, queries->ld, queries->sqn, queries->unknown, queries->mean, xbp, \
-                                                           base->ld, base->sqn, base->mean, base->d, q_begin, nq, P, Nrec,   \
-                                                           list_s.p, list_i.p, nc.p, o_recs.dev, o_rows.dev, o_sims.dev, c->counters)
+    do {                                                                                                                   \
+        if (use_tc)                                                                                                        \
+            rec_finalize_kernel<TQ, TB, TC_LIST, float><<<g, 256, 0, c->stream>>>(xqp, queries->ld, queries->sqn, queries->unknown, queries->mean, xbp, \
+                base->ld, base->sqn, base->mean, base->d, q_begin, nq, P, Nrec, tl_s.p, tl_i.p, nc.p, tc_unscale, 8e-6, o_recs.dev, o_rows.dev, o_sims.dev, c->counters); \
+        else                                                                                                               \
+            rec_finalize_kernel<TQ, TB, LIST, double><<<g, 256, 0, c->stream>>>(xqp, queries->ld, queries->sqn, queries->unknown, queries->mean, xbp, \
+                base->ld, base->sqn, base->mean, base->d, q_begin, nq, P, Nrec, list_s.p, list_i.p, nc.p, 1.0, 1e-12, o_recs.dev, o_rows.dev, o_sims.dev, c->counters); \
+    } while (0)
         if (queries->x64 && base->x64) LAUNCH_F(double, double, queries->x64, base->x64);
         else if (queries->x64) LAUNCH_F(double, float, queries->x64, base->x32);
         else if (base->x64) LAUNCH_F(float, double, queries->x32, base->x64);

@@ -1,0 +1,492 @@
+// tc_scan.cu -- tcgen05 / TMEM / TMA pair-scan engine for sm_100a (see tc_scan.cuh).
+//
+// One CTA = 128 rows of A ("queries" / "points"), resident in shared memory (TMA, 128B swizzle), against
+// ALL 128-column tiles of B streamed through a 4-stage TMA ring.  Warp 0 = TMA producer (one elected
+// lane), warp 1 = tcgen05.mma issuer (one elected lane; also owns the TMEM allocation), warps 2..5 =
+// epilogue: each thread owns ONE row of the 128x128 fp32 accumulator tile (tcgen05.ld 32x32b), so the
+// per-row reductions (masked top-64 list / best + second best) are thread-private -- no shuffles, no
+// atomics.  The accumulator is double-buffered in TMEM (2 x 128 columns) so that the MMAs of tile t+1
+// overlap the epilogue of tile t.
+//
+// Split-fp16 arithmetic: every operand row is stored as [hi blocks | lo blocks] with hi = fp16(v),
+// lo = fp16(v - hi).  For each B block the issuer runs
+//     B.hi_j : D += A.hi_j * B.hi_j ;  D += A.lo_j * B.hi_j
+//     B.lo_j : D += A.hi_j * B.lo_j
+// i.e. hi*hi + lo*hi + hi*lo (lo*lo <= 2^-22 is dropped) with fp32 accumulation: relative error of the
+// dot product <= ~4e-6 of |a||b| -- a FILTER; the exact FP64 kernels decide.
+#include <cuda.h>
+#include <cuda_fp16.h>
+
+#include "tc_scan.cuh"
+
+namespace {
+
+constexpr int TM = 128;            // rows per CTA
+constexpr int TN = 128;            // columns per tile
+constexpr int BLK_BYTES = TM * 64 * 2;  // one 128-row x 64-col fp16 block = 16 KB
+constexpr int NS = 5;              // B ring stages
+constexpr uint32_t IDESC = (1u << 4) /* D = F32 */ | (0u << 7) /* A = F16 */ | (0u << 10) /* B = F16 */ |
+                           ((uint32_t)(TN >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);  // K-major A and B
+
+// ---------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t addr = smem_u32(bar), done;
+    do {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(done)
+            : "r"(addr), "r"(parity)
+            : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* tm, int c0, int c1, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(smem_u32(smem_dst)),
+        "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_mma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(IDESC), "r"(accumulate)
+        : "memory");
+}
+// K-major, 128-byte swizzle, rows at 128 B pitch, 8-row groups 1024 B apart (cute::UMMA::SmemDescriptor)
+__device__ __forceinline__ uint64_t smem_desc(uint32_t addr) {
+    return (uint64_t)((addr & 0x3FFFF) >> 4) | (1ull << 16) /* LBO (ignored) */ | (64ull << 32) /* SBO = 1024 B */ |
+           (1ull << 46) /* version */ | (2ull << 61) /* SWIZZLE_128B */;
+}
+// four K=16 MMAs over one 64-column block; descriptors advance by 32 bytes (>> 4 = 2)
+__device__ __forceinline__ void mma_block(uint32_t tmem_d, uint32_t a_addr, uint32_t b_addr, uint32_t acc_first) {
+    uint64_t ad = smem_desc(a_addr), bd = smem_desc(b_addr);
+#pragma unroll
+    for (int k = 0; k < 4; k++) tc_mma(tmem_d, ad + 2 * k, bd + 2 * k, k == 0 ? acc_first : 1u);
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+struct TcParams {
+    int64_t q0, nq;   // rows of A handled by the grid: [q0, q0 + nq)
+    int64_t nb;       // valid rows of B
+    int ntiles, nkb;
+    // top-P
+    const uint32_t* qcode;
+    const uint32_t* ccode;
+    uint32_t low_mask, high_mask;
+    float* list_s;
+    int32_t* list_i;
+    // argmin
+    const float* half_norm;
+    float* best;
+    float* second;
+    int32_t* best_idx;
+};
+
+constexpr int MODE_TOPP = 0, MODE_ARGMIN = 1;
+constexpr int HL = TC_LIST / 2;   // entries of one half-list (each epilogue half keeps its own top-HL)
+constexpr int LSTRIDE = HL + 4;   // padded row stride (floats): 16-byte aligned rows, conflict-free quarter-warps
+
+// Replace the smallest entry of the row's (full) list, or append while it is filling, then recompute
+// the threshold = smallest kept score.  Rare path (~HL*ln(N/HL) times per row): kept out of line.
+__device__ __noinline__ void list_insert(float* ls, int32_t* li, float s, int32_t idx, int& cnt, float& thr, int& minpos) {
+    if (cnt < HL) {
+        ls[cnt] = s;
+        li[cnt] = idx;
+        cnt++;
+        if (cnt < HL) return;
+    } else {
+        ls[minpos] = s;
+        li[minpos] = idx;
+    }
+    float m = INFINITY;
+    int mp = 0;
+#pragma unroll
+    for (int e = 0; e < HL; e += 4) {
+        float4 v = *reinterpret_cast<const float4*>(ls + e);
+        if (v.x < m) { m = v.x; mp = e; }
+        if (v.y < m) { m = v.y; mp = e + 1; }
+        if (v.z < m) { m = v.z; mp = e + 2; }
+        if (v.w < m) { m = v.w; mp = e + 3; }
+    }
+    thr = m;
+    minpos = mp;
+}
+
+constexpr int NEPI = 8;                       // epilogue warps: two per TMEM lane quarter
+constexpr int NTHREADS_K = 64 + NEPI * 32;    // + producer warp + MMA warp
+
+template <int MODE>
+__global__ void __launch_bounds__(NTHREADS_K, 1)
+tc_scan_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, TcParams p) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const int nblk = 2 * p.nkb;
+    uint8_t* sA = smem;                                    // nblk blocks (<= 64 KB), resident
+    uint8_t* sB = smem + 4 * BLK_BYTES;                    // NS-stage ring
+    float* ls = reinterpret_cast<float*>(smem + (4 + NS) * BLK_BYTES);   // [2 halves][TM][LSTRIDE]  (top-P only)
+    int32_t* li = reinterpret_cast<int32_t*>(ls + 2 * TM * LSTRIDE);
+    uint32_t* stile = MODE == MODE_TOPP ? reinterpret_cast<uint32_t*>(li + 2 * TM * LSTRIDE)
+                                        : reinterpret_cast<uint32_t*>(smem + (4 + NS) * BLK_BYTES);  // [2][TN] codes / half norms
+    uint64_t* bars = reinterpret_cast<uint64_t*>(stile + 2 * TN);
+    uint64_t* a_full = bars;
+    uint64_t* full = bars + 1;
+    uint64_t* empty = full + NS;
+    uint64_t* tfull = empty + NS;
+    uint64_t* tempty = tfull + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+    float* merge = reinterpret_cast<float*>(tmem_slot + 4);  // [TM][3] argmin hand-over between the halves
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        if (smem_u32(smem) & 1023u) __trap();  // the 128B-swizzle atoms need a 1024-byte aligned base
+        mbar_init(a_full, 1);
+        for (int s = 0; s < NS; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        for (int b = 0; b < 2; b++) { mbar_init(&tfull[b], 1); mbar_init(&tempty[b], NEPI); }
+        fence_barrier_init();
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(256u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const int64_t row0 = p.q0 + (int64_t)blockIdx.x * TM;  // first A row of this CTA
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // ---------------- TMA producer ----------------
+            mbar_arrive_expect_tx(a_full, (uint32_t)(nblk * BLK_BYTES));
+            for (int b = 0; b < nblk; b++) tma_load_2d(sA + b * BLK_BYTES, &tmA, b * 64, (int)row0, a_full);
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int t = 0; t < p.ntiles; t++) {
+                for (int b = 0; b < nblk; b++) {
+                    mbar_wait(&empty[stage], phase ^ 1);
+                    mbar_arrive_expect_tx(&full[stage], (uint32_t)BLK_BYTES);
+                    tma_load_2d(sB + stage * BLK_BYTES, &tmB, b * 64, t * TN, &full[stage]);
+                    if (++stage == NS) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            // ---------------- MMA issuer ----------------
+            mbar_wait(a_full, 0);
+            tc_fence_after();
+            const uint32_t a_base = smem_u32(sA), b_base = smem_u32(sB);
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int t = 0; t < p.ntiles; t++) {
+                const int buf = t & 1;
+                const uint32_t bphase = (uint32_t)(t >> 1) & 1u;
+                mbar_wait(&tempty[buf], bphase ^ 1);
+                tc_fence_after();
+                const uint32_t d = tmem_base + (uint32_t)(buf * TN);
+                for (int b = 0; b < nblk; b++) {
+                    mbar_wait(&full[stage], phase);
+                    tc_fence_after();
+                    const uint32_t bs = b_base + stage * BLK_BYTES;
+                    if (b < p.nkb) {  // B.hi_b with A.hi_b and A.lo_b
+                        mma_block(d, a_base + b * BLK_BYTES, bs, b == 0 ? 0u : 1u);
+                        mma_block(d, a_base + (p.nkb + b) * BLK_BYTES, bs, 1u);
+                    } else {          // B.lo_j with A.hi_j
+                        mma_block(d, a_base + (b - p.nkb) * BLK_BYTES, bs, 1u);
+                    }
+                    tc_commit(&empty[stage]);
+                    if (++stage == NS) { stage = 0; phase ^= 1; }
+                }
+                tc_commit(&tfull[buf]);
+            }
+        }
+    } else {
+        // ---------------- epilogue: thread = (row, column half) ----------------
+        const int ew = warp - 2;                 // 0..7
+        const int etid = threadIdx.x - 64;       // 0..255
+        const int quarter = warp & 3;            // TMEM lane quarter this warp may read
+        const int half = ew >> 2;                // columns [64*half, 64*half + 64) of every tile
+        const int me = quarter * 32 + lane;      // row inside the tile
+        const int64_t grow = (int64_t)blockIdx.x * TM + me;  // row relative to q0
+        const bool valid = grow < p.nq;
+        uint32_t cq = 0;
+        float thr = -INFINITY, best = INFINITY, second = INFINITY;
+        int cnt = 0, minpos = 0, bidx = 0x7fffffff;
+        float* myls = ls + (half * TM + me) * LSTRIDE;
+        int32_t* myli = li + (half * TM + me) * LSTRIDE;
+        if (MODE == MODE_TOPP) {
+            if (valid) cq = p.qcode[p.q0 + grow];
+            for (int e = 0; e < HL; e++) { myls[e] = -INFINITY; myli[e] = -1; }
+        }
+        const uint32_t low = p.low_mask, high = p.high_mask;
+        for (int t = 0; t < p.ntiles; t++) {
+            const int buf = t & 1;
+            const uint32_t bphase = (uint32_t)(t >> 1) & 1u;
+            if (etid < TN) {
+                int64_t col = (int64_t)t * TN + etid;
+                uint32_t v;
+                if (MODE == MODE_TOPP) v = col < p.nb ? p.ccode[col] : 0u;
+                else v = __float_as_uint(col < p.nb ? p.half_norm[col] : INFINITY);
+                stile[buf * TN + etid] = v;
+            }
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            mbar_wait(&tfull[buf], bphase);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + (uint32_t)(buf * TN + half * 64) + ((uint32_t)(quarter * 32) << 16);
+#pragma unroll 1
+            for (int ch = 0; ch < 2; ch++) {
+                uint32_t r[32];
+                tmem_ld32(taddr + ch * 32, r);
+                if (ch == 1) {  // this warp's part of the tile is in registers: hand the TMEM buffer back
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&tempty[buf]);
+                }
+                const uint4* st4 = reinterpret_cast<const uint4*>(stile + buf * TN + half * 64 + ch * 32);
+                const int cbase = t * TN + half * 64 + ch * 32;
+                if (MODE == MODE_TOPP) {
+                    // branch-free pass: bit j = "column j shares a table bucket with this row AND beats the threshold"
+                    uint32_t bits = 0;
+#pragma unroll
+                    for (int g = 0; g < 8; g++) {
+                        uint4 cc = st4[g];
+                        uint32_t c4[4] = {cc.x, cc.y, cc.z, cc.w};
+#pragma unroll
+                        for (int u = 0; u < 4; u++) {
+                            uint32_t x = cq ^ c4[u];
+                            uint32_t m = (x - low) & ~x & high;  // some k-bit field of x is zero
+                            bool pass = (m != 0u) && (__uint_as_float(r[g * 4 + u]) > thr);
+                            bits |= pass ? (1u << (g * 4 + u)) : 0u;
+                        }
+                    }
+                    if (bits != 0u && valid) {
+#pragma unroll
+                        for (int j = 0; j < 32; j++) {
+                            if (bits & (1u << j)) {
+                                float s = __uint_as_float(r[j]);
+                                int c = cbase + j;
+                                if (s > thr && c < p.nb) list_insert(myls, myli, s, c, cnt, thr, minpos);
+                            }
+                        }
+                    }
+                } else {
+#pragma unroll
+                    for (int g = 0; g < 8; g++) {
+                        uint4 cc = st4[g];
+                        uint32_t c4[4] = {cc.x, cc.y, cc.z, cc.w};
+#pragma unroll
+                        for (int u = 0; u < 4; u++) {
+                            float v = __uint_as_float(c4[u]) - __uint_as_float(r[g * 4 + u]);
+                            float nbst = fminf(v, best);
+                            second = fminf(second, fmaxf(v, best));
+                            bidx = v < best ? cbase + g * 4 + u : bidx;
+                            best = nbst;
+                        }
+                    }
+                }
+            }
+        }
+        if (MODE == MODE_TOPP) {
+            if (valid) {
+                for (int e = 0; e < HL; e++) {
+                    p.list_s[grow * TC_LIST + half * HL + e] = myls[e];
+                    p.list_i[grow * TC_LIST + half * HL + e] = myli[e];
+                }
+            }
+        } else {
+            if (half == 1) { merge[me * 3 + 0] = best; merge[me * 3 + 1] = second; merge[me * 3 + 2] = __int_as_float(bidx); }
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            if (half == 0 && valid) {
+                float b1 = merge[me * 3 + 0], s1 = merge[me * 3 + 1];
+                int i1 = __float_as_int(merge[me * 3 + 2]);
+                float sec = fminf(fminf(second, s1), fmaxf(best, b1));
+                bool take1 = b1 < best || (b1 == best && i1 < bidx);
+                p.best[grow] = take1 ? b1 : best;
+                p.second[grow] = sec;
+                p.best_idx[grow] = take1 ? i1 : bidx;
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256u) : "memory");
+    }
+}
+
+// ---------------------------------------------------------------- operand preparation
+template <typename T>
+__global__ void tc_prep_rows_kernel(const T* __restrict__ x, int ld, int D, const double* __restrict__ sqn, int64_t n,
+                                    int mode, double scale, int nkb, __half* __restrict__ out) {
+    int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    int lane = threadIdx.x & 31;
+    if (row >= n) return;
+    double s = scale;
+    if (mode == 0) {
+        double nn = sqn[row];
+        s = nn > 0.0 ? scale / sqrt(nn) : 0.0;
+    }
+    int W = nkb * 64;
+    __half* o = out + row * (size_t)(2 * W);
+    for (int c = lane; c < W; c += 32) {
+        double v = c < D ? (double)x[row * ld + c] * s : 0.0;
+        __half hi = __double2half(v);
+        __half lo = __double2half(v - (double)__half2float(hi));
+        o[c] = hi;
+        o[W + c] = lo;
+    }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+int make_tensor_map(const TcOperand& op, CUtensorMap* tm) {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* ptr = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres);
+        if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !ptr) {
+            crx_set_error("cuTensorMapEncodeTiled is not available from the driver (%s)", cudaGetErrorString(e));
+            return CRX_ERR_CUDA;
+        }
+        fn = (EncodeTiledFn)ptr;
+    }
+    cuuint64_t cols = (cuuint64_t)op.nkb * 2 * 64;
+    cuuint64_t gdim[2] = {cols, (cuuint64_t)op.rows_pad};
+    cuuint64_t gstride[1] = {cols * sizeof(__half)};
+    cuuint32_t box[2] = {64, (cuuint32_t)TM};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, op.data, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        crx_set_error("cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+        return CRX_ERR_CUDA;
+    }
+    return CRX_OK;
+}
+
+size_t smem_for(int mode) {
+    size_t s = (size_t)(4 + NS) * BLK_BYTES + 2 * TN * 4 + (1 + 2 * NS + 4) * 8 + 16 + TM * 3 * 4;
+    if (mode == MODE_TOPP) s += (size_t)2 * TM * LSTRIDE * 8;
+    return s;
+}
+
+int alloc_operand(crx_ctx* c, int64_t rows, int D, TcOperand* out) {
+    out->rows = rows;
+    out->rows_pad = (rows + TM - 1) / TM * TM;
+    out->nkb = D <= 64 ? 1 : 2;
+    size_t bytes = (size_t)out->rows_pad * out->nkb * 2 * 64 * sizeof(__half);
+    cudaError_t e = cudaMalloc(&out->data, bytes);
+    if (e != cudaSuccess) {
+        crx_set_error("tensor operand: cudaMalloc(%zu) -> %s", bytes, cudaGetErrorString(e));
+        return CRX_ERR_NOMEM;
+    }
+    CRX_CUDA(cudaMemsetAsync(out->data, 0, bytes, c->stream));
+    return CRX_OK;
+}
+
+}  // namespace
+
+int crx_tc_prepare(crx_ctx* c, const crx_points* p, int mode, double scale_log2, TcOperand* out) {
+    CRX_REQUIRE(p->d <= 128, "tensor path supports D <= 128");
+    CRX_TRY(alloc_operand(c, p->n, p->d, out));
+    out->scale_log2 = scale_log2;
+    double scale = ldexp(1.0, (int)scale_log2);
+    int g = (int)((p->n + 7) / 8);
+    CRX_KERNEL(c, "tc_prep");
+    if (p->x64) tc_prep_rows_kernel<double><<<g, 256, 0, c->stream>>>(p->x64, p->ld, p->d, p->sqn, p->n, mode, scale, out->nkb, (__half*)out->data);
+    else tc_prep_rows_kernel<float><<<g, 256, 0, c->stream>>>(p->x32, p->ld, p->d, p->sqn, p->n, mode, scale, out->nkb, (__half*)out->data);
+    CRX_CUDA(cudaGetLastError());
+    return CRX_OK;
+}
+
+int crx_tc_prepare_matrix(crx_ctx* c, const double* m, int K, int D, int ld, double scale_log2, TcOperand* out) {
+    CRX_REQUIRE(D <= 128, "tensor path supports D <= 128");
+    CRX_TRY(alloc_operand(c, K, D, out));
+    out->scale_log2 = scale_log2;
+    int g = (K + 7) / 8;
+    CRX_KERNEL(c, "tc_prep");
+    tc_prep_rows_kernel<double><<<g, 256, 0, c->stream>>>(m, ld, D, nullptr, K, 1, ldexp(1.0, (int)scale_log2), out->nkb, (__half*)out->data);
+    CRX_CUDA(cudaGetLastError());
+    return CRX_OK;
+}
+
+int crx_tc_topp(crx_ctx* c, const TcOperand& A, int64_t q0, int64_t nq, const TcOperand& B, const uint32_t* qcode,
+                const uint32_t* ccode, int k, int L, float* list_s, int32_t* list_i) {
+    CRX_REQUIRE(A.nkb == B.nkb, "operand widths differ");
+    CRX_REQUIRE(k * L <= 32 && k >= 1, "packed codes need k*L <= 32");
+    CUtensorMap tmA, tmB;
+    CRX_TRY(make_tensor_map(A, &tmA));
+    CRX_TRY(make_tensor_map(B, &tmB));
+    TcParams p;
+    memset(&p, 0, sizeof(p));
+    p.q0 = q0; p.nq = nq; p.nb = B.rows; p.ntiles = (int)((B.rows + TN - 1) / TN); p.nkb = A.nkb;
+    p.qcode = qcode; p.ccode = ccode;
+    uint32_t low = 0, high = 0;
+    for (int l = 0; l < L; l++) { low |= 1u << (l * k); high |= 1u << (l * k + k - 1); }
+    p.low_mask = low; p.high_mask = high;
+    p.list_s = list_s; p.list_i = list_i;
+    size_t smem = smem_for(MODE_TOPP);
+    CRX_CUDA(cudaFuncSetAttribute(tc_scan_kernel<MODE_TOPP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int grid = (int)((nq + TM - 1) / TM);
+    CRX_KERNEL(c, "tc_topp_scan");
+    tc_scan_kernel<MODE_TOPP><<<grid, NTHREADS_K, smem, c->stream>>>(tmA, tmB, p);
+    CRX_CUDA(cudaGetLastError());
+    return CRX_OK;
+}
+
+int crx_tc_argmin(crx_ctx* c, const TcOperand& A, int64_t r0, int64_t nr, const TcOperand& B, const float* half_norm,
+                  float* best, float* second, int32_t* best_idx) {
+    CRX_REQUIRE(A.nkb == B.nkb, "operand widths differ");
+    CUtensorMap tmA, tmB;
+    CRX_TRY(make_tensor_map(A, &tmA));
+    CRX_TRY(make_tensor_map(B, &tmB));
+    TcParams p;
+    memset(&p, 0, sizeof(p));
+    p.q0 = r0; p.nq = nr; p.nb = B.rows; p.ntiles = (int)((B.rows + TN - 1) / TN); p.nkb = A.nkb;
+    p.half_norm = half_norm; p.best = best; p.second = second; p.best_idx = best_idx;
+    size_t smem = smem_for(MODE_ARGMIN);
+    CRX_CUDA(cudaFuncSetAttribute(tc_scan_kernel<MODE_ARGMIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int grid = (int)((nr + TM - 1) / TM);
+    CRX_KERNEL(c, "tc_argmin_scan");
+    tc_scan_kernel<MODE_ARGMIN><<<grid, NTHREADS_K, smem, c->stream>>>(tmA, tmB, p);
+    CRX_CUDA(cudaGetLastError());
+    return CRX_OK;
+}

@@ -1,0 +1,38 @@
+// tc_scan.cuh -- declarations of the tcgen05 (5th-gen tensor core) pair-scan engine.
+//
+// The contraction-bound kernels of this path (K9 cosine top-P scan, K5 Lloyd assignment at large K)
+// are "row block x ALL columns" GEMMs followed by a per-row reduction.  tc_scan.cu runs them on the
+// tensor cores as a FILTER: operands are split into fp16 hi + lo parts (22 significant bits), three
+// products hi*hi + hi*lo + lo*hi are accumulated in fp32 in TMEM, and the epilogue keeps, per row,
+// either the 64 best masked scores (top-P) or the best and second-best value (argmin).  The exact
+// FP64 kernels then re-evaluate only the survivors, so results stay those of the reference.
+#pragma once
+#include "common.cuh"
+
+// [rows][4*64 or 2*64] fp16: hi blocks first, then lo blocks, 64 columns per block (one 128-byte
+// swizzle atom); rows padded to a multiple of 128 with zeros.
+struct TcOperand {
+    void* data = nullptr;     // __half [rows_pad][nkb*2*64]
+    int64_t rows = 0, rows_pad = 0;
+    int nkb = 0;              // 64-column blocks per part (1 for D <= 64, 2 for D <= 128)
+    double scale_log2 = 0;    // values were multiplied by 2^scale_log2 before the split
+    void free_all() { cudaFree(data); data = nullptr; }
+};
+
+// mode 0: rows scaled to unit length times 2^10 (cosine);  mode 1: all rows times 2^scale_log2
+int crx_tc_prepare(crx_ctx* c, const crx_points* p, int mode, double scale_log2, TcOperand* out);
+// same for a [K][ld] double matrix (centroids)
+int crx_tc_prepare_matrix(crx_ctx* c, const double* m, int K, int D, int ld, double scale_log2, TcOperand* out);
+
+constexpr int TC_LIST = 64;  // per-row candidate list of the top-P filter
+
+// top-P filter: for query rows [q0, q0+nq) of A against all rows of B, keep the TC_LIST best scores among
+// the columns whose packed code shares at least one k-bit field with the query's code.
+//   list_s[nq][TC_LIST] (float, scaled by 2^(sa+sb)), list_i[nq][TC_LIST] (column, -1 = empty)
+int crx_tc_topp(crx_ctx* c, const TcOperand& A, int64_t q0, int64_t nq, const TcOperand& B, const uint32_t* qcode,
+                const uint32_t* ccode, int k, int L, float* list_s, int32_t* list_i);
+
+// argmin filter: for rows [r0, r0+nr) of A against the K rows of B: best / second-best of
+// half_norm[j] - dot(a, b_j) (scaled units) and the best column.
+int crx_tc_argmin(crx_ctx* c, const TcOperand& A, int64_t r0, int64_t nr, const TcOperand& B, const float* half_norm,
+                  float* best, float* second, int32_t* best_idx);
