@@ -250,12 +250,16 @@ def run_crx(args):
     flops_per_launch = 2.0 * d * ncand_total * args.steps / max(1, scan_launches)
     achieved_tf = flops_per_launch / (scan_ms / max(1, scan_launches) * 1e-3) / 1e12 if scan_ms > 0 else 0.0
     tc = scan_name == "tc_topp_scan"
-    # tensor path: 3 fp16 products (hi*hi, lo*hi, hi*lo) over the D padded to 128 columns => 3*128/D tensor flops per algorithmic flop
+    # tensor path: 3 fp16 products (hi*hi, lo*hi, hi*lo) over D rounded up to a multiple of 16 columns
+    tc_factor = 3.0 * (16 * ((d + 15) // 16)) / d
     roofline = {"kernel": ("tc_scan_kernel<TOPP> (tcgen05 split-fp16 cosine scan, per-row top-64 in the epilogue)" if tc else
                            "topp_scan_kernel (FP64 SIMT masked cosine scan + per-query top-32 list)"), "bound": "tensor",
                 "achieved": achieved_tf, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s", "frac": achieved_tf / peaks["bf16_tflops"],
                 "traffic": None, "peak_source": peaks["which"] + " bf16 dense GEMM (burst)",
-                "pipe": ("tcgen05.mma kind::f16, fp32 accumulate in TMEM; executed tensor flops = %.2fx algorithmic (3 split products, D padded to 128)" % (3 * 128.0 / d)) if tc else "FP64 SIMT FMA",
+                "pipe": ("tcgen05.mma kind::f16 M128 N256 K16, fp32 accumulate in TMEM; executed tensor flops = %.2fx algorithmic "
+                         "(3 split-fp16 products, D padded to a multiple of 16)" % tc_factor) if tc else "FP64 SIMT FMA",
+                "executed_tensor_tflops": achieved_tf * tc_factor if tc else None,
+                "executed_frac_of_peak": achieved_tf * tc_factor / peaks["bf16_tflops"] if tc else None,
                 "algorithmic_flops": "2*D*sum|cand(u)|", "kernel_ms_all": kernel_ms,
                 "kernel_ms_per_step": scan_ms / args.steps, "share_of_step": scan_ms / args.steps / ms_step}
 

@@ -159,6 +159,22 @@ struct IoBuf {
     }
 };
 
+// long-lived device buffers of handles: stream-ordered pool allocations too (the pool keeps freed memory,
+// so rebuilding tables / points every step does not go back to the driver)
+template <typename T>
+static inline int crx_alloc(crx_ctx* c, T** p, size_t count) {
+    cudaError_t e = cudaMallocAsync((void**)p, (count ? count : 1) * sizeof(T), c->stream);
+    if (e != cudaSuccess) {
+        crx_set_error("cudaMallocAsync(%zu bytes) -> %s", count * sizeof(T), cudaGetErrorString(e));
+        *p = nullptr;
+        return CRX_ERR_NOMEM;
+    }
+    return CRX_OK;
+}
+static inline void crx_free(crx_ctx* c, void* p) {
+    if (p) cudaFreeAsync(p, c->stream);
+}
+
 static inline int crx_grid(int64_t work, int block) { return (int)((work + block - 1) / block); }
 
 // ------------------------------------------------------------------------------------------------
@@ -245,18 +261,27 @@ __device__ __forceinline__ double metric_dist_exact(int metric, const TA* a, con
 // utils.hpp:97-98 for (int, int)
 __host__ __device__ __forceinline__ int mod_ii(int x, int n) { return (x % n + n) % n; }
 
-// crypto_rec.hpp:235-277: Lomuto partition (pivot = last, `>=` goes left) over two parallel
-// arrays, explicit stack.  n <= 128 in the device use (coins of one user).
+// crypto_rec.hpp:235-277: Lomuto partition (pivot = last, `>=` goes left) over two parallel arrays, explicit
+// stack instead of recursion.  Two shortcuts that cannot change the result of the literal algorithm:
+//   * a range whose keys are all equal is left untouched by it (every partition swaps elements with
+//     themselves and recurses on the prefix) -- skip it instead of spending O(n^2) compares; predicted
+//     scores tie massively (every coin unknown to all neighbours predicts exactly the user's mean);
+//   * only the first `need` positions are consumed (resize(N), crypto_rec.hpp:322): ranges that start at or
+//     beyond `need` never influence them and are skipped (quickselect-style pruning).
 template <typename K, typename V>
-__host__ __device__ inline void lomuto_desc(K* key, V* val, int n) {
+__host__ __device__ inline void lomuto_desc(K* key, V* val, int n, int need) {
     int stack_lo[64], stack_hi[64];
     int sp = 0;
     stack_lo[0] = 0; stack_hi[0] = n - 1; sp = 1;
     while (sp > 0) {
         sp--;
         int lo = stack_lo[sp], hi = stack_hi[sp];
-        while (lo < hi) {
+        while (lo < hi && lo < need) {
             K pivot = key[hi];
+            bool all_equal = true;
+            for (int j = lo; j < hi; j++)
+                if (!(key[j] == pivot)) { all_equal = false; break; }
+            if (all_equal) break;
             int i = lo - 1;
             for (int j = lo; j < hi; j++) {
                 if (key[j] >= pivot) {
@@ -268,7 +293,7 @@ __host__ __device__ inline void lomuto_desc(K* key, V* val, int n) {
             K tk = key[i + 1]; key[i + 1] = key[hi]; key[hi] = tk;
             V tv = val[i + 1]; val[i + 1] = val[hi]; val[hi] = tv;
             int p = i + 1;
-            // recurse on the smaller side via the stack, iterate on the larger: depth <= log2(n)+1
+            // push the larger side, continue with the smaller: stack depth <= log2(n) + 1
             int llo = lo, lhi = p - 1, rlo = p + 1, rhi = hi;
             if (lhi - llo < rhi - rlo) {
                 if (sp < 64) { stack_lo[sp] = rlo; stack_hi[sp] = rhi; sp++; }
@@ -280,3 +305,5 @@ __host__ __device__ inline void lomuto_desc(K* key, V* val, int n) {
         }
     }
 }
+template <typename K, typename V>
+__host__ __device__ inline void lomuto_desc(K* key, V* val, int n) { lomuto_desc(key, val, n, n); }

@@ -192,13 +192,12 @@ int crx_points_create(crx_ctx* c, const void* data, int dtype, int64_t n, int32_
     crx_points* p = new crx_points();
     p->ctx = c; p->n = n; p->d = d; p->ld = (d + 3) & ~3;
     size_t elems = (size_t)n * p->ld;
-    cudaError_t e = cudaMalloc((void**)&p->x32, elems * sizeof(float));
-    if (e == cudaSuccess && dtype == CRX_F64) e = cudaMalloc((void**)&p->x64, elems * sizeof(double));
-    if (e == cudaSuccess) e = cudaMalloc((void**)&p->sqn, (size_t)n * sizeof(double));
-    if (e != cudaSuccess) {
-        crx_set_error("crx_points_create: cudaMalloc -> %s", cudaGetErrorString(e));
+    int st = crx_alloc(c, &p->x32, elems);
+    if (st == CRX_OK && dtype == CRX_F64) st = crx_alloc(c, &p->x64, elems);
+    if (st == CRX_OK) st = crx_alloc(c, &p->sqn, (size_t)n);
+    if (st != CRX_OK) {
         crx_points_destroy(p);
-        return CRX_ERR_NOMEM;
+        return st;
     }
     size_t esz = dtype == CRX_F32 ? 4 : 8;
     const void* src = data;
@@ -232,8 +231,8 @@ int crx_points_set_ratings(crx_points* p, const uint8_t* unknown, const double* 
     crx_ctx* c = p->ctx;
     CRX_CUDA(cudaSetDevice(c->device));
     size_t nu = (size_t)p->n * p->d;
-    if (!p->unknown) CRX_CUDA(cudaMalloc((void**)&p->unknown, nu));
-    if (!p->mean) CRX_CUDA(cudaMalloc((void**)&p->mean, (size_t)p->n * sizeof(double)));
+    if (!p->unknown) CRX_TRY(crx_alloc(c, &p->unknown, nu));
+    if (!p->mean) CRX_TRY(crx_alloc(c, &p->mean, (size_t)p->n));
     cudaMemcpyKind kind = mem == CRX_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice;
     CRX_CUDA(cudaMemcpyAsync(p->unknown, unknown, nu, kind, c->stream));
     CRX_CUDA(cudaMemcpyAsync(p->mean, known_mean, (size_t)p->n * sizeof(double), kind, c->stream));
@@ -243,8 +242,10 @@ int crx_points_set_ratings(crx_points* p, const uint8_t* unknown, const double* 
 
 int crx_points_destroy(crx_points* p) {
     if (!p) return CRX_OK;
-    if (p->ctx) { cudaSetDevice(p->ctx->device); cudaStreamSynchronize(p->ctx->stream); }
-    cudaFree(p->x32); cudaFree(p->x64); cudaFree(p->sqn); cudaFree(p->unknown); cudaFree(p->mean);
+    if (p->ctx) {
+        cudaSetDevice(p->ctx->device);
+        crx_free(p->ctx, p->x32); crx_free(p->ctx, p->x64); crx_free(p->ctx, p->sqn); crx_free(p->ctx, p->unknown); crx_free(p->ctx, p->mean);
+    }
     delete p;
     return CRX_OK;
 }

@@ -213,10 +213,10 @@ static int sort_pairs(crx_ctx* c, const int32_t* kin, int32_t* kout, const int32
 }
 
 int crx_build_segments(crx_ctx* c, const int32_t* keys, int64_t n, int nkeys, Segments* out) {
-    out->n = n; out->nkeys = nkeys;
-    CRX_CUDA(cudaMalloc((void**)&out->perm, n * sizeof(int32_t)));
-    CRX_CUDA(cudaMalloc((void**)&out->sorted, n * sizeof(int32_t)));
-    CRX_CUDA(cudaMalloc((void**)&out->off, ((size_t)nkeys + 1) * sizeof(int32_t)));
+    out->n = n; out->nkeys = nkeys; out->owner = c;
+    CRX_TRY(crx_alloc(c, &out->perm, n));
+    CRX_TRY(crx_alloc(c, &out->sorted, n));
+    CRX_TRY(crx_alloc(c, &out->off, (size_t)nkeys + 1));
     DevBuf<int32_t> iota;
     CRX_TRY(iota.alloc(c, n));
     { CRX_KERNEL(c, "iota"); iota_kernel<<<crx_grid(n, 256), 256, 0, c->stream>>>(iota.p, n); }
@@ -277,10 +277,10 @@ static int build_tuple_groups(crx_ctx* c, const int32_t* hv /* [N][k] */, int64_
     CRX_CUDA(cudaMemcpyAsync(&last, kb.p + (n - 1), sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
     CRX_CUDA(cudaStreamSynchronize(c->stream));
     *ngroups = last + 1;
-    seg->n = n; seg->nkeys = *ngroups;
-    CRX_CUDA(cudaMalloc((void**)&seg->perm, n * sizeof(int32_t)));
-    CRX_CUDA(cudaMalloc((void**)&seg->sorted, n * sizeof(int32_t)));
-    CRX_CUDA(cudaMalloc((void**)&seg->off, ((size_t)*ngroups + 1) * sizeof(int32_t)));
+    seg->n = n; seg->nkeys = *ngroups; seg->owner = c;
+    CRX_TRY(crx_alloc(c, &seg->perm, n));
+    CRX_TRY(crx_alloc(c, &seg->sorted, n));
+    CRX_TRY(crx_alloc(c, &seg->off, (size_t)*ngroups + 1));
     CRX_CUDA(cudaMemcpyAsync(seg->perm, pin, n * sizeof(int32_t), cudaMemcpyDeviceToDevice, c->stream));
     CRX_CUDA(cudaMemcpyAsync(seg->sorted, kb.p, n * sizeof(int32_t), cudaMemcpyDeviceToDevice, c->stream));
     { CRX_KERNEL(c, "bucket_offsets"); offsets_kernel<<<crx_grid(*ngroups + 1, 256), 256, 0, c->stream>>>(seg->sorted, n, *ngroups, seg->off); }
@@ -315,8 +315,8 @@ static int upload_proj(crx_ctx* c, int H, int D, int ld, const double* cos_r, co
         }
         pn[h] = std::sqrt(s) * 1.0000001;
     }
-    CRX_CUDA(cudaMalloc((void**)d_proj, proj.size() * sizeof(double)));
-    CRX_CUDA(cudaMalloc((void**)d_pnorm, pn.size() * sizeof(double)));
+    CRX_TRY(crx_alloc(c, d_proj, proj.size()));
+    CRX_TRY(crx_alloc(c, d_pnorm, pn.size()));
     CRX_CUDA(cudaMemcpyAsync(*d_proj, proj.data(), proj.size() * sizeof(double), cudaMemcpyHostToDevice, c->stream));
     CRX_CUDA(cudaMemcpyAsync(*d_pnorm, pn.data(), pn.size() * sizeof(double), cudaMemcpyHostToDevice, c->stream));
     CRX_CUDA(cudaStreamSynchronize(c->stream));
@@ -415,10 +415,10 @@ int crx_get_num_hamming_dist_from(int num, int dist, int min_bit, int bits, int3
 int crx_lsh_destroy(crx_lsh* t) {
     if (!t) return CRX_OK;
     cudaSetDevice(t->ctx->device);
-    cudaStreamSynchronize(t->ctx->stream);
-    cudaFree(t->d_proj); cudaFree(t->d_pnorm); cudaFree(t->d_t); cudaFree(t->d_r);
-    cudaFree(t->hvals); cudaFree(t->bucket);
-    if (t->gid != t->bucket) cudaFree(t->gid);
+    crx_ctx* c = t->ctx;
+    crx_free(c, t->d_proj); crx_free(c, t->d_pnorm); crx_free(c, t->d_t); crx_free(c, t->d_r);
+    crx_free(c, t->hvals); crx_free(c, t->bucket);
+    if (t->gid != t->bucket) crx_free(c, t->gid);
     for (size_t l = 0; l < t->by_bucket.size(); l++) {
         if (l < t->by_group.size() && t->by_group[l].perm != t->by_bucket[l].perm) t->by_group[l].free_all();
         t->by_bucket[l].free_all();
@@ -465,17 +465,17 @@ int crx_create_LSH_hashtables(crx_ctx* c, const crx_points* pts, int metric, int
                          metric == CRX_EUCLIDEAN ? t->euc_v.data() : nullptr, &t->d_proj, &t->d_pnorm);
     if (st != CRX_OK) { crx_lsh_destroy(t); return st; }
     if (metric == CRX_EUCLIDEAN) {
-        CRX_CUDA(cudaMalloc((void**)&t->d_t, H * sizeof(float)));
-        CRX_CUDA(cudaMalloc((void**)&t->d_r, H * sizeof(int32_t)));
+        CRX_TRY(crx_alloc(c, &t->d_t, H));
+        CRX_TRY(crx_alloc(c, &t->d_r, H));
         CRX_CUDA(cudaMemcpyAsync(t->d_t, t->euc_t.data(), H * sizeof(float), cudaMemcpyHostToDevice, c->stream));
         CRX_CUDA(cudaMemcpyAsync(t->d_r, t->euc_r.data(), H * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
-        CRX_CUDA(cudaMalloc((void**)&t->hvals, (size_t)L * N * k * sizeof(int32_t)));
+        CRX_TRY(crx_alloc(c, &t->hvals, (size_t)L * N * k));
     }
-    CRX_CUDA(cudaMalloc((void**)&t->bucket, (size_t)L * N * sizeof(int32_t)));
+    CRX_TRY(crx_alloc(c, &t->bucket, (size_t)L * N));
     st = crx_hash_rows(c, pts, metric, k, L, t->d_proj, t->ldp, t->d_pnorm, t->d_t, t->d_r, t->w, t->nbuckets, t->hvals, t->bucket);
     if (st != CRX_OK) { crx_lsh_destroy(t); return st; }
     t->by_bucket.resize(L); t->by_group.resize(L); t->ngroups.resize(L);
-    if (metric == CRX_EUCLIDEAN) CRX_CUDA(cudaMalloc((void**)&t->gid, (size_t)L * N * sizeof(int32_t)));
+    if (metric == CRX_EUCLIDEAN) CRX_TRY(crx_alloc(c, &t->gid, (size_t)L * N));
     else t->gid = t->bucket;
     for (int l = 0; l < L; l++) {
         st = crx_build_segments(c, t->bucket + (size_t)l * N, N, t->nbuckets, &t->by_bucket[l]);
@@ -550,8 +550,7 @@ int crx_get_LSH_combined_buckets(const crx_lsh* t, int64_t q, int filtered, int3
 int crx_cube_destroy(crx_cube* cu) {
     if (!cu) return CRX_OK;
     cudaSetDevice(cu->ctx->device);
-    cudaStreamSynchronize(cu->ctx->stream);
-    cudaFree(cu->vertex);
+    crx_free(cu->ctx, cu->vertex);
     cu->by_vertex.free_all();
     delete cu;
     return CRX_OK;
@@ -580,12 +579,12 @@ int crx_create_hypercube(crx_ctx* c, const crx_points* pts, int metric, int k, d
     int st = upload_proj(c, k, D, pts->ld, metric == CRX_COSINE ? cu->cos_r.data() : nullptr,
                          metric == CRX_EUCLIDEAN ? cu->euc_v.data() : nullptr, &d_proj, &d_pnorm);
     if (st != CRX_OK) { crx_cube_destroy(cu); return st; }
-    CRX_CUDA(cudaMalloc((void**)&cu->vertex, N * sizeof(int32_t)));
+    CRX_TRY(crx_alloc(c, &cu->vertex, N));
     int nvert = 1 << k;
     if (metric == CRX_COSINE) {
         st = crx_hash_rows(c, pts, metric, k, 1, d_proj, pts->ld, d_pnorm, nullptr, nullptr, 0.f, nvert, nullptr, cu->vertex);
     } else {
-        CRX_CUDA(cudaMalloc((void**)&d_t, k * sizeof(float)));
+        CRX_TRY(crx_alloc(c, &d_t, k));
         CRX_CUDA(cudaMemcpyAsync(d_t, cu->euc_t.data(), k * sizeof(float), cudaMemcpyHostToDevice, c->stream));
         DevBuf<int32_t> hv;
         CRX_TRY(hv.alloc(c, (size_t)N * k));
@@ -649,7 +648,7 @@ int crx_create_hypercube(crx_ctx* c, const crx_points* pts, int metric, int k, d
             CRX_CUDA(cudaStreamSynchronize(c->stream));
         }
     }
-    cudaFree(d_proj); cudaFree(d_pnorm); cudaFree(d_t);
+    crx_free(c, d_proj); crx_free(c, d_pnorm); crx_free(c, d_t);
     if (st != CRX_OK) { crx_cube_destroy(cu); return st; }
     st = crx_build_segments(c, cu->vertex, N, nvert, &cu->by_vertex);
     if (st != CRX_OK) { crx_cube_destroy(cu); return st; }

@@ -198,18 +198,32 @@ rec_finalize_kernel(const TQ* __restrict__ xq, int ldq, const double* __restrict
     // scores at most max over FULL groups of (smallest approximate score of the group)
     double floor_s = -INFINITY;
     int nvalid = 0;
+    // this lane's 4 coordinates of the query row
+    double qv[4] = {0.0, 0.0, 0.0, 0.0};
+    if (4 * lane < ldq) pt::ld4(q + 4 * lane, qv);
+    const double nq_ = sqn_q[qrow];
 #pragma unroll
     for (int e = 0; e < EPL; e++) {
         int slot = e * 32 + lane;
         int idx = list_i[qrel * LISTN + slot];
-        double sim = -INFINITY, ap = INFINITY;
-        if (idx >= 0) {
-            sim = cos_sim_exact(xb + (size_t)idx * ldb, q, D, sqn_b[idx], sqn_q[qrow]);  // crypto_rec.hpp:220
-            ap = (double)list_s[qrel * LISTN + slot];
+        double ap = idx >= 0 ? (double)list_s[qrel * LISTN + slot] : INFINITY;
+        unsigned vm = __ballot_sync(0xffffffffu, idx >= 0);
+        // exact similarity of every listed candidate (crypto_rec.hpp:220): the warp walks the candidates,
+        // lanes split the coordinates (one 16-byte load each), FP64 FMA + shuffle tree
+        double mysim = -INFINITY;
+        for (int cnd = 0; cnd < 32; cnd++) {
+            if (!((vm >> cnd) & 1u)) continue;
+            int ci = __shfl_sync(0xffffffffu, idx, cnd);
+            double cv[4] = {0.0, 0.0, 0.0, 0.0};
+            if (4 * lane < ldb) pt::ld4(xb + (size_t)ci * ldb + 4 * lane, cv);
+            double part = __fma_rn(cv[0], qv[0], __fma_rn(cv[1], qv[1], __fma_rn(cv[2], qv[2], __dmul_rn(cv[3], qv[3]))));
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) part += __shfl_xor_sync(0xffffffffu, part, off);
+            if (lane == cnd) mysim = cos_sim_from(part, sqn_b[ci], nq_);
         }
         a_idx[warp][slot] = idx;
-        a_sim[warp][slot] = sim;
-        int gcount = __popc(__ballot_sync(0xffffffffu, idx >= 0));
+        a_sim[warp][slot] = mysim;
+        int gcount = __popc(vm);
 #pragma unroll
         for (int off = 16; off > 0; off >>= 1) ap = fmin(ap, __shfl_xor_sync(0xffffffffu, ap, off));
         nvalid += gcount;
@@ -276,7 +290,7 @@ rec_finalize_kernel(const TQ* __restrict__ xq, int ldq, const double* __restrict
         nu += __popc(um);
     }
     __syncwarp();
-    if (lane == 0) lomuto_desc(s_pred[warp], s_coin[warp], nu);  // crypto_rec.hpp:320
+    if (lane == 0) lomuto_desc(s_pred[warp], s_coin[warp], nu, Nrec);  // crypto_rec.hpp:320
     __syncwarp();
     for (int j = lane; j < Nrec; j += 32) recs[qrel * Nrec + j] = j < nu ? s_coin[warp][j] : 0;  // resize(N) pads with 0
 }
@@ -308,6 +322,13 @@ __global__ void subset_hist_kernel(const uint32_t* __restrict__ code, int64_t n,
     if (i >= n) return;
     uint32_t c = code[i];
     for (int S = 1; S < (1 << L); S++) atomicAdd(&hist[hoff[S] + subcode(c, S, k, L)], 1);
+}
+__global__ void sum_counts_kernel(const int32_t* __restrict__ v, int64_t n, unsigned long long* __restrict__ out) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned long long x = i < n ? (unsigned long long)v[i] : 0ull;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+    if ((threadIdx.x & 31) == 0 && x) atomicAdd(out, x);
 }
 __global__ void subset_count_kernel(const uint32_t* __restrict__ qcode, int64_t q_begin, int64_t nq, int k, int L,
                                     const int64_t* __restrict__ hoff, const int* __restrict__ hist, int32_t* __restrict__ ncand) {
@@ -384,7 +405,7 @@ rec_cluster_kernel(const TQ* __restrict__ xq, int ldq, const double* __restrict_
         nu += __popc(um);
     }
     __syncwarp();
-    if (lane == 0) lomuto_desc(s_pred[warp], s_coin[warp], nu);
+    if (lane == 0) lomuto_desc(s_pred[warp], s_coin[warp], nu, Nrec);
     __syncwarp();
     for (int j = lane; j < Nrec; j += 32) recs[qrow * Nrec + j] = j < nu ? s_coin[warp][j] : 0;
 }
@@ -488,9 +509,17 @@ int crx_recommend_lsh(crx_ctx* c, const crx_lsh* t, const crx_points* queries, i
         TcOperand opB, opA;
         int st = crx_tc_prepare(c, base, 0, 10.0, &opB);
         if (st == CRX_OK && !self) st = crx_tc_prepare(c, queries, 0, 10.0, &opA);
-        if (st == CRX_OK) st = crx_tc_topp(c, self ? opB : opA, q_begin, nq, opB, qcode, ccode.p, k, L, tl_s.p, tl_i.p);
+        // candidate density decides the hot-loop variant of the filter
+        DevBuf<unsigned long long> tot;
+        CRX_TRY(tot.alloc(c, 1));
+        CRX_CUDA(cudaMemsetAsync(tot.p, 0, sizeof(unsigned long long), c->stream));
+        { CRX_KERNEL(c, "sum_counts"); sum_counts_kernel<<<crx_grid(nq, 256), 256, 0, c->stream>>>(nc.p, nq, tot.p); }
+        unsigned long long h_tot = 0;
+        CRX_CUDA(cudaMemcpyAsync(&h_tot, tot.p, sizeof(h_tot), cudaMemcpyDeviceToHost, c->stream));
+        CRX_CUDA(cudaStreamSynchronize(c->stream));
+        bool dense_cols = (double)h_tot >= 0.9 * (double)nq * (double)N;
+        if (st == CRX_OK) st = crx_tc_topp(c, self ? opB : opA, q_begin, nq, opB, qcode, ccode.p, k, L, dense_cols, tl_s.p, tl_i.p);
         tc_unscale = ldexp(1.0, -20);
-        cudaStreamSynchronize(c->stream);
         opB.free_all();
         opA.free_all();
         if (st != CRX_OK) return st;

@@ -13,8 +13,9 @@ struct Segments {
     int32_t* off = nullptr;  // [nkeys + 1]
     int64_t n = 0;
     int nkeys = 0;
+    crx_ctx* owner = nullptr;
     void free_all() {
-        cudaFree(perm); cudaFree(sorted); cudaFree(off);
+        if (owner) { crx_free(owner, perm); crx_free(owner, sorted); crx_free(owner, off); }
         perm = sorted = off = nullptr;
     }
 };

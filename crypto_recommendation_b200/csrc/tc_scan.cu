@@ -1,12 +1,12 @@
 // tc_scan.cu -- tcgen05 / TMEM / TMA pair-scan engine for sm_100a (see tc_scan.cuh).
 //
 // One CTA = 128 rows of A ("queries" / "points"), resident in shared memory (TMA, 128B swizzle), against
-// ALL 128-column tiles of B streamed through a 4-stage TMA ring.  Warp 0 = TMA producer (one elected
-// lane), warp 1 = tcgen05.mma issuer (one elected lane; also owns the TMEM allocation), warps 2..5 =
-// epilogue: each thread owns ONE row of the 128x128 fp32 accumulator tile (tcgen05.ld 32x32b), so the
-// per-row reductions (masked top-64 list / best + second best) are thread-private -- no shuffles, no
-// atomics.  The accumulator is double-buffered in TMEM (2 x 128 columns) so that the MMAs of tile t+1
-// overlap the epilogue of tile t.
+// ALL 128-column tiles of B streamed through a 5-stage TMA ring.  Warp 0 = TMA producer (one elected
+// lane), warp 1 = tcgen05.mma issuer (one elected lane; also owns the TMEM allocation), warps 2..9 =
+// epilogue: each thread owns ONE row x ONE 64-column half of the 128x128 fp32 accumulator tile
+// (tcgen05.ld 32x32b), so the per-row reductions (masked top-32 list per half / best + second best) are
+// thread-private -- no shuffles, no atomics.  The accumulator is double-buffered in TMEM (2 x 128 columns)
+// so that the MMAs of tile t+1 overlap the epilogue of tile t.
 //
 // Split-fp16 arithmetic: every operand row is stored as [hi blocks | lo blocks] with hi = fp16(v),
 // lo = fp16(v - hi).  For each B block the issuer runs
@@ -22,9 +22,10 @@
 namespace {
 
 constexpr int TM = 128;            // rows per CTA
-constexpr int TN = 128;            // columns per tile
-constexpr int BLK_BYTES = TM * 64 * 2;  // one 128-row x 64-col fp16 block = 16 KB
-constexpr int NS = 5;              // B ring stages
+constexpr int TN = 256;            // columns per tile (UMMA N = 256: A 4 KB + B 8 KB of smem reads per 128-cycle MMA)
+constexpr int BLK_BYTES = TM * 64 * 2;   // one 128-row x 64-col fp16 block of A = 16 KB
+constexpr int BBLK_BYTES = TN * 64 * 2;  // one 256-row x 64-col fp16 block of B = 32 KB
+constexpr int NS = 3;              // B ring stages
 constexpr uint32_t IDESC = (1u << 4) /* D = F32 */ | (0u << 7) /* A = F16 */ | (0u << 10) /* B = F16 */ |
                            ((uint32_t)(TN >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);  // K-major A and B
 
@@ -81,13 +82,15 @@ __device__ __forceinline__ uint64_t smem_desc(uint32_t addr) {
     return (uint64_t)((addr & 0x3FFFF) >> 4) | (1ull << 16) /* LBO (ignored) */ | (64ull << 32) /* SBO = 1024 B */ |
            (1ull << 46) /* version */ | (2ull << 61) /* SWIZZLE_128B */;
 }
-// four K=16 MMAs over one 64-column block; descriptors advance by 32 bytes (>> 4 = 2)
-__device__ __forceinline__ void mma_block(uint32_t tmem_d, uint32_t a_addr, uint32_t b_addr, uint32_t acc_first) {
+// up to four K=16 MMAs over one 64-column block; descriptors advance by 32 bytes (>> 4 = 2).  `steps` < 4
+// skips the all-zero padding columns of the last block (D = 100 needs 7 of the 8 K=16 slices).
+__device__ __forceinline__ void mma_block(uint32_t tmem_d, uint32_t a_addr, uint32_t b_addr, uint32_t acc_first, int steps) {
     uint64_t ad = smem_desc(a_addr), bd = smem_desc(b_addr);
 #pragma unroll
-    for (int k = 0; k < 4; k++) tc_mma(tmem_d, ad + 2 * k, bd + 2 * k, k == 0 ? acc_first : 1u);
+    for (int k = 0; k < 4; k++)
+        if (k < steps) tc_mma(tmem_d, ad + 2 * k, bd + 2 * k, k == 0 ? acc_first : 1u);
 }
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+__device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t (&r)[32]) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
         "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
@@ -97,13 +100,13 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
           "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
           "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
         : "r"(taddr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
 struct TcParams {
     int64_t q0, nq;   // rows of A handled by the grid: [q0, q0 + nq)
     int64_t nb;       // valid rows of B
     int ntiles, nkb;
+    int last_steps;   // K=16 slices of the last 64-column block that hold data
     // top-P
     const uint32_t* qcode;
     const uint32_t* ccode;
@@ -119,29 +122,40 @@ struct TcParams {
 
 constexpr int MODE_TOPP = 0, MODE_ARGMIN = 1;
 constexpr int HL = TC_LIST / 2;   // entries of one half-list (each epilogue half keeps its own top-HL)
-constexpr int LSTRIDE = HL + 4;   // padded row stride (floats): 16-byte aligned rows, conflict-free quarter-warps
+
+// r[j] for a run-time j: 5-level select tree (registers cannot be indexed dynamically)
+__device__ __forceinline__ uint32_t pick32(const uint32_t (&r)[32], int j) {
+    uint32_t a[16], b[8], c[4], d[2];
+#pragma unroll
+    for (int i = 0; i < 16; i++) a[i] = (j & 1) ? r[2 * i + 1] : r[2 * i];
+#pragma unroll
+    for (int i = 0; i < 8; i++) b[i] = (j & 2) ? a[2 * i + 1] : a[2 * i];
+#pragma unroll
+    for (int i = 0; i < 4; i++) c[i] = (j & 4) ? b[2 * i + 1] : b[2 * i];
+#pragma unroll
+    for (int i = 0; i < 2; i++) d[i] = (j & 8) ? c[2 * i + 1] : c[2 * i];
+    return (j & 16) ? d[1] : d[0];
+}
 
 // Replace the smallest entry of the row's (full) list, or append while it is filling, then recompute
-// the threshold = smallest kept score.  Rare path (~HL*ln(N/HL) times per row): kept out of line.
-__device__ __noinline__ void list_insert(float* ls, int32_t* li, float s, int32_t idx, int& cnt, float& thr, int& minpos) {
+// the threshold = smallest kept score.  Rare path (~HL*ln(N/HL) times per row).
+__device__ __forceinline__ void list_insert(float* ls, int32_t* li, float s, int32_t idx, int& cnt, float& thr, int& minpos) {
+    // ls / li point at this thread's column of the [entry][row] arrays: entry e lives at e * TM
     if (cnt < HL) {
-        ls[cnt] = s;
-        li[cnt] = idx;
+        ls[cnt * TM] = s;
+        li[cnt * TM] = idx;
         cnt++;
         if (cnt < HL) return;
     } else {
-        ls[minpos] = s;
-        li[minpos] = idx;
+        ls[minpos * TM] = s;
+        li[minpos * TM] = idx;
     }
     float m = INFINITY;
     int mp = 0;
 #pragma unroll
-    for (int e = 0; e < HL; e += 4) {
-        float4 v = *reinterpret_cast<const float4*>(ls + e);
-        if (v.x < m) { m = v.x; mp = e; }
-        if (v.y < m) { m = v.y; mp = e + 1; }
-        if (v.z < m) { m = v.z; mp = e + 2; }
-        if (v.w < m) { m = v.w; mp = e + 3; }
+    for (int e = 0; e < HL; e++) {
+        float v = ls[e * TM];
+        if (v < m) { m = v; mp = e; }
     }
     thr = m;
     minpos = mp;
@@ -150,17 +164,20 @@ __device__ __noinline__ void list_insert(float* ls, int32_t* li, float s, int32_
 constexpr int NEPI = 8;                       // epilogue warps: two per TMEM lane quarter
 constexpr int NTHREADS_K = 64 + NEPI * 32;    // + producer warp + MMA warp
 
-template <int MODE>
+// DENSE (top-P only): nearly every column shares a bucket with every row (f = mean|cand|/N close to 1), so the
+// hot loop only tracks the running maximum of the raw scores (1 FMNMX per score) and the table mask is
+// evaluated in the rare path; otherwise the mask is applied before the maximum (5 instructions per score).
+template <int MODE, bool DENSE>
 __global__ void __launch_bounds__(NTHREADS_K, 1)
 tc_scan_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, TcParams p) {
     extern __shared__ __align__(1024) uint8_t smem[];
     const int nblk = 2 * p.nkb;
     uint8_t* sA = smem;                                    // nblk blocks (<= 64 KB), resident
-    uint8_t* sB = smem + 4 * BLK_BYTES;                    // NS-stage ring
-    float* ls = reinterpret_cast<float*>(smem + (4 + NS) * BLK_BYTES);   // [2 halves][TM][LSTRIDE]  (top-P only)
-    int32_t* li = reinterpret_cast<int32_t*>(ls + 2 * TM * LSTRIDE);
-    uint32_t* stile = MODE == MODE_TOPP ? reinterpret_cast<uint32_t*>(li + 2 * TM * LSTRIDE)
-                                        : reinterpret_cast<uint32_t*>(smem + (4 + NS) * BLK_BYTES);  // [2][TN] codes / half norms
+    uint8_t* sB = smem + 4 * BLK_BYTES;                    // NS-stage ring of 32 KB blocks
+    float* ls = reinterpret_cast<float*>(smem + 4 * BLK_BYTES + NS * BBLK_BYTES);   // [2 halves][HL][TM]  (top-P only)
+    int32_t* li = reinterpret_cast<int32_t*>(ls + 2 * HL * TM);
+    uint32_t* stile = MODE == MODE_TOPP ? reinterpret_cast<uint32_t*>(li + 2 * HL * TM)
+                                        : reinterpret_cast<uint32_t*>(smem + 4 * BLK_BYTES + NS * BBLK_BYTES);  // [2][TN] codes / half norms
     uint64_t* bars = reinterpret_cast<uint64_t*>(stile + 2 * TN);
     uint64_t* a_full = bars;
     uint64_t* full = bars + 1;
@@ -179,7 +196,7 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         fence_barrier_init();
     }
     if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(256u) : "memory");
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     tc_fence_before();
@@ -198,8 +215,8 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             for (int t = 0; t < p.ntiles; t++) {
                 for (int b = 0; b < nblk; b++) {
                     mbar_wait(&empty[stage], phase ^ 1);
-                    mbar_arrive_expect_tx(&full[stage], (uint32_t)BLK_BYTES);
-                    tma_load_2d(sB + stage * BLK_BYTES, &tmB, b * 64, t * TN, &full[stage]);
+                    mbar_arrive_expect_tx(&full[stage], (uint32_t)BBLK_BYTES);
+                    tma_load_2d(sB + stage * BBLK_BYTES, &tmB, b * 64, t * TN, &full[stage]);
                     if (++stage == NS) { stage = 0; phase ^= 1; }
                 }
             }
@@ -217,16 +234,18 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 const uint32_t bphase = (uint32_t)(t >> 1) & 1u;
                 mbar_wait(&tempty[buf], bphase ^ 1);
                 tc_fence_after();
-                const uint32_t d = tmem_base + (uint32_t)(buf * TN);
+                const uint32_t d = tmem_base + (uint32_t)(buf * TN);  // 256 fp32 columns per buffer
                 for (int b = 0; b < nblk; b++) {
                     mbar_wait(&full[stage], phase);
                     tc_fence_after();
-                    const uint32_t bs = b_base + stage * BLK_BYTES;
-                    if (b < p.nkb) {  // B.hi_b with A.hi_b and A.lo_b
-                        mma_block(d, a_base + b * BLK_BYTES, bs, b == 0 ? 0u : 1u);
-                        mma_block(d, a_base + (p.nkb + b) * BLK_BYTES, bs, 1u);
+                    const uint32_t bs = b_base + stage * BBLK_BYTES;
+                    const int j = b < p.nkb ? b : b - p.nkb;                 // 64-column block index inside a part
+                    const int steps = j == p.nkb - 1 ? p.last_steps : 4;
+                    if (b < p.nkb) {  // B.hi_j with A.hi_j and A.lo_j
+                        mma_block(d, a_base + j * BLK_BYTES, bs, b == 0 ? 0u : 1u, steps);
+                        mma_block(d, a_base + (p.nkb + j) * BLK_BYTES, bs, 1u, steps);
                     } else {          // B.lo_j with A.hi_j
-                        mma_block(d, a_base + (b - p.nkb) * BLK_BYTES, bs, 1u);
+                        mma_block(d, a_base + j * BLK_BYTES, bs, 1u, steps);
                     }
                     tc_commit(&empty[stage]);
                     if (++stage == NS) { stage = 0; phase ^= 1; }
@@ -239,68 +258,97 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int ew = warp - 2;                 // 0..7
         const int etid = threadIdx.x - 64;       // 0..255
         const int quarter = warp & 3;            // TMEM lane quarter this warp may read
-        const int half = ew >> 2;                // columns [64*half, 64*half + 64) of every tile
+        const int half = ew >> 2;                // columns [128*half, 128*half + 128) of every tile
         const int me = quarter * 32 + lane;      // row inside the tile
         const int64_t grow = (int64_t)blockIdx.x * TM + me;  // row relative to q0
         const bool valid = grow < p.nq;
         uint32_t cq = 0;
         float thr = -INFINITY, best = INFINITY, second = INFINITY;
         int cnt = 0, minpos = 0, bidx = 0x7fffffff;
-        float* myls = ls + (half * TM + me) * LSTRIDE;
-        int32_t* myli = li + (half * TM + me) * LSTRIDE;
+        float* myls = ls + half * HL * TM + me;
+        int32_t* myli = li + half * HL * TM + me;
         if (MODE == MODE_TOPP) {
             if (valid) cq = p.qcode[p.q0 + grow];
-            for (int e = 0; e < HL; e++) { myls[e] = -INFINITY; myli[e] = -1; }
+            for (int e = 0; e < HL; e++) { myls[e * TM] = -INFINITY; myli[e * TM] = -1; }
         }
         const uint32_t low = p.low_mask, high = p.high_mask;
+        // staging value (packed code / half norm) of this thread's column of the NEXT tile, fetched one tile ahead
+        auto fetch_col = [&](int t) -> uint32_t {
+            int64_t col = (int64_t)t * TN + etid;
+            if (t >= p.ntiles) return 0u;
+            if (MODE == MODE_TOPP) return col < p.nb ? p.ccode[col] : 0u;
+            return __float_as_uint(col < p.nb ? p.half_norm[col] : INFINITY);
+        };
+        uint32_t next_col = fetch_col(0);
         for (int t = 0; t < p.ntiles; t++) {
             const int buf = t & 1;
             const uint32_t bphase = (uint32_t)(t >> 1) & 1u;
-            if (etid < TN) {
-                int64_t col = (int64_t)t * TN + etid;
-                uint32_t v;
-                if (MODE == MODE_TOPP) v = col < p.nb ? p.ccode[col] : 0u;
-                else v = __float_as_uint(col < p.nb ? p.half_norm[col] : INFINITY);
-                stile[buf * TN + etid] = v;
-            }
+            stile[buf * TN + etid] = next_col;
+            next_col = fetch_col(t + 1);
             asm volatile("bar.sync 1, 256;" ::: "memory");
             mbar_wait(&tfull[buf], bphase);
             tc_fence_after();
-            const uint32_t taddr = tmem_base + (uint32_t)(buf * TN + half * 64) + ((uint32_t)(quarter * 32) << 16);
+            const uint32_t taddr = tmem_base + (uint32_t)(buf * TN + half * 128) + ((uint32_t)(quarter * 32) << 16);
+            // this thread's 128 columns in two rounds of two 32-column chunks; the TMEM buffer is handed back as
+            // soon as the second round sits in registers
 #pragma unroll 1
+            for (int rnd = 0; rnd < 2; rnd++) {
+            uint32_t r0[32], r1[32];
+            tmem_ld32_nowait(taddr + rnd * 64, r0);
+            tmem_ld32_nowait(taddr + rnd * 64 + 32, r1);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            if (rnd == 1) {
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tempty[buf]);
+            }
+#pragma unroll
             for (int ch = 0; ch < 2; ch++) {
-                uint32_t r[32];
-                tmem_ld32(taddr + ch * 32, r);
-                if (ch == 1) {  // this warp's part of the tile is in registers: hand the TMEM buffer back
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&tempty[buf]);
-                }
-                const uint4* st4 = reinterpret_cast<const uint4*>(stile + buf * TN + half * 64 + ch * 32);
-                const int cbase = t * TN + half * 64 + ch * 32;
+                uint32_t (&r)[32] = ch == 0 ? r0 : r1;
+                const uint4* st4 = reinterpret_cast<const uint4*>(stile + buf * TN + half * 128 + rnd * 64 + ch * 32);
+                const int cbase = t * TN + half * 128 + rnd * 64 + ch * 32;
                 if (MODE == MODE_TOPP) {
-                    // branch-free pass: bit j = "column j shares a table bucket with this row AND beats the threshold"
-                    uint32_t bits = 0;
+                    // hot loop: running maximum of the (masked) scores, four independent chains
+                    float vm[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+                    if (DENSE) {
 #pragma unroll
-                    for (int g = 0; g < 8; g++) {
-                        uint4 cc = st4[g];
-                        uint32_t c4[4] = {cc.x, cc.y, cc.z, cc.w};
+                        for (int j = 0; j < 32; j++) vm[j & 3] = fmaxf(vm[j & 3], __uint_as_float(r[j]));
+                    } else {
 #pragma unroll
-                        for (int u = 0; u < 4; u++) {
-                            uint32_t x = cq ^ c4[u];
-                            uint32_t m = (x - low) & ~x & high;  // some k-bit field of x is zero
-                            bool pass = (m != 0u) && (__uint_as_float(r[g * 4 + u]) > thr);
-                            bits |= pass ? (1u << (g * 4 + u)) : 0u;
+                        for (int g = 0; g < 8; g++) {
+                            uint4 cc = st4[g];
+                            uint32_t c4[4] = {cc.x, cc.y, cc.z, cc.w};
+#pragma unroll
+                            for (int u = 0; u < 4; u++) {
+                                uint32_t x = cq ^ c4[u];
+                                uint32_t m = (x - low) & ~x & high;  // some k-bit field of x is zero
+                                vm[u] = fmaxf(vm[u], m != 0u ? __uint_as_float(r[g * 4 + u]) : -INFINITY);
+                            }
                         }
                     }
-                    if (bits != 0u && valid) {
+                    if (fmaxf(fmaxf(vm[0], vm[1]), fmaxf(vm[2], vm[3])) > thr && valid) {
+                        // rare path: which columns share a table bucket with this row AND beat the threshold
+                        uint32_t bits = 0;
 #pragma unroll
-                        for (int j = 0; j < 32; j++) {
-                            if (bits & (1u << j)) {
-                                float s = __uint_as_float(r[j]);
-                                int c = cbase + j;
-                                if (s > thr && c < p.nb) list_insert(myls, myli, s, c, cnt, thr, minpos);
+                        for (int g = 0; g < 8; g++) {
+                            uint4 cc = st4[g];
+                            uint32_t c4[4] = {cc.x, cc.y, cc.z, cc.w};
+#pragma unroll
+                            for (int u = 0; u < 4; u++) {
+                                uint32_t x = cq ^ c4[u];
+                                uint32_t m = (x - low) & ~x & high;
+                                bool pass = (m != 0u) & (__uint_as_float(r[g * 4 + u]) > thr);
+                                bits |= pass ? (1u << (g * 4 + u)) : 0u;
                             }
+                        }
+                        // lane-local loop over the set bits: all lanes that have a candidate in this chunk walk
+                        // it TOGETHER, so one pass of the insertion code serves the whole warp
+                        while (bits != 0u) {
+                            const int j = __ffs(bits) - 1;
+                            bits &= bits - 1u;
+                            const float s = __uint_as_float(pick32(r, j));
+                            const int c = cbase + j;
+                            if (s > thr && c < p.nb) list_insert(myls, myli, s, c, cnt, thr, minpos);
                         }
                     }
                 } else {
@@ -319,12 +367,13 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     }
                 }
             }
+            }
         }
         if (MODE == MODE_TOPP) {
             if (valid) {
                 for (int e = 0; e < HL; e++) {
-                    p.list_s[grow * TC_LIST + half * HL + e] = myls[e];
-                    p.list_i[grow * TC_LIST + half * HL + e] = myli[e];
+                    p.list_s[grow * TC_LIST + half * HL + e] = myls[e * TM];
+                    p.list_i[grow * TC_LIST + half * HL + e] = myli[e * TM];
                 }
             }
         } else {
@@ -345,7 +394,7 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     __syncthreads();
     if (warp == 1) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256u) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
     }
 }
 
@@ -376,7 +425,7 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-int make_tensor_map(const TcOperand& op, CUtensorMap* tm) {
+int make_tensor_map(const TcOperand& op, int box_rows, CUtensorMap* tm) {
     static EncodeTiledFn fn = nullptr;
     if (!fn) {
         void* ptr = nullptr;
@@ -391,7 +440,7 @@ int make_tensor_map(const TcOperand& op, CUtensorMap* tm) {
     cuuint64_t cols = (cuuint64_t)op.nkb * 2 * 64;
     cuuint64_t gdim[2] = {cols, (cuuint64_t)op.rows_pad};
     cuuint64_t gstride[1] = {cols * sizeof(__half)};
-    cuuint32_t box[2] = {64, (cuuint32_t)TM};
+    cuuint32_t box[2] = {64, (cuuint32_t)box_rows};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, op.data, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -403,21 +452,25 @@ int make_tensor_map(const TcOperand& op, CUtensorMap* tm) {
 }
 
 size_t smem_for(int mode) {
-    size_t s = (size_t)(4 + NS) * BLK_BYTES + 2 * TN * 4 + (1 + 2 * NS + 4) * 8 + 16 + TM * 3 * 4;
-    if (mode == MODE_TOPP) s += (size_t)2 * TM * LSTRIDE * 8;
+    size_t s = (size_t)4 * BLK_BYTES + (size_t)NS * BBLK_BYTES + 2 * TN * 4 + (1 + 2 * NS + 4) * 8 + 16;
+    if (mode == MODE_TOPP) s += (size_t)2 * HL * TM * 8;
+    else s += TM * 3 * 4;
     return s;
 }
 
+int last_steps_of(const TcOperand& op) {
+    int rem = op.d - 64 * (op.nkb - 1);
+    return (rem + 15) / 16;
+}
+
 int alloc_operand(crx_ctx* c, int64_t rows, int D, TcOperand* out) {
+    out->d = D;
     out->rows = rows;
     out->rows_pad = (rows + TM - 1) / TM * TM;
     out->nkb = D <= 64 ? 1 : 2;
     size_t bytes = (size_t)out->rows_pad * out->nkb * 2 * 64 * sizeof(__half);
-    cudaError_t e = cudaMalloc(&out->data, bytes);
-    if (e != cudaSuccess) {
-        crx_set_error("tensor operand: cudaMalloc(%zu) -> %s", bytes, cudaGetErrorString(e));
-        return CRX_ERR_NOMEM;
-    }
+    out->owner = c;
+    CRX_TRY(crx_alloc(c, (char**)&out->data, bytes));
     CRX_CUDA(cudaMemsetAsync(out->data, 0, bytes, c->stream));
     return CRX_OK;
 }
@@ -449,25 +502,31 @@ int crx_tc_prepare_matrix(crx_ctx* c, const double* m, int K, int D, int ld, dou
 }
 
 int crx_tc_topp(crx_ctx* c, const TcOperand& A, int64_t q0, int64_t nq, const TcOperand& B, const uint32_t* qcode,
-                const uint32_t* ccode, int k, int L, float* list_s, int32_t* list_i) {
+                const uint32_t* ccode, int k, int L, bool dense, float* list_s, int32_t* list_i) {
     CRX_REQUIRE(A.nkb == B.nkb, "operand widths differ");
     CRX_REQUIRE(k * L <= 32 && k >= 1, "packed codes need k*L <= 32");
     CUtensorMap tmA, tmB;
-    CRX_TRY(make_tensor_map(A, &tmA));
-    CRX_TRY(make_tensor_map(B, &tmB));
+    CRX_TRY(make_tensor_map(A, TM, &tmA));
+    CRX_TRY(make_tensor_map(B, TN, &tmB));
     TcParams p;
     memset(&p, 0, sizeof(p));
     p.q0 = q0; p.nq = nq; p.nb = B.rows; p.ntiles = (int)((B.rows + TN - 1) / TN); p.nkb = A.nkb;
+    p.last_steps = last_steps_of(A);
     p.qcode = qcode; p.ccode = ccode;
     uint32_t low = 0, high = 0;
     for (int l = 0; l < L; l++) { low |= 1u << (l * k); high |= 1u << (l * k + k - 1); }
     p.low_mask = low; p.high_mask = high;
     p.list_s = list_s; p.list_i = list_i;
     size_t smem = smem_for(MODE_TOPP);
-    CRX_CUDA(cudaFuncSetAttribute(tc_scan_kernel<MODE_TOPP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int grid = (int)((nq + TM - 1) / TM);
     CRX_KERNEL(c, "tc_topp_scan");
-    tc_scan_kernel<MODE_TOPP><<<grid, NTHREADS_K, smem, c->stream>>>(tmA, tmB, p);
+    if (dense) {
+        CRX_CUDA(cudaFuncSetAttribute(tc_scan_kernel<MODE_TOPP, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        tc_scan_kernel<MODE_TOPP, true><<<grid, NTHREADS_K, smem, c->stream>>>(tmA, tmB, p);
+    } else {
+        CRX_CUDA(cudaFuncSetAttribute(tc_scan_kernel<MODE_TOPP, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        tc_scan_kernel<MODE_TOPP, false><<<grid, NTHREADS_K, smem, c->stream>>>(tmA, tmB, p);
+    }
     CRX_CUDA(cudaGetLastError());
     return CRX_OK;
 }
@@ -476,17 +535,18 @@ int crx_tc_argmin(crx_ctx* c, const TcOperand& A, int64_t r0, int64_t nr, const 
                   float* best, float* second, int32_t* best_idx) {
     CRX_REQUIRE(A.nkb == B.nkb, "operand widths differ");
     CUtensorMap tmA, tmB;
-    CRX_TRY(make_tensor_map(A, &tmA));
-    CRX_TRY(make_tensor_map(B, &tmB));
+    CRX_TRY(make_tensor_map(A, TM, &tmA));
+    CRX_TRY(make_tensor_map(B, TN, &tmB));
     TcParams p;
     memset(&p, 0, sizeof(p));
     p.q0 = r0; p.nq = nr; p.nb = B.rows; p.ntiles = (int)((B.rows + TN - 1) / TN); p.nkb = A.nkb;
+    p.last_steps = last_steps_of(A);
     p.half_norm = half_norm; p.best = best; p.second = second; p.best_idx = best_idx;
     size_t smem = smem_for(MODE_ARGMIN);
-    CRX_CUDA(cudaFuncSetAttribute(tc_scan_kernel<MODE_ARGMIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CRX_CUDA(cudaFuncSetAttribute(tc_scan_kernel<MODE_ARGMIN, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int grid = (int)((nr + TM - 1) / TM);
     CRX_KERNEL(c, "tc_argmin_scan");
-    tc_scan_kernel<MODE_ARGMIN><<<grid, NTHREADS_K, smem, c->stream>>>(tmA, tmB, p);
+    tc_scan_kernel<MODE_ARGMIN, false><<<grid, NTHREADS_K, smem, c->stream>>>(tmA, tmB, p);
     CRX_CUDA(cudaGetLastError());
     return CRX_OK;
 }

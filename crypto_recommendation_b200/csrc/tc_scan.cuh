@@ -15,8 +15,10 @@ struct TcOperand {
     void* data = nullptr;     // __half [rows_pad][nkb*2*64]
     int64_t rows = 0, rows_pad = 0;
     int nkb = 0;              // 64-column blocks per part (1 for D <= 64, 2 for D <= 128)
+    int d = 0;                // true number of columns
     double scale_log2 = 0;    // values were multiplied by 2^scale_log2 before the split
-    void free_all() { cudaFree(data); data = nullptr; }
+    crx_ctx* owner = nullptr;
+    void free_all() { if (owner) crx_free(owner, data); data = nullptr; }
 };
 
 // mode 0: rows scaled to unit length times 2^10 (cosine);  mode 1: all rows times 2^scale_log2
@@ -29,8 +31,9 @@ constexpr int TC_LIST = 64;  // per-row candidate list of the top-P filter
 // top-P filter: for query rows [q0, q0+nq) of A against all rows of B, keep the TC_LIST best scores among
 // the columns whose packed code shares at least one k-bit field with the query's code.
 //   list_s[nq][TC_LIST] (float, scaled by 2^(sa+sb)), list_i[nq][TC_LIST] (column, -1 = empty)
+// dense: the caller knows that (nearly) every column is a candidate of every row (mean |cand| / N > 0.9)
 int crx_tc_topp(crx_ctx* c, const TcOperand& A, int64_t q0, int64_t nq, const TcOperand& B, const uint32_t* qcode,
-                const uint32_t* ccode, int k, int L, float* list_s, int32_t* list_i);
+                const uint32_t* ccode, int k, int L, bool dense, float* list_s, int32_t* list_i);
 
 // argmin filter: for rows [r0, r0+nr) of A against the K rows of B: best / second-best of
 // half_norm[j] - dot(a, b_j) (scaled units) and the best column.
