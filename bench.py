@@ -307,21 +307,29 @@ def run_crx(args):
         ctx.profile_reset(); ctx.profile(True)
         step_kmeans(); torch.cuda.synchronize(dev)
         ctx.profile(False)
-        breakdown = {k: round(ctx.kernel_time(k)[0], 3) for k in ("lloyd_scan", "chunk_sums", "combine_sums", "kmeans_finish", "select_centroids", "bucket_offsets", "iota", "pad_centroids")}
+        breakdown = {k: round(ctx.kernel_time(k)[0], 3) for k in ("tc_argmin_scan", "lloyd_refine", "lloyd_scan", "tc_prep", "maxabs", "half_norm", "chunk_sums",
+                                                                   "combine_sums", "kmeans_finish", "select_centroids", "bucket_offsets", "iota", "pad_centroids")}
         ctx.profile_reset(); ctx.profile(True)
         for _ in range(args.steps):
             step_assign()
         torch.cuda.synchronize(dev)
         ctx.profile(False)
-        lk_ms, lk_n = ctx.kernel_time("lloyd_scan")
+        ltc = ctx.kernel_time("tc_argmin_scan")[1] > 0
+        lk_ms, lk_n = ctx.kernel_time("tc_argmin_scan" if ltc else "lloyd_scan")
+        lr_ms, _ = ctx.kernel_time("lloyd_refine")
+        lfac = 3.0 * (16 * ((dd + 15) // 16)) / dd
         fl = 2.0 * dd * npts * kk
         lloyd = {"metric": "Lloyd assign pts*centroids/s", "value": world * npts * kk / (a_ms / 1e3), "unit": "pts*centroids/s",
                  "ms_per_step": a_ms, "kmeans_iteration_ms": k_ms, "kmeans_kernel_ms": breakdown, "scaling": "weak",
                  "config": {"workload": "C4 shard: %d x %d fp32 points per GPU, K=%d, euclidean; bit-exact FP64 distances" % (npts, dd, kk)},
-                 "roofline": {"kernel": "lloyd_scan_kernel", "bound": "tensor", "achieved": fl / (lk_ms / max(1, lk_n) * 1e-3) / 1e12,
+                 "roofline": {"kernel": "tc_scan_kernel<ARGMIN> (tcgen05 split-fp16 filter) + lloyd_refine_kernel (exact FP64 distance of the winner)" if ltc else "lloyd_scan_kernel (FP64 SIMT)",
+                              "bound": "tensor", "achieved": fl / (lk_ms / max(1, lk_n) * 1e-3) / 1e12,
                               "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
                               "frac": fl / (lk_ms / max(1, lk_n) * 1e-3) / 1e12 / peaks["bf16_tflops"], "traffic": None,
-                              "pipe": "FP64 SIMT (sub, mul, add per element: 3 FP64 ops for the 2 algorithmic flops)",
+                              "executed_tensor_tflops": fl * lfac / (lk_ms / max(1, lk_n) * 1e-3) / 1e12 if ltc else None,
+                              "pipe": ("tcgen05.mma kind::f16, 3 split-fp16 products (%.2fx algorithmic flops), then exact FP64 refine" % lfac) if ltc
+                                      else "FP64 SIMT (sub, mul, add per element: 3 FP64 ops for the 2 algorithmic flops)",
+                              "scan_ms": lk_ms / max(1, lk_n), "refine_ms": lr_ms / max(1, lk_n),
                               "hbm_floor_ms": npts * (4 * dd + 12) / (peaks["hbm_gbs"] * 1e6)}}
         Q.close()
 

@@ -10,6 +10,7 @@
 #include "pair_tile.cuh"
 #include "rowwalk.cuh"
 #include "tables.cuh"
+#include "tc_scan.cuh"
 
 void crx_cube_probe_sequence(int home, int probes, int k, std::vector<int>& seq);  // hash.cu
 
@@ -190,6 +191,181 @@ static int lloyd_scan(crx_ctx* c, const crx_points* p, const int32_t* d_rowmap, 
     else { if (metric == CRX_EUCLIDEAN) LAUNCH_L(float, CRX_EUCLIDEAN, p->x32); else LAUNCH_L(float, CRX_COSINE, p->x32); }
 #undef LAUNCH_L
     CRX_CUDA(cudaGetLastError());
+    return CRX_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K5 on the tensor cores (Euclidean, K >= 32): tc_scan's argmin filter gives, per point, the best and the
+// second-best value of  0.5 ||c||^2 - x.c  from split-fp16 products.  A point whose margin exceeds twice
+// the filter's error bound keeps the filter's label (its distance is then computed exactly, as the
+// reference does); the others -- near-ties and exact ties -- are re-scanned by the exact FP64 kernel, so
+// labels and distances stay bit-identical to the reference.
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void maxabs_kernel(const T* __restrict__ x, size_t n, unsigned int* __restrict__ out) {
+    float m = 0.f;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) m = fmaxf(m, fabsf((float)x[i]));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0) atomicMax(out, __float_as_uint(m));  // non-negative floats order like their bit patterns
+}
+
+__global__ void half_norm_kernel(const double* __restrict__ csqn, int K, double scale, float* __restrict__ hn, unsigned int* __restrict__ cmax_bits) {
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= K) return;
+    hn[c] = (float)(0.5 * csqn[c] * scale);
+    atomicMax(cmax_bits, __float_as_uint((float)sqrt(csqn[c]) * 1.000001f));
+}
+
+// One warp = 32 consecutive points.  The point rows are staged 32 x 16 through shared memory (coalesced
+// 64-byte reads), each lane then walks ITS row in index order against the row of ITS winning centroid
+// (128 contiguous bytes per 16 coordinates, L2 resident): the reference's own sequence of operations.
+template <typename T>
+__global__ void __launch_bounds__(256)
+lloyd_refine_kernel(const T* __restrict__ x, int ld, int D, const double* __restrict__ sqn, int64_t N, const double* __restrict__ cent,
+                    const float* __restrict__ best, const float* __restrict__ second, const int32_t* __restrict__ bidx, int K,
+                    double scale, const unsigned int* __restrict__ cmax_bits, int32_t* __restrict__ labels, double* __restrict__ dists,
+                    int32_t* __restrict__ amb_rows, int* __restrict__ amb_count) {
+    __shared__ rw::WarpTile tiles[8];
+    int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    int64_t row0 = ((int64_t)blockIdx.x * 8 + warp) * 32;
+    if (row0 >= N) return;
+    int64_t i = row0 + lane;
+    bool valid = i < N;
+    double cmax = (double)__uint_as_float(*cmax_bits);
+    double xn = valid ? sqrt(sqn[i]) : 0.0;
+    // |filter value - true value| <= E (scaled units): split + dropped lo*lo (3 * 2^-22), fp32 accumulation over
+    // 21 K-slices (21 * 2^-23, truncation assumed), fp32 rounding of the half norm and of the subtraction
+    double E = scale * (6e-6 * xn * cmax + 2.5e-7 * (0.5 * cmax * cmax + xn * cmax));
+    int b = valid ? bidx[i] : 0;
+    double margin = valid ? (double)second[i] - (double)best[i] : 0.0;
+    bool sure = valid && b >= 0 && b < K && margin > 2.0 * E;
+    const double* crow = cent + (size_t)(sure ? b : 0) * ld;
+    double acc = 0.0;
+    for (int c0 = 0; c0 < D; c0 += 16) {
+#pragma unroll 4
+        for (int it = 0; it < 16; it++) {
+            int r = it * 2 + (lane >> 4);
+            int64_t src = row0 + r;
+            int col = c0 + (lane & 15);
+            tiles[warp][r][lane & 15] = (src < N && col < D) ? (double)x[src * ld + col] : 0.0;
+        }
+        __syncwarp();
+        double cv[16];
+#pragma unroll
+        for (int k = 0; k < 16; k += 2) {  // ld is a multiple of 4 and the padding holds zeros
+            double2 v = (c0 + k < ld) ? *reinterpret_cast<const double2*>(crow + c0 + k) : make_double2(0.0, 0.0);
+            cv[k] = v.x; cv[k + 1] = v.y;
+        }
+        int lim = min(16, D - c0);
+#pragma unroll
+        for (int k = 0; k < 16; k++) {
+            if (k < lim) {
+                double t = __dsub_rn(tiles[warp][lane][k], cv[k]);
+                acc = __dadd_rn(acc, __dmul_rn(t, t));
+            }
+        }
+        __syncwarp();
+    }
+    if (sure) {
+        labels[i] = b;
+        dists[i] = __dsqrt_rn(acc);
+    } else if (valid) {
+        amb_rows[atomicAdd(amb_count, 1)] = (int32_t)i;
+    }
+}
+
+static int points_maxabs(crx_ctx* c, const crx_points* p, double* out) {
+    if (p->maxabs < 0) {
+        DevBuf<unsigned int> m;
+        CRX_TRY(m.alloc(c, 1));
+        CRX_CUDA(cudaMemsetAsync(m.p, 0, sizeof(unsigned int), c->stream));
+        size_t n = (size_t)p->n * p->ld;
+        int g = (int)std::min<size_t>((size_t)c->sm_count * 16, (n + 255) / 256);
+        { CRX_KERNEL(c, "maxabs"); maxabs_kernel<float><<<g, 256, 0, c->stream>>>(p->x32, n, m.p); }
+        unsigned int bits = 0;
+        CRX_CUDA(cudaMemcpyAsync(&bits, m.p, sizeof(bits), cudaMemcpyDeviceToHost, c->stream));
+        CRX_CUDA(cudaStreamSynchronize(c->stream));
+        float f;
+        memcpy(&f, &bits, 4);
+        p->maxabs = (double)f;
+    }
+    *out = p->maxabs;
+    return CRX_OK;
+}
+
+static int scale_for(double maxabs) {  // 2^s * maxabs in [4096, 8192): far from fp16 overflow, lo parts stay normal
+    if (!(maxabs > 0.0) || !std::isfinite(maxabs)) return 0;
+    int e;
+    frexp(maxabs, &e);  // maxabs = m * 2^e, m in [0.5, 1)
+    return 13 - e;
+}
+
+static bool tc_disabled() {
+    static const bool off = getenv("CRX_NO_TC") != nullptr && getenv("CRX_NO_TC")[0] == '1';
+    return off;
+}
+
+static int lloyd_scan_tc(crx_ctx* c, const crx_points* p, const Centroids& cen, int32_t* d_labels, double* d_dists) {
+    int64_t N = p->n;
+    int K = cen.K, D = p->d, ld = p->ld;
+    double mx = 0;
+    CRX_TRY(points_maxabs(c, p, &mx));
+    if (!p->tc_l2) {
+        TcOperand* op = new TcOperand();
+        int sx = scale_for(mx);
+        int st = crx_tc_prepare(c, p, 1, (double)sx, op);
+        if (st != CRX_OK) { delete op; return st; }
+        p->tc_l2 = op;
+        p->tc_l2_scale = sx;
+    }
+    // centroids: scale from their own magnitude
+    DevBuf<unsigned int> cm, cmaxn;
+    CRX_TRY(cm.alloc(c, 1)); CRX_TRY(cmaxn.alloc(c, 1));
+    CRX_CUDA(cudaMemsetAsync(cm.p, 0, sizeof(unsigned int), c->stream));
+    CRX_CUDA(cudaMemsetAsync(cmaxn.p, 0, sizeof(unsigned int), c->stream));
+    { CRX_KERNEL(c, "maxabs"); maxabs_kernel<double><<<std::min(64, crx_grid((int64_t)K * ld, 256)), 256, 0, c->stream>>>(cen.pad.p, (size_t)K * ld, cm.p); }
+    unsigned int cbits = 0;
+    CRX_CUDA(cudaMemcpyAsync(&cbits, cm.p, sizeof(cbits), cudaMemcpyDeviceToHost, c->stream));
+    CRX_CUDA(cudaStreamSynchronize(c->stream));
+    float cf;
+    memcpy(&cf, &cbits, 4);
+    int sc = scale_for((double)cf), sx = p->tc_l2_scale;
+    double scale = ldexp(1.0, sx + sc);
+    TcOperand opC;
+    int st = crx_tc_prepare_matrix(c, cen.pad.p, K, D, ld, (double)sc, &opC);
+    if (st != CRX_OK) return st;
+    DevBuf<float> hn, best, second;
+    DevBuf<int32_t> bidx, amb;
+    DevBuf<int> amb_count;
+    CRX_TRY(hn.alloc(c, K)); CRX_TRY(best.alloc(c, N)); CRX_TRY(second.alloc(c, N)); CRX_TRY(bidx.alloc(c, N));
+    CRX_TRY(amb.alloc(c, N)); CRX_TRY(amb_count.alloc(c, 1));
+    CRX_CUDA(cudaMemsetAsync(amb_count.p, 0, sizeof(int), c->stream));
+    { CRX_KERNEL(c, "half_norm"); half_norm_kernel<<<crx_grid(K, 128), 128, 0, c->stream>>>(cen.sqn.p, K, scale, hn.p, cmaxn.p); }
+    st = crx_tc_argmin(c, *p->tc_l2, 0, N, opC, hn.p, best.p, second.p, bidx.p);
+    if (st == CRX_OK) {
+        CRX_KERNEL(c, "lloyd_refine");
+        int g = (int)((N + 255) / 256);
+        if (p->x64) lloyd_refine_kernel<double><<<g, 256, 0, c->stream>>>(p->x64, ld, D, p->sqn, N, cen.pad.p, best.p, second.p, bidx.p, K, scale, cmaxn.p, d_labels, d_dists, amb.p, amb_count.p);
+        else lloyd_refine_kernel<float><<<g, 256, 0, c->stream>>>(p->x32, ld, D, p->sqn, N, cen.pad.p, best.p, second.p, bidx.p, K, scale, cmaxn.p, d_labels, d_dists, amb.p, amb_count.p);
+        CRX_CUDA(cudaGetLastError());
+    }
+    int h_amb = 0;
+    CRX_CUDA(cudaMemcpyAsync(&h_amb, amb_count.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CRX_CUDA(cudaStreamSynchronize(c->stream));
+    opC.free_all();
+    if (st != CRX_OK) return st;
+    if (h_amb > 0) {
+        unsigned long long add = (unsigned long long)h_amb;
+        // exact FP64 scan of the ambiguous rows (ties included: lowest index wins there)
+        CRX_TRY(lloyd_scan(c, p, amb.p, h_amb, cen, CRX_EUCLIDEAN, d_labels, d_dists));
+        unsigned long long cur = 0;
+        CRX_CUDA(cudaMemcpyAsync(&cur, c->counters + CRX_CNT_LLOYD_EXACT, sizeof(cur), cudaMemcpyDeviceToHost, c->stream));
+        CRX_CUDA(cudaStreamSynchronize(c->stream));
+        cur += add;
+        CRX_CUDA(cudaMemcpyAsync(c->counters + CRX_CNT_LLOYD_EXACT, &cur, sizeof(cur), cudaMemcpyHostToDevice, c->stream));
+        CRX_CUDA(cudaStreamSynchronize(c->stream));
+    }
     return CRX_OK;
 }
 
@@ -775,7 +951,8 @@ int crx_lloyds_assignment(crx_ctx* c, const crx_points* p, const double* centroi
     IoBuf<double> dis;
     CRX_TRY(lab.bind(c, labels, p->n, mem, false));
     CRX_TRY(dis.bind(c, dists, p->n, mem, false));
-    CRX_TRY(lloyd_scan(c, p, nullptr, p->n, cen, metric, lab.dev, dis.dev));
+    if (metric == CRX_EUCLIDEAN && K >= 32 && p->n >= 1024 && !tc_disabled()) CRX_TRY(lloyd_scan_tc(c, p, cen, lab.dev, dis.dev));
+    else CRX_TRY(lloyd_scan(c, p, nullptr, p->n, cen, metric, lab.dev, dis.dev));
     if (crow) {
         DevBuf<int32_t> d_crow;
         CRX_TRY(d_crow.alloc(c, K));

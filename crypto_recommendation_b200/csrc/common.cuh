@@ -72,6 +72,10 @@ struct crx_points {
     double* sqn = nullptr;   // [n] sum of squares, double, index order (cust_vector.hpp:148-151)
     uint8_t* unknown = nullptr;  // [n][d]
     double* mean = nullptr;      // [n]
+    // lazily built caches of the tensor-core path (tc_scan.cuh); owned by the points object
+    mutable double maxabs = -1.0;          // max |x| over all coordinates
+    mutable struct TcOperand* tc_l2 = nullptr;   // split-fp16 rows times 2^tc_l2_scale (Euclidean scans)
+    mutable int tc_l2_scale = 0;
 };
 
 // ------------------------------------------------------------------------------------------------

@@ -2,6 +2,7 @@
 #include <cstdarg>
 
 #include "common.cuh"
+#include "tc_scan.cuh"
 
 static thread_local char g_err[1024] = "";
 
@@ -242,6 +243,7 @@ int crx_points_set_ratings(crx_points* p, const uint8_t* unknown, const double* 
 
 int crx_points_destroy(crx_points* p) {
     if (!p) return CRX_OK;
+    if (p->tc_l2) { p->tc_l2->free_all(); delete p->tc_l2; p->tc_l2 = nullptr; }
     if (p->ctx) {
         cudaSetDevice(p->ctx->device);
         crx_free(p->ctx, p->x32); crx_free(p->ctx, p->x64); crx_free(p->ctx, p->sqn); crx_free(p->ctx, p->unknown); crx_free(p->ctx, p->mean);

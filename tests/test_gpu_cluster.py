@@ -221,3 +221,32 @@ def test_full_clustering_loop_matches_oracle(ctx, port):
             rows = None
             if not cont:
                 break
+
+
+def test_lloyd_tensor_path_ties_and_margins(ctx, port):
+    # K >= 32 and N >= 1024 route the Euclidean assignment through the tcgen05 filter + exact refine.
+    # Duplicate centroids, points equidistant from two centroids and points within 1e-7 of a bisector must
+    # still come out bit-identical (the filter flags them as ambiguous and the exact FP64 scan decides).
+    rng = np.random.default_rng(9)
+    K, D, N = 48, 20, 6000
+    C = rng.normal(size=(K, D)) * 3
+    C[7] = C[3]                      # exact duplicate: the lower index must win
+    C[40] = C[41] + 1e-9             # near duplicate
+    X = C[rng.integers(0, K, N)] + rng.normal(size=(N, D)) * 0.7
+    X[:200] = 0.5 * (C[1] + C[2])    # exactly on a bisector
+    X[200:400] = 0.5 * (C[5] + C[6]) + rng.normal(size=(200, D)) * 1e-7
+    X[400:600] = C[3]                # exactly on a duplicated centroid
+    P = ctx.points(X)
+    ctx.counters(reset=True)
+    lab, dist = capi.lloyds_assignment(ctx, P, C, None, EUCLIDEAN)
+    rl, rd = port.lloyds_assignment(X, C, None, EUCLIDEAN)
+    assert np.array_equal(lab, rl), np.flatnonzero(lab != rl)[:10]
+    assert np.array_equal(dist, rd)
+    assert ctx.counters()["lloyd_exact"] >= 600
+    # float32 points, K not a multiple of the tile width, larger magnitudes
+    X32 = (X * 1000).astype(np.float32)
+    C2 = C[:37] * 1000
+    P32 = ctx.points(X32)
+    lab, dist = capi.lloyds_assignment(ctx, P32, C2, None, EUCLIDEAN)
+    rl, rd = port.lloyds_assignment(X32.astype(np.float64), C2, None, EUCLIDEAN)
+    assert np.array_equal(lab, rl) and np.array_equal(dist, rd)
