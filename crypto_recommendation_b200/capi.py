@@ -30,7 +30,7 @@ SYMBOLS = [
     "crx_rand_selection", "crx_k_means_pp", "crx_lloyds_assignment", "crx_lloyds_for_remaining",
     "crx_lsh_range_assignment", "crx_cube_range_assignment", "crx_cluster_sums", "crx_k_means_finish",
     "crx_k_means", "crx_pam_lloyds", "crx_silhouette_cluster", "crx_recommend_lsh", "crx_recommend_cluster",
-    "crx_parallel_quickSort",
+    "crx_parallel_quickSort", "crx_get_P_closest", "crx_get_top_N_recom", "crx_lsh_hash_vector",
 ]
 
 
@@ -235,6 +235,14 @@ class LshTables:
                                                   ctypes.c_int64(len(out)), ctypes.byref(cnt)))
         return out[:cnt.value].copy()
 
+    def hash_vector(self, x):
+        """CustHashtable::getHash of a vector that is not stored: (bucket_ids[L], detailed[L][k] or None)."""
+        x = _np(x, np.float64)
+        ids = np.zeros(self.L, np.int32)
+        det = np.zeros((self.L, self.k), np.int32) if self.metric == EUCLIDEAN else None
+        _check(lib().crx_lsh_hash_vector(self.h, _ptr(x)[0], _ptr(ids)[0], _ptr(det)[0]))
+        return ids, det
+
     def params(self):
         H, D = self.L * self.k, self.pts.d
         if self.metric == COSINE:
@@ -417,3 +425,23 @@ def recommend_cluster(ctx, users, labels, K, Nrec, queries=None, qlabels=None):
     _check(lib().crx_recommend_cluster(ctx.h, users.h, _ptr(labels)[0], HOST, K, queries.h if queries is not None else None,
                                        _ptr(ql)[0], int(Nrec), _ptr(recs)[0], HOST))
     return recs
+
+
+def get_P_closest(ctx, users, neighbor_rows, query_set, query_row, P):
+    """get_P_closest (crypto_rec.hpp:214): returns (kept rows, similarities)."""
+    nb = _np(neighbor_rows, np.int32).copy()
+    sims = np.zeros(max(1, min(len(nb), P)))
+    kept = ctypes.c_int64()
+    _check(lib().crx_get_P_closest(ctx.h, users.h, _ptr(nb)[0], ctypes.c_int64(len(nb)), query_set.h, ctypes.c_int64(query_row), int(P),
+                                   _ptr(sims)[0], ctypes.byref(kept)))
+    return nb[:kept.value], sims[:kept.value]
+
+
+def get_top_N_recom(ctx, users, neighbor_rows, similarities, query_set, query_row, N):
+    """get_top_N_recom (crypto_rec.hpp:310 / :328 when similarities is None): returns (recs[N], predicted[D])."""
+    nb = _np(neighbor_rows, np.int32)
+    sm = None if similarities is None else _np(similarities, np.float64)
+    recs = np.zeros(N, np.int32); pred = np.zeros(users.d)
+    _check(lib().crx_get_top_N_recom(ctx.h, users.h, _ptr(nb)[0], _ptr(sm)[0], ctypes.c_int64(len(nb)), query_set.h,
+                                     ctypes.c_int64(query_row), int(N), _ptr(pred)[0], _ptr(recs)[0]))
+    return recs, pred

@@ -510,6 +510,28 @@ int crx_lsh_detailed_hashes(const crx_lsh* t, int32_t* out, int mem) {
     return CRX_OK;
 }
 
+int crx_lsh_hash_vector(const crx_lsh* t, const double* x, int32_t* bucket_ids, int32_t* detailed) {
+    CRX_REQUIRE(t && x && bucket_ids, "NULL argument");
+    crx_ctx* c = t->ctx;
+    CRX_CUDA(cudaSetDevice(c->device));
+    crx_points* q = nullptr;
+    CRX_TRY(crx_points_create(c, x, CRX_F64, 1, t->D, CRX_HOST, &q));
+    DevBuf<int32_t> b, h;
+    int st = b.alloc(c, t->L);
+    if (st == CRX_OK && t->metric == CRX_EUCLIDEAN) st = h.alloc(c, (size_t)t->L * t->k);
+    if (st == CRX_OK)
+        st = crx_hash_rows(c, q, t->metric, t->k, t->L, t->d_proj, t->ldp, t->d_pnorm, t->d_t, t->d_r, t->w, t->nbuckets,
+                           t->metric == CRX_EUCLIDEAN ? h.p : nullptr, b.p);
+    if (st == CRX_OK) {
+        cudaMemcpyAsync(bucket_ids, b.p, t->L * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream);
+        if (detailed && t->metric == CRX_EUCLIDEAN)
+            cudaMemcpyAsync(detailed, h.p, (size_t)t->L * t->k * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream);
+        if (cudaStreamSynchronize(c->stream) != cudaSuccess) st = CRX_ERR_CUDA;
+    }
+    crx_points_destroy(q);
+    return st;
+}
+
 int crx_lsh_params(const crx_lsh* t, double* cos_r, float* euc_v, float* euc_t, int32_t* euc_r) {
     CRX_REQUIRE(t, "NULL argument");
     if (cos_r && !t->cos_r.empty()) memcpy(cos_r, t->cos_r.data(), t->cos_r.size() * sizeof(double));

@@ -211,15 +211,27 @@ rec_finalize_kernel(const TQ* __restrict__ xq, int ldq, const double* __restrict
         // exact similarity of every listed candidate (crypto_rec.hpp:220): the warp walks the candidates,
         // lanes split the coordinates (one 16-byte load each), FP64 FMA + shuffle tree
         double mysim = -INFINITY;
-        for (int cnd = 0; cnd < 32; cnd++) {
-            if (!((vm >> cnd) & 1u)) continue;
-            int ci = __shfl_sync(0xffffffffu, idx, cnd);
-            double cv[4] = {0.0, 0.0, 0.0, 0.0};
-            if (4 * lane < ldb) pt::ld4(xb + (size_t)ci * ldb + 4 * lane, cv);
-            double part = __fma_rn(cv[0], qv[0], __fma_rn(cv[1], qv[1], __fma_rn(cv[2], qv[2], __dmul_rn(cv[3], qv[3]))));
+        for (int c0 = 0; c0 < 32; c0 += 4) {
+            if (!((vm >> c0) & 0xfu)) continue;
+            int ci[4];
+            double cv[4][4], part[4];
 #pragma unroll
-            for (int off = 16; off > 0; off >>= 1) part += __shfl_xor_sync(0xffffffffu, part, off);
-            if (lane == cnd) mysim = cos_sim_from(part, sqn_b[ci], nq_);
+            for (int u = 0; u < 4; u++) {  // four independent 16-byte loads in flight
+                ci[u] = __shfl_sync(0xffffffffu, idx, c0 + u);
+                cv[u][0] = cv[u][1] = cv[u][2] = cv[u][3] = 0.0;
+                if (ci[u] >= 0 && 4 * lane < ldb) pt::ld4(xb + (size_t)ci[u] * ldb + 4 * lane, cv[u]);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; u++)
+                part[u] = __fma_rn(cv[u][0], qv[0], __fma_rn(cv[u][1], qv[1], __fma_rn(cv[u][2], qv[2], __dmul_rn(cv[u][3], qv[3]))));
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) {
+#pragma unroll
+                for (int u = 0; u < 4; u++) part[u] += __shfl_xor_sync(0xffffffffu, part[u], off);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; u++)
+                if (lane == c0 + u && ci[u] >= 0) mysim = cos_sim_from(part[u], sqn_b[ci[u]], nq_);
         }
         a_idx[warp][slot] = idx;
         a_sim[warp][slot] = mysim;
@@ -263,31 +275,51 @@ rec_finalize_kernel(const TQ* __restrict__ xq, int ldq, const double* __restrict
         for (int j = lane; j < Nrec; j += 32) recs[qrel * Nrec + j] = -1;
         return;
     }
-    // crypto_rec.hpp:281-306 for the unknown coins, neighbours in descending-similarity order
+    // crypto_rec.hpp:281-306 for the unknown coins, neighbours in descending-similarity order.  This lane owns
+    // coins 4*lane .. 4*lane+3; every neighbour row is read as one 16-byte piece per lane.
     double mq = mean_q[qrow];
-    int nu = 0;
-    for (int j0 = 0; j0 < D; j0 += 32) {
-        int j = j0 + lane;
-        bool u = j < D && unk_q[qrow * D + j] != 0;
-        double pred = 0.0;
-        if (u) {
-            double main_sum = 0.0, abs_sum = 0.0;
-            for (int i = 0; i < keep; i++) {
-                double s = s_sim[warp][i];
+    double main_sum[4] = {0.0, 0.0, 0.0, 0.0}, abs_sum = 0.0;
+    for (int i0 = 0; i0 < keep; i0 += 4) {
+        double nv[4][4], nm[4], ns[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            int i = i0 + u;
+            nv[u][0] = nv[u][1] = nv[u][2] = nv[u][3] = 0.0;
+            ns[u] = 0.0; nm[u] = 0.0;
+            if (i < keep) {
                 int nb = s_idx[warp][i];
-                abs_sum = __dadd_rn(abs_sum, fabs(s));
-                double v = (double)xb[(size_t)nb * ldb + j];
-                main_sum = __dadd_rn(main_sum, __dmul_rn(s, __dsub_rn(v, mean_b[nb])));
+                ns[u] = s_sim[warp][i];
+                nm[u] = mean_b[nb];
+                if (4 * lane < ldb) pt::ld4(xb + (size_t)nb * ldb + 4 * lane, nv[u]);
             }
-            pred = __dadd_rn(__ddiv_rn(main_sum, abs_sum), mq);
         }
-        unsigned um = __ballot_sync(0xffffffffu, u);
-        if (u) {
-            int slot = nu + __popc(um & ((1u << lane) - 1));
-            s_pred[warp][slot] = pred;
-            s_coin[warp][slot] = j;
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            if (i0 + u < keep) {
+                abs_sum = __dadd_rn(abs_sum, fabs(ns[u]));
+#pragma unroll
+                for (int t = 0; t < 4; t++) main_sum[t] = __dadd_rn(main_sum[t], __dmul_rn(ns[u], __dsub_rn(nv[u][t], nm[u])));
+            }
         }
-        nu += __popc(um);
+    }
+    unsigned um[4];
+    bool unk[4];
+#pragma unroll
+    for (int t = 0; t < 4; t++) {
+        int j = 4 * lane + t;
+        unk[t] = j < D && unk_q[qrow * D + j] != 0;
+        um[t] = __ballot_sync(0xffffffffu, unk[t]);
+    }
+    unsigned lt = (1u << lane) - 1u;
+    int before = __popc(um[0] & lt) + __popc(um[1] & lt) + __popc(um[2] & lt) + __popc(um[3] & lt);
+    int nu = __popc(um[0]) + __popc(um[1]) + __popc(um[2]) + __popc(um[3]);
+#pragma unroll
+    for (int t = 0; t < 4; t++) {
+        if (unk[t]) {
+            s_pred[warp][before] = __dadd_rn(__ddiv_rn(main_sum[t], abs_sum), mq);
+            s_coin[warp][before] = 4 * lane + t;
+            before++;
+        }
     }
     __syncwarp();
     if (lane == 0) lomuto_desc(s_pred[warp], s_coin[warp], nu, Nrec);  // crypto_rec.hpp:320
@@ -408,6 +440,63 @@ rec_cluster_kernel(const TQ* __restrict__ xq, int ldq, const double* __restrict_
     if (lane == 0) lomuto_desc(s_pred[warp], s_coin[warp], nu, Nrec);
     __syncwarp();
     for (int j = lane; j < Nrec; j += 32) recs[qrow * Nrec + j] = j < nu ? s_coin[warp][j] : 0;
+}
+
+// get_predicted_user_sim (crypto_rec.hpp:281-306) + get_top_N_recom (:310-345) for ONE user and an explicit
+// neighbour list (rows of `xb`, in the given order).  sims == NULL: similarities to all neighbours are computed
+// first (crypto_rec.hpp:331-333).  One warp.
+template <typename TQ, typename TB>
+__global__ void rec_list_kernel(const TQ* __restrict__ q, int D, double sqn_q, const uint8_t* __restrict__ unk_q, double mean_q,
+                                const TB* __restrict__ xb, int ldb, const double* __restrict__ sqn_b, const double* __restrict__ mean_b,
+                                const int32_t* __restrict__ nbr, const double* __restrict__ sims_in, int n, int Nrec,
+                                double* __restrict__ predicted /* [D] or NULL */, int32_t* __restrict__ recs /* [Nrec] or NULL */) {
+    __shared__ int s_idx[32];
+    __shared__ double s_sim[32];
+    __shared__ double s_pred[128];
+    __shared__ int s_coin[128];
+    int lane = threadIdx.x & 31;
+    double main_sum[4] = {0, 0, 0, 0}, abs_sum = 0.0;
+    for (int base = 0; base < n; base += 32) {
+        int p = base + lane;
+        int nb = p < n ? nbr[p] : -1;
+        s_idx[lane] = nb;
+        s_sim[lane] = nb >= 0 ? (sims_in ? sims_in[p] : cos_sim_exact(xb + (size_t)nb * ldb, q, D, sqn_b[nb], sqn_q)) : 0.0;
+        __syncwarp();
+        int lim = min(32, n - base);
+        for (int i = 0; i < lim; i++) {
+            double s = s_sim[i];
+            int r = s_idx[i];
+            abs_sum = __dadd_rn(abs_sum, fabs(s));
+            double mb = mean_b[r];
+#pragma unroll
+            for (int t = 0; t < 4; t++) {
+                int j = lane + 32 * t;
+                if (j < D) main_sum[t] = __dadd_rn(main_sum[t], __dmul_rn(s, __dsub_rn((double)xb[(size_t)r * ldb + j], mb)));
+            }
+        }
+        __syncwarp();
+    }
+    int nu = 0;
+#pragma unroll
+    for (int t = 0; t < 4; t++) {
+        int j = lane + 32 * t;
+        bool u = j < D && unk_q[j] != 0;
+        double pr = u ? __dadd_rn(__ddiv_rn(main_sum[t], abs_sum), mean_q) : (j < D ? (double)q[j] : 0.0);
+        if (predicted && j < D) predicted[j] = pr;
+        unsigned um = __ballot_sync(0xffffffffu, u);
+        if (u) {
+            int slot = nu + __popc(um & ((1u << lane) - 1));
+            s_pred[slot] = pr;
+            s_coin[slot] = j;
+        }
+        nu += __popc(um);
+    }
+    __syncwarp();
+    if (recs) {
+        if (lane == 0) lomuto_desc(s_pred, s_coin, nu, Nrec);
+        __syncwarp();
+        for (int j = lane; j < Nrec; j += 32) recs[j] = j < nu ? s_coin[j] : 0;
+    }
 }
 
 __global__ void quicksort_kernel(double* sims, int32_t* ids, int n) {
@@ -657,6 +746,59 @@ int crx_recommend_cluster(crx_ctx* c, const crx_points* users, const int32_t* la
     CRX_CUDA(cudaStreamSynchronize(c->stream));
     seg.free_all();
     return st;
+}
+
+int crx_get_P_closest(crx_ctx* c, const crx_points* users, int32_t* neighbor_rows, int64_t n, const crx_points* query_set,
+                      int64_t query_row, int P, double* similarities, int64_t* kept) {
+    CRX_REQUIRE(c && users && neighbor_rows && query_set && similarities && kept, "NULL argument");
+    CRX_REQUIRE(users->d == query_set->d, "dimension mismatch");
+    CRX_REQUIRE(query_row >= 0 && query_row < query_set->n && n >= 0 && P >= 0, "argument range");
+    *kept = std::min<int64_t>(n, P);
+    if (n == 0) return CRX_OK;
+    std::vector<int32_t> qrows((size_t)n, (int32_t)query_row);
+    std::vector<double> sims((size_t)n);
+    // similarities (crypto_rec.hpp:219-220), then the literal co-sort (:223) on the device
+    CRX_TRY(crx_pair_op(c, users, neighbor_rows, query_set, qrows.data(), n, 3, sims.data()));
+    CRX_TRY(crx_parallel_quickSort(c, sims.data(), neighbor_rows, (int)n));
+    for (int64_t i = 0; i < *kept; i++) similarities[i] = sims[i];
+    return CRX_OK;
+}
+
+int crx_get_top_N_recom(crx_ctx* c, const crx_points* users, const int32_t* neighbor_rows, const double* similarities,
+                        int64_t n, const crx_points* query_set, int64_t query_row, int N, double* predicted, int32_t* recs) {
+    CRX_REQUIRE(c && users && query_set && (neighbor_rows || n == 0), "NULL argument");
+    CRX_REQUIRE(users->d == query_set->d && users->d <= 128, "dimension");
+    CRX_REQUIRE(users->mean && query_set->unknown && query_set->mean, "ratings metadata missing (crx_points_set_ratings)");
+    CRX_REQUIRE(query_row >= 0 && query_row < query_set->n && N >= 0 && N <= 128, "argument range");
+    CRX_CUDA(cudaSetDevice(c->device));
+    int D = users->d;
+    IoBuf<int32_t> nb, out;
+    IoBuf<double> sm, pr;
+    CRX_TRY(nb.bind(c, neighbor_rows, (size_t)n, CRX_HOST, true));
+    CRX_TRY(sm.bind(c, similarities, (size_t)n, CRX_HOST, true));
+    CRX_TRY(pr.bind(c, predicted, (size_t)D, CRX_HOST, false));
+    CRX_TRY(out.bind(c, recs, (size_t)N, CRX_HOST, false));
+    double h_sq, h_mean;
+    CRX_CUDA(cudaMemcpyAsync(&h_sq, query_set->sqn + query_row, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CRX_CUDA(cudaMemcpyAsync(&h_mean, query_set->mean + query_row, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CRX_CUDA(cudaStreamSynchronize(c->stream));
+    {
+        CRX_KERNEL(c, "rec_list");
+        const uint8_t* unk = query_set->unknown + (size_t)query_row * D;
+#define LAUNCH_L(TQ, TB, xqp, xbp) \
+    rec_list_kernel<TQ, TB><<<1, 32, 0, c->stream>>>(xqp + (size_t)query_row * query_set->ld, D, h_sq, unk, h_mean, xbp, users->ld, users->sqn, \
+                                                      users->mean, nb.dev, sm.dev, (int)n, N, pr.dev, out.dev)
+        if (query_set->x64 && users->x64) LAUNCH_L(double, double, query_set->x64, users->x64);
+        else if (query_set->x64) LAUNCH_L(double, float, query_set->x64, users->x32);
+        else if (users->x64) LAUNCH_L(float, double, query_set->x32, users->x64);
+        else LAUNCH_L(float, float, query_set->x32, users->x32);
+#undef LAUNCH_L
+    }
+    CRX_CUDA(cudaGetLastError());
+    CRX_TRY(pr.flush());
+    CRX_TRY(out.flush());
+    CRX_CUDA(cudaStreamSynchronize(c->stream));
+    return CRX_OK;
 }
 
 int crx_parallel_quickSort(crx_ctx* c, double* sims, int32_t* ids, int n) {

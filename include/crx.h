@@ -90,6 +90,9 @@ int crx_lsh_detailed_hashes(const crx_lsh* t, int32_t* out, int mem);
  * (filtered=1, lsh_cube.hpp:94) for a stored row; ascending row order; *count may exceed cap */
 int crx_get_LSH_combined_buckets(const crx_lsh* t, int64_t query_row, int filtered, int32_t* out /* host */,
                                  int64_t cap, int64_t* count);
+/* CustHashtable::getHash of a vector that is NOT stored in the tables (e.g. a query user, main.cpp:207):
+ * bucket_ids[L]; detailed[L][k] (euclidean, may be NULL).  x[D] doubles on the host. */
+int crx_lsh_hash_vector(const crx_lsh* t, const double* x, int32_t* bucket_ids, int32_t* detailed);
 /* hash parameters actually drawn (for inspection / parity): cosine r[L][k][D] doubles,
  * euclidean v[L][k][D] floats, t[L][k] floats, r_i[L][k] ints.  Any pointer may be NULL.  Host. */
 int crx_lsh_params(const crx_lsh* t, double* cos_r, float* euc_v, float* euc_t, int32_t* euc_r);
@@ -162,6 +165,15 @@ int crx_recommend_lsh(crx_ctx* ctx, const crx_lsh* lsh_hashtables, const crx_poi
  * (crypto_rec.hpp:328).  queries NULL => users themselves with qlabels = labels. */
 int crx_recommend_cluster(crx_ctx* ctx, const crx_points* users, const int32_t* labels, int lmem, int K,
                           const crx_points* queries, const int32_t* qlabels, int Nrec, int32_t* recs, int mem);
+/* Per-user forms of the same functions, for the drop-in headers (include/crx/lib/crypto_rec.hpp):
+ * get_P_closest (crypto_rec.hpp:214): similarities of the listed neighbours to the user, literal co-sort,
+ *   first min(n, P) kept.  neighbor_rows[n] is reordered in place (host), similarities[min(n,P)] (host). */
+int crx_get_P_closest(crx_ctx* ctx, const crx_points* users, int32_t* neighbor_rows, int64_t n, const crx_points* query_set,
+                      int64_t query_row, int P, double* similarities, int64_t* kept);
+/* get_predicted_user_sim (:281) and get_top_N_recom (:310 with similarities, :328 with similarities == NULL) for
+ *   one user and an explicit neighbour list.  predicted[D] and recs[N] are host buffers; either may be NULL. */
+int crx_get_top_N_recom(crx_ctx* ctx, const crx_points* users, const int32_t* neighbor_rows, const double* similarities,
+                        int64_t n, const crx_points* query_set, int64_t query_row, int N, double* predicted, int32_t* recs);
 /* parallel_quickSort (crypto_rec.hpp:269) on the device, one thread: known-answer tests only */
 int crx_parallel_quickSort(crx_ctx* ctx, double* sims /* host, in/out */, int32_t* ids /* host, in/out */, int n);
 

@@ -1,0 +1,107 @@
+// crx_shim.hpp -- glue shared by the drop-in headers under include/crx/lib/: a process-wide context, the
+// seed source, and packing of std::vector<CustVector<T>> into the contiguous buffers of the C ABI
+// (include/crx.h).  Host side only marshals; every arithmetic step runs in libcrx.so on the GPU.
+#ifndef CRX_SHIM_HPP
+#define CRX_SHIM_HPP
+
+#include <chrono>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <set>
+#include <string>
+#include <vector>
+
+extern "C" {
+#include "../crx.h"
+}
+
+template <typename dim_type>
+class CustVector;
+
+namespace crx {
+
+inline void check(int status, const char* what) {
+    if (status != CRX_OK) {  // the reference has no error channel: fail loudly instead of computing on the CPU
+        std::fprintf(stderr, "crx: %s failed (%d): %s\n", what, status, crx_last_error());
+        std::abort();
+    }
+}
+
+inline crx_ctx* context() {
+    static crx_ctx* ctx = nullptr;
+    if (!ctx) {
+        const char* dev = std::getenv("CRX_DEVICE");
+        check(crx_ctx_create(dev ? std::atoi(dev) : 0, nullptr, &ctx), "crx_ctx_create");
+    }
+    return ctx;
+}
+
+// The reference seeds every engine from system_clock::now() (lsh_cube.hpp:49; initialization.hpp:42).
+// set_seed() pins the value for reproducible runs; next_seed() is what each drop-in function consumes.
+inline uint64_t& pinned_seed() { static uint64_t s = 0; return s; }
+inline bool& seed_is_pinned() { static bool p = false; return p; }
+inline void set_seed(uint64_t s) { pinned_seed() = s; seed_is_pinned() = true; }
+inline void unset_seed() { seed_is_pinned() = false; }
+inline uint64_t next_seed() {
+    if (seed_is_pinned()) return pinned_seed();
+    return (uint64_t)std::chrono::system_clock::now().time_since_epoch().count();
+}
+
+inline int metric_code(const std::string& m) {
+    if (m == "euclidean") return CRX_EUCLIDEAN;
+    if (m == "cosine") return CRX_COSINE;
+    std::fprintf(stderr, "crx: unknown metric_type '%s'\n", m.c_str());
+    std::abort();
+}
+
+// RAII handle over crx_points built from CustVector objects
+template <typename T>
+struct Packed {
+    crx_points* pts = nullptr;
+    int64_t n = 0;
+    int d = 0;
+    Packed() {}
+    Packed(const Packed&) = delete;
+    Packed& operator=(const Packed&) = delete;
+    ~Packed() { if (pts) crx_points_destroy(pts); }
+
+    template <typename Getter>
+    void build(int64_t count, Getter get, bool ratings) {
+        n = count;
+        d = count ? (int)get(0)->getDimNumber() : 0;
+        std::vector<double> buf((size_t)n * d);
+        std::vector<uint8_t> unk;
+        std::vector<double> mean;
+        if (ratings) { unk.assign((size_t)n * d, 0); mean.resize(n); }
+        for (int64_t i = 0; i < n; i++) {
+            CustVector<T>* v = get(i);
+            const std::vector<T>& dims = *v->getDimensions();
+            for (int j = 0; j < d; j++) buf[(size_t)i * d + j] = (double)dims[j];
+            if (ratings) {
+                for (int u : v->getUnknownIndexesSet()) if (u >= 0 && u < d) unk[(size_t)i * d + u] = 1;
+                mean[i] = v->getKnownMean();
+            }
+        }
+        check(crx_points_create(context(), buf.data(), CRX_F64, n, d, CRX_HOST, &pts), "crx_points_create");
+        if (ratings) check(crx_points_set_ratings(pts, unk.data(), mean.data(), CRX_HOST), "crx_points_set_ratings");
+    }
+    void from_vector(std::vector<CustVector<T> >& vecs, bool ratings = false) {
+        build((int64_t)vecs.size(), [&](int64_t i) { return &vecs[i]; }, ratings);
+    }
+    void from_pointers(const std::vector<CustVector<T>*>& vecs, bool ratings = false) {
+        build((int64_t)vecs.size(), [&](int64_t i) { return vecs[i]; }, ratings);
+    }
+};
+
+// row of `p` inside `vecs`, or -1 when the pointer does not alias an element (e.g. k_means centres)
+template <typename T>
+inline int32_t row_of(std::vector<CustVector<T> >& vecs, const CustVector<T>* p) {
+    if (vecs.empty()) return -1;
+    const CustVector<T>* b = &vecs[0];
+    if (p >= b && p < b + vecs.size()) return (int32_t)(p - b);
+    return -1;
+}
+
+}  // namespace crx
+#endif

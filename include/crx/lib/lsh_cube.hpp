@@ -1,0 +1,95 @@
+// Drop-in for lib/lsh_cube.hpp (reference lsh_cube.hpp:28-177): same free functions, same signatures.
+#ifndef LSH_CUBE_HPP
+#define LSH_CUBE_HPP
+
+#include <algorithm>
+#include <set>
+#include <string>
+#include <vector>
+
+#include "./data_structures/cust_hashtable.hpp"
+#include "./data_structures/cust_vector.hpp"
+#include "utils.hpp"
+
+// lsh_cube.hpp:45-74.  The L returned objects share one GPU table set; delete each as the reference does.
+template <typename vector_type>
+std::vector<CustHashtable<vector_type>*> create_LSH_hashtables(std::vector<CustVector<vector_type> >& input_vectors, const std::string metric_type,
+                                                               int k, int L, int lsh_bucket_div, double euclidean_h_w) {
+    auto set = std::make_shared<crx::TableSet<vector_type> >();
+    set->base = &input_vectors;
+    set->metric = crx::metric_code(metric_type);
+    set->k = k;
+    set->L = L;
+    set->pts.from_vector(input_vectors, false);
+    crx::check(crx_create_LSH_hashtables(crx::context(), set->pts.pts, set->metric, k, L, lsh_bucket_div, euclidean_h_w, crx::next_seed(), &set->lsh),
+               "crx_create_LSH_hashtables");
+    std::vector<CustHashtable<vector_type>*> tables;
+    tables.reserve(L);
+    for (int l = 0; l < L; l++) tables.emplace_back(new CustHashtable<vector_type>(set, l));
+    return tables;
+}
+
+namespace crx {
+template <typename T>
+std::vector<CustVector<T>*> combined(std::vector<CustHashtable<T>*>& tables, CustVector<T>* q, bool filtered) {
+    std::vector<CustVector<T>*> out;
+    if (tables.empty()) return out;
+    auto& set = tables[0]->set;
+    int32_t row = row_of(*set->base, q);
+    if (row >= 0 && (int)tables.size() == set->L) {  // stored query, all tables: one engine call
+        std::vector<int32_t> rows((size_t)set->n());
+        int64_t count = 0;
+        check(crx_get_LSH_combined_buckets(set->lsh, row, filtered ? 1 : 0, rows.data(), (int64_t)rows.size(), &count), "crx_get_LSH_combined_buckets");
+        for (int64_t i = 0; i < count; i++) out.push_back(&(*set->base)[rows[i]]);
+        return out;
+    }
+    std::set<CustVector<T>*> u;  // pointer order == row order (lsh_cube.hpp:96,104)
+    for (auto t : tables) {
+        std::vector<CustVector<T>*> b = filtered ? t->getFilteredBucketFor(q) : t->getBucketFor(q);
+        u.insert(b.begin(), b.end());
+    }
+    return std::vector<CustVector<T>*>(u.begin(), u.end());
+}
+}  // namespace crx
+
+template <typename vector_type>
+std::vector<CustVector<vector_type>*> get_LSH_combined_buckets(std::vector<CustHashtable<vector_type>*>& lshHashtables, CustVector<vector_type>* queryVec) {
+    return crx::combined(lshHashtables, queryVec, false);  // lsh_cube.hpp:78-90
+}
+
+template <typename vector_type>
+std::vector<CustVector<vector_type>*> get_LSH_filtered_combined_buckets(std::vector<CustHashtable<vector_type>*>& lshHashtables, CustVector<vector_type>* queryVec) {
+    return crx::combined(lshHashtables, queryVec, true);  // lsh_cube.hpp:94-106
+}
+
+// lsh_cube.hpp:109-136
+template <typename vector_type>
+CustHashtable<vector_type>* create_hypercube(std::vector<CustVector<vector_type> >& input_vectors, const std::string metric_type, int k, double euclidean_h_w) {
+    auto set = std::make_shared<crx::TableSet<vector_type> >();
+    set->base = &input_vectors;
+    set->metric = crx::metric_code(metric_type);
+    set->k = k;
+    set->L = 1;
+    set->pts.from_vector(input_vectors, false);
+    crx::check(crx_create_hypercube(crx::context(), set->pts.pts, set->metric, k, euclidean_h_w, crx::next_seed(), &set->cube), "crx_create_hypercube");
+    return new CustHashtable<vector_type>(set, 0);
+}
+
+// lsh_cube.hpp:140-177: home vertex, then Hamming-1 vertices, Hamming-2, ... one probe per extra vertex
+template <typename vector_type>
+std::vector<CustVector<vector_type>*> get_hypercube_combined_buckets(CustHashtable<vector_type>& hypercube, CustVector<vector_type>* queryVec, int probes, int k) {
+    auto& set = hypercube.set;
+    std::vector<CustVector<vector_type>*> out;
+    int32_t row = crx::row_of(*set->base, queryVec);
+    if (row < 0 || k != set->k) {
+        std::fprintf(stderr, "crx: get_hypercube_combined_buckets needs a stored query row and the cube's own k\n");
+        std::abort();
+    }
+    std::vector<int32_t> rows((size_t)set->n());
+    int64_t count = 0;
+    crx::check(crx_get_hypercube_combined_buckets(set->cube, row, probes, rows.data(), (int64_t)rows.size(), &count), "crx_get_hypercube_combined_buckets");
+    for (int64_t i = 0; i < count && i < (int64_t)rows.size(); i++) out.push_back(&(*set->base)[rows[i]]);
+    return out;
+}
+
+#endif  // LSH_CUBE_HPP
