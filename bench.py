@@ -242,7 +242,7 @@ def run_crx(args):
     scan_name = "tc_topp_scan" if ctx.kernel_time("tc_topp_scan")[1] > 0 else "topp_scan"
     scan_ms, scan_launches = ctx.kernel_time(scan_name)
     kernel_ms = {k: round(ctx.kernel_time(k)[0] / args.steps, 3) for k in (
-        "tc_topp_scan", "topp_scan", "rec_finalize", "hash_rows", "tc_prep", "pack_codes", "subset_hist", "subset_count",
+        "tc_topp_scan", "topp_scan", "rec_finalize", "rec_topn", "hash_rows", "tc_prep", "pack_codes", "subset_hist", "subset_count",
         "iota", "bucket_offsets", "fill_lists", "sq_sizes")}
     ncand_total = float(out_dev["ncand"].to(torch.float64).sum().item())
     counters = ctx.counters()

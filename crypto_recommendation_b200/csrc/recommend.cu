@@ -170,6 +170,88 @@ topp_scan_kernel(const TQ* __restrict__ xq, int ldq, const double* __restrict__ 
 }
 
 // ------------------------------------------------------------------------------------------------
+// Warp-cooperative form of the literal Lomuto quicksort (crypto_rec.hpp:235-277) when only the first `need`
+// positions of the result are consumed (resize(N), crypto_rec.hpp:322).  key/val live in shared memory, n <= 128.
+//
+// One partition of [lo, hi] with pivot key[hi] leaves (a) the elements >= pivot in their ORIGINAL order in
+// [lo, p), (b) the pivot at p = lo + #{>= pivot}, (c) the elements < pivot, permuted, in (p, hi].  Ranges that
+// start at or beyond `need` never influence the consumed prefix, so (c) only matters when p + 1 < need; then the
+// step is done literally by one lane.  Otherwise (a) is a stable compaction done by the whole warp with ballots.
+// A range whose keys all equal the pivot is left untouched by the literal algorithm and is skipped.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void warp_lomuto_topn(double* key, int* val, int n, int need) {
+    const int lane = threadIdx.x & 31;
+    const unsigned lt = (1u << lane) - 1u;
+    int st_lo[128], st_hi[128];  // at most one pending right part per consumed position (need <= 128)
+    int sp = 1;
+    st_lo[0] = 0; st_hi[0] = n - 1;
+    while (sp > 0) {
+        sp--;
+        int lo = st_lo[sp], hi = st_hi[sp];
+        while (lo < hi && lo < need) {
+            const double pivot = key[hi];
+            const int m = hi - lo;  // elements in front of the pivot
+            double kk[4];
+            int vv[4];
+            unsigned ge[4];
+            bool alleq = true;
+            int cnt = 0;
+#pragma unroll
+            for (int t = 0; t < 4; t++) {
+                int e = t * 32 + lane;
+                bool in = e < m;
+                kk[t] = in ? key[lo + e] : 0.0;
+                vv[t] = in ? val[lo + e] : 0;
+                bool g = in && (kk[t] >= pivot);
+                ge[t] = __ballot_sync(0xffffffffu, g);
+                alleq = alleq && __all_sync(0xffffffffu, !in || (kk[t] == pivot));
+                cnt += __popc(ge[t]);
+            }
+            if (alleq) break;
+            const int p = lo + cnt;
+            if (p + 1 < need && p < hi) {
+                // the right part reaches into the consumed prefix: literal partition by one lane
+                __syncwarp();
+                if (lane == 0) {
+                    int i = lo - 1;
+                    for (int j = lo; j < hi; j++) {
+                        if (key[j] >= pivot) {
+                            i++;
+                            double tk = key[i]; key[i] = key[j]; key[j] = tk;
+                            int tv = val[i]; val[i] = val[j]; val[j] = tv;
+                        }
+                    }
+                    double tk = key[i + 1]; key[i + 1] = key[hi]; key[hi] = tk;
+                    int tv = val[i + 1]; val[i + 1] = val[hi]; val[hi] = tv;
+                }
+                __syncwarp();
+                if (sp < 128) { st_lo[sp] = p + 1; st_hi[sp] = hi; sp++; }  // right part afterwards
+                hi = p - 1;                                                  // left part first
+                continue;
+            }
+            if (cnt < m) {  // something moves: stable compaction of the ">= pivot" elements, pivot behind them
+                const int pv = val[hi];
+                __syncwarp();
+                int base = 0;
+#pragma unroll
+                for (int t = 0; t < 4; t++) {
+                    if ((ge[t] >> lane) & 1u) {
+                        int dst = lo + base + __popc(ge[t] & lt);
+                        key[dst] = kk[t];
+                        val[dst] = vv[t];
+                    }
+                    base += __popc(ge[t]);
+                }
+                if (lane == 0) { key[p] = pivot; val[p] = pv; }
+                __syncwarp();
+            }
+            hi = p - 1;  // [p + 1, hi] starts at or beyond `need` (or is empty): never consumed
+        }
+    }
+    __syncwarp();
+}
+
+// ------------------------------------------------------------------------------------------------
 // K10: refine + predict + top-N.  One warp per query.  LISTN = 32 (FP64 scan, double scores) or
 // 64 (tensor-core filter, float scores scaled by `approx_scale`, filter error `approx_eps`).
 // ------------------------------------------------------------------------------------------------
@@ -275,6 +357,8 @@ rec_finalize_kernel(const TQ* __restrict__ xq, int ldq, const double* __restrict
         for (int j = lane; j < Nrec; j += 32) recs[qrel * Nrec + j] = -1;
         return;
     }
+    double* s_pred_q = s_pred[warp];
+    int* s_coin_q = s_coin[warp];
     // crypto_rec.hpp:281-306 for the unknown coins, neighbours in descending-similarity order.  This lane owns
     // coins 4*lane .. 4*lane+3; every neighbour row is read as one 16-byte piece per lane.
     double mq = mean_q[qrow];
@@ -316,15 +400,14 @@ rec_finalize_kernel(const TQ* __restrict__ xq, int ldq, const double* __restrict
 #pragma unroll
     for (int t = 0; t < 4; t++) {
         if (unk[t]) {
-            s_pred[warp][before] = __dadd_rn(__ddiv_rn(main_sum[t], abs_sum), mq);
-            s_coin[warp][before] = 4 * lane + t;
+            s_pred_q[before] = __dadd_rn(__ddiv_rn(main_sum[t], abs_sum), mq);
+            s_coin_q[before] = 4 * lane + t;
             before++;
         }
     }
     __syncwarp();
-    if (lane == 0) lomuto_desc(s_pred[warp], s_coin[warp], nu, Nrec);  // crypto_rec.hpp:320
-    __syncwarp();
-    for (int j = lane; j < Nrec; j += 32) recs[qrel * Nrec + j] = j < nu ? s_coin[warp][j] : 0;  // resize(N) pads with 0
+    warp_lomuto_topn(s_pred_q, s_coin_q, nu, Nrec);  // crypto_rec.hpp:320
+    for (int j = lane; j < Nrec; j += 32) recs[qrel * Nrec + j] = j < nu ? s_coin_q[j] : 0;  // resize(N) pads with coin 0
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -437,8 +520,7 @@ rec_cluster_kernel(const TQ* __restrict__ xq, int ldq, const double* __restrict_
         nu += __popc(um);
     }
     __syncwarp();
-    if (lane == 0) lomuto_desc(s_pred[warp], s_coin[warp], nu, Nrec);
-    __syncwarp();
+    warp_lomuto_topn(s_pred[warp], s_coin[warp], nu, Nrec);
     for (int j = lane; j < Nrec; j += 32) recs[qrow * Nrec + j] = j < nu ? s_coin[warp][j] : 0;
 }
 
@@ -493,8 +575,7 @@ __global__ void rec_list_kernel(const TQ* __restrict__ q, int D, double sqn_q, c
     }
     __syncwarp();
     if (recs) {
-        if (lane == 0) lomuto_desc(s_pred, s_coin, nu, Nrec);
-        __syncwarp();
+        warp_lomuto_topn(s_pred, s_coin, nu, Nrec);
         for (int j = lane; j < Nrec; j += 32) recs[j] = j < nu ? s_coin[j] : 0;
     }
 }
@@ -678,6 +759,7 @@ int crx_recommend_lsh(crx_ctx* c, const crx_lsh* t, const crx_points* queries, i
     }
     IoBuf<int32_t> o_recs, o_rows, o_nc;
     IoBuf<double> o_sims;
+
     CRX_TRY(o_recs.bind(c, recs, (size_t)nq * Nrec, mem, false));
     CRX_TRY(o_rows.bind(c, nbr_rows, (size_t)nq * P, mem, false));
     CRX_TRY(o_sims.bind(c, nbr_sims, (size_t)nq * P, mem, false));
