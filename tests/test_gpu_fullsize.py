@@ -1,0 +1,134 @@
+"""GPU, BASELINE.json sizes: the oracle cannot run whole configs, so these tests check (a) sampled units against
+the oracle run on the FULL inputs and (b) size-independent properties of every output."""
+import numpy as np
+import pytest
+
+from oracle import EUCLIDEAN, COSINE, RecHandle
+from crypto_recommendation_b200 import capi, synth
+
+pytestmark = pytest.mark.gpu
+
+
+def test_c2_one_million_users_top_p_recommendation(ctx, port):
+    n, d, P, Nrec, k, L = 1_000_000, 100, 20, 5, 4, 5
+    X = synth.normal_points(n, d, seed=2, dtype=np.float32)        # continuous => no similarity ties
+    rng = np.random.default_rng(2)
+    unk = (rng.random((n, d), dtype=np.float32) < 0.9).astype(np.uint8)
+    known = unk == 0
+    mean = (np.where(known, X, 0).sum(1, dtype=np.float64) / np.maximum(1, known.sum(1))).astype(np.float32).astype(np.float64)
+    pts = ctx.points(X, unk, mean)
+    t = capi.LshTables(ctx, pts, "cosine", k, L, 100, 0.4, 12345)
+    out = capi.recommend_lsh(ctx, t, P, Nrec)
+    nbr, sim, ncand, recs = out["nbr_rows"], out["nbr_sims"], out["ncand"], out["recs"]
+    # properties over all 1M queries
+    assert np.array_equal(nbr[:, 0], np.arange(n)), "every user is its own nearest neighbour"
+    assert np.abs(sim[:, 0] - 1.0).max() < 1e-12
+    assert (np.diff(sim, axis=1) <= 0).all(), "similarities are sorted descending"
+    assert (nbr >= 0).all() and (nbr < n).all() and (ncand >= P).all()
+    assert (np.sort(nbr, axis=1)[:, 1:] != np.sort(nbr, axis=1)[:, :-1]).all(), "no duplicate neighbours"
+    assert (recs >= 0).all() and (recs < d).all()
+    assert (np.take_along_axis(unk, recs.astype(np.int64), axis=1) == 1).all(), "only unknown coins are recommended"
+    # candidate counts: brute force over the packed bucket ids for a sample of queries
+    ids = t.bucket_ids()
+    sample = rng.integers(0, n, 200)
+    for q in sample:
+        m = np.zeros(n, bool)
+        for l in range(L):
+            m |= ids[l] == ids[l, q]
+        assert ncand[q] == m.sum()
+        assert m[nbr[q]].all(), "neighbours come from the query's buckets"
+    frac = ncand.mean() / n
+    assert 0.2 < frac < 0.35, frac
+    # sampled queries against the oracle run over the FULL 1M-user table
+    h = RecHandle(port, X.astype(np.float64), unk, mean, COSINE, k, L, 100, 0.4, 12345)
+    for q in rng.integers(0, n - 1, 10):
+        r, nc = h.query(int(q), int(q) + 1, P, Nrec)
+        assert nc[0] == ncand[q]
+        assert np.array_equal(r[0], recs[q]), (q, r[0], recs[q])
+    h.close()
+    assert ctx.counters()["hash_dd"] >= 0
+
+
+def test_c4_shard_lloyd_k1024(ctx, port):
+    n, d, K = 4_000_000, 128, 1024
+    X = synth.gaussian_mixture(n, d, K, seed=4, dtype=np.float32)
+    pts = ctx.points(X)
+    rng = np.random.default_rng(4)
+    cidx = rng.choice(n, K, replace=False).astype(np.int32)
+    C = X[cidx].astype(np.float64)
+    lab, dist = capi.lloyds_assignment(ctx, pts, C, None, "euclidean")
+    lab2, dist2 = capi.lloyds_assignment(ctx, pts, C, None, "euclidean")
+    assert np.array_equal(lab, lab2) and np.array_equal(dist, dist2), "deterministic"
+    assert lab.min() >= 0 and lab.max() < K
+    assert (lab[cidx] == np.arange(K)).all() and (dist[cidx] == 0).all(), "a centroid row is nearest to itself"
+    # sampled points: exact argmin (lowest index on ties) and the reference's own distance value, bit for bit
+    for v in rng.integers(0, n, 64):
+        x = X[v].astype(np.float64)
+        dd = np.array([port.euclidean_distance(x, C[c]) for c in range(K)])
+        assert lab[v] == int(np.argmin(dd)), v
+        assert dist[v] == dd[lab[v]], v
+    # k-means update on the same labels: sums are deterministic and match numpy to 1e-12
+    sums, counts = capi.cluster_sums(ctx, pts, lab, K)
+    assert counts.sum() == n and np.array_equal(counts, np.bincount(lab, minlength=K))
+    for c in rng.integers(0, K, 8):
+        ref = X[lab == c].astype(np.float64).sum(0)
+        assert np.allclose(sums[c], ref, rtol=1e-12, atol=1e-9)
+
+
+def test_c3_cube_range_assignment_one_million(ctx, port):
+    n, d, K, kk, probes, w = 1_000_000, 128, 64, 12, 20, 6.0
+    X = synth.gaussian_mixture(n, d, 64, seed=3, dtype=np.float32)
+    pts = ctx.points(X)
+    cube = capi.Hypercube(ctx, pts, "euclidean", kk, w, 31)
+    vid = cube.vertex_ids()
+    assert vid.min() >= 0 and vid.max() < (1 << kk)
+    cidx = capi.rand_selection(ctx, pts, K, 77)
+    assert np.array_equal(cidx, port.rand_selection(np.zeros((n, 1)), K, 77))  # rand_selection depends on N and the seed only
+    lab, dist, before = capi.cube_range_assignment(ctx, pts, cube, cidx, "euclidean", probes)
+    assert (lab >= 0).all() and (lab < K).all()
+    assert (lab[cidx] == np.arange(K)).all() and (dist[cidx] == 0).all()
+    C = X[cidx].astype(np.float64)
+    # r0 = min centroid-centroid distance / 2; a point range-assigned to c lies in c's probed vertices and in an
+    # annulus [r0 2^(j-1), r0 2^j) with j == c (mod K)
+    r0 = min(port.euclidean_distance(C[a], C[b]) for a in range(K) for b in range(a + 1, K)) / 2
+    rng = np.random.default_rng(3)
+    assigned = np.flatnonzero(before >= 0)
+    assert len(assigned) > 0
+    for v in rng.choice(assigned, min(300, len(assigned)), replace=False):
+        c = before[v]
+        dv = port.euclidean_distance(C[c], X[v].astype(np.float64))
+        j = 0 if dv < r0 else int(np.floor(np.log2(dv / r0))) + 1
+        while j > 0 and dv < r0 * 2.0 ** (j - 1):
+            j -= 1
+        while not dv < r0 * 2.0 ** j:
+            j += 1
+        assert j % K == c, (v, c, j)
+        members = set(cube.combined_buckets(int(cidx[c]), probes).tolist())
+        assert int(v) in members
+        assert lab[v] == c or v in cidx
+    # the rest went through lloyds_for_remaining: exact nearest centroid
+    rest = np.flatnonzero(before < 0)
+    for v in rng.choice(rest, 32, replace=False):
+        if v in cidx:
+            continue
+        dd = np.array([port.euclidean_distance(X[v].astype(np.float64), C[c]) for c in range(K)])
+        assert lab[v] == int(np.argmin(dd)) and dist[v] == dd[lab[v]]
+
+
+def test_c5_pam_medoids(ctx, port):
+    n, d, K = 60_000, 100, 16
+    X = synth.gaussian_mixture(n, d, K, seed=5, dtype=np.float32)
+    pts = ctx.points(X)
+    cidx = capi.k_means_pp(ctx, pts, K, "euclidean", 5)
+    lab, _ = capi.lloyds_assignment(ctx, pts, X[cidx].astype(np.float64), cidx, "euclidean")
+    sw, new = capi.pam_lloyds(ctx, pts, lab, cidx, "euclidean")
+    assert (lab[new] == np.arange(K)).all(), "a medoid belongs to its cluster"
+    X64 = X.astype(np.float64)
+    rng = np.random.default_rng(5)
+    for c in range(0, K, 5):
+        mem = np.flatnonzero(lab == c)
+        def rowsum(v):
+            return np.sqrt(((X64[mem] - X64[v]) ** 2).sum(1)).sum()
+        best = rowsum(new[c])
+        for v in rng.choice(mem, 40):
+            assert best <= rowsum(v) * (1 + 1e-12)
