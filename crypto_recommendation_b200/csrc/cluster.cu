@@ -593,18 +593,39 @@ range_finalize_kernel(const T* __restrict__ x, int ld, int D, const double* __re
     }
 }
 
-// min over centroid pairs (utils.hpp:161-178); K is small, one thread per pair row
+// min over centroid pairs (utils.hpp:161-178): one thread per (a, b > a) pair.  Distances are >= 0 (or NaN /
+// -0-ish for cosine, which `d < min` never selects unless first), so the minimum of the non-negative ones is an
+// atomicMin on their bit patterns; the host applies the `-1` sentinel rule.
 template <typename T>
 __global__ void min_pair_kernel(const T* __restrict__ x, int ld, int D, const double* __restrict__ sqn,
-                                const int32_t* __restrict__ crow, int K, int metric, double* __restrict__ rowmin) {
-    int a = blockIdx.x * blockDim.x + threadIdx.x;
-    if (a >= K) return;
-    double m = INFINITY;
-    for (int b = a + 1; b < K; b++) {
-        double d = metric_dist_exact(metric, x + (size_t)crow[a] * ld, x + (size_t)crow[b] * ld, D, sqn[crow[a]], sqn[crow[b]]);
-        if (d < m) m = d;
-    }
-    rowmin[a] = m;
+                                const int32_t* __restrict__ crow, int K, int metric, unsigned long long* __restrict__ minbits,
+                                int* __restrict__ any_negative_or_nan) {
+    long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    long long npairs = (long long)K * (K - 1) / 2;
+    if (t >= npairs) return;
+    // unrank t -> (a, b), a < b, row-major over the strict upper triangle
+    int a = (int)((2.0 * K - 1.0 - sqrt((2.0 * K - 1.0) * (2.0 * K - 1.0) - 8.0 * (double)t)) / 2.0);
+    while ((long long)a * (2 * K - a - 1) / 2 > t) a--;
+    while ((long long)(a + 1) * (2 * K - a - 2) / 2 <= t) a++;
+    int b = (int)(t - (long long)a * (2 * K - a - 1) / 2) + a + 1;
+    double d = metric_dist_exact(metric, x + (size_t)crow[a] * ld, x + (size_t)crow[b] * ld, D, sqn[crow[a]], sqn[crow[b]]);
+    if (d >= 0.0) atomicMin(minbits, (unsigned long long)__double_as_longlong(d));
+    else atomicExch(any_negative_or_nan, 1);
+}
+
+// the reference's scan itself (one thread): used when some pair distance is negative or NaN, where the
+// `min == -1 || d < min` rule is order dependent
+template <typename T>
+__global__ void min_pair_seq_kernel(const T* __restrict__ x, int ld, int D, const double* __restrict__ sqn,
+                                    const int32_t* __restrict__ crow, int K, int metric, double* __restrict__ out) {
+    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    double m = -1;
+    for (int a = 0; a < K; a++)
+        for (int b = a + 1; b < K; b++) {
+            double d = metric_dist_exact(metric, x + (size_t)crow[a] * ld, x + (size_t)crow[b] * ld, D, sqn[crow[a]], sqn[crow[b]]);
+            if (m == -1 || d < m) m = d;
+        }
+    *out = m;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -769,6 +790,12 @@ __global__ void silhouette_reduce_kernel(const double* __restrict__ s, const int
     sils[cl] = acc / (double)(off[cl + 1] - off[cl]);
 }
 
+__global__ void merge_remaining_kernel(const int32_t* __restrict__ tl, const double* __restrict__ td, int64_t n, int32_t* __restrict__ labels,
+                                       double* __restrict__ dists) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && labels[i] == -1) { labels[i] = tl[i]; dists[i] = td[i]; }
+}
+
 __global__ void fill_int_kernel(int* p, int64_t n, int v) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) p[i] = v;
@@ -798,27 +825,43 @@ static int range_assign_common(crx_ctx* c, const crx_points* p, const int32_t* h
     CRX_TRY(bef.bind(c, before, N, mem, false));
     DevBuf<int32_t> d_crow, d_begin, d_end;
     DevBuf<const int32_t*> d_perm;
-    DevBuf<double> rowmin;
     DevBuf<int> key, hist;
     const int NH = 4096;
     CRX_TRY(d_crow.alloc(c, K)); CRX_TRY(d_begin.alloc(c, h_begin.size())); CRX_TRY(d_end.alloc(c, h_end.size()));
-    CRX_TRY(d_perm.alloc(c, h_perm.size())); CRX_TRY(rowmin.alloc(c, K)); CRX_TRY(key.alloc(c, N)); CRX_TRY(hist.alloc(c, NH));
+    CRX_TRY(d_perm.alloc(c, h_perm.size())); CRX_TRY(key.alloc(c, N)); CRX_TRY(hist.alloc(c, NH));
     CRX_CUDA(cudaMemcpyAsync(d_crow.p, h_crow, K * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
     CRX_CUDA(cudaMemcpyAsync(d_begin.p, h_begin.data(), h_begin.size() * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
     CRX_CUDA(cudaMemcpyAsync(d_end.p, h_end.data(), h_end.size() * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
     CRX_CUDA(cudaMemcpyAsync(d_perm.p, h_perm.data(), h_perm.size() * sizeof(const int32_t*), cudaMemcpyHostToDevice, c->stream));
     // r0 = min centroid-centroid distance / 2 (assignment.hpp:161)
-    {
+    DevBuf<unsigned long long> minbits;
+    DevBuf<int> oddflag;
+    CRX_TRY(minbits.alloc(c, 1)); CRX_TRY(oddflag.alloc(c, 1));
+    CRX_CUDA(cudaMemsetAsync(minbits.p, 0xff, sizeof(unsigned long long), c->stream));
+    CRX_CUDA(cudaMemsetAsync(oddflag.p, 0, sizeof(int), c->stream));
+    long long npairs = (long long)K * (K - 1) / 2;
+    if (npairs > 0) {
         CRX_KERNEL(c, "min_pair");
-        if (p->x64) min_pair_kernel<double><<<crx_grid(K, 64), 64, 0, c->stream>>>(p->x64, ld, D, p->sqn, d_crow.p, K, metric, rowmin.p);
-        else min_pair_kernel<float><<<crx_grid(K, 64), 64, 0, c->stream>>>(p->x32, ld, D, p->sqn, d_crow.p, K, metric, rowmin.p);
+        int g = crx_grid(npairs, 128);
+        if (p->x64) min_pair_kernel<double><<<g, 128, 0, c->stream>>>(p->x64, ld, D, p->sqn, d_crow.p, K, metric, minbits.p, oddflag.p);
+        else min_pair_kernel<float><<<g, 128, 0, c->stream>>>(p->x32, ld, D, p->sqn, d_crow.p, K, metric, minbits.p, oddflag.p);
     }
-    std::vector<double> h_rowmin(K);
-    CRX_CUDA(cudaMemcpyAsync(h_rowmin.data(), rowmin.p, K * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    unsigned long long h_minbits = ~0ull;
+    int h_odd = 0;
+    CRX_CUDA(cudaMemcpyAsync(&h_minbits, minbits.p, sizeof(h_minbits), cudaMemcpyDeviceToHost, c->stream));
+    CRX_CUDA(cudaMemcpyAsync(&h_odd, oddflag.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     CRX_CUDA(cudaStreamSynchronize(c->stream));
     double mn = -1;  // find_min_vector_distance's sentinel: K == 1 leaves -1
-    for (int a = 0; a < K; a++)
-        if (h_rowmin[a] != INFINITY && (mn == -1 || h_rowmin[a] < mn)) mn = h_rowmin[a];
+    if (h_minbits != ~0ull) memcpy(&mn, &h_minbits, sizeof(double));
+    if (h_odd) {
+        DevBuf<double> seq;
+        CRX_TRY(seq.alloc(c, 1));
+        CRX_KERNEL(c, "min_pair_seq");
+        if (p->x64) min_pair_seq_kernel<double><<<1, 32, 0, c->stream>>>(p->x64, ld, D, p->sqn, d_crow.p, K, metric, seq.p);
+        else min_pair_seq_kernel<float><<<1, 32, 0, c->stream>>>(p->x32, ld, D, p->sqn, d_crow.p, K, metric, seq.p);
+        CRX_CUDA(cudaMemcpyAsync(&mn, seq.p, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        CRX_CUDA(cudaStreamSynchronize(c->stream));
+    }
     double r0 = mn / 2;
     CRX_CUDA(cudaMemsetAsync(hist.p, 0, NH * sizeof(int), c->stream));
     { CRX_KERNEL(c, "fill_key"); fill_int_kernel<<<crx_grid(N, 256), 256, 0, c->stream>>>(key.p, N, INT_MAX); }
@@ -864,7 +907,18 @@ static int range_assign_common(crx_ctx* c, const crx_points* p, const int32_t* h
     Centroids cen;
     CRX_TRY(cen.stage(c, cmat.p, CRX_DEVICE, K, D, ld));
     CRX_CUDA(cudaStreamSynchronize(c->stream));
-    CRX_TRY(lloyd_scan(c, p, rows.p, h_cnt, cen, metric, lab.dev, dis.dev));
+    if (metric == CRX_EUCLIDEAN && K >= 32 && N >= 1024 && (int64_t)h_cnt * 4 >= N && !tc_disabled()) {
+        // most rows are left (the radius doubles per centroid): tensor-core filter + exact refine over
+        // ALL rows into scratch, then keep the results of the unassigned rows only
+        DevBuf<int32_t> tl;
+        DevBuf<double> td;
+        CRX_TRY(tl.alloc(c, N)); CRX_TRY(td.alloc(c, N));
+        CRX_TRY(lloyd_scan_tc(c, p, cen, tl.p, td.p));
+        CRX_KERNEL(c, "merge_remaining");
+        merge_remaining_kernel<<<crx_grid(N, 256), 256, 0, c->stream>>>(tl.p, td.p, N, lab.dev, dis.dev);
+    } else {
+        CRX_TRY(lloyd_scan(c, p, rows.p, h_cnt, cen, metric, lab.dev, dis.dev));
+    }
     { CRX_KERNEL(c, "self_assign"); self_assign_kernel<<<1, 32, 0, c->stream>>>(d_crow.p, K, lab.dev, dis.dev); }
     CRX_CUDA(cudaGetLastError());
     CRX_TRY(lab.flush());
