@@ -721,6 +721,101 @@ pam_pick_kernel(const T* __restrict__ x, int ld, int D, const double* __restrict
     }
 }
 
+// ---- tensor-engine generation of K8 (Euclidean): approximate row sums with a rigorous error bar from the tcgen05
+// scan, then only the rows whose interval reaches below the smallest upper end are re-summed exactly, sequentially in
+// member order (the reference's own floating-point sum), and the first minimum wins (update.hpp:110-127).
+__global__ void __launch_bounds__(256)
+pam_bounds_kernel(const int32_t* __restrict__ off, const double* __restrict__ rowsum, const double* __restrict__ rowerr, int D,
+                  int32_t* __restrict__ cand /* [N] positions */, int* __restrict__ ncand_total, int32_t* __restrict__ winner /* [K] */) {
+    __shared__ double red[256];
+    __shared__ int count, base;
+    int cl = blockIdx.x;
+    int begin = off[cl], end = off[cl + 1];
+    int n = end - begin;
+    if (n == 0) { if (threadIdx.x == 0) winner[cl] = -1; return; }
+    double m = INFINITY;
+    for (int p = begin + threadIdx.x; p < end; p += blockDim.x) m = fmin(m, rowsum[p] + rowerr[p]);
+    red[threadIdx.x] = m;
+    if (threadIdx.x == 0) count = 0;
+    __syncthreads();
+    for (int s = 128; s > 0; s >>= 1) { if (threadIdx.x < s) red[threadIdx.x] = fmin(red[threadIdx.x], red[threadIdx.x + s]); __syncthreads(); }
+    // the sequential double sums of the reference differ from the real sums by at most n ulps each
+    double U = red[0] * (1.0 + 8.0 * (double)(n + D) * 1.1102230246251565e-16);
+    int mine = 0, first = INT_MAX;
+    for (int p = begin + threadIdx.x; p < end; p += blockDim.x)
+        if (rowsum[p] - rowerr[p] <= U) { mine++; first = min(first, p); }
+    if (mine) atomicAdd(&count, mine);
+    __syncthreads();
+    if (count == 1) {  // its real sum is below every other row's by more than the rounding of the reference's sums
+        if (mine) winner[cl] = first;
+        return;
+    }
+    if (threadIdx.x == 0) { base = atomicAdd(ncand_total, count); winner[cl] = -2; count = 0; }
+    __syncthreads();
+    for (int p = begin + threadIdx.x; p < end; p += blockDim.x)
+        if (rowsum[p] - rowerr[p] <= U) cand[base + atomicAdd(&count, 1)] = p;
+}
+
+// one CTA per candidate: the 8 warps compute 256 exact distances at a time into shared memory, thread 0 adds them in
+// member order (update.hpp:118's own sequential sum) while the warps are already working on the next 256
+template <typename T>
+__global__ void __launch_bounds__(256)
+pam_exact_kernel(const T* __restrict__ x, int ld, int D, const double* __restrict__ sqn, const int32_t* __restrict__ perm,
+                 const int32_t* __restrict__ sorted_label, const int32_t* __restrict__ off, const int32_t* __restrict__ cand,
+                 int ncand, double* __restrict__ exact /* [ncand] */, unsigned long long* counters) {
+    __shared__ rw::WarpTile tiles[8];
+    __shared__ double vecs[8][128];
+    __shared__ double dist[2][256];
+    int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    int i = blockIdx.x;
+    int pos = cand[i];
+    int cl = sorted_label[pos];
+    int begin = off[cl], end = off[cl + 1];
+    int64_t mrow = perm[pos];
+    rw::stage_vector<T>(x, ld, mrow, vecs[warp]);
+    double nm = sqn[mrow], s = 0.0;
+    int buf = 0;
+    for (int b = begin; b < end + 256; b += 256, buf ^= 1) {
+        if (b < end) {
+            int p = b + warp * 32 + lane;
+            int64_t row = p < end ? (int64_t)perm[p] : -1;
+            double d = rw::dist_rows<T, CRX_EUCLIDEAN>(x, ld, D, row, vecs[warp], row >= 0 ? sqn[row] : 1.0, nm, tiles[warp]);
+            dist[buf][threadIdx.x] = d;
+        }
+        if (threadIdx.x == 0 && b > begin) {  // previous batch
+            int cntv = min(256, end - (b - 256));
+            const double* dv = dist[buf ^ 1];
+            for (int j = 0; j < cntv; j++) s = __dadd_rn(s, dv[j]);
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) { exact[i] = s; atomicAdd(&counters[CRX_CNT_PAM_EXACT], 1ull); }
+}
+
+__global__ void pam_final_kernel(const int32_t* __restrict__ perm, const int32_t* __restrict__ sorted_label,
+                                 const int32_t* __restrict__ off, const int32_t* __restrict__ cand, int ncand,
+                                 const double* __restrict__ exact, const int32_t* __restrict__ winner,
+                                 const int32_t* __restrict__ crow, int K, int32_t* __restrict__ new_crow, int* __restrict__ swapped) {
+    int cl = blockIdx.x * blockDim.x + threadIdx.x;
+    if (cl >= K) return;
+    int w = winner[cl];
+    if (w == -1) { new_crow[cl] = crow[cl]; return; }
+    if (w == -2) {
+        double best = 0.0;
+        int bp = INT_MAX;
+        for (int i = 0; i < ncand; i++) {  // few candidates overall; each cluster's are contiguous but unordered
+            int p = cand[i];
+            if (sorted_label[p] != cl) continue;
+            double v = exact[i];
+            if (bp == INT_MAX || v < best || (v == best && p < bp)) { best = v; bp = p; }
+        }
+        w = bp;
+    }
+    int row = perm[w];
+    new_crow[cl] = row;
+    if (row != crow[cl]) atomicExch(swapped, 1);
+}
+
 // ------------------------------------------------------------------------------------------------
 // K11: silhouette (silhouette.hpp:32-144)
 // ------------------------------------------------------------------------------------------------
@@ -1201,6 +1296,57 @@ int crx_k_means(crx_ctx* c, const crx_points* p, const int32_t* labels, int lmem
     return CRX_OK;
 }
 
+// tensor-engine PAM: operand rows permuted into cluster order; one CTA per 128-row tile of a cluster against the
+// cluster's own columns
+static int pam_tensor(crx_ctx* c, const crx_points* p, const Segments& seg, int K, int sx, const int32_t* d_crow, int32_t* d_new,
+                      int* d_sw) {
+    int64_t N = p->n;
+    std::vector<int32_t> off(K + 1);
+    CRX_CUDA(cudaMemcpyAsync(off.data(), seg.off, (K + 1) * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+    CRX_CUDA(cudaStreamSynchronize(c->stream));
+    std::vector<int4> jobs;
+    for (int cl = 0; cl < K; cl++)
+        for (int r = off[cl]; r < off[cl + 1]; r += 128) jobs.push_back(make_int4(r, off[cl + 1], off[cl], off[cl + 1]));
+    // longest clusters first: the tail of the grid is then made of short jobs
+    std::stable_sort(jobs.begin(), jobs.end(), [](const int4& a, const int4& b) { return a.w - a.z > b.w - b.z; });
+    DevBuf<int4> d_jobs;
+    DevBuf<float> norm_s, errw_s;
+    DevBuf<double> rowsum, rowerr, exact;
+    DevBuf<int32_t> cand, winner;
+    DevBuf<int> ncand;
+    CRX_TRY(d_jobs.alloc(c, jobs.size() + 1)); CRX_TRY(norm_s.alloc(c, N)); CRX_TRY(errw_s.alloc(c, N));
+    CRX_TRY(rowsum.alloc(c, N)); CRX_TRY(rowerr.alloc(c, N)); CRX_TRY(cand.alloc(c, N)); CRX_TRY(winner.alloc(c, K)); CRX_TRY(ncand.alloc(c, 1));
+    CRX_CUDA(cudaMemcpyAsync(d_jobs.p, jobs.data(), jobs.size() * sizeof(int4), cudaMemcpyHostToDevice, c->stream));
+    CRX_CUDA(cudaMemsetAsync(ncand.p, 0, sizeof(int), c->stream));
+    TcOperand op;
+    int st = crx_tc_prepare(c, p, 1, (double)sx, &op, seg.perm, norm_s.p, errw_s.p);
+    if (st == CRX_OK) st = crx_tc_rowsum(c, op, d_jobs.p, (int)jobs.size(), norm_s.p, errw_s.p, rowsum.p, rowerr.p);
+    if (st == CRX_OK) {
+        CRX_KERNEL(c, "pam_bounds");
+        pam_bounds_kernel<<<K, 256, 0, c->stream>>>(seg.off, rowsum.p, rowerr.p, p->d, cand.p, ncand.p, winner.p);
+    }
+    int h = 0;
+    cudaError_t e = cudaMemcpyAsync(&h, ncand.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);  // the job list and the operand are also done with here
+    op.free_all();
+    if (st != CRX_OK) return st;
+    CRX_CUDA(e);
+    CRX_TRY(exact.alloc(c, std::max(h, 1)));
+    if (h > 0) {
+        CRX_KERNEL(c, "pam_exact");
+        int g = h;
+        if (p->x64) pam_exact_kernel<double><<<g, 256, 0, c->stream>>>(p->x64, p->ld, p->d, p->sqn, seg.perm, seg.sorted, seg.off, cand.p, h, exact.p, c->counters);
+        else pam_exact_kernel<float><<<g, 256, 0, c->stream>>>(p->x32, p->ld, p->d, p->sqn, seg.perm, seg.sorted, seg.off, cand.p, h, exact.p, c->counters);
+    }
+    {
+        CRX_KERNEL(c, "pam_final");
+        pam_final_kernel<<<crx_grid(K, 128), 128, 0, c->stream>>>(seg.perm, seg.sorted, seg.off, cand.p, h, exact.p, winner.p, d_crow, K, d_new, d_sw);
+    }
+    CRX_CUDA(cudaGetLastError());
+    CRX_CUDA(cudaStreamSynchronize(c->stream));
+    return CRX_OK;
+}
+
 int crx_pam_lloyds(crx_ctx* c, const crx_points* p, const int32_t* labels, int lmem, const int32_t* crow, int K, int metric,
                    int32_t* new_crow, int* swapped) {
     CRX_REQUIRE(c && p && labels && crow && new_crow && swapped, "NULL argument");
@@ -1217,6 +1363,19 @@ int crx_pam_lloyds(crx_ctx* c, const crx_points* p, const int32_t* labels, int l
     CRX_TRY(rowsum.alloc(c, N)); CRX_TRY(d_crow.alloc(c, K)); CRX_TRY(d_new.alloc(c, K)); CRX_TRY(d_sw.alloc(c, 1));
     CRX_CUDA(cudaMemcpyAsync(d_crow.p, crow, K * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
     CRX_CUDA(cudaMemsetAsync(d_sw.p, 0, sizeof(int), c->stream));
+    double mx = 0;
+    if (metric == CRX_EUCLIDEAN && N >= 4096 && p->d <= 128 && !tc_disabled()) CRX_TRY(points_maxabs(c, p, &mx));
+    if (mx > 0.0 && std::isfinite(mx)) {
+        int st2 = pam_tensor(c, p, seg, K, scale_for(mx), d_crow.p, d_new.p, d_sw.p);
+        if (st2 != CRX_OK) { seg.free_all(); return st2; }
+        int h2 = 0;
+        CRX_CUDA(cudaMemcpyAsync(new_crow, d_new.p, K * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+        CRX_CUDA(cudaMemcpyAsync(&h2, d_sw.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+        CRX_CUDA(cudaStreamSynchronize(c->stream));
+        *swapped = h2;
+        seg.free_all();
+        return CRX_OK;
+    }
     int g = (int)((N + 7) / 8);
     {
         CRX_KERNEL(c, "pam_rowsum");

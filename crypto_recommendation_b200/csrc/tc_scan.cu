@@ -118,9 +118,15 @@ struct TcParams {
     float* best;
     float* second;
     int32_t* best_idx;
+    // row sums of Euclidean distances (PAM): one job per CTA = (first row, end of its cluster, column range of the cluster)
+    const int4* jobs;
+    const float* norm_s;   // [rows] scaled squared norms of the operand rows
+    const float* errw_s;   // [rows] error weight of a row: |d2 error| <= errw[a] + errw[b]
+    double* rowsum;
+    double* rowerr;
 };
 
-constexpr int MODE_TOPP = 0, MODE_ARGMIN = 1;
+constexpr int MODE_TOPP = 0, MODE_ARGMIN = 1, MODE_ROWSUM = 2;
 constexpr int HL = TC_LIST / 2;   // entries of one half-list (each epilogue half keeps its own top-HL)
 
 // r[j] for a run-time j: 5-level select tree (registers cannot be indexed dynamically)
@@ -178,14 +184,15 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     int32_t* li = reinterpret_cast<int32_t*>(ls + 2 * HL * TM);
     uint32_t* stile = MODE == MODE_TOPP ? reinterpret_cast<uint32_t*>(li + 2 * HL * TM)
                                         : reinterpret_cast<uint32_t*>(smem + 4 * BLK_BYTES + NS * BBLK_BYTES);  // [2][TN] codes / half norms
-    uint64_t* bars = reinterpret_cast<uint64_t*>(stile + 2 * TN);
+    constexpr int STW = MODE == MODE_ROWSUM ? 2 : 1;       // staged words per column (row sums: norm + error weight)
+    uint64_t* bars = reinterpret_cast<uint64_t*>(stile + 2 * TN * STW);
     uint64_t* a_full = bars;
     uint64_t* full = bars + 1;
     uint64_t* empty = full + NS;
     uint64_t* tfull = empty + NS;
     uint64_t* tempty = tfull + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
-    float* merge = reinterpret_cast<float*>(tmem_slot + 4);  // [TM][3] argmin hand-over between the halves
+    float* merge = reinterpret_cast<float*>(tmem_slot + 4);  // [TM][3] floats (argmin) / [TM][2] doubles (row sums): hand-over between the halves
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
@@ -203,7 +210,14 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    const int64_t row0 = p.q0 + (int64_t)blockIdx.x * TM;  // first A row of this CTA
+    int64_t row0 = p.q0 + (int64_t)blockIdx.x * TM;  // first A row of this CTA
+    int64_t row_end = p.q0 + p.nq, col0 = 0, col_end = p.nb;
+    int ntiles = p.ntiles;
+    if (MODE == MODE_ROWSUM) {
+        const int4 job = p.jobs[blockIdx.x];
+        row0 = job.x; row_end = job.y; col0 = job.z; col_end = job.w;
+        ntiles = (int)((col_end - col0 + TN - 1) / TN);
+    }
 
     if (warp == 0) {
         if (lane == 0) {
@@ -212,11 +226,11 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             for (int b = 0; b < nblk; b++) tma_load_2d(sA + b * BLK_BYTES, &tmA, b * 64, (int)row0, a_full);
             int stage = 0;
             uint32_t phase = 0;
-            for (int t = 0; t < p.ntiles; t++) {
+            for (int t = 0; t < ntiles; t++) {
                 for (int b = 0; b < nblk; b++) {
                     mbar_wait(&empty[stage], phase ^ 1);
                     mbar_arrive_expect_tx(&full[stage], (uint32_t)BBLK_BYTES);
-                    tma_load_2d(sB + stage * BBLK_BYTES, &tmB, b * 64, t * TN, &full[stage]);
+                    tma_load_2d(sB + stage * BBLK_BYTES, &tmB, b * 64, (int)col0 + t * TN, &full[stage]);
                     if (++stage == NS) { stage = 0; phase ^= 1; }
                 }
             }
@@ -229,7 +243,7 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const uint32_t a_base = smem_u32(sA), b_base = smem_u32(sB);
             int stage = 0;
             uint32_t phase = 0;
-            for (int t = 0; t < p.ntiles; t++) {
+            for (int t = 0; t < ntiles; t++) {
                 const int buf = t & 1;
                 const uint32_t bphase = (uint32_t)(t >> 1) & 1u;
                 mbar_wait(&tempty[buf], bphase ^ 1);
@@ -260,8 +274,11 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int quarter = warp & 3;            // TMEM lane quarter this warp may read
         const int half = ew >> 2;                // columns [128*half, 128*half + 128) of every tile
         const int me = quarter * 32 + lane;      // row inside the tile
-        const int64_t grow = (int64_t)blockIdx.x * TM + me;  // row relative to q0
-        const bool valid = grow < p.nq;
+        const int64_t grow = MODE == MODE_ROWSUM ? row0 + me : (int64_t)blockIdx.x * TM + me;  // row relative to q0 (absolute for row sums)
+        const bool valid = MODE == MODE_ROWSUM ? grow < row_end : grow < p.nq;
+        const float na = (MODE == MODE_ROWSUM && valid) ? p.norm_s[grow] : 0.f;
+        const float ea = (MODE == MODE_ROWSUM && valid) ? p.errw_s[grow] : 0.f;
+        double rs_sum = 0.0, rs_err = 0.0;
         uint32_t cq = 0;
         float thr = -INFINITY, best = INFINITY, second = INFINITY;
         int cnt = 0, minpos = 0, bidx = 0x7fffffff;
@@ -274,16 +291,23 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const uint32_t low = p.low_mask, high = p.high_mask;
         // staging value (packed code / half norm) of this thread's column of the NEXT tile, fetched one tile ahead
         auto fetch_col = [&](int t) -> uint32_t {
-            int64_t col = (int64_t)t * TN + etid;
-            if (t >= p.ntiles) return 0u;
+            int64_t col = col0 + (int64_t)t * TN + etid;
+            if (t >= ntiles) return 0u;
             if (MODE == MODE_TOPP) return col < p.nb ? p.ccode[col] : 0u;
+            if (MODE == MODE_ROWSUM) return __float_as_uint(col < col_end ? p.norm_s[col] : -1e30f);  // outside the cluster: d = 0
             return __float_as_uint(col < p.nb ? p.half_norm[col] : INFINITY);
         };
+        auto fetch_col2 = [&](int t) -> float {
+            int64_t col = col0 + (int64_t)t * TN + etid;
+            return (MODE == MODE_ROWSUM && t < ntiles && col < col_end) ? p.errw_s[col] : 0.f;
+        };
         uint32_t next_col = fetch_col(0);
-        for (int t = 0; t < p.ntiles; t++) {
+        float next_col2 = fetch_col2(0);
+        for (int t = 0; t < ntiles; t++) {
             const int buf = t & 1;
             const uint32_t bphase = (uint32_t)(t >> 1) & 1u;
-            stile[buf * TN + etid] = next_col;
+            stile[buf * TN * STW + etid] = next_col;
+            if (MODE == MODE_ROWSUM) { stile[buf * TN * STW + TN + etid] = __float_as_uint(next_col2); next_col2 = fetch_col2(t + 1); }
             next_col = fetch_col(t + 1);
             asm volatile("bar.sync 1, 256;" ::: "memory");
             mbar_wait(&tfull[buf], bphase);
@@ -305,7 +329,7 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
             for (int ch = 0; ch < 2; ch++) {
                 uint32_t (&r)[32] = ch == 0 ? r0 : r1;
-                const uint4* st4 = reinterpret_cast<const uint4*>(stile + buf * TN + half * 128 + rnd * 64 + ch * 32);
+                const uint4* st4 = reinterpret_cast<const uint4*>(stile + buf * TN * STW + half * 128 + rnd * 64 + ch * 32);
                 const int cbase = t * TN + half * 128 + rnd * 64 + ch * 32;
                 if (MODE == MODE_TOPP) {
                     // hot loop: running maximum of the (masked) scores, four independent chains
@@ -351,6 +375,44 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                             if (s > thr && c < p.nb) list_insert(myls, myli, s, c, cnt, thr, minpos);
                         }
                     }
+                } else if (MODE == MODE_ROWSUM) {
+                    // d = sqrt(max(0, |a|^2 + |b|^2 - 2 a.b)) and a running bound on its error.  The squared distance is
+                    // off by at most E = ea + eb (error weights of the two rows: split-fp16 dot, fp32 norms, subnormal low
+                    // parts);  |sqrt(x +- E) - sqrt(x)| <= E / sqrt(x) for x > 4E, and <= 2.5 sqrt(E) below (self pairs,
+                    // duplicates, padding: rare, handled after the hot loop)
+                    const uint4* se4 = st4 + TN / 4;
+                    float ps[4] = {0.f, 0.f, 0.f, 0.f}, pe[4] = {0.f, 0.f, 0.f, 0.f};
+                    uint32_t smallbits = 0;
+#pragma unroll
+                    for (int g = 0; g < 8; g++) {
+                        uint4 cc = st4[g], ee = se4[g];
+                        uint32_t c4[4] = {cc.x, cc.y, cc.z, cc.w}, e4[4] = {ee.x, ee.y, ee.z, ee.w};
+#pragma unroll
+                        for (int u = 0; u < 4; u++) {
+                            float tsum = na + __uint_as_float(c4[u]);
+                            float d2 = fmaf(-2.f, __uint_as_float(r[g * 4 + u]), tsum);
+                            float E = ea + __uint_as_float(e4[u]);
+                            float rs;
+                            asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(rs) : "f"(fmaxf(d2, 1e-30f)));
+                            float dd = fmaxf(d2, 0.f);
+                            bool small = dd <= 4.f * E;
+                            ps[u] = fmaf(dd, rs, ps[u]);
+                            pe[u] += small ? 0.f : E * rs;
+                            smallbits |= small ? (1u << (g * 4 + u)) : 0u;
+                        }
+                    }
+                    float psum = (ps[0] + ps[1]) + (ps[2] + ps[3]), perr = (pe[0] + pe[1]) + (pe[2] + pe[3]);
+                    if (smallbits != 0u) {
+                        const uint32_t* sn = reinterpret_cast<const uint32_t*>(st4);
+                        while (smallbits != 0u) {
+                            const int j = __ffs(smallbits) - 1;
+                            smallbits &= smallbits - 1u;
+                            if (__uint_as_float(sn[j]) > -1e29f) perr += 2.5f * sqrtf(ea + __uint_as_float(sn[TN + j]));
+                        }
+                    }
+                    // fp32 evaluation of the 32 terms: rsqrt.approx (2 ulp), products and <= 10 additions
+                    rs_sum += (double)psum;
+                    rs_err += (double)perr * 1.00001 + 1.5e-6 * (double)psum;
                 } else {
 #pragma unroll
                     for (int g = 0; g < 8; g++) {
@@ -375,6 +437,14 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     p.list_s[grow * TC_LIST + half * HL + e] = myls[e * TM];
                     p.list_i[grow * TC_LIST + half * HL + e] = myli[e * TM];
                 }
+            }
+        } else if (MODE == MODE_ROWSUM) {
+            double* dm = reinterpret_cast<double*>(merge);
+            if (half == 1) { dm[me * 2 + 0] = rs_sum; dm[me * 2 + 1] = rs_err; }
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            if (half == 0 && valid) {
+                p.rowsum[grow] = rs_sum + dm[me * 2 + 0];
+                p.rowerr[grow] = rs_err + dm[me * 2 + 1];
             }
         } else {
             if (half == 1) { merge[me * 3 + 0] = best; merge[me * 3 + 1] = second; merge[me * 3 + 2] = __int_as_float(bidx); }
@@ -401,17 +471,26 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 // ---------------------------------------------------------------- operand preparation
 template <typename T>
 __global__ void tc_prep_rows_kernel(const T* __restrict__ x, int ld, int D, const double* __restrict__ sqn, int64_t n,
-                                    int mode, double scale, int nkb, __half* __restrict__ out) {
-    int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+                                    int mode, double scale, int nkb, const int32_t* __restrict__ rowmap, __half* __restrict__ out,
+                                    float* __restrict__ norm_s, float* __restrict__ errw_s) {
+    int64_t orow = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     int lane = threadIdx.x & 31;
-    if (row >= n) return;
+    if (orow >= n) return;
+    int64_t row = rowmap ? (int64_t)rowmap[orow] : orow;  // operand row orow holds point row
     double s = scale;
     if (mode == 0) {
         double nn = sqn[row];
         s = nn > 0.0 ? scale / sqrt(nn) : 0.0;
     }
+    if (norm_s && lane == 0) {
+        // 6.3e-6 n covers the three-product split-fp16 dot with fp32 accumulation (2 x 3e-6 |a||b| <= 3e-6 (na + nb))
+        // and the fp32 norms; the square-root term covers low parts that fall below the fp16 normal range
+        double nn = sqn[row] * scale * scale;
+        norm_s[orow] = (float)nn;
+        errw_s[orow] = (float)((6.3e-6 * nn + 5.97e-8 * sqrt((double)D * nn)) * 1.000001);
+    }
     int W = nkb * 64;
-    __half* o = out + row * (size_t)(2 * W);
+    __half* o = out + orow * (size_t)(2 * W);
     for (int c = lane; c < W; c += 32) {
         double v = c < D ? (double)x[row * ld + c] * s : 0.0;
         __half hi = __double2half(v);
@@ -454,7 +533,7 @@ int make_tensor_map(const TcOperand& op, int box_rows, CUtensorMap* tm) {
 size_t smem_for(int mode) {
     size_t s = (size_t)4 * BLK_BYTES + (size_t)NS * BBLK_BYTES + 2 * TN * 4 + (1 + 2 * NS + 4) * 8 + 16;
     if (mode == MODE_TOPP) s += (size_t)2 * HL * TM * 8;
-    else s += TM * 3 * 4;
+    else s += TM * 2 * 8 + (mode == MODE_ROWSUM ? 2 * TN * 4 : 0);
     return s;
 }
 
@@ -477,15 +556,15 @@ int alloc_operand(crx_ctx* c, int64_t rows, int D, TcOperand* out) {
 
 }  // namespace
 
-int crx_tc_prepare(crx_ctx* c, const crx_points* p, int mode, double scale_log2, TcOperand* out) {
+int crx_tc_prepare(crx_ctx* c, const crx_points* p, int mode, double scale_log2, TcOperand* out, const int32_t* rowmap, float* norm_s, float* errw_s) {
     CRX_REQUIRE(p->d <= 128, "tensor path supports D <= 128");
     CRX_TRY(alloc_operand(c, p->n, p->d, out));
     out->scale_log2 = scale_log2;
     double scale = ldexp(1.0, (int)scale_log2);
     int g = (int)((p->n + 7) / 8);
     CRX_KERNEL(c, "tc_prep");
-    if (p->x64) tc_prep_rows_kernel<double><<<g, 256, 0, c->stream>>>(p->x64, p->ld, p->d, p->sqn, p->n, mode, scale, out->nkb, (__half*)out->data);
-    else tc_prep_rows_kernel<float><<<g, 256, 0, c->stream>>>(p->x32, p->ld, p->d, p->sqn, p->n, mode, scale, out->nkb, (__half*)out->data);
+    if (p->x64) tc_prep_rows_kernel<double><<<g, 256, 0, c->stream>>>(p->x64, p->ld, p->d, p->sqn, p->n, mode, scale, out->nkb, rowmap, (__half*)out->data, norm_s, errw_s);
+    else tc_prep_rows_kernel<float><<<g, 256, 0, c->stream>>>(p->x32, p->ld, p->d, p->sqn, p->n, mode, scale, out->nkb, rowmap, (__half*)out->data, norm_s, errw_s);
     CRX_CUDA(cudaGetLastError());
     return CRX_OK;
 }
@@ -496,7 +575,7 @@ int crx_tc_prepare_matrix(crx_ctx* c, const double* m, int K, int D, int ld, dou
     out->scale_log2 = scale_log2;
     int g = (K + 7) / 8;
     CRX_KERNEL(c, "tc_prep");
-    tc_prep_rows_kernel<double><<<g, 256, 0, c->stream>>>(m, ld, D, nullptr, K, 1, ldexp(1.0, (int)scale_log2), out->nkb, (__half*)out->data);
+    tc_prep_rows_kernel<double><<<g, 256, 0, c->stream>>>(m, ld, D, nullptr, K, 1, ldexp(1.0, (int)scale_log2), out->nkb, nullptr, (__half*)out->data, nullptr, nullptr);
     CRX_CUDA(cudaGetLastError());
     return CRX_OK;
 }
@@ -547,6 +626,25 @@ int crx_tc_argmin(crx_ctx* c, const TcOperand& A, int64_t r0, int64_t nr, const 
     int grid = (int)((nr + TM - 1) / TM);
     CRX_KERNEL(c, "tc_argmin_scan");
     tc_scan_kernel<MODE_ARGMIN, false><<<grid, NTHREADS_K, smem, c->stream>>>(tmA, tmB, p);
+    CRX_CUDA(cudaGetLastError());
+    return CRX_OK;
+}
+
+int crx_tc_rowsum(crx_ctx* c, const TcOperand& A, const int4* d_jobs, int njobs, const float* norm_s, const float* errw_s,
+                  double* rowsum, double* rowerr) {
+    if (njobs == 0) return CRX_OK;
+    CUtensorMap tmA, tmB;
+    CRX_TRY(make_tensor_map(A, TM, &tmA));
+    CRX_TRY(make_tensor_map(A, TN, &tmB));
+    TcParams p;
+    memset(&p, 0, sizeof(p));
+    p.nkb = A.nkb;
+    p.last_steps = last_steps_of(A);
+    p.jobs = d_jobs; p.norm_s = norm_s; p.errw_s = errw_s; p.rowsum = rowsum; p.rowerr = rowerr;
+    size_t smem = smem_for(MODE_ROWSUM);
+    CRX_CUDA(cudaFuncSetAttribute(tc_scan_kernel<MODE_ROWSUM, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CRX_KERNEL(c, "tc_rowsum_scan");
+    tc_scan_kernel<MODE_ROWSUM, false><<<njobs, NTHREADS_K, smem, c->stream>>>(tmA, tmB, p);
     CRX_CUDA(cudaGetLastError());
     return CRX_OK;
 }

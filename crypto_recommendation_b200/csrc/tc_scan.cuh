@@ -22,7 +22,9 @@ struct TcOperand {
 };
 
 // mode 0: rows scaled to unit length times 2^10 (cosine);  mode 1: all rows times 2^scale_log2
-int crx_tc_prepare(crx_ctx* c, const crx_points* p, int mode, double scale_log2, TcOperand* out);
+// rowmap (nullable): operand row i holds point rowmap[i];  norm_s (nullable): receives the scaled squared norms
+int crx_tc_prepare(crx_ctx* c, const crx_points* p, int mode, double scale_log2, TcOperand* out, const int32_t* rowmap = nullptr,
+                   float* norm_s = nullptr, float* errw_s = nullptr);
 // same for a [K][ld] double matrix (centroids)
 int crx_tc_prepare_matrix(crx_ctx* c, const double* m, int K, int D, int ld, double scale_log2, TcOperand* out);
 
@@ -39,3 +41,8 @@ int crx_tc_topp(crx_ctx* c, const TcOperand& A, int64_t q0, int64_t nq, const Tc
 // half_norm[j] - dot(a, b_j) (scaled units) and the best column.
 int crx_tc_argmin(crx_ctx* c, const TcOperand& A, int64_t r0, int64_t nr, const TcOperand& B, const float* half_norm,
                   float* best, float* second, int32_t* best_idx);
+
+// PAM row sums: job j = {first operand row of a 128-row tile, end row of its cluster, first column, end column};
+// rowsum[row] ~ sum over the cluster of the Euclidean distance (scaled by 2^scale), rowerr[row] bounds its error.
+int crx_tc_rowsum(crx_ctx* c, const TcOperand& A, const int4* d_jobs, int njobs, const float* norm_s, const float* errw_s,
+                  double* rowsum, double* rowerr);

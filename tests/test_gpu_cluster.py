@@ -185,6 +185,47 @@ def test_pam_exact_duplicates(ctx, port):
     assert ctx.counters()["pam_exact"] >= 2
 
 
+@pytest.mark.parametrize("dtype,d", [(np.float32, 24), (np.float64, 100)])
+def test_pam_tensor_path(ctx, port, dtype, d):
+    # N >= 4096 Euclidean goes through the tcgen05 row-sum scan + exact re-sum of the rows it cannot separate;
+    # ragged clusters: an empty one, a singleton, sizes that are not multiples of the 128-row tile
+    n, K = 9000, 6
+    X = synth.gaussian_mixture(n, d, 4, seed=67, dtype=dtype)
+    X64 = X.astype(np.float64)
+    cidx = port.rand_selection(X64, 4, 9)
+    lab4, _ = port.lloyds_assignment(X64, X64[cidx], cidx, EUCLIDEAN)
+    lab = lab4.copy()
+    lab[17] = 5                                   # singleton cluster 5, cluster 4 stays empty
+    cidx = np.concatenate([cidx, [3, 17]]).astype(np.int32)
+    P = ctx.points(X)
+    ctx.profile(True)
+    ctx.profile_reset()
+    sw, new = capi.pam_lloyds(ctx, P, lab, cidx, EUCLIDEAN)
+    _, launches = ctx.kernel_time("tc_rowsum_scan")
+    ctx.profile(False)
+    psw, pnew = port.pam_lloyds(X64, lab, cidx, EUCLIDEAN)
+    assert sw == psw and np.array_equal(new, pnew)
+    assert launches == 1, "the tensor path ran"
+
+
+def test_pam_tensor_path_duplicates_first_wins(ctx, port):
+    # every row appears twice in its cluster: the two copies have identical sums, the earlier member must win, and
+    # the tensor bounds cannot separate them -> exact sequential re-sum
+    rng = np.random.default_rng(12)
+    base = rng.normal(size=(2600, 16)).astype(np.float32)
+    base[1300:] += 6.0
+    X = np.concatenate([base, base])
+    lab = np.concatenate([np.zeros(1300, np.int32), np.ones(1300, np.int32)] * 2)
+    cidx = np.array([5200 - 1, 1300], np.int32)
+    P = ctx.points(X)
+    ctx.counters(reset=True)
+    sw, new = capi.pam_lloyds(ctx, P, lab, cidx, EUCLIDEAN)
+    psw, pnew = port.pam_lloyds(X.astype(np.float64), lab, cidx, EUCLIDEAN)
+    assert sw == psw and np.array_equal(new, pnew)
+    assert (new < 2600).all()
+    assert ctx.counters()["pam_exact"] >= 4
+
+
 def test_cluster_sums_chunking(ctx, port):
     # one cluster far larger than the summation chunk: deterministic, and equal to the sequential sum to ~1e-15
     X = synth.gaussian_mixture(9000, 100, 3, seed=71, dtype=np.float32)

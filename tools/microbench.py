@@ -22,6 +22,8 @@ def main():
     from crypto_recommendation_b200 import capi
     ap = argparse.ArgumentParser()
     ap.add_argument("--scale", type=float, default=1.0)
+    ap.add_argument("--pam-only", action="store_true")
+    ap.add_argument("--pam-points", type=int, default=500_000)
     a = ap.parse_args()
     dev = torch.device("cuda", 0)
     stream = torch.cuda.Stream(dev)
@@ -53,48 +55,52 @@ def main():
         ks = {p: round(ctx.kernel_time(p)[0] / reps, 4) for p in prefixes}
         return {"wall_ms": round(wall, 3), "kernel_ms": ks}
 
-    # ---- C2 shape: 1M x 100, cosine L=5 k=4
-    n = int(1_000_000 * a.scale)
-    X = gen(n, 100, 64, 1)
-    P = capi.Points(ctx, X)
-    r = timed("lsh_c2", lambda: capi.LshTables(ctx, P, "cosine", 4, 5, 100, 0.4, 7).close(), ["hash_rows", "bucket_offsets", "iota"])
-    r["hash_gbs"] = n * (4 * 100 + 4 * 5) / (r["kernel_ms"]["hash_rows"] * 1e6)
-    r["hash_frac_of_hbm"] = r["hash_gbs"] / hbm
-    out["lsh_build_c2_1M_x100_cos_L5k4"] = r
-    P.close(); del X
-    # ---- C3 shape: 10M x 128 euclidean cube d'=16
-    n = int(10_000_000 * a.scale)
-    X = gen(n, 128, 1024, 2)
-    P = capi.Points(ctx, X)
-    del X
-    cube = [None]
-    def build_cube():
-        if cube[0] is not None: cube[0].close()
-        cube[0] = capi.Hypercube(ctx, P, "euclidean", 16, 4.0, 9)
-    r = timed("cube_c3", build_cube, ["hash_rows", "cube_keys", "cube_heads", "cube_vertex", "bucket_offsets"], reps=2)
-    r["hash_gbs"] = n * (4 * 128 + 4 * 16) / (r["kernel_ms"]["hash_rows"] * 1e6)
-    r["hash_frac_of_hbm"] = r["hash_gbs"] / hbm
-    out["cube_build_c3_10M_x128_d16"] = r
-    K = 1024
-    cidx = capi.rand_selection(ctx, P, K, 3)
-    r = timed("cube_range", lambda: capi.cube_range_assignment(ctx, P, cube[0], cidx, "euclidean", 64), ["range_fire", "range_finalize", "min_pair", "lloyd_scan", "compact", "tc_argmin", "lloyd_refine"], reps=1)
-    out["cube_range_assignment_c3_K1024_probes64"] = r
-    # ---- k-means++ rounds on the same 10M x 128 points (K = 9: 8 rounds)
-    r = timed("kpp", lambda: capi.k_means_pp(ctx, P, 9, "euclidean", 5), ["kpp_update", "kpp_prob", "kpp_pick"], reps=1)
-    r["per_round_ms"] = r["kernel_ms"]["kpp_update"] / 8
-    r["update_gbs"] = n * (4 * 128 + 16) / (r["per_round_ms"] * 1e6)
-    r["update_frac_of_hbm"] = r["update_gbs"] / hbm
-    out["kmeanspp_round_10M_x128"] = r
-    # ---- cluster sums (k-means update) on 10M x 128, K=1024
-    lab = torch.randint(0, K, (n,), dtype=torch.int32, device=dev)
-    sums = torch.empty((K, 128), dtype=torch.float64, device=dev); counts = torch.empty(K, dtype=torch.int64, device=dev)
-    r = timed("sums", lambda: capi.cluster_sums(ctx, P, lab, K, sums, counts), ["chunk_sums", "combine_sums", "bucket_offsets", "iota"])
-    r["gbs"] = n * (4 * 128 + 4) / (r["wall_ms"] * 1e6)
-    r["frac_of_hbm"] = r["gbs"] / hbm
-    out["cluster_sums_10M_x128_K1024"] = r
-    cube[0].close(); P.close()
+    def c2_c3():
+        # ---- C2 shape: 1M x 100, cosine L=5 k=4
+        n = int(1_000_000 * a.scale)
+        X = gen(n, 100, 64, 1)
+        P = capi.Points(ctx, X)
+        r = timed("lsh_c2", lambda: capi.LshTables(ctx, P, "cosine", 4, 5, 100, 0.4, 7).close(), ["hash_rows", "bucket_offsets", "iota"])
+        r["hash_gbs"] = n * (4 * 100 + 4 * 5) / (r["kernel_ms"]["hash_rows"] * 1e6)
+        r["hash_frac_of_hbm"] = r["hash_gbs"] / hbm
+        out["lsh_build_c2_1M_x100_cos_L5k4"] = r
+        P.close(); del X
+        # ---- C3 shape: 10M x 128 euclidean cube d'=16
+        n = int(10_000_000 * a.scale)
+        X = gen(n, 128, 1024, 2)
+        P = capi.Points(ctx, X)
+        del X
+        cube = [None]
+        def build_cube():
+            if cube[0] is not None: cube[0].close()
+            cube[0] = capi.Hypercube(ctx, P, "euclidean", 16, 4.0, 9)
+        r = timed("cube_c3", build_cube, ["hash_rows", "cube_keys", "cube_heads", "cube_vertex", "bucket_offsets"], reps=2)
+        r["hash_gbs"] = n * (4 * 128 + 4 * 16) / (r["kernel_ms"]["hash_rows"] * 1e6)
+        r["hash_frac_of_hbm"] = r["hash_gbs"] / hbm
+        out["cube_build_c3_10M_x128_d16"] = r
+        K = 1024
+        cidx = capi.rand_selection(ctx, P, K, 3)
+        r = timed("cube_range", lambda: capi.cube_range_assignment(ctx, P, cube[0], cidx, "euclidean", 64), ["range_fire", "range_finalize", "min_pair", "lloyd_scan", "compact", "tc_argmin", "lloyd_refine"], reps=1)
+        out["cube_range_assignment_c3_K1024_probes64"] = r
+        # ---- k-means++ rounds on the same 10M x 128 points (K = 9: 8 rounds)
+        r = timed("kpp", lambda: capi.k_means_pp(ctx, P, 9, "euclidean", 5), ["kpp_update", "kpp_prob", "kpp_pick"], reps=1)
+        r["per_round_ms"] = r["kernel_ms"]["kpp_update"] / 8
+        r["update_gbs"] = n * (4 * 128 + 16) / (r["per_round_ms"] * 1e6)
+        r["update_frac_of_hbm"] = r["update_gbs"] / hbm
+        out["kmeanspp_round_10M_x128"] = r
+        # ---- cluster sums (k-means update) on 10M x 128, K=1024
+        lab = torch.randint(0, K, (n,), dtype=torch.int32, device=dev)
+        sums = torch.empty((K, 128), dtype=torch.float64, device=dev); counts = torch.empty(K, dtype=torch.int64, device=dev)
+        r = timed("sums", lambda: capi.cluster_sums(ctx, P, lab, K, sums, counts), ["chunk_sums", "combine_sums", "bucket_offsets", "iota"])
+        r["gbs"] = n * (4 * 128 + 4) / (r["wall_ms"] * 1e6)
+        r["frac_of_hbm"] = r["gbs"] / hbm
+        out["cluster_sums_10M_x128_K1024"] = r
+        cube[0].close(); P.close()
+
+    if not a.pam_only:
+        c2_c3()
     # ---- C5 shape (scaled): PAM update + LSH range assignment, 5M x 100, K=256 -> here 500k x 100, K=256
-    n = int(500_000 * a.scale)
+    n = int(a.pam_points * a.scale)
     X = gen(n, 100, 256, 4)
     P = capi.Points(ctx, X)
     del X
@@ -102,13 +108,14 @@ def main():
     t = capi.LshTables(ctx, P, "euclidean", 4, 5, 100, 0.4, 11)
     cidx = capi.k_means_pp(ctx, P, K, "euclidean", 6)
     r = timed("lsh_range", lambda: capi.lsh_range_assignment(ctx, P, t, cidx, "euclidean"), ["range_fire", "range_finalize", "lloyd_scan", "tc_argmin", "lloyd_refine"], reps=1)
-    out["lsh_range_assignment_500k_x100_K256"] = r
+    out["lsh_range_assignment_%d_x100_K256" % n] = r
     lab, _, _ = capi.lsh_range_assignment(ctx, P, t, cidx, "euclidean")
-    r = timed("pam", lambda: capi.pam_lloyds(ctx, P, lab, cidx, "euclidean"), ["pam_rowsum", "pam_pick"], reps=1)
+    r = timed("pam", lambda: capi.pam_lloyds(ctx, P, lab, cidx, "euclidean"), ["pam_rowsum", "pam_pick", "tc_rowsum_scan", "tc_prep", "pam_bounds", "pam_exact", "pam_final"], reps=1)
     sizes = np.bincount(lab, minlength=K).astype(np.float64)
     r["pair_distances"] = float((sizes ** 2).sum())
-    r["pairs_per_s"] = r["pair_distances"] / (r["kernel_ms"]["pam_rowsum"] * 1e-3)
-    out["pam_update_500k_x100_K256"] = r
+    r["pairs_per_s"] = r["pair_distances"] / (max(r["kernel_ms"].get("pam_rowsum", 0), r["kernel_ms"].get("tc_rowsum_scan", 0), 1e-9) * 1e-3)
+    r["pam_exact_resums"] = ctx.counters()["pam_exact"]
+    out["pam_update_%d_x100_K256" % n] = r
     print(json.dumps(out))
 
 
