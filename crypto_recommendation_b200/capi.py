@@ -31,6 +31,7 @@ SYMBOLS = [
     "crx_lsh_range_assignment", "crx_cube_range_assignment", "crx_cluster_sums", "crx_k_means_finish",
     "crx_k_means", "crx_pam_lloyds", "crx_silhouette_cluster", "crx_recommend_lsh", "crx_recommend_cluster",
     "crx_parallel_quickSort", "crx_get_P_closest", "crx_get_top_N_recom", "crx_lsh_hash_vector",
+    "crx_user_vectors_build",
 ]
 
 
@@ -445,3 +446,15 @@ def get_top_N_recom(ctx, users, neighbor_rows, similarities, query_set, query_ro
     _check(lib().crx_get_top_N_recom(ctx.h, users.h, _ptr(nb)[0], _ptr(sm)[0], ctypes.c_int64(len(nb)), query_set.h,
                                      ctypes.c_int64(query_row), int(N), _ptr(pred)[0], _ptr(recs)[0]))
     return recs, pred
+
+
+def user_vectors_build(ctx, mention_user, mention_coin, mention_score, n_users, n_coins):
+    """tweets_to_user_vectors / clusters_to_user_vectors (crypto_rec.hpp:79-210) after string resolution.
+    Returns (X[n_users][n_coins], unknown u8, known_mean, keep u8); rows with keep == 0 are the users the reference drops."""
+    mu = _np(mention_user, np.int32); mc = _np(mention_coin, np.int32); ms = _np(mention_score, np.float64)
+    assert len(mu) == len(mc) == len(ms)
+    X = np.zeros((n_users, n_coins)); unk = np.zeros((n_users, n_coins), np.uint8)
+    mean = np.zeros(n_users); keep = np.zeros(n_users, np.uint8)
+    _check(lib().crx_user_vectors_build(ctx.h, _ptr(mu)[0], _ptr(mc)[0], _ptr(ms)[0], ctypes.c_int64(len(mu)), ctypes.c_int64(n_users),
+                                        int(n_coins), _ptr(X)[0], _ptr(unk)[0], _ptr(mean)[0], _ptr(keep)[0], HOST))
+    return X, unk, mean, keep

@@ -113,6 +113,7 @@ struct TcParams {
     uint32_t low_mask, high_mask;
     float* list_s;
     int32_t* list_i;
+    int nprod;             // 3 = hi.hi + lo.hi + hi.lo (split-fp16), 1 = hi.hi only (coarse filter)
     // argmin
     const float* half_norm;
     float* best;
@@ -226,8 +227,9 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             for (int b = 0; b < nblk; b++) tma_load_2d(sA + b * BLK_BYTES, &tmA, b * 64, (int)row0, a_full);
             int stage = 0;
             uint32_t phase = 0;
+            const int nload = p.nprod == 1 ? p.nkb : nblk;   // single-product filter: high parts only
             for (int t = 0; t < ntiles; t++) {
-                for (int b = 0; b < nblk; b++) {
+                for (int b = 0; b < nload; b++) {
                     mbar_wait(&empty[stage], phase ^ 1);
                     mbar_arrive_expect_tx(&full[stage], (uint32_t)BBLK_BYTES);
                     tma_load_2d(sB + stage * BBLK_BYTES, &tmB, b * 64, (int)col0 + t * TN, &full[stage]);
@@ -249,7 +251,8 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 mbar_wait(&tempty[buf], bphase ^ 1);
                 tc_fence_after();
                 const uint32_t d = tmem_base + (uint32_t)(buf * TN);  // 256 fp32 columns per buffer
-                for (int b = 0; b < nblk; b++) {
+                const int nload = p.nprod == 1 ? p.nkb : nblk;
+                for (int b = 0; b < nload; b++) {
                     mbar_wait(&full[stage], phase);
                     tc_fence_after();
                     const uint32_t bs = b_base + stage * BBLK_BYTES;
@@ -257,7 +260,7 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     const int steps = j == p.nkb - 1 ? p.last_steps : 4;
                     if (b < p.nkb) {  // B.hi_j with A.hi_j and A.lo_j
                         mma_block(d, a_base + j * BLK_BYTES, bs, b == 0 ? 0u : 1u, steps);
-                        mma_block(d, a_base + (p.nkb + j) * BLK_BYTES, bs, 1u, steps);
+                        if (p.nprod != 1) mma_block(d, a_base + (p.nkb + j) * BLK_BYTES, bs, 1u, steps);
                     } else {          // B.lo_j with A.hi_j
                         mma_block(d, a_base + j * BLK_BYTES, bs, 1u, steps);
                     }
@@ -591,6 +594,7 @@ int crx_tc_topp(crx_ctx* c, const TcOperand& A, int64_t q0, int64_t nq, const Tc
     memset(&p, 0, sizeof(p));
     p.q0 = q0; p.nq = nq; p.nb = B.rows; p.ntiles = (int)((B.rows + TN - 1) / TN); p.nkb = A.nkb;
     p.last_steps = last_steps_of(A);
+    p.nprod = 3;
     p.qcode = qcode; p.ccode = ccode;
     uint32_t low = 0, high = 0;
     for (int l = 0; l < L; l++) { low |= 1u << (l * k); high |= 1u << (l * k + k - 1); }
@@ -620,6 +624,7 @@ int crx_tc_argmin(crx_ctx* c, const TcOperand& A, int64_t r0, int64_t nr, const 
     memset(&p, 0, sizeof(p));
     p.q0 = r0; p.nq = nr; p.nb = B.rows; p.ntiles = (int)((B.rows + TN - 1) / TN); p.nkb = A.nkb;
     p.last_steps = last_steps_of(A);
+    p.nprod = 3;
     p.half_norm = half_norm; p.best = best; p.second = second; p.best_idx = best_idx;
     size_t smem = smem_for(MODE_ARGMIN);
     CRX_CUDA(cudaFuncSetAttribute(tc_scan_kernel<MODE_ARGMIN, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -640,6 +645,7 @@ int crx_tc_rowsum(crx_ctx* c, const TcOperand& A, const int4* d_jobs, int njobs,
     memset(&p, 0, sizeof(p));
     p.nkb = A.nkb;
     p.last_steps = last_steps_of(A);
+    p.nprod = 3;
     p.jobs = d_jobs; p.norm_s = norm_s; p.errw_s = errw_s; p.rowsum = rowsum; p.rowerr = rowerr;
     size_t smem = smem_for(MODE_ROWSUM);
     CRX_CUDA(cudaFuncSetAttribute(tc_scan_kernel<MODE_ROWSUM, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -177,6 +177,18 @@ int crx_get_top_N_recom(crx_ctx* ctx, const crx_points* users, const int32_t* ne
 /* parallel_quickSort (crypto_rec.hpp:269) on the device, one thread: known-answer tests only */
 int crx_parallel_quickSort(crx_ctx* ctx, double* sims /* host, in/out */, int32_t* ids /* host, in/out */, int n);
 
+/* ---- the step in front of the path: user rating vectors from tweet mentions ------------------------------
+ * tweets_to_user_vectors (crypto_rec.hpp:79-140) and clusters_to_user_vectors (:143-210) after the strings are
+ * resolved to indices: mention i says "tweet with sentiment mention_score[i] names coin mention_coin[i], posted
+ * by user (or assigned to cluster) mention_user[i]", in the order the reference walks its tweets.  Per user:
+ * X[u][c] = sum of the positive scores of its mentions of c (mention order), known coins = mentioned ones,
+ * known_mean[u] = sum of the known coordinates (coin order) / their count, unknown coordinates := known_mean,
+ * unknown[u][c] = 1 for those, keep[u] = 0 when every coordinate is 0 (the reference drops such users, :127;
+ * their row is left as accumulated).  All buffers live in `mem`. */
+int crx_user_vectors_build(crx_ctx* ctx, const int32_t* mention_user, const int32_t* mention_coin, const double* mention_score,
+                           int64_t n_mentions, int64_t n_users, int n_coins, double* X, uint8_t* unknown, double* known_mean,
+                           uint8_t* keep, int mem);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,10 +1,23 @@
-// Drop-in for the recommendation core of lib/crypto_rec.hpp (reference crypto_rec.hpp:214-345).  The data
-// preparation (:79-210) and 10-fold validation helpers (:349-449) of the same header are out of scope.
+// Drop-in for lib/crypto_rec.hpp: the recommendation core (reference crypto_rec.hpp:214-345), the user-vector
+// construction in front of it (:79-210, on the GPU through crx_user_vectors_build once the strings are resolved to
+// indices; available when the reference's lib/data_structures/tweet.h is on the include path) and the 10-fold
+// validation helpers behind it (:347-449, host-side container shuffling exactly as the reference does it).
 #ifndef CRYPTO_REC_HPP
 #define CRYPTO_REC_HPP
 
+#include <cstdlib>
+#include <ctime>
+#include <set>
 #include <string>
+#include <unordered_map>
 #include <vector>
+
+#if defined(__has_include)
+#if __has_include("./data_structures/tweet.h")
+#include "./data_structures/tweet.h"
+#define CRX_HAVE_TWEET 1
+#endif
+#endif
 
 #include "./data_structures/cust_vector.hpp"
 #include "lsh_cube.hpp"
@@ -95,6 +108,131 @@ std::vector<int> get_top_N_recom(std::vector<CustVector<dim_type>*>& neighbors, 
     for (int64_t i = 0; i < n; i++) rows[i] = (int32_t)i;
     crx::check(crx_get_top_N_recom(crx::context(), U.pts, rows.data(), nullptr, n, U.pts, n, N, nullptr, recs.data()), "crx_get_top_N_recom");
     return std::vector<int>(recs.begin(), recs.end());
+}
+
+// ------------------------------------------------------------------------------------------------
+// user vectors (crypto_rec.hpp:79-210)
+// ------------------------------------------------------------------------------------------------
+namespace crx {
+// mentions -> one CustVector per kept user; ids[u] names user u
+template <typename dim_type>
+std::vector<CustVector<dim_type> > build_user_vectors(const std::vector<int32_t>& m_user, const std::vector<int32_t>& m_coin,
+                                                      const std::vector<double>& m_score, const std::vector<std::string>& ids,
+                                                      int crypto_num) {
+    int64_t n_users = (int64_t)ids.size();
+    std::vector<double> X((size_t)n_users * crypto_num), mean(n_users);
+    std::vector<uint8_t> unk((size_t)n_users * crypto_num), keep(n_users);
+    std::vector<CustVector<dim_type> > out;
+    if (n_users == 0 || crypto_num <= 0) return out;
+    check(crx_user_vectors_build(context(), m_user.data(), m_coin.data(), m_score.data(), (int64_t)m_user.size(), n_users, crypto_num,
+                                 X.data(), unk.data(), mean.data(), keep.data(), CRX_HOST), "crx_user_vectors_build");
+    for (int64_t u = 0; u < n_users; u++) {
+        if (!keep[u]) continue;  // "useless": nothing but zeros (:127 / :196)
+        std::vector<dim_type> dims(X.begin() + (size_t)u * crypto_num, X.begin() + (size_t)(u + 1) * crypto_num);
+        std::set<int> unknown;
+        for (int j = 0; j < crypto_num; j++) if (unk[(size_t)u * crypto_num + j]) unknown.insert(unknown.end(), j);
+        out.emplace_back(CustVector<dim_type>(ids[u], dims, unknown, mean[u]));
+    }
+    return out;
+}
+}  // namespace crx
+
+#ifdef CRX_HAVE_TWEET
+// crypto_rec.hpp:79-140.  Users come out in the iteration order of an unordered_map keyed by user id that saw
+// the same insertions as the reference's user_map, i.e. in the reference's own order.
+template <typename dim_type>
+std::vector<CustVector<dim_type> > tweets_to_user_vectors(std::unordered_map<std::string, Tweet>& tweets, int crypto_num) {
+    std::unordered_map<std::string, int32_t> first_seen;  // user id -> provisional index
+    std::vector<int32_t> m_user, m_coin;
+    std::vector<double> m_score;
+    for (auto& kv : tweets) {
+        std::string uid = kv.second.getUserId();
+        auto it = first_seen.find(uid);
+        if (it == first_seen.end()) it = first_seen.emplace(uid, (int32_t)first_seen.size()).first;
+        double score = kv.second.getSentimentScore();
+        for (int coin : kv.second.getCryptoIndexes()) { m_user.push_back(it->second); m_coin.push_back(coin); m_score.push_back(score); }
+    }
+    // renumber in map iteration order = output order
+    std::vector<int32_t> order(first_seen.size());
+    std::vector<std::string> ids;
+    ids.reserve(first_seen.size());
+    for (auto& kv : first_seen) { order[kv.second] = (int32_t)ids.size(); ids.push_back(kv.first); }
+    for (auto& u : m_user) u = order[u];
+    return crx::build_user_vectors<dim_type>(m_user, m_coin, m_score, ids, crypto_num);
+}
+
+// crypto_rec.hpp:143-210: one "user" per cluster of tweet vectors, id = the cluster number
+template <typename dim_type>
+std::vector<CustVector<dim_type> > clusters_to_user_vectors(std::unordered_map<std::string, Tweet>& tweets,
+                                                            std::vector<CustVector<dim_type> >& vectors, int crypto_num, int user_num) {
+    std::vector<int32_t> m_user, m_coin;
+    std::vector<double> m_score;
+    for (auto& vec : vectors) {
+        auto it = tweets.find(vec.getId());
+        if (it == tweets.end()) continue;
+        double score = it->second.getSentimentScore();
+        for (int coin : it->second.getCryptoIndexes()) { m_user.push_back(vec.getCluster()); m_coin.push_back(coin); m_score.push_back(score); }
+    }
+    std::vector<std::string> ids(user_num > 0 ? user_num : 0);
+    for (int u = 0; u < user_num; u++) ids[u] = std::to_string(u);
+    return crx::build_user_vectors<dim_type>(m_user, m_coin, m_score, ids, crypto_num);
+}
+#endif  // CRX_HAVE_TWEET
+
+// ------------------------------------------------------------------------------------------------
+// 10-fold validation helpers (crypto_rec.hpp:347-449): container shuffling driven by srand(time)/rand()
+// ------------------------------------------------------------------------------------------------
+template <typename dim_type>
+std::vector<std::vector<CustVector<dim_type> > > split_to_10(std::vector<CustVector<dim_type> > input_vectors) {
+    srand((int)time(0));
+    size_t per_fold = input_vectors.size() / 10;
+    std::vector<std::vector<CustVector<dim_type> > > folds(10);
+    for (auto& fold : folds) {
+        fold.reserve(per_fold);
+        while (fold.size() < per_fold && !input_vectors.empty()) {
+            size_t pick = (size_t)rand() % input_vectors.size();
+            fold.emplace_back(input_vectors[pick]);
+            input_vectors.erase(input_vectors.begin() + pick);
+        }
+    }
+    return folds;
+}
+
+template <typename dim_type>
+std::vector<CustVector<dim_type> > merge_except_for(std::vector<std::vector<CustVector<dim_type> > > vectors_to_merge, int not_merge_index) {
+    std::vector<CustVector<dim_type> > merged;
+    for (int i = 0; i < (int)vectors_to_merge.size(); i++)
+        if (i != not_merge_index) merged.insert(merged.end(), vectors_to_merge[i].begin(), vectors_to_merge[i].end());
+    return merged;
+}
+
+// crypto_rec.hpp:393-449.  Kept quirk: the random position inside the list of known coins is used directly as a
+// coordinate index (:411-412), and every coordinate except that one enters the new mean (:421-430).
+template <typename dim_type>
+bool hide_one_score(CustVector<dim_type>& inVector, double* old_score) {
+    std::vector<dim_type>& dims = *inVector.getDimensions();
+    std::set<int> unknown = inVector.getUnknownIndexesSet();
+    size_t known = dims.size() - unknown.size();
+    if (known < 2) return false;
+    srand((int)time(0));
+    int hide = rand() % (int)known;
+    *old_score = dims[hide];
+    for (int i : unknown) dims[i] = 0;
+    double total = 0;
+    int counted = 0;
+    bool all_zero = true;
+    for (int i = 0; i < (int)dims.size(); i++) {
+        if (i == hide) continue;
+        total = total + dims[i];
+        counted++;
+        if (dims[i] != 0) all_zero = false;
+    }
+    if (all_zero) return false;
+    double new_mean = total / counted;
+    dims[hide] = new_mean;
+    inVector.setKnownMean(new_mean);
+    inVector.setUnknownIndexes(std::set<int>{hide});
+    return true;
 }
 
 #endif  // CRYPTO_REC_HPP
