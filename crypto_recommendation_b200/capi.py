@@ -32,6 +32,8 @@ SYMBOLS = [
     "crx_k_means", "crx_pam_lloyds", "crx_silhouette_cluster", "crx_recommend_lsh", "crx_recommend_cluster",
     "crx_parallel_quickSort", "crx_get_P_closest", "crx_get_top_N_recom", "crx_lsh_hash_vector",
     "crx_user_vectors_build",
+    "crx_k_means_pp_sharded", "crx_k_means_sharded", "crx_pam_lloyds_sharded", "crx_silhouette_cluster_sharded",
+    "crx_lsh_range_assignment_sharded", "crx_cube_range_assignment_sharded",
 ]
 
 
@@ -303,6 +305,37 @@ def k_means_pp(ctx, pts, cluster_num, metric_type, seed):
     return out
 
 
+def _comm_ptr(comm):
+    return comm.ptr() if comm is not None else None
+
+
+def k_means_pp_sharded(ctx, local_pts, row_offset, n_global, cluster_num, metric_type, seed, comm):
+    """k_means_pp over rows sharded by contiguous range (crx_k_means_pp_sharded): (global rows[K], vectors[K][D])."""
+    rows = np.zeros(cluster_num, np.int64)
+    vecs = np.zeros((cluster_num, local_pts.d))
+    _check(lib().crx_k_means_pp_sharded(ctx.h, local_pts.h, ctypes.c_int64(row_offset), ctypes.c_int64(n_global), cluster_num,
+                                        METRICS[metric_type], ctypes.c_uint64(seed), _comm_ptr(comm), _ptr(rows)[0], _ptr(vecs)[0]))
+    return rows, vecs
+
+
+def k_means_sharded(ctx, local_pts, labels, centroids, metric_type, min_dist, comm):
+    """k_means with the rows sharded: local sums, all-reduce, redundant finish.  labels / centroids: numpy or torch."""
+    K = centroids.shape[0]
+    pl, lmem = _ptr(labels if _is_torch(labels) else _np(labels, np.int32))
+    if not _is_torch(centroids):
+        centroids = _np(centroids, np.float64)
+    pc, cmem = _ptr(centroids)
+    if _is_torch(centroids):
+        import torch
+        newc = torch.empty_like(centroids)
+    else:
+        newc = np.zeros_like(centroids)
+    cont = ctypes.c_int()
+    _check(lib().crx_k_means_sharded(ctx.h, local_pts.h, pl, lmem, pc, K, METRICS[metric_type], ctypes.c_double(min_dist),
+                                     _comm_ptr(comm), _ptr(newc)[0], cmem, ctypes.byref(cont)))
+    return bool(cont.value), newc
+
+
 def _out_pair(pts, labels, dists):
     if labels is None:
         labels = np.zeros(pts.n, np.int32)
@@ -333,19 +366,20 @@ def lloyds_for_remaining(ctx, pts, centroids, metric_type, labels, dists):
     return labels, dists
 
 
-def lsh_range_assignment(ctx, pts, tables, centroid_rows, metric_type):
+def lsh_range_assignment(ctx, pts, tables, centroid_rows, metric_type, comm=None):
+    """comm: dist.Comm -- the centroids (and the Lloyd pass over the remainder) are split over its ranks."""
     cr = _np(centroid_rows, np.int32)
     labels = np.zeros(pts.n, np.int32); dists = np.zeros(pts.n); before = np.zeros(pts.n, np.int32)
-    _check(lib().crx_lsh_range_assignment(ctx.h, pts.h, tables.h, _ptr(cr)[0], len(cr), METRICS[metric_type],
-                                          _ptr(labels)[0], _ptr(dists)[0], HOST, _ptr(before)[0]))
+    _check(lib().crx_lsh_range_assignment_sharded(ctx.h, pts.h, tables.h, _ptr(cr)[0], len(cr), METRICS[metric_type], _comm_ptr(comm),
+                                                  _ptr(labels)[0], _ptr(dists)[0], HOST, _ptr(before)[0]))
     return labels, dists, before
 
 
-def cube_range_assignment(ctx, pts, cube, centroid_rows, metric_type, probes):
+def cube_range_assignment(ctx, pts, cube, centroid_rows, metric_type, probes, comm=None):
     cr = _np(centroid_rows, np.int32)
     labels = np.zeros(pts.n, np.int32); dists = np.zeros(pts.n); before = np.zeros(pts.n, np.int32)
-    _check(lib().crx_cube_range_assignment(ctx.h, pts.h, cube.h, _ptr(cr)[0], len(cr), METRICS[metric_type], int(probes),
-                                           _ptr(labels)[0], _ptr(dists)[0], HOST, _ptr(before)[0]))
+    _check(lib().crx_cube_range_assignment_sharded(ctx.h, pts.h, cube.h, _ptr(cr)[0], len(cr), METRICS[metric_type], int(probes),
+                                                   _comm_ptr(comm), _ptr(labels)[0], _ptr(dists)[0], HOST, _ptr(before)[0]))
     return labels, dists, before
 
 
@@ -380,19 +414,22 @@ def k_means(ctx, pts, labels, centroids, metric_type, min_dist):
     return bool(cont.value), newc
 
 
-def pam_lloyds(ctx, pts, labels, centroid_rows, metric_type):
+def pam_lloyds(ctx, pts, labels, centroid_rows, metric_type, comm=None):
+    """comm: dist.Comm -- the candidate medoid rows are split over its ranks (points replicated)."""
     labels = _np(labels, np.int32); cr = _np(centroid_rows, np.int32)
     new = np.zeros(len(cr), np.int32)
     sw = ctypes.c_int()
-    _check(lib().crx_pam_lloyds(ctx.h, pts.h, _ptr(labels)[0], HOST, _ptr(cr)[0], len(cr), METRICS[metric_type], _ptr(new)[0], ctypes.byref(sw)))
+    _check(lib().crx_pam_lloyds_sharded(ctx.h, pts.h, _ptr(labels)[0], HOST, _ptr(cr)[0], len(cr), METRICS[metric_type], _comm_ptr(comm),
+                                        _ptr(new)[0], ctypes.byref(sw)))
     return bool(sw.value), new
 
 
-def silhouette_cluster(ctx, pts, labels, centroids, metric_type):
+def silhouette_cluster(ctx, pts, labels, centroids, metric_type, comm=None):
     labels = _np(labels, np.int32); centroids = _np(centroids, np.float64)
     K = centroids.shape[0]
     s = np.zeros(K + 1)
-    _check(lib().crx_silhouette_cluster(ctx.h, pts.h, _ptr(labels)[0], HOST, _ptr(centroids)[0], HOST, K, METRICS[metric_type], _ptr(s)[0]))
+    _check(lib().crx_silhouette_cluster_sharded(ctx.h, pts.h, _ptr(labels)[0], HOST, _ptr(centroids)[0], HOST, K, METRICS[metric_type],
+                                                _comm_ptr(comm), _ptr(s)[0]))
     return s
 
 

@@ -169,8 +169,9 @@ __global__ void self_assign_kernel(const int32_t* __restrict__ crow, int K, int3
             if (crow[c] >= 0) { labels[crow[c]] = c; dists[crow[c]] = 0.0; }
 }
 
-__global__ void compact_unassigned_kernel(const int32_t* __restrict__ labels, int64_t n, int32_t* __restrict__ rows, int* count) {
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void compact_unassigned_kernel(const int32_t* __restrict__ labels, int64_t n, int32_t* __restrict__ rows, int* count,
+                                          int64_t row_begin = 0) {
+    int64_t i = row_begin + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n && labels[i] == -1) rows[atomicAdd(count, 1)] = (int32_t)i;
 }
 
@@ -222,13 +223,14 @@ __global__ void half_norm_kernel(const double* __restrict__ csqn, int K, double 
 // (128 contiguous bytes per 16 coordinates, L2 resident): the reference's own sequence of operations.
 template <typename T>
 __global__ void __launch_bounds__(256)
-lloyd_refine_kernel(const T* __restrict__ x, int ld, int D, const double* __restrict__ sqn, int64_t N, const double* __restrict__ cent,
+lloyd_refine_kernel(const T* __restrict__ x, int ld, int D, const double* __restrict__ sqn, int64_t row_begin, int64_t N /* end row */,
+                    const double* __restrict__ cent,
                     const float* __restrict__ best, const float* __restrict__ second, const int32_t* __restrict__ bidx, int K,
                     double scale, const unsigned int* __restrict__ cmax_bits, int32_t* __restrict__ labels, double* __restrict__ dists,
                     int32_t* __restrict__ amb_rows, int* __restrict__ amb_count) {
     __shared__ rw::WarpTile tiles[8];
     int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    int64_t row0 = ((int64_t)blockIdx.x * 8 + warp) * 32;
+    int64_t row0 = row_begin + ((int64_t)blockIdx.x * 8 + warp) * 32;
     if (row0 >= N) return;
     int64_t i = row0 + lane;
     bool valid = i < N;
@@ -306,8 +308,12 @@ static bool tc_disabled() {
     return off;
 }
 
-static int lloyd_scan_tc(crx_ctx* c, const crx_points* p, const Centroids& cen, int32_t* d_labels, double* d_dists) {
+// rows [r0, r1) only (r1 < 0: all rows); labels / dists are indexed by absolute row
+static int lloyd_scan_tc(crx_ctx* c, const crx_points* p, const Centroids& cen, int32_t* d_labels, double* d_dists, int64_t r0 = 0,
+                         int64_t r1 = -1) {
     int64_t N = p->n;
+    if (r1 < 0) r1 = N;
+    if (r1 <= r0) return CRX_OK;
     int K = cen.K, D = p->d, ld = p->ld;
     double mx = 0;
     CRX_TRY(points_maxabs(c, p, &mx));
@@ -342,12 +348,12 @@ static int lloyd_scan_tc(crx_ctx* c, const crx_points* p, const Centroids& cen, 
     CRX_TRY(amb.alloc(c, N)); CRX_TRY(amb_count.alloc(c, 1));
     CRX_CUDA(cudaMemsetAsync(amb_count.p, 0, sizeof(int), c->stream));
     { CRX_KERNEL(c, "half_norm"); half_norm_kernel<<<crx_grid(K, 128), 128, 0, c->stream>>>(cen.sqn.p, K, scale, hn.p, cmaxn.p); }
-    st = crx_tc_argmin(c, *p->tc_l2, 0, N, opC, hn.p, best.p, second.p, bidx.p);
+    st = crx_tc_argmin(c, *p->tc_l2, r0, r1 - r0, opC, hn.p, best.p + r0, second.p + r0, bidx.p + r0);
     if (st == CRX_OK) {
         CRX_KERNEL(c, "lloyd_refine");
-        int g = (int)((N + 255) / 256);
-        if (p->x64) lloyd_refine_kernel<double><<<g, 256, 0, c->stream>>>(p->x64, ld, D, p->sqn, N, cen.pad.p, best.p, second.p, bidx.p, K, scale, cmaxn.p, d_labels, d_dists, amb.p, amb_count.p);
-        else lloyd_refine_kernel<float><<<g, 256, 0, c->stream>>>(p->x32, ld, D, p->sqn, N, cen.pad.p, best.p, second.p, bidx.p, K, scale, cmaxn.p, d_labels, d_dists, amb.p, amb_count.p);
+        int g = (int)((r1 - r0 + 255) / 256);
+        if (p->x64) lloyd_refine_kernel<double><<<g, 256, 0, c->stream>>>(p->x64, ld, D, p->sqn, r0, r1, cen.pad.p, best.p, second.p, bidx.p, K, scale, cmaxn.p, d_labels, d_dists, amb.p, amb_count.p);
+        else lloyd_refine_kernel<float><<<g, 256, 0, c->stream>>>(p->x32, ld, D, p->sqn, r0, r1, cen.pad.p, best.p, second.p, bidx.p, K, scale, cmaxn.p, d_labels, d_dists, amb.p, amb_count.p);
         CRX_CUDA(cudaGetLastError());
     }
     int h_amb = 0;
@@ -456,16 +462,17 @@ __global__ void select_centroids_kernel(const double* __restrict__ newc, const d
 // ------------------------------------------------------------------------------------------------
 template <typename T, int METRIC>
 __global__ void __launch_bounds__(256)
-kpp_update_kernel(const T* __restrict__ x, int ld, int D, const double* __restrict__ sqn, int64_t N, int crow, int first,
+kpp_update_kernel(const T* __restrict__ x, int ld, int D, const double* __restrict__ sqn, int64_t N,
+                  const double* __restrict__ cvec /* [ld] coordinates, [ld] = exact sum of squares */, int first,
                   double* __restrict__ mind, unsigned long long* __restrict__ maxbits) {
     __shared__ rw::WarpTile tiles[8];
     __shared__ double vec[128];
     int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    for (int k = threadIdx.x; k < ld; k += blockDim.x) vec[k] = (double)x[(size_t)crow * ld + k];
+    for (int k = threadIdx.x; k < ld; k += blockDim.x) vec[k] = cvec[k];
     __syncthreads();
     int64_t row = ((int64_t)blockIdx.x * 8 + warp) * 32 + lane;
     bool valid = row < N;
-    double d = rw::dist_rows<T, METRIC>(x, ld, D, valid ? row : -1, vec, valid ? sqn[row] : 1.0, sqn[crow], tiles[warp]);
+    double d = rw::dist_rows<T, METRIC>(x, ld, D, valid ? row : -1, vec, valid ? sqn[row] : 1.0, cvec[ld], tiles[warp]);
     double m = 0.0;
     if (valid) {
         m = mind[row];
@@ -476,6 +483,13 @@ kpp_update_kernel(const T* __restrict__ x, int ld, int D, const double* __restri
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, off));
     if (lane == 0 && mx > 0.0) atomicMax(maxbits, (unsigned long long)__double_as_longlong(mx));
+}
+
+// coordinates of one stored row widened to double, followed by its exact sum of squares
+template <typename T>
+__global__ void stage_row_kernel(const T* __restrict__ x, int ld, const double* __restrict__ sqn, int64_t row, double* __restrict__ out) {
+    for (int k = threadIdx.x; k < ld; k += blockDim.x) out[k] = (double)x[(size_t)row * ld + k];
+    if (threadIdx.x == 0) out[ld] = sqn[row];
 }
 
 // p_v = (min_d / max)^2 (initialization.hpp:122-127, before the running sum)
@@ -536,10 +550,10 @@ range_fire_kernel(const T* __restrict__ x, int ld, int D, const double* __restri
                   const int32_t* __restrict__ seg_end,        // [K*nseg]
                   const int32_t* const* __restrict__ seg_perm,  // [nseg] position -> row (per table) or one shared perm
                   const int32_t* __restrict__ bucket, int64_t N,  // [L][N] bucket ids for the duplicate filter (LSH) or NULL
-                  int chunk, int* __restrict__ key) {
+                  int chunk, int cs0, int* __restrict__ key) {
     __shared__ rw::WarpTile tiles[8];
     __shared__ double vec[128];
-    int cs = blockIdx.x;  // centroid * nseg + seg
+    int cs = cs0 + blockIdx.x;  // centroid * nseg + seg (cs0: first one of this rank's share of the centroids)
     int c = cs / nseg, sgi = cs - c * nseg;
     int begin = seg_begin[cs] + blockIdx.y * chunk;
     int end = min(seg_end[cs], begin + chunk);
@@ -637,13 +651,13 @@ __global__ void min_pair_seq_kernel(const T* __restrict__ x, int ld, int D, cons
 template <typename T, int METRIC>
 __global__ void __launch_bounds__(256)
 pam_rowsum_kernel(const T* __restrict__ x, int ld, int D, const double* __restrict__ sqn, const int32_t* __restrict__ perm,
-                  const int32_t* __restrict__ sorted_label, const int32_t* __restrict__ off, int64_t N,
-                  double* __restrict__ rowsum) {
+                  const int32_t* __restrict__ sorted_label, const int32_t* __restrict__ off, int64_t pos_begin, int64_t pos_end,
+                  double* __restrict__ rowsum, double* __restrict__ rowerr) {
     __shared__ rw::WarpTile tiles[8];
     __shared__ double vecs[8][128];
     int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    int64_t pos = (int64_t)blockIdx.x * 8 + warp;
-    if (pos >= N) return;
+    int64_t pos = pos_begin + (int64_t)blockIdx.x * 8 + warp;
+    if (pos >= pos_end) return;
     int cl = sorted_label[pos];
     int begin = off[cl], end = off[cl + 1];
     int64_t mrow = perm[pos];
@@ -658,72 +672,14 @@ pam_rowsum_kernel(const T* __restrict__ x, int ld, int D, const double* __restri
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-    if (lane == 0) rowsum[pos] = acc;
+    // exact distances, summed in a different order than the reference: off by at most ~n ulps
+    if (lane == 0) { rowsum[pos] = acc; rowerr[pos] = fabs(acc) * (8.0 * (double)(end - begin + D) * 1.1102230246251565e-16); }
 }
 
-template <typename T, int METRIC>
-__global__ void __launch_bounds__(256)
-pam_pick_kernel(const T* __restrict__ x, int ld, int D, const double* __restrict__ sqn, const int32_t* __restrict__ perm,
-                const int32_t* __restrict__ off, const double* __restrict__ rowsum, const int32_t* __restrict__ crow,
-                int32_t* __restrict__ new_crow, int* __restrict__ swapped, unsigned long long* counters) {
-    __shared__ double red[256];
-    __shared__ int redi[256];
-    __shared__ int ncand;
-    int cl = blockIdx.x;
-    int begin = off[cl], end = off[cl + 1];
-    int n = end - begin;
-    if (n == 0) { if (threadIdx.x == 0) new_crow[cl] = crow[cl]; return; }
-    double m = INFINITY;
-    for (int p = begin + threadIdx.x; p < end; p += blockDim.x) { double v = rowsum[p]; if (v < m) m = v; }
-    red[threadIdx.x] = m;
-    if (threadIdx.x == 0) ncand = 0;
-    __syncthreads();
-    for (int s = 128; s > 0; s >>= 1) { if (threadIdx.x < s) red[threadIdx.x] = fmin(red[threadIdx.x], red[threadIdx.x + s]); __syncthreads(); }
-    double mn = red[0];
-    __syncthreads();
-    double tol = mn * (8.0 * (double)(n + D) * 1.1102230246251565e-16);
-    // candidates: rows whose parallel sum is within tolerance of the minimum (NaN sums never qualify)
-    int mycount = 0;
-    for (int p = begin + threadIdx.x; p < end; p += blockDim.x) if (rowsum[p] <= mn + tol) mycount++;
-    if (mycount) atomicAdd(&ncand, mycount);
-    __syncthreads();
-    bool exact = ncand > 1;
-    double best = INFINITY;
-    int bestp = INT_MAX;
-    for (int p = begin + threadIdx.x; p < end; p += blockDim.x) {
-        if (rowsum[p] <= mn + tol) {
-            double s = rowsum[p];
-            if (exact) {  // the reference's own sequential sum over members in input order
-                const T* xm = x + (size_t)perm[p] * ld;
-                s = 0.0;
-                for (int q = begin; q < end; q++)
-                    s = __dadd_rn(s, metric_dist_exact(METRIC, xm, x + (size_t)perm[q] * ld, D, sqn[perm[p]], sqn[perm[q]]));
-                atomicAdd(&counters[CRX_CNT_PAM_EXACT], 1ull);
-            }
-            if (s < best || (s == best && p < bestp)) { best = s; bestp = p; }
-        }
-    }
-    red[threadIdx.x] = best; redi[threadIdx.x] = bestp;
-    __syncthreads();
-    for (int s = 128; s > 0; s >>= 1) {
-        if (threadIdx.x < s) {
-            double ov = red[threadIdx.x + s]; int oi = redi[threadIdx.x + s];
-            if (ov < red[threadIdx.x] || (ov == red[threadIdx.x] && oi < redi[threadIdx.x])) { red[threadIdx.x] = ov; redi[threadIdx.x] = oi; }
-        }
-        __syncthreads();
-    }
-    if (threadIdx.x == 0) {
-        // all sums NaN (cosine with zero vectors): `min_dist_sum == -1 || s < min` keeps member 0
-        int p = redi[0] == INT_MAX ? begin : redi[0];
-        int row = perm[p];
-        if (row != crow[cl]) { new_crow[cl] = row; atomicExch(swapped, 1); }
-        else new_crow[cl] = crow[cl];
-    }
-}
-
-// ---- tensor-engine generation of K8 (Euclidean): approximate row sums with a rigorous error bar from the tcgen05
-// scan, then only the rows whose interval reaches below the smallest upper end are re-summed exactly, sequentially in
-// member order (the reference's own floating-point sum), and the first minimum wins (update.hpp:110-127).
+// ---- picking the medoid from row sums with error bars (exact FP64 distances summed in parallel order, or the
+// tcgen05 row-sum scan for Euclidean): only the rows whose interval reaches below the smallest upper end are re-summed
+// exactly, sequentially in member order (the reference's own floating-point sum), and the first minimum wins
+// (update.hpp:110-127).
 __global__ void __launch_bounds__(256)
 pam_bounds_kernel(const int32_t* __restrict__ off, const double* __restrict__ rowsum, const double* __restrict__ rowerr, int D,
                   int32_t* __restrict__ cand /* [N] positions */, int* __restrict__ ncand_total, int32_t* __restrict__ winner /* [K] */) {
@@ -746,6 +702,10 @@ pam_bounds_kernel(const int32_t* __restrict__ off, const double* __restrict__ ro
         if (rowsum[p] - rowerr[p] <= U) { mine++; first = min(first, p); }
     if (mine) atomicAdd(&count, mine);
     __syncthreads();
+    if (count == 0) {  // every sum is NaN (cosine with a zero vector): `min == -1 || s < min` keeps member 0
+        if (threadIdx.x == 0) winner[cl] = begin;
+        return;
+    }
     if (count == 1) {  // its real sum is below every other row's by more than the rounding of the reference's sums
         if (mine) winner[cl] = first;
         return;
@@ -758,7 +718,7 @@ pam_bounds_kernel(const int32_t* __restrict__ off, const double* __restrict__ ro
 
 // one CTA per candidate: the 8 warps compute 256 exact distances at a time into shared memory, thread 0 adds them in
 // member order (update.hpp:118's own sequential sum) while the warps are already working on the next 256
-template <typename T>
+template <typename T, int METRIC>
 __global__ void __launch_bounds__(256)
 pam_exact_kernel(const T* __restrict__ x, int ld, int D, const double* __restrict__ sqn, const int32_t* __restrict__ perm,
                  const int32_t* __restrict__ sorted_label, const int32_t* __restrict__ off, const int32_t* __restrict__ cand,
@@ -779,7 +739,7 @@ pam_exact_kernel(const T* __restrict__ x, int ld, int D, const double* __restric
         if (b < end) {
             int p = b + warp * 32 + lane;
             int64_t row = p < end ? (int64_t)perm[p] : -1;
-            double d = rw::dist_rows<T, CRX_EUCLIDEAN>(x, ld, D, row, vecs[warp], row >= 0 ? sqn[row] : 1.0, nm, tiles[warp]);
+            double d = rw::dist_rows<T, METRIC>(x, ld, D, row, vecs[warp], row >= 0 ? sqn[row] : 1.0, nm, tiles[warp]);
             dist[buf][threadIdx.x] = d;
         }
         if (threadIdx.x == 0 && b > begin) {  // previous batch
@@ -838,12 +798,12 @@ template <typename T, int METRIC>
 __global__ void __launch_bounds__(256)
 silhouette_point_kernel(const T* __restrict__ x, int ld, int D, const double* __restrict__ sqn, const int32_t* __restrict__ perm,
                         const int32_t* __restrict__ sorted_label, const int32_t* __restrict__ off,
-                        const int32_t* __restrict__ near, int64_t N, double* __restrict__ s_out) {
+                        const int32_t* __restrict__ near, int64_t pos_begin, int64_t pos_end, double* __restrict__ s_out) {
     __shared__ rw::WarpTile tiles[8];
     __shared__ double vecs[8][128];
     int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    int64_t pos = (int64_t)blockIdx.x * 8 + warp;
-    if (pos >= N) return;
+    int64_t pos = pos_begin + (int64_t)blockIdx.x * 8 + warp;
+    if (pos >= pos_end) return;
     int cl = sorted_label[pos];
     int64_t mrow = perm[pos];
     rw::stage_vector<T>(x, ld, mrow, vecs[warp]);
@@ -907,10 +867,36 @@ __global__ void gather_int_kernel(const int32_t* __restrict__ src, const int32_t
 template <typename F32, typename F64>
 static int by_type(const crx_points* p, F32 f32, F64 f64) { return p->x64 ? f64() : f32(); }
 
+// ---- exchange steps of the sharded entry points (include/crx.h, crx_comm) ----
+static inline int comm_world(const crx_comm* cm) { return (cm && cm->world > 1) ? cm->world : 1; }
+static inline int comm_rank(const crx_comm* cm) { return (cm && cm->world > 1) ? cm->rank : 0; }
+static int comm_done(int rc, const char* what) {
+    if (rc == 0) return CRX_OK;
+    crx_set_error("collective %s failed in the caller's callback (%d)", what, rc);
+    return CRX_ERR_COMM;
+}
+static int comm_allreduce(crx_ctx* c, const crx_comm* cm, void* buf, int64_t n, int dtype, int op, int mem) {
+    if (comm_world(cm) == 1 || n == 0) return CRX_OK;
+    CRX_REQUIRE(cm->allreduce, "crx_comm.allreduce is NULL");
+    if (mem == CRX_DEVICE) CRX_CUDA(cudaStreamSynchronize(c->stream));
+    return comm_done(cm->allreduce(cm->user, buf, n, dtype, op, mem), "allreduce");
+}
+static int comm_allgather(crx_ctx* c, const crx_comm* cm, const void* send, void* recv, int64_t n, int dtype, int mem) {
+    CRX_REQUIRE(cm && cm->allgather, "crx_comm.allgather is NULL");
+    if (mem == CRX_DEVICE) CRX_CUDA(cudaStreamSynchronize(c->stream));
+    return comm_done(cm->allgather(cm->user, send, recv, n, dtype, mem), "allgather");
+}
+static int comm_broadcast(crx_ctx* c, const crx_comm* cm, void* buf, int64_t n, int dtype, int root, int mem) {
+    CRX_REQUIRE(cm && cm->broadcast, "crx_comm.broadcast is NULL");
+    if (mem == CRX_DEVICE) CRX_CUDA(cudaStreamSynchronize(c->stream));
+    return comm_done(cm->broadcast(cm->user, buf, n, dtype, root, mem), "broadcast");
+}
+
 static int range_assign_common(crx_ctx* c, const crx_points* p, const int32_t* h_crow, int K, int metric, int nseg,
                                const std::vector<int32_t>& h_begin, const std::vector<int32_t>& h_end,
                                const std::vector<const int32_t*>& h_perm, const int32_t* d_bucket, int32_t* labels,
-                               double* dists, int mem, int32_t* before) {
+                               double* dists, int mem, int32_t* before, const crx_comm* comm) {
+    const int world = comm_world(comm), me = comm_rank(comm);
     int64_t N = p->n;
     int D = p->d, ld = p->ld;
     IoBuf<int32_t> lab, bef;
@@ -960,17 +946,20 @@ static int range_assign_common(crx_ctx* c, const crx_points* p, const int32_t* h
     double r0 = mn / 2;
     CRX_CUDA(cudaMemsetAsync(hist.p, 0, NH * sizeof(int), c->stream));
     { CRX_KERNEL(c, "fill_key"); fill_int_kernel<<<crx_grid(N, 256), 256, 0, c->stream>>>(key.p, N, INT_MAX); }
+    // this rank probes the buckets of its share of the centroids; the firing steps are combined with a min
+    const int c_lo = (int)((int64_t)K * me / world), c_hi = (int)((int64_t)K * (me + 1) / world);
     int maxlen = 0;
-    for (size_t i = 0; i < h_begin.size(); i++) maxlen = std::max(maxlen, h_end[i] - h_begin[i]);
+    for (size_t i = (size_t)c_lo * nseg; i < (size_t)c_hi * nseg; i++) maxlen = std::max(maxlen, h_end[i] - h_begin[i]);
     const int chunk = 8192;
-    dim3 grid((unsigned)(K * nseg), (unsigned)std::max(1, (maxlen + chunk - 1) / chunk));
+    dim3 grid((unsigned)std::max(1, (c_hi - c_lo) * nseg), (unsigned)std::max(1, (maxlen + chunk - 1) / chunk));
     if (maxlen > 0) {
         CRX_KERNEL(c, "range_fire");
-#define LAUNCH_R(T, M, xptr) range_fire_kernel<T, M><<<grid, 256, 0, c->stream>>>(xptr, ld, D, p->sqn, K, d_crow.p, r0, nseg, d_begin.p, d_end.p, d_perm.p, d_bucket, N, chunk, key.p)
+#define LAUNCH_R(T, M, xptr) range_fire_kernel<T, M><<<grid, 256, 0, c->stream>>>(xptr, ld, D, p->sqn, K, d_crow.p, r0, nseg, d_begin.p, d_end.p, d_perm.p, d_bucket, N, chunk, c_lo * nseg, key.p)
         if (p->x64) { if (metric == CRX_EUCLIDEAN) LAUNCH_R(double, CRX_EUCLIDEAN, p->x64); else LAUNCH_R(double, CRX_COSINE, p->x64); }
         else { if (metric == CRX_EUCLIDEAN) LAUNCH_R(float, CRX_EUCLIDEAN, p->x32); else LAUNCH_R(float, CRX_COSINE, p->x32); }
 #undef LAUNCH_R
     }
+    CRX_TRY(comm_allreduce(c, comm, key.p, N, CRX_I32, CRX_MIN, CRX_DEVICE));
     { CRX_KERNEL(c, "range_hist"); range_hist_kernel<<<crx_grid(N, 256), 256, 0, c->stream>>>(key.p, N, K, hist.p, NH); }
     std::vector<int> h_hist(NH);
     CRX_CUDA(cudaMemcpyAsync(h_hist.data(), hist.p, NH * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
@@ -1002,13 +991,32 @@ static int range_assign_common(crx_ctx* c, const crx_points* p, const int32_t* h
     Centroids cen;
     CRX_TRY(cen.stage(c, cmat.p, CRX_DEVICE, K, D, ld));
     CRX_CUDA(cudaStreamSynchronize(c->stream));
-    if (metric == CRX_EUCLIDEAN && K >= 32 && N >= 1024 && (int64_t)h_cnt * 4 >= N && !tc_disabled()) {
-        // most rows are left (the radius doubles per centroid): tensor-core filter + exact refine over
-        // ALL rows into scratch, then keep the results of the unassigned rows only
+    const bool tensor_rest = metric == CRX_EUCLIDEAN && K >= 32 && N >= 1024 && (int64_t)h_cnt * 4 >= N && !tc_disabled();
+    if (tensor_rest || world > 1) {
+        // results for this rank's share of the rows go into scratch (zeros elsewhere), are summed over the ranks, and
+        // the unassigned rows take theirs.  Tensor path (most rows are left -- the radius doubles per centroid,
+        // SURVEY App. A-7): filter + exact refine over all rows of the share; otherwise the exact scan of the
+        // unassigned rows of the share.
+        const int64_t lo = N * me / world, hi = N * (me + 1) / world;
         DevBuf<int32_t> tl;
         DevBuf<double> td;
         CRX_TRY(tl.alloc(c, N)); CRX_TRY(td.alloc(c, N));
-        CRX_TRY(lloyd_scan_tc(c, p, cen, tl.p, td.p));
+        if (world > 1) {
+            CRX_CUDA(cudaMemsetAsync(tl.p, 0, N * sizeof(int32_t), c->stream));
+            CRX_CUDA(cudaMemsetAsync(td.p, 0, N * sizeof(double), c->stream));
+        }
+        if (tensor_rest) {
+            CRX_TRY(lloyd_scan_tc(c, p, cen, tl.p, td.p, lo, hi));
+        } else {
+            CRX_CUDA(cudaMemsetAsync(cnt.p, 0, sizeof(int), c->stream));
+            if (hi > lo) { CRX_KERNEL(c, "compact_unassigned"); compact_unassigned_kernel<<<crx_grid(hi - lo, 256), 256, 0, c->stream>>>(lab.dev, hi, rows.p, cnt.p, lo); }
+            int mine = 0;
+            CRX_CUDA(cudaMemcpyAsync(&mine, cnt.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+            CRX_CUDA(cudaStreamSynchronize(c->stream));
+            CRX_TRY(lloyd_scan(c, p, rows.p, mine, cen, metric, tl.p, td.p));
+        }
+        CRX_TRY(comm_allreduce(c, comm, tl.p, N, CRX_I32, CRX_SUM, CRX_DEVICE));
+        CRX_TRY(comm_allreduce(c, comm, td.p, N, CRX_F64, CRX_SUM, CRX_DEVICE));
         CRX_KERNEL(c, "merge_remaining");
         merge_remaining_kernel<<<crx_grid(N, 256), 256, 0, c->stream>>>(tl.p, td.p, N, lab.dev, dis.dev);
     } else {
@@ -1045,46 +1053,130 @@ int crx_rand_selection(crx_ctx* c, const crx_points* p, int K, uint64_t seed, in
     return CRX_OK;
 }
 
-int crx_k_means_pp(crx_ctx* c, const crx_points* p, int K, int metric, uint64_t seed, int32_t* out) {
+int crx_k_means_pp_sharded(crx_ctx* c, const crx_points* p, int64_t row_offset, int64_t n_global, int K, int metric, uint64_t seed,
+                           const crx_comm* comm, int64_t* out, double* out_vectors) {
     CRX_REQUIRE(c && p && out, "NULL argument");
     CRX_REQUIRE(K >= 1, "cluster_num");
     CRX_REQUIRE(metric == CRX_EUCLIDEAN || metric == CRX_COSINE, "metric");
+    CRX_REQUIRE(n_global >= 1 && n_global < (1ll << 31) && row_offset >= 0 && row_offset + p->n <= n_global, "row range");
     CRX_CUDA(cudaSetDevice(c->device));
+    const int world = comm_world(comm), me = comm_rank(comm);
     int64_t N = p->n;
+    int ld = p->ld, D = p->d;
+    // who owns which rows
+    std::vector<int64_t> offs(world, 0), lens(world, N);
+    if (world > 1) {
+        int64_t mine[2] = {row_offset, N};
+        std::vector<int64_t> all((size_t)2 * world);
+        CRX_TRY(comm_allgather(c, comm, mine, all.data(), 2, CRX_I64, CRX_HOST));
+        for (int r = 0; r < world; r++) { offs[r] = all[2 * r]; lens[r] = all[2 * r + 1]; }
+    } else offs[0] = row_offset;
+    auto owner_of = [&](int64_t g) { for (int r = 0; r < world; r++) if (g >= offs[r] && g < offs[r] + lens[r]) return r; return -1; };
     std::default_random_engine e;
     e.seed((unsigned long)seed);
-    std::uniform_int_distribution<int> ui(0, (int)N - 1);
+    std::uniform_int_distribution<int> ui(0, (int)n_global - 1);
     out[0] = ui(e);
-    DevBuf<double> mind, prob, P;
+    DevBuf<double> mind, prob, P, cvec;
     DevBuf<unsigned long long> mx;
     DevBuf<int32_t> chosen;
     DevBuf<char> tmp;
     CRX_TRY(mind.alloc(c, N)); CRX_TRY(prob.alloc(c, N)); CRX_TRY(P.alloc(c, N)); CRX_TRY(mx.alloc(c, 1)); CRX_TRY(chosen.alloc(c, 1));
+    CRX_TRY(cvec.alloc(c, ld + 1));
+    std::vector<double> hvec(ld + 1);
     size_t bytes = 0;
-    CRX_CUDA(cub::DeviceScan::InclusiveSum(nullptr, bytes, prob.p, P.p, (int)N, c->stream));
+    if (N > 0) CRX_CUDA(cub::DeviceScan::InclusiveSum(nullptr, bytes, prob.p, P.p, (int)N, c->stream));
     CRX_TRY(tmp.alloc(c, bytes));
     int gridu = (int)((N + 255) / 256);
-    for (int i = 1; i < K; i++) {
+    for (int i = 1; i <= K; i++) {
+        // coordinates of the centroid picked last: staged by its owner, shared with everybody
+        int64_t g = out[i - 1];
+        int own = owner_of(g);
+        CRX_REQUIRE(own >= 0, "the shards do not cover the chosen row");
+        if (own == me) {
+            if (p->x64) stage_row_kernel<double><<<1, 128, 0, c->stream>>>(p->x64, ld, p->sqn, g - row_offset, cvec.p);
+            else stage_row_kernel<float><<<1, 128, 0, c->stream>>>(p->x32, ld, p->sqn, g - row_offset, cvec.p);
+            if (world > 1 || out_vectors) {
+                CRX_CUDA(cudaMemcpyAsync(hvec.data(), cvec.p, (ld + 1) * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+                CRX_CUDA(cudaStreamSynchronize(c->stream));
+            }
+        }
+        if (world > 1) {
+            CRX_TRY(comm_broadcast(c, comm, hvec.data(), ld + 1, CRX_F64, own, CRX_HOST));
+            if (own != me) CRX_CUDA(cudaMemcpyAsync(cvec.p, hvec.data(), (ld + 1) * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+        }
+        if (out_vectors) memcpy(out_vectors + (size_t)(i - 1) * D, hvec.data(), D * sizeof(double));
+        if (i == K) break;
         CRX_CUDA(cudaMemsetAsync(mx.p, 0, sizeof(unsigned long long), c->stream));
-        {
+        if (N > 0) {
             CRX_KERNEL(c, "kpp_update");
-#define LAUNCH_K(T, M, xptr) kpp_update_kernel<T, M><<<gridu, 256, 0, c->stream>>>(xptr, p->ld, p->d, p->sqn, N, out[i - 1], i == 1, mind.p, mx.p)
+#define LAUNCH_K(T, M, xptr) kpp_update_kernel<T, M><<<gridu, 256, 0, c->stream>>>(xptr, ld, D, p->sqn, N, cvec.p, i == 1, mind.p, mx.p)
             if (p->x64) { if (metric == CRX_EUCLIDEAN) LAUNCH_K(double, CRX_EUCLIDEAN, p->x64); else LAUNCH_K(double, CRX_COSINE, p->x64); }
             else { if (metric == CRX_EUCLIDEAN) LAUNCH_K(float, CRX_EUCLIDEAN, p->x32); else LAUNCH_K(float, CRX_COSINE, p->x32); }
 #undef LAUNCH_K
         }
-        { CRX_KERNEL(c, "kpp_prob"); kpp_prob_kernel<<<crx_grid(N, 256), 256, 0, c->stream>>>(mind.p, N, mx.p, prob.p); }
-        CRX_CUDA(cub::DeviceScan::InclusiveSum(tmp.p, bytes, prob.p, P.p, (int)N, c->stream));
+        if (world > 1) {  // max_for_normalizing over all shards (initialization.hpp:116-117)
+            double hm = 0;
+            CRX_CUDA(cudaMemcpyAsync(&hm, mx.p, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+            CRX_CUDA(cudaStreamSynchronize(c->stream));
+            CRX_TRY(comm_allreduce(c, comm, &hm, 1, CRX_F64, CRX_MAX, CRX_HOST));
+            CRX_CUDA(cudaMemcpyAsync(mx.p, &hm, sizeof(double), cudaMemcpyHostToDevice, c->stream));
+        }
         double total = 0;
-        CRX_CUDA(cudaMemcpyAsync(&total, P.p + (N - 1), sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        if (N > 0) {
+            { CRX_KERNEL(c, "kpp_prob"); kpp_prob_kernel<<<crx_grid(N, 256), 256, 0, c->stream>>>(mind.p, N, mx.p, prob.p); }
+            CRX_CUDA(cub::DeviceScan::InclusiveSum(tmp.p, bytes, prob.p, P.p, (int)N, c->stream));
+            CRX_CUDA(cudaMemcpyAsync(&total, P.p + (N - 1), sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        }
         CRX_CUDA(cudaStreamSynchronize(c->stream));
-        std::uniform_real_distribution<double> ur(0.0, total);  // initialization.hpp:132-133
+        // running sum of the shard totals = the prefix sum at every shard boundary (initialization.hpp:123-129)
+        std::vector<double> cum(world, total);
+        if (world > 1) {
+            CRX_TRY(comm_allgather(c, comm, &total, cum.data(), 1, CRX_F64, CRX_HOST));
+            for (int r = 1; r < world; r++) cum[r] = cum[r - 1] + cum[r];
+        }
+        std::uniform_real_distribution<double> ur(0.0, cum[world - 1]);  // initialization.hpp:132-133
         double xr = ur(e);
-        { CRX_KERNEL(c, "kpp_pick"); kpp_pick_kernel<<<1, 32, 0, c->stream>>>(P.p, N, xr, chosen.p, c->counters); }
-        CRX_CUDA(cudaMemcpyAsync(&out[i], chosen.p, sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
-        CRX_CUDA(cudaStreamSynchronize(c->stream));
+        int pick_rank = world - 1;
+        for (int r = 0; r < world; r++) if (lens[r] > 0 && xr <= cum[r]) { pick_rank = r; break; }
+        int64_t picked = 0;
+        if (pick_rank == me) {
+            double xl = pick_rank > 0 ? xr - cum[pick_rank - 1] : xr;
+            int32_t h = 0;
+            { CRX_KERNEL(c, "kpp_pick"); kpp_pick_kernel<<<1, 32, 0, c->stream>>>(P.p, N, xl, chosen.p, c->counters); }
+            CRX_CUDA(cudaMemcpyAsync(&h, chosen.p, sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+            CRX_CUDA(cudaStreamSynchronize(c->stream));
+            picked = row_offset + h;
+        }
+        if (world > 1) CRX_TRY(comm_broadcast(c, comm, &picked, 1, CRX_I64, pick_rank, CRX_HOST));
+        out[i] = picked;
     }
     CRX_CUDA(cudaGetLastError());
+    return CRX_OK;
+}
+
+int crx_k_means_pp(crx_ctx* c, const crx_points* p, int K, int metric, uint64_t seed, int32_t* out) {
+    CRX_REQUIRE(c && p && out, "NULL argument");
+    CRX_REQUIRE(K >= 1, "cluster_num");
+    std::vector<int64_t> rows(K);
+    CRX_TRY(crx_k_means_pp_sharded(c, p, 0, p->n, K, metric, seed, nullptr, rows.data(), nullptr));
+    for (int i = 0; i < K; i++) out[i] = (int32_t)rows[i];
+    return CRX_OK;
+}
+
+int crx_k_means_sharded(crx_ctx* c, const crx_points* p, const int32_t* labels, int lmem, const double* oldc, int K, int metric,
+                        double min_dist, const crx_comm* comm, double* newc, int cmem, int* cont) {
+    CRX_REQUIRE(c && p && labels && oldc && newc && cont, "NULL argument");
+    DevBuf<double> sums, o, n;
+    DevBuf<long long> cnt;
+    size_t kd = (size_t)K * p->d;
+    CRX_TRY(sums.alloc(c, kd)); CRX_TRY(cnt.alloc(c, K)); CRX_TRY(o.alloc(c, kd)); CRX_TRY(n.alloc(c, kd));
+    CRX_CUDA(cudaMemcpyAsync(o.p, oldc, kd * sizeof(double), cmem == CRX_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, c->stream));
+    CRX_TRY(crx_cluster_sums(c, p, labels, lmem, K, sums.p, (int64_t*)cnt.p, CRX_DEVICE));
+    CRX_TRY(comm_allreduce(c, comm, sums.p, (int64_t)kd, CRX_F64, CRX_SUM, CRX_DEVICE));
+    CRX_TRY(comm_allreduce(c, comm, cnt.p, K, CRX_I64, CRX_SUM, CRX_DEVICE));
+    CRX_TRY(crx_k_means_finish(c, sums.p, (const int64_t*)cnt.p, o.p, K, p->d, metric, min_dist, n.p, CRX_DEVICE, cont));
+    CRX_CUDA(cudaMemcpyAsync(newc, n.p, kd * sizeof(double), cmem == CRX_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice, c->stream));
+    CRX_CUDA(cudaStreamSynchronize(c->stream));
     return CRX_OK;
 }
 
@@ -1143,8 +1235,8 @@ int crx_lloyds_for_remaining(crx_ctx* c, const crx_points* p, const double* cent
     return CRX_OK;
 }
 
-int crx_lsh_range_assignment(crx_ctx* c, const crx_points* p, const crx_lsh* t, const int32_t* crow, int K, int metric,
-                             int32_t* labels, double* dists, int mem, int32_t* before) {
+int crx_lsh_range_assignment_sharded(crx_ctx* c, const crx_points* p, const crx_lsh* t, const int32_t* crow, int K, int metric,
+                                     const crx_comm* comm, int32_t* labels, double* dists, int mem, int32_t* before) {
     CRX_REQUIRE(c && p && t && crow && labels && dists, "NULL argument");
     CRX_REQUIRE(t->pts == p, "the tables were built over a different point set");
     CRX_REQUIRE(K >= 1, "K");
@@ -1177,11 +1269,16 @@ int crx_lsh_range_assignment(crx_ctx* c, const crx_points* p, const crx_lsh* t, 
             hb[(size_t)cc * L + l] = offs[l][b];
             he[(size_t)cc * L + l] = offs[l][b + 1];
         }
-    return range_assign_common(c, p, crow, K, metric, L, hb, he, perms, t->bucket, labels, dists, mem, before);
+    return range_assign_common(c, p, crow, K, metric, L, hb, he, perms, t->bucket, labels, dists, mem, before, comm);
 }
 
-int crx_cube_range_assignment(crx_ctx* c, const crx_points* p, const crx_cube* cu, const int32_t* crow, int K, int metric,
-                              int probes, int32_t* labels, double* dists, int mem, int32_t* before) {
+int crx_lsh_range_assignment(crx_ctx* c, const crx_points* p, const crx_lsh* t, const int32_t* crow, int K, int metric,
+                             int32_t* labels, double* dists, int mem, int32_t* before) {
+    return crx_lsh_range_assignment_sharded(c, p, t, crow, K, metric, nullptr, labels, dists, mem, before);
+}
+
+int crx_cube_range_assignment_sharded(crx_ctx* c, const crx_points* p, const crx_cube* cu, const int32_t* crow, int K, int metric,
+                                      int probes, const crx_comm* comm, int32_t* labels, double* dists, int mem, int32_t* before) {
     CRX_REQUIRE(c && p && cu && crow && labels && dists, "NULL argument");
     CRX_REQUIRE(cu->pts == p, "the hypercube was built over a different point set");
     CRX_REQUIRE(K >= 1, "K");
@@ -1203,7 +1300,12 @@ int crx_cube_range_assignment(crx_ctx* c, const crx_points* p, const crx_cube* c
     for (int cc = 0; cc < K; cc++)
         for (size_t s = 0; s < seqs[cc].size(); s++) { hb[cc * nseg + s] = off[seqs[cc][s]]; he[cc * nseg + s] = off[seqs[cc][s] + 1]; }
     std::vector<const int32_t*> perms(1, cu->by_vertex.perm);
-    return range_assign_common(c, p, crow, K, metric, (int)nseg, hb, he, perms, nullptr, labels, dists, mem, before);
+    return range_assign_common(c, p, crow, K, metric, (int)nseg, hb, he, perms, nullptr, labels, dists, mem, before, comm);
+}
+
+int crx_cube_range_assignment(crx_ctx* c, const crx_points* p, const crx_cube* cu, const int32_t* crow, int K, int metric,
+                              int probes, int32_t* labels, double* dists, int mem, int32_t* before) {
+    return crx_cube_range_assignment_sharded(c, p, cu, crow, K, metric, probes, nullptr, labels, dists, mem, before);
 }
 
 int crx_cluster_sums(crx_ctx* c, const crx_points* p, const int32_t* labels, int lmem, int K, double* sums, int64_t* counts, int mem) {
@@ -1283,148 +1385,134 @@ int crx_k_means_finish(crx_ctx* c, const double* sums, const int64_t* counts, co
 
 int crx_k_means(crx_ctx* c, const crx_points* p, const int32_t* labels, int lmem, const double* oldc, int K, int metric,
                 double min_dist, double* newc, int cmem, int* cont) {
-    CRX_REQUIRE(c && p && labels && oldc && newc && cont, "NULL argument");
-    DevBuf<double> sums, o, n;
-    DevBuf<long long> cnt;
-    size_t kd = (size_t)K * p->d;
-    CRX_TRY(sums.alloc(c, kd)); CRX_TRY(cnt.alloc(c, K)); CRX_TRY(o.alloc(c, kd)); CRX_TRY(n.alloc(c, kd));
-    CRX_CUDA(cudaMemcpyAsync(o.p, oldc, kd * sizeof(double), cmem == CRX_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, c->stream));
-    CRX_TRY(crx_cluster_sums(c, p, labels, lmem, K, sums.p, (int64_t*)cnt.p, CRX_DEVICE));
-    CRX_TRY(crx_k_means_finish(c, sums.p, (const int64_t*)cnt.p, o.p, K, p->d, metric, min_dist, n.p, CRX_DEVICE, cont));
-    CRX_CUDA(cudaMemcpyAsync(newc, n.p, kd * sizeof(double), cmem == CRX_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice, c->stream));
-    CRX_CUDA(cudaStreamSynchronize(c->stream));
-    return CRX_OK;
+    return crx_k_means_sharded(c, p, labels, lmem, oldc, K, metric, min_dist, nullptr, newc, cmem, cont);
 }
 
-// tensor-engine PAM: operand rows permuted into cluster order; one CTA per 128-row tile of a cluster against the
-// cluster's own columns
-static int pam_tensor(crx_ctx* c, const crx_points* p, const Segments& seg, int K, int sx, const int32_t* d_crow, int32_t* d_new,
-                      int* d_sw) {
+// pam_lloyds: row sums with error bars for this rank's share of the candidate rows (tensor engine: operand rows
+// permuted into cluster order, one CTA per 128-row tile of a cluster against the cluster's own columns; otherwise exact
+// FP64 distances, one warp per candidate), all-reduce, then the pick (identical on every rank)
+int crx_pam_lloyds_sharded(crx_ctx* c, const crx_points* p, const int32_t* labels, int lmem, const int32_t* crow, int K, int metric,
+                           const crx_comm* comm, int32_t* new_crow, int* swapped) {
+    CRX_REQUIRE(c && p && labels && crow && new_crow && swapped, "NULL argument");
+    CRX_REQUIRE(metric == CRX_EUCLIDEAN || metric == CRX_COSINE, "metric");
+    CRX_CUDA(cudaSetDevice(c->device));
+    const int world = comm_world(comm), me = comm_rank(comm);
     int64_t N = p->n;
-    std::vector<int32_t> off(K + 1);
-    CRX_CUDA(cudaMemcpyAsync(off.data(), seg.off, (K + 1) * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
-    CRX_CUDA(cudaStreamSynchronize(c->stream));
-    std::vector<int4> jobs;
-    for (int cl = 0; cl < K; cl++)
-        for (int r = off[cl]; r < off[cl + 1]; r += 128) jobs.push_back(make_int4(r, off[cl + 1], off[cl], off[cl + 1]));
-    // longest clusters first: the tail of the grid is then made of short jobs
-    std::stable_sort(jobs.begin(), jobs.end(), [](const int4& a, const int4& b) { return a.w - a.z > b.w - b.z; });
-    DevBuf<int4> d_jobs;
-    DevBuf<float> norm_s, errw_s;
+    IoBuf<int32_t> lab;
+    CRX_TRY(lab.bind(c, labels, N, lmem, true));
+    struct SegGuard { Segments s; ~SegGuard() { s.free_all(); } } sg;
+    Segments& seg = sg.s;
+    CRX_TRY(crx_build_segments(c, lab.dev, N, K, &seg));
     DevBuf<double> rowsum, rowerr, exact;
-    DevBuf<int32_t> cand, winner;
-    DevBuf<int> ncand;
-    CRX_TRY(d_jobs.alloc(c, jobs.size() + 1)); CRX_TRY(norm_s.alloc(c, N)); CRX_TRY(errw_s.alloc(c, N));
-    CRX_TRY(rowsum.alloc(c, N)); CRX_TRY(rowerr.alloc(c, N)); CRX_TRY(cand.alloc(c, N)); CRX_TRY(winner.alloc(c, K)); CRX_TRY(ncand.alloc(c, 1));
-    CRX_CUDA(cudaMemcpyAsync(d_jobs.p, jobs.data(), jobs.size() * sizeof(int4), cudaMemcpyHostToDevice, c->stream));
+    DevBuf<int32_t> d_crow, d_new, cand, winner;
+    DevBuf<int> d_sw, ncand;
+    CRX_TRY(rowsum.alloc(c, N)); CRX_TRY(rowerr.alloc(c, N)); CRX_TRY(d_crow.alloc(c, K)); CRX_TRY(d_new.alloc(c, K));
+    CRX_TRY(d_sw.alloc(c, 1)); CRX_TRY(cand.alloc(c, N)); CRX_TRY(winner.alloc(c, K)); CRX_TRY(ncand.alloc(c, 1));
+    CRX_CUDA(cudaMemcpyAsync(d_crow.p, crow, K * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+    CRX_CUDA(cudaMemsetAsync(d_sw.p, 0, sizeof(int), c->stream));
     CRX_CUDA(cudaMemsetAsync(ncand.p, 0, sizeof(int), c->stream));
-    TcOperand op;
-    int st = crx_tc_prepare(c, p, 1, (double)sx, &op, seg.perm, norm_s.p, errw_s.p);
-    if (st == CRX_OK) st = crx_tc_rowsum(c, op, d_jobs.p, (int)jobs.size(), norm_s.p, errw_s.p, rowsum.p, rowerr.p);
-    if (st == CRX_OK) {
+    if (world > 1) {
+        CRX_CUDA(cudaMemsetAsync(rowsum.p, 0, N * sizeof(double), c->stream));
+        CRX_CUDA(cudaMemsetAsync(rowerr.p, 0, N * sizeof(double), c->stream));
+    }
+    double mx = 0;
+    if (metric == CRX_EUCLIDEAN && N >= 4096 && p->d <= 128 && !tc_disabled()) CRX_TRY(points_maxabs(c, p, &mx));
+    if (mx > 0.0 && std::isfinite(mx)) {
+        std::vector<int32_t> off(K + 1);
+        CRX_CUDA(cudaMemcpyAsync(off.data(), seg.off, (K + 1) * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+        CRX_CUDA(cudaStreamSynchronize(c->stream));
+        std::vector<int4> jobs, mine;
+        for (int cl = 0; cl < K; cl++)
+            for (int r = off[cl]; r < off[cl + 1]; r += 128) jobs.push_back(make_int4(r, off[cl + 1], off[cl], off[cl + 1]));
+        // longest clusters first: the tail of the grid is then made of short jobs; ranks take them round-robin
+        std::stable_sort(jobs.begin(), jobs.end(), [](const int4& a, const int4& b) { return a.w - a.z > b.w - b.z; });
+        for (size_t j = (size_t)me; j < jobs.size(); j += world) mine.push_back(jobs[j]);
+        DevBuf<int4> d_jobs;
+        DevBuf<float> norm_s, errw_s;
+        CRX_TRY(d_jobs.alloc(c, mine.size() + 1)); CRX_TRY(norm_s.alloc(c, N)); CRX_TRY(errw_s.alloc(c, N));
+        if (!mine.empty()) CRX_CUDA(cudaMemcpyAsync(d_jobs.p, mine.data(), mine.size() * sizeof(int4), cudaMemcpyHostToDevice, c->stream));
+        TcOperand op;
+        int st = crx_tc_prepare(c, p, 1, (double)scale_for(mx), &op, seg.perm, norm_s.p, errw_s.p);
+        if (st == CRX_OK) st = crx_tc_rowsum(c, op, d_jobs.p, (int)mine.size(), norm_s.p, errw_s.p, rowsum.p, rowerr.p);
+        cudaError_t e = cudaStreamSynchronize(c->stream);  // the job list and the operand are done with
+        op.free_all();
+        if (st != CRX_OK) return st;
+        CRX_CUDA(e);
+    } else {
+        int64_t lo = N * me / world, hi = N * (me + 1) / world;
+        int g = (int)((hi - lo + 7) / 8);
+        if (g > 0) {
+            CRX_KERNEL(c, "pam_rowsum");
+#define LAUNCH_P(T, M, xptr) pam_rowsum_kernel<T, M><<<g, 256, 0, c->stream>>>(xptr, p->ld, p->d, p->sqn, seg.perm, seg.sorted, seg.off, lo, hi, rowsum.p, rowerr.p)
+            if (p->x64) { if (metric == CRX_EUCLIDEAN) LAUNCH_P(double, CRX_EUCLIDEAN, p->x64); else LAUNCH_P(double, CRX_COSINE, p->x64); }
+            else { if (metric == CRX_EUCLIDEAN) LAUNCH_P(float, CRX_EUCLIDEAN, p->x32); else LAUNCH_P(float, CRX_COSINE, p->x32); }
+#undef LAUNCH_P
+        }
+    }
+    CRX_TRY(comm_allreduce(c, comm, rowsum.p, N, CRX_F64, CRX_SUM, CRX_DEVICE));
+    CRX_TRY(comm_allreduce(c, comm, rowerr.p, N, CRX_F64, CRX_SUM, CRX_DEVICE));
+    {
         CRX_KERNEL(c, "pam_bounds");
         pam_bounds_kernel<<<K, 256, 0, c->stream>>>(seg.off, rowsum.p, rowerr.p, p->d, cand.p, ncand.p, winner.p);
     }
     int h = 0;
-    cudaError_t e = cudaMemcpyAsync(&h, ncand.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);  // the job list and the operand are also done with here
-    op.free_all();
-    if (st != CRX_OK) return st;
-    CRX_CUDA(e);
+    CRX_CUDA(cudaMemcpyAsync(&h, ncand.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CRX_CUDA(cudaStreamSynchronize(c->stream));
     CRX_TRY(exact.alloc(c, std::max(h, 1)));
     if (h > 0) {
         CRX_KERNEL(c, "pam_exact");
-        int g = h;
-        if (p->x64) pam_exact_kernel<double><<<g, 256, 0, c->stream>>>(p->x64, p->ld, p->d, p->sqn, seg.perm, seg.sorted, seg.off, cand.p, h, exact.p, c->counters);
-        else pam_exact_kernel<float><<<g, 256, 0, c->stream>>>(p->x32, p->ld, p->d, p->sqn, seg.perm, seg.sorted, seg.off, cand.p, h, exact.p, c->counters);
+#define LAUNCH_E(T, M, xptr) pam_exact_kernel<T, M><<<h, 256, 0, c->stream>>>(xptr, p->ld, p->d, p->sqn, seg.perm, seg.sorted, seg.off, cand.p, h, exact.p, c->counters)
+        if (p->x64) { if (metric == CRX_EUCLIDEAN) LAUNCH_E(double, CRX_EUCLIDEAN, p->x64); else LAUNCH_E(double, CRX_COSINE, p->x64); }
+        else { if (metric == CRX_EUCLIDEAN) LAUNCH_E(float, CRX_EUCLIDEAN, p->x32); else LAUNCH_E(float, CRX_COSINE, p->x32); }
+#undef LAUNCH_E
     }
     {
         CRX_KERNEL(c, "pam_final");
-        pam_final_kernel<<<crx_grid(K, 128), 128, 0, c->stream>>>(seg.perm, seg.sorted, seg.off, cand.p, h, exact.p, winner.p, d_crow, K, d_new, d_sw);
+        pam_final_kernel<<<crx_grid(K, 128), 128, 0, c->stream>>>(seg.perm, seg.sorted, seg.off, cand.p, h, exact.p, winner.p, d_crow.p, K, d_new.p, d_sw.p);
     }
     CRX_CUDA(cudaGetLastError());
+    int hs = 0;
+    CRX_CUDA(cudaMemcpyAsync(new_crow, d_new.p, K * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+    CRX_CUDA(cudaMemcpyAsync(&hs, d_sw.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     CRX_CUDA(cudaStreamSynchronize(c->stream));
+    *swapped = hs;
     return CRX_OK;
 }
 
 int crx_pam_lloyds(crx_ctx* c, const crx_points* p, const int32_t* labels, int lmem, const int32_t* crow, int K, int metric,
                    int32_t* new_crow, int* swapped) {
-    CRX_REQUIRE(c && p && labels && crow && new_crow && swapped, "NULL argument");
-    CRX_CUDA(cudaSetDevice(c->device));
-    int64_t N = p->n;
-    IoBuf<int32_t> lab;
-    CRX_TRY(lab.bind(c, labels, N, lmem, true));
-    Segments seg;
-    int st = crx_build_segments(c, lab.dev, N, K, &seg);
-    if (st != CRX_OK) { seg.free_all(); return st; }
-    DevBuf<double> rowsum;
-    DevBuf<int32_t> d_crow, d_new;
-    DevBuf<int> d_sw;
-    CRX_TRY(rowsum.alloc(c, N)); CRX_TRY(d_crow.alloc(c, K)); CRX_TRY(d_new.alloc(c, K)); CRX_TRY(d_sw.alloc(c, 1));
-    CRX_CUDA(cudaMemcpyAsync(d_crow.p, crow, K * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
-    CRX_CUDA(cudaMemsetAsync(d_sw.p, 0, sizeof(int), c->stream));
-    double mx = 0;
-    if (metric == CRX_EUCLIDEAN && N >= 4096 && p->d <= 128 && !tc_disabled()) CRX_TRY(points_maxabs(c, p, &mx));
-    if (mx > 0.0 && std::isfinite(mx)) {
-        int st2 = pam_tensor(c, p, seg, K, scale_for(mx), d_crow.p, d_new.p, d_sw.p);
-        if (st2 != CRX_OK) { seg.free_all(); return st2; }
-        int h2 = 0;
-        CRX_CUDA(cudaMemcpyAsync(new_crow, d_new.p, K * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
-        CRX_CUDA(cudaMemcpyAsync(&h2, d_sw.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-        CRX_CUDA(cudaStreamSynchronize(c->stream));
-        *swapped = h2;
-        seg.free_all();
-        return CRX_OK;
-    }
-    int g = (int)((N + 7) / 8);
-    {
-        CRX_KERNEL(c, "pam_rowsum");
-#define LAUNCH_P(T, M, xptr) pam_rowsum_kernel<T, M><<<g, 256, 0, c->stream>>>(xptr, p->ld, p->d, p->sqn, seg.perm, seg.sorted, seg.off, N, rowsum.p)
-        if (p->x64) { if (metric == CRX_EUCLIDEAN) LAUNCH_P(double, CRX_EUCLIDEAN, p->x64); else LAUNCH_P(double, CRX_COSINE, p->x64); }
-        else { if (metric == CRX_EUCLIDEAN) LAUNCH_P(float, CRX_EUCLIDEAN, p->x32); else LAUNCH_P(float, CRX_COSINE, p->x32); }
-#undef LAUNCH_P
-    }
-    {
-        CRX_KERNEL(c, "pam_pick");
-#define LAUNCH_Q(T, M, xptr) pam_pick_kernel<T, M><<<K, 256, 0, c->stream>>>(xptr, p->ld, p->d, p->sqn, seg.perm, seg.off, rowsum.p, d_crow.p, d_new.p, d_sw.p, c->counters)
-        if (p->x64) { if (metric == CRX_EUCLIDEAN) LAUNCH_Q(double, CRX_EUCLIDEAN, p->x64); else LAUNCH_Q(double, CRX_COSINE, p->x64); }
-        else { if (metric == CRX_EUCLIDEAN) LAUNCH_Q(float, CRX_EUCLIDEAN, p->x32); else LAUNCH_Q(float, CRX_COSINE, p->x32); }
-#undef LAUNCH_Q
-    }
-    CRX_CUDA(cudaGetLastError());
-    int h = 0;
-    CRX_CUDA(cudaMemcpyAsync(new_crow, d_new.p, K * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
-    CRX_CUDA(cudaMemcpyAsync(&h, d_sw.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-    CRX_CUDA(cudaStreamSynchronize(c->stream));
-    *swapped = h;
-    seg.free_all();
-    return CRX_OK;
+    return crx_pam_lloyds_sharded(c, p, labels, lmem, crow, K, metric, nullptr, new_crow, swapped);
 }
 
-int crx_silhouette_cluster(crx_ctx* c, const crx_points* p, const int32_t* labels, int lmem, const double* centroids,
-                           int cmem, int K, int metric, double* sils) {
+int crx_silhouette_cluster_sharded(crx_ctx* c, const crx_points* p, const int32_t* labels, int lmem, const double* centroids,
+                                   int cmem, int K, int metric, const crx_comm* comm, double* sils) {
     CRX_REQUIRE(c && p && labels && centroids && sils, "NULL argument");
     CRX_CUDA(cudaSetDevice(c->device));
+    const int world = comm_world(comm), me = comm_rank(comm);
     int64_t N = p->n;
     IoBuf<int32_t> lab;
     CRX_TRY(lab.bind(c, labels, N, lmem, true));
     Centroids cen;
     CRX_TRY(cen.stage(c, centroids, cmem, K, p->d, p->ld));
-    Segments seg;
-    int st = crx_build_segments(c, lab.dev, N, K, &seg);
-    if (st != CRX_OK) { seg.free_all(); return st; }
+    struct SegGuard { Segments s; ~SegGuard() { s.free_all(); } } sg;
+    Segments& seg = sg.s;
+    CRX_TRY(crx_build_segments(c, lab.dev, N, K, &seg));
     DevBuf<int32_t> near;
     DevBuf<double> s, d_sils, raw;
     CRX_TRY(near.alloc(c, K)); CRX_TRY(s.alloc(c, N)); CRX_TRY(d_sils.alloc(c, K)); CRX_TRY(raw.alloc(c, K));
+    if (world > 1) CRX_CUDA(cudaMemsetAsync(s.p, 0, N * sizeof(double), c->stream));
     { CRX_KERNEL(c, "near_centroid"); near_centroid_kernel<<<crx_grid(K, 64), 64, 0, c->stream>>>(cen.pad.p, cen.sqn.p, K, p->ld, p->d, metric, near.p); }
-    int g = (int)((N + 7) / 8);
-    {
+    // this rank's share of the points (positions in cluster order); the others contribute zeros to the all-reduce
+    int64_t lo = N * me / world, hi = N * (me + 1) / world;
+    int g = (int)((hi - lo + 7) / 8);
+    if (g > 0) {
         CRX_KERNEL(c, "silhouette_point");
-#define LAUNCH_S(T, M, xptr) silhouette_point_kernel<T, M><<<g, 256, 0, c->stream>>>(xptr, p->ld, p->d, p->sqn, seg.perm, seg.sorted, seg.off, near.p, N, s.p)
+#define LAUNCH_S(T, M, xptr) silhouette_point_kernel<T, M><<<g, 256, 0, c->stream>>>(xptr, p->ld, p->d, p->sqn, seg.perm, seg.sorted, seg.off, near.p, lo, hi, s.p)
         if (p->x64) { if (metric == CRX_EUCLIDEAN) LAUNCH_S(double, CRX_EUCLIDEAN, p->x64); else LAUNCH_S(double, CRX_COSINE, p->x64); }
         else { if (metric == CRX_EUCLIDEAN) LAUNCH_S(float, CRX_EUCLIDEAN, p->x32); else LAUNCH_S(float, CRX_COSINE, p->x32); }
 #undef LAUNCH_S
     }
+    CRX_TRY(comm_allreduce(c, comm, s.p, N, CRX_F64, CRX_SUM, CRX_DEVICE));
     { CRX_KERNEL(c, "silhouette_reduce"); silhouette_reduce_kernel<<<crx_grid(K, 64), 64, 0, c->stream>>>(s.p, seg.off, K, d_sils.p, raw.p); }
     CRX_CUDA(cudaGetLastError());
     std::vector<double> h_raw(K);
@@ -1434,8 +1522,12 @@ int crx_silhouette_cluster(crx_ctx* c, const crx_points* p, const int32_t* label
     double total = 0;  // sils[K] accumulates the per-cluster sums in cluster order (silhouette.hpp:78)
     for (int cl = 0; cl < K; cl++) total = total + h_raw[cl];
     sils[K] = total / (double)N;
-    seg.free_all();
     return CRX_OK;
+}
+
+int crx_silhouette_cluster(crx_ctx* c, const crx_points* p, const int32_t* labels, int lmem, const double* centroids,
+                           int cmem, int K, int metric, double* sils) {
+    return crx_silhouette_cluster_sharded(c, p, labels, lmem, centroids, cmem, K, metric, nullptr, sils);
 }
 
 } // extern "C"

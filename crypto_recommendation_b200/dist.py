@@ -1,13 +1,124 @@
 """Multi-GPU plumbing (one process per GPU, torch.distributed; NCCL on GPUs, gloo in the CPU tests).
 
-Only two exchanges exist on this path:
+Exchanges on this path:
   * k-means update: all-reduce(sum) of the per-cluster coordinate sums [K][D] and counts [K];
+  * k-means++ over sharded rows: all-reduce(max), all-gather of shard totals, broadcast of the pick, per round;
+  * PAM / silhouette / range-search assignment with split work: one all-reduce of an N-long device array;
   * top-P with sharded CANDIDATES: all-gather of the per-shard (similarity, row) lists and a P-way merge.
 Queries, projections and Lloyd assignment shard with no data-path collective.
+
+`Comm` is the crx_comm of include/crx.h: the engine (libcrx.so) drives the sharded algorithms and calls back into
+this module for the collectives, which run on torch.distributed (NCCL for device buffers; with the gloo backend
+device buffers are staged through the host).
 """
+import ctypes
 import os
 
 import numpy as np
+
+_ALLREDUCE = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c_int, ctypes.c_int)
+_ALLGATHER = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c_int)
+_BROADCAST = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c_int, ctypes.c_int)
+
+
+class CrxComm(ctypes.Structure):
+    """struct crx_comm (include/crx.h)."""
+    _fields_ = [("rank", ctypes.c_int), ("world", ctypes.c_int), ("user", ctypes.c_void_p),
+                ("allreduce", _ALLREDUCE), ("allgather", _ALLGATHER), ("broadcast", _BROADCAST)]
+
+
+_NP_DTYPES = {0: np.float32, 1: np.float64, 2: np.int32, 3: np.int64}   # CRX_F32, CRX_F64, CRX_I32, CRX_I64
+
+
+class _DevView:
+    """A raw device pointer as something torch.as_tensor understands (no copy)."""
+    def __init__(self, ptr, count, dt):
+        self.__cuda_array_interface__ = {"shape": (int(count),), "typestr": np.dtype(dt).str, "data": (int(ptr), False),
+                                         "version": 3, "strides": None}
+
+
+class Comm:
+    """crx_comm over torch.distributed.  Keep the object alive while the engine may call it (callbacks are owned here)."""
+
+    def __init__(self, group=None):
+        import torch.distributed as dist
+        self.dist = dist
+        self.group = group
+        self.on = dist.is_initialized() and dist.get_world_size(group) > 1
+        self.rank = dist.get_rank(group) if self.on else 0
+        self.world = dist.get_world_size(group) if self.on else 1
+        self.backend = dist.get_backend(group) if self.on else None
+        self.calls = {"allreduce": 0, "allgather": 0, "broadcast": 0}
+        self.error = None
+        self._cbs = (_ALLREDUCE(self._allreduce), _ALLGATHER(self._allgather), _BROADCAST(self._broadcast))
+        self.struct = CrxComm(self.rank, self.world, None, *self._cbs)
+
+    def ptr(self):
+        return ctypes.byref(self.struct)
+
+    # a (tensor the collective can run on, write-back function) pair for a raw buffer
+    def _tensor(self, ptr, count, dtype, mem):
+        import torch
+        dt = _NP_DTYPES[dtype]
+        if mem == 0:  # host
+            arr = np.ctypeslib.as_array(ctypes.cast(ptr, ctypes.POINTER(np.ctypeslib.as_ctypes_type(dt))), shape=(int(count),))
+            t = torch.from_numpy(arr)
+            if self.backend == "nccl":
+                d = t.cuda()
+                return d, lambda: t.copy_(d.cpu())
+            return t, lambda: None
+        t = torch.as_tensor(_DevView(ptr, count, dt), device=torch.device("cuda", torch.cuda.current_device()))
+        if self.backend != "nccl":   # gloo: stage through the host
+            h = t.cpu()
+            return h, lambda: t.copy_(h)
+        return t, lambda: None
+
+    def _finish(self, mem):
+        if mem == 1 or self.backend == "nccl":
+            import torch
+            torch.cuda.synchronize()
+
+    def _guard(self, name, fn):
+        try:
+            self.calls[name] += 1
+            fn()
+            return 0
+        except Exception as e:  # the engine reports CRX_ERR_COMM; the text is kept here
+            self.error = "%s: %r" % (name, e)
+            return 1
+
+    def _allreduce(self, user, buf, count, dtype, op, mem):
+        def run():
+            t, back = self._tensor(buf, count, dtype, mem)
+            ops = {0: self.dist.ReduceOp.SUM, 1: self.dist.ReduceOp.MAX, 2: self.dist.ReduceOp.MIN}
+            self.dist.all_reduce(t, op=ops[op], group=self.group)
+            self._finish(mem)
+            back()
+            self._finish(mem)
+        return self._guard("allreduce", run)
+
+    def _allgather(self, user, send, recv, count, dtype, mem):
+        def run():
+            import torch
+            s, _ = self._tensor(send, count, dtype, mem)
+            r, back = self._tensor(recv, count * self.world, dtype, mem)
+            parts = [torch.empty_like(s) for _ in range(self.world)]
+            self.dist.all_gather(parts, s.clone(), group=self.group)
+            r.copy_(torch.cat(parts))
+            self._finish(mem)
+            back()
+            self._finish(mem)
+        return self._guard("allgather", run)
+
+    def _broadcast(self, user, buf, count, dtype, root, mem):
+        def run():
+            t, back = self._tensor(buf, count, dtype, mem)
+            src = root if self.group is None else self.dist.get_global_rank(self.group, root)
+            self.dist.broadcast(t, src=src, group=self.group)
+            self._finish(mem)
+            back()
+            self._finish(mem)
+        return self._guard("broadcast", run)
 
 
 def shard_range(n, rank, world):

@@ -152,6 +152,49 @@ int crx_pam_lloyds(crx_ctx* ctx, const crx_points* input_vectors, const int32_t*
 int crx_silhouette_cluster(crx_ctx* ctx, const crx_points* input_vectors, const int32_t* labels, int lmem,
                            const double* centroids, int cmem, int K, int metric, double* sils);
 
+/* ---- the same phases with the work split over several GPUs ---------------------------
+ * One process per GPU.  The engine drives the algorithm and calls back into the host for the (few) exchange steps:
+ * the caller supplies the three collectives (torch.distributed over NCCL in crypto_recommendation_b200/dist.py, or
+ * ncclAllReduce & co. directly from C++).  A callback returns 0 on success; buffers are host memory (mem ==
+ * CRX_HOST) or device memory of the context's GPU (CRX_DEVICE; the context's stream is idle when the callback runs
+ * and the callback must have finished the transfer when it returns).  comm == NULL or world == 1: no exchange. */
+enum { CRX_I32 = 2, CRX_I64 = 3 };               /* with CRX_F32 / CRX_F64: element types of a collective */
+enum { CRX_SUM = 0, CRX_MAX = 1, CRX_MIN = 2 };
+typedef struct crx_comm {
+    int rank, world;
+    void* user;
+    int (*allreduce)(void* user, void* buf, int64_t count, int dtype, int op, int mem);                 /* in place */
+    int (*allgather)(void* user, const void* send, void* recv, int64_t count_per_rank, int dtype, int mem);
+    int (*broadcast)(void* user, void* buf, int64_t count, int dtype, int root, int mem);
+} crx_comm;
+#define CRX_ERR_COMM -5
+/* k_means_pp with the points sharded by contiguous row range: this rank holds global rows
+ * [row_offset, row_offset + n_local).  Per round: all-reduce(max) of the normaliser, all-gather of the per-shard
+ * totals, the owner shard searches its prefix sums, broadcast of the chosen row and of its vector.
+ * centroid_rows[K]: GLOBAL rows, identical on every rank; centroid_vectors[K][D] (host, nullable): their coordinates. */
+int crx_k_means_pp_sharded(crx_ctx* ctx, const crx_points* local_vectors, int64_t row_offset, int64_t n_global,
+                           int cluster_num, int metric, uint64_t seed, const crx_comm* comm, int64_t* centroid_rows,
+                           double* centroid_vectors);
+/* k_means over sharded rows: local cluster sums, all-reduce(sum) of K*D sums + K counts, redundant finish */
+int crx_k_means_sharded(crx_ctx* ctx, const crx_points* local_vectors, const int32_t* labels, int lmem,
+                        const double* old_centroids, int K, int metric, double min_dist, const crx_comm* comm,
+                        double* new_centroids, int cmem, int* continue_clustering);
+/* pam_lloyds / silhouette_cluster / range assignment with the points REPLICATED and the work split: candidate
+ * medoid rows (PAM), silhouette rows, centroids (range search; the Lloyd pass over the remainder is split by
+ * rows).  One all-reduce of an N-long device array per call; results identical on every rank and bit-identical
+ * to the single-GPU call. */
+int crx_pam_lloyds_sharded(crx_ctx* ctx, const crx_points* input_vectors, const int32_t* labels, int lmem,
+                           const int32_t* centroid_rows, int K, int metric, const crx_comm* comm,
+                           int32_t* new_centroid_rows, int* median_swapped);
+int crx_silhouette_cluster_sharded(crx_ctx* ctx, const crx_points* input_vectors, const int32_t* labels, int lmem,
+                                   const double* centroids, int cmem, int K, int metric, const crx_comm* comm, double* sils);
+int crx_lsh_range_assignment_sharded(crx_ctx* ctx, const crx_points* input_vectors, const crx_lsh* lsh_hashtables,
+                                     const int32_t* centroid_rows, int K, int metric, const crx_comm* comm,
+                                     int32_t* labels, double* dists, int mem, int32_t* labels_before_lloyd);
+int crx_cube_range_assignment_sharded(crx_ctx* ctx, const crx_points* input_vectors, const crx_cube* hypercube,
+                                      const int32_t* centroid_rows, int K, int metric, int probes, const crx_comm* comm,
+                                      int32_t* labels, double* dists, int mem, int32_t* labels_before_lloyd);
+
 /* ---- recommendation (crypto_rec.hpp:214-345; loops of main.cpp:159-170, 205-216, 260-269, 353-373) ---- */
 /* For queries [q_begin, q_end) of `queries` (NULL => the table's own rows, rec A):
  *   neighbours = get_LSH_filtered_combined_buckets; sims = get_P_closest(neighbours, user, P);

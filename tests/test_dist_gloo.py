@@ -66,8 +66,24 @@ def _worker(rank, world, port, q):
     want = np.lexsort((np.broadcast_to(np.arange(N), sims_all.shape), -sims_all), axis=1)[:, :P]
     ok2 = np.array_equal(mr, want)
     ok3 = cdist.max_over_ranks(float(rank + 1)) == float(world)
+    # the crx_comm callbacks exactly as libcrx.so invokes them (host buffers): all-reduce sum/max/min, all-gather, broadcast
+    import ctypes
+    comm = cdist.Comm()
+    cs = comm.struct
+    ok4 = comm.world == world and comm.rank == rank
+    a = np.arange(6, dtype=np.float64) * (rank + 1)
+    ok4 &= cs.allreduce(None, a.ctypes.data, 6, 1, 0, 0) == 0 and np.array_equal(a, np.arange(6) * 3.0)
+    m = np.array([rank, 10 - rank, 5], np.int32)
+    ok4 &= cs.allreduce(None, m.ctypes.data, 3, 2, 1, 0) == 0 and m.tolist() == [1, 10, 5]
+    m = np.array([rank, 10 - rank, 5], np.int32)
+    ok4 &= cs.allreduce(None, m.ctypes.data, 3, 2, 2, 0) == 0 and m.tolist() == [0, 9, 5]
+    send = np.array([100 + rank, 200 + rank], np.int64); recv = np.zeros(4, np.int64)
+    ok4 &= cs.allgather(None, send.ctypes.data, recv.ctypes.data, 2, 3, 0) == 0 and recv.tolist() == [100, 200, 101, 201]
+    b = np.full(4, float(rank + 7))
+    ok4 &= cs.broadcast(None, b.ctypes.data, 4, 1, 1, 0) == 0 and (b == 8.0).all()
+    ok4 &= comm.error is None and comm.calls == {"allreduce": 3, "allgather": 1, "broadcast": 1}
     cdist.barrier()
-    q.put((rank, ok1, ok2, ok3))
+    q.put((rank, ok1, ok2, ok3 and bool(ok4)))
     dist.destroy_process_group()
 
 
