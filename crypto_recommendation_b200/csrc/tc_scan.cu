@@ -354,28 +354,40 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         }
                     }
                     if (fmaxf(fmaxf(vm[0], vm[1]), fmaxf(vm[2], vm[3])) > thr && valid) {
-                        // rare path: which columns share a table bucket with this row AND beat the threshold
+                        // rare path.  vm[u] is the maximum of chain u = entries j with j % 4 == u: only the chains that
+                        // beat the threshold are looked at (8 entries each); an entry that is alone in its chain IS the
+                        // chain maximum, so its value needs no register select tree
                         uint32_t bits = 0;
 #pragma unroll
-                        for (int g = 0; g < 8; g++) {
-                            uint4 cc = st4[g];
-                            uint32_t c4[4] = {cc.x, cc.y, cc.z, cc.w};
+                        for (int u = 0; u < 4; u++) {
+                            if (vm[u] > thr) {
 #pragma unroll
-                            for (int u = 0; u < 4; u++) {
-                                uint32_t x = cq ^ c4[u];
-                                uint32_t m = (x - low) & ~x & high;
-                                bool pass = (m != 0u) & (__uint_as_float(r[g * 4 + u]) > thr);
-                                bits |= pass ? (1u << (g * 4 + u)) : 0u;
+                                for (int g = 0; g < 8; g++) {
+                                    bool pass = __uint_as_float(r[g * 4 + u]) > thr;
+                                    if (!DENSE) {  // the chain maximum was taken over the masked scores
+                                        uint32_t x = cq ^ reinterpret_cast<const uint32_t*>(st4)[g * 4 + u];
+                                        pass &= ((x - low) & ~x & high) != 0u;
+                                    }
+                                    bits |= pass ? (1u << (g * 4 + u)) : 0u;
+                                }
                             }
                         }
-                        // lane-local loop over the set bits: all lanes that have a candidate in this chunk walk
-                        // it TOGETHER, so one pass of the insertion code serves the whole warp
+                        const uint32_t all = bits;
+                        // lane-local loop over the set bits: all lanes that have a candidate in this chunk walk it TOGETHER
                         while (bits != 0u) {
                             const int j = __ffs(bits) - 1;
                             bits &= bits - 1u;
-                            const float s = __uint_as_float(pick32(r, j));
+                            const int u = j & 3;
+                            float s;
+                            if (__popc(all & (0x11111111u << u)) == 1) s = u == 0 ? vm[0] : (u == 1 ? vm[1] : (u == 2 ? vm[2] : vm[3]));
+                            else s = __uint_as_float(pick32(r, j));
                             const int c = cbase + j;
-                            if (s > thr && c < p.nb) list_insert(myls, myli, s, c, cnt, thr, minpos);
+                            bool ok = s > thr && c < p.nb;
+                            if (DENSE && ok) {  // the table mask was not part of the hot loop
+                                uint32_t x = cq ^ reinterpret_cast<const uint32_t*>(st4)[j];
+                                ok = ((x - low) & ~x & high) != 0u;
+                            }
+                            if (ok) list_insert(myls, myli, s, c, cnt, thr, minpos);
                         }
                     }
                 } else if (MODE == MODE_ROWSUM) {
@@ -475,7 +487,8 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 template <typename T>
 __global__ void tc_prep_rows_kernel(const T* __restrict__ x, int ld, int D, const double* __restrict__ sqn, int64_t n,
                                     int mode, double scale, int nkb, const int32_t* __restrict__ rowmap, __half* __restrict__ out,
-                                    float* __restrict__ norm_s, float* __restrict__ errw_s) {
+                                    float* __restrict__ norm_s, float* __restrict__ errw_s, float* __restrict__ resid,
+                                    unsigned int* __restrict__ resid_max) {
     int64_t orow = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     int lane = threadIdx.x & 31;
     if (orow >= n) return;
@@ -494,12 +507,24 @@ __global__ void tc_prep_rows_kernel(const T* __restrict__ x, int ld, int D, cons
     }
     int W = nkb * 64;
     __half* o = out + orow * (size_t)(2 * W);
+    double r2 = 0.0;
     for (int c = lane; c < W; c += 32) {
         double v = c < D ? (double)x[row * ld + c] * s : 0.0;
         __half hi = __double2half(v);
-        __half lo = __double2half(v - (double)__half2float(hi));
+        double rest = v - (double)__half2float(hi);
+        __half lo = __double2half(rest);
         o[c] = hi;
         o[W + c] = lo;
+        r2 += rest * rest;
+    }
+    if (resid) {  // |row - hi part| relative to the scaled unit length: what a single-product (hi.hi) score can be off by
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) r2 += __shfl_xor_sync(0xffffffffu, r2, off);
+        if (lane == 0) {
+            float rr = (float)(sqrt(r2) / scale * 1.000001);
+            resid[orow] = rr;
+            if (resid_max) atomicMax(resid_max, __float_as_uint(rr));
+        }
     }
 }
 
@@ -559,15 +584,16 @@ int alloc_operand(crx_ctx* c, int64_t rows, int D, TcOperand* out) {
 
 }  // namespace
 
-int crx_tc_prepare(crx_ctx* c, const crx_points* p, int mode, double scale_log2, TcOperand* out, const int32_t* rowmap, float* norm_s, float* errw_s) {
+int crx_tc_prepare(crx_ctx* c, const crx_points* p, int mode, double scale_log2, TcOperand* out, const int32_t* rowmap, float* norm_s, float* errw_s,
+                   float* resid, unsigned int* resid_max) {
     CRX_REQUIRE(p->d <= 128, "tensor path supports D <= 128");
     CRX_TRY(alloc_operand(c, p->n, p->d, out));
     out->scale_log2 = scale_log2;
     double scale = ldexp(1.0, (int)scale_log2);
     int g = (int)((p->n + 7) / 8);
     CRX_KERNEL(c, "tc_prep");
-    if (p->x64) tc_prep_rows_kernel<double><<<g, 256, 0, c->stream>>>(p->x64, p->ld, p->d, p->sqn, p->n, mode, scale, out->nkb, rowmap, (__half*)out->data, norm_s, errw_s);
-    else tc_prep_rows_kernel<float><<<g, 256, 0, c->stream>>>(p->x32, p->ld, p->d, p->sqn, p->n, mode, scale, out->nkb, rowmap, (__half*)out->data, norm_s, errw_s);
+    if (p->x64) tc_prep_rows_kernel<double><<<g, 256, 0, c->stream>>>(p->x64, p->ld, p->d, p->sqn, p->n, mode, scale, out->nkb, rowmap, (__half*)out->data, norm_s, errw_s, resid, resid_max);
+    else tc_prep_rows_kernel<float><<<g, 256, 0, c->stream>>>(p->x32, p->ld, p->d, p->sqn, p->n, mode, scale, out->nkb, rowmap, (__half*)out->data, norm_s, errw_s, resid, resid_max);
     CRX_CUDA(cudaGetLastError());
     return CRX_OK;
 }
@@ -578,13 +604,13 @@ int crx_tc_prepare_matrix(crx_ctx* c, const double* m, int K, int D, int ld, dou
     out->scale_log2 = scale_log2;
     int g = (K + 7) / 8;
     CRX_KERNEL(c, "tc_prep");
-    tc_prep_rows_kernel<double><<<g, 256, 0, c->stream>>>(m, ld, D, nullptr, K, 1, ldexp(1.0, (int)scale_log2), out->nkb, nullptr, (__half*)out->data, nullptr, nullptr);
+    tc_prep_rows_kernel<double><<<g, 256, 0, c->stream>>>(m, ld, D, nullptr, K, 1, ldexp(1.0, (int)scale_log2), out->nkb, nullptr, (__half*)out->data, nullptr, nullptr, nullptr, nullptr);
     CRX_CUDA(cudaGetLastError());
     return CRX_OK;
 }
 
 int crx_tc_topp(crx_ctx* c, const TcOperand& A, int64_t q0, int64_t nq, const TcOperand& B, const uint32_t* qcode,
-                const uint32_t* ccode, int k, int L, bool dense, float* list_s, int32_t* list_i) {
+                const uint32_t* ccode, int k, int L, bool dense, float* list_s, int32_t* list_i, int nprod) {
     CRX_REQUIRE(A.nkb == B.nkb, "operand widths differ");
     CRX_REQUIRE(k * L <= 32 && k >= 1, "packed codes need k*L <= 32");
     CUtensorMap tmA, tmB;
@@ -594,7 +620,7 @@ int crx_tc_topp(crx_ctx* c, const TcOperand& A, int64_t q0, int64_t nq, const Tc
     memset(&p, 0, sizeof(p));
     p.q0 = q0; p.nq = nq; p.nb = B.rows; p.ntiles = (int)((B.rows + TN - 1) / TN); p.nkb = A.nkb;
     p.last_steps = last_steps_of(A);
-    p.nprod = 3;
+    p.nprod = nprod == 1 ? 1 : 3;
     p.qcode = qcode; p.ccode = ccode;
     uint32_t low = 0, high = 0;
     for (int l = 0; l < L; l++) { low |= 1u << (l * k); high |= 1u << (l * k + k - 1); }
