@@ -167,11 +167,26 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+def dram_traffic(kernel, units):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one launch of `kernel`, from the committed `ncu --set full` capture
+    (profiles/traffic.json, written next to the summaries); None when no capture exists for this workload size."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            t = json.load(f).get(kernel)
+        if t and int(t.get("units", -1)) == int(units):
+            return {"dram_bytes_per_launch": t["dram_bytes_per_launch"], "source": t.get("source")}
+    except (OSError, ValueError):
+        pass
+    return None
+
+
 def workload_config(n, d):
     return {"workload": "C2: %d users x %d coins, rating-like vectors (2-9 known coins/user), cosine LSH L=%d k=%d, top-P=%d neighbours, top-%d coins; "
                         "step = create_LSH_hashtables + rec-A loop of main.cpp:159-170 over every user" % (n, d, L_TABLES, K_HASH, P_NEIGH, N_REC),
             "users": n, "coins": d, "L": L_TABLES, "k": K_HASH, "P": P_NEIGH, "N_rec": N_REC,
-            "l2": "inputs (%.0f MB of user vectors) exceed the 126 MB L2; no explicit flush" % (n * d * 4 / 1e6)}
+            "l2": ("inputs (%.0f MB of user vectors + %.0f MB of split-fp16 operands) exceed the 126 MB L2; no explicit flush"
+                   % (n * d * 4 / 1e6, n * 512 / 1e6)) if n * d * 4 > 126e6 else
+                  ("inputs (%.0f MB) FIT the 126 MB L2 at this --users: not a valid bench size, use the default" % (n * d * 4 / 1e6))}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -255,7 +270,7 @@ def run_crx(args):
     roofline = {"kernel": ("tc_scan_kernel<TOPP> (tcgen05 split-fp16 cosine scan, per-row top-64 in the epilogue)" if tc else
                            "topp_scan_kernel (FP64 SIMT masked cosine scan + per-query top-32 list)"), "bound": "tensor",
                 "achieved": achieved_tf, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s", "frac": achieved_tf / peaks["bf16_tflops"],
-                "traffic": None, "peak_source": peaks["which"] + " bf16 dense GEMM (burst)",
+                "traffic": dram_traffic("tc_topp_scan" if tc else "topp_scan", n), "peak_source": peaks["which"] + " bf16 dense GEMM (burst)",
                 "pipe": ("tcgen05.mma kind::f16 M128 N256 K16, fp32 accumulate in TMEM; executed tensor flops = %.2fx algorithmic "
                          "(3 split-fp16 products, D padded to a multiple of 16)" % tc_factor) if tc else "FP64 SIMT FMA",
                 "executed_tensor_tflops": achieved_tf * tc_factor if tc else None,
@@ -263,7 +278,7 @@ def run_crx(args):
                 "algorithmic_flops": "2*D*sum|cand(u)|", "kernel_ms_all": kernel_ms,
                 "kernel_ms_per_step": scan_ms / args.steps, "share_of_step": scan_ms / args.steps / ms_step}
 
-    e2e_ms, _, _ = timed(step_e2e, max(1, min(2, args.steps)), 1)
+    e2e_ms, _, _ = timed(step_e2e, max(1, min(2, args.steps)), 2)
     h2d = U_pin.numel() * 4 + unk_pin.numel() + mean_pin.numel() * 8
     d2h = recs_host.numel() * 4
     e2e = {"value": world * n / (e2e_ms / 1e3), "unit": "recs/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
@@ -325,7 +340,8 @@ def run_crx(args):
                  "roofline": {"kernel": "tc_scan_kernel<ARGMIN> (tcgen05 split-fp16 filter) + lloyd_refine_kernel (exact FP64 distance of the winner)" if ltc else "lloyd_scan_kernel (FP64 SIMT)",
                               "bound": "tensor", "achieved": fl / (lk_ms / max(1, lk_n) * 1e-3) / 1e12,
                               "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
-                              "frac": fl / (lk_ms / max(1, lk_n) * 1e-3) / 1e12 / peaks["bf16_tflops"], "traffic": None,
+                              "frac": fl / (lk_ms / max(1, lk_n) * 1e-3) / 1e12 / peaks["bf16_tflops"],
+                              "traffic": dram_traffic("tc_argmin_scan" if ltc else "lloyd_scan", npts),
                               "executed_tensor_tflops": fl * lfac / (lk_ms / max(1, lk_n) * 1e-3) / 1e12 if ltc else None,
                               "pipe": ("tcgen05.mma kind::f16, 3 split-fp16 products (%.2fx algorithmic flops), then exact FP64 refine" % lfac) if ltc
                                       else "FP64 SIMT (sub, mul, add per element: 3 FP64 ops for the 2 algorithmic flops)",

@@ -464,25 +464,98 @@ template <typename T, int METRIC>
 __global__ void __launch_bounds__(256)
 kpp_update_kernel(const T* __restrict__ x, int ld, int D, const double* __restrict__ sqn, int64_t N,
                   const double* __restrict__ cvec /* [ld] coordinates, [ld] = exact sum of squares */, int first,
-                  double* __restrict__ mind, unsigned long long* __restrict__ maxbits) {
+                  double* __restrict__ mind, unsigned long long* __restrict__ maxbits,
+                  const int32_t* __restrict__ rowmap /* nullable: only these rows */, const int* __restrict__ nrows_dev) {
     __shared__ rw::WarpTile tiles[8];
     __shared__ double vec[128];
     int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     for (int k = threadIdx.x; k < ld; k += blockDim.x) vec[k] = cvec[k];
     __syncthreads();
-    int64_t row = ((int64_t)blockIdx.x * 8 + warp) * 32 + lane;
-    bool valid = row < N;
-    double d = rw::dist_rows<T, METRIC>(x, ld, D, valid ? row : -1, vec, valid ? sqn[row] : 1.0, cvec[ld], tiles[warp]);
-    double m = 0.0;
-    if (valid) {
-        m = mind[row];
-        if (first || d < m) { m = d; mind[row] = d; }  // running form of the `min == -1 || d < min` scan
-    }
-    // max over values > 0 (max_for_normalizing starts at 0 and uses '>', initialization.hpp:116-117)
-    double mx = (valid && m > 0.0) ? m : 0.0;
+    const int64_t total = rowmap ? (int64_t)*nrows_dev : N;
+    for (int64_t base = ((int64_t)blockIdx.x * 8 + warp) * 32; base < total; base += (int64_t)gridDim.x * 256) {
+        int64_t idx = base + lane;
+        bool valid = idx < total;
+        int64_t row = valid ? (rowmap ? (int64_t)rowmap[idx] : idx) : -1;
+        double d = rw::dist_rows<T, METRIC>(x, ld, D, row, vec, valid ? sqn[row] : 1.0, cvec[ld], tiles[warp]);
+        double m = 0.0;
+        if (valid) {
+            m = mind[row];
+            if (first || d < m) { m = d; mind[row] = d; }  // running form of the `min == -1 || d < min` scan
+        }
+        // max over values > 0 (max_for_normalizing starts at 0 and uses '>', initialization.hpp:116-117)
+        double mx = (valid && m > 0.0) ? m : 0.0;
 #pragma unroll
-    for (int off = 16; off > 0; off >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, off));
-    if (lane == 0 && mx > 0.0) atomicMax(maxbits, (unsigned long long)__double_as_longlong(mx));
+        for (int off = 16; off > 0; off >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, off));
+        if (lane == 0 && mx > 0.0) atomicMax(maxbits, (unsigned long long)__double_as_longlong(mx));
+    }
+}
+
+// Rounds after the first, fp32 data: a point's minimum only changes when the new centroid is closer, which is rare.
+// One streaming pass computes the distance in fp32 (a warp per row, one 16-byte load per lane, 8 rows in flight;
+// relative error <= (D + 4) 2^-24 for the difference form, absolute for the cosine form) and lists only the rows that
+// are not CERTAINLY farther than their current minimum; kpp_update_kernel then evaluates those exactly.  Rows that
+// are not listed contribute their unchanged minimum to the normaliser here.
+template <int METRIC>
+__global__ void __launch_bounds__(256)
+kpp_filter_kernel(const float* __restrict__ x, int ld, int D, const double* __restrict__ sqn, int64_t N,
+                  const double* __restrict__ cvec, const double* __restrict__ mind, int32_t* __restrict__ flagged,
+                  int* __restrict__ nflag, unsigned long long* __restrict__ maxbits) {
+    constexpr int R = 8;
+    int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float4 cv = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (4 * lane < ld) cv = make_float4((float)cvec[4 * lane], (float)cvec[4 * lane + 1], (float)cvec[4 * lane + 2], (float)cvec[4 * lane + 3]);
+    const double cn = cvec[ld];
+    const float slack = (float)(D + 4) * 1.2e-7f;
+    double wmax = 0.0;
+    for (int64_t base = ((int64_t)blockIdx.x * 8 + warp) * R; base < N; base += (int64_t)gridDim.x * 8 * R) {
+        float acc[R];
+        // the decision inputs of this lane's row travel together with the row data (one latency, not two)
+        const int64_t row = base + ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
+        const bool have = (lane & 3) == 0 && row < N;
+        double m = 0.0, nrow = 1.0;
+        if (have) { m = mind[row]; if (METRIC == CRX_COSINE) nrow = sqn[row]; }
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+            int64_t row = base + r;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (row < N && 4 * lane < ld) v = __ldg(reinterpret_cast<const float4*>(x + row * ld + 4 * lane));
+            if (METRIC == CRX_EUCLIDEAN) {
+                float a = v.x - cv.x, b = v.y - cv.y, c2 = v.z - cv.z, d2 = v.w - cv.w;
+                acc[r] = fmaf(a, a, fmaf(b, b, fmaf(c2, c2, d2 * d2)));
+            } else {
+                acc[r] = fmaf(v.x, cv.x, fmaf(v.y, cv.y, fmaf(v.z, cv.z, v.w * cv.w)));
+            }
+        }
+        // 8 rows x 32 partial sums -> lane L ends with the total of row 4 b4 + 2 b3 + b2 (bits of L): halving exchanges
+        // (4 + 2 + 1 shuffles), then two plain butterfly steps over bits 1 and 0
+        const bool h4 = lane & 16, h3 = lane & 8, h2 = lane & 4;
+        float k4[4], k2[2], mine;
+#pragma unroll
+        for (int r = 0; r < 4; r++) k4[r] = (h4 ? acc[r + 4] : acc[r]) + __shfl_xor_sync(0xffffffffu, h4 ? acc[r] : acc[r + 4], 16);
+#pragma unroll
+        for (int r = 0; r < 2; r++) k2[r] = (h3 ? k4[r + 2] : k4[r]) + __shfl_xor_sync(0xffffffffu, h3 ? k4[r] : k4[r + 2], 8);
+        mine = (h2 ? k2[1] : k2[0]) + __shfl_xor_sync(0xffffffffu, h2 ? k2[0] : k2[1], 4);
+        mine += __shfl_xor_sync(0xffffffffu, mine, 2);
+        mine += __shfl_xor_sync(0xffffffffu, mine, 1);
+        bool flag = false;
+        if (have) {
+            double lower;  // a certain lower bound of the exact distance
+            if (METRIC == CRX_EUCLIDEAN) lower = (double)(sqrtf(fmaxf(mine, 0.f)) * (1.f - slack));
+            else lower = 1.0 - ((double)mine / (sqrt(nrow) * sqrt(cn)) + (double)slack + 1e-7);
+            flag = !(lower > m);  // NaN (zero vector under cosine) is listed too
+        }
+        unsigned fm = __ballot_sync(0xffffffffu, flag);
+        if (fm) {
+            int start = 0;
+            if (lane == 0) start = atomicAdd(nflag, __popc(fm));
+            start = __shfl_sync(0xffffffffu, start, 0);
+            if (flag) flagged[start + __popc(fm & ((1u << lane) - 1u))] = (int32_t)row;
+        }
+        if (have && !flag && m > wmax) wmax = m;
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) wmax = fmax(wmax, __shfl_xor_sync(0xffffffffu, wmax, off));
+    if (lane == 0 && wmax > 0.0) atomicMax(maxbits, (unsigned long long)__double_as_longlong(wmax));
 }
 
 // coordinates of one stored row widened to double, followed by its exact sum of squares
@@ -1082,6 +1155,9 @@ int crx_k_means_pp_sharded(crx_ctx* c, const crx_points* p, int64_t row_offset, 
     DevBuf<char> tmp;
     CRX_TRY(mind.alloc(c, N)); CRX_TRY(prob.alloc(c, N)); CRX_TRY(P.alloc(c, N)); CRX_TRY(mx.alloc(c, 1)); CRX_TRY(chosen.alloc(c, 1));
     CRX_TRY(cvec.alloc(c, ld + 1));
+    DevBuf<int32_t> flagged;
+    DevBuf<int> nflag;
+    CRX_TRY(flagged.alloc(c, N)); CRX_TRY(nflag.alloc(c, 1));
     std::vector<double> hvec(ld + 1);
     size_t bytes = 0;
     if (N > 0) CRX_CUDA(cub::DeviceScan::InclusiveSum(nullptr, bytes, prob.p, P.p, (int)N, c->stream));
@@ -1107,9 +1183,22 @@ int crx_k_means_pp_sharded(crx_ctx* c, const crx_points* p, int64_t row_offset, 
         if (out_vectors) memcpy(out_vectors + (size_t)(i - 1) * D, hvec.data(), D * sizeof(double));
         if (i == K) break;
         CRX_CUDA(cudaMemsetAsync(mx.p, 0, sizeof(unsigned long long), c->stream));
-        if (N > 0) {
+        const bool filter = i > 1 && p->x32 != nullptr && N >= 4096;
+        if (N > 0 && filter) {
+            CRX_CUDA(cudaMemsetAsync(nflag.p, 0, sizeof(int), c->stream));
+            {
+                CRX_KERNEL(c, "kpp_filter");
+                int gf = (int)std::min<int64_t>((N + 63) / 64, (int64_t)c->sm_count * 8);
+                if (metric == CRX_EUCLIDEAN) kpp_filter_kernel<CRX_EUCLIDEAN><<<gf, 256, 0, c->stream>>>(p->x32, ld, D, p->sqn, N, cvec.p, mind.p, flagged.p, nflag.p, mx.p);
+                else kpp_filter_kernel<CRX_COSINE><<<gf, 256, 0, c->stream>>>(p->x32, ld, D, p->sqn, N, cvec.p, mind.p, flagged.p, nflag.p, mx.p);
+            }
             CRX_KERNEL(c, "kpp_update");
-#define LAUNCH_K(T, M, xptr) kpp_update_kernel<T, M><<<gridu, 256, 0, c->stream>>>(xptr, ld, D, p->sqn, N, cvec.p, i == 1, mind.p, mx.p)
+            int ge = c->sm_count * 2;  // the list is short; its length stays on the device
+            if (metric == CRX_EUCLIDEAN) kpp_update_kernel<float, CRX_EUCLIDEAN><<<ge, 256, 0, c->stream>>>(p->x32, ld, D, p->sqn, N, cvec.p, 0, mind.p, mx.p, flagged.p, nflag.p);
+            else kpp_update_kernel<float, CRX_COSINE><<<ge, 256, 0, c->stream>>>(p->x32, ld, D, p->sqn, N, cvec.p, 0, mind.p, mx.p, flagged.p, nflag.p);
+        } else if (N > 0) {
+            CRX_KERNEL(c, "kpp_update");
+#define LAUNCH_K(T, M, xptr) kpp_update_kernel<T, M><<<gridu, 256, 0, c->stream>>>(xptr, ld, D, p->sqn, N, cvec.p, i == 1, mind.p, mx.p, nullptr, nullptr)
             if (p->x64) { if (metric == CRX_EUCLIDEAN) LAUNCH_K(double, CRX_EUCLIDEAN, p->x64); else LAUNCH_K(double, CRX_COSINE, p->x64); }
             else { if (metric == CRX_EUCLIDEAN) LAUNCH_K(float, CRX_EUCLIDEAN, p->x32); else LAUNCH_K(float, CRX_COSINE, p->x32); }
 #undef LAUNCH_K

@@ -242,6 +242,28 @@ def test_cluster_sums_chunking(ctx, port):
     assert_float_close(s1[0], seq[0], 1e-13)
 
 
+@pytest.mark.parametrize("metric", METRICS)
+def test_kmeanspp_filter_with_duplicates_and_zero_rows(ctx, port, metric):
+    # fp32 data, N >= 4096: rounds after the first go through the fp32 filter + exact update of the listed rows.
+    # Duplicated rows (distance exactly 0 to a chosen centroid), tightly clustered rows (filter margin) and, for
+    # cosine, zero vectors (NaN distances) must not change the chosen rows.
+    rng = np.random.default_rng(77)
+    base = synth.gaussian_mixture(3000, 40, 6, seed=43, dtype=np.float32)
+    X = np.concatenate([base, base[:1500], base[:700] * np.float32(1.0000001), (base[:300] * 1e-3).astype(np.float32)])
+    if metric == COSINE:
+        X[[17, 4000]] = 0
+    X = X[rng.permutation(len(X))]
+    P = ctx.points(X)
+    ctx.profile(True); ctx.profile_reset(); ctx.counters(reset=True)
+    got = capi.k_means_pp(ctx, P, 14, metric, 31)
+    _, nfilter = ctx.kernel_time("kpp_filter")
+    ctx.profile(False)
+    want = port.k_means_pp(X.astype(np.float64), 14, metric, 31)
+    assert nfilter == 12, "rounds 2..13 use the filter"
+    if ctx.counters()["kpp_near"] == 0:
+        assert np.array_equal(got, want)
+
+
 def test_full_clustering_loop_matches_oracle(ctx, port):
     # the loop of main.cpp:96-103 / 246-254: init -> (assign, update) x iters
     X = synth.gaussian_mixture(8000, 100, 12, seed=81, dtype=np.float32)
