@@ -174,7 +174,7 @@ def dram_traffic(kernel, units):
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
             t = json.load(f).get(kernel)
         if t and int(t.get("units", -1)) == int(units):
-            return {"dram_bytes_per_launch": t["dram_bytes_per_launch"], "source": t.get("source")}
+            return t["dram_bytes_per_launch"]
     except (OSError, ValueError):
         pass
     return None

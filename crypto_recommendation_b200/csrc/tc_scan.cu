@@ -179,26 +179,33 @@ __global__ void __launch_bounds__(NTHREADS_K, 1)
 tc_scan_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, TcParams p) {
     extern __shared__ __align__(1024) uint8_t smem[];
     const int nblk = 2 * p.nkb;
-    uint8_t* sA = smem;                                    // nblk blocks (<= 64 KB), resident
-    uint8_t* sB = smem + 4 * BLK_BYTES;                    // NS-stage ring of 32 KB blocks
-    float* ls = reinterpret_cast<float*>(smem + 4 * BLK_BYTES + NS * BBLK_BYTES);   // [2 halves][HL][TM]  (top-P only)
+    // ARGMIN is persistent: the CTA walks row tiles blockIdx.x, blockIdx.x + gridDim.x, ... with TWO A buffers, so the
+    // A load, the pipeline fill and the drain of one row tile hide behind the MMAs of its neighbours (K = 1024 columns
+    // are only 4 tiles per row tile).  TOPP / ROWSUM keep one row tile per CTA (their lists / long scans fill the CTA).
+    constexpr int NA = MODE == MODE_ARGMIN ? 2 : 1;
+    uint8_t* sA = smem;                                    // NA x (nblk blocks, <= 64 KB)
+    uint8_t* sB = smem + NA * 4 * BLK_BYTES;               // NS-stage ring of 32 KB blocks
+    float* ls = reinterpret_cast<float*>(smem + NA * 4 * BLK_BYTES + NS * BBLK_BYTES);   // [2 halves][HL][TM]  (top-P only)
     int32_t* li = reinterpret_cast<int32_t*>(ls + 2 * HL * TM);
     uint32_t* stile = MODE == MODE_TOPP ? reinterpret_cast<uint32_t*>(li + 2 * HL * TM)
-                                        : reinterpret_cast<uint32_t*>(smem + 4 * BLK_BYTES + NS * BBLK_BYTES);  // [2][TN] codes / half norms
+                                        : reinterpret_cast<uint32_t*>(smem + NA * 4 * BLK_BYTES + NS * BBLK_BYTES);  // [2][TN] codes / half norms
     constexpr int STW = MODE == MODE_ROWSUM ? 2 : 1;       // staged words per column (row sums: norm + error weight)
     uint64_t* bars = reinterpret_cast<uint64_t*>(stile + 2 * TN * STW);
-    uint64_t* a_full = bars;
-    uint64_t* full = bars + 1;
+    uint64_t* a_full = bars;            // [2]
+    uint64_t* a_empty = bars + 2;       // [2]
+    uint64_t* full = bars + 4;
     uint64_t* empty = full + NS;
     uint64_t* tfull = empty + NS;
     uint64_t* tempty = tfull + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
-    float* merge = reinterpret_cast<float*>(tmem_slot + 4);  // [TM][3] floats (argmin) / [TM][2] doubles (row sums): hand-over between the halves
+    // hand-over between the column halves: [TM][3] floats (argmin: aliases the staging tile, shared memory is full) or
+    // [TM][2] doubles (row sums)
+    float* merge = MODE == MODE_ARGMIN ? reinterpret_cast<float*>(stile) : reinterpret_cast<float*>(tmem_slot + 4);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
         if (smem_u32(smem) & 1023u) __trap();  // the 128B-swizzle atoms need a 1024-byte aligned base
-        mbar_init(a_full, 1);
+        for (int b = 0; b < 2; b++) { mbar_init(&a_full[b], 1); mbar_init(&a_empty[b], 1); }
         for (int s = 0; s < NS; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
         for (int b = 0; b < 2; b++) { mbar_init(&tfull[b], 1); mbar_init(&tempty[b], NEPI); }
         fence_barrier_init();
@@ -211,9 +218,11 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    int64_t row0 = p.q0 + (int64_t)blockIdx.x * TM;  // first A row of this CTA
+    int64_t row0 = p.q0 + (int64_t)blockIdx.x * TM;  // first A row of this CTA (of its first row tile: ARGMIN)
     int64_t row_end = p.q0 + p.nq, col0 = 0, col_end = p.nb;
     int ntiles = p.ntiles;
+    const int n_row_tiles = MODE == MODE_ARGMIN ? (int)((p.nq + TM - 1) / TM) : (int)blockIdx.x + 1;
+    const int rt_step = MODE == MODE_ARGMIN ? (int)gridDim.x : n_row_tiles;   // non-persistent modes: exactly one pass
     if (MODE == MODE_ROWSUM) {
         const int4 job = p.jobs[blockIdx.x];
         row0 = job.x; row_end = job.y; col0 = job.z; col_end = job.w;
@@ -223,31 +232,43 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (warp == 0) {
         if (lane == 0) {
             // ---------------- TMA producer ----------------
-            mbar_arrive_expect_tx(a_full, (uint32_t)(nblk * BLK_BYTES));
-            for (int b = 0; b < nblk; b++) tma_load_2d(sA + b * BLK_BYTES, &tmA, b * 64, (int)row0, a_full);
             int stage = 0;
             uint32_t phase = 0;
             const int nload = p.nprod == 1 ? p.nkb : nblk;   // single-product filter: high parts only
-            for (int t = 0; t < ntiles; t++) {
-                for (int b = 0; b < nload; b++) {
-                    mbar_wait(&empty[stage], phase ^ 1);
-                    mbar_arrive_expect_tx(&full[stage], (uint32_t)BBLK_BYTES);
-                    tma_load_2d(sB + stage * BBLK_BYTES, &tmB, b * 64, (int)col0 + t * TN, &full[stage]);
-                    if (++stage == NS) { stage = 0; phase ^= 1; }
+            int it = 0;
+            for (int rt = blockIdx.x; rt < n_row_tiles; rt += rt_step, it++) {
+                const int ab = it & (NA - 1);
+                const uint32_t use = (uint32_t)(it / NA);
+                mbar_wait(&a_empty[ab], (use & 1u) ^ 1u);   // the MMAs of the previous row tile in this buffer are done
+                mbar_arrive_expect_tx(&a_full[ab], (uint32_t)(nblk * BLK_BYTES));
+                const int arow = MODE == MODE_ARGMIN ? (int)(p.q0 + (int64_t)rt * TM) : (int)row0;
+                for (int b = 0; b < nblk; b++) tma_load_2d(sA + ab * 4 * BLK_BYTES + b * BLK_BYTES, &tmA, b * 64, arow, &a_full[ab]);
+                for (int t = 0; t < ntiles; t++) {
+                    for (int b = 0; b < nload; b++) {
+                        mbar_wait(&empty[stage], phase ^ 1);
+                        mbar_arrive_expect_tx(&full[stage], (uint32_t)BBLK_BYTES);
+                        tma_load_2d(sB + stage * BBLK_BYTES, &tmB, b * 64, (int)col0 + t * TN, &full[stage]);
+                        if (++stage == NS) { stage = 0; phase ^= 1; }
+                    }
                 }
             }
         }
     } else if (warp == 1) {
         if (lane == 0) {
             // ---------------- MMA issuer ----------------
-            mbar_wait(a_full, 0);
-            tc_fence_after();
-            const uint32_t a_base = smem_u32(sA), b_base = smem_u32(sB);
+            const uint32_t b_base = smem_u32(sB);
             int stage = 0;
             uint32_t phase = 0;
+            int it = 0;
+            for (int rt = blockIdx.x; rt < n_row_tiles; rt += rt_step, it++) {
+            const int ab = it & (NA - 1);
+            mbar_wait(&a_full[ab], (uint32_t)(it / NA) & 1u);
+            tc_fence_after();
+            const uint32_t a_base = smem_u32(sA) + ab * 4 * BLK_BYTES;
             for (int t = 0; t < ntiles; t++) {
-                const int buf = t & 1;
-                const uint32_t bphase = (uint32_t)(t >> 1) & 1u;
+                const int g = it * ntiles + t;                 // running tile number: TMEM buffer and its phase
+                const int buf = g & 1;
+                const uint32_t bphase = (uint32_t)(g >> 1) & 1u;
                 mbar_wait(&tempty[buf], bphase ^ 1);
                 tc_fence_after();
                 const uint32_t d = tmem_base + (uint32_t)(buf * TN);  // 256 fp32 columns per buffer
@@ -269,6 +290,8 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 }
                 tc_commit(&tfull[buf]);
             }
+            tc_commit(&a_empty[ab]);   // arrives when every MMA issued so far has read its operands
+            }
         }
     } else {
         // ---------------- epilogue: thread = (row, column half) ----------------
@@ -277,7 +300,9 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int quarter = warp & 3;            // TMEM lane quarter this warp may read
         const int half = ew >> 2;                // columns [128*half, 128*half + 128) of every tile
         const int me = quarter * 32 + lane;      // row inside the tile
-        const int64_t grow = MODE == MODE_ROWSUM ? row0 + me : (int64_t)blockIdx.x * TM + me;  // row relative to q0 (absolute for row sums)
+        int it = 0;
+        for (int rt = blockIdx.x; rt < n_row_tiles; rt += rt_step, it++) {
+        const int64_t grow = MODE == MODE_ROWSUM ? row0 + me : (int64_t)rt * TM + me;  // row relative to q0 (absolute for row sums)
         const bool valid = MODE == MODE_ROWSUM ? grow < row_end : grow < p.nq;
         const float na = (MODE == MODE_ROWSUM && valid) ? p.norm_s[grow] : 0.f;
         const float ea = (MODE == MODE_ROWSUM && valid) ? p.errw_s[grow] : 0.f;
@@ -307,8 +332,9 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         uint32_t next_col = fetch_col(0);
         float next_col2 = fetch_col2(0);
         for (int t = 0; t < ntiles; t++) {
-            const int buf = t & 1;
-            const uint32_t bphase = (uint32_t)(t >> 1) & 1u;
+            const int g = it * ntiles + t;             // running tile number (as in the MMA issuer)
+            const int buf = g & 1;
+            const uint32_t bphase = (uint32_t)(g >> 1) & 1u;
             stile[buf * TN * STW + etid] = next_col;
             if (MODE == MODE_ROWSUM) { stile[buf * TN * STW + TN + etid] = __float_as_uint(next_col2); next_col2 = fetch_col2(t + 1); }
             next_col = fetch_col(t + 1);
@@ -462,6 +488,7 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 p.rowerr[grow] = rs_err + dm[me * 2 + 1];
             }
         } else {
+            asm volatile("bar.sync 1, 256;" ::: "memory");   // the staging tile is free: it doubles as the hand-over buffer
             if (half == 1) { merge[me * 3 + 0] = best; merge[me * 3 + 1] = second; merge[me * 3 + 2] = __int_as_float(bidx); }
             asm volatile("bar.sync 1, 256;" ::: "memory");
             if (half == 0 && valid) {
@@ -473,7 +500,9 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 p.second[grow] = sec;
                 p.best_idx[grow] = take1 ? i1 : bidx;
             }
+            asm volatile("bar.sync 1, 256;" ::: "memory");   // before the next row tile stages its first column tile
         }
+        }  // row tiles
     }
     tc_fence_before();
     __syncthreads();
@@ -559,9 +588,10 @@ int make_tensor_map(const TcOperand& op, int box_rows, CUtensorMap* tm) {
 }
 
 size_t smem_for(int mode) {
-    size_t s = (size_t)4 * BLK_BYTES + (size_t)NS * BBLK_BYTES + 2 * TN * 4 + (1 + 2 * NS + 4) * 8 + 16;
+    size_t s = (size_t)4 * BLK_BYTES + (size_t)NS * BBLK_BYTES + 2 * TN * 4 + (8 + 2 * NS) * 8 + 16;
     if (mode == MODE_TOPP) s += (size_t)2 * HL * TM * 8;
-    else s += TM * 2 * 8 + (mode == MODE_ROWSUM ? 2 * TN * 4 : 0);
+    else if (mode == MODE_ROWSUM) s += TM * 2 * 8 + 2 * TN * 4;
+    else s += 4 * BLK_BYTES;   // ARGMIN: second A buffer; the hand-over of the halves aliases the staging tile
     return s;
 }
 
@@ -654,7 +684,7 @@ int crx_tc_argmin(crx_ctx* c, const TcOperand& A, int64_t r0, int64_t nr, const 
     p.half_norm = half_norm; p.best = best; p.second = second; p.best_idx = best_idx;
     size_t smem = smem_for(MODE_ARGMIN);
     CRX_CUDA(cudaFuncSetAttribute(tc_scan_kernel<MODE_ARGMIN, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int grid = (int)((nr + TM - 1) / TM);
+    int grid = (int)std::min<int64_t>((nr + TM - 1) / TM, (int64_t)c->sm_count);   // persistent: one CTA per SM walks the row tiles
     CRX_KERNEL(c, "tc_argmin_scan");
     tc_scan_kernel<MODE_ARGMIN, false><<<grid, NTHREADS_K, smem, c->stream>>>(tmA, tmB, p);
     CRX_CUDA(cudaGetLastError());

@@ -46,6 +46,21 @@ def main():
         C = torch.from_numpy(np.zeros((K, 100))).to(dev)
         lab = torch.randint(0, K, (n,), dtype=torch.int32, device=dev).cpu().numpy()
         print(capi.pam_lloyds(ctx, P, lab, cidx, "euclidean")[0])
+    elif what == "lloyd_pam":
+        # one ARGMIN launch at the C4 shard size, then one ROWSUM launch at a C5-like size
+        n, K = 12_500_000, 1024
+        X = gen(n, 128, K)
+        P = capi.Points(ctx, X)
+        C = X[torch.randint(0, n, (K,), generator=g, device=dev)].to(torch.float64).contiguous()
+        lab = torch.empty(n, dtype=torch.int32, device=dev); dis = torch.empty(n, dtype=torch.float64, device=dev)
+        capi.lloyds_assignment(ctx, P, C, None, "euclidean", lab, dis)
+        print(int(lab[:5].sum()))
+        P.close(); del X, lab, dis
+        n, K = 5_000_000, 256
+        P = capi.Points(ctx, gen(n, 100, K))
+        cidx = capi.k_means_pp(ctx, P, K, "euclidean", 6)
+        lab = torch.randint(0, K, (n,), dtype=torch.int32, device=dev).cpu().numpy()
+        print(capi.pam_lloyds(ctx, P, lab, cidx, "euclidean")[0])
     ctx.synchronize()
 
 
