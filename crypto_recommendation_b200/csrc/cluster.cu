@@ -222,15 +222,16 @@ __global__ void half_norm_kernel(const double* __restrict__ csqn, int K, double 
 // 64-byte reads), each lane then walks ITS row in index order against the row of ITS winning centroid
 // (128 contiguous bytes per 16 coordinates, L2 resident): the reference's own sequence of operations.
 template <typename T>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(128)
 lloyd_refine_kernel(const T* __restrict__ x, int ld, int D, const double* __restrict__ sqn, int64_t row_begin, int64_t N /* end row */,
                     const double* __restrict__ cent,
                     const float* __restrict__ best, const float* __restrict__ second, const int32_t* __restrict__ bidx, int K,
                     double scale, const unsigned int* __restrict__ cmax_bits, int32_t* __restrict__ labels, double* __restrict__ dists,
                     int32_t* __restrict__ amb_rows, int* __restrict__ amb_count) {
-    __shared__ rw::WarpTile tiles[8];
+    __shared__ rw::WarpTile tiles[4];    // 32 rows x 16 coordinates of x
+    __shared__ rw::WarpTile ctiles[4];   // the same 16 coordinates of each row's winning centroid
     int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    int64_t row0 = row_begin + ((int64_t)blockIdx.x * 8 + warp) * 32;
+    int64_t row0 = row_begin + ((int64_t)blockIdx.x * 4 + warp) * 32;
     if (row0 >= N) return;
     int64_t i = row0 + lane;
     bool valid = i < N;
@@ -242,28 +243,46 @@ lloyd_refine_kernel(const T* __restrict__ x, int ld, int D, const double* __rest
     int b = valid ? bidx[i] : 0;
     double margin = valid ? (double)second[i] - (double)best[i] : 0.0;
     bool sure = valid && b >= 0 && b < K && margin > 2.0 * E;
-    const double* crow = cent + (size_t)(sure ? b : 0) * ld;
+    const int bsel = sure ? b : 0;
     double acc = 0.0;
     for (int c0 = 0; c0 < D; c0 += 16) {
+        if constexpr (sizeof(T) == 4) {  // 16-byte pieces: 8 rows x 64 bytes per load instruction
+#pragma unroll
+            for (int it = 0; it < 4; it++) {
+                int r = it * 8 + (lane >> 2);
+                int piece = (lane & 3) * 4;
+                int64_t src = row0 + r;
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (src < N && c0 + piece < ld) v = *reinterpret_cast<const float4*>(x + src * ld + c0 + piece);
+                tiles[warp][r][piece] = (double)v.x; tiles[warp][r][piece + 1] = (double)v.y;
+                tiles[warp][r][piece + 2] = (double)v.z; tiles[warp][r][piece + 3] = (double)v.w;
+            }
+        } else {
 #pragma unroll 4
-        for (int it = 0; it < 16; it++) {
-            int r = it * 2 + (lane >> 4);
-            int64_t src = row0 + r;
-            int col = c0 + (lane & 15);
-            tiles[warp][r][lane & 15] = (src < N && col < D) ? (double)x[src * ld + col] : 0.0;
+            for (int it = 0; it < 16; it++) {
+                int r = it * 2 + (lane >> 4);
+                int64_t src = row0 + r;
+                int col = c0 + (lane & 15);
+                tiles[warp][r][lane & 15] = (src < N && col < D) ? (double)x[src * ld + col] : 0.0;
+            }
+        }
+        // centroid pieces are fetched cooperatively: 8 lanes read the 128 contiguous bytes of one row's centroid (4 full
+        // sectors per row instead of a 32-sector request per lane-private 16-byte load: the L1 was the limiter)
+#pragma unroll
+        for (int it = 0; it < 8; it++) {  // ld is a multiple of 4 and the padding holds zeros
+            int r = it * 4 + (lane >> 3);
+            int piece = (lane & 7) * 2;
+            int br = __shfl_sync(0xffffffffu, bsel, r);
+            double2 v = (c0 + piece < ld) ? *reinterpret_cast<const double2*>(cent + (size_t)br * ld + c0 + piece) : make_double2(0.0, 0.0);
+            ctiles[warp][r][piece] = v.x;
+            ctiles[warp][r][piece + 1] = v.y;
         }
         __syncwarp();
-        double cv[16];
-#pragma unroll
-        for (int k = 0; k < 16; k += 2) {  // ld is a multiple of 4 and the padding holds zeros
-            double2 v = (c0 + k < ld) ? *reinterpret_cast<const double2*>(crow + c0 + k) : make_double2(0.0, 0.0);
-            cv[k] = v.x; cv[k + 1] = v.y;
-        }
         int lim = min(16, D - c0);
 #pragma unroll
         for (int k = 0; k < 16; k++) {
             if (k < lim) {
-                double t = __dsub_rn(tiles[warp][lane][k], cv[k]);
+                double t = __dsub_rn(tiles[warp][lane][k], ctiles[warp][lane][k]);
                 acc = __dadd_rn(acc, __dmul_rn(t, t));
             }
         }
@@ -351,9 +370,9 @@ static int lloyd_scan_tc(crx_ctx* c, const crx_points* p, const Centroids& cen, 
     st = crx_tc_argmin(c, *p->tc_l2, r0, r1 - r0, opC, hn.p, best.p + r0, second.p + r0, bidx.p + r0);
     if (st == CRX_OK) {
         CRX_KERNEL(c, "lloyd_refine");
-        int g = (int)((r1 - r0 + 255) / 256);
-        if (p->x64) lloyd_refine_kernel<double><<<g, 256, 0, c->stream>>>(p->x64, ld, D, p->sqn, r0, r1, cen.pad.p, best.p, second.p, bidx.p, K, scale, cmaxn.p, d_labels, d_dists, amb.p, amb_count.p);
-        else lloyd_refine_kernel<float><<<g, 256, 0, c->stream>>>(p->x32, ld, D, p->sqn, r0, r1, cen.pad.p, best.p, second.p, bidx.p, K, scale, cmaxn.p, d_labels, d_dists, amb.p, amb_count.p);
+        int g = (int)((r1 - r0 + 127) / 128);
+        if (p->x64) lloyd_refine_kernel<double><<<g, 128, 0, c->stream>>>(p->x64, ld, D, p->sqn, r0, r1, cen.pad.p, best.p, second.p, bidx.p, K, scale, cmaxn.p, d_labels, d_dists, amb.p, amb_count.p);
+        else lloyd_refine_kernel<float><<<g, 128, 0, c->stream>>>(p->x32, ld, D, p->sqn, r0, r1, cen.pad.p, best.p, second.p, bidx.p, K, scale, cmaxn.p, d_labels, d_dists, amb.p, amb_count.p);
         CRX_CUDA(cudaGetLastError());
     }
     int h_amb = 0;
