@@ -317,8 +317,19 @@ def run_crx(args):
             cdist.allreduce_cluster_sums(sums, counts)
             capi.k_means_finish(ctx, sums, counts, C, "euclidean", 0.05, newC)
 
+        def step_assign_labels():   # dists = NULL: what the k-means loop needs (main.cpp:96-103 never reads the stored distance)
+            capi.lloyds_assignment(ctx, Q, C, None, "euclidean", labels, want_dists=False)
+
+        def step_kmeans_labels():
+            capi.lloyds_assignment(ctx, Q, C, None, "euclidean", labels, want_dists=False)
+            capi.cluster_sums(ctx, Q, labels, kk, sums, counts)
+            cdist.allreduce_cluster_sums(sums, counts)
+            capi.k_means_finish(ctx, sums, counts, C, "euclidean", 0.05, newC)
+
         a_ms, a_launch, _ = timed(step_assign, args.steps, args.min_warmup)
         k_ms, _, _ = timed(step_kmeans, args.steps, 1)
+        al_ms, _, _ = timed(step_assign_labels, args.steps, 1)
+        kl_ms, _, _ = timed(step_kmeans_labels, args.steps, 1)
         ctx.profile_reset(); ctx.profile(True)
         step_kmeans(); torch.cuda.synchronize(dev)
         ctx.profile(False)
@@ -336,6 +347,8 @@ def run_crx(args):
         fl = 2.0 * dd * npts * kk
         lloyd = {"metric": "Lloyd assign pts*centroids/s", "value": world * npts * kk / (a_ms / 1e3), "unit": "pts*centroids/s",
                  "ms_per_step": a_ms, "kmeans_iteration_ms": k_ms, "kmeans_kernel_ms": breakdown, "scaling": "weak",
+                 "labels_only": {"assign_ms": al_ms, "kmeans_iteration_ms": kl_ms, "value": world * npts * kk / (al_ms / 1e3),
+                                 "note": "crx_lloyds_assignment with dists = NULL; NOT the headline (the reference stores the distance)"},
                  "config": {"workload": "C4 shard: %d x %d fp32 points per GPU, K=%d, euclidean; bit-exact FP64 distances" % (npts, dd, kk)},
                  "roofline": {"kernel": "tc_scan_kernel<ARGMIN> (tcgen05 split-fp16 filter) + lloyd_refine_kernel (exact FP64 distance of the winner)" if ltc else "lloyd_scan_kernel (FP64 SIMT)",
                               "bound": "tensor", "achieved": fl / (lk_ms / max(1, lk_n) * 1e-3) / 1e12,

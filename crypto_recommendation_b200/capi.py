@@ -343,14 +343,19 @@ def _out_pair(pts, labels, dists):
     return labels, dists
 
 
-def lloyds_assignment(ctx, pts, centroids, centroid_rows, metric_type, labels=None, dists=None):
+def lloyds_assignment(ctx, pts, centroids, centroid_rows, metric_type, labels=None, dists=None, want_dists=True):
     """centroids: [K][D] float64 (numpy or CUDA tensor).  labels/dists: optional preallocated outputs
-    (numpy -> host, CUDA tensors -> written in place on the device)."""
+    (numpy -> host, CUDA tensors -> written in place on the device).  want_dists=False: labels only (dists = None)."""
     if not _is_torch(centroids):
         centroids = _np(centroids, np.float64)
     K = centroids.shape[0]
     cr = None if centroid_rows is None else _np(centroid_rows, np.int32)
-    labels, dists = _out_pair(pts, labels, dists)
+    if want_dists:
+        labels, dists = _out_pair(pts, labels, dists)
+    else:
+        dists = None
+        if labels is None:
+            labels = np.zeros(pts.n, np.int32)
     pc, cmem = _ptr(centroids)
     pl, mem = _ptr(labels)
     _check(lib().crx_lloyds_assignment(ctx.h, pts.h, pc, cmem, K, _ptr(cr)[0], METRICS[metric_type], pl, _ptr(dists)[0], mem))

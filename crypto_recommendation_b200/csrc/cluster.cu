@@ -166,7 +166,7 @@ lloyd_scan_kernel(const T* __restrict__ x, int ld, int D, const double* __restri
 __global__ void self_assign_kernel(const int32_t* __restrict__ crow, int K, int32_t* labels, double* dists) {
     if (blockIdx.x == 0 && threadIdx.x == 0)
         for (int c = 0; c < K; c++)  // sequential: a later centroid aliasing the same row wins (assignment.hpp:77-78)
-            if (crow[c] >= 0) { labels[crow[c]] = c; dists[crow[c]] = 0.0; }
+            if (crow[c] >= 0) { labels[crow[c]] = c; if (dists) dists[crow[c]] = 0.0; }
 }
 
 __global__ void compact_unassigned_kernel(const int32_t* __restrict__ labels, int64_t n, int32_t* __restrict__ rows, int* count,
@@ -296,6 +296,23 @@ lloyd_refine_kernel(const T* __restrict__ x, int ld, int D, const double* __rest
     }
 }
 
+// labels only (the caller passed no distance buffer): the same certification as lloyd_refine_kernel without the
+// exact distance of the winner -- 20 bytes per point instead of the whole row
+__global__ void lloyd_label_kernel(const double* __restrict__ sqn, int64_t row_begin, int64_t row_end, const float* __restrict__ best,
+                                   const float* __restrict__ second, const int32_t* __restrict__ bidx, int K, double scale,
+                                   const unsigned int* __restrict__ cmax_bits, int32_t* __restrict__ labels,
+                                   int32_t* __restrict__ amb_rows, int* __restrict__ amb_count) {
+    int64_t i = row_begin + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= row_end) return;
+    double cmax = (double)__uint_as_float(*cmax_bits);
+    double xn = sqrt(sqn[i]);
+    double E = scale * (6e-6 * xn * cmax + 2.5e-7 * (0.5 * cmax * cmax + xn * cmax));
+    int b = bidx[i];
+    double margin = (double)second[i] - (double)best[i];
+    if (b >= 0 && b < K && margin > 2.0 * E) labels[i] = b;
+    else amb_rows[atomicAdd(amb_count, 1)] = (int32_t)i;
+}
+
 static int points_maxabs(crx_ctx* c, const crx_points* p, double* out) {
     if (p->maxabs < 0) {
         DevBuf<unsigned int> m;
@@ -368,7 +385,11 @@ static int lloyd_scan_tc(crx_ctx* c, const crx_points* p, const Centroids& cen, 
     CRX_CUDA(cudaMemsetAsync(amb_count.p, 0, sizeof(int), c->stream));
     { CRX_KERNEL(c, "half_norm"); half_norm_kernel<<<crx_grid(K, 128), 128, 0, c->stream>>>(cen.sqn.p, K, scale, hn.p, cmaxn.p); }
     st = crx_tc_argmin(c, *p->tc_l2, r0, r1 - r0, opC, hn.p, best.p + r0, second.p + r0, bidx.p + r0);
-    if (st == CRX_OK) {
+    if (st == CRX_OK && !d_dists) {
+        CRX_KERNEL(c, "lloyd_label");
+        lloyd_label_kernel<<<crx_grid(r1 - r0, 256), 256, 0, c->stream>>>(p->sqn, r0, r1, best.p, second.p, bidx.p, K, scale, cmaxn.p, d_labels, amb.p, amb_count.p);
+        CRX_CUDA(cudaGetLastError());
+    } else if (st == CRX_OK) {
         CRX_KERNEL(c, "lloyd_refine");
         int g = (int)((r1 - r0 + 127) / 128);
         if (p->x64) lloyd_refine_kernel<double><<<g, 128, 0, c->stream>>>(p->x64, ld, D, p->sqn, r0, r1, cen.pad.p, best.p, second.p, bidx.p, K, scale, cmaxn.p, d_labels, d_dists, amb.p, amb_count.p);
@@ -383,7 +404,9 @@ static int lloyd_scan_tc(crx_ctx* c, const crx_points* p, const Centroids& cen, 
     if (h_amb > 0) {
         unsigned long long add = (unsigned long long)h_amb;
         // exact FP64 scan of the ambiguous rows (ties included: lowest index wins there)
-        CRX_TRY(lloyd_scan(c, p, amb.p, h_amb, cen, CRX_EUCLIDEAN, d_labels, d_dists));
+        DevBuf<double> scratch;
+        if (!d_dists) CRX_TRY(scratch.alloc(c, N));
+        CRX_TRY(lloyd_scan(c, p, amb.p, h_amb, cen, CRX_EUCLIDEAN, d_labels, d_dists ? d_dists : scratch.p));
         unsigned long long cur = 0;
         CRX_CUDA(cudaMemcpyAsync(&cur, c->counters + CRX_CNT_LLOYD_EXACT, sizeof(cur), cudaMemcpyDeviceToHost, c->stream));
         CRX_CUDA(cudaStreamSynchronize(c->stream));
@@ -1290,7 +1313,7 @@ int crx_k_means_sharded(crx_ctx* c, const crx_points* p, const int32_t* labels, 
 
 int crx_lloyds_assignment(crx_ctx* c, const crx_points* p, const double* centroids, int cmem, int K, const int32_t* crow,
                           int metric, int32_t* labels, double* dists, int mem) {
-    CRX_REQUIRE(c && p && centroids && labels && dists, "NULL argument");
+    CRX_REQUIRE(c && p && centroids && labels, "NULL argument");
     CRX_REQUIRE(K >= 1, "K");
     CRX_REQUIRE(metric == CRX_EUCLIDEAN || metric == CRX_COSINE, "metric");
     CRX_CUDA(cudaSetDevice(c->device));
@@ -1299,9 +1322,14 @@ int crx_lloyds_assignment(crx_ctx* c, const crx_points* p, const double* centroi
     IoBuf<int32_t> lab;
     IoBuf<double> dis;
     CRX_TRY(lab.bind(c, labels, p->n, mem, false));
-    CRX_TRY(dis.bind(c, dists, p->n, mem, false));
+    CRX_TRY(dis.bind(c, dists, p->n, mem, false));   // dists == NULL: labels only
     if (metric == CRX_EUCLIDEAN && K >= 32 && p->n >= 1024 && !tc_disabled()) CRX_TRY(lloyd_scan_tc(c, p, cen, lab.dev, dis.dev));
-    else CRX_TRY(lloyd_scan(c, p, nullptr, p->n, cen, metric, lab.dev, dis.dev));
+    else {
+        DevBuf<double> scratch;
+        if (!dis.dev) CRX_TRY(scratch.alloc(c, p->n));
+        CRX_TRY(lloyd_scan(c, p, nullptr, p->n, cen, metric, lab.dev, dis.dev ? dis.dev : scratch.p));
+        CRX_CUDA(cudaStreamSynchronize(c->stream));
+    }
     if (crow) {
         DevBuf<int32_t> d_crow;
         CRX_TRY(d_crow.alloc(c, K));

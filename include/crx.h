@@ -117,7 +117,8 @@ int crx_k_means_pp(crx_ctx* ctx, const crx_points* input_vectors, int cluster_nu
 /* ---- clustering: assignment (assignment.hpp:55-217) ---- */
 /* centroids: [K][D] doubles in `cmem`; centroid_rows[K] (host, may be NULL): row the centroid pointer
  * aliases or -1 -- reproduces `centroids[c]->setCluster(c,0)` (assignment.hpp:77-78).
- * labels[N] int32, dists[N] double in `mem`. */
+ * labels[N] int32, dists[N] double in `mem`.  dists may be NULL (labels only: the k-means loop of main.cpp:96-103
+ * never reads the stored distance; at K >= 32 this skips the exact-distance pass over the rows). */
 int crx_lloyds_assignment(crx_ctx* ctx, const crx_points* input_vectors, const double* centroids, int cmem, int K,
                           const int32_t* centroid_rows, int metric, int32_t* labels, double* dists, int mem);
 /* assignment.hpp:84-105: only rows with labels[v] == -1 are (re)assigned; labels/dists are in/out */

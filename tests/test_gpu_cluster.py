@@ -242,6 +242,23 @@ def test_cluster_sums_chunking(ctx, port):
     assert_float_close(s1[0], seq[0], 1e-13)
 
 
+@pytest.mark.parametrize("K,metric", [(64, EUCLIDEAN), (7, EUCLIDEAN), (40, COSINE)])
+def test_lloyd_labels_only_equals_full_call(ctx, port, K, metric):
+    # dists == NULL: same labels (tensor filter + exact re-scan of ambiguous rows at K >= 32, exact scan otherwise),
+    # including duplicated centroids (exact ties -> lowest index) and the centroid self-assignment
+    X = synth.gaussian_mixture(9000, 48, 10, seed=91, dtype=np.float32)
+    X64 = X.astype(np.float64)
+    cidx = port.rand_selection(X64, K, 4)
+    C = X64[cidx].copy()
+    C[K - 1] = C[0]
+    P = ctx.points(X)
+    lab, dist = capi.lloyds_assignment(ctx, P, C, cidx, metric)
+    lab2, none = capi.lloyds_assignment(ctx, P, C, cidx, metric, want_dists=False)
+    assert none is None and np.array_equal(lab, lab2)
+    rl, _ = port.lloyds_assignment(X64, C, cidx, metric)
+    assert np.array_equal(lab2, rl)
+
+
 @pytest.mark.parametrize("metric", METRICS)
 def test_kmeanspp_filter_with_duplicates_and_zero_rows(ctx, port, metric):
     # fp32 data, N >= 4096: rounds after the first go through the fp32 filter + exact update of the listed rows.
