@@ -18,7 +18,11 @@ struct TcOperand {
     int d = 0;                // true number of columns
     double scale_log2 = 0;    // values were multiplied by 2^scale_log2 before the split
     crx_ctx* owner = nullptr;
-    void free_all() { if (owner) crx_free(owner, data); data = nullptr; }
+    TcOperand() {}
+    TcOperand(const TcOperand&) = delete;
+    TcOperand& operator=(const TcOperand&) = delete;
+    ~TcOperand() { free_all(); }   // stream-ordered free: safe after the launches that read it were enqueued
+    void free_all() { if (owner && data) crx_free(owner, data); data = nullptr; }
 };
 
 // mode 0: rows scaled to unit length times 2^10 (cosine);  mode 1: all rows times 2^scale_log2
