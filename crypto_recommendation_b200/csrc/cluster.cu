@@ -471,7 +471,8 @@ __global__ void kmeans_finish_kernel(const double* __restrict__ sums, const long
     int cl = blockIdx.x * blockDim.x + threadIdx.x;
     if (cl >= K) return;
     double div = (double)counts[cl];
-    double na = 0.0, nb = 0.0, acc = 0.0, s = 0.0, comp = 0.0;
+    double na = 0.0, nb = 0.0, acc = 0.0;
+    X87 ip = {0.0, 0.0};
     for (int i = 0; i < D; i++) {
         double v = sums[(size_t)cl * D + i];
         if (div != 0.0) v = __ddiv_rn(v, div);  // divDimensionsByD skips count 0 (cust_vector.hpp:189)
@@ -483,13 +484,10 @@ __global__ void kmeans_finish_kernel(const double* __restrict__ sums, const long
         } else {
             na = __dadd_rn(na, __dmul_rn(v, v));
             nb = __dadd_rn(nb, __dmul_rn(o, o));
-            double p, pe, se;
-            two_prod(v, o, p, pe);
-            two_sum(s, p, s, se);
-            comp = __dadd_rn(comp, __dadd_rn(pe, se));
+            x87_add(ip, __dmul_rn(v, o));
         }
     }
-    double dist = metric == CRX_EUCLIDEAN ? __dsqrt_rn(acc) : __dsub_rn(1.0, cos_sim_from(__dadd_rn(s, comp), na, nb));
+    double dist = metric == CRX_EUCLIDEAN ? __dsqrt_rn(acc) : __dsub_rn(1.0, cos_sim_x87(ip, na, nb));
     if (dist > min_dist) atomicExch(moved, 1);
 }
 

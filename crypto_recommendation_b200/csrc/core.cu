@@ -69,7 +69,7 @@ __global__ void pair_op_kernel(const TA* __restrict__ xa, int lda, const double*
     const TA* a = xa + (int64_t)ia[i] * lda;
     const TB* b = xb + (int64_t)ib[i] * ldb;
     double r;
-    if (op == 0) r = dot_accurate(a, b, d);
+    if (op == 0) r = x87_to_double(dot_x87(a, b, d));   // the long double of cust_vector.hpp:107-121, rounded to double
     else if (op == 1) r = euclid_exact(a, b, d);
     else if (op == 2) r = __dsub_rn(1.0, cos_sim_exact(a, b, d, na[ia[i]], nb[ib[i]]));
     else r = cos_sim_exact(a, b, d, na[ia[i]], nb[ib[i]]);

@@ -11,7 +11,7 @@ constexpr int TW = 17;  // padded tile width (doubles)
 typedef double WarpTile[32][TW];
 
 // result of a walk: Euclidean => acc = sum (x_k - v_k)^2 exactly as the reference;
-// cosine => (hi, lo) compensated dot product x . v
+// cosine => (h, l) = the reference's x87 inner product x . v (64-bit mantissa, sequentially rounded)
 struct Walk {
     double a, b;
 };
@@ -21,7 +21,8 @@ template <typename T, int METRIC>
 __device__ __forceinline__ Walk walk_rows(const T* __restrict__ x, int ld, int d, int64_t myrow, const double* __restrict__ vec,
                                           WarpTile& tile) {
     int lane = threadIdx.x & 31;
-    double s = 0.0, c = 0.0;
+    double s = 0.0;
+    X87 acc = {0.0, 0.0};
     for (int c0 = 0; c0 < d; c0 += 16) {
 #pragma unroll 4
         for (int it = 0; it < 16; it++) {
@@ -38,18 +39,13 @@ __device__ __forceinline__ Walk walk_rows(const T* __restrict__ x, int ld, int d
                 s = __dadd_rn(s, __dmul_rn(t, t));
             }
         } else {
-            for (int k = 0; k < lim; k++) {
-                double p, pe, se;
-                two_prod(tile[lane][k], vec[c0 + k], p, pe);
-                two_sum(s, p, s, se);
-                c = __dadd_rn(c, __dadd_rn(pe, se));
-            }
+            for (int k = 0; k < lim; k++) x87_add(acc, __dmul_rn(tile[lane][k], vec[c0 + k]));
         }
         __syncwarp();
     }
     Walk w;
     if (METRIC == CRX_EUCLIDEAN) { w.a = s; w.b = 0.0; }
-    else two_sum(s, c, w.a, w.b);
+    else { w.a = acc.h; w.b = acc.l; }
     return w;
 }
 
@@ -59,7 +55,8 @@ __device__ __forceinline__ double dist_rows(const T* __restrict__ x, int ld, int
                                             double nrow, double nvec, WarpTile& tile) {
     Walk w = walk_rows<T, METRIC>(x, ld, d, myrow, vec, tile);
     if (METRIC == CRX_EUCLIDEAN) return __dsqrt_rn(w.a);
-    return __dsub_rn(1.0, cos_sim_from(w.a, nrow, nvec));
+    X87 ip = {w.a, w.b};
+    return __dsub_rn(1.0, cos_sim_x87(ip, nrow, nvec));
 }
 
 // stage one row of x into shared memory as doubles (all 32 lanes of the calling warp)

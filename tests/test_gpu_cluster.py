@@ -25,26 +25,21 @@ def test_golden_clustering(ctx, port, golden, metric):
     assert np.array_equal(cidx, g["cl_kpp_%s" % name])
     lab, dist = capi.lloyds_assignment(ctx, P, X[cidx], cidx, metric)
     assert_labels(lab, g["cl_lloyd_lab_%s" % name], dist_fn(port, X, X[cidx], metric))
-    if metric == EUCLIDEAN:
-        assert np.array_equal(dist, g["cl_lloyd_dist_%s" % name])  # bit-exact
-    else:
-        assert_float_close(dist, g["cl_lloyd_dist_%s" % name], 1e-12)
+    assert np.array_equal(dist, g["cl_lloyd_dist_%s" % name])  # bit-exact, both metrics (cosine: x87 emulation)
     ret, newc = capi.k_means(ctx, P, g["cl_lloyd_lab_%s" % name], X[cidx], metric, 0.05)
     assert ret == bool(g["cl_kmeans_ret_%s" % name])
     assert_float_close(newc, g["cl_kmeans_C_%s" % name], 1e-12)
     lab2, dist2 = capi.lloyds_assignment(ctx, P, g["cl_kmeans_C_%s" % name], None, metric)
     assert_labels(lab2, g["cl_lloyd2_lab_%s" % name], dist_fn(port, X, g["cl_kmeans_C_%s" % name], metric))
-    assert_float_close(dist2, g["cl_lloyd2_dist_%s" % name], 1e-12)
+    assert np.array_equal(dist2, g["cl_lloyd2_dist_%s" % name])
     t = capi.LshTables(ctx, P, metric, 4, 5, 10, 4.0, 8003)
     l, d, b = capi.lsh_range_assignment(ctx, P, t, cidx, metric)
     assert np.array_equal(b, g["cl_lshrange_before_%s" % name])
-    assert_labels(l, g["cl_lshrange_lab_%s" % name], dist_fn(port, X, X[cidx], metric))
-    assert_float_close(d, g["cl_lshrange_dist_%s" % name], 1e-12)
+    assert np.array_equal(l, g["cl_lshrange_lab_%s" % name]) and np.array_equal(d, g["cl_lshrange_dist_%s" % name])
     cube = capi.Hypercube(ctx, P, metric, 5, 4.0, 8004)
     l, d, b = capi.cube_range_assignment(ctx, P, cube, cidx, metric, 6)
     assert np.array_equal(b, g["cl_cuberange_before_%s" % name])
-    assert_labels(l, g["cl_cuberange_lab_%s" % name], dist_fn(port, X, X[cidx], metric))
-    assert_float_close(d, g["cl_cuberange_dist_%s" % name], 1e-12)
+    assert np.array_equal(l, g["cl_cuberange_lab_%s" % name]) and np.array_equal(d, g["cl_cuberange_dist_%s" % name])
     sw, new = capi.pam_lloyds(ctx, P, g["cl_lloyd_lab_%s" % name], cidx, metric)
     assert sw == bool(g["cl_pam_sw_%s" % name]) and np.array_equal(new, g["cl_pam_new_%s" % name])
     assert_float_close(capi.silhouette_cluster(ctx, P, g["cl_lloyd_lab_%s" % name], X[cidx], metric), g["cl_sil_%s" % name], 1e-10)
@@ -64,12 +59,8 @@ def test_lloyd_kmeans_oracle(ctx, port, metric, dtype, n, d, k):
     C = X64[cidx]
     lab, dist = capi.lloyds_assignment(ctx, P, C, cidx, metric)
     rl, rd = port.lloyds_assignment(X64, C, cidx, metric)
-    near = assert_labels(lab, rl, dist_fn(port, X64, C, metric), max_near=0 if metric == EUCLIDEAN else 3)
-    ok = lab == rl
-    if metric == EUCLIDEAN:
-        assert np.array_equal(dist[ok], rd[ok])
-    else:
-        assert_float_close(dist[ok], rd[ok], 1e-12)
+    near = assert_labels(lab, rl, dist_fn(port, X64, C, metric), max_near=0)
+    assert np.array_equal(lab, rl) and np.array_equal(dist, rd)   # bit-exact for both metrics
     ret, newc = capi.k_means(ctx, P, rl, C, metric, 0.05)
     pret, pC = port.k_means(X64, rl, C, metric, 0.05)
     assert ret == pret
@@ -138,17 +129,13 @@ def test_range_assignment_oracle(ctx, port, metric, dtype):
         l, d, b = capi.lsh_range_assignment(ctx, P, t, cidx, metric)
         rl, rd, rb = port.lsh_range_assignment(X64, cidx, metric, k, L, div, w, 112)
         assert np.array_equal(b, rb), (np.sum(b != rb), (rb >= 0).sum())
-        assert_labels(l, rl, fn, max_near=0 if metric == EUCLIDEAN else 3)
-        ok = l == rl
-        assert_float_close(d[ok], rd[ok], 1e-12)
+        assert np.array_equal(l, rl) and np.array_equal(d, rd)   # labels and distances bit-exact, both metrics
     for (k, w, probes) in [(8, 6.0, 20), (6, 0.4, 1), (10, 3.0, 64)]:
         cube = capi.Hypercube(ctx, P, metric, k, w, 113)
         l, d, b = capi.cube_range_assignment(ctx, P, cube, cidx, metric, probes)
         rl, rd, rb = port.cube_range_assignment(X64, cidx, metric, k, w, probes, 113)
         assert np.array_equal(b, rb), (np.sum(b != rb), (rb >= 0).sum())
-        assert_labels(l, rl, fn, max_near=0 if metric == EUCLIDEAN else 3)
-        ok = l == rl
-        assert_float_close(d[ok], rd[ok], 1e-12)
+        assert np.array_equal(l, rl) and np.array_equal(d, rd)   # labels and distances bit-exact, both metrics
 
 
 @pytest.mark.parametrize("metric", METRICS)

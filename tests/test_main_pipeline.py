@@ -39,6 +39,33 @@ def test_reference_main_reproduces_golden(tmp_path):
     assert mg.run_main(REF_BIN, str(tmp_path)) == expected()
 
 
+def expected_validation():
+    with open(os.path.join(ROOT, "tests", "golden", "main_validate_expected.txt")) as f:
+        return f.read().splitlines()
+
+
+@pytest.mark.skipif(not os.path.exists(REF_BIN), reason="oracle/_ref/recommendation_ref not built (needs /root/reference)")
+def test_reference_validation_reproduces_golden(tmp_path):
+    mg.make_inputs(str(tmp_path))
+    lines, val = mg.run_main(REF_BIN, str(tmp_path), validate=True)
+    assert lines == expected() and val == expected_validation()
+
+
+@pytest.mark.gpu
+def test_ten_fold_validation_over_dropin_headers_matches_reference(tmp_path):
+    # f-3: main.cpp -validate = split_to_10 / merge_except_for / hide_one_score (drop-in mirrors) around ten rebuilds of
+    # the LSH tables + get_P_closest + get_predicted_user_sim on the engine; every running error sum and the MAE printed
+    # by main.cpp:393-437 must equal the reference build's
+    assert os.path.exists(CRX_BIN), "oracle/_ref/recommendation_crx missing: run tools/build_main_dropin.sh where /root/reference exists"
+    mg.make_inputs(str(tmp_path))
+    lines, val = mg.run_main(CRX_BIN, str(tmp_path), validate=True)
+    want = expected_validation()
+    assert len(val) == len(want) and len(want) > 100
+    bad = [(i, a, b) for i, (a, b) in enumerate(zip(val, want)) if a != b]
+    assert not bad, "%d of %d validation lines differ, first: %r" % (len(bad), len(want), bad[:3])
+    assert [l for l in lines] == expected()
+
+
 @pytest.mark.gpu
 def test_main_cpp_over_dropin_headers_matches_reference(tmp_path):
     assert os.path.exists(CRX_BIN), "oracle/_ref/recommendation_crx missing: run tools/build_main_dropin.sh where /root/reference exists"
