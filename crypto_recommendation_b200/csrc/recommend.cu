@@ -256,7 +256,7 @@ __device__ __forceinline__ void warp_lomuto_topn(double* key, int* val, int n, i
 // 64 (tensor-core filter, float scores scaled by `approx_scale`, filter error `approx_eps`).
 // ------------------------------------------------------------------------------------------------
 template <typename TQ, typename TB, int LISTN, typename TS>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(128)
 rec_finalize_kernel(const TQ* __restrict__ xq, int ldq, const double* __restrict__ sqn_q, const uint8_t* __restrict__ unk_q,
                     const double* __restrict__ mean_q, const TB* __restrict__ xb, int ldb, const double* __restrict__ sqn_b,
                     const double* __restrict__ mean_b, int D, int64_t q_begin, int64_t nq, int P, int Nrec,
@@ -264,25 +264,25 @@ rec_finalize_kernel(const TQ* __restrict__ xq, int ldq, const double* __restrict
                     double approx_scale, double approx_eps, int32_t* __restrict__ recs, int32_t* __restrict__ nbr_rows,
                     double* __restrict__ nbr_sims, unsigned long long* counters) {
     constexpr int EPL = LISTN / 32;  // list entries per lane
-    __shared__ int a_idx[8][LISTN];
-    __shared__ double a_sim[8][LISTN];
-    __shared__ int s_idx[8][32];
-    __shared__ double s_sim[8][32];
-    __shared__ double s_pred[8][128];
-    __shared__ int s_coin[8][128];
+    constexpr int QW = 4;            // queries (warps) per block
+    __shared__ int a_idx[QW][LISTN];
+    __shared__ double a_sim[QW][LISTN];
+    __shared__ int s_idx[QW][32];
+    __shared__ double s_sim[QW][32];
+    __shared__ double s_pred[QW][128];
+    __shared__ int s_coin[QW][128];
+    __shared__ rw::WarpTile tiles[QW];
+    __shared__ double qvec[QW][128];
     int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    int64_t qrel = (int64_t)blockIdx.x * 8 + warp;
+    int64_t qrel = (int64_t)blockIdx.x * QW + warp;
     if (qrel >= nq) return;
     int64_t qrow = q_begin + qrel;
-    const TQ* q = xq + qrow * ldq;
     // every 32-slot group of the list is an independent "best 32 of its share of the columns" list
     // (the FP64 scan has one, the tensor-core filter one per column half): a candidate outside the lists
     // scores at most max over FULL groups of (smallest approximate score of the group)
     double floor_s = -INFINITY;
     int nvalid = 0;
-    // this lane's 4 coordinates of the query row
-    double qv[4] = {0.0, 0.0, 0.0, 0.0};
-    if (4 * lane < ldq) pt::ld4(q + 4 * lane, qv);
+    rw::stage_vector<TQ>(xq, ldq, qrow, qvec[warp]);
     const double nq_ = sqn_q[qrow];
 #pragma unroll
     for (int e = 0; e < EPL; e++) {
@@ -290,30 +290,12 @@ rec_finalize_kernel(const TQ* __restrict__ xq, int ldq, const double* __restrict
         int idx = list_i[qrel * LISTN + slot];
         double ap = idx >= 0 ? (double)list_s[qrel * LISTN + slot] : INFINITY;
         unsigned vm = __ballot_sync(0xffffffffu, idx >= 0);
-        // exact similarity of every listed candidate (crypto_rec.hpp:220): the warp walks the candidates,
-        // lanes split the coordinates (one 16-byte load each), FP64 FMA + shuffle tree
+        // the reference's own similarity of every listed candidate (crypto_rec.hpp:220, cust_vector.hpp:160-174): each
+        // lane walks ITS candidate in index order with the x87 accumulation, rows staged through shared memory
         double mysim = -INFINITY;
-        for (int c0 = 0; c0 < 32; c0 += 4) {
-            if (!((vm >> c0) & 0xfu)) continue;
-            int ci[4];
-            double cv[4][4], part[4];
-#pragma unroll
-            for (int u = 0; u < 4; u++) {  // four independent 16-byte loads in flight
-                ci[u] = __shfl_sync(0xffffffffu, idx, c0 + u);
-                cv[u][0] = cv[u][1] = cv[u][2] = cv[u][3] = 0.0;
-                if (ci[u] >= 0 && 4 * lane < ldb) pt::ld4(xb + (size_t)ci[u] * ldb + 4 * lane, cv[u]);
-            }
-#pragma unroll
-            for (int u = 0; u < 4; u++)
-                part[u] = __fma_rn(cv[u][0], qv[0], __fma_rn(cv[u][1], qv[1], __fma_rn(cv[u][2], qv[2], __dmul_rn(cv[u][3], qv[3]))));
-#pragma unroll
-            for (int off = 16; off > 0; off >>= 1) {
-#pragma unroll
-                for (int u = 0; u < 4; u++) part[u] += __shfl_xor_sync(0xffffffffu, part[u], off);
-            }
-#pragma unroll
-            for (int u = 0; u < 4; u++)
-                if (lane == c0 + u && ci[u] >= 0) mysim = cos_sim_from(part[u], sqn_b[ci[u]], nq_);
+        if (vm) {
+            rw::Walk w = rw::walk_rows<TB, CRX_COSINE>(xb, ldb, D, idx >= 0 ? (int64_t)idx : -1, qvec[warp], tiles[warp]);
+            if (idx >= 0) { X87 ip = {w.a, w.b}; mysim = cos_sim_x87(ip, sqn_b[idx], nq_); }
         }
         a_idx[warp][slot] = idx;
         a_sim[warp][slot] = mysim;
@@ -765,14 +747,14 @@ int crx_recommend_lsh(crx_ctx* c, const crx_lsh* t, const crx_points* queries, i
     CRX_TRY(o_sims.bind(c, nbr_sims, (size_t)nq * P, mem, false));
     {
         CRX_KERNEL(c, "rec_finalize");
-        int g = (int)((nq + 7) / 8);
+        int g = (int)((nq + 3) / 4);
 #define LAUNCH_F(TQ, TB, xqp, xbp)                                                                                         \
     do {                                                                                                                   \
         if (use_tc)                                                                                                        \
-            rec_finalize_kernel<TQ, TB, TC_LIST, float><<<g, 256, 0, c->stream>>>(xqp, queries->ld, queries->sqn, queries->unknown, queries->mean, xbp, \
+            rec_finalize_kernel<TQ, TB, TC_LIST, float><<<g, 128, 0, c->stream>>>(xqp, queries->ld, queries->sqn, queries->unknown, queries->mean, xbp, \
                 base->ld, base->sqn, base->mean, base->d, q_begin, nq, P, Nrec, tl_s.p, tl_i.p, nc.p, tc_unscale, 8e-6, o_recs.dev, o_rows.dev, o_sims.dev, c->counters); \
         else                                                                                                               \
-            rec_finalize_kernel<TQ, TB, LIST, double><<<g, 256, 0, c->stream>>>(xqp, queries->ld, queries->sqn, queries->unknown, queries->mean, xbp, \
+            rec_finalize_kernel<TQ, TB, LIST, double><<<g, 128, 0, c->stream>>>(xqp, queries->ld, queries->sqn, queries->unknown, queries->mean, xbp, \
                 base->ld, base->sqn, base->mean, base->d, q_begin, nq, P, Nrec, list_s.p, list_i.p, nc.p, 1.0, 1e-12, o_recs.dev, o_rows.dev, o_sims.dev, c->counters); \
     } while (0)
         if (queries->x64 && base->x64) LAUNCH_F(double, double, queries->x64, base->x64);

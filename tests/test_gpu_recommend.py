@@ -22,7 +22,7 @@ def check_rec(out, ref_out, max_soft_frac=0.0):
     assert hard == 0, "%d queries with a wrong neighbour list" % hard
     assert soft <= max_soft_frac * nq, "%d of %d queries differ by near-ties (allowed %.0f%%)" % (soft, nq, 100 * max_soft_frac)
     same = np.all(out["nbr_rows"] == nbr, axis=1)
-    assert_float_close(out["nbr_sims"][same], sim[same], 1e-12, "similarities")
+    assert np.array_equal(out["nbr_sims"][same], sim[same]), "similarities are the reference's own doubles (x87 accumulation), bit for bit"
     bad = np.flatnonzero(~np.all(out["recs"] == recs, axis=1) & same)
     assert len(bad) == 0, "recommended coins differ for %d queries with identical neighbours, e.g. %s vs %s" % (
         len(bad), out["recs"][bad[:2]].tolist(), recs[bad[:2]].tolist())
