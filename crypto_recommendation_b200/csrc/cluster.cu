@@ -423,39 +423,41 @@ static int lloyd_scan_tc(crx_ctx* c, const crx_points* p, const Centroids& cen, 
 // j owns coordinate j and walks the rows IN INPUT ORDER; chunk partials are then added in order.
 // A cluster of <= CH members therefore gets the reference's own sequential sum, bit for bit.
 // ------------------------------------------------------------------------------------------------
-constexpr int SUM_CH = 1024;
+constexpr int SUM_CH = 1024;        // smallest chunk
+constexpr int SUM_CH_MAX = 1 << 20; // largest: a cluster up to this size can still be one sequential sum
 
 template <typename T>
 __global__ void __launch_bounds__(128)
 chunk_sums_kernel(const T* __restrict__ x, int ld, int D, const int32_t* __restrict__ perm, const int32_t* __restrict__ off,
-                  const int32_t* __restrict__ chunk_cluster, const int32_t* __restrict__ chunk_index,
+                  const int32_t* __restrict__ chunk_cluster, const int32_t* __restrict__ chunk_index, int ch_len,
                   double* __restrict__ partial /* [nchunks][D] */) {
     int ch = blockIdx.x;
     int cl = chunk_cluster[ch];
-    int begin = off[cl] + chunk_index[ch] * SUM_CH;
-    int end = min(off[cl + 1], begin + SUM_CH);
+    int begin = off[cl] + chunk_index[ch] * ch_len;
+    int end = min(off[cl + 1], begin + ch_len);
     int j = threadIdx.x;
     if (j >= D) return;
     double acc = 0.0;
     int r = begin;
-    for (; r + 4 <= end; r += 4) {
-        double v0 = (double)x[(size_t)perm[r] * ld + j];
-        double v1 = (double)x[(size_t)perm[r + 1] * ld + j];
-        double v2 = (double)x[(size_t)perm[r + 2] * ld + j];
-        double v3 = (double)x[(size_t)perm[r + 3] * ld + j];
-        acc = __dadd_rn(acc, v0); acc = __dadd_rn(acc, v1); acc = __dadd_rn(acc, v2); acc = __dadd_rn(acc, v3);
+    for (; r + 16 <= end; r += 16) {  // sixteen independent row reads in flight, added in row order
+        T v[16];
+#pragma unroll
+        for (int u = 0; u < 16; u++) v[u] = x[(size_t)perm[r + u] * ld + j];
+#pragma unroll
+        for (int u = 0; u < 16; u++) acc = __dadd_rn(acc, (double)v[u]);
     }
     for (; r < end; r++) acc = __dadd_rn(acc, (double)x[(size_t)perm[r] * ld + j]);
     partial[(size_t)ch * D + j] = acc;
 }
 
 __global__ void combine_sums_kernel(const double* __restrict__ partial, const int32_t* __restrict__ chunk_first, int K, int D,
-                                    const int32_t* __restrict__ off, double* __restrict__ sums, long long* __restrict__ counts) {
+                                    const int32_t* __restrict__ off, int ch_len, double* __restrict__ sums,
+                                    long long* __restrict__ counts) {
     int cl = blockIdx.x, j = threadIdx.x;
     int n = off[cl + 1] - off[cl];
     if (j == 0) counts[cl] = n;
     if (j >= D) return;
-    int nch = (n + SUM_CH - 1) / SUM_CH;
+    int nch = (n + ch_len - 1) / ch_len;
     double acc = 0.0;
     for (int ch = 0; ch < nch; ch++) {
         double v = partial[(size_t)(chunk_first[cl] + ch) * D + j];
@@ -1460,10 +1462,15 @@ int crx_cluster_sums(crx_ctx* c, const crx_points* p, const int32_t* labels, int
     std::vector<int32_t> off(K + 1);
     CRX_CUDA(cudaMemcpyAsync(off.data(), seg.off, (K + 1) * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
     CRX_CUDA(cudaStreamSynchronize(c->stream));
+    // chunk length: whole clusters are summed sequentially (= the reference's own sum, bit for bit) as long as that
+    // leaves at least two chunks per SM; only a few very large clusters are cut into pieces
+    int ch_len = SUM_CH;
+    auto chunks_at = [&](int len) { long long t = 0; for (int cl = 0; cl < K; cl++) t += (off[cl + 1] - off[cl] + len - 1) / len; return t; };
+    while (ch_len < SUM_CH_MAX && chunks_at(ch_len * 2) >= 2ll * c->sm_count) ch_len *= 2;
     std::vector<int32_t> ch_cluster, ch_index, ch_first(K + 1, 0);
     for (int cl = 0; cl < K; cl++) {
         int n = off[cl + 1] - off[cl];
-        int nch = (n + SUM_CH - 1) / SUM_CH;
+        int nch = (n + ch_len - 1) / ch_len;
         ch_first[cl] = (int32_t)ch_cluster.size();
         for (int i = 0; i < nch; i++) { ch_cluster.push_back(cl); ch_index.push_back(i); }
     }
@@ -1480,10 +1487,10 @@ int crx_cluster_sums(crx_ctx* c, const crx_points* p, const int32_t* labels, int
     CRX_CUDA(cudaMemcpyAsync(d_cf.p, ch_first.data(), (K + 1) * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
     if (nchunks) {
         CRX_KERNEL(c, "chunk_sums");
-        if (p->x64) chunk_sums_kernel<double><<<nchunks, 128, 0, c->stream>>>(p->x64, p->ld, D, seg.perm, seg.off, d_cc.p, d_ci.p, partial.p);
-        else chunk_sums_kernel<float><<<nchunks, 128, 0, c->stream>>>(p->x32, p->ld, D, seg.perm, seg.off, d_cc.p, d_ci.p, partial.p);
+        if (p->x64) chunk_sums_kernel<double><<<nchunks, 128, 0, c->stream>>>(p->x64, p->ld, D, seg.perm, seg.off, d_cc.p, d_ci.p, ch_len, partial.p);
+        else chunk_sums_kernel<float><<<nchunks, 128, 0, c->stream>>>(p->x32, p->ld, D, seg.perm, seg.off, d_cc.p, d_ci.p, ch_len, partial.p);
     }
-    { CRX_KERNEL(c, "combine_sums"); combine_sums_kernel<<<K, 128, 0, c->stream>>>(partial.p, d_cf.p, K, D, seg.off, out.dev, cnt.dev); }
+    { CRX_KERNEL(c, "combine_sums"); combine_sums_kernel<<<K, 128, 0, c->stream>>>(partial.p, d_cf.p, K, D, seg.off, ch_len, out.dev, cnt.dev); }
     CRX_CUDA(cudaGetLastError());
     st = out.flush();
     if (st == CRX_OK) st = cnt.flush();

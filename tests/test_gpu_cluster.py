@@ -268,6 +268,20 @@ def test_kmeanspp_filter_with_duplicates_and_zero_rows(ctx, port, metric):
         assert np.array_equal(got, want)
 
 
+def test_kmeans_sums_are_sequential_when_clusters_are_many(ctx, port):
+    # 300 clusters of ~2000 members (> the 1024-row base chunk): with at least two chunks per SM left, every cluster is
+    # summed as ONE sequential chain in input order, so the new centres equal the reference's bit for bit
+    rng = np.random.default_rng(5)
+    n, d, K = 600_000, 16, 300
+    X = rng.normal(size=(n, d)).astype(np.float32)
+    lab = rng.integers(0, K, n).astype(np.int32)
+    C = rng.normal(size=(K, d))
+    P = ctx.points(X)
+    cont, newc = capi.k_means(ctx, P, lab, C, EUCLIDEAN, 0.05)
+    pcont, pC = port.k_means(X.astype(np.float64), lab, C, EUCLIDEAN, 0.05)
+    assert cont == pcont and np.array_equal(newc, pC)
+
+
 def test_full_clustering_loop_matches_oracle(ctx, port):
     # the loop of main.cpp:96-103 / 246-254: init -> (assign, update) x iters
     X = synth.gaussian_mixture(8000, 100, 12, seed=81, dtype=np.float32)
