@@ -147,6 +147,27 @@ def cpu_reference_rate(U, unk, mean, threads, seconds, steps=1, warmup=0):
                       % (sample, steps, n, build_s)}, sample
 
 
+def cpu_lloyd_rate(dd, kk, seconds):
+    """pts*centroids/s of the reference's own lloyds_assignment (assignment.hpp:55-80) on one host core: a bounded
+    sample of points of the same mixture against all K centroids."""
+    from oracle import load, EUCLIDEAN
+    o = load("reference") or load("port")
+    rng = np.random.default_rng(SEED)
+    C = rng.normal(size=(kk, dd)) * 4.0
+    probe = 200
+    X = C[rng.integers(0, kk, probe)] + rng.normal(size=(probe, dd))
+    t0 = time.perf_counter()
+    o.lloyds_assignment(X, C, None, EUCLIDEAN)
+    per_pt = max(1e-6, (time.perf_counter() - t0) / probe)
+    n = int(min(200_000, max(probe, seconds / per_pt)))
+    X = C[rng.integers(0, kk, n)] + rng.normal(size=(n, dd))
+    t0 = time.perf_counter()
+    o.lloyds_assignment(X, C, None, EUCLIDEAN)
+    dt = time.perf_counter() - t0
+    return {"value": n * kk / dt, "unit": "pts*centroids/s", "cores": 1, "kind": o.kind,
+            "sample": "%d points x %d centroids x %d dims, lloyds_assignment on one core" % (n, kk, dd)}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", 0))
     if rank != 0:
@@ -365,6 +386,8 @@ def run_crx(args):
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu, _ = cpu_reference_rate(U, unk, mean, 1, args.cpu_seconds)
+        if lloyd is not None:
+            lloyd["cpu_baseline"] = cpu_lloyd_rate(args.lloyd_d, args.lloyd_k, min(8.0, args.cpu_seconds))
 
     if rank == 0:
         line = {"metric": "recs/sec (cosine LSH top-P recommendation)", "value": value, "unit": "recs/s", "n_gpus": world,
