@@ -175,10 +175,49 @@ __global__ void compact_unassigned_kernel(const int32_t* __restrict__ labels, in
     if (i < n && labels[i] == -1) rows[atomicAdd(count, 1)] = (int32_t)i;
 }
 
+// D > 128 (e.g. the 203-dimensional tweet vectors clustered in front of the recommendation, main.cpp:78-110): the tile
+// engine keeps whole rows of both tiles in shared memory and does not fit.  Plain exact form instead: a warp owns 32
+// rows (one per lane), the centroids pass by one at a time through shared memory, every lane walks its row in index
+// order (rowwalk.cuh) and keeps the running `min == -1 || d < min` of assignment.hpp:62-71.
+constexpr int CRX_MAXD = 512;   // crx_points_create accepts d <= CRX_MAXD; everything but the clustering core stays at d <= 128
+template <typename T, int METRIC>
+__global__ void __launch_bounds__(128)
+lloyd_scan_wide_kernel(const T* __restrict__ x, int ld, int D, const double* __restrict__ sqn, const int32_t* __restrict__ rowmap,
+                       int64_t nrows, const double* __restrict__ cent, const double* __restrict__ csqn, int K,
+                       int32_t* __restrict__ labels, double* __restrict__ dists) {
+    __shared__ rw::WarpTile tiles[4];
+    __shared__ double vec[CRX_MAXD];
+    int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    int64_t pos = ((int64_t)blockIdx.x * 4 + warp) * 32 + lane;
+    bool valid = pos < nrows;
+    int64_t row = valid ? (rowmap ? (int64_t)rowmap[pos] : pos) : -1;
+    double nrow = valid ? sqn[row] : 1.0;
+    double best = 0.0;
+    int arg = 0;
+    for (int cc = 0; cc < K; cc++) {
+        __syncthreads();
+        for (int k = threadIdx.x; k < ld; k += blockDim.x) vec[k] = cent[(size_t)cc * ld + k];
+        __syncthreads();
+        double d = rw::dist_rows<T, METRIC>(x, ld, D, row, vec, nrow, csqn[cc], tiles[warp]);
+        if (cc == 0 || d < best) { best = d; arg = cc; }   // a NaN at centroid 0 stays (the reference's -1 sentinel)
+    }
+    if (valid) { labels[row] = arg; dists[row] = best; }
+}
+
 static int lloyd_scan(crx_ctx* c, const crx_points* p, const int32_t* d_rowmap, int64_t nrows, const Centroids& cen,
                       int metric, int32_t* d_labels, double* d_dists) {
     if (nrows == 0) return CRX_OK;
     int ld = p->ld;
+    if (p->d > 128) {
+        CRX_KERNEL(c, "lloyd_scan_wide");
+        int g = (int)((nrows + 127) / 128);
+#define LAUNCH_W(T, M, xptr) lloyd_scan_wide_kernel<T, M><<<g, 128, 0, c->stream>>>(xptr, ld, p->d, p->sqn, d_rowmap, nrows, cen.pad.p, cen.sqn.p, cen.K, d_labels, d_dists)
+        if (p->x64) { if (metric == CRX_EUCLIDEAN) LAUNCH_W(double, CRX_EUCLIDEAN, p->x64); else LAUNCH_W(double, CRX_COSINE, p->x64); }
+        else { if (metric == CRX_EUCLIDEAN) LAUNCH_W(float, CRX_EUCLIDEAN, p->x32); else LAUNCH_W(float, CRX_COSINE, p->x32); }
+#undef LAUNCH_W
+        CRX_CUDA(cudaGetLastError());
+        return CRX_OK;
+    }
     size_t smem = pt::smem_bytes(ld) + pt::BN * sizeof(double);
     int grid = (int)((nrows + pt::BM - 1) / pt::BM);
     CRX_KERNEL(c, "lloyd_scan");
@@ -421,13 +460,14 @@ static int lloyd_scan_tc(crx_ctx* c, const crx_points* p, const Centroids& cen, 
 // cluster sums (the data-parallel half of k_means, update.hpp:50-58): rows are grouped by label
 // with the stable segment sort, every (cluster, chunk of CH rows) is summed by one CTA whose thread
 // j owns coordinate j and walks the rows IN INPUT ORDER; chunk partials are then added in order.
-// A cluster of <= CH members therefore gets the reference's own sequential sum, bit for bit.
+// A cluster that fits one chunk therefore gets the reference's own sequential sum, bit for bit: always up to 16384
+// members, and at any size as long as cutting less still leaves two chunks per SM.
 // ------------------------------------------------------------------------------------------------
-constexpr int SUM_CH = 1024;        // smallest chunk
+constexpr int SUM_CH = 16384;       // smallest chunk: a cluster up to this size is ALWAYS one sequential sum (bit-exact)
 constexpr int SUM_CH_MAX = 1 << 20; // largest: a cluster up to this size can still be one sequential sum
 
 template <typename T>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(CRX_MAXD)
 chunk_sums_kernel(const T* __restrict__ x, int ld, int D, const int32_t* __restrict__ perm, const int32_t* __restrict__ off,
                   const int32_t* __restrict__ chunk_cluster, const int32_t* __restrict__ chunk_index, int ch_len,
                   double* __restrict__ partial /* [nchunks][D] */) {
@@ -509,7 +549,7 @@ kpp_update_kernel(const T* __restrict__ x, int ld, int D, const double* __restri
                   double* __restrict__ mind, unsigned long long* __restrict__ maxbits,
                   const int32_t* __restrict__ rowmap /* nullable: only these rows */, const int* __restrict__ nrows_dev) {
     __shared__ rw::WarpTile tiles[8];
-    __shared__ double vec[128];
+    __shared__ double vec[CRX_MAXD];
     int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     for (int k = threadIdx.x; k < ld; k += blockDim.x) vec[k] = cvec[k];
     __syncthreads();
@@ -1225,7 +1265,7 @@ int crx_k_means_pp_sharded(crx_ctx* c, const crx_points* p, int64_t row_offset, 
         if (out_vectors) memcpy(out_vectors + (size_t)(i - 1) * D, hvec.data(), D * sizeof(double));
         if (i == K) break;
         CRX_CUDA(cudaMemsetAsync(mx.p, 0, sizeof(unsigned long long), c->stream));
-        const bool filter = i > 1 && p->x32 != nullptr && N >= 4096;
+        const bool filter = i > 1 && p->x32 != nullptr && N >= 4096 && ld <= 128;   // one 16-byte piece per lane covers the row
         if (N > 0 && filter) {
             CRX_CUDA(cudaMemsetAsync(nflag.p, 0, sizeof(int), c->stream));
             {
@@ -1323,7 +1363,7 @@ int crx_lloyds_assignment(crx_ctx* c, const crx_points* p, const double* centroi
     IoBuf<double> dis;
     CRX_TRY(lab.bind(c, labels, p->n, mem, false));
     CRX_TRY(dis.bind(c, dists, p->n, mem, false));   // dists == NULL: labels only
-    if (metric == CRX_EUCLIDEAN && K >= 32 && p->n >= 1024 && !tc_disabled()) CRX_TRY(lloyd_scan_tc(c, p, cen, lab.dev, dis.dev));
+    if (metric == CRX_EUCLIDEAN && K >= 32 && p->n >= 1024 && p->d <= 128 && !tc_disabled()) CRX_TRY(lloyd_scan_tc(c, p, cen, lab.dev, dis.dev));
     else {
         DevBuf<double> scratch;
         if (!dis.dev) CRX_TRY(scratch.alloc(c, p->n));
@@ -1476,6 +1516,7 @@ int crx_cluster_sums(crx_ctx* c, const crx_points* p, const int32_t* labels, int
     }
     ch_first[K] = (int32_t)ch_cluster.size();
     int nchunks = (int)ch_cluster.size();
+    const int sums_block = std::max(128, ((D + 31) / 32) * 32);   // thread j owns coordinate j
     DevBuf<int32_t> d_cc, d_ci, d_cf;
     DevBuf<double> partial;
     CRX_TRY(d_cc.alloc(c, nchunks)); CRX_TRY(d_ci.alloc(c, nchunks)); CRX_TRY(d_cf.alloc(c, K + 1));
@@ -1487,10 +1528,10 @@ int crx_cluster_sums(crx_ctx* c, const crx_points* p, const int32_t* labels, int
     CRX_CUDA(cudaMemcpyAsync(d_cf.p, ch_first.data(), (K + 1) * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
     if (nchunks) {
         CRX_KERNEL(c, "chunk_sums");
-        if (p->x64) chunk_sums_kernel<double><<<nchunks, 128, 0, c->stream>>>(p->x64, p->ld, D, seg.perm, seg.off, d_cc.p, d_ci.p, ch_len, partial.p);
-        else chunk_sums_kernel<float><<<nchunks, 128, 0, c->stream>>>(p->x32, p->ld, D, seg.perm, seg.off, d_cc.p, d_ci.p, ch_len, partial.p);
+        if (p->x64) chunk_sums_kernel<double><<<nchunks, sums_block, 0, c->stream>>>(p->x64, p->ld, D, seg.perm, seg.off, d_cc.p, d_ci.p, ch_len, partial.p);
+        else chunk_sums_kernel<float><<<nchunks, sums_block, 0, c->stream>>>(p->x32, p->ld, D, seg.perm, seg.off, d_cc.p, d_ci.p, ch_len, partial.p);
     }
-    { CRX_KERNEL(c, "combine_sums"); combine_sums_kernel<<<K, 128, 0, c->stream>>>(partial.p, d_cf.p, K, D, seg.off, ch_len, out.dev, cnt.dev); }
+    { CRX_KERNEL(c, "combine_sums"); combine_sums_kernel<<<K, sums_block, 0, c->stream>>>(partial.p, d_cf.p, K, D, seg.off, ch_len, out.dev, cnt.dev); }
     CRX_CUDA(cudaGetLastError());
     st = out.flush();
     if (st == CRX_OK) st = cnt.flush();
@@ -1536,6 +1577,7 @@ int crx_pam_lloyds_sharded(crx_ctx* c, const crx_points* p, const int32_t* label
                            const crx_comm* comm, int32_t* new_crow, int* swapped) {
     CRX_REQUIRE(c && p && labels && crow && new_crow && swapped, "NULL argument");
     CRX_REQUIRE(metric == CRX_EUCLIDEAN || metric == CRX_COSINE, "metric");
+    CRX_NARROW(p);
     CRX_CUDA(cudaSetDevice(c->device));
     const int world = comm_world(comm), me = comm_rank(comm);
     int64_t N = p->n;
@@ -1628,6 +1670,7 @@ int crx_pam_lloyds(crx_ctx* c, const crx_points* p, const int32_t* labels, int l
 int crx_silhouette_cluster_sharded(crx_ctx* c, const crx_points* p, const int32_t* labels, int lmem, const double* centroids,
                                    int cmem, int K, int metric, const crx_comm* comm, double* sils) {
     CRX_REQUIRE(c && p && labels && centroids && sils, "NULL argument");
+    CRX_NARROW(p);
     CRX_CUDA(cudaSetDevice(c->device));
     const int world = comm_world(comm), me = comm_rank(comm);
     int64_t N = p->n;

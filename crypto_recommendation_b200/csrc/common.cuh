@@ -39,6 +39,10 @@ void crx_set_error(const char* fmt, ...);
             return CRX_ERR_INVALID;                                            \
         }                                                                      \
     } while (0)
+// rows wider than 128 coordinates are accepted by the clustering core only (k_means_pp, lloyds_assignment,
+// lloyds_for_remaining, k_means, pair_op); every other entry point says so instead of misbehaving
+#define CRX_NARROW(p) CRX_REQUIRE((p)->d <= 128, "this entry point supports d <= 128 (wider rows: k_means_pp, lloyds_assignment, k_means, pair_op)")
+
 
 // ------------------------------------------------------------------------------------------------
 // handles

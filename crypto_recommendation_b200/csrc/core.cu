@@ -187,7 +187,7 @@ int crx_ctx_counters(crx_ctx* c, int64_t out[8], int reset) {
 int crx_points_create(crx_ctx* c, const void* data, int dtype, int64_t n, int32_t d, int mem, crx_points** out) {
     CRX_REQUIRE(c && data && out, "NULL argument");
     CRX_REQUIRE(n > 0 && n < (1ll << 31), "n must be in [1, 2^31)");
-    CRX_REQUIRE(d > 0 && d <= 128, "d must be in [1, 128]");
+    CRX_REQUIRE(d > 0 && d <= 512, "d must be in [1, 512]");
     CRX_REQUIRE(dtype == CRX_F32 || dtype == CRX_F64, "dtype");
     CRX_CUDA(cudaSetDevice(c->device));
     crx_points* p = new crx_points();

@@ -429,6 +429,8 @@ int crx_lsh_destroy(crx_lsh* t) {
 
 int crx_create_LSH_hashtables(crx_ctx* c, const crx_points* pts, int metric, int k, int L, int lsh_bucket_div,
                               double euclidean_h_w, uint64_t seed, crx_lsh** out) {
+    CRX_REQUIRE(pts, "NULL argument");
+    CRX_NARROW(pts);
     CRX_REQUIRE(c && pts && out, "NULL argument");
     CRX_REQUIRE(metric == CRX_EUCLIDEAN || metric == CRX_COSINE, "metric");
     CRX_REQUIRE(k >= 1 && k <= 16 && L >= 1 && L <= 16, "k in [1,16], L in [1,16]");
@@ -580,6 +582,8 @@ int crx_cube_destroy(crx_cube* cu) {
 
 int crx_create_hypercube(crx_ctx* c, const crx_points* pts, int metric, int k, double euclidean_h_w, uint64_t seed,
                          crx_cube** out) {
+    CRX_REQUIRE(pts, "NULL argument");
+    CRX_NARROW(pts);
     CRX_REQUIRE(c && pts && out, "NULL argument");
     CRX_REQUIRE(metric == CRX_EUCLIDEAN || metric == CRX_COSINE, "metric");
     CRX_REQUIRE(k >= 1 && k <= 16, "cube dimension k must be in [1,16]");

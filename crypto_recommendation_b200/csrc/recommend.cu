@@ -606,6 +606,7 @@ int crx_recommend_lsh(crx_ctx* c, const crx_lsh* t, const crx_points* queries, i
     CRX_REQUIRE(Nrec >= 0 && Nrec <= 128, "Nrec");
     if (recs) CRX_REQUIRE(base->mean && queries->unknown && queries->mean, "ratings metadata missing (crx_points_set_ratings)");
     CRX_REQUIRE(self || t->metric == CRX_COSINE, "external queries are supported for cosine tables only in this round");
+    CRX_NARROW(queries);
     CRX_CUDA(cudaSetDevice(c->device));
     int64_t nq = q_end - q_begin;
     if (nq == 0) return CRX_OK;

@@ -214,19 +214,22 @@ def test_pam_tensor_path_duplicates_first_wins(ctx, port):
 
 
 def test_cluster_sums_chunking(ctx, port):
-    # one cluster far larger than the summation chunk: deterministic, and equal to the sequential sum to ~1e-15
-    X = synth.gaussian_mixture(9000, 100, 3, seed=71, dtype=np.float32)
-    lab = (np.arange(9000) % 10 == 0).astype(np.int32)  # cluster 0: 8100 rows, cluster 1: 900 rows
+    # one cluster larger than the 16384-row chunk with too few clusters to fill the GPU otherwise: it is cut into chunks
+    # (deterministic, equal to the sequential sum to ~1e-15); clusters of up to 16384 rows are one sequential sum
+    n = 40_000
+    X = synth.gaussian_mixture(n, 24, 3, seed=71, dtype=np.float32)
+    lab = (np.arange(n) % 10 == 0).astype(np.int32)  # cluster 0: 36000 rows, cluster 1: 4000 rows
     P = ctx.points(X)
     s1, c1 = capi.cluster_sums(ctx, P, lab, 3)
     s2, c2 = capi.cluster_sums(ctx, P, lab, 3)
-    assert np.array_equal(s1, s2) and c1.tolist() == [8100, 900, 0]
+    assert np.array_equal(s1, s2) and c1.tolist() == [36000, 4000, 0]
     X64 = X.astype(np.float64)
-    seq = np.zeros((3, 100))
-    for v in range(9000):
+    seq = np.zeros((3, 24))
+    for v in range(n):
         seq[lab[v]] += X64[v]
-    assert np.array_equal(s1[1], seq[1])          # <= 1024 members: the reference's own sequential sum
+    assert np.array_equal(s1[1], seq[1])          # fits one chunk: the reference's own sequential sum
     assert_float_close(s1[0], seq[0], 1e-13)
+    assert not s1[2].any()
 
 
 @pytest.mark.parametrize("K,metric", [(64, EUCLIDEAN), (7, EUCLIDEAN), (40, COSINE)])
@@ -280,6 +283,47 @@ def test_kmeans_sums_are_sequential_when_clusters_are_many(ctx, port):
     cont, newc = capi.k_means(ctx, P, lab, C, EUCLIDEAN, 0.05)
     pcont, pC = port.k_means(X.astype(np.float64), lab, C, EUCLIDEAN, 0.05)
     assert cont == pcont and np.array_equal(newc, pC)
+
+
+@pytest.mark.parametrize("metric", METRICS)
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_wide_rows_clustering_loop(ctx, port, metric, dtype):
+    # D = 203 (> 128): the tweet vectors main.cpp clusters in front of the recommendation (main.cpp:78-110).  The
+    # clustering core takes rows up to 512 wide: k-means++, Lloyd assignment (+ for remaining), k-means, pair_op --
+    # all bit-exact against the oracle; the other entry points refuse such rows with a clear error.
+    n, d, K = 1500, 203, 11
+    rng = np.random.default_rng(203)
+    X = (rng.gamma(2.0, 1.0, size=(n, d)) * (rng.random((n, d)) < 0.3)).astype(dtype) + dtype(0.01)
+    X64 = X.astype(np.float64)
+    P = ctx.points(X)
+    ctx.counters(reset=True)
+    cidx = capi.k_means_pp(ctx, P, K, metric, 77)
+    want = port.k_means_pp(X64, K, metric, 77)
+    if ctx.counters()["kpp_near"] == 0:
+        assert np.array_equal(cidx, want)
+    cidx = want
+    C = X64[cidx]; rows = cidx
+    for it in range(3):
+        lab, dist = capi.lloyds_assignment(ctx, P, C, rows, metric)
+        rl, rd = port.lloyds_assignment(X64, C, rows, metric)
+        assert np.array_equal(lab, rl) and np.array_equal(dist, rd)
+        cont, C2 = capi.k_means(ctx, P, lab, C, metric, 0.05)
+        pcont, pC = port.k_means(X64, rl, C, metric, 0.05)
+        assert cont == pcont and np.array_equal(C2, pC)
+        C = pC; rows = None
+    lab[::7] = -1
+    rl2 = lab.copy(); rd2 = dist.copy()
+    l3, d3 = capi.lloyds_for_remaining(ctx, P, C, metric, lab.copy(), dist.copy())
+    full_l, full_d = port.lloyds_assignment(X64, C, None, metric)
+    assert np.array_equal(l3[::7], full_l[::7]) and np.array_equal(d3[::7], full_d[::7])
+    idx = np.arange(0, 40)
+    for op, f in ((0, port.inner_product), (1, port.euclidean_distance), (2, port.cosine_distance), (3, port.cosine_similarity)):
+        got = capi.pair_op(ctx, P, idx, P, idx[::-1].copy(), op)
+        assert np.array_equal(got, np.array([f(X64[i], X64[j]) for i, j in zip(idx, idx[::-1])]))
+    for bad in (lambda: capi.LshTables(ctx, P, "cosine", 4, 5, 100, 0.4, 1), lambda: capi.Hypercube(ctx, P, "cosine", 4, 1.0, 1),
+                lambda: capi.pam_lloyds(ctx, P, lab.clip(0), cidx, metric), lambda: capi.silhouette_cluster(ctx, P, lab.clip(0), C, metric)):
+        with pytest.raises(capi.CrxError):
+            bad()
 
 
 def test_full_clustering_loop_matches_oracle(ctx, port):

@@ -124,4 +124,4 @@ def test_errors(ctx):
     with pytest.raises(capi.CrxError):
         capi.LshTables(ctx, P, "cosine", 40, 5, 100, 0.4, 1)
     with pytest.raises(capi.CrxError):
-        ctx.points(np.zeros((4, 200)))
+        ctx.points(np.zeros((4, 600)))   # rows wider than 512

@@ -59,17 +59,17 @@ def main():
     with open(os.path.join(a.out, "tweets.tsv"), "w") as f:
         f.write("\n".join(lines) + "\n")
     # project-2 tweet vectors: id, then non-negative "tf-idf"-like coordinates around proj2 cluster centres
-    d2 = 24
-    # sparse centres (5 active coordinates each): cosine distances between a tweet and its cluster mean stay well
+    d2 = 203   # wider than 128: the tweet vectors of the original data set are of this kind
+    # sparse centres (12 active coordinates each): cosine distances between a tweet and its cluster mean stay well
     # above min_dist_kmeans, so the first k_means call replaces the centres (main.cpp:109-110 frees them afterwards)
     centres = np.zeros((a.proj2_clusters, d2))
     for c in range(a.proj2_clusters):
-        centres[c, rng.choice(d2, 5, replace=False)] = rng.gamma(4.0, 1.0, size=5)
+        centres[c, rng.choice(d2, 12, replace=False)] = rng.gamma(4.0, 1.0, size=12)
     with open(os.path.join(a.out, "proj2_input.csv"), "w") as f:
         for t in tweet_ids:
             if t % 23 == 5:
                 continue  # a tweet without a vector
-            v = centres[int(rng.integers(0, a.proj2_clusters))] * rng.uniform(0.6, 1.4, size=d2) + rng.gamma(1.0, 0.5, size=d2) * (rng.random(d2) < 0.4)
+            v = centres[int(rng.integers(0, a.proj2_clusters))] * rng.uniform(0.6, 1.4, size=d2) + rng.gamma(1.0, 0.5, size=d2) * (rng.random(d2) < 0.08)
             f.write("%d,%s\n" % (t, ",".join("%.6f" % x for x in v)))
     with open(os.path.join(a.out, "cluster.conf"), "w") as f:
         f.write("proj_2_input ./proj2_input.csv\nproj_2_csv_delimiter ,\nproj_2_number_of_clusters %d\n" % a.proj2_clusters)
