@@ -516,8 +516,7 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 template <typename T>
 __global__ void tc_prep_rows_kernel(const T* __restrict__ x, int ld, int D, const double* __restrict__ sqn, int64_t n,
                                     int mode, double scale, int nkb, const int32_t* __restrict__ rowmap, __half* __restrict__ out,
-                                    float* __restrict__ norm_s, float* __restrict__ errw_s, float* __restrict__ resid,
-                                    unsigned int* __restrict__ resid_max) {
+                                    float* __restrict__ norm_s, float* __restrict__ errw_s) {
     int64_t orow = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     int lane = threadIdx.x & 31;
     if (orow >= n) return;
@@ -536,24 +535,12 @@ __global__ void tc_prep_rows_kernel(const T* __restrict__ x, int ld, int D, cons
     }
     int W = nkb * 64;
     __half* o = out + orow * (size_t)(2 * W);
-    double r2 = 0.0;
     for (int c = lane; c < W; c += 32) {
         double v = c < D ? (double)x[row * ld + c] * s : 0.0;
         __half hi = __double2half(v);
-        double rest = v - (double)__half2float(hi);
-        __half lo = __double2half(rest);
+        __half lo = __double2half(v - (double)__half2float(hi));
         o[c] = hi;
         o[W + c] = lo;
-        r2 += rest * rest;
-    }
-    if (resid) {  // |row - hi part| relative to the scaled unit length: what a single-product (hi.hi) score can be off by
-#pragma unroll
-        for (int off = 16; off > 0; off >>= 1) r2 += __shfl_xor_sync(0xffffffffu, r2, off);
-        if (lane == 0) {
-            float rr = (float)(sqrt(r2) / scale * 1.000001);
-            resid[orow] = rr;
-            if (resid_max) atomicMax(resid_max, __float_as_uint(rr));
-        }
     }
 }
 
@@ -614,16 +601,15 @@ int alloc_operand(crx_ctx* c, int64_t rows, int D, TcOperand* out) {
 
 }  // namespace
 
-int crx_tc_prepare(crx_ctx* c, const crx_points* p, int mode, double scale_log2, TcOperand* out, const int32_t* rowmap, float* norm_s, float* errw_s,
-                   float* resid, unsigned int* resid_max) {
+int crx_tc_prepare(crx_ctx* c, const crx_points* p, int mode, double scale_log2, TcOperand* out, const int32_t* rowmap, float* norm_s, float* errw_s) {
     CRX_REQUIRE(p->d <= 128, "tensor path supports D <= 128");
     CRX_TRY(alloc_operand(c, p->n, p->d, out));
     out->scale_log2 = scale_log2;
     double scale = ldexp(1.0, (int)scale_log2);
     int g = (int)((p->n + 7) / 8);
     CRX_KERNEL(c, "tc_prep");
-    if (p->x64) tc_prep_rows_kernel<double><<<g, 256, 0, c->stream>>>(p->x64, p->ld, p->d, p->sqn, p->n, mode, scale, out->nkb, rowmap, (__half*)out->data, norm_s, errw_s, resid, resid_max);
-    else tc_prep_rows_kernel<float><<<g, 256, 0, c->stream>>>(p->x32, p->ld, p->d, p->sqn, p->n, mode, scale, out->nkb, rowmap, (__half*)out->data, norm_s, errw_s, resid, resid_max);
+    if (p->x64) tc_prep_rows_kernel<double><<<g, 256, 0, c->stream>>>(p->x64, p->ld, p->d, p->sqn, p->n, mode, scale, out->nkb, rowmap, (__half*)out->data, norm_s, errw_s);
+    else tc_prep_rows_kernel<float><<<g, 256, 0, c->stream>>>(p->x32, p->ld, p->d, p->sqn, p->n, mode, scale, out->nkb, rowmap, (__half*)out->data, norm_s, errw_s);
     CRX_CUDA(cudaGetLastError());
     return CRX_OK;
 }
@@ -634,7 +620,7 @@ int crx_tc_prepare_matrix(crx_ctx* c, const double* m, int K, int D, int ld, dou
     out->scale_log2 = scale_log2;
     int g = (K + 7) / 8;
     CRX_KERNEL(c, "tc_prep");
-    tc_prep_rows_kernel<double><<<g, 256, 0, c->stream>>>(m, ld, D, nullptr, K, 1, ldexp(1.0, (int)scale_log2), out->nkb, nullptr, (__half*)out->data, nullptr, nullptr, nullptr, nullptr);
+    tc_prep_rows_kernel<double><<<g, 256, 0, c->stream>>>(m, ld, D, nullptr, K, 1, ldexp(1.0, (int)scale_log2), out->nkb, nullptr, (__half*)out->data, nullptr, nullptr);
     CRX_CUDA(cudaGetLastError());
     return CRX_OK;
 }

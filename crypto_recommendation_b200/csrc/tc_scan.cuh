@@ -27,10 +27,9 @@ struct TcOperand {
 
 // mode 0: rows scaled to unit length times 2^10 (cosine);  mode 1: all rows times 2^scale_log2
 // rowmap (nullable): operand row i holds point rowmap[i];  norm_s / errw_s (nullable, together): scaled squared norms and
-// the row-sum error weights;  resid (nullable): |row - its hi part| / |row| per operand row (mode 0), resid_max: the
-// maximum of those as float bits (atomicMax; the caller zeroes it)
+// the row-sum error weights
 int crx_tc_prepare(crx_ctx* c, const crx_points* p, int mode, double scale_log2, TcOperand* out, const int32_t* rowmap = nullptr,
-                   float* norm_s = nullptr, float* errw_s = nullptr, float* resid = nullptr, unsigned int* resid_max = nullptr);
+                   float* norm_s = nullptr, float* errw_s = nullptr);
 // same for a [K][ld] double matrix (centroids)
 int crx_tc_prepare_matrix(crx_ctx* c, const double* m, int K, int D, int ld, double scale_log2, TcOperand* out);
 
@@ -40,8 +39,8 @@ constexpr int TC_LIST = 64;  // per-row candidate list of the top-P filter
 // the columns whose packed code shares at least one k-bit field with the query's code.
 //   list_s[nq][TC_LIST] (float, scaled by 2^(sa+sb)), list_i[nq][TC_LIST] (column, -1 = empty)
 // dense: the caller knows that (nearly) every column is a candidate of every row (mean |cand| / N > 0.9)
-// nprod: 3 = split-fp16 products hi.hi + lo.hi + hi.lo (error ~6e-6 |a||b|); 1 = hi.hi only, a coarse filter whose
-//        error is bounded by the operands' residuals (crx_tc_prepare resid): |score - a.b| <= ra + rb + ra rb (unit rows)
+// nprod: 3 = split-fp16 products hi.hi + lo.hi + hi.lo (error ~6e-6 |a||b|); 1 = hi.hi only (error ~2^-10 |a||b|): kept for
+//        the measurement recorded in DESIGN.md section 8 -- TMEM reads, not the MMAs, bound it, so it is not used
 int crx_tc_topp(crx_ctx* c, const TcOperand& A, int64_t q0, int64_t nq, const TcOperand& B, const uint32_t* qcode,
                 const uint32_t* ccode, int k, int L, bool dense, float* list_s, int32_t* list_i, int nprod = 3);
 
