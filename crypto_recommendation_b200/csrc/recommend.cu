@@ -284,26 +284,69 @@ rec_finalize_kernel(const TQ* __restrict__ xq, int ldq, const double* __restrict
     int nvalid = 0;
     rw::stage_vector<TQ>(xq, ldq, qrow, qvec[warp]);
     const double nq_ = sqn_q[qrow];
+    int idx_e[EPL];
+    double val_e[EPL];   // approximate score, -inf for an empty slot
 #pragma unroll
     for (int e = 0; e < EPL; e++) {
         int slot = e * 32 + lane;
-        int idx = list_i[qrel * LISTN + slot];
-        double ap = idx >= 0 ? (double)list_s[qrel * LISTN + slot] : INFINITY;
-        unsigned vm = __ballot_sync(0xffffffffu, idx >= 0);
-        // the reference's own similarity of every listed candidate (crypto_rec.hpp:220, cust_vector.hpp:160-174): each
-        // lane walks ITS candidate in index order with the x87 accumulation, rows staged through shared memory
-        double mysim = -INFINITY;
-        if (vm) {
-            rw::Walk w = rw::walk_rows<TB, CRX_COSINE>(xb, ldb, D, idx >= 0 ? (int64_t)idx : -1, qvec[warp], tiles[warp]);
-            if (idx >= 0) { X87 ip = {w.a, w.b}; mysim = cos_sim_x87(ip, sqn_b[idx], nq_); }
-        }
-        a_idx[warp][slot] = idx;
-        a_sim[warp][slot] = mysim;
-        int gcount = __popc(vm);
+        idx_e[e] = list_i[qrel * LISTN + slot];
+        double ap = idx_e[e] >= 0 ? (double)list_s[qrel * LISTN + slot] : INFINITY;
+        val_e[e] = idx_e[e] >= 0 ? ap : -INFINITY;
+        int gcount = __popc(__ballot_sync(0xffffffffu, idx_e[e] >= 0));
 #pragma unroll
         for (int off = 16; off > 0; off >>= 1) ap = fmin(ap, __shfl_xor_sync(0xffffffffu, ap, off));
         nvalid += gcount;
         if (gcount == 32) floor_s = fmax(floor_s, ap);
+    }
+    // Listed candidates whose approximate score is more than twice the filter error below the P-th best approximate
+    // score cannot be among the exact P best: they are dropped before the exact (expensive) evaluation.  When at most 32
+    // survive, one row walk serves them all.
+    bool one_walk = false;
+    if (EPL == 2 && nvalid > P) {
+        int g0 = 0, g1 = 0;
+        for (int t = 0; t < 32; t++) {
+            double o0 = __shfl_sync(0xffffffffu, val_e[0], t), o1 = __shfl_sync(0xffffffffu, val_e[EPL - 1], t);
+            g0 += (o0 > val_e[0]) + (o1 > val_e[0]);
+            g1 += (o0 > val_e[EPL - 1]) + (o1 > val_e[EPL - 1]);
+        }
+        // P-th largest = the smallest value that has fewer than P strictly larger ones
+        double T = fmin(g0 < P ? val_e[0] : INFINITY, g1 < P ? val_e[EPL - 1] : INFINITY);
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) T = fmin(T, __shfl_xor_sync(0xffffffffu, T, off));
+        double cut = T - 2.02 * approx_eps / approx_scale;   // approx_eps is in similarity units, the list in filter units
+        bool k0 = idx_e[0] >= 0 && val_e[0] >= cut, k1 = idx_e[EPL - 1] >= 0 && val_e[EPL - 1] >= cut;
+        unsigned b0 = __ballot_sync(0xffffffffu, k0), b1 = __ballot_sync(0xffffffffu, k1);
+        int count = __popc(b0) + __popc(b1);
+        if (count <= 32) {
+            one_walk = true;
+            unsigned lt = (1u << lane) - 1u;
+            if (k0) a_idx[warp][__popc(b0 & lt)] = idx_e[0];
+            if (k1) a_idx[warp][__popc(b0) + __popc(b1 & lt)] = idx_e[EPL - 1];
+            __syncwarp();
+            int mine = lane < count ? a_idx[warp][lane] : -1;
+            __syncwarp();
+            rw::Walk w = rw::walk_rows<TB, CRX_COSINE>(xb, ldb, D, mine >= 0 ? (int64_t)mine : -1, qvec[warp], tiles[warp]);
+            double mysim = -INFINITY;
+            if (mine >= 0) { X87 ip = {w.a, w.b}; mysim = cos_sim_x87(ip, sqn_b[mine], nq_); }
+            a_idx[warp][lane] = mine; a_sim[warp][lane] = mysim;
+            a_idx[warp][32 + lane] = -1; a_sim[warp][32 + lane] = -INFINITY;
+        }
+    }
+    if (!one_walk) {
+#pragma unroll
+        for (int e = 0; e < EPL; e++) {
+            int slot = e * 32 + lane;
+            int idx = idx_e[e];
+            // the reference's own similarity of every listed candidate (crypto_rec.hpp:220, cust_vector.hpp:160-174): each
+            // lane walks ITS candidate in index order with the x87 accumulation, rows staged through shared memory
+            double mysim = -INFINITY;
+            if (__ballot_sync(0xffffffffu, idx >= 0)) {
+                rw::Walk w = rw::walk_rows<TB, CRX_COSINE>(xb, ldb, D, idx >= 0 ? (int64_t)idx : -1, qvec[warp], tiles[warp]);
+                if (idx >= 0) { X87 ip = {w.a, w.b}; mysim = cos_sim_x87(ip, sqn_b[idx], nq_); }
+            }
+            a_idx[warp][slot] = idx;
+            a_sim[warp][slot] = mysim;
+        }
     }
     __syncwarp();
     int keep = min(P, nvalid);
