@@ -371,20 +371,30 @@ def lloyds_for_remaining(ctx, pts, centroids, metric_type, labels, dists):
     return labels, dists
 
 
-def lsh_range_assignment(ctx, pts, tables, centroid_rows, metric_type, comm=None):
-    """comm: dist.Comm -- the centroids (and the Lloyd pass over the remainder) are split over its ranks."""
+def _range_outputs(pts, out):
+    """(labels, dists, before): fresh host arrays, or the caller's (all numpy or all CUDA tensors -> results stay on the device)."""
+    if out is not None:
+        return out
+    return np.zeros(pts.n, np.int32), np.zeros(pts.n), np.zeros(pts.n, np.int32)
+
+
+def lsh_range_assignment(ctx, pts, tables, centroid_rows, metric_type, comm=None, out=None):
+    """comm: dist.Comm -- the centroids (and the Lloyd pass over the remainder) are split over its ranks.
+    out: optional preallocated (labels int32, dists float64, labels_before_lloyd int32)."""
     cr = _np(centroid_rows, np.int32)
-    labels = np.zeros(pts.n, np.int32); dists = np.zeros(pts.n); before = np.zeros(pts.n, np.int32)
+    labels, dists, before = _range_outputs(pts, out)
+    pl, mem = _ptr(labels)
     _check(lib().crx_lsh_range_assignment_sharded(ctx.h, pts.h, tables.h, _ptr(cr)[0], len(cr), METRICS[metric_type], _comm_ptr(comm),
-                                                  _ptr(labels)[0], _ptr(dists)[0], HOST, _ptr(before)[0]))
+                                                  pl, _ptr(dists)[0], mem, _ptr(before)[0]))
     return labels, dists, before
 
 
-def cube_range_assignment(ctx, pts, cube, centroid_rows, metric_type, probes, comm=None):
+def cube_range_assignment(ctx, pts, cube, centroid_rows, metric_type, probes, comm=None, out=None):
     cr = _np(centroid_rows, np.int32)
-    labels = np.zeros(pts.n, np.int32); dists = np.zeros(pts.n); before = np.zeros(pts.n, np.int32)
+    labels, dists, before = _range_outputs(pts, out)
+    pl, mem = _ptr(labels)
     _check(lib().crx_cube_range_assignment_sharded(ctx.h, pts.h, cube.h, _ptr(cr)[0], len(cr), METRICS[metric_type], int(probes),
-                                                   _comm_ptr(comm), _ptr(labels)[0], _ptr(dists)[0], HOST, _ptr(before)[0]))
+                                                   _comm_ptr(comm), pl, _ptr(dists)[0], mem, _ptr(before)[0]))
     return labels, dists, before
 
 

@@ -80,7 +80,10 @@ def main():
         out["cube_build_c3_10M_x128_d16"] = r
         K = 1024
         cidx = capi.rand_selection(ctx, P, K, 3)
-        r = timed("cube_range", lambda: capi.cube_range_assignment(ctx, P, cube[0], cidx, "euclidean", 64), ["range_fire", "range_finalize", "min_pair", "lloyd_scan", "compact", "tc_argmin", "lloyd_refine"], reps=1)
+        dev_out = (torch.empty(n, dtype=torch.int32, device=dev), torch.empty(n, dtype=torch.float64, device=dev), torch.empty(n, dtype=torch.int32, device=dev))
+        r = timed("cube_range", lambda: capi.cube_range_assignment(ctx, P, cube[0], cidx, "euclidean", 64, out=dev_out), ["range_fire", "range_finalize", "range_hist", "min_pair", "fill_key", "lloyd_scan", "compact", "tc_argmin", "lloyd_refine",
+                    "gather_rows", "gather_int", "pad_centroids", "merge_remaining", "self_assign", "maxabs", "half_norm", "tc_prep", ""], reps=1)
+        r["kernel_ms_total"] = r["kernel_ms"].pop("")
         out["cube_range_assignment_c3_K1024_probes64"] = r
         # ---- k-means++ rounds on the same 10M x 128 points (K = 9: 8 rounds)
         r = timed("kpp", lambda: capi.k_means_pp(ctx, P, 9, "euclidean", 5), ["kpp_update", "kpp_filter", "kpp_prob", "kpp_pick", "DeviceScan"], reps=1)

@@ -79,7 +79,9 @@ def main():
     del X
     cube = capi.Hypercube(ctx, P, "euclidean", 16, 4.0, 9)
     cidx = capi.rand_selection(ctx, P, 1024, 3)
-    ms = timed(lambda: capi.cube_range_assignment(ctx, P, cube, cidx, "euclidean", 64, comm=comm))
+    dev_out = (torch.empty(n, dtype=torch.int32, device=dev), torch.empty(n, dtype=torch.float64, device=dev), torch.empty(n, dtype=torch.int32, device=dev))
+    ms = timed(lambda: capi.cube_range_assignment(ctx, P, cube, cidx, "euclidean", 64, comm=comm, out=dev_out))
+    del dev_out
     out["cube_range_assignment_c3_%d_K1024_probes64" % n] = {"ms": ms}
     cube.close(); P.close()
     # ---- C5 (strong): points replicated, candidate rows split
@@ -90,7 +92,9 @@ def main():
     cidx = capi.k_means_pp(ctx, P, 256, "euclidean", 6)
     t = capi.LshTables(ctx, P, "euclidean", 4, 5, 100, 0.4, 11)
     lab, _, _ = capi.lsh_range_assignment(ctx, P, t, cidx, "euclidean", comm=comm)
-    ms = timed(lambda: capi.lsh_range_assignment(ctx, P, t, cidx, "euclidean", comm=comm))
+    dev_out = (torch.empty(n, dtype=torch.int32, device=dev), torch.empty(n, dtype=torch.float64, device=dev), torch.empty(n, dtype=torch.int32, device=dev))
+    ms = timed(lambda: capi.lsh_range_assignment(ctx, P, t, cidx, "euclidean", comm=comm, out=dev_out))
+    del dev_out
     out["lsh_range_assignment_c5_%d_K256" % n] = {"ms": ms}
     ms = timed(lambda: capi.pam_lloyds(ctx, P, lab, cidx, "euclidean", comm=comm))
     sizes = np.bincount(lab, minlength=256).astype(np.float64)
