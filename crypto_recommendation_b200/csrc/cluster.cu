@@ -463,18 +463,20 @@ static int lloyd_scan_tc(crx_ctx* c, const crx_points* p, const Centroids& cen, 
 // A cluster that fits one chunk therefore gets the reference's own sequential sum, bit for bit: always up to 16384
 // members, and at any size as long as cutting less still leaves two chunks per SM.
 // ------------------------------------------------------------------------------------------------
-constexpr int SUM_CH = 16384;       // smallest chunk: a cluster up to this size is ALWAYS one sequential sum (bit-exact)
+constexpr int SUM_CH = 16384;       // a cluster up to this size is ALWAYS one sequential sum (bit-exact)
+constexpr int SUM_CH_SHORT = 1024;  // chunk used when some cluster is too long for that
 constexpr int SUM_CH_MAX = 1 << 20; // largest: a cluster up to this size can still be one sequential sum
 
 template <typename T>
 __global__ void __launch_bounds__(CRX_MAXD)
 chunk_sums_kernel(const T* __restrict__ x, int ld, int D, const int32_t* __restrict__ perm, const int32_t* __restrict__ off,
-                  const int32_t* __restrict__ chunk_cluster, const int32_t* __restrict__ chunk_index, int ch_len,
+                  const int32_t* __restrict__ chunk_cluster, const int32_t* __restrict__ chunk_index, int whole_max, int ch_len,
                   double* __restrict__ partial /* [nchunks][D] */) {
     int ch = blockIdx.x;
     int cl = chunk_cluster[ch];
-    int begin = off[cl] + chunk_index[ch] * ch_len;
-    int end = min(off[cl + 1], begin + ch_len);
+    int len = (off[cl + 1] - off[cl]) <= whole_max ? whole_max : ch_len;   // whole cluster in one chain, or short chunks
+    int begin = off[cl] + chunk_index[ch] * len;
+    int end = min(off[cl + 1], begin + len);
     int j = threadIdx.x;
     if (j >= D) return;
     double acc = 0.0;
@@ -491,13 +493,14 @@ chunk_sums_kernel(const T* __restrict__ x, int ld, int D, const int32_t* __restr
 }
 
 __global__ void combine_sums_kernel(const double* __restrict__ partial, const int32_t* __restrict__ chunk_first, int K, int D,
-                                    const int32_t* __restrict__ off, int ch_len, double* __restrict__ sums,
+                                    const int32_t* __restrict__ off, int whole_max, int ch_len, double* __restrict__ sums,
                                     long long* __restrict__ counts) {
     int cl = blockIdx.x, j = threadIdx.x;
     int n = off[cl + 1] - off[cl];
     if (j == 0) counts[cl] = n;
     if (j >= D) return;
-    int nch = (n + ch_len - 1) / ch_len;
+    int len = n <= whole_max ? whole_max : ch_len;
+    int nch = (n + len - 1) / len;
     double acc = 0.0;
     for (int ch = 0; ch < nch; ch++) {
         double v = partial[(size_t)(chunk_first[cl] + ch) * D + j];
@@ -1502,15 +1505,19 @@ int crx_cluster_sums(crx_ctx* c, const crx_points* p, const int32_t* labels, int
     std::vector<int32_t> off(K + 1);
     CRX_CUDA(cudaMemcpyAsync(off.data(), seg.off, (K + 1) * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
     CRX_CUDA(cudaStreamSynchronize(c->stream));
-    // chunk length: whole clusters are summed sequentially (= the reference's own sum, bit for bit) as long as that
-    // leaves at least two chunks per SM; only a few very large clusters are cut into pieces
-    int ch_len = SUM_CH;
-    auto chunks_at = [&](int len) { long long t = 0; for (int cl = 0; cl < K; cl++) t += (off[cl + 1] - off[cl] + len - 1) / len; return t; };
-    while (ch_len < SUM_CH_MAX && chunks_at(ch_len * 2) >= 2ll * c->sm_count) ch_len *= 2;
+    // A cluster of up to `whole_max` members is summed as ONE sequential chain = the reference's own sum, bit for bit:
+    // 16384 always (a chain of that length costs < 0.5 ms), up to 2^20 when there are at least two clusters per SM to
+    // keep the GPU busy.  Longer clusters are cut into 1024-row chunks (deterministic, ~1e-15 relative).
+    int maxc = 0, nonempty = 0;
+    for (int cl = 0; cl < K; cl++) { int n = off[cl + 1] - off[cl]; maxc = std::max(maxc, n); nonempty += n > 0; }
+    int whole_max = SUM_CH;
+    if (nonempty >= 2 * c->sm_count) while (whole_max < maxc && whole_max < SUM_CH_MAX) whole_max *= 2;
+    const int ch_len = SUM_CH_SHORT;
     std::vector<int32_t> ch_cluster, ch_index, ch_first(K + 1, 0);
     for (int cl = 0; cl < K; cl++) {
         int n = off[cl + 1] - off[cl];
-        int nch = (n + ch_len - 1) / ch_len;
+        int len = n <= whole_max ? whole_max : ch_len;
+        int nch = (n + len - 1) / len;
         ch_first[cl] = (int32_t)ch_cluster.size();
         for (int i = 0; i < nch; i++) { ch_cluster.push_back(cl); ch_index.push_back(i); }
     }
@@ -1528,10 +1535,10 @@ int crx_cluster_sums(crx_ctx* c, const crx_points* p, const int32_t* labels, int
     CRX_CUDA(cudaMemcpyAsync(d_cf.p, ch_first.data(), (K + 1) * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
     if (nchunks) {
         CRX_KERNEL(c, "chunk_sums");
-        if (p->x64) chunk_sums_kernel<double><<<nchunks, sums_block, 0, c->stream>>>(p->x64, p->ld, D, seg.perm, seg.off, d_cc.p, d_ci.p, ch_len, partial.p);
-        else chunk_sums_kernel<float><<<nchunks, sums_block, 0, c->stream>>>(p->x32, p->ld, D, seg.perm, seg.off, d_cc.p, d_ci.p, ch_len, partial.p);
+        if (p->x64) chunk_sums_kernel<double><<<nchunks, sums_block, 0, c->stream>>>(p->x64, p->ld, D, seg.perm, seg.off, d_cc.p, d_ci.p, whole_max, ch_len, partial.p);
+        else chunk_sums_kernel<float><<<nchunks, sums_block, 0, c->stream>>>(p->x32, p->ld, D, seg.perm, seg.off, d_cc.p, d_ci.p, whole_max, ch_len, partial.p);
     }
-    { CRX_KERNEL(c, "combine_sums"); combine_sums_kernel<<<K, sums_block, 0, c->stream>>>(partial.p, d_cf.p, K, D, seg.off, ch_len, out.dev, cnt.dev); }
+    { CRX_KERNEL(c, "combine_sums"); combine_sums_kernel<<<K, sums_block, 0, c->stream>>>(partial.p, d_cf.p, K, D, seg.off, whole_max, ch_len, out.dev, cnt.dev); }
     CRX_CUDA(cudaGetLastError());
     st = out.flush();
     if (st == CRX_OK) st = cnt.flush();
