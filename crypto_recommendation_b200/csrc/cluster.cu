@@ -690,7 +690,7 @@ __global__ void kpp_pick_kernel(const double* __restrict__ P, int64_t N, double 
 // firing steps gives the assignment.  The reference stops after the first sweep that assigned
 // nothing; the per-sweep counts reproduce that cut-off afterwards.
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ int annulus_index(double d, double r0) {
+__host__ __device__ __forceinline__ int annulus_index(double d, double r0) {
     if (!(r0 > 0.0) || !(d >= 0.0)) return -1;  // radius stays <= 0 for ever / NaN or negative distance never fires
     if (d < r0) return 0;
     int j = ilogb(d / r0) + 1;
@@ -1104,8 +1104,25 @@ static int range_assign_common(crx_ctx* c, const crx_points* p, const int32_t* h
     double r0 = mn / 2;
     CRX_CUDA(cudaMemsetAsync(hist.p, 0, NH * sizeof(int), c->stream));
     { CRX_KERNEL(c, "fill_key"); fill_int_kernel<<<crx_grid(N, 256), 256, 0, c->stream>>>(key.p, N, INT_MAX); }
-    // this rank probes the buckets of its share of the centroids; the firing steps are combined with a min
-    const int c_lo = (int)((int64_t)K * me / world), c_hi = (int)((int64_t)K * (me + 1) / world);
+    // Centroid c only fires for distances in [r0 2^(c-1+sK), r0 2^(c+sK)): with the radius doubling after every centroid
+    //  the annuli of all but the first few centroids lie beyond the diameter of the data, so their
+    // buckets need not be probed at all -- nothing in them can fire.  dmax bounds every distance from above.
+    int c_limit = K;
+    {
+        double dmax = 2.0 + 1e-9;   // cosine distance
+        if (metric == CRX_EUCLIDEAN) {
+            double mx = 0;
+            CRX_TRY(points_maxabs(c, p, &mx));
+            dmax = 2.0 * sqrt((double)D) * mx * 1.00001;
+        }
+        if (std::isfinite(dmax)) {
+            int a_max = annulus_index(dmax, r0);           // largest step any pair can fire at (-1: the radius never grows)
+            if (a_max < 0) c_limit = (r0 > 0.0) ? K : 0;   // -1 with r0 > 0 means "beyond the step cap": probe everything
+            else if (a_max < K) c_limit = a_max + 1;
+        }
+    }
+    // this rank probes the buckets of its share of those centroids; the firing steps are combined with a min
+    const int c_lo = (int)((int64_t)c_limit * me / world), c_hi = (int)((int64_t)c_limit * (me + 1) / world);
     int maxlen = 0;
     for (size_t i = (size_t)c_lo * nseg; i < (size_t)c_hi * nseg; i++) maxlen = std::max(maxlen, h_end[i] - h_begin[i]);
     const int chunk = 8192;

@@ -84,6 +84,17 @@ def main():
         r = timed("cube_range", lambda: capi.cube_range_assignment(ctx, P, cube[0], cidx, "euclidean", 64, out=dev_out), ["range_fire", "range_finalize", "range_hist", "min_pair", "fill_key", "lloyd_scan", "compact", "tc_argmin", "lloyd_refine",
                     "gather_rows", "gather_int", "pad_centroids", "merge_remaining", "self_assign", "maxabs", "half_norm", "tc_prep", ""], reps=1)
         r["kernel_ms_total"] = r["kernel_ms"].pop("")
+        # how many (centroid, bucket member) pairs the probes evaluate: home vertex + 64 extra vertices per centroid
+        vid = cube[0].vertex_ids()
+        sizes = np.bincount(vid, minlength=1 << 16)
+        pairs = 0
+        for cr in cidx:
+            home = int(vid[cr])
+            seq = [home] + capi.get_num_hamming_dist_from(home, 1, 0, 16) + capi.get_num_hamming_dist_from(home, 2, 0, 16)
+            pairs += int(sizes[seq[:65]].sum())
+        r["probe_pairs"] = pairs
+        r["range_fire_gather_gbs"] = pairs * 512 / (r["kernel_ms"]["range_fire"] * 1e6)
+        r["vertex_sizes"] = {"nonempty": int((sizes > 0).sum()), "max": int(sizes.max()), "mean_nonempty": float(sizes[sizes > 0].mean())}
         out["cube_range_assignment_c3_K1024_probes64"] = r
         # ---- k-means++ rounds on the same 10M x 128 points (K = 9: 8 rounds)
         r = timed("kpp", lambda: capi.k_means_pp(ctx, P, 9, "euclidean", 5), ["kpp_update", "kpp_filter", "kpp_prob", "kpp_pick", "DeviceScan"], reps=1)
