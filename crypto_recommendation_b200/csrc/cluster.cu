@@ -1640,7 +1640,9 @@ int crx_pam_lloyds_sharded(crx_ctx* c, const crx_points* p, const int32_t* label
         if (!mine.empty()) CRX_CUDA(cudaMemcpyAsync(d_jobs.p, mine.data(), mine.size() * sizeof(int4), cudaMemcpyHostToDevice, c->stream));
         TcOperand op;
         int st = crx_tc_prepare(c, p, 1, (double)scale_for(mx), &op, seg.perm, norm_s.p, errw_s.p);
-        if (st == CRX_OK) st = crx_tc_rowsum(c, op, d_jobs.p, (int)mine.size(), norm_s.p, errw_s.p, rowsum.p, rowerr.p);
+        // every scaled squared norm is at most D (max|x| 2^scale)^2
+        const double nn_max = (double)p->d * ldexp(mx, scale_for(mx)) * ldexp(mx, scale_for(mx)) * 1.0001;
+        if (st == CRX_OK) st = crx_tc_rowsum(c, op, d_jobs.p, (int)mine.size(), norm_s.p, errw_s.p, (float)(crx_tc_errw(nn_max, p->d) * 1.0001), rowsum.p, rowerr.p);
         cudaError_t e = cudaStreamSynchronize(c->stream);  // the job list and the operand are done with
         op.free_all();
         if (st != CRX_OK) return st;

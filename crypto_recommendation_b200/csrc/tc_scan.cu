@@ -123,6 +123,7 @@ struct TcParams {
     const int4* jobs;
     const float* norm_s;   // [rows] scaled squared norms of the operand rows
     const float* errw_s;   // [rows] error weight of a row: |d2 error| <= errw[a] + errw[b]
+    float errw_max;        // an upper bound of every errw_s[]
     double* rowsum;
     double* rowerr;
 };
@@ -306,6 +307,7 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const bool valid = MODE == MODE_ROWSUM ? grow < row_end : grow < p.nq;
         const float na = (MODE == MODE_ROWSUM && valid) ? p.norm_s[grow] : 0.f;
         const float ea = (MODE == MODE_ROWSUM && valid) ? p.errw_s[grow] : 0.f;
+        const float thr4 = 4.f * (ea + p.errw_max);   // d2 above this is certainly outside the small regime
         double rs_sum = 0.0, rs_err = 0.0;
         uint32_t cq = 0;
         float thr = -INFINITY, best = INFINITY, second = INFINITY;
@@ -422,7 +424,10 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     // parts);  |sqrt(x +- E) - sqrt(x)| <= E / sqrt(x) for x > 4E, and <= 2.5 sqrt(E) below (self pairs,
                     // duplicates, padding: rare, handled after the hot loop)
                     const uint4* se4 = st4 + TN / 4;
-                    float ps[4] = {0.f, 0.f, 0.f, 0.f}, pe[4] = {0.f, 0.f, 0.f, 0.f};
+                    // hot loop, 10 instructions per pair: with rs = rsqrt(d2) the distance is d2 rs and the error term
+                    // (ea + eb) rs is accumulated as ea * sum(rs) + sum(eb rs).  Pairs that MAY be in the small regime
+                    // (d2 <= 4 (ea + max eb), a superset of d2 <= 4E) contribute no error term here and are revisited below.
+                    float ps[4] = {0.f, 0.f, 0.f, 0.f}, srs[4] = {0.f, 0.f, 0.f, 0.f}, seb[4] = {0.f, 0.f, 0.f, 0.f};
                     uint32_t smallbits = 0;
 #pragma unroll
                     for (int g = 0; g < 8; g++) {
@@ -432,23 +437,30 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         for (int u = 0; u < 4; u++) {
                             float tsum = na + __uint_as_float(c4[u]);
                             float d2 = fmaf(-2.f, __uint_as_float(r[g * 4 + u]), tsum);
-                            float E = ea + __uint_as_float(e4[u]);
+                            float ddc = fmaxf(d2, 1e-30f);
                             float rs;
-                            asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(rs) : "f"(fmaxf(d2, 1e-30f)));
-                            float dd = fmaxf(d2, 0.f);
-                            bool small = dd <= 4.f * E;
-                            ps[u] = fmaf(dd, rs, ps[u]);
-                            pe[u] += small ? 0.f : E * rs;
+                            asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(rs) : "f"(ddc));
+                            ps[u] = fmaf(ddc, rs, ps[u]);
+                            bool small = d2 <= thr4;
+                            float rse = small ? 0.f : rs;
+                            srs[u] += rse;
+                            seb[u] = fmaf(__uint_as_float(e4[u]), rse, seb[u]);
                             smallbits |= small ? (1u << (g * 4 + u)) : 0u;
                         }
                     }
-                    float psum = (ps[0] + ps[1]) + (ps[2] + ps[3]), perr = (pe[0] + pe[1]) + (pe[2] + pe[3]);
+                    float psum = (ps[0] + ps[1]) + (ps[2] + ps[3]);
+                    float perr = fmaf(ea, (srs[0] + srs[1]) + (srs[2] + srs[3]), (seb[0] + seb[1]) + (seb[2] + seb[3])) + 4e-14f;
                     if (smallbits != 0u) {
                         const uint32_t* sn = reinterpret_cast<const uint32_t*>(st4);
                         while (smallbits != 0u) {
                             const int j = __ffs(smallbits) - 1;
                             smallbits &= smallbits - 1u;
-                            if (__uint_as_float(sn[j]) > -1e29f) perr += 2.5f * sqrtf(ea + __uint_as_float(sn[TN + j]));
+                            const float nb = __uint_as_float(sn[j]);
+                            if (nb > -1e29f) {  // a real column (padding columns have d = 0 and no error)
+                                const float E = ea + __uint_as_float(sn[TN + j]);
+                                const float dd = fmaxf(fmaf(-2.f, __uint_as_float(pick32(r, j)), na + nb), 0.f);
+                                perr += dd <= 4.f * E ? 2.5f * sqrtf(E) : E * rsqrtf(dd);
+                            }
                         }
                     }
                     // fp32 evaluation of the 32 terms: rsqrt.approx (2 ulp), products and <= 10 additions
@@ -531,7 +543,7 @@ __global__ void tc_prep_rows_kernel(const T* __restrict__ x, int ld, int D, cons
         // and the fp32 norms; the square-root term covers low parts that fall below the fp16 normal range
         double nn = sqn[row] * scale * scale;
         norm_s[orow] = (float)nn;
-        errw_s[orow] = (float)((6.3e-6 * nn + 5.97e-8 * sqrt((double)D * nn)) * 1.000001);
+        errw_s[orow] = (float)crx_tc_errw(nn, D);
     }
     int W = nkb * 64;
     __half* o = out + orow * (size_t)(2 * W);
@@ -678,7 +690,7 @@ int crx_tc_argmin(crx_ctx* c, const TcOperand& A, int64_t r0, int64_t nr, const 
 }
 
 int crx_tc_rowsum(crx_ctx* c, const TcOperand& A, const int4* d_jobs, int njobs, const float* norm_s, const float* errw_s,
-                  double* rowsum, double* rowerr) {
+                  float errw_max, double* rowsum, double* rowerr) {
     if (njobs == 0) return CRX_OK;
     CUtensorMap tmA, tmB;
     CRX_TRY(make_tensor_map(A, TM, &tmA));
@@ -688,7 +700,7 @@ int crx_tc_rowsum(crx_ctx* c, const TcOperand& A, const int4* d_jobs, int njobs,
     p.nkb = A.nkb;
     p.last_steps = last_steps_of(A);
     p.nprod = 3;
-    p.jobs = d_jobs; p.norm_s = norm_s; p.errw_s = errw_s; p.rowsum = rowsum; p.rowerr = rowerr;
+    p.jobs = d_jobs; p.norm_s = norm_s; p.errw_s = errw_s; p.errw_max = errw_max; p.rowsum = rowsum; p.rowerr = rowerr;
     size_t smem = smem_for(MODE_ROWSUM);
     CRX_CUDA(cudaFuncSetAttribute(tc_scan_kernel<MODE_ROWSUM, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     CRX_KERNEL(c, "tc_rowsum_scan");

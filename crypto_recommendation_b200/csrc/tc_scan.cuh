@@ -51,5 +51,10 @@ int crx_tc_argmin(crx_ctx* c, const TcOperand& A, int64_t r0, int64_t nr, const 
 
 // PAM row sums: job j = {first operand row of a 128-row tile, end row of its cluster, first column, end column};
 // rowsum[row] ~ sum over the cluster of the Euclidean distance (scaled by 2^scale), rowerr[row] bounds its error.
+// errw_max: an upper bound of errw_s[] (crx_tc_errw of the largest scaled squared norm)
 int crx_tc_rowsum(crx_ctx* c, const TcOperand& A, const int4* d_jobs, int njobs, const float* norm_s, const float* errw_s,
-                  double* rowsum, double* rowerr);
+                  float errw_max, double* rowsum, double* rowerr);
+// error weight of a row with scaled squared norm nn: the squared distance of two rows is off by at most errw(a) + errw(b).
+// 6.3e-6 nn covers the three-product split-fp16 dot with fp32 accumulation (2 x 3e-6 |a||b| <= 3e-6 (na + nb)) and the fp32
+// norms; the square-root term covers low parts that fall below the fp16 normal range
+__host__ __device__ inline double crx_tc_errw(double nn, int D) { return (6.3e-6 * nn + 5.97e-8 * sqrt((double)D * nn)) * 1.000001; }
