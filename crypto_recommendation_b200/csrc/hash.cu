@@ -59,11 +59,18 @@ __global__ void __launch_bounds__(128)
 hash_rows_kernel(const T* __restrict__ x, int ld, const double* __restrict__ sqn, int64_t N, int D, int metric, int k,
                  int L, const double* __restrict__ proj, int ldp, const double* __restrict__ pnorm,
                  const float* __restrict__ tt, const int32_t* __restrict__ rr, float w, int nbuckets,
-                 int32_t* __restrict__ hvals, int32_t* __restrict__ bucket, unsigned long long* counters) {
+                 int32_t* __restrict__ hvals, int32_t* __restrict__ bucket, unsigned long long* counters,
+                 const int32_t* __restrict__ rowlist /* nullable: only these rows */, const int* __restrict__ nlist) {
     extern __shared__ double sproj[];  // [k][ldp]
     int64_t i0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 2;
     int64_t i1 = i0 + 1;
     bool v0 = i0 < N, v1 = i1 < N;
+    if (rowlist) {  // the rows the fp32 filter could not decide
+        const int64_t cnt = *nlist;
+        v0 = i0 < cnt; v1 = i1 < cnt;
+        i0 = v0 ? rowlist[i0] : 0;
+        i1 = v1 ? rowlist[i1] : 0;
+    }
     const T* row0 = x + (v0 ? i0 : 0) * ld;
     const T* row1 = x + (v1 ? i1 : 0) * ld;
     double nx0 = v0 ? sqrt(sqn[i0]) : 0.0, nx1 = v1 ? sqrt(sqn[i1]) : 0.0;
@@ -151,19 +158,157 @@ hash_rows_kernel(const T* __restrict__ x, int ld, const double* __restrict__ sqn
     }
 }
 
+// ---- fp32 generation of K1/K2 -----------------------------------------------------------------------------------
+// All H = L*k projections of a row in ONE pass over its fp32 copy: a thread owns two rows, the projection vectors sit in
+// shared memory as floats and are read four coordinates at a time (one broadcast LDS.128 feeds 8 FFMA), which is what
+// lifts the kernel off the shared-memory bandwidth the FP64 version is bound by.  Every decision (sign, floor) is taken
+// only when the fp32 value clears its boundary by more than the rounding bound
+//   |fp32 dot - exact| <= (3 D + 8) 2^-24 |x| |r|      (FMA chain + the float conversions of x and r);
+// rows with an undecided projection are listed and redone by the exact kernel above.
+template <int KH>
+__global__ void __launch_bounds__(128)
+hash_rows32_kernel(const float* __restrict__ x, int ld, const double* __restrict__ sqn, int64_t N, int D, int metric, int k,
+                   int L, const double* __restrict__ proj, int ldp, const double* __restrict__ pnorm,
+                   const float* __restrict__ tt, const int32_t* __restrict__ rr, float w, int nbuckets,
+                   int32_t* __restrict__ hvals, int32_t* __restrict__ bucket, int32_t* __restrict__ rowlist, int* __restrict__ nlist) {
+    extern __shared__ float sp32[];          // [H][ldp] projections, then the row tile
+    const int H = L * k;
+    float* tile = sp32 + H * ldp;             // [256 rows][17]: 16 coordinates of the block's 256 rows, conflict-free
+    for (int e = threadIdx.x; e < H * ldp; e += blockDim.x) sp32[e] = (float)proj[e];
+    // thread t owns rows base + t and base + 128 + t; the global reads are cooperative and coalesced (64-byte pieces)
+    const int64_t base = (int64_t)blockIdx.x * 256;
+    const int t = threadIdx.x;
+    int64_t i0 = base + t, i1 = base + 128 + t;
+    bool v0 = i0 < N, v1 = i1 < N;
+    float a0[KH], a1[KH];
+#pragma unroll
+    for (int h = 0; h < KH; h++) { a0[h] = 0.f; a1[h] = 0.f; }
+    for (int c0 = 0; c0 < ld; c0 += 16) {
+        __syncthreads();   // previous tile consumed (and, first time, the projections staged)
+#pragma unroll
+        for (int it = 0; it < 8; it++) {
+            int idx = it * 128 + t;
+            int row = idx >> 2, piece = (idx & 3) * 4;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (base + row < N && c0 + piece < ld) v = *reinterpret_cast<const float4*>(x + (base + row) * ld + c0 + piece);
+            float* dst = tile + row * 17 + piece;
+            dst[0] = v.x; dst[1] = v.y; dst[2] = v.z; dst[3] = v.w;
+        }
+        __syncthreads();
+        float p0[16], p1[16];
+#pragma unroll
+        for (int i = 0; i < 16; i++) { p0[i] = tile[t * 17 + i]; p1[i] = tile[(128 + t) * 17 + i]; }
+        if (c0 + 16 <= ld) {
+#pragma unroll
+            for (int h = 0; h < KH; h++) {
+                if (h < H) {
+#pragma unroll
+                    for (int j = 0; j < 4; j++) {   // one broadcast LDS.128 feeds 8 FFMA
+                        float4 r = *reinterpret_cast<const float4*>(sp32 + h * ldp + c0 + 4 * j);
+                        a0[h] = fmaf(p0[4 * j], r.x, a0[h]); a1[h] = fmaf(p1[4 * j], r.x, a1[h]);
+                        a0[h] = fmaf(p0[4 * j + 1], r.y, a0[h]); a1[h] = fmaf(p1[4 * j + 1], r.y, a1[h]);
+                        a0[h] = fmaf(p0[4 * j + 2], r.z, a0[h]); a1[h] = fmaf(p1[4 * j + 2], r.z, a1[h]);
+                        a0[h] = fmaf(p0[4 * j + 3], r.w, a0[h]); a1[h] = fmaf(p1[4 * j + 3], r.w, a1[h]);
+                    }
+                }
+            }
+        } else {   // last, partial chunk (ld is a multiple of 4)
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                if (c0 + 4 * j < ld) {
+#pragma unroll
+                    for (int h = 0; h < KH; h++) {
+                        if (h < H) {
+                            float4 r = *reinterpret_cast<const float4*>(sp32 + h * ldp + c0 + 4 * j);
+                            a0[h] = fmaf(p0[4 * j], r.x, a0[h]); a1[h] = fmaf(p1[4 * j], r.x, a1[h]);
+                            a0[h] = fmaf(p0[4 * j + 1], r.y, a0[h]); a1[h] = fmaf(p1[4 * j + 1], r.y, a1[h]);
+                            a0[h] = fmaf(p0[4 * j + 2], r.z, a0[h]); a1[h] = fmaf(p1[4 * j + 2], r.z, a1[h]);
+                            a0[h] = fmaf(p0[4 * j + 3], r.w, a0[h]); a1[h] = fmaf(p1[4 * j + 3], r.w, a1[h]);
+                        }
+                    }
+                }
+            }
+        }
+    }
+    const double cb = (double)(3 * D + 8) * 5.9604644775390625e-8 * 1.001;
+    const double nx0 = v0 ? sqrt(sqn[i0]) : 0.0, nx1 = v1 ? sqrt(sqn[i1]) : 0.0;
+    const double dw = (double)w;
+    bool unsure0 = false, unsure1 = false;
+    for (int l = 0; l < L; l++) {
+        int g0 = 0, g1 = 0;
+        unsigned int phi0 = 0, phi1 = 0;
+#pragma unroll
+        for (int h = 0; h < KH; h++) {
+            if (h >= l * k && h < (l + 1) * k) {   // (compile-time h, run-time table bounds: registers stay registers)
+                double pn = pnorm[h];
+                double E0 = cb * nx0 * pn, E1 = cb * nx1 * pn;
+                int r0, r1;
+                if (metric == CRX_COSINE) {
+                    unsure0 |= fabs((double)a0[h]) <= E0;
+                    unsure1 |= fabs((double)a1[h]) <= E1;
+                    r0 = a0[h] >= 0.f ? 1 : 0;
+                    r1 = a1[h] >= 0.f ? 1 : 0;
+                    g0 = (g0 << 1) + r0;
+                    g1 = (g1 << 1) + r1;
+                } else {
+                    double t = (double)tt[h];
+                    {
+                        double sv = (double)a0[h] + t, y = sv / dw, f = floor(y), fr = y - f;
+                        double Ey = (E0 + fabs(sv) * 2.3e-16) / dw + fabs(y) * 2.3e-16;
+                        unsure0 |= !(fmin(fr, 1.0 - fr) > Ey);
+                        r0 = f2i_x87(f);
+                    }
+                    {
+                        double sv = (double)a1[h] + t, y = sv / dw, f = floor(y), fr = y - f;
+                        double Ey = (E1 + fabs(sv) * 2.3e-16) / dw + fabs(y) * 2.3e-16;
+                        unsure1 |= !(fmin(fr, 1.0 - fr) > Ey);
+                        r1 = f2i_x87(f);
+                    }
+                    if (hvals) {
+                        if (v0) hvals[((size_t)l * N + i0) * k + (h - l * k)] = r0;
+                        if (v1) hvals[((size_t)l * N + i1) * k + (h - l * k)] = r1;
+                    }
+                    if (rr) {  // euclidean_phi_gen.hpp:85-96
+                        int ri = rr[h];
+                        long long t0 = (long long)(int)((unsigned int)r0 * (unsigned int)ri);
+                        long long t1 = (long long)(int)((unsigned int)r1 * (unsigned int)ri);
+                        phi0 += (unsigned int)(int)((t0 % PHI_M + PHI_M) % PHI_M);
+                        phi1 += (unsigned int)(int)((t1 % PHI_M + PHI_M) % PHI_M);
+                    }
+                }
+            }
+        }
+        if (bucket) {
+            if (metric == CRX_COSINE) {
+                if (v0) bucket[(size_t)l * N + i0] = g0 % nbuckets;
+                if (v1) bucket[(size_t)l * N + i1] = g1 % nbuckets;
+            } else if (rr) {
+                unsigned int M = (unsigned int)PHI_M;
+                unsigned int f0 = (phi0 % M + M) % M, f1 = (phi1 % M + M) % M;
+                if (v0) bucket[(size_t)l * N + i0] = (int)((unsigned long long)f0 % (unsigned long long)nbuckets);
+                if (v1) bucket[(size_t)l * N + i1] = (int)((unsigned long long)f1 % (unsigned long long)nbuckets);
+            }
+        }
+    }
+    if (v0 && unsure0) rowlist[atomicAdd(nlist, 1)] = (int32_t)i0;
+    if (v1 && unsure1) rowlist[atomicAdd(nlist, 1)] = (int32_t)i1;
+}
+
 template <typename T>
 static int launch_hash(crx_ctx* c, const T* x, const crx_points* pts, int metric, int k, int L, const double* d_proj,
                        int ldp, const double* d_pnorm, const float* d_t, const int32_t* d_r, float w, int nbuckets,
-                       int32_t* hvals, int32_t* bucket) {
+                       int32_t* hvals, int32_t* bucket, const int32_t* rowlist = nullptr, const int* nlist = nullptr,
+                       int64_t list_cap = 0) {
     int64_t N = pts->n;
-    int grid = (int)((N + 255) / 256);
+    int grid = (int)(((rowlist ? list_cap : N) + 255) / 256);
+    if (grid == 0) return CRX_OK;
     size_t smem = (size_t)k * ldp * sizeof(double);
     CRX_KERNEL(c, "hash_rows");
 #define LAUNCH_H(KC)                                                                                              \
     do {                                                                                                          \
         CRX_CUDA(cudaFuncSetAttribute(hash_rows_kernel<T, KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
         hash_rows_kernel<T, KC><<<grid, 128, smem, c->stream>>>(x, pts->ld, pts->sqn, N, pts->d, metric, k, L, d_proj, ldp, \
-                                                                 d_pnorm, d_t, d_r, w, nbuckets, hvals, bucket, c->counters); \
+                                                                 d_pnorm, d_t, d_r, w, nbuckets, hvals, bucket, c->counters, rowlist, nlist); \
     } while (0)
     if (k <= 4) LAUNCH_H(4);
     else if (k <= 8) LAUNCH_H(8);
@@ -178,9 +323,48 @@ int crx_hash_rows(crx_ctx* c, const crx_points* pts, int metric, int k, int L, c
                   int32_t* bucket) {
     CRX_REQUIRE(k >= 1 && k <= 16, "k (hash functions per table / cube dimension) must be in [1,16]");
     CRX_REQUIRE(ldp == pts->ld, "projection stride");
+    const int H = L * k;
+    static const bool f32_off = getenv("CRX_HASH_F64") != nullptr && getenv("CRX_HASH_F64")[0] == '1';
+    const int32_t* rowlist = nullptr;
+    const int* nlist = nullptr;
+    DevBuf<int32_t> list;
+    DevBuf<int> count;
+    int64_t cap = 0;
+    if (!f32_off && H <= 32 && pts->n >= 1024) {
+        // fp32 pass over every row, then the exact kernel over the rows it could not decide
+        int64_t N = pts->n;
+        CRX_TRY(list.alloc(c, N)); CRX_TRY(count.alloc(c, 1));
+        CRX_CUDA(cudaMemsetAsync(count.p, 0, sizeof(int), c->stream));
+        int grid = (int)((N + 255) / 256);
+        size_t smem = ((size_t)H * ldp + 256 * 17) * sizeof(float);
+        {
+            CRX_KERNEL(c, "hash_rows32");
+#define LAUNCH_F(KH)                                                                                                       \
+    do {                                                                                                                   \
+        CRX_CUDA(cudaFuncSetAttribute(hash_rows32_kernel<KH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));    \
+        hash_rows32_kernel<KH><<<grid, 128, smem, c->stream>>>(pts->x32, pts->ld, pts->sqn, N, pts->d, metric, k, L, d_proj, ldp, d_pnorm, d_t, \
+                                                              d_r, w, nbuckets, hvals, bucket, list.p, count.p);           \
+    } while (0)
+            if (H <= 8) LAUNCH_F(8);
+            else if (H <= 16) LAUNCH_F(16);
+            else if (H <= 24) LAUNCH_F(24);
+            else LAUNCH_F(32);
+#undef LAUNCH_F
+            CRX_CUDA(cudaGetLastError());
+        }
+        int h_count = 0;
+        CRX_CUDA(cudaMemcpyAsync(&h_count, count.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+        CRX_CUDA(cudaStreamSynchronize(c->stream));
+        if (h_count == 0) return CRX_OK;
+        rowlist = list.p; nlist = count.p; cap = h_count;
+    }
+    int st;
     if (pts->x64)
-        return launch_hash<double>(c, pts->x64, pts, metric, k, L, d_proj, ldp, d_pnorm, d_t, d_r, w, nbuckets, hvals, bucket);
-    return launch_hash<float>(c, pts->x32, pts, metric, k, L, d_proj, ldp, d_pnorm, d_t, d_r, w, nbuckets, hvals, bucket);
+        st = launch_hash<double>(c, pts->x64, pts, metric, k, L, d_proj, ldp, d_pnorm, d_t, d_r, w, nbuckets, hvals, bucket, rowlist, nlist, cap);
+    else
+        st = launch_hash<float>(c, pts->x32, pts, metric, k, L, d_proj, ldp, d_pnorm, d_t, d_r, w, nbuckets, hvals, bucket, rowlist, nlist, cap);
+    if (st == CRX_OK && rowlist) CRX_CUDA(cudaStreamSynchronize(c->stream));   // the list is freed on return
+    return st;
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -60,7 +60,7 @@ def main():
         n = int(1_000_000 * a.scale)
         X = gen(n, 100, 64, 1)
         P = capi.Points(ctx, X)
-        r = timed("lsh_c2", lambda: capi.LshTables(ctx, P, "cosine", 4, 5, 100, 0.4, 7).close(), ["hash_rows", "bucket_offsets", "iota"])
+        r = timed("lsh_c2", lambda: capi.LshTables(ctx, P, "cosine", 4, 5, 100, 0.4, 7).close(), ["hash_rows", "hash_rows32", "bucket_offsets", "iota"])
         r["hash_gbs"] = n * (4 * 100 + 4 * 5) / (r["kernel_ms"]["hash_rows"] * 1e6)
         r["hash_frac_of_hbm"] = r["hash_gbs"] / hbm
         out["lsh_build_c2_1M_x100_cos_L5k4"] = r
@@ -74,7 +74,7 @@ def main():
         def build_cube():
             if cube[0] is not None: cube[0].close()
             cube[0] = capi.Hypercube(ctx, P, "euclidean", 16, 4.0, 9)
-        r = timed("cube_c3", build_cube, ["hash_rows", "cube_keys", "cube_heads", "cube_vertex", "bucket_offsets"], reps=2)
+        r = timed("cube_c3", build_cube, ["hash_rows", "hash_rows32", "cube_keys", "cube_heads", "cube_vertex", "bucket_offsets"], reps=2)
         r["hash_gbs"] = n * (4 * 128 + 4 * 16) / (r["kernel_ms"]["hash_rows"] * 1e6)
         r["hash_frac_of_hbm"] = r["hash_gbs"] / hbm
         out["cube_build_c3_10M_x128_d16"] = r
