@@ -550,7 +550,8 @@ __global__ void __launch_bounds__(256)
 kpp_update_kernel(const T* __restrict__ x, int ld, int D, const double* __restrict__ sqn, int64_t N,
                   const double* __restrict__ cvec /* [ld] coordinates, [ld] = exact sum of squares */, int first,
                   double* __restrict__ mind, unsigned long long* __restrict__ maxbits,
-                  const int32_t* __restrict__ rowmap /* nullable: only these rows */, const int* __restrict__ nrows_dev) {
+                  const int32_t* __restrict__ rowmap /* nullable: only these rows */, const int* __restrict__ nrows_dev,
+                  int32_t* __restrict__ nearest /* nullable: which chosen centroid gives mind */, int cur) {
     __shared__ rw::WarpTile tiles[8];
     __shared__ double vec[CRX_MAXD];
     int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -565,7 +566,7 @@ kpp_update_kernel(const T* __restrict__ x, int ld, int D, const double* __restri
         double m = 0.0;
         if (valid) {
             m = mind[row];
-            if (first || d < m) { m = d; mind[row] = d; }  // running form of the `min == -1 || d < min` scan
+            if (first || d < m) { m = d; mind[row] = d; if (nearest) nearest[row] = cur; }  // running form of the `min == -1 || d < min` scan
         }
         // max over values > 0 (max_for_normalizing starts at 0 and uses '>', initialization.hpp:116-117)
         double mx = (valid && m > 0.0) ? m : 0.0;
@@ -573,6 +574,43 @@ kpp_update_kernel(const T* __restrict__ x, int ld, int D, const double* __restri
         for (int off = 16; off > 0; off >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, off));
         if (lane == 0 && mx > 0.0) atomicMax(maxbits, (unsigned long long)__double_as_longlong(mx));
     }
+}
+
+// Euclidean rounds after the first: by the triangle inequality a point whose nearest chosen centroid c_j lies at
+// d(c_new, c_j) >= 2 mind cannot be closer to the new centroid than mind, so its row need not even be read: the pass
+// below touches 12 bytes per point (mind, nearest) instead of the row, lists the rest for the exact update and feeds
+// the unchanged minima into the normaliser.  The 1e-9 slack dwarfs the rounding of the three distances involved.
+__global__ void kpp_cdist_kernel(const double* __restrict__ cmat, int ld, int D, int ncent, const double* __restrict__ cvec,
+                                 double* __restrict__ cd) {
+    int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= ncent) return;
+    cd[j] = euclid_exact(cmat + (size_t)j * ld, cvec, D);
+}
+__global__ void __launch_bounds__(256)
+kpp_prune_kernel(const double* __restrict__ mind, const int32_t* __restrict__ nearest, const double* __restrict__ cd, int64_t N,
+                 int32_t* __restrict__ flagged, int* __restrict__ nflag, unsigned long long* __restrict__ maxbits) {
+    int lane = threadIdx.x & 31;
+    double wmax = 0.0;
+    for (int64_t base = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) - lane; base < N; base += (int64_t)gridDim.x * blockDim.x) {
+        int64_t i = base + lane;
+        bool flag = false;
+        double m = 0.0;
+        if (i < N) {
+            m = mind[i];
+            flag = !(cd[nearest[i]] >= 2.0 * m * (1.0 + 1e-9));   // NaN is listed too
+            if (!flag && m > wmax) wmax = m;
+        }
+        unsigned fm = __ballot_sync(0xffffffffu, flag);
+        if (fm) {
+            int start = 0;
+            if (lane == 0) start = atomicAdd(nflag, __popc(fm));
+            start = __shfl_sync(0xffffffffu, start, 0);
+            if (flag) flagged[start + __popc(fm & ((1u << lane) - 1u))] = (int32_t)i;
+        }
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) wmax = fmax(wmax, __shfl_xor_sync(0xffffffffu, wmax, off));
+    if (lane == 0 && wmax > 0.0) atomicMax(maxbits, (unsigned long long)__double_as_longlong(wmax));
 }
 
 // Rounds after the first, fp32 data: a point's minimum only changes when the new centroid is closer, which is rare.
@@ -584,7 +622,8 @@ template <int METRIC>
 __global__ void __launch_bounds__(256)
 kpp_filter_kernel(const float* __restrict__ x, int ld, int D, const double* __restrict__ sqn, int64_t N,
                   const double* __restrict__ cvec, const double* __restrict__ mind, int32_t* __restrict__ flagged,
-                  int* __restrict__ nflag, unsigned long long* __restrict__ maxbits) {
+                  int* __restrict__ nflag, unsigned long long* __restrict__ maxbits,
+                  const int32_t* __restrict__ rowlist /* nullable: only these rows */, const int* __restrict__ nlist) {
     constexpr int R = 8;
     int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     float4 cv = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -592,18 +631,21 @@ kpp_filter_kernel(const float* __restrict__ x, int ld, int D, const double* __re
     const double cn = cvec[ld];
     const float slack = (float)(D + 4) * 1.2e-7f;
     double wmax = 0.0;
-    for (int64_t base = ((int64_t)blockIdx.x * 8 + warp) * R; base < N; base += (int64_t)gridDim.x * 8 * R) {
+    const int64_t total = rowlist ? (int64_t)*nlist : N;
+    for (int64_t base = ((int64_t)blockIdx.x * 8 + warp) * R; base < total; base += (int64_t)gridDim.x * 8 * R) {
         float acc[R];
         // the decision inputs of this lane's row travel together with the row data (one latency, not two)
-        const int64_t row = base + ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
-        const bool have = (lane & 3) == 0 && row < N;
+        const int64_t pos = base + ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
+        const bool have = (lane & 3) == 0 && pos < total;
+        const int64_t row = have ? (rowlist ? (int64_t)rowlist[pos] : pos) : 0;
         double m = 0.0, nrow = 1.0;
         if (have) { m = mind[row]; if (METRIC == CRX_COSINE) nrow = sqn[row]; }
 #pragma unroll
         for (int r = 0; r < R; r++) {
-            int64_t row = base + r;
+            int64_t rpos = base + r;
+            int64_t row = rpos < total ? (rowlist ? (int64_t)rowlist[rpos] : rpos) : -1;
             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (row < N && 4 * lane < ld) v = __ldg(reinterpret_cast<const float4*>(x + row * ld + 4 * lane));
+            if (row >= 0 && 4 * lane < ld) v = __ldg(reinterpret_cast<const float4*>(x + row * ld + 4 * lane));
             if (METRIC == CRX_EUCLIDEAN) {
                 float a = v.x - cv.x, b = v.y - cv.y, c2 = v.z - cv.z, d2 = v.w - cv.w;
                 acc[r] = fmaf(a, a, fmaf(b, b, fmaf(c2, c2, d2 * d2)));
@@ -1257,9 +1299,18 @@ int crx_k_means_pp_sharded(crx_ctx* c, const crx_points* p, int64_t row_offset, 
     DevBuf<char> tmp;
     CRX_TRY(mind.alloc(c, N)); CRX_TRY(prob.alloc(c, N)); CRX_TRY(P.alloc(c, N)); CRX_TRY(mx.alloc(c, 1)); CRX_TRY(chosen.alloc(c, 1));
     CRX_TRY(cvec.alloc(c, ld + 1));
-    DevBuf<int32_t> flagged;
+    DevBuf<int32_t> flagged, nearest;
     DevBuf<int> nflag;
+    DevBuf<double> cmat, cd;   // coordinates of the centroids chosen so far, and their distances to the newest one
     CRX_TRY(flagged.alloc(c, N)); CRX_TRY(nflag.alloc(c, 1));
+    static const bool prune_off = getenv("CRX_KPP_NOPRUNE") != nullptr && getenv("CRX_KPP_NOPRUNE")[0] == '1';
+    const bool prune = metric == CRX_EUCLIDEAN && N >= 4096 && !prune_off;
+    DevBuf<int32_t> flagged2;
+    DevBuf<int> nflag2;
+    if (prune) {
+        CRX_TRY(nearest.alloc(c, N)); CRX_TRY(cmat.alloc(c, (size_t)K * ld)); CRX_TRY(cd.alloc(c, K));
+        CRX_TRY(flagged2.alloc(c, N)); CRX_TRY(nflag2.alloc(c, 1));
+    }
     std::vector<double> hvec(ld + 1);
     size_t bytes = 0;
     if (N > 0) CRX_CUDA(cub::DeviceScan::InclusiveSum(nullptr, bytes, prob.p, P.p, (int)N, c->stream));
@@ -1285,22 +1336,39 @@ int crx_k_means_pp_sharded(crx_ctx* c, const crx_points* p, int64_t row_offset, 
         if (out_vectors) memcpy(out_vectors + (size_t)(i - 1) * D, hvec.data(), D * sizeof(double));
         if (i == K) break;
         CRX_CUDA(cudaMemsetAsync(mx.p, 0, sizeof(unsigned long long), c->stream));
-        const bool filter = i > 1 && p->x32 != nullptr && N >= 4096 && ld <= 128;   // one 16-byte piece per lane covers the row
-        if (N > 0 && filter) {
+        const bool filter = i > 1 && p->x64 == nullptr && N >= 4096 && ld <= 128;   // fp32 data only (its fp32 copy is exact); one 16-byte piece per lane covers the row
+        if (prune) CRX_CUDA(cudaMemcpyAsync(cmat.p + (size_t)(i - 1) * ld, cvec.p, ld * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+        if (prune && i > 1) {
+            CRX_CUDA(cudaMemsetAsync(nflag.p, 0, sizeof(int), c->stream));
+            { CRX_KERNEL(c, "kpp_cdist"); kpp_cdist_kernel<<<crx_grid(i - 1, 64), 64, 0, c->stream>>>(cmat.p, ld, D, i - 1, cvec.p, cd.p); }
+            { CRX_KERNEL(c, "kpp_prune"); kpp_prune_kernel<<<c->sm_count * 8, 256, 0, c->stream>>>(mind.p, nearest.p, cd.p, N, flagged.p, nflag.p, mx.p); }
+            const int32_t* list = flagged.p;
+            const int* nl = nflag.p;
+            if (p->x64 == nullptr && ld <= 128) {   // fp32 data: the survivors' rows are read once in fp32; what that cannot rule out is exact
+                CRX_CUDA(cudaMemsetAsync(nflag2.p, 0, sizeof(int), c->stream));
+                CRX_KERNEL(c, "kpp_filter");
+                kpp_filter_kernel<CRX_EUCLIDEAN><<<c->sm_count * 8, 256, 0, c->stream>>>(p->x32, ld, D, p->sqn, N, cvec.p, mind.p, flagged2.p, nflag2.p, mx.p, flagged.p, nflag.p);
+                list = flagged2.p; nl = nflag2.p;
+            }
+            CRX_KERNEL(c, "kpp_update");
+            int ge = c->sm_count * 4;
+            if (p->x64) kpp_update_kernel<double, CRX_EUCLIDEAN><<<ge, 256, 0, c->stream>>>(p->x64, ld, D, p->sqn, N, cvec.p, 0, mind.p, mx.p, list, nl, nearest.p, i - 1);
+            else kpp_update_kernel<float, CRX_EUCLIDEAN><<<ge, 256, 0, c->stream>>>(p->x32, ld, D, p->sqn, N, cvec.p, 0, mind.p, mx.p, list, nl, nearest.p, i - 1);
+        } else if (N > 0 && filter) {
             CRX_CUDA(cudaMemsetAsync(nflag.p, 0, sizeof(int), c->stream));
             {
                 CRX_KERNEL(c, "kpp_filter");
                 int gf = (int)std::min<int64_t>((N + 63) / 64, (int64_t)c->sm_count * 8);
-                if (metric == CRX_EUCLIDEAN) kpp_filter_kernel<CRX_EUCLIDEAN><<<gf, 256, 0, c->stream>>>(p->x32, ld, D, p->sqn, N, cvec.p, mind.p, flagged.p, nflag.p, mx.p);
-                else kpp_filter_kernel<CRX_COSINE><<<gf, 256, 0, c->stream>>>(p->x32, ld, D, p->sqn, N, cvec.p, mind.p, flagged.p, nflag.p, mx.p);
+                if (metric == CRX_EUCLIDEAN) kpp_filter_kernel<CRX_EUCLIDEAN><<<gf, 256, 0, c->stream>>>(p->x32, ld, D, p->sqn, N, cvec.p, mind.p, flagged.p, nflag.p, mx.p, nullptr, nullptr);
+                else kpp_filter_kernel<CRX_COSINE><<<gf, 256, 0, c->stream>>>(p->x32, ld, D, p->sqn, N, cvec.p, mind.p, flagged.p, nflag.p, mx.p, nullptr, nullptr);
             }
             CRX_KERNEL(c, "kpp_update");
             int ge = c->sm_count * 2;  // the list is short; its length stays on the device
-            if (metric == CRX_EUCLIDEAN) kpp_update_kernel<float, CRX_EUCLIDEAN><<<ge, 256, 0, c->stream>>>(p->x32, ld, D, p->sqn, N, cvec.p, 0, mind.p, mx.p, flagged.p, nflag.p);
-            else kpp_update_kernel<float, CRX_COSINE><<<ge, 256, 0, c->stream>>>(p->x32, ld, D, p->sqn, N, cvec.p, 0, mind.p, mx.p, flagged.p, nflag.p);
+            if (metric == CRX_EUCLIDEAN) kpp_update_kernel<float, CRX_EUCLIDEAN><<<ge, 256, 0, c->stream>>>(p->x32, ld, D, p->sqn, N, cvec.p, 0, mind.p, mx.p, flagged.p, nflag.p, nullptr, 0);
+            else kpp_update_kernel<float, CRX_COSINE><<<ge, 256, 0, c->stream>>>(p->x32, ld, D, p->sqn, N, cvec.p, 0, mind.p, mx.p, flagged.p, nflag.p, nullptr, 0);
         } else if (N > 0) {
             CRX_KERNEL(c, "kpp_update");
-#define LAUNCH_K(T, M, xptr) kpp_update_kernel<T, M><<<gridu, 256, 0, c->stream>>>(xptr, ld, D, p->sqn, N, cvec.p, i == 1, mind.p, mx.p, nullptr, nullptr)
+#define LAUNCH_K(T, M, xptr) kpp_update_kernel<T, M><<<gridu, 256, 0, c->stream>>>(xptr, ld, D, p->sqn, N, cvec.p, i == 1, mind.p, mx.p, nullptr, nullptr, prune ? nearest.p : nullptr, i - 1)
             if (p->x64) { if (metric == CRX_EUCLIDEAN) LAUNCH_K(double, CRX_EUCLIDEAN, p->x64); else LAUNCH_K(double, CRX_COSINE, p->x64); }
             else { if (metric == CRX_EUCLIDEAN) LAUNCH_K(float, CRX_EUCLIDEAN, p->x32); else LAUNCH_K(float, CRX_COSINE, p->x32); }
 #undef LAUNCH_K

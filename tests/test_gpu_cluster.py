@@ -264,9 +264,11 @@ def test_kmeanspp_filter_with_duplicates_and_zero_rows(ctx, port, metric):
     ctx.profile(True); ctx.profile_reset(); ctx.counters(reset=True)
     got = capi.k_means_pp(ctx, P, 14, metric, 31)
     _, nfilter = ctx.kernel_time("kpp_filter")
+    _, nprune = ctx.kernel_time("kpp_prune")
     ctx.profile(False)
     want = port.k_means_pp(X.astype(np.float64), 14, metric, 31)
-    assert nfilter == 12, "rounds 2..13 use the filter"
+    assert nfilter == 12, "rounds 2..13 use the fp32 filter"
+    assert nprune == (12 if metric == EUCLIDEAN else 0), "Euclidean rounds are pruned by the triangle inequality first"
     if ctx.counters()["kpp_near"] == 0:
         assert np.array_equal(got, want)
 

@@ -97,11 +97,14 @@ def main():
         r["vertex_sizes"] = {"nonempty": int((sizes > 0).sum()), "max": int(sizes.max()), "mean_nonempty": float(sizes[sizes > 0].mean())}
         out["cube_range_assignment_c3_K1024_probes64"] = r
         # ---- k-means++ rounds on the same 10M x 128 points (K = 9: 8 rounds)
-        r = timed("kpp", lambda: capi.k_means_pp(ctx, P, 9, "euclidean", 5), ["kpp_update", "kpp_filter", "kpp_prob", "kpp_pick", "DeviceScan"], reps=1)
-        r17 = timed("kpp", lambda: capi.k_means_pp(ctx, P, 17, "euclidean", 5), ["kpp_update", "kpp_filter"], reps=1)
-        # rounds 9..16 = difference of the two runs: steady state (filter pass + exact update of the listed rows)
-        r["steady_round_ms_kernels"] = (r17["kernel_ms"]["kpp_update"] + r17["kernel_ms"]["kpp_filter"] - r["kernel_ms"]["kpp_update"] - r["kernel_ms"]["kpp_filter"]) / 8
-        r["steady_round_ms_wall"] = (r17["wall_ms"] - r["wall_ms"]) / 8
+        r = timed("kpp", lambda: capi.k_means_pp(ctx, P, 9, "euclidean", 5), ["kpp_update", "kpp_filter", "kpp_prune", "kpp_cdist", "kpp_prob", "kpp_pick"], reps=1)
+        names = ["kpp_update", "kpp_filter", "kpp_prune", "kpp_cdist", "kpp_prob", "kpp_pick"]
+        r17 = timed("kpp", lambda: capi.k_means_pp(ctx, P, 65, "euclidean", 5), names, reps=1)
+        r9 = timed("kpp", lambda: capi.k_means_pp(ctx, P, 33, "euclidean", 5), names, reps=1)
+        # rounds 33..64 = difference of the two runs: steady state (prune pass + exact update of the listed rows + prob + pick)
+        r["steady_round_ms_kernels"] = (sum(r17["kernel_ms"].values()) - sum(r9["kernel_ms"].values())) / 32
+        r["wall_ms_K65"] = r17["wall_ms"]
+        r["steady_round_ms_wall"] = (r17["wall_ms"] - r9["wall_ms"]) / 32
         r["steady_gbs"] = n * (4 * 128 + 8) / (r["steady_round_ms_kernels"] * 1e6)
         r["steady_frac_of_hbm"] = r["steady_gbs"] / hbm
         out["kmeanspp_round_10M_x128"] = r

@@ -28,6 +28,14 @@ def main():
     if what == "kpp":
         P = capi.Points(ctx, gen(10_000_000, 128, 1024))
         print(capi.k_means_pp(ctx, P, 6, "euclidean", 5))
+    elif what == "kpp1024":
+        import time
+        P = capi.Points(ctx, gen(10_000_000, 128, 1024))
+        capi.k_means_pp(ctx, P, 3, "euclidean", 5)
+        torch.cuda.synchronize(); t0 = time.perf_counter()
+        rows = capi.k_means_pp(ctx, P, 1024, "euclidean", 5)
+        torch.cuda.synchronize()
+        print("k-means++ K=1024 on 10M x 128: %.1f ms, checksum %d" % ((time.perf_counter() - t0) * 1e3, int(rows.astype(np.int64).sum())))
     elif what == "sums":
         n, K = 10_000_000, 1024
         P = capi.Points(ctx, gen(n, 128, 1024))
