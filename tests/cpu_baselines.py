@@ -3,7 +3,7 @@
 reference headers compiled here; the port when that is absent) on ONE host thread, at sizes that finish in seconds,
 for every sub-path of the hot path.  TEST/BENCH INFRASTRUCTURE: this is the checker being timed, never the product.
 
-    python tools/cpu_baselines.py          # prints one JSON object; `nproc` of the box is recorded
+    python tests/cpu_baselines.py          # prints one JSON object; `nproc` of the box is recorded
 """
 import json
 import os
@@ -12,7 +12,7 @@ import time
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))  # repo root (this file lives under tests/: only tests may use oracle/)
 sys.path.insert(0, ROOT)
 
 
