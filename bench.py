@@ -310,8 +310,9 @@ def run_crx(args):
     lloyd = None
     if not args.no_lloyd:
         npts, dd, kk = args.lloyd_points, args.lloyd_d, args.lloyd_k
-        g = torch.Generator(device=dev); g.manual_seed(1234 + rank)
-        centres = torch.randn((kk, dd), generator=g, device=dev) * 4.0
+        g = torch.Generator(device=dev); g.manual_seed(1234)
+        centres = torch.randn((kk, dd), generator=g, device=dev) * 4.0   # ONE mixture for the whole job ...
+        g.manual_seed(1235 + rank)                                       # ... every rank draws its own shard of points from it
         X = torch.empty((npts, dd), dtype=torch.float32, device=dev)
         CH = 1 << 20
         for lo in range(0, npts, CH):  # mixture of K unit Gaussians, generated on the device in chunks
@@ -348,9 +349,9 @@ def run_crx(args):
             capi.k_means_finish(ctx, sums, counts, C, "euclidean", 0.05, newC)
 
         a_ms, a_launch, _ = timed(step_assign, args.steps, args.min_warmup)
-        k_ms, _, _ = timed(step_kmeans, args.steps, 1)
+        k_ms, _, _ = timed(step_kmeans, args.steps, 3)   # the first all-reduces set up NCCL channels
         al_ms, _, _ = timed(step_assign_labels, args.steps, 1)
-        kl_ms, _, _ = timed(step_kmeans_labels, args.steps, 1)
+        kl_ms, _, _ = timed(step_kmeans_labels, args.steps, 2)
         ctx.profile_reset(); ctx.profile(True)
         step_kmeans(); torch.cuda.synchronize(dev)
         ctx.profile(False)

@@ -465,7 +465,7 @@ static int lloyd_scan_tc(crx_ctx* c, const crx_points* p, const Centroids& cen, 
 // ------------------------------------------------------------------------------------------------
 constexpr int SUM_CH = 16384;       // a cluster up to this size is ALWAYS one sequential sum (bit-exact)
 constexpr int SUM_CH_SHORT = 1024;  // chunk used when some cluster is too long for that
-constexpr int SUM_CH_MAX = 1 << 20; // largest: a cluster up to this size can still be one sequential sum
+constexpr int SUM_CH_MAX = 1 << 15; // largest sequential chain (~130 ns per row: a longer one would stall the whole step)
 
 template <typename T>
 __global__ void __launch_bounds__(CRX_MAXD)
@@ -1591,7 +1591,7 @@ int crx_cluster_sums(crx_ctx* c, const crx_points* p, const int32_t* labels, int
     CRX_CUDA(cudaMemcpyAsync(off.data(), seg.off, (K + 1) * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
     CRX_CUDA(cudaStreamSynchronize(c->stream));
     // A cluster of up to `whole_max` members is summed as ONE sequential chain = the reference's own sum, bit for bit:
-    // 16384 always (a chain of that length costs < 0.5 ms), up to 2^20 when there are at least two clusters per SM to
+    // 16384 always (a chain of that length costs ~2 ms at most), 32768 when there are at least two clusters per SM to
     // keep the GPU busy.  Longer clusters are cut into 1024-row chunks (deterministic, ~1e-15 relative).
     int maxc = 0, nonempty = 0;
     for (int cl = 0; cl < K; cl++) { int n = off[cl + 1] - off[cl]; maxc = std::max(maxc, n); nonempty += n > 0; }
