@@ -1311,16 +1311,14 @@ int crx_k_means_pp_sharded(crx_ctx* c, const crx_points* p, int64_t row_offset, 
         CRX_TRY(nearest.alloc(c, N)); CRX_TRY(cmat.alloc(c, (size_t)K * ld)); CRX_TRY(cd.alloc(c, K));
         CRX_TRY(flagged2.alloc(c, N)); CRX_TRY(nflag2.alloc(c, 1));
     }
-    std::vector<double> hvec(ld + 1);
     size_t bytes = 0;
     if (N > 0) CRX_CUDA(cub::DeviceScan::InclusiveSum(nullptr, bytes, prob.p, P.p, (int)N, c->stream));
     CRX_TRY(tmp.alloc(c, bytes));
     int gridu = (int)((N + 255) / 256);
-    for (int i = 1; i <= K; i++) {
-        // coordinates of the centroid picked last: staged by its owner, shared with everybody
-        int64_t g = out[i - 1];
-        int own = owner_of(g);
-        CRX_REQUIRE(own >= 0, "the shards do not cover the chosen row");
+    // coordinates (+ exact sum of squares, + the global row as a double) of a chosen centroid: staged by its owner and
+    // shared with everybody in ONE broadcast; cvec (device) and hvec (host) hold them afterwards on every rank
+    std::vector<double> hvec(ld + 2);
+    auto share_centroid = [&](int64_t g, int own) -> int {
         if (own == me) {
             if (p->x64) stage_row_kernel<double><<<1, 128, 0, c->stream>>>(p->x64, ld, p->sqn, g - row_offset, cvec.p);
             else stage_row_kernel<float><<<1, 128, 0, c->stream>>>(p->x32, ld, p->sqn, g - row_offset, cvec.p);
@@ -1328,11 +1326,21 @@ int crx_k_means_pp_sharded(crx_ctx* c, const crx_points* p, int64_t row_offset, 
                 CRX_CUDA(cudaMemcpyAsync(hvec.data(), cvec.p, (ld + 1) * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
                 CRX_CUDA(cudaStreamSynchronize(c->stream));
             }
+            hvec[ld + 1] = (double)g;
         }
         if (world > 1) {
-            CRX_TRY(comm_broadcast(c, comm, hvec.data(), ld + 1, CRX_F64, own, CRX_HOST));
+            CRX_TRY(comm_broadcast(c, comm, hvec.data(), ld + 2, CRX_F64, own, CRX_HOST));
             if (own != me) CRX_CUDA(cudaMemcpyAsync(cvec.p, hvec.data(), (ld + 1) * sizeof(double), cudaMemcpyHostToDevice, c->stream));
         }
+        return CRX_OK;
+    };
+    {
+        int own = owner_of(out[0]);
+        CRX_REQUIRE(own >= 0, "the shards do not cover the chosen row");
+        CRX_TRY(share_centroid(out[0], own));
+    }
+    for (int i = 1; i <= K; i++) {
+        // cvec / hvec hold centroid i-1 (shared at the end of the previous round, together with its row number)
         if (out_vectors) memcpy(out_vectors + (size_t)(i - 1) * D, hvec.data(), D * sizeof(double));
         if (i == K) break;
         CRX_CUDA(cudaMemsetAsync(mx.p, 0, sizeof(unsigned long long), c->stream));
@@ -1406,7 +1414,9 @@ int crx_k_means_pp_sharded(crx_ctx* c, const crx_points* p, int64_t row_offset, 
             CRX_CUDA(cudaStreamSynchronize(c->stream));
             picked = row_offset + h;
         }
-        if (world > 1) CRX_TRY(comm_broadcast(c, comm, &picked, 1, CRX_I64, pick_rank, CRX_HOST));
+        // the owner announces the picked row and its coordinates in one message
+        CRX_TRY(share_centroid(picked, pick_rank));
+        if (world > 1) picked = (int64_t)hvec[ld + 1];
         out[i] = picked;
     }
     CRX_CUDA(cudaGetLastError());

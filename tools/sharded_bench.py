@@ -26,6 +26,8 @@ def main():
     from crypto_recommendation_b200 import dist as cdist
     ap = argparse.ArgumentParser()
     ap.add_argument("--scale", type=float, default=1.0)
+    ap.add_argument("--kpp-k", type=int, default=17, help="centroids drawn by the sharded k-means++ (C4: 1024)")
+    ap.add_argument("--only-c4", action="store_true", help="skip the replicated C3 / C5 sections")
     a = ap.parse_args()
     rank, local_rank, world = cdist.init_process_group()
     dev = torch.device("cuda", local_rank)
@@ -61,7 +63,7 @@ def main():
     X = gen(n, 128, 1024, 100 + rank)     # different rows on every rank
     P = capi.Points(ctx, X)
     del X
-    K = 17
+    K = a.kpp_k
     ms = timed(lambda: capi.k_means_pp_sharded(ctx, P, rank * n, world * n, K, "euclidean", 5, comm), reps=1)
     out["kmeanspp_sharded_%dx128" % (world * n)] = {"ms_total": ms, "ms_per_round": round(ms / (K - 1), 3), "rounds": K - 1,
                                                     "points_total": world * n}
@@ -72,6 +74,16 @@ def main():
     ms = timed(lambda: capi.k_means_sharded(ctx, P, lab, C, "euclidean", 0.05, comm))
     out["kmeans_update_sharded_K64"] = {"ms": ms}
     P.close(); del lab, dis
+    if a.only_c4:
+        out["collectives"] = dict(comm.calls)
+        out["comm_error"] = comm.error
+        if rank == 0:
+            print(json.dumps(out))
+        cdist.barrier()
+        import torch.distributed as dist
+        if dist.is_initialized():
+            dist.destroy_process_group()
+        return
     # ---- C3 (strong): points replicated, centroids split
     n = int(10_000_000 * a.scale)
     X = gen(n, 128, 1024, 2)
