@@ -223,12 +223,9 @@ __device__ __forceinline__ double euclid_exact(const TA* __restrict__ a, const T
     return __dsqrt_rn(euclid_acc_exact(a, b, d));
 }
 
-// error-free transformations
-__device__ __forceinline__ void two_sum(double a, double b, double& s, double& e) {
-    s = __dadd_rn(a, b);
-    double bb = __dsub_rn(s, a);
-    e = __dadd_rn(__dsub_rn(a, __dsub_rn(s, bb)), __dsub_rn(b, bb));
-}
+#include "x87.cuh"   // two_sum, X87, x87_add, cos_sim_x87 (host-compilable: tests/test_x87_cpu.py checks them against long double)
+
+// error-free product
 __device__ __forceinline__ void two_prod(double a, double b, double& p, double& e) {
     p = __dmul_rn(a, b);
     e = __fma_rn(a, b, -p);
@@ -252,50 +249,11 @@ __device__ __forceinline__ double dot_accurate(const TA* __restrict__ a, const T
     return hi;
 }
 
-// ---- the reference's own dot product and cosine, bit for bit --------------------------------------------------
-// cust_vector.hpp:107-121 accumulates the double-rounded products in an x87 `long double`: every addition is
-// rounded to a 64-bit mantissa (round to nearest even).  Such a value is held here as h + l with h a double and
-// l a multiple of ulp64 = 2^-11 ulp(h): after each exact addition (two_sum) the low part is rounded to that grid with
-// the add-and-subtract-a-constant trick.  cust_vector.hpp:160-174 then divides in extended precision and converts
-// the quotient to double: two roundings, reproduced by cos_sim_x87.  (Inputs whose exact sum sits within 2^-105 of
-// a rounding tie are the only cases that can differ: probability ~2^-40 per operation.)
-struct X87 {
-    double h, l;
-};
-// v rounded to the 64-bit-mantissa grid of the value s + v (|v| <= ulp(s))
-__device__ __forceinline__ double x87_round_low(double s, double v) {
-    long long b = __double_as_longlong(s);
-    long long eb = b & 0x7ff0000000000000LL;
-    if (eb < (13LL << 52)) return v;                    // zero / tiny: nothing to round in any realistic input
-    bool pow2 = (b & 0x000fffffffffffffLL) == 0;        // s = +-2^e and v pulls the value below it: one binade down
-    bool opposite = v != 0.0 && ((v < 0.0) != (s < 0.0));
-    long long me = eb - (11LL << 52) - ((pow2 && opposite) ? (1LL << 52) : 0LL);
-    double M = __longlong_as_double(me | 0x0008000000000000LL);   // 1.5 * 2^(e-11): ulp(M) = 2^(e-63) = ulp64
-    return __dsub_rn(__dadd_rn(v, M), M);
-}
-__device__ __forceinline__ void x87_add(X87& acc, double p) {   // acc = round64(acc + p)
-    double s, e, s2, v2;
-    two_sum(acc.h, p, s, e);
-    two_sum(s, __dadd_rn(acc.l, e), s2, v2);
-    acc.h = s2;
-    acc.l = x87_round_low(s2, v2);
-}
 template <typename TA, typename TB>
 __device__ __forceinline__ X87 dot_x87(const TA* __restrict__ a, const TB* __restrict__ b, int d) {
     X87 acc = {0.0, 0.0};
     for (int i = 0; i < d; i++) x87_add(acc, __dmul_rn(ldv(a, i), ldv(b, i)));
     return acc;
-}
-__device__ __forceinline__ double x87_to_double(const X87& a) { return __dadd_rn(a.h, a.l); }
-// double(inner_product / denom), denom = sqrt(na) * sqrt(nb) in double (cust_vector.hpp:171-173)
-__device__ __forceinline__ double cos_sim_x87(const X87& ip, double na, double nb) {
-    double denom = __dmul_rn(__dsqrt_rn(na), __dsqrt_rn(nb));
-    double q1 = __ddiv_rn(ip.h, denom);
-    double r = __fma_rn(-q1, denom, ip.h);              // exact remainder of the first quotient digit block
-    double q2 = __ddiv_rn(__dadd_rn(r, ip.l), denom);
-    double s, v;
-    two_sum(q1, q2, s, v);
-    return __dadd_rn(s, x87_round_low(s, v));           // round to 64 bits, then to double
 }
 // cosine similarity from a plain double inner product (filters and the batched top-P refine)
 __device__ __forceinline__ double cos_sim_from(double ip, double na, double nb) {
