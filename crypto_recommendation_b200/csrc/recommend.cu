@@ -605,8 +605,30 @@ __global__ void rec_list_kernel(const TQ* __restrict__ q, int D, double sqn_q, c
     }
 }
 
-__global__ void quicksort_kernel(double* sims, int32_t* ids, int n) {
-    if (blockIdx.x == 0 && threadIdx.x == 0) lomuto_desc(sims, ids, n);
+// The literal Lomuto quicksort is one sequential walk; it runs on one thread, in shared memory when the arrays fit (12
+// bytes per element: up to ~18k neighbours), and stops refining ranges that lie beyond the first `need` positions.
+__global__ void __launch_bounds__(256)
+quicksort_kernel(double* sims, int32_t* ids, int n, int need, int in_smem) {
+    extern __shared__ double qs_keys[];
+    if (in_smem) {
+        int32_t* qs_ids = reinterpret_cast<int32_t*>(qs_keys + n);
+        for (int i = threadIdx.x; i < n; i += blockDim.x) { qs_keys[i] = sims[i]; qs_ids[i] = ids[i]; }
+        __syncthreads();
+        if (threadIdx.x == 0) lomuto_desc(qs_keys, qs_ids, n, need);
+        __syncthreads();
+        for (int i = threadIdx.x; i < n; i += blockDim.x) { sims[i] = qs_keys[i]; ids[i] = qs_ids[i]; }
+    } else if (threadIdx.x == 0) {
+        lomuto_desc(sims, ids, n, need);
+    }
+}
+static int launch_quicksort(crx_ctx* c, double* d_sims, int32_t* d_ids, int n, int need) {
+    size_t smem = (size_t)n * (sizeof(double) + sizeof(int32_t));
+    int in_smem = smem <= 200 * 1024;
+    if (in_smem) CRX_CUDA(cudaFuncSetAttribute(quicksort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CRX_KERNEL(c, "quicksort");
+    quicksort_kernel<<<1, 256, in_smem ? smem : 0, c->stream>>>(d_sims, d_ids, n, need, in_smem);
+    CRX_CUDA(cudaGetLastError());
+    return CRX_OK;
 }
 
 __global__ void fill_lists_kernel(double* s, int32_t* i, int32_t* nc, int64_t nq) {
@@ -867,7 +889,15 @@ int crx_get_P_closest(crx_ctx* c, const crx_points* users, int32_t* neighbor_row
     std::vector<double> sims((size_t)n);
     // similarities (crypto_rec.hpp:219-220), then the literal co-sort (:223) on the device
     CRX_TRY(crx_pair_op(c, users, neighbor_rows, query_set, qrows.data(), n, 3, sims.data()));
-    CRX_TRY(crx_parallel_quickSort(c, sims.data(), neighbor_rows, (int)n));
+    {   // only the first min(n, P) positions are consumed (crypto_rec.hpp:225-228): ranges beyond them are left unrefined
+        IoBuf<double> sb;
+        IoBuf<int32_t> ib;
+        CRX_TRY(sb.bind(c, sims.data(), (size_t)n, CRX_HOST, true));
+        CRX_TRY(ib.bind(c, neighbor_rows, (size_t)n, CRX_HOST, true));
+        CRX_TRY(launch_quicksort(c, sb.dev, ib.dev, (int)n, (int)*kept));
+        CRX_TRY(sb.flush());
+        CRX_TRY(ib.flush());
+    }
     for (int64_t i = 0; i < *kept; i++) similarities[i] = sims[i];
     return CRX_OK;
 }
@@ -917,8 +947,7 @@ int crx_parallel_quickSort(crx_ctx* c, double* sims, int32_t* ids, int n) {
     IoBuf<int32_t> d;
     CRX_TRY(s.bind(c, sims, n, CRX_HOST, true));
     CRX_TRY(d.bind(c, ids, n, CRX_HOST, true));
-    { CRX_KERNEL(c, "quicksort"); quicksort_kernel<<<1, 32, 0, c->stream>>>(s.dev, d.dev, n); }
-    CRX_CUDA(cudaGetLastError());
+    CRX_TRY(launch_quicksort(c, s.dev, d.dev, n, n));
     CRX_TRY(s.flush());
     return d.flush();
 }

@@ -211,7 +211,8 @@ int crx_recommend_cluster(crx_ctx* ctx, const crx_points* users, const int32_t* 
                           const crx_points* queries, const int32_t* qlabels, int Nrec, int32_t* recs, int mem);
 /* Per-user forms of the same functions, for the drop-in headers (include/crx/lib/crypto_rec.hpp):
  * get_P_closest (crypto_rec.hpp:214): similarities of the listed neighbours to the user, literal co-sort,
- *   first min(n, P) kept.  neighbor_rows[n] is reordered in place (host), similarities[min(n,P)] (host). */
+ *   first min(n, P) kept.  neighbor_rows[n] is reordered in place (host): its first min(n, P) entries are the reference's,
+ *   the rest is some permutation of the remaining neighbours; similarities[min(n,P)] (host). */
 int crx_get_P_closest(crx_ctx* ctx, const crx_points* users, int32_t* neighbor_rows, int64_t n, const crx_points* query_set,
                       int64_t query_row, int P, double* similarities, int64_t* kept);
 /* get_predicted_user_sim (:281) and get_top_N_recom (:310 with similarities, :328 with similarities == NULL) for
