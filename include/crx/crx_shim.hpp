@@ -7,6 +7,7 @@
 #include <chrono>
 #include <cstdint>
 #include <cstdio>
+#include <cstddef>
 #include <cstdlib>
 #include <set>
 #include <string>
@@ -93,6 +94,42 @@ struct Packed {
         build((int64_t)vecs.size(), [&](int64_t i) { return vecs[i]; }, ratings);
     }
 };
+
+// Vectors that already live on the GPU: a table set registers the caller's vector (the one its tables point into, as
+// the reference's tables do, lsh_cube.hpp:70) for exactly its own lifetime.  Functions that receive pointers into such
+// a vector (the neighbour lists of the recommendation loop) then pass row numbers instead of packing and uploading the
+// neighbours again on every call.
+struct Registered {
+    const char* begin;
+    const char* end;
+    size_t stride;
+    crx_points* pts;   // built with the rating metadata
+};
+inline std::vector<Registered>& registry() { static std::vector<Registered> r; return r; }
+inline void register_points(const void* base, size_t n, size_t stride, crx_points* pts) {
+    registry().push_back(Registered{(const char*)base, (const char*)base + n * stride, stride, pts});
+}
+inline void unregister_points(crx_points* pts) {
+    auto& r = registry();
+    for (size_t i = 0; i < r.size(); i++) if (r[i].pts == pts) { r.erase(r.begin() + i); return; }
+}
+// the registered set that holds ALL of `ptrs` (rows[] receives their row numbers), or NULL
+template <typename T>
+inline crx_points* registered_rows(const std::vector<CustVector<T>*>& ptrs, std::vector<int32_t>& rows) {
+    if (ptrs.empty()) return nullptr;
+    for (const Registered& reg : registry()) {
+        const char* p0 = (const char*)ptrs[0];
+        if (p0 < reg.begin || p0 >= reg.end || reg.stride != sizeof(CustVector<T>)) continue;
+        rows.resize(ptrs.size());
+        for (size_t i = 0; i < ptrs.size(); i++) {
+            const char* q = (const char*)ptrs[i];
+            if (q < reg.begin || q >= reg.end) return nullptr;
+            rows[i] = (int32_t)((q - reg.begin) / (ptrdiff_t)reg.stride);
+        }
+        return reg.pts;
+    }
+    return nullptr;
+}
 
 // row of `p` inside `vecs`, or -1 when the pointer does not alias an element (e.g. k_means centres)
 template <typename T>

@@ -23,13 +23,34 @@
 #include "lsh_cube.hpp"
 
 namespace crx {
-// neighbours + user packed into one point set: rows 0..n-1 = neighbours, row n = the user
+// The neighbours and the user as rows of device point sets.  Fast path: the neighbours point into a vector a table set
+// has registered (create_LSH_hashtables) -- nothing but row numbers travels; the user is a row of the same set or a
+// one-row set of its own.  Otherwise neighbours + user are packed into one fresh set (rows 0..n-1, user = row n).
 template <typename T>
-void pack_users(std::vector<CustVector<T>*>& neighbors, CustVector<T>& user, Packed<T>& P) {
-    std::vector<CustVector<T>*> all(neighbors.begin(), neighbors.end());
-    all.push_back(&user);
-    P.from_pointers(all, true);
-}
+struct Resolved {
+    Packed<T> own;            // owns whatever had to be packed for this call
+    crx_points* users = nullptr;
+    crx_points* query_set = nullptr;
+    int64_t query_row = 0;
+    std::vector<int32_t> rows;
+    Resolved(std::vector<CustVector<T>*>& neighbors, CustVector<T>& user) {
+        users = registered_rows(neighbors, rows);
+        if (users) {
+            std::vector<CustVector<T>*> one(1, &user);
+            std::vector<int32_t> ur;
+            if (registered_rows(one, ur) == users) { query_set = users; query_row = ur[0]; }
+            else { own.from_pointers(one, true); query_set = own.pts; query_row = 0; }
+            return;
+        }
+        std::vector<CustVector<T>*> all(neighbors.begin(), neighbors.end());
+        all.push_back(&user);
+        own.from_pointers(all, true);
+        users = query_set = own.pts;
+        query_row = (int64_t)neighbors.size();
+        rows.resize(neighbors.size());
+        for (size_t i = 0; i < rows.size(); i++) rows[i] = (int32_t)i;
+    }
+};
 }  // namespace crx
 
 // crypto_rec.hpp:235-277 on (similarity, payload) pairs: literal Lomuto, descending, `>=` pivot
@@ -51,20 +72,23 @@ void parallel_quickSort(std::vector<dim_type>& sim, std::vector<type>& neighbors
 template <typename dim_type>
 std::vector<double> get_P_closest(std::vector<CustVector<dim_type>*>& neighbors, CustVector<dim_type>& user, int P) {
     int64_t n = (int64_t)neighbors.size();
-    std::vector<double> sims;
-    if (n == 0) return sims;
-    crx::Packed<dim_type> U;
-    crx::pack_users(neighbors, user, U);
-    std::vector<int32_t> rows(n);
-    for (int64_t i = 0; i < n; i++) rows[i] = (int32_t)i;
-    sims.resize((size_t)std::min<int64_t>(n, std::max(P, 0)));
+    if (n == 0) return std::vector<double>();
+    crx::Resolved<dim_type> R(neighbors, user);
+    // position -> neighbour, carried through the co-sort as the payload
+    std::vector<int32_t> order(R.rows);
     int64_t kept = 0;
     std::vector<double> buf((size_t)std::max<int64_t>(1, std::min<int64_t>(n, std::max(P, 0))));
-    crx::check(crx_get_P_closest(crx::context(), U.pts, rows.data(), n, U.pts, n, P, buf.data(), &kept), "crx_get_P_closest");
-    std::vector<CustVector<dim_type>*> sorted((size_t)n);
-    for (int64_t i = 0; i < n; i++) sorted[i] = neighbors[rows[i]];
+    crx::check(crx_get_P_closest(crx::context(), R.users, order.data(), n, R.query_set, R.query_row, P, buf.data(), &kept), "crx_get_P_closest");
+    // rows -> pointers: rows are unique inside one call (a neighbour list holds every vector once)
+    std::vector<CustVector<dim_type>*> sorted((size_t)kept);
+    if (R.own.pts == R.users) {
+        for (int64_t i = 0; i < kept; i++) sorted[i] = neighbors[order[i]];
+    } else {
+        const char* base = nullptr;
+        for (const crx::Registered& reg : crx::registry()) if (reg.pts == R.users) base = reg.begin;
+        for (int64_t i = 0; i < kept; i++) sorted[i] = (CustVector<dim_type>*)(const_cast<char*>(base) + (size_t)order[i] * sizeof(CustVector<dim_type>));
+    }
     if (n > P) {  // crypto_rec.hpp:225-228
-        sorted.resize(P);
         neighbors = sorted;
         return std::vector<double>(buf.begin(), buf.begin() + kept);
     }
@@ -76,37 +100,30 @@ std::vector<double> get_P_closest(std::vector<CustVector<dim_type>*>& neighbors,
 // crypto_rec.hpp:281-306
 template <typename dim_type>
 std::vector<dim_type> get_predicted_user_sim(std::vector<CustVector<dim_type>*>& neighbors, CustVector<dim_type>& user, std::vector<double> similarities) {
-    crx::Packed<dim_type> U;
-    crx::pack_users(neighbors, user, U);
+    crx::Resolved<dim_type> R(neighbors, user);
     int64_t n = (int64_t)neighbors.size();
-    std::vector<int32_t> rows(n);
-    for (int64_t i = 0; i < n; i++) rows[i] = (int32_t)i;
     std::vector<double> pred(user.getDimNumber());
-    crx::check(crx_get_top_N_recom(crx::context(), U.pts, rows.data(), similarities.data(), n, U.pts, n, 0, pred.data(), nullptr), "crx_get_top_N_recom");
+    crx::check(crx_get_top_N_recom(crx::context(), R.users, R.rows.data(), similarities.data(), n, R.query_set, R.query_row, 0, pred.data(), nullptr), "crx_get_top_N_recom");
     return std::vector<dim_type>(pred.begin(), pred.end());
 }
 
 // crypto_rec.hpp:310-324
 template <typename dim_type>
 std::vector<int> get_top_N_recom(std::vector<CustVector<dim_type>*>& neighbors, CustVector<dim_type>& user, int N, std::vector<double> similarities) {
-    crx::Packed<dim_type> U;
-    crx::pack_users(neighbors, user, U);
+    crx::Resolved<dim_type> R(neighbors, user);
     int64_t n = (int64_t)neighbors.size();
-    std::vector<int32_t> rows(n), recs(N);
-    for (int64_t i = 0; i < n; i++) rows[i] = (int32_t)i;
-    crx::check(crx_get_top_N_recom(crx::context(), U.pts, rows.data(), similarities.data(), n, U.pts, n, N, nullptr, recs.data()), "crx_get_top_N_recom");
+    std::vector<int32_t> recs(N);
+    crx::check(crx_get_top_N_recom(crx::context(), R.users, R.rows.data(), similarities.data(), n, R.query_set, R.query_row, N, nullptr, recs.data()), "crx_get_top_N_recom");
     return std::vector<int>(recs.begin(), recs.end());
 }
 
 // crypto_rec.hpp:328-345: similarities to ALL neighbours are computed first, no top-P cut
 template <typename dim_type>
 std::vector<int> get_top_N_recom(std::vector<CustVector<dim_type>*>& neighbors, CustVector<dim_type>& user, int N) {
-    crx::Packed<dim_type> U;
-    crx::pack_users(neighbors, user, U);
+    crx::Resolved<dim_type> R(neighbors, user);
     int64_t n = (int64_t)neighbors.size();
-    std::vector<int32_t> rows(n), recs(N);
-    for (int64_t i = 0; i < n; i++) rows[i] = (int32_t)i;
-    crx::check(crx_get_top_N_recom(crx::context(), U.pts, rows.data(), nullptr, n, U.pts, n, N, nullptr, recs.data()), "crx_get_top_N_recom");
+    std::vector<int32_t> recs(N);
+    crx::check(crx_get_top_N_recom(crx::context(), R.users, R.rows.data(), nullptr, n, R.query_set, R.query_row, N, nullptr, recs.data()), "crx_get_top_N_recom");
     return std::vector<int>(recs.begin(), recs.end());
 }
 

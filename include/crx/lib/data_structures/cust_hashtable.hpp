@@ -23,6 +23,7 @@ struct TableSet {
     std::vector<int32_t> det;   // [L][N][k] euclidean h tuples
     std::vector<std::vector<std::vector<int32_t> > > members;  // [L][bucket] rows in insertion order
     ~TableSet() {
+        if (pts.pts) unregister_points(pts.pts);
         if (lsh) crx_lsh_destroy(lsh);
         if (cube) crx_cube_destroy(cube);
     }

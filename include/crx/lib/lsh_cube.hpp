@@ -20,7 +20,8 @@ std::vector<CustHashtable<vector_type>*> create_LSH_hashtables(std::vector<CustV
     set->metric = crx::metric_code(metric_type);
     set->k = k;
     set->L = L;
-    set->pts.from_vector(input_vectors, false);
+    set->pts.from_vector(input_vectors, true);   // with the rating metadata: the recommendation calls reuse these rows
+    if (!input_vectors.empty()) crx::register_points(&input_vectors[0], input_vectors.size(), sizeof(CustVector<vector_type>), set->pts.pts);
     crx::check(crx_create_LSH_hashtables(crx::context(), set->pts.pts, set->metric, k, L, lsh_bucket_div, euclidean_h_w, crx::next_seed(), &set->lsh),
                "crx_create_LSH_hashtables");
     std::vector<CustHashtable<vector_type>*> tables;
