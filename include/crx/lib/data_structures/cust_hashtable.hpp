@@ -104,6 +104,22 @@ public:
 
     std::vector<CustVector<dim_type>*> getBucketFor(CustVector<dim_type>* queryVector) { return getBucketFromIndex(getHash(queryVector)); }
 
+    // members of bucket `index`; with a k-tuple of h values only those stored with the same tuple (cust_hashtable.hpp:81-97)
+    std::vector<CustVector<dim_type>*> membersOf(int index, const int32_t* tuple) {
+        if (!tuple) return getBucketFromIndex(index);
+        set->load();
+        std::vector<CustVector<dim_type>*> out;
+        int64_t N = set->n();
+        if (index >= 0 && index < (int)set->members[table].size())
+            for (int32_t r : set->members[table][index]) {
+                const int32_t* t = &set->det[((size_t)table * N + r) * set->k];
+                bool same = true;
+                for (int j = 0; j < set->k; j++) if (t[j] != tuple[j]) { same = false; break; }
+                if (same) out.push_back(&(*set->base)[r]);
+            }
+        return out;
+    }
+
     // cust_hashtable.hpp:74-103: euclidean tables keep only the bucket members whose k-tuple of h equals the query's
     std::vector<CustVector<dim_type>*> getFilteredBucketFor(CustVector<dim_type>* queryVector) {
         int32_t b;

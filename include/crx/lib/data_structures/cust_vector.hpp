@@ -13,6 +13,32 @@
 
 #include "../../crx_shim.hpp"
 
+namespace crx {
+// One-row device copies of the vectors the per-pair operations are called on, kept in a small cache: loops like
+// `for (c : centroids) user.euclideanDistance(c)` (main.cpp:356-363) then upload each vector once, not once per call.
+// An entry is reused only when both the address and the coordinates are unchanged.
+struct OneRow {
+    const void* key = nullptr;
+    std::vector<double> dims;
+    crx_points* pts = nullptr;
+    unsigned long stamp = 0;
+};
+inline crx_points* one_row_points(const void* key, const std::vector<double>& dims) {
+    static std::vector<OneRow> cache(64);
+    static unsigned long clock_ = 0;
+    OneRow* victim = &cache[0];
+    for (OneRow& e : cache) {
+        if (e.pts && e.key == key && e.dims == dims) { e.stamp = ++clock_; return e.pts; }
+        if (e.stamp < victim->stamp) victim = &e;
+    }
+    if (victim->pts) crx_points_destroy(victim->pts);
+    victim->pts = nullptr;
+    check(crx_points_create(context(), dims.data(), CRX_F64, 1, (int)dims.size(), CRX_HOST, &victim->pts), "crx_points_create");
+    victim->key = key; victim->dims = dims; victim->stamp = ++clock_;
+    return victim->pts;
+}
+}  // namespace crx
+
 template <typename dim_type>
 class CustVector {
 private:
@@ -28,14 +54,12 @@ private:
         std::vector<in_dim_type>* od = other->getDimensions();
         int d = (int)dimensions.size();
         std::vector<double> a(dimensions.begin(), dimensions.end()), b(od->begin(), od->end());
-        crx_points *pa = nullptr, *pb = nullptr;
-        crx::check(crx_points_create(crx::context(), a.data(), CRX_F64, 1, d, CRX_HOST, &pa), "crx_points_create");
-        crx::check(crx_points_create(crx::context(), b.data(), CRX_F64, 1, d, CRX_HOST, &pb), "crx_points_create");
+        (void)d;
+        crx_points* pa = crx::one_row_points(this, a);
+        crx_points* pb = crx::one_row_points(other, b);   // (both stay valid: the cache holds 64 entries)
         int32_t zero = 0;
         double out = 0;
         crx::check(crx_pair_op(crx::context(), pa, &zero, pb, &zero, 1, op, &out), "crx_pair_op");
-        crx_points_destroy(pa);
-        crx_points_destroy(pb);
         return out;
     }
 

@@ -45,6 +45,18 @@ std::vector<CustVector<T>*> combined(std::vector<CustHashtable<T>*>& tables, Cus
         return out;
     }
     std::set<CustVector<T>*> u;  // pointer order == row order (lsh_cube.hpp:96,104)
+    if (row < 0 && set->lsh) {
+        // a vector that is not stored: ONE engine call hashes it for every table of the set
+        set->load();
+        std::vector<double> x(q->getDimensions()->begin(), q->getDimensions()->end());
+        std::vector<int32_t> b(set->L), d((size_t)set->L * set->k);
+        check(crx_lsh_hash_vector(set->lsh, x.data(), b.data(), set->metric == CRX_EUCLIDEAN ? d.data() : nullptr), "crx_lsh_hash_vector");
+        for (auto t : tables) {
+            std::vector<CustVector<T>*> m = t->membersOf(b[t->table], filtered && set->metric == CRX_EUCLIDEAN ? &d[(size_t)t->table * set->k] : nullptr);
+            u.insert(m.begin(), m.end());
+        }
+        return std::vector<CustVector<T>*>(u.begin(), u.end());
+    }
     for (auto t : tables) {
         std::vector<CustVector<T>*> b = filtered ? t->getFilteredBucketFor(q) : t->getBucketFor(q);
         u.insert(b.begin(), b.end());
