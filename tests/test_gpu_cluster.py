@@ -1,4 +1,6 @@
 """GPU parity (through the C ABI): clustering phases vs the CPU oracle."""
+import os
+
 import numpy as np
 import pytest
 
@@ -8,6 +10,9 @@ from helpers import assert_float_close, assert_labels
 
 pytestmark = pytest.mark.gpu
 METRICS = [EUCLIDEAN, COSINE]
+# the A/B switches of DESIGN.md section 5 change which kernels run, never the results: the suite passes under them too
+NO_TC = os.environ.get("CRX_NO_TC") == "1"
+NO_PRUNE = os.environ.get("CRX_KPP_NOPRUNE") == "1"
 
 
 def dist_fn(port, X64, C, metric):
@@ -192,7 +197,7 @@ def test_pam_tensor_path(ctx, port, dtype, d):
     ctx.profile(False)
     psw, pnew = port.pam_lloyds(X64, lab, cidx, EUCLIDEAN)
     assert sw == psw and np.array_equal(new, pnew)
-    assert launches == 1, "the tensor path ran"
+    assert launches == (0 if NO_TC else 1), "the tensor path ran"
 
 
 def test_pam_tensor_path_duplicates_first_wins(ctx, port):
@@ -268,7 +273,7 @@ def test_kmeanspp_filter_with_duplicates_and_zero_rows(ctx, port, metric):
     ctx.profile(False)
     want = port.k_means_pp(X.astype(np.float64), 14, metric, 31)
     assert nfilter == 12, "rounds 2..13 use the fp32 filter"
-    assert nprune == (12 if metric == EUCLIDEAN else 0), "Euclidean rounds are pruned by the triangle inequality first"
+    assert nprune == (12 if metric == EUCLIDEAN and not NO_PRUNE else 0), "Euclidean rounds are pruned by the triangle inequality first"
     if ctx.counters()["kpp_near"] == 0:
         assert np.array_equal(got, want)
 
@@ -369,7 +374,7 @@ def test_lloyd_tensor_path_ties_and_margins(ctx, port):
     rl, rd = port.lloyds_assignment(X, C, None, EUCLIDEAN)
     assert np.array_equal(lab, rl), np.flatnonzero(lab != rl)[:10]
     assert np.array_equal(dist, rd)
-    assert ctx.counters()["lloyd_exact"] >= 600
+    assert NO_TC or ctx.counters()["lloyd_exact"] >= 600
     # float32 points, K not a multiple of the tile width, larger magnitudes
     X32 = (X * 1000).astype(np.float32)
     C2 = C[:37] * 1000
