@@ -565,6 +565,29 @@ __global__ void cube_heads_kernel(const unsigned long long* __restrict__ keys, c
         if (s < cap) { hkeys[s] = keys[p]; hpos[s] = pos[p]; }
     }
 }
+// Dense alternative to the sort when the h values of every f span a small range (w not tiny): per-f minimum / maximum,
+// then table[f][h - min_f] = smallest position p = row * k + f at which (f, h) occurs.  The table is read before the
+// atomic, so once the early rows have claimed their entries the pass is read-only.
+__global__ void cube_minmax_kernel(const int32_t* __restrict__ hv, int64_t total, int k, int* __restrict__ mn, int* __restrict__ mx) {
+    __shared__ int smn[16], smx[16];
+    if (threadIdx.x < 16) { smn[threadIdx.x] = INT_MAX; smx[threadIdx.x] = INT_MIN; }
+    __syncthreads();
+    for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < total; p += (int64_t)gridDim.x * blockDim.x) {
+        int f = (int)(p % k), h = hv[p];
+        if (h < smn[f]) atomicMin(&smn[f], h);
+        if (h > smx[f]) atomicMax(&smx[f], h);
+    }
+    __syncthreads();
+    if (threadIdx.x < k) { atomicMin(&mn[threadIdx.x], smn[threadIdx.x]); atomicMax(&mx[threadIdx.x], smx[threadIdx.x]); }
+}
+__global__ void cube_first_kernel(const int32_t* __restrict__ hv, int64_t total, int k, const int* __restrict__ mn,
+                                  const int64_t* __restrict__ toff, uint32_t* __restrict__ table) {
+    int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= total) return;
+    int f = (int)(p % k);
+    int64_t idx = toff[f] + ((int64_t)hv[p] - (int64_t)mn[f]);
+    if ((uint32_t)p < table[idx]) atomicMin(&table[idx], (uint32_t)p);
+}
 // vertex = concatenation of f_i(h_i) bits, f_0 = MSB (hypercube_gen.hpp:63-73); maps: sorted h per f
 __global__ void cube_vertex_kernel(const int32_t* __restrict__ hv, int64_t N, int k, const int32_t* __restrict__ map_h,
                                    const int32_t* __restrict__ map_bit, const int32_t* __restrict__ map_off,
@@ -803,6 +826,45 @@ int crx_create_hypercube(crx_ctx* c, const crx_points* pts, int metric, int k, d
             // first-occurrence order of the distinct (f, h) pairs in (row-major, f-minor) order:
             // that is the order in which EuclideanFGen draws its 1-or-2 (euclidean_f_gen.hpp:65-79)
             int64_t total = N * k;
+            std::vector<unsigned long long> hk;
+            std::vector<uint32_t> hp;
+            int nheads = 0;
+            // ---- dense tables when the h ranges are small
+            bool dense = false;
+            {
+                DevBuf<int> dmn, dmx;
+                CRX_TRY(dmn.alloc(c, 16)); CRX_TRY(dmx.alloc(c, 16));
+                std::vector<int> hmn(16, INT_MAX), hmx(16, INT_MIN);
+                CRX_CUDA(cudaMemcpyAsync(dmn.p, hmn.data(), 16 * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+                CRX_CUDA(cudaMemcpyAsync(dmx.p, hmx.data(), 16 * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+                { CRX_KERNEL(c, "cube_minmax"); cube_minmax_kernel<<<c->sm_count * 8, 256, 0, c->stream>>>(hv.p, total, k, dmn.p, dmx.p); }
+                CRX_CUDA(cudaMemcpyAsync(hmn.data(), dmn.p, 16 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+                CRX_CUDA(cudaMemcpyAsync(hmx.data(), dmx.p, 16 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+                CRX_CUDA(cudaStreamSynchronize(c->stream));
+                std::vector<int64_t> toff(k + 1, 0);
+                for (int f = 0; f < k; f++) toff[f + 1] = toff[f] + ((int64_t)hmx[f] - (int64_t)hmn[f] + 1);
+                if (toff[k] <= (1ll << 22)) {
+                    dense = true;
+                    DevBuf<int64_t> dtoff;
+                    DevBuf<uint32_t> table;
+                    CRX_TRY(dtoff.alloc(c, k + 1)); CRX_TRY(table.alloc(c, toff[k]));
+                    CRX_CUDA(cudaMemcpyAsync(dtoff.p, toff.data(), (k + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, c->stream));
+                    CRX_CUDA(cudaMemsetAsync(table.p, 0xff, toff[k] * sizeof(uint32_t), c->stream));
+                    { CRX_KERNEL(c, "cube_first"); cube_first_kernel<<<crx_grid(total, 256), 256, 0, c->stream>>>(hv.p, total, k, dmn.p, dtoff.p, table.p); }
+                    std::vector<uint32_t> ht(toff[k]);
+                    CRX_CUDA(cudaMemcpyAsync(ht.data(), table.p, toff[k] * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+                    CRX_CUDA(cudaStreamSynchronize(c->stream));
+                    for (int f = 0; f < k; f++)
+                        for (int64_t j = toff[f]; j < toff[f + 1]; j++)
+                            if (ht[j] != 0xffffffffu) {
+                                int32_t h = (int32_t)((int64_t)hmn[f] + (j - toff[f]));
+                                hk.push_back(((unsigned long long)f << 32) | (unsigned long long)((uint32_t)h ^ 0x80000000u));
+                                hp.push_back(ht[j]);
+                            }
+                    nheads = (int)hk.size();
+                }
+            }
+            if (!dense) {
             DevBuf<unsigned long long> keys, keys2, hkeys;
             DevBuf<uint32_t> pos, pos2, hpos;
             DevBuf<int> cnt;
@@ -815,7 +877,7 @@ int crx_create_hypercube(crx_ctx* c, const crx_points* pts, int metric, int k, d
             DevBuf<char> tmp;
             CRX_TRY(tmp.alloc(c, bytes));
             CRX_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, bytes, keys.p, keys2.p, pos.p, pos2.p, (int)total, 0, 37, c->stream));
-            int cap = 1 << 20, nheads = 0;
+            int cap = 1 << 20;
             for (int attempt = 0; attempt < 2; attempt++) {
                 CRX_TRY(hkeys.alloc(c, cap)); CRX_TRY(hpos.alloc(c, cap));
                 CRX_CUDA(cudaMemsetAsync(cnt.p, 0, sizeof(int), c->stream));
@@ -825,11 +887,11 @@ int crx_create_hypercube(crx_ctx* c, const crx_points* pts, int metric, int k, d
                 if (nheads <= cap) break;
                 cap = nheads;
             }
-            std::vector<unsigned long long> hk(nheads);
-            std::vector<uint32_t> hp(nheads);
+            hk.resize(nheads); hp.resize(nheads);
             CRX_CUDA(cudaMemcpyAsync(hk.data(), hkeys.p, nheads * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
             CRX_CUDA(cudaMemcpyAsync(hp.data(), hpos.p, nheads * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
             CRX_CUDA(cudaStreamSynchronize(c->stream));
+            }  // sort path
             std::vector<int> order(nheads);
             for (int i = 0; i < nheads; i++) order[i] = i;
             std::sort(order.begin(), order.end(), [&](int a, int b) { return hp[a] < hp[b]; });

@@ -74,7 +74,7 @@ def main():
         def build_cube():
             if cube[0] is not None: cube[0].close()
             cube[0] = capi.Hypercube(ctx, P, "euclidean", 16, 4.0, 9)
-        r = timed("cube_c3", build_cube, ["hash_rows", "hash_rows32", "cube_keys", "cube_heads", "cube_vertex", "bucket_offsets"], reps=2)
+        r = timed("cube_c3", build_cube, ["hash_rows", "hash_rows32", "cube_keys", "cube_heads", "cube_minmax", "cube_first", "cube_vertex", "bucket_offsets"], reps=2)
         r["hash_gbs"] = n * (4 * 128 + 4 * 16) / (r["kernel_ms"]["hash_rows"] * 1e6)
         r["hash_frac_of_hbm"] = r["hash_gbs"] / hbm
         out["cube_build_c3_10M_x128_d16"] = r
