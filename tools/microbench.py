@@ -125,6 +125,9 @@ def main():
     P = capi.Points(ctx, X)
     del X
     K = 256
+    r = timed("lsh_c5", lambda: capi.LshTables(ctx, P, "euclidean", 4, 5, 100, 0.4, 11).close(), ["hash_rows", "hash_rows32", "gather_h", "tuple_flag", "scatter_rank", "bucket_offsets", "iota", ""], reps=1)
+    r["kernel_ms_total"] = r["kernel_ms"].pop("")
+    out["lsh_build_c5_%d_x100_euc_L5k4" % n] = r
     t = capi.LshTables(ctx, P, "euclidean", 4, 5, 100, 0.4, 11)
     cidx = capi.k_means_pp(ctx, P, K, "euclidean", 6)
     r = timed("lsh_range", lambda: capi.lsh_range_assignment(ctx, P, t, cidx, "euclidean"), ["range_fire", "range_finalize", "lloyd_scan", "tc_argmin", "lloyd_refine"], reps=1)
