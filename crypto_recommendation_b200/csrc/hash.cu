@@ -438,17 +438,79 @@ __global__ void scatter_rank_kernel(const int32_t* __restrict__ rank, const int3
     if (i < n) gid[perm[i]] = rank[i];
 }
 
+// minimum / maximum of the j-th h value over all rows, j = 0..k-1 (hv is [rows][k]; mn / mx preset to INT_MAX / INT_MIN)
+__global__ void cube_minmax_kernel(const int32_t* __restrict__ hv, int64_t total, int k, int* __restrict__ mn, int* __restrict__ mx) {
+    __shared__ int smn[16], smx[16];
+    if (threadIdx.x < 16) { smn[threadIdx.x] = INT_MAX; smx[threadIdx.x] = INT_MIN; }
+    __syncthreads();
+    for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < total; p += (int64_t)gridDim.x * blockDim.x) {
+        int f = (int)(p % k), h = hv[p];
+        if (h < smn[f]) atomicMin(&smn[f], h);
+        if (h > smx[f]) atomicMax(&smx[f], h);
+    }
+    __syncthreads();
+    if (threadIdx.x < k) { atomicMin(&mn[threadIdx.x], smn[threadIdx.x]); atomicMax(&mx[threadIdx.x], smx[threadIdx.x]); }
+}
+// lexicographic key of the k-tuple in as few bits as its value ranges allow: h_0 most significant
+__global__ void pack_tuple_kernel(const int32_t* __restrict__ hv, int64_t n, int k, const int* __restrict__ mn,
+                                  const int* __restrict__ shift, unsigned long long* __restrict__ key, int32_t* __restrict__ idx) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    unsigned long long v = 0;
+    for (int j = 0; j < k; j++) v |= (unsigned long long)((long long)hv[i * k + j] - (long long)mn[j]) << shift[j];
+    key[i] = v;
+    idx[i] = (int32_t)i;
+}
+
 static int build_tuple_groups(crx_ctx* c, const int32_t* hv /* [N][k] */, int64_t n, int k, int32_t* gid, Segments* seg,
                               int* ngroups) {
     DevBuf<int32_t> pa, pb, ka, kb;
     CRX_TRY(pa.alloc(c, n)); CRX_TRY(pb.alloc(c, n)); CRX_TRY(ka.alloc(c, n)); CRX_TRY(kb.alloc(c, n));
     int g = crx_grid(n, 256);
-    { CRX_KERNEL(c, "iota"); iota_kernel<<<g, 256, 0, c->stream>>>(pa.p, n); }
     int32_t* pin = pa.p; int32_t* pout = pb.p;
-    for (int j = k - 1; j >= 0; j--) {  // LSD passes, each stable => lexicographic order, ties by row
-        { CRX_KERNEL(c, "gather_h"); gather_h_kernel<<<g, 256, 0, c->stream>>>(hv, pin, n, k, j, ka.p); }
-        CRX_TRY(sort_pairs(c, ka.p, kb.p, pin, pout, n, 32));
-        std::swap(pin, pout);
+    // value ranges of the k components: when the whole tuple fits 64 bits, ONE stable sort of the packed key replaces the
+    // k LSD passes over 32-bit keys
+    bool packed = false;
+    if (k <= 16) {
+        DevBuf<int> dmn, dmx, dshift;
+        CRX_TRY(dmn.alloc(c, 16)); CRX_TRY(dmx.alloc(c, 16)); CRX_TRY(dshift.alloc(c, 16));
+        std::vector<int> hmn(16, INT_MAX), hmx(16, INT_MIN), shift(16, 0);
+        CRX_CUDA(cudaMemcpyAsync(dmn.p, hmn.data(), 16 * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+        CRX_CUDA(cudaMemcpyAsync(dmx.p, hmx.data(), 16 * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+        { CRX_KERNEL(c, "cube_minmax"); cube_minmax_kernel<<<c->sm_count * 8, 256, 0, c->stream>>>(hv, n * k, k, dmn.p, dmx.p); }
+        CRX_CUDA(cudaMemcpyAsync(hmn.data(), dmn.p, 16 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+        CRX_CUDA(cudaMemcpyAsync(hmx.data(), dmx.p, 16 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+        CRX_CUDA(cudaStreamSynchronize(c->stream));
+        int bits = 0;
+        for (int j = k - 1; j >= 0; j--) {
+            unsigned long long range = (unsigned long long)((long long)hmx[j] - (long long)hmn[j]);
+            int b = 1;
+            while (b < 33 && (range >> b) != 0) b++;
+            shift[j] = bits;
+            bits += b;
+        }
+        if (bits <= 64) {
+            packed = true;
+            DevBuf<unsigned long long> k0, k1;
+            CRX_TRY(k0.alloc(c, n)); CRX_TRY(k1.alloc(c, n));
+            CRX_CUDA(cudaMemcpyAsync(dshift.p, shift.data(), 16 * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+            { CRX_KERNEL(c, "pack_tuple"); pack_tuple_kernel<<<g, 256, 0, c->stream>>>(hv, n, k, dmn.p, dshift.p, k0.p, pin); }
+            size_t sb = 0;
+            CRX_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, sb, k0.p, k1.p, pin, pout, (int)n, 0, bits, c->stream));
+            DevBuf<char> stmp;
+            CRX_TRY(stmp.alloc(c, sb));
+            CRX_CUDA(cub::DeviceRadixSort::SortPairs(stmp.p, sb, k0.p, k1.p, pin, pout, (int)n, 0, bits, c->stream));
+            CRX_CUDA(cudaStreamSynchronize(c->stream));   // the temporaries go out of scope
+            std::swap(pin, pout);
+        }
+    }
+    if (!packed) {
+        { CRX_KERNEL(c, "iota"); iota_kernel<<<g, 256, 0, c->stream>>>(pa.p, n); }
+        for (int j = k - 1; j >= 0; j--) {  // LSD passes, each stable => lexicographic order, ties by row
+            { CRX_KERNEL(c, "gather_h"); gather_h_kernel<<<g, 256, 0, c->stream>>>(hv, pin, n, k, j, ka.p); }
+            CRX_TRY(sort_pairs(c, ka.p, kb.p, pin, pout, n, 32));
+            std::swap(pin, pout);
+        }
     }
     { CRX_KERNEL(c, "tuple_flag"); tuple_flag_kernel<<<g, 256, 0, c->stream>>>(hv, pin, n, k, ka.p); }
     size_t bytes = 0;
@@ -565,21 +627,9 @@ __global__ void cube_heads_kernel(const unsigned long long* __restrict__ keys, c
         if (s < cap) { hkeys[s] = keys[p]; hpos[s] = pos[p]; }
     }
 }
-// Dense alternative to the sort when the h values of every f span a small range (w not tiny): per-f minimum / maximum,
-// then table[f][h - min_f] = smallest position p = row * k + f at which (f, h) occurs.  The table is read before the
+// Dense alternative to the sort when the h values of every f span a small range (w not tiny): per-f minimum / maximum
+// (cube_minmax_kernel above), then table[f][h - min_f] = smallest position p = row * k + f at which (f, h) occurs.  The table is read before the
 // atomic, so once the early rows have claimed their entries the pass is read-only.
-__global__ void cube_minmax_kernel(const int32_t* __restrict__ hv, int64_t total, int k, int* __restrict__ mn, int* __restrict__ mx) {
-    __shared__ int smn[16], smx[16];
-    if (threadIdx.x < 16) { smn[threadIdx.x] = INT_MAX; smx[threadIdx.x] = INT_MIN; }
-    __syncthreads();
-    for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < total; p += (int64_t)gridDim.x * blockDim.x) {
-        int f = (int)(p % k), h = hv[p];
-        if (h < smn[f]) atomicMin(&smn[f], h);
-        if (h > smx[f]) atomicMax(&smx[f], h);
-    }
-    __syncthreads();
-    if (threadIdx.x < k) { atomicMin(&mn[threadIdx.x], smn[threadIdx.x]); atomicMax(&mx[threadIdx.x], smx[threadIdx.x]); }
-}
 __global__ void cube_first_kernel(const int32_t* __restrict__ hv, int64_t total, int k, const int* __restrict__ mn,
                                   const int64_t* __restrict__ toff, uint32_t* __restrict__ table) {
     int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
