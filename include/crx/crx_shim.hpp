@@ -77,10 +77,10 @@ struct Packed {
         if (ratings) { unk.assign((size_t)n * d, 0); mean.resize(n); }
         for (int64_t i = 0; i < n; i++) {
             CustVector<T>* v = get(i);
-            const std::vector<T>& dims = *v->getDimensions();
+            const std::vector<T>& dims = v->crxDimsRef();
             for (int j = 0; j < d; j++) buf[(size_t)i * d + j] = (double)dims[j];
             if (ratings) {
-                for (int u : v->getUnknownIndexesSet()) if (u >= 0 && u < d) unk[(size_t)i * d + u] = 1;
+                for (int u : v->crxUnknownRef()) if (u >= 0 && u < d) unk[(size_t)i * d + u] = 1;
                 mean[i] = v->getKnownMean();
             }
         }

@@ -110,6 +110,10 @@ public:
     std::vector<dim_type>* getDimensions() { return &dimensions; }
     std::vector<int> getUnknownIndexes() { return std::vector<int>(unknown_indexes.begin(), unknown_indexes.end()); }
     std::set<int> getUnknownIndexesSet() { return unknown_indexes; }
+    // not in the reference: read-only views for the packing code of the drop-in headers (the getters above copy, as the
+    // reference's do: cust_vector.hpp:229-236)
+    const std::set<int>& crxUnknownRef() const { return unknown_indexes; }
+    const std::vector<dim_type>& crxDimsRef() const { return dimensions; }
     double getKnownMean() { return known_mean; }
     unsigned int getDimNumber() { return (unsigned int)dimensions.size(); }
     int getCluster() { return cluster_i; }
