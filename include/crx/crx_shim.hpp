@@ -67,15 +67,15 @@ struct Packed {
     Packed& operator=(const Packed&) = delete;
     ~Packed() { if (pts) crx_points_destroy(pts); }
 
+    // host image of `count` vectors: coordinates, unknown flags, known means
     template <typename Getter>
-    void build(int64_t count, Getter get, bool ratings) {
-        n = count;
+    static void pack_host(int64_t count, Getter get, bool ratings, int& d, std::vector<double>& buf, std::vector<uint8_t>& unk,
+                          std::vector<double>& mean) {
         d = count ? (int)get(0)->getDimNumber() : 0;
-        std::vector<double> buf((size_t)n * d);
-        std::vector<uint8_t> unk;
-        std::vector<double> mean;
-        if (ratings) { unk.assign((size_t)n * d, 0); mean.resize(n); }
-        for (int64_t i = 0; i < n; i++) {
+        buf.assign((size_t)count * d, 0.0);
+        unk.clear(); mean.clear();
+        if (ratings) { unk.assign((size_t)count * d, 0); mean.resize(count); }
+        for (int64_t i = 0; i < count; i++) {
             CustVector<T>* v = get(i);
             const std::vector<T>& dims = v->crxDimsRef();
             for (int j = 0; j < d; j++) buf[(size_t)i * d + j] = (double)dims[j];
@@ -84,8 +84,19 @@ struct Packed {
                 mean[i] = v->getKnownMean();
             }
         }
+    }
+    void upload(int64_t count, int dims, const std::vector<double>& buf, const std::vector<uint8_t>& unk, const std::vector<double>& mean) {
+        n = count; d = dims;
         check(crx_points_create(context(), buf.data(), CRX_F64, n, d, CRX_HOST, &pts), "crx_points_create");
-        if (ratings) check(crx_points_set_ratings(pts, unk.data(), mean.data(), CRX_HOST), "crx_points_set_ratings");
+        if (!unk.empty()) check(crx_points_set_ratings(pts, unk.data(), mean.data(), CRX_HOST), "crx_points_set_ratings");
+    }
+    template <typename Getter>
+    void build(int64_t count, Getter get, bool ratings) {
+        std::vector<double> buf, mean;
+        std::vector<uint8_t> unk;
+        int dims = 0;
+        pack_host(count, get, ratings, dims, buf, unk, mean);
+        upload(count, dims, buf, unk, mean);
     }
     void from_vector(std::vector<CustVector<T> >& vecs, bool ratings = false) {
         build((int64_t)vecs.size(), [&](int64_t i) { return &vecs[i]; }, ratings);
