@@ -130,7 +130,8 @@ class Context:
         out = (ctypes.c_int64 * 8)()
         _check(lib().crx_ctx_counters(self.h, out, int(reset)))
         v = list(out)
-        return {"hash_dd": v[0], "topp_uncertified": v[1], "kpp_near": v[2], "pam_exact": v[3], "lloyd_exact": v[4]}
+        return {"hash_dd": v[0], "topp_uncertified": v[1], "kpp_near": v[2], "pam_exact": v[3], "lloyd_exact": v[4],
+                "topp_tie_order": v[5], "topp_tied": v[6]}
 
     # ---- vector<CustVector<T>> -------------------------------------------------------------
     def points(self, X, unknown=None, known_mean=None):

@@ -262,7 +262,7 @@ rec_finalize_kernel(const TQ* __restrict__ xq, int ldq, const double* __restrict
                     const double* __restrict__ mean_b, int D, int64_t q_begin, int64_t nq, int P, int Nrec,
                     const TS* __restrict__ list_s, const int32_t* __restrict__ list_i, const int32_t* __restrict__ ncand,
                     double approx_scale, double approx_eps, int32_t* __restrict__ recs, int32_t* __restrict__ nbr_rows,
-                    double* __restrict__ nbr_sims, unsigned long long* counters) {
+                    double* __restrict__ nbr_sims, unsigned long long* counters, int tie_order) {
     constexpr int EPL = LISTN / 32;  // list entries per lane
     constexpr int QW = 4;            // queries (warps) per block
     __shared__ int a_idx[QW][LISTN];
@@ -302,6 +302,8 @@ rec_finalize_kernel(const TQ* __restrict__ xq, int ldq, const double* __restrict
     // score cannot be among the exact P best: they are dropped before the exact (expensive) evaluation.  When at most 32
     // survive, one row walk serves them all.
     bool one_walk = false;
+    int walked = 0;              // one-walk path: slots of a_idx / a_sim in use
+    double cut = -INFINITY;      // filter units: listed candidates below it are not evaluated (one-walk path)
     if (EPL == 2 && nvalid > P) {
         int g0 = 0, g1 = 0;
         for (int t = 0; t < 32; t++) {
@@ -313,11 +315,13 @@ rec_finalize_kernel(const TQ* __restrict__ xq, int ldq, const double* __restrict
         double T = fmin(g0 < P ? val_e[0] : INFINITY, g1 < P ? val_e[EPL - 1] : INFINITY);
 #pragma unroll
         for (int off = 16; off > 0; off >>= 1) T = fmin(T, __shfl_xor_sync(0xffffffffu, T, off));
-        double cut = T - 2.02 * approx_eps / approx_scale;   // approx_eps is in similarity units, the list in filter units
+        const double margin = 2.02 * approx_eps / approx_scale;   // approx_eps is in similarity units, the list in filter units
+        cut = T - margin;
         bool k0 = idx_e[0] >= 0 && val_e[0] >= cut, k1 = idx_e[EPL - 1] >= 0 && val_e[EPL - 1] >= cut;
         unsigned b0 = __ballot_sync(0xffffffffu, k0), b1 = __ballot_sync(0xffffffffu, k1);
         int count = __popc(b0) + __popc(b1);
         if (count <= 32) {
+            walked = count;
             one_walk = true;
             unsigned lt = (1u << lane) - 1u;
             if (k0) a_idx[warp][__popc(b0 & lt)] = idx_e[0];
@@ -350,6 +354,9 @@ rec_finalize_kernel(const TQ* __restrict__ xq, int ldq, const double* __restrict
     }
     __syncwarp();
     int keep = min(P, nvalid);
+    bool tied[EPL];
+#pragma unroll
+    for (int e = 0; e < EPL; e++) tied[e] = false;
     // descending similarity, ties by ascending row
 #pragma unroll
     for (int e = 0; e < EPL; e++) {
@@ -357,23 +364,157 @@ rec_finalize_kernel(const TQ* __restrict__ xq, int ldq, const double* __restrict
         int idx = a_idx[warp][slot];
         double sim = a_sim[warp][slot];
         if (idx >= 0) {
-            int rank = 0;
+            int rank = 0, same = 0;
             for (int t = 0; t < LISTN; t++) {
                 int oi = a_idx[warp][t];
                 double os = a_sim[warp][t];
                 if (oi >= 0 && (os > sim || (os == sim && oi < idx))) rank++;
+                same += oi >= 0 && os == sim;
             }
             if (rank < 32) { s_idx[warp][rank] = idx; s_sim[warp][rank] = sim; }
+            tied[e] = same > 1;
         }
     }
     __syncwarp();
     int nc = ncand[qrel];
     // certification: every candidate outside the list has an approximate similarity <= the smallest
     // approximate one in it; the exact P-th best must clear that by more than the filter's error
-    if (floor_s > -INFINITY && keep > 0 && lane == 0) {
-        double floor_ = floor_s * approx_scale;
-        double pth = s_sim[warp][keep - 1];
-        if (!(pth > floor_ + approx_eps * fmax(1.0, fabs(floor_)))) atomicAdd(&counters[CRX_CNT_TOPP_RESCAN], 1ull);
+    if (keep > 0) {
+        const double floor_ = floor_s * approx_scale;
+        const double unlisted = floor_s > -INFINITY ? floor_ + approx_eps * fmax(1.0, fabs(floor_)) : -INFINITY;
+        const double pth = s_sim[warp][keep - 1];
+        if (!(pth > unlisted)) {
+            if (lane == 0) atomicAdd(&counters[CRX_CNT_TOPP_RESCAN], 1ull);
+        } else {
+            bool t = false;
+#pragma unroll
+            for (int e = 0; e < EPL; e++) t |= tied[e] && a_sim[warp][e * 32 + lane] >= pth;
+            const bool any_tie = __any_sync(0xffffffffu, t);
+            if (any_tie && lane == 0) {
+                atomicAdd(&counters[CRX_CNT_TOPP_TIED], 1ull);
+                if (!tie_order) atomicAdd(&counters[CRX_CNT_TOPP_TIES], 1ull);
+            }
+            if (any_tie && tie_order) {
+                // ---- equal similarities among the P best: reproduce the order of the reference's quicksort ----
+                // (crypto_rec.hpp:235-277 over the candidates in std::set order = row order, lsh_cube.hpp:96-104.)  While
+                // the ">= pivot" side of a partition still holds P elements only that side is consumed, and it keeps
+                // the row order; so the consumed prefix equals the literal sort of
+                //     R = { candidates before row r' with similarity >= t' },  in row order,
+                // t' = the best similarity stored behind the last member e* of the P best (ties included), r' = the
+                // first row behind e* that reaches t' (DESIGN.md section 3).  R is known exactly when every candidate
+                // above t' has been evaluated: unlisted ones are below `unlisted`, unevaluated listed ones below `cut2`.
+                int estar = -1;
+#pragma unroll
+                for (int e = 0; e < EPL; e++)
+                    if (a_idx[warp][e * 32 + lane] >= 0 && a_sim[warp][e * 32 + lane] >= pth) estar = max(estar, a_idx[warp][e * 32 + lane]);
+#pragma unroll
+                for (int off = 16; off > 0; off >>= 1) estar = max(estar, __shfl_xor_sync(0xffffffffu, estar, off));
+                double s_estar = -INFINITY;
+#pragma unroll
+                for (int e = 0; e < EPL; e++) if (a_idx[warp][e * 32 + lane] == estar) s_estar = a_sim[warp][e * 32 + lane];
+#pragma unroll
+                for (int off = 16; off > 0; off >>= 1) s_estar = fmax(s_estar, __shfl_xor_sync(0xffffffffu, s_estar, off));
+                int before = 0;
+#pragma unroll
+                for (int e = 0; e < EPL; e++)
+                    before += __popc(__ballot_sync(0xffffffffu, a_idx[warp][e * 32 + lane] >= 0 && a_idx[warp][e * 32 + lane] < estar &&
+                                                                    a_sim[warp][e * 32 + lane] >= s_estar));
+                double known_above = unlisted, tp = -INFINITY;
+                int rlim = 0x7fffffff;
+                bool resolved = true;
+                if (before >= keep) {
+                    // e* itself is still a pivot with P elements on its ">=" side (a plateau reaching beyond the P-th place):
+                    // R = the members of the P best (ties included) in front of e*
+                    tp = s_estar; rlim = estar;
+                } else {
+                    if (one_walk) {
+                        // evaluate the listed candidates down to the best one stored behind e* (by approximate score)
+                        double tm = -INFINITY;
+#pragma unroll
+                        for (int e = 0; e < EPL; e++) if (idx_e[e] > estar) tm = fmax(tm, val_e[e]);
+#pragma unroll
+                        for (int off = 16; off > 0; off >>= 1) tm = fmax(tm, __shfl_xor_sync(0xffffffffu, tm, off));
+                        if (tm > -INFINITY || floor_s == -INFINITY) {
+                            const double cut2 = tm > -INFINITY ? tm - 2.02 * approx_eps / approx_scale : -INFINITY;
+                            if (cut2 > -INFINITY) known_above = fmax(unlisted, cut2 * approx_scale + 1.01 * approx_eps);
+#pragma unroll
+                            for (int e = 0; e < EPL; e++) {
+                                bool add = idx_e[e] >= 0 && val_e[e] >= cut2 && !(val_e[e] >= cut);
+                                unsigned bm = __ballot_sync(0xffffffffu, add);
+                                if (bm) {
+                                    rw::Walk w = rw::walk_rows<TB, CRX_COSINE>(xb, ldb, D, add ? (int64_t)idx_e[e] : -1, qvec[warp], tiles[warp]);
+                                    if (add) {
+                                        X87 ip = {w.a, w.b};
+                                        int dst = walked + __popc(bm & ((1u << lane) - 1u));
+                                        a_idx[warp][dst] = idx_e[e];
+                                        a_sim[warp][dst] = cos_sim_x87(ip, sqn_b[idx_e[e]], nq_);
+                                    }
+                                    walked += __popc(bm);
+                                }
+                            }
+                            __syncwarp();
+                        } else {
+                            resolved = false;   // nothing listed behind e*
+                        }
+                    }
+                    if (resolved) {
+#pragma unroll
+                        for (int e = 0; e < EPL; e++) {
+                            int oi = a_idx[warp][e * 32 + lane];
+                            double os = a_sim[warp][e * 32 + lane];
+                            if (oi > estar && os > known_above) tp = fmax(tp, os);
+                        }
+#pragma unroll
+                        for (int off = 16; off > 0; off >>= 1) tp = fmax(tp, __shfl_xor_sync(0xffffffffu, tp, off));
+#pragma unroll
+                        for (int e = 0; e < EPL; e++) {
+                            int oi = a_idx[warp][e * 32 + lane];
+                            if (oi > estar && a_sim[warp][e * 32 + lane] == tp) rlim = min(rlim, oi);
+                        }
+#pragma unroll
+                        for (int off = 16; off > 0; off >>= 1) rlim = min(rlim, __shfl_xor_sync(0xffffffffu, rlim, off));
+                        // nothing behind e*: R = everything, provided everything has been evaluated
+                        resolved = tp > -INFINITY || known_above == -INFINITY;
+                    }
+                }
+                int m_idx[EPL];
+                double m_sim[EPL];
+#pragma unroll
+                for (int e = 0; e < EPL; e++) {
+                    m_idx[e] = a_idx[warp][e * 32 + lane];
+                    m_sim[e] = a_sim[warp][e * 32 + lane];
+                    if (m_idx[e] >= 0 && !(m_sim[e] > known_above)) m_idx[e] = -1;   // outside the exactly known set
+                }
+                if (resolved) {
+                    double* rk = s_pred[warp];
+                    int* rv = s_coin[warp];
+                    __syncwarp();
+                    int m = 0;
+#pragma unroll
+                    for (int e = 0; e < EPL; e++) {
+                        bool in = m_idx[e] >= 0 && m_idx[e] < rlim && m_sim[e] >= tp;
+                        if (in) {
+                            int pos = 0;
+                            for (int t = 0; t < LISTN; t++) {
+                                int oi = a_idx[warp][t];
+                                double os = a_sim[warp][t];
+                                pos += oi >= 0 && os > known_above && oi < rlim && os >= tp && oi < m_idx[e];
+                            }
+                            rk[pos] = m_sim[e];
+                            rv[pos] = m_idx[e];
+                        }
+                        m += __popc(__ballot_sync(0xffffffffu, in));
+                    }
+                    __syncwarp();
+                    warp_lomuto_topn(rk, rv, m, keep);
+                    __syncwarp();
+                    if (lane < keep) { s_idx[warp][lane] = rv[lane]; s_sim[warp][lane] = rk[lane]; }
+                    __syncwarp();
+                } else if (lane == 0) {
+                    atomicAdd(&counters[CRX_CNT_TOPP_TIES], 1ull);   // kept: descending similarity, ties by row
+                }
+            }
+        }
     }
     if (nbr_rows) for (int j = lane; j < P; j += 32) nbr_rows[qrel * P + j] = j < keep ? s_idx[warp][j] : -1;
     if (nbr_sims) for (int j = lane; j < P; j += 32) nbr_sims[qrel * P + j] = j < keep ? s_sim[warp][j] : 0.0;
@@ -697,6 +838,8 @@ int crx_recommend_lsh(crx_ctx* c, const crx_lsh* t, const crx_points* queries, i
     // Tensor-core filter (tcgen05, tc_scan.cu): cosine tables whose L k-bit bucket ids pack into 32 bits and
     // whose sub-code histograms stay small.  CRX_NO_TC=1 forces the FP64 scan (tests compare the two paths).
     static const bool tc_off = getenv("CRX_NO_TC") != nullptr && getenv("CRX_NO_TC")[0] == '1';
+    // CRX_TIE_ORDER=0: skip the reconstruction of the reference's order among equal similarities (they are then counted)
+    static const int tie_order = !(getenv("CRX_TIE_ORDER") != nullptr && getenv("CRX_TIE_ORDER")[0] == '0');
     const bool use_tc = !tc_off && t->metric == CRX_COSINE && t->k * L <= 32 && L <= 8 &&
                         pow(1.0 + (double)(1 << t->k), (double)L) <= (double)(1 << 24);
     if (use_tc) {
@@ -818,10 +961,10 @@ int crx_recommend_lsh(crx_ctx* c, const crx_lsh* t, const crx_points* queries, i
     do {                                                                                                                   \
         if (use_tc)                                                                                                        \
             rec_finalize_kernel<TQ, TB, TC_LIST, float><<<g, 128, 0, c->stream>>>(xqp, queries->ld, queries->sqn, queries->unknown, queries->mean, xbp, \
-                base->ld, base->sqn, base->mean, base->d, q_begin, nq, P, Nrec, tl_s.p, tl_i.p, nc.p, tc_unscale, 8e-6, o_recs.dev, o_rows.dev, o_sims.dev, c->counters); \
+                base->ld, base->sqn, base->mean, base->d, q_begin, nq, P, Nrec, tl_s.p, tl_i.p, nc.p, tc_unscale, 8e-6, o_recs.dev, o_rows.dev, o_sims.dev, c->counters, tie_order); \
         else                                                                                                               \
             rec_finalize_kernel<TQ, TB, LIST, double><<<g, 128, 0, c->stream>>>(xqp, queries->ld, queries->sqn, queries->unknown, queries->mean, xbp, \
-                base->ld, base->sqn, base->mean, base->d, q_begin, nq, P, Nrec, list_s.p, list_i.p, nc.p, 1.0, 1e-12, o_recs.dev, o_rows.dev, o_sims.dev, c->counters); \
+                base->ld, base->sqn, base->mean, base->d, q_begin, nq, P, Nrec, list_s.p, list_i.p, nc.p, 1.0, 1e-12, o_recs.dev, o_rows.dev, o_sims.dev, c->counters, tie_order); \
     } while (0)
         if (queries->x64 && base->x64) LAUNCH_F(double, double, queries->x64, base->x64);
         else if (queries->x64) LAUNCH_F(double, float, queries->x64, base->x32);

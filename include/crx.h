@@ -61,7 +61,10 @@ int crx_ctx_kernel_time(crx_ctx* ctx, const char* prefix, double* total_ms, int6
 /* near-boundary / fallback counters since the last reset (see DESIGN.md "exactness"):
  * [0] hash projections recomputed in double-double, [1] top-P queries that needed the exhaustive
  * re-scan, [2] k-means++ draws within tolerance of a prefix boundary, [3] PAM rows re-summed exactly,
- * [4] Lloyd points re-evaluated exactly, [5..7] reserved */
+ * [4] Lloyd points re-evaluated exactly, [5] top-P queries with equal similarities among the P best whose
+ * reference order (quicksort partition history) could not be reconstructed from the listed candidates: they are
+ * returned in descending similarity, ties by row, [6] top-P queries with equal similarities among the P best (all),
+ * [7] reserved */
 int crx_ctx_counters(crx_ctx* ctx, int64_t out[8], int reset);
 
 /* ---- points: vector<CustVector<T>> (cust_vector.hpp:23-72) ---- */
