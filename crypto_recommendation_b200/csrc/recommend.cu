@@ -179,6 +179,7 @@ topp_scan_kernel(const TQ* __restrict__ xq, int ldq, const double* __restrict__ 
 // step is done literally by one lane.  Otherwise (a) is a stable compaction done by the whole warp with ballots.
 // A range whose keys all equal the pivot is left untouched by the literal algorithm and is skipped.
 // ------------------------------------------------------------------------------------------------
+template <int NT = 4>   // n <= 32 * NT
 __device__ __forceinline__ void warp_lomuto_topn(double* key, int* val, int n, int need) {
     const int lane = threadIdx.x & 31;
     const unsigned lt = (1u << lane) - 1u;
@@ -191,13 +192,13 @@ __device__ __forceinline__ void warp_lomuto_topn(double* key, int* val, int n, i
         while (lo < hi && lo < need) {
             const double pivot = key[hi];
             const int m = hi - lo;  // elements in front of the pivot
-            double kk[4];
-            int vv[4];
-            unsigned ge[4];
+            double kk[NT];
+            int vv[NT];
+            unsigned ge[NT];
             bool alleq = true;
             int cnt = 0;
 #pragma unroll
-            for (int t = 0; t < 4; t++) {
+            for (int t = 0; t < NT; t++) {
                 int e = t * 32 + lane;
                 bool in = e < m;
                 kk[t] = in ? key[lo + e] : 0.0;
@@ -234,7 +235,7 @@ __device__ __forceinline__ void warp_lomuto_topn(double* key, int* val, int n, i
                 __syncwarp();
                 int base = 0;
 #pragma unroll
-                for (int t = 0; t < 4; t++) {
+                for (int t = 0; t < NT; t++) {
                     if ((ge[t] >> lane) & 1u) {
                         int dst = lo + base + __popc(ge[t] & lt);
                         key[dst] = kk[t];
@@ -489,24 +490,28 @@ rec_finalize_kernel(const TQ* __restrict__ xq, int ldq, const double* __restrict
                     double* rk = s_pred[warp];
                     int* rv = s_coin[warp];
                     __syncwarp();
+                    // R in row order: position = number of members with a smaller row
+                    unsigned mem[EPL];
+                    int pos[EPL];
                     int m = 0;
 #pragma unroll
                     for (int e = 0; e < EPL; e++) {
-                        bool in = m_idx[e] >= 0 && m_idx[e] < rlim && m_sim[e] >= tp;
-                        if (in) {
-                            int pos = 0;
-                            for (int t = 0; t < LISTN; t++) {
-                                int oi = a_idx[warp][t];
-                                double os = a_sim[warp][t];
-                                pos += oi >= 0 && os > known_above && oi < rlim && os >= tp && oi < m_idx[e];
-                            }
-                            rk[pos] = m_sim[e];
-                            rv[pos] = m_idx[e];
-                        }
-                        m += __popc(__ballot_sync(0xffffffffu, in));
+                        mem[e] = __ballot_sync(0xffffffffu, m_idx[e] >= 0 && m_idx[e] < rlim && m_sim[e] >= tp);
+                        pos[e] = 0;
+                        m += __popc(mem[e]);
                     }
+#pragma unroll
+                    for (int f = 0; f < EPL; f++)
+                        for (unsigned left = mem[f]; left; left &= left - 1) {
+                            int oi = a_idx[warp][f * 32 + __ffs(left) - 1];
+#pragma unroll
+                            for (int e = 0; e < EPL; e++) pos[e] += oi < m_idx[e];
+                        }
+#pragma unroll
+                    for (int e = 0; e < EPL; e++)
+                        if ((mem[e] >> lane) & 1u) { rk[pos[e]] = m_sim[e]; rv[pos[e]] = m_idx[e]; }
                     __syncwarp();
-                    warp_lomuto_topn(rk, rv, m, keep);
+                    warp_lomuto_topn<EPL>(rk, rv, m, keep);
                     __syncwarp();
                     if (lane < keep) { s_idx[warp][lane] = rv[lane]; s_sim[warp][lane] = rk[lane]; }
                     __syncwarp();
