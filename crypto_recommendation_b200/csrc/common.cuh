@@ -190,9 +190,10 @@ static inline int crx_grid(int64_t work, int block) { return (int)((work + block
 //
 // The reference is strict (non-fused) double arithmetic in index order, except its dot product,
 // which accumulates double-rounded products in x87 extended precision.  The helpers below
-// reproduce the former bit for bit (no FMA contraction: explicit __d*_rn intrinsics) and compute
-// the latter with a compensated ("dot2") algorithm whose result is the correctly rounded true
-// value in all but ~2^-50 of the cases -- tighter than the x87 value itself.
+// reproduce the former bit for bit (no FMA contraction: explicit __d*_rn intrinsics) and the
+// latter by emulating the 64-bit-mantissa accumulator (x87.cuh: dot_x87 / cos_sim_x87, bit-identical
+// to the long double code).  The compensated "dot2" product only decides hash signs / floors that
+// fall inside the error bound of the fast projection (hash.cu).
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ double ldv(const float* p, int i) { return (double)p[i]; }
 __device__ __forceinline__ double ldv(const double* p, int i) { return p[i]; }
@@ -242,13 +243,6 @@ __device__ __forceinline__ void dot2(const TA* __restrict__ a, const TB* __restr
     }
     two_sum(s, c, hi, lo);
 }
-template <typename TA, typename TB>
-__device__ __forceinline__ double dot_accurate(const TA* __restrict__ a, const TB* __restrict__ b, int d) {
-    double hi, lo;
-    dot2(a, b, d, hi, lo);
-    return hi;
-}
-
 template <typename TA, typename TB>
 __device__ __forceinline__ X87 dot_x87(const TA* __restrict__ a, const TB* __restrict__ b, int d) {
     X87 acc = {0.0, 0.0};
