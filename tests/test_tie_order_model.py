@@ -78,3 +78,18 @@ def test_row_order_fallback_is_not_the_reference_order(port):
     assert sorted(range(8), key=lambda j: (-s[j], j)) != rows.tolist()
     got, kind = model(port, s.tolist(), 5, 64)
     assert got == [6, 1, 3, 2, 5] and kind in ("tail", "all", "plateau")
+
+
+def test_rule_with_unbounded_lists_always_resolves(port):
+    """With every candidate known (what a second, targeted pass over the counted queries would provide: DESIGN.md
+    section 9) the rule reproduces the full sort for EVERY query: nothing is left to count."""
+    rng = np.random.default_rng(12)
+    for it in range(3000):
+        n = int(rng.integers(1, 600))
+        P = int(rng.integers(1, 33))
+        levels = int(rng.choice([2, 5, 20, 200, 100000]))
+        s = rng.integers(0, levels + 1, n).astype(np.float64) / levels
+        _, full = port.quicksort(s, np.arange(n, dtype=np.int32))
+        got, kind = model(port, s.tolist(), P, 10 ** 9)
+        assert got is not None, kind
+        assert got == full[:min(P, n)].tolist(), (kind, n, P, levels)
