@@ -29,7 +29,7 @@ SYMBOLS = [
     "crx_cube_vertex_ids", "crx_get_hypercube_combined_buckets", "crx_get_num_hamming_dist_from",
     "crx_rand_selection", "crx_k_means_pp", "crx_lloyds_assignment", "crx_lloyds_for_remaining",
     "crx_lsh_range_assignment", "crx_cube_range_assignment", "crx_cluster_sums", "crx_k_means_finish",
-    "crx_k_means", "crx_pam_lloyds", "crx_silhouette_cluster", "crx_recommend_lsh", "crx_recommend_cluster",
+    "crx_k_means", "crx_pam_lloyds", "crx_silhouette_cluster", "crx_recommend_lsh", "crx_recommend_lsh_status", "crx_recommend_cluster",
     "crx_parallel_quickSort", "crx_get_P_closest", "crx_get_top_N_recom", "crx_lsh_hash_vector",
     "crx_user_vectors_build",
     "crx_k_means_pp_sharded", "crx_k_means_sharded", "crx_pam_lloyds_sharded", "crx_silhouette_cluster_sharded",
@@ -450,9 +450,13 @@ def silhouette_cluster(ctx, pts, labels, centroids, metric_type, comm=None):
 
 
 # ---- recommendation (crypto_rec.hpp) ------------------------------------------------------------------
+Q_EXACT, Q_PLATEAU, Q_TIE_ORDER = 0, 1, 2
+
+
 def recommend_lsh(ctx, tables, P, Nrec, queries=None, q_begin=0, q_end=None, out=None, want=("recs", "nbr_rows", "nbr_sims", "ncand")):
     """The per-user loop of main.cpp:159-170 (queries=None) / 205-216 (queries = other users).
-    out: optional dict of preallocated outputs (numpy or CUDA tensors, all in the same memory)."""
+    out: optional dict of preallocated outputs (numpy or CUDA tensors, all in the same memory).
+    "status" in want (or in out): per-query Q_EXACT / Q_PLATEAU / Q_TIE_ORDER through crx_recommend_lsh_status."""
     nqtot = tables.pts.n if queries is None else queries.n
     if q_end is None:
         q_end = nqtot
@@ -463,8 +467,15 @@ def recommend_lsh(ctx, tables, P, Nrec, queries=None, q_begin=0, q_end=None, out
         if "nbr_rows" in want: out["nbr_rows"] = np.zeros((nq, P), np.int32)
         if "nbr_sims" in want: out["nbr_sims"] = np.zeros((nq, P))
         if "ncand" in want: out["ncand"] = np.zeros(nq, np.int32)
+        if "status" in want: out["status"] = np.zeros(nq, np.int32)
     mems = {_ptr(v)[1] for v in out.values()}
     assert len(mems) == 1
+    if "status" in out:
+        _check(lib().crx_recommend_lsh_status(ctx.h, tables.h, queries.h if queries is not None else None, ctypes.c_int64(q_begin),
+                                              ctypes.c_int64(q_end), int(P), int(Nrec), _ptr(out.get("recs"))[0],
+                                              _ptr(out.get("nbr_rows"))[0], _ptr(out.get("nbr_sims"))[0], _ptr(out.get("ncand"))[0],
+                                              _ptr(out["status"])[0], mems.pop()))
+        return out
     _check(lib().crx_recommend_lsh(ctx.h, tables.h, queries.h if queries is not None else None, ctypes.c_int64(q_begin),
                                    ctypes.c_int64(q_end), int(P), int(Nrec), _ptr(out.get("recs"))[0], _ptr(out.get("nbr_rows"))[0],
                                    _ptr(out.get("nbr_sims"))[0], _ptr(out.get("ncand"))[0], mems.pop()))

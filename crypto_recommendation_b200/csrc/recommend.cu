@@ -263,7 +263,7 @@ rec_finalize_kernel(const TQ* __restrict__ xq, int ldq, const double* __restrict
                     const double* __restrict__ mean_b, int D, int64_t q_begin, int64_t nq, int P, int Nrec,
                     const TS* __restrict__ list_s, const int32_t* __restrict__ list_i, const int32_t* __restrict__ ncand,
                     double approx_scale, double approx_eps, int32_t* __restrict__ recs, int32_t* __restrict__ nbr_rows,
-                    double* __restrict__ nbr_sims, unsigned long long* counters, int tie_order) {
+                    double* __restrict__ nbr_sims, unsigned long long* counters, int tie_order, int32_t* __restrict__ qstatus) {
     constexpr int EPL = LISTN / 32;  // list entries per lane
     constexpr int QW = 4;            // queries (warps) per block
     __shared__ int a_idx[QW][LISTN];
@@ -380,17 +380,20 @@ rec_finalize_kernel(const TQ* __restrict__ xq, int ldq, const double* __restrict
     int nc = ncand[qrel];
     // certification: every candidate outside the list has an approximate similarity <= the smallest
     // approximate one in it; the exact P-th best must clear that by more than the filter's error
+    int status = CRX_Q_EXACT;
     if (keep > 0) {
         const double floor_ = floor_s * approx_scale;
         const double unlisted = floor_s > -INFINITY ? floor_ + approx_eps * fmax(1.0, fabs(floor_)) : -INFINITY;
         const double pth = s_sim[warp][keep - 1];
         if (!(pth > unlisted)) {
+            status = CRX_Q_PLATEAU;
             if (lane == 0) atomicAdd(&counters[CRX_CNT_TOPP_RESCAN], 1ull);
         } else {
             bool t = false;
 #pragma unroll
             for (int e = 0; e < EPL; e++) t |= tied[e] && a_sim[warp][e * 32 + lane] >= pth;
             const bool any_tie = __any_sync(0xffffffffu, t);
+            if (any_tie && !tie_order) status = CRX_Q_TIE_ORDER;
             if (any_tie && lane == 0) {
                 atomicAdd(&counters[CRX_CNT_TOPP_TIED], 1ull);
                 if (!tie_order) atomicAdd(&counters[CRX_CNT_TOPP_TIES], 1ull);
@@ -515,12 +518,14 @@ rec_finalize_kernel(const TQ* __restrict__ xq, int ldq, const double* __restrict
                     __syncwarp();
                     if (lane < keep) { s_idx[warp][lane] = rv[lane]; s_sim[warp][lane] = rk[lane]; }
                     __syncwarp();
-                } else if (lane == 0) {
-                    atomicAdd(&counters[CRX_CNT_TOPP_TIES], 1ull);   // kept: descending similarity, ties by row
+                } else {
+                    status = CRX_Q_TIE_ORDER;   // kept: descending similarity, ties by row
+                    if (lane == 0) atomicAdd(&counters[CRX_CNT_TOPP_TIES], 1ull);
                 }
             }
         }
     }
+    if (qstatus && lane == 0) qstatus[qrel] = status;
     if (nbr_rows) for (int j = lane; j < P; j += 32) nbr_rows[qrel * P + j] = j < keep ? s_idx[warp][j] : -1;
     if (nbr_sims) for (int j = lane; j < P; j += 32) nbr_sims[qrel * P + j] = j < keep ? s_sim[warp][j] : 0.0;
     if (!recs) return;
@@ -805,8 +810,8 @@ __global__ void sq_sizes_kernel(const int32_t* __restrict__ off, int ngroups, do
 
 extern "C" {
 
-int crx_recommend_lsh(crx_ctx* c, const crx_lsh* t, const crx_points* queries, int64_t q_begin, int64_t q_end, int P,
-                      int Nrec, int32_t* recs, int32_t* nbr_rows, double* nbr_sims, int32_t* ncand, int mem) {
+static int recommend_lsh_impl(crx_ctx* c, const crx_lsh* t, const crx_points* queries, int64_t q_begin, int64_t q_end, int P,
+                              int Nrec, int32_t* recs, int32_t* nbr_rows, double* nbr_sims, int32_t* ncand, int32_t* status, int mem) {
     CRX_REQUIRE(c && t, "NULL argument");
     const crx_points* base = t->pts;
     bool self = queries == nullptr || queries == base;
@@ -953,8 +958,9 @@ int crx_recommend_lsh(crx_ctx* c, const crx_lsh* t, const crx_points* queries, i
             }
         }
     }
-    IoBuf<int32_t> o_recs, o_rows, o_nc;
+    IoBuf<int32_t> o_recs, o_rows, o_nc, o_status;
     IoBuf<double> o_sims;
+    CRX_TRY(o_status.bind(c, status, (size_t)nq, mem, false));
 
     CRX_TRY(o_recs.bind(c, recs, (size_t)nq * Nrec, mem, false));
     CRX_TRY(o_rows.bind(c, nbr_rows, (size_t)nq * P, mem, false));
@@ -966,10 +972,10 @@ int crx_recommend_lsh(crx_ctx* c, const crx_lsh* t, const crx_points* queries, i
     do {                                                                                                                   \
         if (use_tc)                                                                                                        \
             rec_finalize_kernel<TQ, TB, TC_LIST, float><<<g, 128, 0, c->stream>>>(xqp, queries->ld, queries->sqn, queries->unknown, queries->mean, xbp, \
-                base->ld, base->sqn, base->mean, base->d, q_begin, nq, P, Nrec, tl_s.p, tl_i.p, nc.p, tc_unscale, 8e-6, o_recs.dev, o_rows.dev, o_sims.dev, c->counters, tie_order); \
+                base->ld, base->sqn, base->mean, base->d, q_begin, nq, P, Nrec, tl_s.p, tl_i.p, nc.p, tc_unscale, 8e-6, o_recs.dev, o_rows.dev, o_sims.dev, c->counters, tie_order, o_status.dev); \
         else                                                                                                               \
             rec_finalize_kernel<TQ, TB, LIST, double><<<g, 128, 0, c->stream>>>(xqp, queries->ld, queries->sqn, queries->unknown, queries->mean, xbp, \
-                base->ld, base->sqn, base->mean, base->d, q_begin, nq, P, Nrec, list_s.p, list_i.p, nc.p, 1.0, 1e-12, o_recs.dev, o_rows.dev, o_sims.dev, c->counters, tie_order); \
+                base->ld, base->sqn, base->mean, base->d, q_begin, nq, P, Nrec, list_s.p, list_i.p, nc.p, 1.0, 1e-12, o_recs.dev, o_rows.dev, o_sims.dev, c->counters, tie_order, o_status.dev); \
     } while (0)
         if (queries->x64 && base->x64) LAUNCH_F(double, double, queries->x64, base->x64);
         else if (queries->x64) LAUNCH_F(double, float, queries->x64, base->x32);
@@ -984,8 +990,18 @@ int crx_recommend_lsh(crx_ctx* c, const crx_lsh* t, const crx_points* queries, i
     CRX_TRY(o_recs.flush());
     CRX_TRY(o_rows.flush());
     CRX_TRY(o_sims.flush());
+    CRX_TRY(o_status.flush());
     if (mem == CRX_HOST) CRX_CUDA(cudaStreamSynchronize(c->stream));
     return CRX_OK;
+}
+
+int crx_recommend_lsh(crx_ctx* c, const crx_lsh* t, const crx_points* queries, int64_t q_begin, int64_t q_end, int P,
+                      int Nrec, int32_t* recs, int32_t* nbr_rows, double* nbr_sims, int32_t* ncand, int mem) {
+    return recommend_lsh_impl(c, t, queries, q_begin, q_end, P, Nrec, recs, nbr_rows, nbr_sims, ncand, nullptr, mem);
+}
+int crx_recommend_lsh_status(crx_ctx* c, const crx_lsh* t, const crx_points* queries, int64_t q_begin, int64_t q_end, int P,
+                             int Nrec, int32_t* recs, int32_t* nbr_rows, double* nbr_sims, int32_t* ncand, int32_t* status, int mem) {
+    return recommend_lsh_impl(c, t, queries, q_begin, q_end, P, Nrec, recs, nbr_rows, nbr_sims, ncand, status, mem);
 }
 
 int crx_recommend_cluster(crx_ctx* c, const crx_points* users, const int32_t* labels, int lmem, int K,

@@ -208,6 +208,15 @@ int crx_cube_range_assignment_sharded(crx_ctx* ctx, const crx_points* input_vect
 int crx_recommend_lsh(crx_ctx* ctx, const crx_lsh* lsh_hashtables, const crx_points* queries, int64_t q_begin,
                       int64_t q_end, int P, int Nrec, int32_t* recs, int32_t* nbr_rows, double* nbr_sims,
                       int32_t* ncand, int mem);
+/* The same call with a per-query status (the per-query form of counters [1] and [5]): status[q] = CRX_Q_EXACT when the
+ * neighbour list is the reference's, order of equal similarities included; CRX_Q_PLATEAU when more equal similarities
+ * reach the P-th place than the candidate list of the query holds; CRX_Q_TIE_ORDER when equal similarities among the P
+ * best come back ordered by row because the reference's order could not be rebuilt.  A caller that needs the literal
+ * result for those queries runs crx_get_P_closest on them. */
+enum { CRX_Q_EXACT = 0, CRX_Q_PLATEAU = 1, CRX_Q_TIE_ORDER = 2 };
+int crx_recommend_lsh_status(crx_ctx* ctx, const crx_lsh* lsh_hashtables, const crx_points* queries, int64_t q_begin,
+                             int64_t q_end, int P, int Nrec, int32_t* recs, int32_t* nbr_rows, double* nbr_sims,
+                             int32_t* ncand, int32_t* status /* [nq] */, int mem);
 /* neighbours = all rows of `users` with labels == qlabels[q]; get_top_N_recom without similarities
  * (crypto_rec.hpp:328).  queries NULL => users themselves with qlabels = labels. */
 int crx_recommend_cluster(crx_ctx* ctx, const crx_points* users, const int32_t* labels, int lmem, int K,

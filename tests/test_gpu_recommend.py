@@ -7,6 +7,7 @@ from crypto_recommendation_b200 import capi, synth
 from helpers import assert_float_close, topp_compare
 
 pytestmark = pytest.mark.gpu
+WANT = ("recs", "nbr_rows", "nbr_sims", "ncand", "status")
 
 
 @pytest.fixture(autouse=True)
@@ -33,6 +34,11 @@ def check_rec(ctx, out, ref_out, max_soft_frac=0.0):
     print("check_rec: %d of %d queries differ only inside tie groups (%.2f%%); the engine counted %d unresolved (allowed %.0f%%)"
           % (soft, nq, 100.0 * soft / nq, counted, 100 * max_soft_frac))
     assert soft <= counted, "%d queries differ inside tie groups but only %d were counted as unresolved" % (soft, counted)
+    if "status" in out:   # per-query form of the same statement: a query that differs from the oracle is flagged
+        differs = ~np.all(out["nbr_rows"] == nbr, axis=1)
+        flagged = out["status"] != capi.Q_EXACT
+        assert not (differs & ~flagged).any(), "queries %s differ but carry status EXACT" % np.flatnonzero(differs & ~flagged)[:5]
+        assert int(flagged.sum()) == counted, (int(flagged.sum()), counted)
     assert soft <= max_soft_frac * nq, "%d of %d queries differ by near-ties (allowed %.0f%%)" % (soft, nq, 100 * max_soft_frac)
     same = np.all(out["nbr_rows"] == nbr, axis=1)
     assert np.array_equal(out["nbr_sims"][same], sim[same]), "similarities are the reference's own doubles (x87 accumulation), bit for bit"
@@ -50,7 +56,7 @@ def test_golden_rec_A(ctx, golden):
     g = golden
     P = ctx.points(g["rec_U"], g["rec_unk"], g["rec_mean"])
     t = capi.LshTables(ctx, P, "cosine", 4, 5, 100, 0.4, 9001)
-    out = capi.recommend_lsh(ctx, t, 20, 5)
+    out = capi.recommend_lsh(ctx, t, 20, 5, want=WANT)
     check_rec(ctx, out, (g["rec_A_recs"], g["rec_A_nbr"], g["rec_A_sim"], g["rec_A_ncand"]), 0.12)
 
 
@@ -60,7 +66,7 @@ def test_golden_rec_B(ctx, golden):
     V = ctx.points(U[:25], unk[:25], mean[:25])
     Q = ctx.points(U[25:], unk[25:], mean[25:])
     t = capi.LshTables(ctx, V, "cosine", 4, 5, 100, 0.4, 9002)
-    out = capi.recommend_lsh(ctx, t, 20, 2, queries=Q)
+    out = capi.recommend_lsh(ctx, t, 20, 2, queries=Q, want=WANT)
     check_rec(ctx, out, (g["rec_B_recs"], g["rec_B_nbr"], g["rec_B_sim"], g["rec_B_ncand"]), 0.12)
 
 
@@ -77,14 +83,14 @@ def test_rec_lsh_cosine_oracle(ctx, port, dtype, n, P_, Nrec, k, L):
     U, unk, mean = synth.rating_users(n, 100, seed=300 + n, dtype=dtype)
     P = ctx.points(U, unk, mean)
     t = capi.LshTables(ctx, P, "cosine", k, L, 100, 0.4, 31337)
-    out = capi.recommend_lsh(ctx, t, P_, Nrec)
+    out = capi.recommend_lsh(ctx, t, P_, Nrec, want=WANT)
     ref = port.recommend_lsh(U.astype(np.float64), unk, mean, COSINE, k, L, 100, 0.4, P_, Nrec, 31337)
     check_rec(ctx, out, ref, 0.12)
     # query sub-range == slice of the full result (this is how queries are sharded across GPUs)
     lo, hi = n // 3, n // 3 + 257
     hi = min(hi, P.n)
-    part = capi.recommend_lsh(ctx, t, P_, Nrec, q_begin=lo, q_end=hi)
-    for key in ("recs", "nbr_rows", "ncand"):
+    part = capi.recommend_lsh(ctx, t, P_, Nrec, q_begin=lo, q_end=hi, want=WANT)
+    for key in ("recs", "nbr_rows", "ncand", "status"):
         assert np.array_equal(part[key], out[key][lo:hi]), key
 
 
@@ -96,7 +102,7 @@ def test_rec_lsh_normal_data_dense_and_table_modes(ctx, port):
     mean = np.where(unk == 0, X.astype(np.float64), 0).sum(1) / np.maximum(1, (unk == 0).sum(1))
     P = ctx.points(X, unk, mean)
     t = capi.LshTables(ctx, P, "cosine", 4, 5, 100, 0.4, 4711)
-    out = capi.recommend_lsh(ctx, t, 20, 5)
+    out = capi.recommend_lsh(ctx, t, 20, 5, want=WANT)
     ref = port.recommend_lsh(X.astype(np.float64), unk, mean, COSINE, 4, 5, 100, 0.4, 20, 5, 4711)
     assert check_rec(ctx, out, ref, 0.002) <= 2  # continuous data: ties are (next to) impossible
     frac = ref[3].mean() / 2500
@@ -109,7 +115,7 @@ def test_rec_lsh_euclidean_oracle(ctx, port, dtype):
     P = ctx.points(U, unk, mean)
     for (k, L, div, w) in [(4, 5, 100, 0.4), (2, 3, 10, 1.0)]:
         t = capi.LshTables(ctx, P, "euclidean", k, L, div, w, 2024)
-        out = capi.recommend_lsh(ctx, t, 20, 5)
+        out = capi.recommend_lsh(ctx, t, 20, 5, want=WANT)
         ref = port.recommend_lsh(U.astype(np.float64), unk, mean, EUCLIDEAN, k, L, div, w, 20, 5, 2024)
         check_rec(ctx, out, ref, 0.12)
 
@@ -120,7 +126,7 @@ def test_rec_B_external_queries(ctx, port):
     V = ctx.points(U[:nb], unk[:nb], mean[:nb])
     Q = ctx.points(U[nb:], unk[nb:], mean[nb:])
     t = capi.LshTables(ctx, V, "cosine", 4, 5, 100, 0.4, 808)
-    out = capi.recommend_lsh(ctx, t, 20, 2, queries=Q)
+    out = capi.recommend_lsh(ctx, t, 20, 2, queries=Q, want=WANT)
     ref = port.recommend_lsh(U[:nb], unk[:nb], mean[:nb], COSINE, 4, 5, 100, 0.4, 20, 2, 808, Xq=U[nb:], unknown_q=unk[nb:], mean_q=mean[nb:])
     check_rec(ctx, out, ref, 0.12)
 
@@ -148,7 +154,7 @@ def test_few_unknown_coins_pads_with_zero(ctx, port):
     unk[:, 3:] = 0
     P = ctx.points(U, unk, mean)
     t = capi.LshTables(ctx, P, "cosine", 4, 5, 100, 0.4, 5)
-    out = capi.recommend_lsh(ctx, t, 20, 5)
+    out = capi.recommend_lsh(ctx, t, 20, 5, want=WANT)
     ref = port.recommend_lsh(U, unk, mean, COSINE, 4, 5, 100, 0.4, 20, 5, 5)
     check_rec(ctx, out, ref, 0.12)
     assert (out["recs"][:, 3:] == 0).all()
