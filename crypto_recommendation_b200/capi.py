@@ -30,7 +30,7 @@ SYMBOLS = [
     "crx_rand_selection", "crx_k_means_pp", "crx_lloyds_assignment", "crx_lloyds_for_remaining",
     "crx_lsh_range_assignment", "crx_cube_range_assignment", "crx_cluster_sums", "crx_k_means_finish",
     "crx_k_means", "crx_pam_lloyds", "crx_silhouette_cluster", "crx_recommend_lsh", "crx_recommend_lsh_status", "crx_recommend_cluster",
-    "crx_parallel_quickSort", "crx_get_P_closest", "crx_get_top_N_recom", "crx_lsh_hash_vector",
+    "crx_parallel_quickSort", "crx_parallel_quickSort_topn", "crx_get_P_closest", "crx_get_top_N_recom", "crx_lsh_hash_vector",
     "crx_user_vectors_build",
     "crx_k_means_pp_sharded", "crx_k_means_sharded", "crx_pam_lloyds_sharded", "crx_silhouette_cluster_sharded",
     "crx_lsh_range_assignment_sharded", "crx_cube_range_assignment_sharded",
@@ -131,7 +131,7 @@ class Context:
         _check(lib().crx_ctx_counters(self.h, out, int(reset)))
         v = list(out)
         return {"hash_dd": v[0], "topp_uncertified": v[1], "kpp_near": v[2], "pam_exact": v[3], "lloyd_exact": v[4],
-                "topp_tie_order": v[5], "topp_tied": v[6]}
+                "topp_tie_order": v[5], "topp_tied": v[6], "topp_pass2": v[7]}
 
     # ---- vector<CustVector<T>> -------------------------------------------------------------
     def points(self, X, unknown=None, known_mean=None):
@@ -143,6 +143,12 @@ class Context:
         d = _np(ids, np.int32).copy()
         _check(lib().crx_parallel_quickSort(self.h, _ptr(s)[0], _ptr(d)[0], len(s)))
         return s, d
+
+    def parallel_quickSort_topn(self, sims, ids, need):
+        s = _np(sims, np.float64).copy()
+        d = _np(ids, np.int32).copy()
+        _check(lib().crx_parallel_quickSort_topn(self.h, _ptr(s)[0], _ptr(d)[0], len(s), int(need)))
+        return s[:need], d[:need]
 
 
 def get_num_hamming_dist_from(num, dist, min_bit, bits):

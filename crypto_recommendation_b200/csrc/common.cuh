@@ -52,7 +52,7 @@ struct crx_prof_rec {
     cudaEvent_t e0, e1;
 };
 
-enum { CRX_CNT_HASH_DD = 0, CRX_CNT_TOPP_RESCAN = 1, CRX_CNT_KPP_NEAR = 2, CRX_CNT_PAM_EXACT = 3, CRX_CNT_LLOYD_EXACT = 4, CRX_CNT_TOPP_TIES = 5, CRX_CNT_TOPP_TIED = 6 };
+enum { CRX_CNT_HASH_DD = 0, CRX_CNT_TOPP_RESCAN = 1, CRX_CNT_KPP_NEAR = 2, CRX_CNT_PAM_EXACT = 3, CRX_CNT_LLOYD_EXACT = 4, CRX_CNT_TOPP_TIES = 5, CRX_CNT_TOPP_TIED = 6, CRX_CNT_TOPP_PASS2 = 7 };
 
 struct crx_ctx {
     int device = 0;

@@ -6,6 +6,8 @@
 #include <algorithm>
 #include <climits>
 
+#include <cub/cub.cuh>
+
 #include "pair_tile.cuh"
 #include "rowwalk.cuh"
 #include "tables.cuh"
@@ -252,6 +254,8 @@ __device__ __forceinline__ void warp_lomuto_topn(double* key, int* val, int n, i
     __syncwarp();
 }
 
+#include "recommend_pass2.cuh"
+
 // ------------------------------------------------------------------------------------------------
 // K10: refine + predict + top-N.  One warp per query.  LISTN = 32 (FP64 scan, double scores) or
 // 64 (tensor-core filter, float scores scaled by `approx_scale`, filter error `approx_eps`).
@@ -263,7 +267,8 @@ rec_finalize_kernel(const TQ* __restrict__ xq, int ldq, const double* __restrict
                     const double* __restrict__ mean_b, int D, int64_t q_begin, int64_t nq, int P, int Nrec,
                     const TS* __restrict__ list_s, const int32_t* __restrict__ list_i, const int32_t* __restrict__ ncand,
                     double approx_scale, double approx_eps, int32_t* __restrict__ recs, int32_t* __restrict__ nbr_rows,
-                    double* __restrict__ nbr_sims, unsigned long long* counters, int tie_order, int32_t* __restrict__ qstatus) {
+                    double* __restrict__ nbr_sims, unsigned long long* counters, int tie_order, int32_t* __restrict__ qstatus,
+                    int pass2, P2Queue w2, P2Blocks blk) {
     constexpr int EPL = LISTN / 32;  // list entries per lane
     constexpr int QW = 4;            // queries (warps) per block
     __shared__ int a_idx[QW][LISTN];
@@ -387,7 +392,11 @@ rec_finalize_kernel(const TQ* __restrict__ xq, int ldq, const double* __restrict
         const double pth = s_sim[warp][keep - 1];
         if (!(pth > unlisted)) {
             status = CRX_Q_PLATEAU;
-            if (lane == 0) atomicAdd(&counters[CRX_CNT_TOPP_RESCAN], 1ull);
+            if (lane == 0) {
+                // second pass: every candidate that can reach the P-th best listed similarity
+                if (pass2) p2_emit(w2, (int)qrel, pth - 2.1 * approx_eps, 0x7fffffff, CRX_Q_PLATEAU << P2_KIND_SHIFT);
+                else atomicAdd(&counters[CRX_CNT_TOPP_RESCAN], 1ull);
+            }
         } else {
             bool t = false;
 #pragma unroll
@@ -396,7 +405,10 @@ rec_finalize_kernel(const TQ* __restrict__ xq, int ldq, const double* __restrict
             if (any_tie && !tie_order) status = CRX_Q_TIE_ORDER;
             if (any_tie && lane == 0) {
                 atomicAdd(&counters[CRX_CNT_TOPP_TIED], 1ull);
-                if (!tie_order) atomicAdd(&counters[CRX_CNT_TOPP_TIES], 1ull);
+                if (!tie_order) {
+                    if (pass2) p2_emit(w2, (int)qrel, pth - 2.1 * approx_eps, 0x7fffffff, CRX_Q_TIE_ORDER << P2_KIND_SHIFT);
+                    else atomicAdd(&counters[CRX_CNT_TOPP_TIES], 1ull);
+                }
             }
             if (any_tie && tie_order) {
                 // ---- equal similarities among the P best: reproduce the order of the reference's quicksort ----
@@ -519,8 +531,14 @@ rec_finalize_kernel(const TQ* __restrict__ xq, int ldq, const double* __restrict
                     if (lane < keep) { s_idx[warp][lane] = rv[lane]; s_sim[warp][lane] = rk[lane]; }
                     __syncwarp();
                 } else {
-                    status = CRX_Q_TIE_ORDER;   // kept: descending similarity, ties by row
-                    if (lane == 0) atomicAdd(&counters[CRX_CNT_TOPP_TIES], 1ull);
+                    status = CRX_Q_TIE_ORDER;   // kept: descending similarity, ties by row (second pass: the tail behind e*)
+                    if (lane == 0) {
+                        if (pass2) {
+                            int cx;
+                            double th = p2_tail_theta(blk, qrel, estar, pth, approx_eps, INFINITY, cx);
+                            p2_emit(w2, (int)qrel, th, cx, CRX_Q_TIE_ORDER << P2_KIND_SHIFT);
+                        } else atomicAdd(&counters[CRX_CNT_TOPP_TIES], 1ull);
+                    }
                 }
             }
         }
@@ -533,57 +551,9 @@ rec_finalize_kernel(const TQ* __restrict__ xq, int ldq, const double* __restrict
         for (int j = lane; j < Nrec; j += 32) recs[qrel * Nrec + j] = -1;
         return;
     }
-    double* s_pred_q = s_pred[warp];
-    int* s_coin_q = s_coin[warp];
-    // crypto_rec.hpp:281-306 for the unknown coins, neighbours in descending-similarity order.  This lane owns
-    // coins 4*lane .. 4*lane+3; every neighbour row is read as one 16-byte piece per lane.
-    double mq = mean_q[qrow];
-    double main_sum[4] = {0.0, 0.0, 0.0, 0.0}, abs_sum = 0.0;
-    for (int i0 = 0; i0 < keep; i0 += 4) {
-        double nv[4][4], nm[4], ns[4];
-#pragma unroll
-        for (int u = 0; u < 4; u++) {
-            int i = i0 + u;
-            nv[u][0] = nv[u][1] = nv[u][2] = nv[u][3] = 0.0;
-            ns[u] = 0.0; nm[u] = 0.0;
-            if (i < keep) {
-                int nb = s_idx[warp][i];
-                ns[u] = s_sim[warp][i];
-                nm[u] = mean_b[nb];
-                if (4 * lane < ldb) pt::ld4(xb + (size_t)nb * ldb + 4 * lane, nv[u]);
-            }
-        }
-#pragma unroll
-        for (int u = 0; u < 4; u++) {
-            if (i0 + u < keep) {
-                abs_sum = __dadd_rn(abs_sum, fabs(ns[u]));
-#pragma unroll
-                for (int t = 0; t < 4; t++) main_sum[t] = __dadd_rn(main_sum[t], __dmul_rn(ns[u], __dsub_rn(nv[u][t], nm[u])));
-            }
-        }
-    }
-    unsigned um[4];
-    bool unk[4];
-#pragma unroll
-    for (int t = 0; t < 4; t++) {
-        int j = 4 * lane + t;
-        unk[t] = j < D && unk_q[qrow * D + j] != 0;
-        um[t] = __ballot_sync(0xffffffffu, unk[t]);
-    }
-    unsigned lt = (1u << lane) - 1u;
-    int before = __popc(um[0] & lt) + __popc(um[1] & lt) + __popc(um[2] & lt) + __popc(um[3] & lt);
-    int nu = __popc(um[0]) + __popc(um[1]) + __popc(um[2]) + __popc(um[3]);
-#pragma unroll
-    for (int t = 0; t < 4; t++) {
-        if (unk[t]) {
-            s_pred_q[before] = __dadd_rn(__ddiv_rn(main_sum[t], abs_sum), mq);
-            s_coin_q[before] = 4 * lane + t;
-            before++;
-        }
-    }
-    __syncwarp();
-    warp_lomuto_topn(s_pred_q, s_coin_q, nu, Nrec);  // crypto_rec.hpp:320
-    for (int j = lane; j < Nrec; j += 32) recs[qrel * Nrec + j] = j < nu ? s_coin_q[j] : 0;  // resize(N) pads with coin 0
+    // crypto_rec.hpp:281-345 over the neighbours in their final order
+    predict_and_recommend<TB>(xb, ldb, mean_b, unk_q + qrow * D, mean_q[qrow], D, s_idx[warp], s_sim[warp], keep, Nrec, s_pred[warp],
+                              s_coin[warp], recs + qrel * Nrec);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -782,6 +752,14 @@ static int launch_quicksort(crx_ctx* c, double* d_sims, int32_t* d_ids, int n, i
     return CRX_OK;
 }
 
+// one warp: the warp-parallel form of the literal quicksort (recommend_pass2.cuh) on arrays in global memory
+__global__ void __launch_bounds__(32) warp_qs_kernel(double* sims, int32_t* ids, int n, int need) {
+    __shared__ int posge[128];
+    __shared__ double hk[128];
+    __shared__ int hv[128];
+    warp_qs_topn_big(sims, ids, n, need, posge, hk, hv);
+}
+
 __global__ void fill_lists_kernel(double* s, int32_t* i, int32_t* nc, int64_t nq) {
     int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t < nq * LIST) { s[t] = -INFINITY; i[t] = -1; }
@@ -806,6 +784,162 @@ __global__ void sq_sizes_kernel(const int32_t* __restrict__ off, int ngroups, do
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     if ((threadIdx.x & 31) == 0 && v != 0.0) atomicAdd(out, v);
+}
+
+// ------------------------------------------------------------------------------------------------
+// second pass of the batched top-P: rounds of collect -> evaluate -> resolve over the queued queries
+// (recommend_pass2.cuh) until every query carries the reference's list
+// ------------------------------------------------------------------------------------------------
+struct P2Host {
+    const crx_points* base; const crx_points* queries;
+    int64_t q_begin, nq;
+    int P, Nrec;
+    const int32_t* nc;
+    bool use_tc;
+    const TcOperand* opQ; const TcOperand* opB;        // tensor path: query / base operands
+    const uint32_t* qcode; const uint32_t* ccode; int k, L; bool dense;
+    const int32_t* qgid; int64_t qstride; const int32_t* cgid; int64_t cstride;   // SIMT path: group ids
+    double eps, unscale;
+    P2Blocks blocks;
+    int32_t* recs; int32_t* rows; double* sims; int32_t* status;
+};
+
+struct P2QueueBuf {
+    DevBuf<int32_t> q, colx, tries;
+    DevBuf<double> theta;
+    DevBuf<unsigned int> count;
+    int alloc(crx_ctx* c, size_t n) {
+        CRX_TRY(q.alloc(c, n)); CRX_TRY(colx.alloc(c, n)); CRX_TRY(tries.alloc(c, n)); CRX_TRY(theta.alloc(c, n)); CRX_TRY(count.alloc(c, 1));
+        CRX_CUDA(cudaMemsetAsync(count.p, 0, sizeof(unsigned int), c->stream));
+        return CRX_OK;
+    }
+    P2Queue view() const { P2Queue w; w.q = q.p; w.theta = theta.p; w.colx = colx.p; w.tries = tries.p; w.count = count.p; return w; }
+};
+
+__global__ void p2_trim_kernel(const int64_t* __restrict__ off, unsigned int n, int64_t limit, int32_t* __restrict__ ovf) {
+    unsigned int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && off[i + 1] > limit) ovf[i] = 1;
+}
+
+static int p2_scan_sizes(crx_ctx* c, const int32_t* count, const int32_t* ovf, unsigned int n, DevBuf<int64_t>& seg, DevBuf<int64_t>& off,
+                         DevBuf<char>& tmp, size_t& tmp_bytes, int64_t* h_total) {
+    { CRX_KERNEL(c, "p2_sizes"); p2_sizes_kernel<<<crx_grid((int64_t)n + 1, 256), 256, 0, c->stream>>>(count, ovf, n, seg.p); }
+    size_t need = 0;
+    CRX_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, need, seg.p, off.p, (int)(n + 1), c->stream));
+    if (need > tmp_bytes) { CRX_TRY(tmp.alloc(c, need)); tmp_bytes = need; }
+    CRX_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, need, seg.p, off.p, (int)(n + 1), c->stream));
+    CRX_CUDA(cudaMemcpyAsync(h_total, off.p + n, sizeof(int64_t), cudaMemcpyDeviceToHost, c->stream));
+    CRX_CUDA(cudaStreamSynchronize(c->stream));
+    return CRX_OK;
+}
+
+static int pass2_run(crx_ctx* c, const P2Host& h, P2QueueBuf* qa, P2QueueBuf* qb) {
+    const crx_points* base = h.base;
+    const crx_points* queries = h.queries;
+    const int64_t N = base->n;
+    P2QueueBuf* cur = qa;
+    P2QueueBuf* nxt = qb;
+    unsigned int n = 0;
+    CRX_CUDA(cudaMemcpyAsync(&n, cur->count.p, sizeof(n), cudaMemcpyDeviceToHost, c->stream));
+    CRX_CUDA(cudaStreamSynchronize(c->stream));
+    static const int max_rounds = getenv("CRX_P2_ROUNDS") ? atoi(getenv("CRX_P2_ROUNDS")) : 16;
+    for (int round = 0; n > 0 && round < max_rounds; round++) {
+        CRX_CUDA(cudaMemsetAsync(nxt->count.p, 0, sizeof(unsigned int), c->stream));
+        size_t free_b = 0, total_b = 0;
+        CRX_CUDA(cudaMemGetInfo(&free_b, &total_b));
+        DevBuf<int32_t> head, count, ovf, qrow_abs, cols, pool;
+        DevBuf<float> theta_f;
+        DevBuf<unsigned int> pool_next;
+        DevBuf<int64_t> seg, off;
+        DevBuf<char> tmp;
+        DevBuf<double> xs;
+        size_t tmp_bytes = 0;
+        int64_t total = 0;
+        CRX_TRY(count.alloc(c, n)); CRX_TRY(ovf.alloc(c, n)); CRX_TRY(seg.alloc(c, (size_t)n + 1)); CRX_TRY(off.alloc(c, (size_t)n + 1));
+        CRX_CUDA(cudaMemsetAsync(ovf.p, 0, (size_t)n * sizeof(int32_t), c->stream));
+        P2Queue w = cur->view();
+        // budget for the collected lists (4 B per entry in the pool, then 12 B per entry as rows + similarities)
+        const int64_t budget = (int64_t)std::max<size_t>(free_b / 2, (size_t)64 << 20);
+        if (h.use_tc) {
+            CRX_TRY(head.alloc(c, n)); CRX_TRY(qrow_abs.alloc(c, n)); CRX_TRY(theta_f.alloc(c, n)); CRX_TRY(pool_next.alloc(c, 1));
+            { CRX_KERNEL(c, "p2_prepare"); p2_prepare_kernel<<<crx_grid(n, 256), 256, 0, c->stream>>>(w, n, h.q_begin, 1.0 / h.unscale, theta_f.p, qrow_abs.p); }
+            TcOperand opA;
+            CRX_TRY(crx_tc_gather(c, *h.opQ, qrow_abs.p, n, &opA));
+            int64_t pool_bytes = std::min<int64_t>(budget / 4, (int64_t)n * (N * 4 + 4096) + ((int64_t)1 << 20));
+            unsigned int chunks = (unsigned int)std::min<int64_t>(pool_bytes / (TC_CHUNK * 4), (int64_t)0x7ffffff0);
+            CRX_TRY(pool.alloc(c, (size_t)chunks * TC_CHUNK));
+            CRX_CUDA(cudaMemsetAsync(pool_next.p, 0, sizeof(unsigned int), c->stream));
+            CRX_TRY(crx_tc_collect(c, opA, n, *h.opB, h.qcode, qrow_abs.p, h.ccode, h.k, h.L, h.dense, theta_f.p, w.colx, pool.p, pool_next.p, chunks,
+                                   head.p, count.p, ovf.p));
+        } else {
+            CRX_KERNEL(c, "p2_collect_simt");
+#define LAUNCH_S(TQ, TB, xqp, xbp, FILL)                                                                                          \
+    p2_collect_simt_kernel<TQ, TB, FILL><<<n, 256, 0, c->stream>>>(xqp, queries->ld, queries->sqn, xbp, base->ld, base->sqn, base->d, N, \
+        h.q_begin, w, h.L, h.qgid, h.qstride, h.cgid, h.cstride, count.p, ovf.p, off.p, cols.p)
+            if (queries->x64 && base->x64) LAUNCH_S(double, double, queries->x64, base->x64, false);
+            else if (queries->x64) LAUNCH_S(double, float, queries->x64, base->x32, false);
+            else if (base->x64) LAUNCH_S(float, double, queries->x32, base->x64, false);
+            else LAUNCH_S(float, float, queries->x32, base->x32, false);
+            CRX_CUDA(cudaGetLastError());
+        }
+        CRX_TRY(p2_scan_sizes(c, count.p, ovf.p, n, seg, off, tmp, tmp_bytes, &total));
+        if (total * 12 > budget) {   // too many rows for this round: the queries behind the budget wait for the next one
+            { CRX_KERNEL(c, "p2_trim"); p2_trim_kernel<<<crx_grid(n, 256), 256, 0, c->stream>>>(off.p, n, budget / 12, ovf.p); }
+            CRX_TRY(p2_scan_sizes(c, count.p, ovf.p, n, seg, off, tmp, tmp_bytes, &total));
+        }
+        CRX_TRY(cols.alloc(c, (size_t)total)); CRX_TRY(xs.alloc(c, (size_t)total));
+        if (h.use_tc) {
+            CRX_KERNEL(c, "p2_linearize");
+            p2_linearize_kernel<<<crx_grid(n, 8), 256, 0, c->stream>>>(pool.p, head.p, count.p, ovf.p, off.p, n, cols.p);
+            CRX_CUDA(cudaGetLastError());
+            pool.release();
+        } else {
+            CRX_KERNEL(c, "p2_collect_simt");
+            // (a trimmed query writes nothing: its segment is empty)
+            if (queries->x64 && base->x64) LAUNCH_S(double, double, queries->x64, base->x64, true);
+            else if (queries->x64) LAUNCH_S(double, float, queries->x64, base->x32, true);
+            else if (base->x64) LAUNCH_S(float, double, queries->x32, base->x64, true);
+            else LAUNCH_S(float, float, queries->x32, base->x32, true);
+#undef LAUNCH_S
+            CRX_CUDA(cudaGetLastError());
+        }
+        if (total > 0) {
+            CRX_KERNEL(c, "p2_exact");
+            const int64_t nblocks = total / 32;
+            int grid = (int)std::min<int64_t>((nblocks + 7) / 8, (int64_t)c->sm_count * 16);
+#define LAUNCH_E(TQ, TB, xqp, xbp) \
+    p2_exact_kernel<TQ, TB><<<grid, 256, 0, c->stream>>>(xqp, queries->ld, queries->sqn, xbp, base->ld, base->sqn, base->d, h.q_begin, w.q, off.p, n, nblocks, cols.p, xs.p)
+            if (queries->x64 && base->x64) LAUNCH_E(double, double, queries->x64, base->x64);
+            else if (queries->x64) LAUNCH_E(double, float, queries->x64, base->x32);
+            else if (base->x64) LAUNCH_E(float, double, queries->x32, base->x64);
+            else LAUNCH_E(float, float, queries->x32, base->x32);
+#undef LAUNCH_E
+            CRX_CUDA(cudaGetLastError());
+        }
+        {
+            CRX_KERNEL(c, "p2_resolve");
+            P2Resolve a;
+            memset(&a, 0, sizeof(a));
+            a.unk_q = queries->unknown; a.mean_q = queries->mean; a.mean_b = base->mean;
+            a.ldb = base->ld; a.D = base->d; a.P = h.P; a.Nrec = h.Nrec; a.q_begin = h.q_begin; a.ncand = h.nc;
+            a.cur = w; a.next = nxt->view(); a.n = n;
+            a.off = off.p; a.count = count.p; a.ovf = ovf.p; a.cols = cols.p; a.xs = xs.p;
+            a.eps = h.eps; a.blocks = h.blocks;
+            a.recs = h.recs; a.nbr_rows = h.rows; a.nbr_sims = h.sims; a.qstatus = h.status; a.counters = c->counters;
+            if (base->x64) p2_resolve_kernel<double><<<crx_grid(n, 4), 128, 0, c->stream>>>(base->x64, a);
+            else p2_resolve_kernel<float><<<crx_grid(n, 4), 128, 0, c->stream>>>(base->x32, a);
+            CRX_CUDA(cudaGetLastError());
+        }
+        std::swap(cur, nxt);
+        CRX_CUDA(cudaMemcpyAsync(&n, cur->count.p, sizeof(n), cudaMemcpyDeviceToHost, c->stream));
+        CRX_CUDA(cudaStreamSynchronize(c->stream));
+    }
+    if (n > 0) {
+        CRX_KERNEL(c, "p2_leftover");
+        p2_leftover_kernel<<<crx_grid(n, 256), 256, 0, c->stream>>>(cur->view(), n, c->counters);
+        CRX_CUDA(cudaGetLastError());
+    }
+    return CRX_OK;
 }
 
 extern "C" {
@@ -841,10 +975,21 @@ static int recommend_lsh_impl(crx_ctx* c, const crx_lsh* t, const crx_points* qu
     }
     DevBuf<double> list_s;
     DevBuf<int32_t> list_i, nc;
-    DevBuf<float> tl_s;
+    DevBuf<float> tl_s, blockmax;
     DevBuf<int32_t> tl_i;
+    DevBuf<uint32_t> ccode, qcode_buf;     // packed table codes: also read by the second pass
+    const uint32_t* qcode = nullptr;
+    TcOperand opB, opA;                    // split-fp16 operands: kept until the second pass is through
+    bool dense_cols = false;
     double tc_unscale = 1.0;
     CRX_TRY(nc.alloc(c, nq));
+    // second, targeted pass for the queries whose list does not decide the reference's order (recommend_pass2.cuh);
+    // CRX_TOPP_EXACT=0 leaves them counted instead (counters [1] and [5])
+    static const int pass2 = !(getenv("CRX_TOPP_EXACT") != nullptr && getenv("CRX_TOPP_EXACT")[0] == '0');
+    P2QueueBuf p2a, p2b;
+    P2Blocks blk;
+    memset(&blk, 0, sizeof(blk));
+    if (pass2) { CRX_TRY(p2a.alloc(c, (size_t)nq)); CRX_TRY(p2b.alloc(c, (size_t)nq)); }
     // Tensor-core filter (tcgen05, tc_scan.cu): cosine tables whose L k-bit bucket ids pack into 32 bits and
     // whose sub-code histograms stay small.  CRX_NO_TC=1 forces the FP64 scan (tests compare the two paths).
     static const bool tc_off = getenv("CRX_NO_TC") != nullptr && getenv("CRX_NO_TC")[0] == '1';
@@ -855,10 +1000,9 @@ static int recommend_lsh_impl(crx_ctx* c, const crx_lsh* t, const crx_points* qu
     if (use_tc) {
         int k = t->k;
         CRX_TRY(tl_s.alloc(c, (size_t)nq * TC_LIST)); CRX_TRY(tl_i.alloc(c, (size_t)nq * TC_LIST));
-        DevBuf<uint32_t> ccode, qcode_buf;
         CRX_TRY(ccode.alloc(c, N));
         { CRX_KERNEL(c, "pack_codes"); pack_codes_kernel<<<crx_grid(N, 256), 256, 0, c->stream>>>(t->bucket, N, N, k, L, ccode.p); }
-        const uint32_t* qcode = ccode.p;
+        qcode = ccode.p;
         if (!self) {
             CRX_TRY(qcode_buf.alloc(c, queries->n));
             { CRX_KERNEL(c, "pack_codes"); pack_codes_kernel<<<crx_grid(queries->n, 256), 256, 0, c->stream>>>(qgid_base, qstride, queries->n, k, L, qcode_buf.p); }
@@ -877,7 +1021,6 @@ static int recommend_lsh_impl(crx_ctx* c, const crx_lsh* t, const crx_points* qu
         { CRX_KERNEL(c, "subset_count"); subset_count_kernel<<<crx_grid(nq, 256), 256, 0, c->stream>>>(qcode, q_begin, nq, k, L, d_hoff.p, hist.p, nc.p); }
         CRX_CUDA(cudaGetLastError());
         // split-fp16 operands: unit rows times 2^10, so the accumulators hold 2^20 * cosine
-        TcOperand opB, opA;
         int st = crx_tc_prepare(c, base, 0, 10.0, &opB);
         if (st == CRX_OK && !self) st = crx_tc_prepare(c, queries, 0, 10.0, &opA);
         // candidate density decides the hot-loop variant of the filter
@@ -888,11 +1031,15 @@ static int recommend_lsh_impl(crx_ctx* c, const crx_lsh* t, const crx_points* qu
         unsigned long long h_tot = 0;
         CRX_CUDA(cudaMemcpyAsync(&h_tot, tot.p, sizeof(h_tot), cudaMemcpyDeviceToHost, c->stream));
         CRX_CUDA(cudaStreamSynchronize(c->stream));
-        bool dense_cols = (double)h_tot >= 0.9 * (double)nq * (double)N;
-        if (st == CRX_OK) st = crx_tc_topp(c, self ? opB : opA, q_begin, nq, opB, qcode, ccode.p, k, L, dense_cols, tl_s.p, tl_i.p);
+        dense_cols = (double)h_tot >= 0.9 * (double)nq * (double)N;
+        if (pass2) {
+            CRX_TRY(blockmax.alloc(c, (size_t)nq * 2 * TC_NBLK));
+            blk.blockmax = blockmax.p;
+            blk.nblk = crx_tc_blocks(N, blk.bt);
+            blk.unscale = ldexp(1.0, -20);
+        }
+        if (st == CRX_OK) st = crx_tc_topp(c, self ? opB : opA, q_begin, nq, opB, qcode, ccode.p, k, L, dense_cols, tl_s.p, tl_i.p, 3, blockmax.p);
         tc_unscale = ldexp(1.0, -20);
-        opB.free_all();
-        opA.free_all();
         if (st != CRX_OK) return st;
     } else {
         CRX_TRY(list_s.alloc(c, (size_t)nq * LIST)); CRX_TRY(list_i.alloc(c, (size_t)nq * LIST));
@@ -972,10 +1119,10 @@ static int recommend_lsh_impl(crx_ctx* c, const crx_lsh* t, const crx_points* qu
     do {                                                                                                                   \
         if (use_tc)                                                                                                        \
             rec_finalize_kernel<TQ, TB, TC_LIST, float><<<g, 128, 0, c->stream>>>(xqp, queries->ld, queries->sqn, queries->unknown, queries->mean, xbp, \
-                base->ld, base->sqn, base->mean, base->d, q_begin, nq, P, Nrec, tl_s.p, tl_i.p, nc.p, tc_unscale, 8e-6, o_recs.dev, o_rows.dev, o_sims.dev, c->counters, tie_order, o_status.dev); \
+                base->ld, base->sqn, base->mean, base->d, q_begin, nq, P, Nrec, tl_s.p, tl_i.p, nc.p, tc_unscale, 8e-6, o_recs.dev, o_rows.dev, o_sims.dev, c->counters, tie_order, o_status.dev, pass2, p2a.view(), blk); \
         else                                                                                                               \
             rec_finalize_kernel<TQ, TB, LIST, double><<<g, 128, 0, c->stream>>>(xqp, queries->ld, queries->sqn, queries->unknown, queries->mean, xbp, \
-                base->ld, base->sqn, base->mean, base->d, q_begin, nq, P, Nrec, list_s.p, list_i.p, nc.p, 1.0, 1e-12, o_recs.dev, o_rows.dev, o_sims.dev, c->counters, tie_order, o_status.dev); \
+                base->ld, base->sqn, base->mean, base->d, q_begin, nq, P, Nrec, list_s.p, list_i.p, nc.p, 1.0, 1e-12, o_recs.dev, o_rows.dev, o_sims.dev, c->counters, tie_order, o_status.dev, pass2, p2a.view(), blk); \
     } while (0)
         if (queries->x64 && base->x64) LAUNCH_F(double, double, queries->x64, base->x64);
         else if (queries->x64) LAUNCH_F(double, float, queries->x64, base->x32);
@@ -984,6 +1131,18 @@ static int recommend_lsh_impl(crx_ctx* c, const crx_lsh* t, const crx_points* qu
 #undef LAUNCH_F
     }
     CRX_CUDA(cudaGetLastError());
+    if (pass2) {
+        P2Host h;
+        memset(&h, 0, sizeof(h));
+        h.base = base; h.queries = queries; h.q_begin = q_begin; h.nq = nq; h.P = P; h.Nrec = Nrec; h.nc = nc.p; h.use_tc = use_tc;
+        h.opQ = self ? &opB : &opA; h.opB = &opB; h.qcode = qcode; h.ccode = ccode.p; h.k = t->k; h.L = L; h.dense = dense_cols;
+        h.qgid = qgid_base; h.qstride = qstride; h.cgid = t->gid; h.cstride = N;
+        h.eps = use_tc ? 8e-6 : 1e-12; h.unscale = tc_unscale; h.blocks = blk;
+        h.recs = o_recs.dev; h.rows = o_rows.dev; h.sims = o_sims.dev; h.status = o_status.dev;
+        CRX_TRY(pass2_run(c, h, &p2a, &p2b));
+    }
+    opB.free_all();
+    opA.free_all();
     if (ncand) {
         CRX_CUDA(cudaMemcpyAsync(ncand, nc.p, nq * sizeof(int32_t), mem == CRX_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice, c->stream));
     }
@@ -1101,6 +1260,23 @@ int crx_get_top_N_recom(crx_ctx* c, const crx_points* users, const int32_t* neig
     CRX_TRY(out.flush());
     CRX_CUDA(cudaStreamSynchronize(c->stream));
     return CRX_OK;
+}
+
+int crx_parallel_quickSort_topn(crx_ctx* c, double* sims, int32_t* ids, int n, int need) {
+    CRX_REQUIRE(c && sims && ids && n >= 0 && need >= 0 && need <= 126, "argument");
+    if (n == 0) return CRX_OK;
+    CRX_CUDA(cudaSetDevice(c->device));
+    IoBuf<double> s;
+    IoBuf<int32_t> d;
+    CRX_TRY(s.bind(c, sims, n, CRX_HOST, true));
+    CRX_TRY(d.bind(c, ids, n, CRX_HOST, true));
+    {
+        CRX_KERNEL(c, "warp_qs");
+        warp_qs_kernel<<<1, 32, 0, c->stream>>>(s.dev, d.dev, n, need);
+        CRX_CUDA(cudaGetLastError());
+    }
+    CRX_TRY(s.flush());
+    return d.flush();
 }
 
 int crx_parallel_quickSort(crx_ctx* c, double* sims, int32_t* ids, int n) {

@@ -1,0 +1,512 @@
+// recommend_pass2.cuh -- second, targeted pass of the batched top-P (included by recommend.cu).
+//
+// get_P_closest (crypto_rec.hpp:213-232) sorts ALL candidates of a user -- in row order (lsh_cube.hpp:96-104) -- with the
+// Lomuto quicksort of crypto_rec.hpp:235-277 and keeps the first P.  A partition keeps the ">= pivot" elements in their order,
+// so while that side still holds P elements only it is consumed: reading the similarities from the last row backwards, every
+// weak running maximum (r_j, v_j) is a pivot that merely drops what is below it, and after pivot j the sequence is
+//     S_j = { rows < r_j with similarity >= v_j }      (in row order).
+// The first P outputs of the literal sort of ANY S_j that is still in front of the first pivot with fewer than P elements on
+// its ">=" side equal the reference's.  With H = the P best (ties at the P-th place included) and e* = its last row, the last
+// such state is R = { rows < r' with similarity >= t' }, t' = the best similarity behind e*, r' = the first row behind e* that
+// reaches it (when e* itself is a minimum of H, H alone decides: DESIGN.md section 3).
+//
+// rec_finalize resolves a query when R lies inside its 64-entry list.  The others (R larger than the list: the chance is
+// ~P/64 per tied query; or a plateau of equal similarities larger than the list) come here:
+//   collect   every candidate whose filter score reaches a per-query threshold theta (tcgen05 threshold scan over the
+//             compacted queries, tc_scan.cu MODE_COLLECT; exact FP64 SIMT scan for tables the tensor path does not take),
+//   evaluate  the reference's own similarity (x87 accumulation) of every collected candidate,
+//   resolve   one warp per query: P-th best T_P, H, e*, (t', r') from the collected tail, R, and the literal quicksort on R
+//             (warp-parallel form of the Lomuto partition, below); a query whose collected set does not yet decide it is
+//             queued again with a lower threshold / an "everything behind e*" column bound.
+// Rounds repeat until the queue is empty: every query ends with the reference's list.
+#pragma once
+
+struct P2Queue {
+    int32_t* q;        // query row relative to q_begin
+    double* theta;     // collect candidates with exact similarity >= theta + 2 eps  (filter score >= theta)
+    int32_t* colx;     // ... and every candidate in a row > colx
+    int32_t* tries;
+    unsigned int* count;
+};
+
+__device__ __forceinline__ void p2_emit(const P2Queue& w, int q, double theta, int colx, int tries) {
+    unsigned int i = atomicAdd(w.count, 1u);
+    w.q[i] = q; w.theta[i] = theta; w.colx[i] = colx; w.tries[i] = tries;
+}
+
+struct P2Blocks {
+    const float* blockmax;   // [nq][2][TC_NBLK] filter units, or NULL
+    int nblk;
+    int bt[TC_NBLK + 1];
+    double unscale;          // filter units -> similarity
+};
+
+// threshold that certainly reaches the best candidate behind row `estar`: the largest filter score of the whole column blocks
+// behind it (an upper bound that a candidate normally attains), never above T_P.  No whole block behind e*: colx = e*.
+__device__ __forceinline__ double p2_tail_theta(const P2Blocks& b, int64_t qrel, int estar, double TP, double eps, double theta_old, int& colx) {
+    colx = 0x7fffffff;
+    double cap = fmin(TP - 2.02 * eps, theta_old);
+    if (b.blockmax != nullptr) {
+        const int tile = estar / TC_TILE_COLS;
+        float bm = -INFINITY;
+        bool any = false;
+        for (int j = 1; j < b.nblk; j++)
+            if (b.bt[j] > tile) {
+                any = true;
+                bm = fmaxf(bm, fmaxf(b.blockmax[(qrel * 2 + 0) * TC_NBLK + j], b.blockmax[(qrel * 2 + 1) * TC_NBLK + j]));
+            }
+        if (any && bm > -INFINITY) {
+            double th = (double)bm * b.unscale - 2.02 * eps;
+            if (th < theta_old - 0.5 * eps || theta_old == INFINITY) return fmin(th, cap);   // new information
+        }
+    }
+    colx = estar;
+    return cap;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Warp-parallel literal Lomuto quicksort (crypto_rec.hpp:235-277), first `need` positions final, arrays of any length in
+// shared or global memory.  One partition of [lo, hi], pivot = key[hi], cnt = #{>= pivot in front}, p = lo + cnt:
+//   * the ">=" elements land in [lo, p) in their order, the pivot at p;
+//   * the "<" elements: with q1 = the first of them and rho = #{>= behind q1} + 1, the swaps of the literal loop rotate the
+//     "<" block once per ">=" element met behind q1 and once more for the pivot.  In closed form: every "<" element at a
+//     position >= q1 + rho STAYS where it is, and the holes left there by ">=" elements (and the pivot's slot hi) receive the
+//     "<" elements of [q1, q1 + rho): hole number r (r-th ">=" element behind q1; the pivot slot is number rho) receives
+//     the content of position q1 + r - 1, which, when that position holds the r''-th ">=" element itself, is the content of
+//     hole r''.  (tests/test_qs_model.py checks this form against the literal loop.)
+//   * ranges that start at or beyond `need` are never consumed: when p + 1 >= need only the ">=" side is produced;
+//   * a pivot that is a minimum of its range stays in place together with all equal elements behind the last larger one.
+// `need` <= 126.  posge / hk / hv: per-warp scratch of 128 entries each.
+// ------------------------------------------------------------------------------------------------
+__device__ __noinline__ void warp_qs_topn_big(double* key, int* val, int n, int need, int* posge, double* hk, int* hv) {
+    const int lane = threadIdx.x & 31;
+    const unsigned lt = (1u << lane) - 1u;
+    int st_lo[128], st_hi[128];
+    int sp = 1;
+    st_lo[0] = 0; st_hi[0] = n - 1;
+    while (sp > 0) {
+        sp--;
+        int lo = st_lo[sp], hi = st_hi[sp];
+        while (lo < hi && lo < need) {
+            const double pivot = key[hi];
+            const int m = hi - lo;
+            int cnt = 0, lastgt = -1, q1 = 0x7fffffff;
+            bool alleq = true;
+            for (int base = lo; base < hi; base += 32) {
+                const int e = base + lane;
+                const bool in = e < hi;
+                const double k = in ? key[e] : 0.0;
+                const unsigned bg = __ballot_sync(0xffffffffu, in && k >= pivot);
+                const unsigned bgt = __ballot_sync(0xffffffffu, in && k > pivot);
+                const unsigned blt = __ballot_sync(0xffffffffu, in && !(k >= pivot));
+                alleq = alleq && __all_sync(0xffffffffu, !in || k == pivot);
+                cnt += __popc(bg);
+                if (bgt) lastgt = base + 31 - __clz(bgt);
+                if (blt && q1 == 0x7fffffff) q1 = base + __ffs(blt) - 1;
+            }
+            if (alleq) break;
+            if (cnt == m) { hi = lastgt; continue; }   // the pivot and its equals behind the last larger element stay
+            const int p = lo + cnt;
+            const int pv = val[hi];
+            const bool literal = p + 1 < need && p < hi;
+            int rho = 0;
+            if (literal) {
+                // ranks of the ">=" elements behind q1
+                int seen = 0;
+                for (int base = q1 + 1; base < hi; base += 32) {
+                    const int e = base + lane;
+                    const bool g = e < hi && key[e] >= pivot;
+                    const unsigned bg = __ballot_sync(0xffffffffu, g);
+                    if (g) { int r = seen + __popc(bg & lt) + 1; if (r < 127) posge[r] = e; }
+                    seen += __popc(bg);
+                }
+                rho = seen + 1;
+                if (lane == 0) posge[rho] = hi;
+                __syncwarp();
+                if (lane == 0) {
+                    int pp = 1;
+                    for (int r = 1; r <= rho; r++) {
+                        const int src = q1 + r - 1;
+                        const double ks = key[src];
+                        if (!(ks >= pivot)) { hk[r] = ks; hv[r] = val[src]; }
+                        else {
+                            while (posge[pp] < src) pp++;
+                            hk[r] = hk[pp]; hv[r] = hv[pp];
+                        }
+                    }
+                }
+                __syncwarp();
+            }
+            // stable compaction of the ">=" elements to [lo, p)
+            {
+                int done = 0;
+                for (int base = lo; base < hi; base += 32) {
+                    const int e = base + lane;
+                    const bool in = e < hi;
+                    const double k = in ? key[e] : 0.0;
+                    const int v = in ? val[e] : 0;
+                    const bool g = in && k >= pivot;
+                    const unsigned bg = __ballot_sync(0xffffffffu, g);
+                    __syncwarp();
+                    if (g) {
+                        const int dst = lo + done + __popc(bg & lt);
+                        if (dst != e) { key[dst] = k; val[dst] = v; }
+                    }
+                    done += __popc(bg);
+                    __syncwarp();
+                }
+            }
+            if (lane == 0) { key[p] = pivot; val[p] = pv; }
+            if (literal) {
+                for (int r = 1 + lane; r <= rho; r += 32)
+                    if (posge[r] > p) { key[posge[r]] = hk[r]; val[posge[r]] = hv[r]; }
+                __syncwarp();
+                if (sp < 128) { st_lo[sp] = p + 1; st_hi[sp] = hi; sp++; }
+            }
+            __syncwarp();
+            hi = p - 1;
+        }
+    }
+    __syncwarp();
+}
+
+// ------------------------------------------------------------------------------------------------
+// crypto_rec.hpp:281-345 for one query and its (<= 32) neighbours in s_idx / s_sim: weighted rating prediction of the unknown
+// coins (neighbours in the given order, the reference's sequential double operations) and the literal Lomuto top-N over them.
+// All 32 lanes of the warp; lane owns coins 4*lane .. 4*lane+3; every neighbour row is read as one 16-byte piece per lane.
+// ------------------------------------------------------------------------------------------------
+template <typename TB>
+__device__ __forceinline__ void predict_and_recommend(const TB* __restrict__ xb, int ldb, const double* __restrict__ mean_b,
+                                                      const uint8_t* __restrict__ unk_row, double mq, int D, const int* s_idx,
+                                                      const double* s_sim, int keep, int Nrec, double* s_pred_q, int* s_coin_q,
+                                                      int32_t* __restrict__ recs_row) {
+    const int lane = threadIdx.x & 31;
+    double main_sum[4] = {0.0, 0.0, 0.0, 0.0}, abs_sum = 0.0;
+    for (int i0 = 0; i0 < keep; i0 += 4) {
+        double nv[4][4], nm[4], ns[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            int i = i0 + u;
+            nv[u][0] = nv[u][1] = nv[u][2] = nv[u][3] = 0.0;
+            ns[u] = 0.0; nm[u] = 0.0;
+            if (i < keep) {
+                int nb = s_idx[i];
+                ns[u] = s_sim[i];
+                nm[u] = mean_b[nb];
+                if (4 * lane < ldb) pt::ld4(xb + (size_t)nb * ldb + 4 * lane, nv[u]);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            if (i0 + u < keep) {
+                abs_sum = __dadd_rn(abs_sum, fabs(ns[u]));
+#pragma unroll
+                for (int t = 0; t < 4; t++) main_sum[t] = __dadd_rn(main_sum[t], __dmul_rn(ns[u], __dsub_rn(nv[u][t], nm[u])));
+            }
+        }
+    }
+    unsigned um[4];
+    bool unk[4];
+#pragma unroll
+    for (int t = 0; t < 4; t++) {
+        int j = 4 * lane + t;
+        unk[t] = j < D && unk_row[j] != 0;
+        um[t] = __ballot_sync(0xffffffffu, unk[t]);
+    }
+    unsigned lt = (1u << lane) - 1u;
+    int before = __popc(um[0] & lt) + __popc(um[1] & lt) + __popc(um[2] & lt) + __popc(um[3] & lt);
+    int nu = __popc(um[0]) + __popc(um[1]) + __popc(um[2]) + __popc(um[3]);
+#pragma unroll
+    for (int t = 0; t < 4; t++) {
+        if (unk[t]) {
+            s_pred_q[before] = __dadd_rn(__ddiv_rn(main_sum[t], abs_sum), mq);
+            s_coin_q[before] = 4 * lane + t;
+            before++;
+        }
+    }
+    __syncwarp();
+    warp_lomuto_topn(s_pred_q, s_coin_q, nu, Nrec);  // crypto_rec.hpp:320
+    for (int j = lane; j < Nrec; j += 32) recs_row[j] = j < nu ? s_coin_q[j] : 0;  // resize(N) pads with coin 0
+}
+
+// ------------------------------------------------------------------------------------------------
+// round plumbing
+// ------------------------------------------------------------------------------------------------
+constexpr int P2_KIND_SHIFT = 16;   // tries = attempts | (status the query carried out of rec_finalize << 16)
+
+__global__ void p2_prepare_kernel(P2Queue w, unsigned int n, int64_t q_begin, double scale, float* __restrict__ theta_f,
+                                  int32_t* __restrict__ qrow_abs) {
+    unsigned int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double th = w.theta[i] * scale;
+    float f = (float)th;
+    if (isfinite(f)) f = f - fabsf(f) * 1.2e-7f - 1e-30f;   // never above the double threshold
+    theta_f[i] = f;
+    qrow_abs[i] = (int32_t)(q_begin + w.q[i]);
+}
+
+__global__ void p2_sizes_kernel(const int32_t* __restrict__ count, const int32_t* __restrict__ ovf, unsigned int n, int64_t* __restrict__ seg) {
+    unsigned int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i > n) return;
+    seg[i] = (i < n && !(ovf && ovf[i])) ? (((int64_t)count[i] + 31) / 32) * 32 : 0;
+}
+
+__global__ void p2_linearize_kernel(const int32_t* __restrict__ pool, const int32_t* __restrict__ head, const int32_t* __restrict__ count,
+                                    const int32_t* __restrict__ ovf, const int64_t* __restrict__ off, unsigned int n, int32_t* __restrict__ cols) {
+    unsigned int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    int lane = threadIdx.x & 31;
+    if (i >= n || ovf[i]) return;
+    const int total = count[i];
+    int32_t* out = cols + off[i];
+    int c = head[i], written = 0;
+    while (c >= 0 && written < total) {
+        const int32_t* ch = pool + (size_t)c * TC_CHUNK;
+        const int next = ch[0];
+        const int m = min(TC_CHUNK - 1, total - written);
+        for (int j = lane; j < m; j += 32) out[written + j] = ch[1 + j];
+        written += m;
+        c = next;
+    }
+    for (int j = total + lane; j < (total + 31) / 32 * 32; j += 32) out[j] = -1;
+}
+
+// plain FP64 filter for tables the tensor path does not take: one block per queued query, columns in order.
+// FILL = false: count[i] = number of passing candidates;  FILL = true: their rows, ascending, at cols[off[i] ...]
+template <typename TQ, typename TB, bool FILL>
+__global__ void __launch_bounds__(256)
+p2_collect_simt_kernel(const TQ* __restrict__ xq, int ldq, const double* __restrict__ sqn_q, const TB* __restrict__ xb, int ldb,
+                       const double* __restrict__ sqn_b, int D, int64_t nb, int64_t q_begin, P2Queue w, int L,
+                       const int32_t* __restrict__ qgid, int64_t qstride, const int32_t* __restrict__ cgid, int64_t cstride,
+                       int32_t* __restrict__ count, const int32_t* __restrict__ ovf, const int64_t* __restrict__ off,
+                       int32_t* __restrict__ cols) {
+    if (FILL && ovf[blockIdx.x]) return;   // waits for the next round (its segment is empty)
+    __shared__ double qv[128];
+    __shared__ int qg[MAXL];
+    __shared__ int wsum[8];
+    __shared__ int running;
+    const unsigned int i = blockIdx.x;
+    const int64_t qrow = q_begin + w.q[i];
+    const double theta = w.theta[i];
+    const int colx = w.colx[i];
+    for (int k = threadIdx.x; k < 128; k += 256) qv[k] = k < D ? (double)xq[qrow * ldq + k] : 0.0;
+    if (threadIdx.x < L) qg[threadIdx.x] = qgid[(size_t)threadIdx.x * qstride + qrow];
+    if (threadIdx.x == 0) running = 0;
+    __syncthreads();
+    const double qinv = 1.0 / sqrt(sqn_q[qrow]);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    int32_t* out = FILL ? cols + off[i] : nullptr;
+    for (int64_t c0 = 0; c0 < nb; c0 += 256) {
+        const int64_t c = c0 + threadIdx.x;
+        bool pass = false;
+        if (c < nb) {
+            bool match = false;
+            for (int l = 0; l < L; l++) { int g = cgid[(size_t)l * cstride + c]; match |= (g == qg[l] && g >= 0); }
+            if (match) {
+                double acc = 0.0;
+                const TB* row = xb + (size_t)c * ldb;
+                for (int k = 0; k < D; k++) acc = fma((double)row[k], qv[k], acc);
+                double s = acc * qinv / sqrt(sqn_b[c]);
+                pass = s >= theta || c > colx;
+            }
+        }
+        const unsigned bm = __ballot_sync(0xffffffffu, pass);
+        if (lane == 0) wsum[warp] = __popc(bm);
+        __syncthreads();
+        int before = running;
+        for (int x = 0; x < warp; x++) before += wsum[x];
+        if (FILL && pass) out[before + __popc(bm & ((1u << lane) - 1u))] = (int32_t)c;
+        __syncthreads();
+        if (threadIdx.x == 0) { int t = 0; for (int x = 0; x < 8; x++) t += wsum[x]; running += t; }
+        __syncthreads();
+    }
+    if (!FILL && threadIdx.x == 0) count[i] = running;
+    if (FILL) for (int j = running + threadIdx.x; j < (running + 31) / 32 * 32; j += 256) out[j] = -1;
+}
+
+// the reference's own similarity of every collected candidate (crypto_rec.hpp:220, cust_vector.hpp:160-174): a warp takes 32
+// consecutive entries (segments are padded to multiples of 32, so they belong to one query), each lane walks its row
+template <typename TQ, typename TB>
+__global__ void __launch_bounds__(256)
+p2_exact_kernel(const TQ* __restrict__ xq, int ldq, const double* __restrict__ sqn_q, const TB* __restrict__ xb, int ldb,
+                const double* __restrict__ sqn_b, int D, int64_t q_begin, const int32_t* __restrict__ wq, const int64_t* __restrict__ off,
+                unsigned int n, int64_t nblocks, const int32_t* __restrict__ cols, double* __restrict__ xs) {
+    __shared__ rw::WarpTile tiles[8];
+    __shared__ double qvec[8][128];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int64_t b = (int64_t)blockIdx.x * 8 + warp; b < nblocks; b += (int64_t)gridDim.x * 8) {
+        const int64_t base = b * 32;
+        // item = the last i with off[i] <= base  (off[n] = total > base)
+        unsigned int lo = 0, hi = n;
+        while (lo < hi) { unsigned int m = (lo + hi + 1) >> 1; if (off[m] <= base) lo = m; else hi = m - 1; }
+        const int64_t qrow = q_begin + wq[lo];
+        rw::stage_vector<TQ>(xq, ldq, qrow, qvec[warp]);
+        const int mine = cols[base + lane];
+        rw::Walk wk = rw::walk_rows<TB, CRX_COSINE>(xb, ldb, D, mine >= 0 ? (int64_t)mine : -1, qvec[warp], tiles[warp]);
+        double sim = -INFINITY;
+        if (mine >= 0) { X87 ip = {wk.a, wk.b}; sim = cos_sim_x87(ip, sqn_b[mine], sqn_q[qrow]); }
+        xs[base + lane] = sim;
+        __syncwarp();
+    }
+}
+
+struct P2Resolve {
+    const uint8_t* unk_q; const double* mean_q; const double* mean_b;
+    int ldb, D, P, Nrec;
+    int64_t q_begin;
+    const int32_t* ncand;
+    P2Queue cur, next;
+    unsigned int n;
+    const int64_t* off; const int32_t* count; const int32_t* ovf;
+    int32_t* cols; double* xs;
+    double eps;
+    P2Blocks blocks;
+    int32_t* recs; int32_t* nbr_rows; double* nbr_sims; int32_t* qstatus;
+    unsigned long long* counters;
+};
+
+template <typename TB>
+__global__ void __launch_bounds__(128)
+p2_resolve_kernel(const TB* __restrict__ xb, P2Resolve a) {
+    constexpr int QW = 4;
+    __shared__ int posge[QW][128];
+    __shared__ double hk[QW][128];
+    __shared__ int hv[QW][128];
+    __shared__ int s_idx[QW][32];
+    __shared__ double s_sim[QW][32];
+    __shared__ double s_pred[QW][128];
+    __shared__ int s_coin[QW][128];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const unsigned lt = (1u << lane) - 1u;
+    const unsigned int i = blockIdx.x * QW + warp;
+    if (i >= a.n) return;
+    const int qrel = a.cur.q[i];
+    const double theta = a.cur.theta[i];
+    const int colx = a.cur.colx[i];
+    const int tries = a.cur.tries[i];
+    const double eps = a.eps;
+    if (a.ovf && a.ovf[i]) {   // the chunk pool ran dry in this round: again (the next round has fewer lists to hold)
+        if (lane == 0) p2_emit(a.next, qrel, theta, colx, tries + 1);
+        return;
+    }
+    const int cnt = a.count[i];
+    double* key = a.xs + a.off[i];
+    int* val = a.cols + a.off[i];
+    const int nc = a.ncand[qrel];
+    const int keep = min(a.P, nc);
+    const bool complete = cnt >= nc;
+    const double kappa = theta + 1.05 * eps;   // every candidate with an exact similarity above kappa is in the list
+    const double lower = ldexp(64.0 * eps, 2 * min(tries & 0xffff, 8));
+    if (cnt < keep) {
+        if (lane == 0) p2_emit(a.next, qrel, (tries & 0xffff) > 8 ? -INFINITY : theta - lower, colx, tries + 1);
+        return;
+    }
+    // ---- T_P = the keep-th best similarity: sorted list of the best `keep`, one entry per lane
+    double mine = -INFINITY, thr = -INFINITY;
+    int filled = 0;
+    for (int base = 0; base < cnt; base += 32) {
+        const int e = base + lane;
+        const double k = e < cnt ? key[e] : -INFINITY;
+        unsigned want = __ballot_sync(0xffffffffu, e < cnt && k == k && (k > thr || filled < keep));
+        while (want) {
+            const int src = __ffs(want) - 1;
+            want &= want - 1;
+            const double x = __shfl_sync(0xffffffffu, k, src);
+            if (x > thr || filled < keep) {
+                const int pos = __popc(__ballot_sync(0xffffffffu, mine >= x));
+                const double up = __shfl_up_sync(0xffffffffu, mine, 1);
+                mine = lane < pos ? mine : (lane == pos ? x : up);
+                if (filled < keep) filled++;
+                thr = filled < keep ? -INFINITY : __shfl_sync(0xffffffffu, mine, keep - 1);
+            }
+        }
+    }
+    const double TP = __shfl_sync(0xffffffffu, mine, keep - 1);
+    if (!(TP > kappa) && !complete) {   // the P best are not all known yet
+        if (lane == 0) p2_emit(a.next, qrel, fmin(theta - lower, TP - 2.1 * eps), colx, tries + 1);
+        return;
+    }
+    // ---- H = { >= T_P }, e* = its last row
+    int idx_e = -1;
+    for (int base = 0; base < cnt; base += 32) {
+        const int e = base + lane;
+        const unsigned b = __ballot_sync(0xffffffffu, e < cnt && key[e] >= TP);
+        if (b) idx_e = base + 31 - __clz(b);
+    }
+    const int estar = val[idx_e];
+    const double s_estar = key[idx_e];
+    // ---- the tail behind e*: best known similarity and the first row that reaches it
+    const bool tail_all = complete || estar >= colx;
+    double tk = -INFINITY;
+    int te = 0x7fffffff;
+    for (int base = (idx_e + 1) & ~31; base < cnt; base += 32) {
+        const int e = base + lane;
+        if (e > idx_e && e < cnt) {
+            const double k = key[e];
+            if ((tail_all || k > kappa) && k > tk) { tk = k; te = e; }   // ascending e per lane: the first one is kept
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const double ok = __shfl_xor_sync(0xffffffffu, tk, o);
+        const int oe = __shfl_xor_sync(0xffffffffu, te, o);
+        if (ok > tk || (ok == tk && oe < te)) { tk = ok; te = oe; }
+    }
+    const bool found = te != 0x7fffffff;
+    double tp;
+    int rlim;   // R = entries e < rlim with key >= tp
+    if (s_estar == TP) {            // e* is a minimum of H: H alone decides (no candidate below T_P is ever consumed)
+        tp = TP; rlim = idx_e + 1;
+    } else if (!(tail_all || found)) {
+        if (lane == 0) {
+            int cx;
+            double th = p2_tail_theta(a.blocks, qrel, estar, TP, eps, theta, cx);
+            p2_emit(a.next, qrel, th, cx, tries + 1);
+        }
+        return;
+    } else if (!found) {            // no candidate behind e*: R = every candidate
+        if (!complete) { if (lane == 0) p2_emit(a.next, qrel, -INFINITY, 0x7fffffff, tries + 1); return; }
+        tp = -INFINITY; rlim = cnt;
+    } else {
+        tp = tk; rlim = te;
+        if (!(tp > kappa) && !complete) {   // t' is known, the rows in front that reach it are not all listed
+            if (lane == 0) p2_emit(a.next, qrel, tp - 2.1 * eps, 0x7fffffff, tries + 1);
+            return;
+        }
+    }
+    // ---- R to the front, in row order
+    int m = 0;
+    for (int base = 0; base < rlim; base += 32) {
+        const int e = base + lane;
+        const bool in = e < rlim;
+        const double k = in ? key[e] : 0.0;
+        const int v = in ? val[e] : 0;
+        const bool g = in && (k >= tp || tp == -INFINITY);
+        const unsigned bg = __ballot_sync(0xffffffffu, g);
+        __syncwarp();
+        if (g) { const int dst = m + __popc(bg & lt); if (dst != e) { key[dst] = k; val[dst] = v; } }
+        m += __popc(bg);
+        __syncwarp();
+    }
+    warp_qs_topn_big(key, val, m, keep, posge[warp], hk[warp], hv[warp]);
+    if (lane < keep) { s_idx[warp][lane] = val[lane]; s_sim[warp][lane] = key[lane]; }
+    __syncwarp();
+    if (lane == 0) {
+        atomicAdd(&a.counters[CRX_CNT_TOPP_PASS2], 1ull);
+        if (a.qstatus) a.qstatus[qrel] = CRX_Q_EXACT;
+    }
+    if (a.nbr_rows) for (int j = lane; j < a.P; j += 32) a.nbr_rows[(size_t)qrel * a.P + j] = j < keep ? s_idx[warp][j] : -1;
+    if (a.nbr_sims) for (int j = lane; j < a.P; j += 32) a.nbr_sims[(size_t)qrel * a.P + j] = j < keep ? s_sim[warp][j] : 0.0;
+    if (a.recs) {
+        const int64_t qrow = a.q_begin + qrel;
+        predict_and_recommend<TB>(xb, a.ldb, a.mean_b, a.unk_q + qrow * a.D, a.mean_q[qrow], a.D, s_idx[warp], s_sim[warp], keep, a.Nrec,
+                                  s_pred[warp], s_coin[warp], a.recs + (size_t)qrel * a.Nrec);
+    }
+}
+
+// queries still queued after the last round keep the provisional answer of rec_finalize and are counted
+__global__ void p2_leftover_kernel(P2Queue w, unsigned int n, unsigned long long* counters) {
+    unsigned int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int kind = w.tries[i] >> P2_KIND_SHIFT;
+    atomicAdd(&counters[kind == CRX_Q_PLATEAU ? CRX_CNT_TOPP_RESCAN : CRX_CNT_TOPP_TIES], 1ull);
+}

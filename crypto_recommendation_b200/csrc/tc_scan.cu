@@ -1,12 +1,13 @@
 // tc_scan.cu -- tcgen05 / TMEM / TMA pair-scan engine for sm_100a (see tc_scan.cuh).
 //
 // One CTA = 128 rows of A ("queries" / "points"), resident in shared memory (TMA, 128B swizzle), against
-// ALL 128-column tiles of B streamed through a 5-stage TMA ring.  Warp 0 = TMA producer (one elected
-// lane), warp 1 = tcgen05.mma issuer (one elected lane; also owns the TMEM allocation), warps 2..9 =
-// epilogue: each thread owns ONE row x ONE 64-column half of the 128x128 fp32 accumulator tile
-// (tcgen05.ld 32x32b), so the per-row reductions (masked top-32 list per half / best + second best) are
-// thread-private -- no shuffles, no atomics.  The accumulator is double-buffered in TMEM (2 x 128 columns)
-// so that the MMAs of tile t+1 overlap the epilogue of tile t.
+// ALL 256-column tiles of B streamed through a 3-stage ring of 32 KB TMA boxes.  Warp 0 = TMA producer (one
+// elected lane), warp 1 = tcgen05.mma issuer (one elected lane; also owns the TMEM allocation), warps 2..9 =
+// epilogue: each thread owns ONE row x ONE 128-column half of the 128x256 fp32 accumulator tile
+// (tcgen05.ld 32x32b.x32), so the per-row reductions (masked top-32 list per half / best + second best / row
+// sums / threshold collection) are thread-private -- no shuffles, no atomics.  The accumulator is
+// double-buffered in TMEM (2 x 256 columns = all of TMEM) so that the MMAs of tile t+1 overlap the epilogue of
+// tile t.
 //
 // Split-fp16 arithmetic: every operand row is stored as [hi blocks | lo blocks] with hi = fp16(v),
 // lo = fp16(v - hi).  For each B block the issuer runs
@@ -126,9 +127,24 @@ struct TcParams {
     float errw_max;        // an upper bound of every errw_s[]
     double* rowsum;
     double* rowerr;
+    // top-P: maxima of the raw scores over geometric column blocks (block j = tiles [bt[j], bt[j+1])), per row and half
+    float* blockmax;       // [nq][2][TC_NBLK] or NULL
+    int nblk;
+    int bt[TC_NBLK + 1];
+    // threshold collection (second pass of the top-P): compact row i of A is query c_qrow[i]; every masked column with
+    // score >= c_theta[i] or column index > c_colx[i] is appended, in column order, to the row's chunk list
+    const float* c_theta;
+    const int32_t* c_colx;
+    const int32_t* c_qrow;
+    int32_t* pool;          // [pool_chunks][TC_CHUNK]: word 0 = next chunk (-1 = none), then TC_CHUNK - 1 columns
+    unsigned int* pool_next;
+    unsigned int pool_chunks;
+    int32_t* c_head;        // [rows] first chunk (-1 = empty)
+    int32_t* c_count;       // [rows] entries (counted even when the pool ran dry)
+    int32_t* c_ovf;         // [rows] 1 = the pool ran dry: the list is incomplete
 };
 
-constexpr int MODE_TOPP = 0, MODE_ARGMIN = 1, MODE_ROWSUM = 2;
+constexpr int MODE_TOPP = 0, MODE_ARGMIN = 1, MODE_ROWSUM = 2, MODE_COLLECT = 3;
 constexpr int HL = TC_LIST / 2;   // entries of one half-list (each epilogue half keeps its own top-HL)
 
 // r[j] for a run-time j: 5-level select tree (registers cannot be indexed dynamically)
@@ -202,6 +218,8 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // hand-over between the column halves: [TM][3] floats (argmin: aliases the staging tile, shared memory is full) or
     // [TM][2] doubles (row sums)
     float* merge = MODE == MODE_ARGMIN ? reinterpret_cast<float*>(stile) : reinterpret_cast<float*>(tmem_slot + 4);
+    // collection: pass masks of the previous tile, [tile parity][word 0..7 = half * 4 + chunk][row]
+    uint32_t* mbuf = reinterpret_cast<uint32_t*>(tmem_slot + 4);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
@@ -318,12 +336,48 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             if (valid) cq = p.qcode[p.q0 + grow];
             for (int e = 0; e < HL; e++) { myls[e * TM] = -INFINITY; myli[e * TM] = -1; }
         }
+        // top-P: running maximum of the raw scores of the current geometric column block
+        float bm = -INFINITY;
+        int bnext = 1;
+        // collection: threshold, "everything behind" column and the row's chunk list (appended by the half-0 thread)
+        float c_th = INFINITY;
+        int c_cx = 0x7fffffff, c_cur = -1, c_fill = 0, c_total = 0, c_hd = -1, c_ov = 0;
+        if (MODE == MODE_COLLECT && valid) {
+            cq = p.qcode[p.c_qrow[grow]];
+            c_th = p.c_theta[grow];
+            c_cx = p.c_colx[grow];
+        }
+        auto c_append_tile = [&](int tprev) {
+            // the pass masks of tile `tprev` of this row (both halves), in column order
+            const uint32_t* mb = mbuf + (tprev & 1) * 8 * TM + me;
+#pragma unroll 1
+            for (int w = 0; w < 8; w++) {
+                uint32_t bits = mb[w * TM];
+                const int cb = tprev * TN + w * 32;
+                while (bits != 0u) {
+                    const int j = __ffs(bits) - 1;
+                    bits &= bits - 1u;
+                    c_total++;
+                    if (c_ov) continue;
+                    if (c_cur < 0 || c_fill == TC_CHUNK - 1) {
+                        const unsigned int nc = atomicAdd(p.pool_next, 1u);
+                        if (nc >= p.pool_chunks) { c_ov = 1; continue; }
+                        p.pool[(size_t)nc * TC_CHUNK] = -1;
+                        if (c_cur < 0) c_hd = (int)nc; else p.pool[(size_t)c_cur * TC_CHUNK] = (int)nc;
+                        c_cur = (int)nc;
+                        c_fill = 0;
+                    }
+                    p.pool[(size_t)c_cur * TC_CHUNK + 1 + c_fill] = cb + j;
+                    c_fill++;
+                }
+            }
+        };
         const uint32_t low = p.low_mask, high = p.high_mask;
         // staging value (packed code / half norm) of this thread's column of the NEXT tile, fetched one tile ahead
         auto fetch_col = [&](int t) -> uint32_t {
             int64_t col = col0 + (int64_t)t * TN + etid;
             if (t >= ntiles) return 0u;
-            if (MODE == MODE_TOPP) return col < p.nb ? p.ccode[col] : 0u;
+            if (MODE == MODE_TOPP || MODE == MODE_COLLECT) return col < p.nb ? p.ccode[col] : 0u;
             if (MODE == MODE_ROWSUM) return __float_as_uint(col < col_end ? p.norm_s[col] : -1e30f);  // outside the cluster: d = 0
             return __float_as_uint(col < p.nb ? p.half_norm[col] : INFINITY);
         };
@@ -341,6 +395,12 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             if (MODE == MODE_ROWSUM) { stile[buf * TN * STW + TN + etid] = __float_as_uint(next_col2); next_col2 = fetch_col2(t + 1); }
             next_col = fetch_col(t + 1);
             asm volatile("bar.sync 1, 256;" ::: "memory");
+            if (MODE == MODE_COLLECT && half == 0 && t > 0 && valid) c_append_tile(t - 1);
+            if (MODE == MODE_TOPP && p.blockmax != nullptr && t == p.bt[bnext]) {
+                if (valid) p.blockmax[(grow * 2 + half) * TC_NBLK + bnext - 1] = bm;
+                bm = -INFINITY;
+                bnext++;
+            }
             mbar_wait(&tfull[buf], bphase);
             tc_fence_after();
             const uint32_t taddr = tmem_base + (uint32_t)(buf * TN + half * 128) + ((uint32_t)(quarter * 32) << 16);
@@ -381,7 +441,9 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                             }
                         }
                     }
-                    if (fmaxf(fmaxf(vm[0], vm[1]), fmaxf(vm[2], vm[3])) > thr && valid) {
+                    const float mx4 = fmaxf(fmaxf(vm[0], vm[1]), fmaxf(vm[2], vm[3]));
+                    bm = fmaxf(bm, mx4);
+                    if (mx4 > thr && valid) {
                         // rare path.  vm[u] is the maximum of chain u = entries j with j % 4 == u: only the chains that
                         // beat the threshold are looked at (8 entries each); an entry that is alone in its chain IS the
                         // chain maximum, so its value needs no register select tree
@@ -418,6 +480,36 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                             if (ok) list_insert(myls, myli, s, c, cnt, thr, minpos);
                         }
                     }
+                } else if (MODE == MODE_COLLECT) {
+                    float vm[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+                    if (DENSE) {
+#pragma unroll
+                        for (int j = 0; j < 32; j++) vm[j & 3] = fmaxf(vm[j & 3], __uint_as_float(r[j]));
+                    } else {
+#pragma unroll
+                        for (int g = 0; g < 8; g++) {
+                            uint4 cc = st4[g];
+                            uint32_t c4[4] = {cc.x, cc.y, cc.z, cc.w};
+#pragma unroll
+                            for (int u = 0; u < 4; u++) {
+                                uint32_t x = cq ^ c4[u];
+                                uint32_t m = (x - low) & ~x & high;
+                                vm[u] = fmaxf(vm[u], m != 0u ? __uint_as_float(r[g * 4 + u]) : -INFINITY);
+                            }
+                        }
+                    }
+                    const float mx4 = fmaxf(fmaxf(vm[0], vm[1]), fmaxf(vm[2], vm[3]));
+                    uint32_t bits = 0;
+                    if (valid && (mx4 >= c_th || cbase + 31 > c_cx)) {
+#pragma unroll
+                        for (int j = 0; j < 32; j++) {
+                            const int c = cbase + j;
+                            uint32_t x = cq ^ reinterpret_cast<const uint32_t*>(st4)[j];
+                            bool pass = (__uint_as_float(r[j]) >= c_th || c > c_cx) && c < p.nb && ((x - low) & ~x & high) != 0u;
+                            bits |= pass ? (1u << j) : 0u;
+                        }
+                    }
+                    mbuf[((t & 1) * 8 + half * 4 + rnd * 2 + ch) * TM + me] = bits;
                 } else if (MODE == MODE_ROWSUM) {
                     // d = sqrt(max(0, |a|^2 + |b|^2 - 2 a.b)) and a running bound on its error.  The squared distance is
                     // off by at most E = ea + eb (error weights of the two rows: split-fp16 dot, fp32 norms, subnormal low
@@ -490,6 +582,18 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     p.list_s[grow * TC_LIST + half * HL + e] = myls[e * TM];
                     p.list_i[grow * TC_LIST + half * HL + e] = myli[e * TM];
                 }
+                if (p.blockmax != nullptr) {
+                    p.blockmax[(grow * 2 + half) * TC_NBLK + bnext - 1] = bm;
+                    for (int b = bnext; b < TC_NBLK; b++) p.blockmax[(grow * 2 + half) * TC_NBLK + b] = -INFINITY;
+                }
+            }
+        } else if (MODE == MODE_COLLECT) {
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            if (half == 0 && valid) {
+                if (ntiles > 0) c_append_tile(ntiles - 1);
+                p.c_head[grow] = c_hd;
+                p.c_count[grow] = c_total;
+                p.c_ovf[grow] = c_ov;
             }
         } else if (MODE == MODE_ROWSUM) {
             double* dm = reinterpret_cast<double*>(merge);
@@ -589,6 +693,7 @@ int make_tensor_map(const TcOperand& op, int box_rows, CUtensorMap* tm) {
 size_t smem_for(int mode) {
     size_t s = (size_t)4 * BLK_BYTES + (size_t)NS * BBLK_BYTES + 2 * TN * 4 + (8 + 2 * NS) * 8 + 16;
     if (mode == MODE_TOPP) s += (size_t)2 * HL * TM * 8;
+    else if (mode == MODE_COLLECT) s += (size_t)2 * 8 * TM * 4;
     else if (mode == MODE_ROWSUM) s += TM * 2 * 8 + 2 * TN * 4;
     else s += 4 * BLK_BYTES;   // ARGMIN: second A buffer; the hand-over of the halves aliases the staging tile
     return s;
@@ -637,8 +742,83 @@ int crx_tc_prepare_matrix(crx_ctx* c, const double* m, int K, int D, int ld, dou
     return CRX_OK;
 }
 
+// geometric column blocks: block 0 = the first half of the tiles, block 1 = the next quarter, ... , the last block = one tile
+int crx_tc_blocks(int64_t b_rows, int* bt) {
+    const int nt = (int)((b_rows + TN - 1) / TN);
+    int nblk = 1;
+    bt[0] = 0;
+    for (int j = 1; j < TC_NBLK && (nt >> j) >= 1; j++) {
+        int b = nt - (nt >> j);
+        if (b <= bt[nblk - 1]) continue;
+        bt[nblk++] = b;
+    }
+    bt[nblk] = nt;
+    return nblk;
+}
+
+namespace {
+__global__ void tc_gather_rows_kernel(const uint4* __restrict__ src, const int32_t* __restrict__ rows, int64_t n, int64_t n_pad,
+                                      int row_u4, uint4* __restrict__ dst) {
+    int64_t i = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    int lane = threadIdx.x & 31;
+    if (i >= n_pad) return;
+    for (int c = lane; c < row_u4; c += 32)
+        dst[i * row_u4 + c] = i < n ? src[(int64_t)rows[i] * row_u4 + c] : make_uint4(0u, 0u, 0u, 0u);
+}
+}  // namespace
+
+int crx_tc_gather(crx_ctx* c, const TcOperand& src, const int32_t* d_rows, int64_t n, TcOperand* out) {
+    out->d = src.d;
+    out->rows = n;
+    out->rows_pad = (n + TM - 1) / TM * TM;
+    out->nkb = src.nkb;
+    out->scale_log2 = src.scale_log2;
+    out->owner = c;
+    const int row_u4 = src.nkb * 2 * 64 * (int)sizeof(__half) / 16;
+    CRX_TRY(crx_alloc(c, (char**)&out->data, (size_t)out->rows_pad * row_u4 * 16));
+    CRX_KERNEL(c, "tc_gather");
+    tc_gather_rows_kernel<<<crx_grid(out->rows_pad, 8), 256, 0, c->stream>>>((const uint4*)src.data, d_rows, n, out->rows_pad, row_u4, (uint4*)out->data);
+    CRX_CUDA(cudaGetLastError());
+    return CRX_OK;
+}
+
+int crx_tc_collect(crx_ctx* c, const TcOperand& A, int64_t nrows, const TcOperand& B, const uint32_t* qcode, const int32_t* d_qrow,
+                   const uint32_t* ccode, int k, int L, bool dense, const float* d_theta, const int32_t* d_colx, int32_t* pool,
+                   unsigned int* pool_next, unsigned int pool_chunks, int32_t* d_head, int32_t* d_count, int32_t* d_ovf) {
+    CRX_REQUIRE(A.nkb == B.nkb, "operand widths differ");
+    CRX_REQUIRE(k * L <= 32 && k >= 1, "packed codes need k*L <= 32");
+    if (nrows == 0) return CRX_OK;
+    CUtensorMap tmA, tmB;
+    CRX_TRY(make_tensor_map(A, TM, &tmA));
+    CRX_TRY(make_tensor_map(B, TN, &tmB));
+    TcParams p;
+    memset(&p, 0, sizeof(p));
+    p.q0 = 0; p.nq = nrows; p.nb = B.rows; p.ntiles = (int)((B.rows + TN - 1) / TN); p.nkb = A.nkb;
+    p.last_steps = last_steps_of(A);
+    p.nprod = 3;
+    p.qcode = qcode; p.ccode = ccode;
+    uint32_t low = 0, high = 0;
+    for (int l = 0; l < L; l++) { low |= 1u << (l * k); high |= 1u << (l * k + k - 1); }
+    p.low_mask = low; p.high_mask = high;
+    p.c_theta = d_theta; p.c_colx = d_colx; p.c_qrow = d_qrow;
+    p.pool = pool; p.pool_next = pool_next; p.pool_chunks = pool_chunks;
+    p.c_head = d_head; p.c_count = d_count; p.c_ovf = d_ovf;
+    size_t smem = smem_for(MODE_COLLECT);
+    int grid = (int)((nrows + TM - 1) / TM);
+    CRX_KERNEL(c, "tc_collect_scan");
+    if (dense) {
+        CRX_CUDA(cudaFuncSetAttribute(tc_scan_kernel<MODE_COLLECT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        tc_scan_kernel<MODE_COLLECT, true><<<grid, NTHREADS_K, smem, c->stream>>>(tmA, tmB, p);
+    } else {
+        CRX_CUDA(cudaFuncSetAttribute(tc_scan_kernel<MODE_COLLECT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        tc_scan_kernel<MODE_COLLECT, false><<<grid, NTHREADS_K, smem, c->stream>>>(tmA, tmB, p);
+    }
+    CRX_CUDA(cudaGetLastError());
+    return CRX_OK;
+}
+
 int crx_tc_topp(crx_ctx* c, const TcOperand& A, int64_t q0, int64_t nq, const TcOperand& B, const uint32_t* qcode,
-                const uint32_t* ccode, int k, int L, bool dense, float* list_s, int32_t* list_i, int nprod) {
+                const uint32_t* ccode, int k, int L, bool dense, float* list_s, int32_t* list_i, int nprod, float* blockmax) {
     CRX_REQUIRE(A.nkb == B.nkb, "operand widths differ");
     CRX_REQUIRE(k * L <= 32 && k >= 1, "packed codes need k*L <= 32");
     CUtensorMap tmA, tmB;
@@ -654,6 +834,8 @@ int crx_tc_topp(crx_ctx* c, const TcOperand& A, int64_t q0, int64_t nq, const Tc
     for (int l = 0; l < L; l++) { low |= 1u << (l * k); high |= 1u << (l * k + k - 1); }
     p.low_mask = low; p.high_mask = high;
     p.list_s = list_s; p.list_i = list_i;
+    p.blockmax = blockmax;
+    p.nblk = crx_tc_blocks(B.rows, p.bt);
     size_t smem = smem_for(MODE_TOPP);
     int grid = (int)((nq + TM - 1) / TM);
     CRX_KERNEL(c, "tc_topp_scan");

@@ -34,6 +34,8 @@ int crx_tc_prepare(crx_ctx* c, const crx_points* p, int mode, double scale_log2,
 int crx_tc_prepare_matrix(crx_ctx* c, const double* m, int K, int D, int ld, double scale_log2, TcOperand* out);
 
 constexpr int TC_LIST = 64;  // per-row candidate list of the top-P filter
+constexpr int TC_NBLK = 16;  // geometric column blocks whose score maxima the top-P filter reports (crx_tc_blocks)
+constexpr int TC_CHUNK = 256;  // words per chunk of a collected list: [next chunk | 255 columns]
 
 // top-P filter: for query rows [q0, q0+nq) of A against all rows of B, keep the TC_LIST best scores among
 // the columns whose packed code shares at least one k-bit field with the query's code.
@@ -41,8 +43,24 @@ constexpr int TC_LIST = 64;  // per-row candidate list of the top-P filter
 // dense: the caller knows that (nearly) every column is a candidate of every row (mean |cand| / N > 0.9)
 // nprod: 3 = split-fp16 products hi.hi + lo.hi + hi.lo (error ~6e-6 |a||b|); 1 = hi.hi only (error ~2^-10 |a||b|): kept for
 //        the measurement recorded in DESIGN.md section 8 -- TMEM reads, not the MMAs, bound it, so it is not used
+// blockmax (nullable): [nq][2][TC_NBLK] maxima of the raw scores (table mask applied only in the non-dense variant) of each
+//        row over the geometric column blocks of crx_tc_blocks, per epilogue half -- an upper bound of every candidate's score
 int crx_tc_topp(crx_ctx* c, const TcOperand& A, int64_t q0, int64_t nq, const TcOperand& B, const uint32_t* qcode,
-                const uint32_t* ccode, int k, int L, bool dense, float* list_s, int32_t* list_i, int nprod = 3);
+                const uint32_t* ccode, int k, int L, bool dense, float* list_s, int32_t* list_i, int nprod = 3,
+                float* blockmax = nullptr);
+// first tile of each geometric block into bt[0..nblk], bt[nblk] = number of 256-column tiles; returns nblk <= TC_NBLK
+int crx_tc_blocks(int64_t b_rows, int* bt);
+constexpr int TC_TILE_COLS = 256;
+
+// operand rows d_rows[0..n) of `src` copied into a compact operand (padded with zero rows to a multiple of 128)
+int crx_tc_gather(crx_ctx* c, const TcOperand& src, const int32_t* d_rows, int64_t n, TcOperand* out);
+
+// threshold collection (second pass of the top-P): for compact row i of A (= query row d_qrow[i], which indexes qcode) every
+// column j of B that shares a bucket with the query and has score >= d_theta[i] (filter units) or j > d_colx[i] is appended,
+// in ascending column order, to the row's chunk list in `pool` (d_head / d_count / d_ovf per row; *pool_next must start at 0)
+int crx_tc_collect(crx_ctx* c, const TcOperand& A, int64_t nrows, const TcOperand& B, const uint32_t* qcode, const int32_t* d_qrow,
+                   const uint32_t* ccode, int k, int L, bool dense, const float* d_theta, const int32_t* d_colx, int32_t* pool,
+                   unsigned int* pool_next, unsigned int pool_chunks, int32_t* d_head, int32_t* d_count, int32_t* d_ovf);
 
 // argmin filter: for rows [r0, r0+nr) of A against the K rows of B: best / second-best of
 // half_norm[j] - dot(a, b_j) (scaled units) and the best column.

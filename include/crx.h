@@ -64,7 +64,9 @@ int crx_ctx_kernel_time(crx_ctx* ctx, const char* prefix, double* total_ms, int6
  * [4] Lloyd points re-evaluated exactly, [5] top-P queries with equal similarities among the P best whose
  * reference order (quicksort partition history) could not be reconstructed from the listed candidates: they are
  * returned in descending similarity, ties by row, [6] top-P queries with equal similarities among the P best (all),
- * [7] reserved */
+ * [7] top-P queries decided by the second, targeted pass (threshold re-scan + exact similarities + literal sort).
+ * With the second pass on (the default; CRX_TOPP_EXACT=0 switches it off) [1] and [5] stay 0: every query carries
+ * the reference's list. */
 int crx_ctx_counters(crx_ctx* ctx, int64_t out[8], int reset);
 
 /* ---- points: vector<CustVector<T>> (cust_vector.hpp:23-72) ---- */
@@ -211,8 +213,8 @@ int crx_recommend_lsh(crx_ctx* ctx, const crx_lsh* lsh_hashtables, const crx_poi
 /* The same call with a per-query status (the per-query form of counters [1] and [5]): status[q] = CRX_Q_EXACT when the
  * neighbour list is the reference's, order of equal similarities included; CRX_Q_PLATEAU when more equal similarities
  * reach the P-th place than the candidate list of the query holds; CRX_Q_TIE_ORDER when equal similarities among the P
- * best come back ordered by row because the reference's order could not be rebuilt.  A caller that needs the literal
- * result for those queries runs crx_get_P_closest on them. */
+ * best come back ordered by row because the reference's order could not be rebuilt.  Both only occur with the second
+ * pass switched off (CRX_TOPP_EXACT=0): by default every query is CRX_Q_EXACT. */
 enum { CRX_Q_EXACT = 0, CRX_Q_PLATEAU = 1, CRX_Q_TIE_ORDER = 2 };
 int crx_recommend_lsh_status(crx_ctx* ctx, const crx_lsh* lsh_hashtables, const crx_points* queries, int64_t q_begin,
                              int64_t q_end, int P, int Nrec, int32_t* recs, int32_t* nbr_rows, double* nbr_sims,
@@ -233,6 +235,10 @@ int crx_get_top_N_recom(crx_ctx* ctx, const crx_points* users, const int32_t* ne
                         int64_t n, const crx_points* query_set, int64_t query_row, int N, double* predicted, int32_t* recs);
 /* parallel_quickSort (crypto_rec.hpp:269) on the device, one thread: known-answer tests only */
 int crx_parallel_quickSort(crx_ctx* ctx, double* sims /* host, in/out */, int32_t* ids /* host, in/out */, int n);
+/* The same sort when only the first `need` (<= 126) positions are consumed, as get_P_closest does (crypto_rec.hpp:225-228):
+ * the warp-parallel closed form of the Lomuto partition that the second pass of crx_recommend_lsh runs on candidate sets
+ * of any size.  The first min(n, need) entries of sims / ids are the literal sort's; the rest is unspecified. */
+int crx_parallel_quickSort_topn(crx_ctx* ctx, double* sims /* host, in/out */, int32_t* ids /* host, in/out */, int n, int need);
 
 /* ---- the step in front of the path: user rating vectors from tweet mentions ------------------------------
  * tweets_to_user_vectors (crypto_rec.hpp:79-140) and clusters_to_user_vectors (:143-210) after the strings are

@@ -215,6 +215,14 @@ class RecHandle:
         self.o.lib.orc_rec_handle_query(self.h, ctypes.c_int64(q_begin), ctypes.c_int64(q_end), P, Nrec, _p(recs), _p(ncand))
         return recs, ncand
 
+    def query_nbr(self, q_begin, q_end, P, Nrec):
+        """query() plus the neighbours get_P_closest kept: (recs, ncand, nbr_rows[nq][P], nbr_sims[nq][P])."""
+        nq = q_end - q_begin
+        recs = np.zeros((nq, Nrec), np.int32); ncand = np.zeros(nq, np.int32)
+        nidx = np.zeros((nq, P), np.int32); nsim = np.zeros((nq, P))
+        self.o.lib.orc_rec_handle_query_nbr(self.h, ctypes.c_int64(q_begin), ctypes.c_int64(q_end), P, Nrec, _p(recs), _p(ncand), _p(nidx), _p(nsim))
+        return recs, ncand, nidx, nsim
+
     def close(self):
         if self.h:
             self.o.lib.orc_rec_handle_destroy(self.h)

@@ -751,7 +751,8 @@ void* orc_rec_handle_create(const double* X, const uint8_t* unknown, const doubl
     return h;
 }
 
-int orc_rec_handle_query(void* hv, int64_t q_begin, int64_t q_end, int P, int Nrec, int32_t* recs, int32_t* ncand) {
+int orc_rec_handle_query_nbr(void* hv, int64_t q_begin, int64_t q_end, int P, int Nrec, int32_t* recs, int32_t* ncand,
+                             int32_t* nbr_idx, double* nbr_sim) {
     PortRecHandle* h = (PortRecHandle*)hv;
     int D = h->D;
     std::vector<int32_t> cand;
@@ -761,15 +762,21 @@ int orc_rec_handle_query(void* hv, int64_t q_begin, int64_t q_end, int P, int Nr
         h->lsh.candidates(q, 1, cand);
         ncand[u - q_begin] = (int32_t)cand.size();
         for (int j = 0; j < Nrec; j++) recs[(u - q_begin) * Nrec + j] = -1;
+        if (nbr_idx) for (int j = 0; j < P; j++) { nbr_idx[(u - q_begin) * P + j] = -1; nbr_sim[(u - q_begin) * P + j] = 0; }
         if (cand.empty()) continue;
         sims.resize(cand.size());
         for (size_t i = 0; i < cand.size(); i++) sims[i] = cos_sim_n(h->X + (size_t)cand[i] * D, q, D, h->nrm[cand[i]], h->nrm[u]);
         lomuto_desc(sims.data(), cand.data(), 0, (int)cand.size() - 1);
         int keep = (int)std::min<size_t>(cand.size(), (size_t)P);
+        if (nbr_idx) for (int j = 0; j < keep; j++) { nbr_idx[(u - q_begin) * P + j] = cand[j]; nbr_sim[(u - q_begin) * P + j] = sims[j]; }
         top_n_from_neighbours(h->X, h->mean, D, cand.data(), sims.data(), keep, h->unknown + u * D, h->mean[u], Nrec,
                               recs + (u - q_begin) * Nrec);
     }
     return 0;
+}
+
+int orc_rec_handle_query(void* hv, int64_t q_begin, int64_t q_end, int P, int Nrec, int32_t* recs, int32_t* ncand) {
+    return orc_rec_handle_query_nbr(hv, q_begin, q_end, P, Nrec, recs, ncand, nullptr, nullptr);
 }
 
 void orc_rec_handle_destroy(void* hv) { delete (PortRecHandle*)hv; }

@@ -96,6 +96,9 @@ int orc_recommend_cluster(const double* X, const uint8_t* unknown, const double*
 void* orc_rec_handle_create(const double* X, const uint8_t* unknown, const double* mean, int64_t N, int D, int metric,
                             int k, int L, int lsh_bucket_div, double w, uint64_t seed);
 int orc_rec_handle_query(void* h, int64_t q_begin, int64_t q_end, int P, int Nrec, int32_t* recs, int32_t* ncand);
+/* the same, also returning the neighbours get_P_closest kept: nbr_idx[nq][P] (-1 padded), nbr_sim[nq][P] */
+int orc_rec_handle_query_nbr(void* h, int64_t q_begin, int64_t q_end, int P, int Nrec, int32_t* recs, int32_t* ncand,
+                             int32_t* nbr_idx, double* nbr_sim);
 void orc_rec_handle_destroy(void* h);
 
 #ifdef __cplusplus

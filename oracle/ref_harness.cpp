@@ -406,20 +406,31 @@ void* orc_rec_handle_create(const double* X, const uint8_t* unknown, const doubl
     return h;
 }
 
-int orc_rec_handle_query(void* hv, int64_t q_begin, int64_t q_end, int P, int Nrec, int32_t* recs, int32_t* ncand) {
+int orc_rec_handle_query_nbr(void* hv, int64_t q_begin, int64_t q_end, int P, int Nrec, int32_t* recs, int32_t* ncand,
+                             int32_t* nbr_idx, double* nbr_sim) {
     RefRecHandle* h = (RefRecHandle*)hv;
     for (int64_t u = q_begin; u < q_end; u++) {
         CV& user = h->base[u];
         vector<CV*> neighbors = get_LSH_filtered_combined_buckets(h->tabs, &user);
         ncand[u - q_begin] = (int32_t)neighbors.size();
         for (int j = 0; j < Nrec; j++) recs[(u - q_begin) * Nrec + j] = -1;
+        if (nbr_idx) for (int j = 0; j < P; j++) { nbr_idx[(u - q_begin) * P + j] = -1; nbr_sim[(u - q_begin) * P + j] = 0; }
         if (!neighbors.empty()) {
             vector<double> sims = get_P_closest(neighbors, user, P);
+            if (nbr_idx)
+                for (size_t j = 0; j < neighbors.size(); j++) {
+                    nbr_idx[(u - q_begin) * P + j] = (int32_t)(neighbors[j] - &h->base[0]);
+                    nbr_sim[(u - q_begin) * P + j] = sims[j];
+                }
             vector<int> r = get_top_N_recom(neighbors, user, Nrec, sims);
             for (int j = 0; j < Nrec; j++) recs[(u - q_begin) * Nrec + j] = r[j];
         }
     }
     return 0;
+}
+
+int orc_rec_handle_query(void* hv, int64_t q_begin, int64_t q_end, int P, int Nrec, int32_t* recs, int32_t* ncand) {
+    return orc_rec_handle_query_nbr(hv, q_begin, q_end, P, Nrec, recs, ncand, nullptr, nullptr);
 }
 
 void orc_rec_handle_destroy(void* hv) {

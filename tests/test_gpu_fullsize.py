@@ -49,6 +49,44 @@ def test_c2_one_million_users_top_p_recommendation(ctx, port):
     assert ctx.counters()["hash_dd"] >= 0
 
 
+def test_c2_bench_workload_rating_like_users_against_the_oracle(ctx, port, ref):
+    """C2-(i), the workload bench.py times: 1M rating-like users (47% of the queries have equal similarities among their 20
+    best, plateaus of tens of thousands of mathematically equal similarities).  Every query must be CRX_Q_EXACT; a sample that
+    force-includes queries the second pass decided (plateau / tie-order / untouched) is compared -- neighbour rows in the
+    reference's order, similarity doubles, recommended coins -- with the oracle run over the FULL table."""
+    import bench
+    n, d, P, Nrec = 1_000_000, 100, bench.P_NEIGH, bench.N_REC
+    U, unk, mean = bench.make_users(n, d, bench.SEED)
+    pts = ctx.points(U, unk, mean)
+    t = capi.LshTables(ctx, pts, "cosine", bench.K_HASH, bench.L_TABLES, bench.LSH_BUCKET_DIV, bench.EUCLID_W, 7)
+    ctx.counters(reset=True)
+    out = capi.recommend_lsh(ctx, t, P, Nrec, want=("recs", "nbr_rows", "nbr_sims", "ncand", "status"))
+    cnt = ctx.counters(reset=True)
+    print("C2-(i) counters:", cnt)
+    assert (out["status"] == capi.Q_EXACT).all(), int((out["status"] != capi.Q_EXACT).sum())
+    assert cnt["topp_uncertified"] == 0 and cnt["topp_tie_order"] == 0, cnt
+    assert cnt["topp_pass2"] > 100_000, "a quarter of these queries need the second pass"
+    nbr, sim = out["nbr_rows"], out["nbr_sims"]
+    assert (np.diff(sim, axis=1) <= 0).all(), "similarities are sorted descending"
+    assert (np.sort(nbr, axis=1)[:, 1:] != np.sort(nbr, axis=1)[:, :-1]).all(), "no duplicate neighbours"
+    # which queries went through the second pass: run the same batch once more with the pass switched off in a child
+    # process?  No -- the tie structure itself tells: ties among the P best or a P-th best that is repeated further down
+    tied = (np.diff(sim, axis=1) == 0).any(axis=1)
+    rng = np.random.default_rng(2)
+    sample = np.concatenate([rng.choice(np.flatnonzero(tied), 40, replace=False), rng.choice(np.flatnonzero(~tied), 12, replace=False)])
+    # the port (bit-identical to the reference build, tests/test_oracle_pin.py) skips all-equal ranges in its quicksort; the
+    # reference's own O(n^2) walk over a 50k plateau takes minutes per query
+    h = RecHandle(port, U.astype(np.float64), unk, mean, COSINE, bench.K_HASH, bench.L_TABLES, bench.LSH_BUCKET_DIV, bench.EUCLID_W, 7)
+    bad = []
+    for q in sample:
+        r, nc, ni, ns = h.query_nbr(int(q), int(q) + 1, P, Nrec)
+        assert nc[0] == out["ncand"][q]
+        if not (np.array_equal(ni[0], nbr[q]) and np.array_equal(ns[0], sim[q]) and np.array_equal(r[0], out["recs"][q])):
+            bad.append(int(q))
+    h.close()
+    assert not bad, "queries that differ from the oracle: %s" % bad
+
+
 def test_c4_shard_lloyd_k1024(ctx, port):
     n, d, K = 4_000_000, 128, 1024
     X = synth.gaussian_mixture(n, d, K, seed=4, dtype=np.float32)

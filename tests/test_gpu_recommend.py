@@ -17,38 +17,33 @@ def _fresh_counters(ctx):
 
 
 def check_rec(ctx, out, ref_out, max_soft_frac=0.0):
-    """No hard mismatch ever.  `soft` = queries whose neighbour list differs from the oracle's ONLY at
-    positions where the oracle's own similarities tie (north_star: counted and reported separately).
-    Rating-like vectors tie massively by construction (users with the same pattern of zero / single
-    ratings have equal similarities to a query), and the reference orders those ties by the partition
-    history of its Lomuto quicksort.  The engine reproduces that order whenever the candidates involved
-    are all in its per-query lists and COUNTS the queries where they are not (`topp_uncertified`,
-    `topp_tie_order`): a soft difference is only accepted for a counted query."""
+    """Every query must carry the reference's own neighbour list -- rows, order among equal similarities (the partition
+    history of its Lomuto quicksort, crypto_rec.hpp:235-277) and similarity doubles -- and therefore its coins.
+    Rating-like vectors tie massively by construction (users with the same pattern of zero / single ratings have equal
+    similarities to a query); the queries whose 64-entry list does not decide the order go through the second, targeted
+    pass (`topp_pass2`), so nothing is left to count: `topp_uncertified` == `topp_tie_order` == 0 and every status is
+    EXACT.  `max_soft_frac` is kept in the signature for the one continuous-data test that bounds near ties; it is 0
+    everywhere else."""
     recs, nbr, sim, ncand = ref_out
     nq = nbr.shape[0]
     assert np.array_equal(out["ncand"], ncand)
     hard, soft = topp_compare(out["nbr_rows"], out["nbr_sims"], nbr, sim)
-    assert hard == 0, "%d queries with a wrong neighbour list" % hard
     cnt = ctx.counters(reset=True)
-    counted = cnt["topp_uncertified"] + cnt["topp_tie_order"]
-    print("check_rec: %d of %d queries differ only inside tie groups (%.2f%%); the engine counted %d unresolved (allowed %.0f%%)"
-          % (soft, nq, 100.0 * soft / nq, counted, 100 * max_soft_frac))
-    assert soft <= counted, "%d queries differ inside tie groups but only %d were counted as unresolved" % (soft, counted)
-    if "status" in out:   # per-query form of the same statement: a query that differs from the oracle is flagged
-        differs = ~np.all(out["nbr_rows"] == nbr, axis=1)
-        flagged = out["status"] != capi.Q_EXACT
-        assert not (differs & ~flagged).any(), "queries %s differ but carry status EXACT" % np.flatnonzero(differs & ~flagged)[:5]
-        assert int(flagged.sum()) == counted, (int(flagged.sum()), counted)
-    assert soft <= max_soft_frac * nq, "%d of %d queries differ by near-ties (allowed %.0f%%)" % (soft, nq, 100 * max_soft_frac)
-    same = np.all(out["nbr_rows"] == nbr, axis=1)
-    assert np.array_equal(out["nbr_sims"][same], sim[same]), "similarities are the reference's own doubles (x87 accumulation), bit for bit"
-    bad = np.flatnonzero(~np.all(out["recs"] == recs, axis=1) & same)
-    assert len(bad) == 0, "recommended coins differ for %d queries with identical neighbours, e.g. %s vs %s" % (
-        len(bad), out["recs"][bad[:2]].tolist(), recs[bad[:2]].tolist())
-    # same neighbour SET in a different order (ties): the coins may only differ through 1-ulp prediction noise
-    sameset = np.array([sorted(a) == sorted(b) for a, b in zip(out["nbr_rows"].tolist(), nbr.tolist())]) & ~same
-    flips = int((~np.all(out["recs"] == recs, axis=1) & sameset).sum())
-    assert flips <= max(2, 0.1 * sameset.sum()), (flips, int(sameset.sum()))
+    print("check_rec: %d queries, %d decided by the second pass, %d with ties among the P best; differing: %d hard, %d inside tie groups"
+          % (nq, cnt["topp_pass2"], cnt["topp_tied"], hard, soft))
+    assert hard == 0, "%d queries with a wrong neighbour list" % hard
+    assert cnt["topp_uncertified"] == 0 and cnt["topp_tie_order"] == 0, cnt
+    if "status" in out:
+        assert (out["status"] == capi.Q_EXACT).all(), np.flatnonzero(out["status"] != capi.Q_EXACT)[:5]
+    assert soft <= max_soft_frac * nq, "%d of %d queries differ inside tie groups" % (soft, nq)
+    if max_soft_frac == 0:
+        assert np.array_equal(out["nbr_rows"], nbr), "neighbour rows, order included"
+        assert np.array_equal(out["nbr_sims"], sim), "similarities are the reference's own doubles (x87 accumulation), bit for bit"
+        assert np.array_equal(out["recs"], recs), "recommended coins"
+    else:
+        same = np.all(out["nbr_rows"] == nbr, axis=1)
+        assert np.array_equal(out["nbr_sims"][same], sim[same])
+        assert np.array_equal(out["recs"][same], recs[same])
     return soft
 
 
@@ -57,7 +52,7 @@ def test_golden_rec_A(ctx, golden):
     P = ctx.points(g["rec_U"], g["rec_unk"], g["rec_mean"])
     t = capi.LshTables(ctx, P, "cosine", 4, 5, 100, 0.4, 9001)
     out = capi.recommend_lsh(ctx, t, 20, 5, want=WANT)
-    check_rec(ctx, out, (g["rec_A_recs"], g["rec_A_nbr"], g["rec_A_sim"], g["rec_A_ncand"]), 0.12)
+    check_rec(ctx, out, (g["rec_A_recs"], g["rec_A_nbr"], g["rec_A_sim"], g["rec_A_ncand"]))
 
 
 def test_golden_rec_B(ctx, golden):
@@ -67,7 +62,7 @@ def test_golden_rec_B(ctx, golden):
     Q = ctx.points(U[25:], unk[25:], mean[25:])
     t = capi.LshTables(ctx, V, "cosine", 4, 5, 100, 0.4, 9002)
     out = capi.recommend_lsh(ctx, t, 20, 2, queries=Q, want=WANT)
-    check_rec(ctx, out, (g["rec_B_recs"], g["rec_B_nbr"], g["rec_B_sim"], g["rec_B_ncand"]), 0.12)
+    check_rec(ctx, out, (g["rec_B_recs"], g["rec_B_nbr"], g["rec_B_sim"], g["rec_B_ncand"]))
 
 
 def test_golden_rec_cluster(ctx, golden):
@@ -85,7 +80,7 @@ def test_rec_lsh_cosine_oracle(ctx, port, dtype, n, P_, Nrec, k, L):
     t = capi.LshTables(ctx, P, "cosine", k, L, 100, 0.4, 31337)
     out = capi.recommend_lsh(ctx, t, P_, Nrec, want=WANT)
     ref = port.recommend_lsh(U.astype(np.float64), unk, mean, COSINE, k, L, 100, 0.4, P_, Nrec, 31337)
-    check_rec(ctx, out, ref, 0.12)
+    check_rec(ctx, out, ref)
     # query sub-range == slice of the full result (this is how queries are sharded across GPUs)
     lo, hi = n // 3, n // 3 + 257
     hi = min(hi, P.n)
@@ -104,7 +99,7 @@ def test_rec_lsh_normal_data_dense_and_table_modes(ctx, port):
     t = capi.LshTables(ctx, P, "cosine", 4, 5, 100, 0.4, 4711)
     out = capi.recommend_lsh(ctx, t, 20, 5, want=WANT)
     ref = port.recommend_lsh(X.astype(np.float64), unk, mean, COSINE, 4, 5, 100, 0.4, 20, 5, 4711)
-    assert check_rec(ctx, out, ref, 0.002) <= 2  # continuous data: ties are (next to) impossible
+    check_rec(ctx, out, ref)  # continuous data: no ties, nothing for the second pass to do
     frac = ref[3].mean() / 2500
     assert 0.15 < frac < 0.45, frac
 
@@ -117,7 +112,7 @@ def test_rec_lsh_euclidean_oracle(ctx, port, dtype):
         t = capi.LshTables(ctx, P, "euclidean", k, L, div, w, 2024)
         out = capi.recommend_lsh(ctx, t, 20, 5, want=WANT)
         ref = port.recommend_lsh(U.astype(np.float64), unk, mean, EUCLIDEAN, k, L, div, w, 20, 5, 2024)
-        check_rec(ctx, out, ref, 0.12)
+        check_rec(ctx, out, ref)
 
 
 def test_rec_B_external_queries(ctx, port):
@@ -128,7 +123,7 @@ def test_rec_B_external_queries(ctx, port):
     t = capi.LshTables(ctx, V, "cosine", 4, 5, 100, 0.4, 808)
     out = capi.recommend_lsh(ctx, t, 20, 2, queries=Q, want=WANT)
     ref = port.recommend_lsh(U[:nb], unk[:nb], mean[:nb], COSINE, 4, 5, 100, 0.4, 20, 2, 808, Xq=U[nb:], unknown_q=unk[nb:], mean_q=mean[nb:])
-    check_rec(ctx, out, ref, 0.12)
+    check_rec(ctx, out, ref)
 
 
 def test_rec_cluster_oracle(ctx, port):
@@ -156,5 +151,35 @@ def test_few_unknown_coins_pads_with_zero(ctx, port):
     t = capi.LshTables(ctx, P, "cosine", 4, 5, 100, 0.4, 5)
     out = capi.recommend_lsh(ctx, t, 20, 5, want=WANT)
     ref = port.recommend_lsh(U, unk, mean, COSINE, 4, 5, 100, 0.4, 20, 5, 5)
-    check_rec(ctx, out, ref, 0.12)
+    check_rec(ctx, out, ref)
     assert (out["recs"][:, 3:] == 0).all()
+
+
+@pytest.mark.parametrize("nmax,count", [(300, 300), (5000, 40), (70000, 4)])
+def test_warp_quicksort_topn_matches_literal(ctx, port, nmax, count):
+    """crx_parallel_quickSort_topn = the warp-parallel closed form of the Lomuto partition (second pass of the top-P) on
+    tie-heavy sequences of any length, against the oracle's literal sort."""
+    rng = np.random.default_rng(nmax)
+    for it in range(count):
+        n = int(rng.integers(max(1, nmax // 4), nmax))
+        levels = int(rng.choice([1, 2, 3, 10, 1000, 100000]))
+        s = rng.integers(0, levels + 1, n) / levels
+        if it % 3 == 0:
+            s = np.where(rng.random(n) < 0.95, 0.5, s)
+        need = int(rng.integers(1, 33)) if it % 4 else min(n, 126)
+        _, full = port.quicksort(s, np.arange(n, dtype=np.int32))
+        gs, gi = ctx.parallel_quickSort_topn(s, np.arange(n, dtype=np.int32), need)
+        k = min(need, n)
+        assert np.array_equal(gi[:k], full[:k]), (n, need, levels)
+        assert np.array_equal(gs[:k], s[full[:k]])
+
+
+def test_second_pass_off_counts_instead(ctx, port, monkeypatch):
+    """CRX_TOPP_EXACT=0 is read once per process, so this only documents the default: the second pass is on."""
+    U, unk, mean = synth.rating_users(1200, 100, seed=5)
+    P = ctx.points(U, unk, mean)
+    t = capi.LshTables(ctx, P, "cosine", 4, 5, 100, 0.4, 11)
+    out = capi.recommend_lsh(ctx, t, 20, 5, want=WANT)
+    cnt = ctx.counters(reset=True)
+    assert cnt["topp_pass2"] > 0, "rating-like users at P = 20 always leave some queries for the second pass"
+    assert (out["status"] == capi.Q_EXACT).all()
