@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJDIR = os.path.join(HERE, "_obj")
 LIB = os.path.join(HERE, "libcrx.so")
-SOURCES = ["core.cu", "hash.cu", "cluster.cu", "recommend.cu", "tc_scan.cu", "uservec.cu"]
+SOURCES = ["core.cu", "hash.cu", "cluster.cu", "recommend.cu", "tc_scan.cu", "uservec.cu", "comm_nccl.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
          "-Xcompiler", "-fPIC", "-Xcompiler", "-fno-strict-aliasing", "--expt-relaxed-constexpr",
@@ -57,7 +57,7 @@ def build(force=False, verbose=False):
     os.makedirs(OBJDIR, exist_ok=True)
     with ThreadPoolExecutor(max_workers=4) as ex:
         objs = list(ex.map(lambda s: _compile(s, verbose), SOURCES))
-    cmd = [NVCC, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] + objs + ["-lcudart"]
+    cmd = [NVCC, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] + objs + ["-lcudart", "-ldl"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("link failed:\n" + r.stdout + r.stderr)

@@ -34,6 +34,7 @@ SYMBOLS = [
     "crx_user_vectors_build",
     "crx_k_means_pp_sharded", "crx_k_means_sharded", "crx_pam_lloyds_sharded", "crx_silhouette_cluster_sharded",
     "crx_lsh_range_assignment_sharded", "crx_cube_range_assignment_sharded",
+    "crx_comm_nccl_version", "crx_comm_nccl_unique_id", "crx_comm_nccl_create", "crx_comm_nccl_calls", "crx_comm_nccl_destroy",
 ]
 
 

@@ -4,6 +4,8 @@
 //   K11 silhouette.
 #include <algorithm>
 #include <climits>
+#include <sstream>
+
 #include <cub/cub.cuh>
 #include <random>
 
@@ -702,21 +704,81 @@ __global__ void kpp_prob_kernel(const double* __restrict__ mind, int64_t N, cons
     p[i] = __dmul_rn(t, t);
 }
 
-// first index with x <= P[idx] (the reference's custom binary search, initialization.hpp:134-149)
-__global__ void kpp_pick_kernel(const double* __restrict__ P, int64_t N, double x, int32_t* __restrict__ chosen,
-                                unsigned long long* counters) {
-    if (blockIdx.x != 0 || threadIdx.x != 0) return;
-    int64_t lo = 0, hi = N - 1, ch = 0;
-    if (x > P[lo]) {
-        while (hi - lo > 1) {
-            int64_t m = lo + (hi - lo) / 2;
-            if (x <= P[m]) hi = m; else lo = m;
+// ---- the tail of a k-means++ round on the device (no host round trip per round) ----
+// st[]: [KPP_RNG] state of std::default_random_engine (minstd_rand0) as a double, [KPP_TOT + r] own shard total written into
+// slot r = this rank, [KPP_ALL + r] the totals of all shards (all-gathered; world == 1: slot KPP_ALL is written directly)
+constexpr int KPP_RNG = 0, KPP_TOT = 1, KPP_MAXW = 64, KPP_ALL = KPP_TOT + KPP_MAXW;
+__global__ void kpp_total_kernel(const double* __restrict__ P, int64_t N, double* __restrict__ out) { *out = N > 0 ? P[N - 1] : 0.0; }
+
+// initialization.hpp:131-149 for sharded rows: the running sum of the shard totals is the prefix sum at every shard boundary;
+// x ~ U(0, total) from the reference's engine (libstdc++: generate_canonical<double, 53> takes two draws of minstd_rand0,
+// sum = (x1 - 1) + (x2 - 1) R with R = 2147483646, canonical = sum / R^2, then canonical * (b - a) + a); the shard that holds
+// x searches its own prefix sums (the reference's binary search) and stages the picked row: coordinates, exact sum of
+// squares, global row -- the other ranks stage zeros, so an all-reduce(sum) of `share` is the broadcast.
+template <typename T>
+__global__ void kpp_draw_pick_kernel(const T* __restrict__ x, int ld, const double* __restrict__ sqn, const double* __restrict__ P, int64_t N,
+                                     int64_t row_offset, double* __restrict__ st, int world, int me, const int64_t* __restrict__ lens,
+                                     double* __restrict__ share, unsigned long long* counters) {
+    __shared__ int64_t s_row;
+    __shared__ int s_owner;
+    if (threadIdx.x == 0) {
+        const double* tot = world > 1 ? st + KPP_ALL : st + KPP_TOT + me;
+        double cum_prev = 0.0, total = 0.0;
+        for (int r = 0; r < world; r++) total = r == 0 ? tot[0] : __dadd_rn(total, tot[r]);
+        unsigned long long s = (unsigned long long)st[KPP_RNG];
+        s = s * 16807ull % 2147483647ull;
+        const double x1 = (double)(s - 1ull);
+        s = s * 16807ull % 2147483647ull;
+        const double x2 = (double)(s - 1ull);
+        st[KPP_RNG] = (double)s;
+        const double R = 2147483646.0;
+        const double sum = __dadd_rn(x1, __dmul_rn(x2, R));
+        double canon = __ddiv_rn(sum, __dmul_rn(R, R));
+        if (canon >= 1.0) canon = 0.99999999999999988897769753748434595763683319091796875;   // nextafter(1, 0)
+        const double xr = __dadd_rn(__dmul_rn(canon, total), 0.0);
+        int pick = world - 1;
+        double cum = 0.0, before = 0.0;
+        bool found = false;
+        for (int r = 0; r < world; r++) {
+            cum = r == 0 ? tot[0] : __dadd_rn(cum, tot[r]);
+            if (!found && lens[r] > 0 && xr <= cum) { pick = r; before = cum_prev; found = true; }
+            cum_prev = cum;
         }
-        ch = hi;
+        if (!found && world > 1) {   // the last shard: its prefix starts at the running sum in front of it
+            double c2 = 0.0;
+            for (int r = 0; r < world - 1; r++) c2 = r == 0 ? tot[0] : __dadd_rn(c2, tot[r]);
+            before = c2;
+        }
+        s_owner = pick;
+        int64_t ch = 0;
+        if (pick == me && N > 0) {
+            const double xl = pick > 0 ? __dsub_rn(xr, before) : xr;
+            int64_t lo = 0, hi = N - 1;
+            if (xl > P[lo]) {
+                while (hi - lo > 1) {
+                    int64_t m = lo + (hi - lo) / 2;
+                    if (xl <= P[m]) hi = m; else lo = m;
+                }
+                ch = hi;
+            }
+            const double tol = 1e-12 * P[N - 1];
+            if (fabs(xl - P[ch]) <= tol || (ch > 0 && fabs(xl - P[ch - 1]) <= tol)) atomicAdd(&counters[CRX_CNT_KPP_NEAR], 1ull);
+        }
+        s_row = ch;
     }
-    *chosen = (int32_t)ch;
-    double tol = 1e-12 * P[N - 1];
-    if (fabs(x - P[ch]) <= tol || (ch > 0 && fabs(x - P[ch - 1]) <= tol)) atomicAdd(&counters[CRX_CNT_KPP_NEAR], 1ull);
+    __syncthreads();
+    const bool mine = s_owner == me;
+    const int64_t row = s_row;
+    for (int k = threadIdx.x; k < ld; k += blockDim.x) share[k] = mine ? (double)x[(size_t)row * ld + k] : 0.0;
+    if (threadIdx.x == 0) { share[ld] = mine ? sqn[row] : 0.0; share[ld + 1] = mine ? (double)(row_offset + row) : 0.0; }
+}
+
+// after the exchange: `share` holds the new centroid on every rank
+__global__ void kpp_share_kernel(const double* __restrict__ share, int ld, double* __restrict__ cvec, double* __restrict__ vec_out, int D,
+                                 int64_t* __restrict__ out_row) {
+    for (int k = threadIdx.x; k <= ld; k += blockDim.x) cvec[k] = share[k];
+    if (vec_out) for (int k = threadIdx.x; k < D; k += blockDim.x) vec_out[k] = share[k];
+    if (threadIdx.x == 0) *out_row = (int64_t)share[ld + 1];
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1078,20 +1140,14 @@ static int comm_done(int rc, const char* what) {
 static int comm_allreduce(crx_ctx* c, const crx_comm* cm, void* buf, int64_t n, int dtype, int op, int mem) {
     if (comm_world(cm) == 1 || n == 0) return CRX_OK;
     CRX_REQUIRE(cm->allreduce, "crx_comm.allreduce is NULL");
-    if (mem == CRX_DEVICE) CRX_CUDA(cudaStreamSynchronize(c->stream));
+    if (mem == CRX_DEVICE && !cm->stream_ordered) CRX_CUDA(cudaStreamSynchronize(c->stream));
     return comm_done(cm->allreduce(cm->user, buf, n, dtype, op, mem), "allreduce");
 }
 static int comm_allgather(crx_ctx* c, const crx_comm* cm, const void* send, void* recv, int64_t n, int dtype, int mem) {
     CRX_REQUIRE(cm && cm->allgather, "crx_comm.allgather is NULL");
-    if (mem == CRX_DEVICE) CRX_CUDA(cudaStreamSynchronize(c->stream));
+    if (mem == CRX_DEVICE && !cm->stream_ordered) CRX_CUDA(cudaStreamSynchronize(c->stream));
     return comm_done(cm->allgather(cm->user, send, recv, n, dtype, mem), "allgather");
 }
-static int comm_broadcast(crx_ctx* c, const crx_comm* cm, void* buf, int64_t n, int dtype, int root, int mem) {
-    CRX_REQUIRE(cm && cm->broadcast, "crx_comm.broadcast is NULL");
-    if (mem == CRX_DEVICE) CRX_CUDA(cudaStreamSynchronize(c->stream));
-    return comm_done(cm->broadcast(cm->user, buf, n, dtype, root, mem), "broadcast");
-}
-
 static int range_assign_common(crx_ctx* c, const crx_points* p, const int32_t* h_crow, int K, int metric, int nseg,
                                const std::vector<int32_t>& h_begin, const std::vector<int32_t>& h_end,
                                const std::vector<const int32_t*>& h_perm, const int32_t* d_bucket, int32_t* labels,
@@ -1295,9 +1351,8 @@ int crx_k_means_pp_sharded(crx_ctx* c, const crx_points* p, int64_t row_offset, 
     out[0] = ui(e);
     DevBuf<double> mind, prob, P, cvec;
     DevBuf<unsigned long long> mx;
-    DevBuf<int32_t> chosen;
     DevBuf<char> tmp;
-    CRX_TRY(mind.alloc(c, N)); CRX_TRY(prob.alloc(c, N)); CRX_TRY(P.alloc(c, N)); CRX_TRY(mx.alloc(c, 1)); CRX_TRY(chosen.alloc(c, 1));
+    CRX_TRY(mind.alloc(c, N)); CRX_TRY(prob.alloc(c, N)); CRX_TRY(P.alloc(c, N)); CRX_TRY(mx.alloc(c, 1));
     CRX_TRY(cvec.alloc(c, ld + 1));
     DevBuf<int32_t> flagged, nearest;
     DevBuf<int> nflag;
@@ -1315,34 +1370,40 @@ int crx_k_means_pp_sharded(crx_ctx* c, const crx_points* p, int64_t row_offset, 
     if (N > 0) CRX_CUDA(cub::DeviceScan::InclusiveSum(nullptr, bytes, prob.p, P.p, (int)N, c->stream));
     CRX_TRY(tmp.alloc(c, bytes));
     int gridu = (int)((N + 255) / 256);
-    // coordinates (+ exact sum of squares, + the global row as a double) of a chosen centroid: staged by its owner and
-    // shared with everybody in ONE broadcast; cvec (device) and hvec (host) hold them afterwards on every rank
-    std::vector<double> hvec(ld + 2);
-    auto share_centroid = [&](int64_t g, int own) -> int {
-        if (own == me) {
-            if (p->x64) stage_row_kernel<double><<<1, 128, 0, c->stream>>>(p->x64, ld, p->sqn, g - row_offset, cvec.p);
-            else stage_row_kernel<float><<<1, 128, 0, c->stream>>>(p->x32, ld, p->sqn, g - row_offset, cvec.p);
-            if (world > 1 || out_vectors) {
-                CRX_CUDA(cudaMemcpyAsync(hvec.data(), cvec.p, (ld + 1) * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
-                CRX_CUDA(cudaStreamSynchronize(c->stream));
-            }
-            hvec[ld + 1] = (double)g;
-        }
-        if (world > 1) {
-            CRX_TRY(comm_broadcast(c, comm, hvec.data(), ld + 2, CRX_F64, own, CRX_HOST));
-            if (own != me) CRX_CUDA(cudaMemcpyAsync(cvec.p, hvec.data(), (ld + 1) * sizeof(double), cudaMemcpyHostToDevice, c->stream));
-        }
-        return CRX_OK;
-    };
+    // device-side state of the rounds: RNG state, shard totals (own slot + gathered), lengths of the shards
+    DevBuf<double> st, share, vecs_dev;
+    DevBuf<int64_t> rows_dev, lens_dev;
+    CRX_TRY(st.alloc(c, KPP_ALL + world)); CRX_TRY(share.alloc(c, ld + 2)); CRX_TRY(rows_dev.alloc(c, K)); CRX_TRY(lens_dev.alloc(c, world));
+    if (out_vectors) CRX_TRY(vecs_dev.alloc(c, (size_t)K * D));
     {
+        // the engine's state after the first draw (minstd_rand0: one integer), handed to the device
+        std::stringstream ss;
+        ss << e;
+        unsigned long long state = 0;
+        ss >> state;
+        std::vector<double> h_st(KPP_ALL + world, 0.0);
+        h_st[KPP_RNG] = (double)state;
+        CRX_CUDA(cudaMemcpyAsync(st.p, h_st.data(), h_st.size() * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+        CRX_CUDA(cudaMemcpyAsync(lens_dev.p, lens.data(), world * sizeof(int64_t), cudaMemcpyHostToDevice, c->stream));
+        CRX_CUDA(cudaStreamSynchronize(c->stream));   // h_st / lens are stack / heap temporaries
+    }
+    {
+        // the first centroid: its owner stages the row, the others contribute zeros
         int own = owner_of(out[0]);
         CRX_REQUIRE(own >= 0, "the shards do not cover the chosen row");
-        CRX_TRY(share_centroid(out[0], own));
+        CRX_CUDA(cudaMemsetAsync(share.p, 0, (ld + 2) * sizeof(double), c->stream));
+        if (own == me) {
+            if (p->x64) stage_row_kernel<double><<<1, 128, 0, c->stream>>>(p->x64, ld, p->sqn, out[0] - row_offset, share.p);
+            else stage_row_kernel<float><<<1, 128, 0, c->stream>>>(p->x32, ld, p->sqn, out[0] - row_offset, share.p);
+            const double g = (double)out[0];
+            CRX_CUDA(cudaMemcpyAsync(share.p + ld + 1, &g, sizeof(double), cudaMemcpyHostToDevice, c->stream));
+            CRX_CUDA(cudaStreamSynchronize(c->stream));
+        }
+        if (world > 1) CRX_TRY(comm_allreduce(c, comm, share.p, ld + 2, CRX_F64, CRX_SUM, CRX_DEVICE));
+        { CRX_KERNEL(c, "kpp_share"); kpp_share_kernel<<<1, 128, 0, c->stream>>>(share.p, ld, cvec.p, vecs_dev.p, D, rows_dev.p); }
     }
-    for (int i = 1; i <= K; i++) {
-        // cvec / hvec hold centroid i-1 (shared at the end of the previous round, together with its row number)
-        if (out_vectors) memcpy(out_vectors + (size_t)(i - 1) * D, hvec.data(), D * sizeof(double));
-        if (i == K) break;
+    for (int i = 1; i < K; i++) {
+        // cvec holds centroid i-1 (shared at the end of the previous round)
         CRX_CUDA(cudaMemsetAsync(mx.p, 0, sizeof(unsigned long long), c->stream));
         const bool filter = i > 1 && p->x64 == nullptr && N >= 4096 && ld <= 128;   // fp32 data only (its fp32 copy is exact); one 16-byte piece per lane covers the row
         if (prune) CRX_CUDA(cudaMemcpyAsync(cmat.p + (size_t)(i - 1) * ld, cvec.p, ld * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
@@ -1381,44 +1442,29 @@ int crx_k_means_pp_sharded(crx_ctx* c, const crx_points* p, int64_t row_offset, 
             else { if (metric == CRX_EUCLIDEAN) LAUNCH_K(float, CRX_EUCLIDEAN, p->x32); else LAUNCH_K(float, CRX_COSINE, p->x32); }
 #undef LAUNCH_K
         }
-        if (world > 1) {  // max_for_normalizing over all shards (initialization.hpp:116-117)
-            double hm = 0;
-            CRX_CUDA(cudaMemcpyAsync(&hm, mx.p, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
-            CRX_CUDA(cudaStreamSynchronize(c->stream));
-            CRX_TRY(comm_allreduce(c, comm, &hm, 1, CRX_F64, CRX_MAX, CRX_HOST));
-            CRX_CUDA(cudaMemcpyAsync(mx.p, &hm, sizeof(double), cudaMemcpyHostToDevice, c->stream));
-        }
-        double total = 0;
+        // max_for_normalizing over all shards (initialization.hpp:116-117): positive doubles order like their bit patterns
+        if (world > 1) CRX_TRY(comm_allreduce(c, comm, mx.p, 1, CRX_F64, CRX_MAX, CRX_DEVICE));
         if (N > 0) {
             { CRX_KERNEL(c, "kpp_prob"); kpp_prob_kernel<<<crx_grid(N, 256), 256, 0, c->stream>>>(mind.p, N, mx.p, prob.p); }
             CRX_CUDA(cub::DeviceScan::InclusiveSum(tmp.p, bytes, prob.p, P.p, (int)N, c->stream));
-            CRX_CUDA(cudaMemcpyAsync(&total, P.p + (N - 1), sizeof(double), cudaMemcpyDeviceToHost, c->stream));
         }
-        CRX_CUDA(cudaStreamSynchronize(c->stream));
-        // running sum of the shard totals = the prefix sum at every shard boundary (initialization.hpp:123-129)
-        std::vector<double> cum(world, total);
-        if (world > 1) {
-            CRX_TRY(comm_allgather(c, comm, &total, cum.data(), 1, CRX_F64, CRX_HOST));
-            for (int r = 1; r < world; r++) cum[r] = cum[r - 1] + cum[r];
+        // shard totals -> draw -> owner's binary search -> the picked row and its coordinates, all on the device: the round
+        // has no host synchronisation (the draws replicate std::default_random_engine + uniform_real_distribution<double>)
+        { CRX_KERNEL(c, "kpp_total"); kpp_total_kernel<<<1, 1, 0, c->stream>>>(P.p, N, st.p + KPP_TOT + me); }
+        if (world > 1) CRX_TRY(comm_allgather(c, comm, st.p + KPP_TOT + me, st.p + KPP_ALL, 1, CRX_F64, CRX_DEVICE));
+        {
+            CRX_KERNEL(c, "kpp_pick");
+            if (p->x64) kpp_draw_pick_kernel<double><<<1, 128, 0, c->stream>>>(p->x64, ld, p->sqn, P.p, N, row_offset, st.p, world, me, lens_dev.p, share.p, c->counters);
+            else kpp_draw_pick_kernel<float><<<1, 128, 0, c->stream>>>(p->x32, ld, p->sqn, P.p, N, row_offset, st.p, world, me, lens_dev.p, share.p, c->counters);
         }
-        std::uniform_real_distribution<double> ur(0.0, cum[world - 1]);  // initialization.hpp:132-133
-        double xr = ur(e);
-        int pick_rank = world - 1;
-        for (int r = 0; r < world; r++) if (lens[r] > 0 && xr <= cum[r]) { pick_rank = r; break; }
-        int64_t picked = 0;
-        if (pick_rank == me) {
-            double xl = pick_rank > 0 ? xr - cum[pick_rank - 1] : xr;
-            int32_t h = 0;
-            { CRX_KERNEL(c, "kpp_pick"); kpp_pick_kernel<<<1, 32, 0, c->stream>>>(P.p, N, xl, chosen.p, c->counters); }
-            CRX_CUDA(cudaMemcpyAsync(&h, chosen.p, sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
-            CRX_CUDA(cudaStreamSynchronize(c->stream));
-            picked = row_offset + h;
-        }
-        // the owner announces the picked row and its coordinates in one message
-        CRX_TRY(share_centroid(picked, pick_rank));
-        if (world > 1) picked = (int64_t)hvec[ld + 1];
-        out[i] = picked;
+        // the owner's buffer holds the vector, everybody else's zeros: the sum IS the broadcast, with no root to know on the host
+        if (world > 1) CRX_TRY(comm_allreduce(c, comm, share.p, ld + 2, CRX_F64, CRX_SUM, CRX_DEVICE));
+        { CRX_KERNEL(c, "kpp_share"); kpp_share_kernel<<<1, 128, 0, c->stream>>>(share.p, ld, cvec.p, vecs_dev.p ? vecs_dev.p + (size_t)i * D : nullptr, D, rows_dev.p + i); }
     }
+    CRX_CUDA(cudaGetLastError());
+    CRX_CUDA(cudaMemcpyAsync(out, rows_dev.p, (size_t)K * sizeof(int64_t), cudaMemcpyDeviceToHost, c->stream));
+    if (out_vectors) CRX_CUDA(cudaMemcpyAsync(out_vectors, vecs_dev.p, (size_t)K * D * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CRX_CUDA(cudaStreamSynchronize(c->stream));
     CRX_CUDA(cudaGetLastError());
     return CRX_OK;
 }
@@ -1432,17 +1478,27 @@ int crx_k_means_pp(crx_ctx* c, const crx_points* p, int K, int metric, uint64_t 
     return CRX_OK;
 }
 
+__global__ void counts_to_double_kernel(long long* __restrict__ cnt, int K, double* __restrict__ d, int back) {
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= K) return;
+    if (back) cnt[k] = (long long)d[k]; else d[k] = (double)cnt[k];
+}
+
 int crx_k_means_sharded(crx_ctx* c, const crx_points* p, const int32_t* labels, int lmem, const double* oldc, int K, int metric,
                         double min_dist, const crx_comm* comm, double* newc, int cmem, int* cont) {
     CRX_REQUIRE(c && p && labels && oldc && newc && cont, "NULL argument");
     DevBuf<double> sums, o, n;
     DevBuf<long long> cnt;
     size_t kd = (size_t)K * p->d;
-    CRX_TRY(sums.alloc(c, kd)); CRX_TRY(cnt.alloc(c, K)); CRX_TRY(o.alloc(c, kd)); CRX_TRY(n.alloc(c, kd));
+    CRX_TRY(sums.alloc(c, kd + K)); CRX_TRY(cnt.alloc(c, K)); CRX_TRY(o.alloc(c, kd)); CRX_TRY(n.alloc(c, kd));
     CRX_CUDA(cudaMemcpyAsync(o.p, oldc, kd * sizeof(double), cmem == CRX_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, c->stream));
     CRX_TRY(crx_cluster_sums(c, p, labels, lmem, K, sums.p, (int64_t*)cnt.p, CRX_DEVICE));
-    CRX_TRY(comm_allreduce(c, comm, sums.p, (int64_t)kd, CRX_F64, CRX_SUM, CRX_DEVICE));
-    CRX_TRY(comm_allreduce(c, comm, cnt.p, K, CRX_I64, CRX_SUM, CRX_DEVICE));
+    if (comm_world(comm) > 1) {
+        // ONE all-reduce per iteration: the K member counts ride behind the K*D sums as doubles (exact below 2^53)
+        { CRX_KERNEL(c, "pack_counts"); counts_to_double_kernel<<<crx_grid(K, 256), 256, 0, c->stream>>>(cnt.p, K, sums.p + kd, 0); }
+        CRX_TRY(comm_allreduce(c, comm, sums.p, (int64_t)(kd + K), CRX_F64, CRX_SUM, CRX_DEVICE));
+        { CRX_KERNEL(c, "pack_counts"); counts_to_double_kernel<<<crx_grid(K, 256), 256, 0, c->stream>>>(cnt.p, K, sums.p + kd, 1); }
+    }
     CRX_TRY(crx_k_means_finish(c, sums.p, (const int64_t*)cnt.p, o.p, K, p->d, metric, min_dist, n.p, CRX_DEVICE, cont));
     CRX_CUDA(cudaMemcpyAsync(newc, n.p, kd * sizeof(double), cmem == CRX_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice, c->stream));
     CRX_CUDA(cudaStreamSynchronize(c->stream));

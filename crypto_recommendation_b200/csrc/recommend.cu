@@ -842,6 +842,22 @@ static int pass2_run(crx_ctx* c, const P2Host& h, P2QueueBuf* qa, P2QueueBuf* qb
     unsigned int n = 0;
     CRX_CUDA(cudaMemcpyAsync(&n, cur->count.p, sizeof(n), cudaMemcpyDeviceToHost, c->stream));
     CRX_CUDA(cudaStreamSynchronize(c->stream));
+    static const bool p2_debug = getenv("CRX_P2_DEBUG") != nullptr;
+    // rows whose coordinates are all equal (single-coin users): their mutual similarities have a closed form (p2_exact_kernel)
+    DevBuf<double> uval_b, uval_q;
+    if (n > 0) {
+        CRX_KERNEL(c, "uniform_rows");
+        CRX_TRY(uval_b.alloc(c, (size_t)N));
+        if (base->x64) uniform_rows_kernel<double><<<crx_grid(N, 8), 256, 0, c->stream>>>(base->x64, base->ld, base->d, N, uval_b.p);
+        else uniform_rows_kernel<float><<<crx_grid(N, 8), 256, 0, c->stream>>>(base->x32, base->ld, base->d, N, uval_b.p);
+        if (queries != base) {
+            CRX_TRY(uval_q.alloc(c, (size_t)queries->n));
+            if (queries->x64) uniform_rows_kernel<double><<<crx_grid(queries->n, 8), 256, 0, c->stream>>>(queries->x64, queries->ld, queries->d, queries->n, uval_q.p);
+            else uniform_rows_kernel<float><<<crx_grid(queries->n, 8), 256, 0, c->stream>>>(queries->x32, queries->ld, queries->d, queries->n, uval_q.p);
+        }
+        CRX_CUDA(cudaGetLastError());
+    }
+    const double* d_uval_q = queries != base ? uval_q.p : uval_b.p;
     static const int max_rounds = getenv("CRX_P2_ROUNDS") ? atoi(getenv("CRX_P2_ROUNDS")) : 16;
     for (int round = 0; n > 0 && round < max_rounds; round++) {
         CRX_CUDA(cudaMemsetAsync(nxt->count.p, 0, sizeof(unsigned int), c->stream));
@@ -906,9 +922,9 @@ static int pass2_run(crx_ctx* c, const P2Host& h, P2QueueBuf* qa, P2QueueBuf* qb
         if (total > 0) {
             CRX_KERNEL(c, "p2_exact");
             const int64_t nblocks = total / 32;
-            int grid = (int)std::min<int64_t>((nblocks + 7) / 8, (int64_t)c->sm_count * 16);
+            int grid = (int)std::min<int64_t>(((nblocks + P2_RUN - 1) / P2_RUN + 7) / 8, (int64_t)c->sm_count * 16);
 #define LAUNCH_E(TQ, TB, xqp, xbp) \
-    p2_exact_kernel<TQ, TB><<<grid, 256, 0, c->stream>>>(xqp, queries->ld, queries->sqn, xbp, base->ld, base->sqn, base->d, h.q_begin, w.q, off.p, n, nblocks, cols.p, xs.p)
+    p2_exact_kernel<TQ, TB><<<grid, 256, 0, c->stream>>>(xqp, queries->ld, queries->sqn, xbp, base->ld, base->sqn, base->d, h.q_begin, w.q, off.p, n, nblocks, cols.p, xs.p, d_uval_q, uval_b.p)
             if (queries->x64 && base->x64) LAUNCH_E(double, double, queries->x64, base->x64);
             else if (queries->x64) LAUNCH_E(double, float, queries->x64, base->x32);
             else if (base->x64) LAUNCH_E(float, double, queries->x32, base->x64);
@@ -931,8 +947,10 @@ static int pass2_run(crx_ctx* c, const P2Host& h, P2QueueBuf* qa, P2QueueBuf* qb
             CRX_CUDA(cudaGetLastError());
         }
         std::swap(cur, nxt);
+        const unsigned int n_in = n;
         CRX_CUDA(cudaMemcpyAsync(&n, cur->count.p, sizeof(n), cudaMemcpyDeviceToHost, c->stream));
         CRX_CUDA(cudaStreamSynchronize(c->stream));
+        if (p2_debug) fprintf(stderr, "[crx pass2] round %d: %u queued, %lld collected (%.1f per query), %u left\n", round, n_in, (long long)total, (double)total / n_in, n);
     }
     if (n > 0) {
         CRX_KERNEL(c, "p2_leftover");

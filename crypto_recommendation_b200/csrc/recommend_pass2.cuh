@@ -323,28 +323,75 @@ p2_collect_simt_kernel(const TQ* __restrict__ xq, int ldq, const double* __restr
     if (FILL) for (int j = running + threadIdx.x; j < (running + 31) / 32 * 32; j += 256) out[j] = -1;
 }
 
-// the reference's own similarity of every collected candidate (crypto_rec.hpp:220, cust_vector.hpp:160-174): a warp takes 32
-// consecutive entries (segments are padded to multiples of 32, so they belong to one query), each lane walks its row
+// uval[row] = c when every coordinate of the row equals c (a user with ONE known coin: the unknown coins hold the user's
+// mean, crypto_rec.hpp:118-125, so the whole vector is that rating), NaN otherwise.  One warp per row.
+template <typename T>
+__global__ void __launch_bounds__(256) uniform_rows_kernel(const T* __restrict__ x, int ld, int D, int64_t n, double* __restrict__ uval) {
+    const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= n) return;
+    const T first = x[row * ld];
+    bool same = true;
+    for (int k = lane; k < D; k += 32) same = same && x[row * ld + k] == first;
+    same = __all_sync(0xffffffffu, same);
+    if (lane == 0) uval[row] = same ? (double)first : CRX_FROM_BITS(0x7ff8000000000000LL);
+}
+
+// the reference's own similarity of every collected candidate (crypto_rec.hpp:220, cust_vector.hpp:160-174): a warp takes runs
+// of 32 consecutive entries (segments are padded to multiples of 32, so each run belongs to one query), each lane walks its row.
+// Two rows whose coordinates are all equal (c_a and c_b) need no walk: every product is p = fl(c_a c_b), and the extended
+// accumulator holds k p exactly after k additions (53 + 7 bits), so the inner product is D p = h + l with h = fl(D p),
+// l = fma(D, p, -h) -- what the walk would leave in (h, l), checked against long double arithmetic (tests/test_x87_cpu.py).
+// Single-coin users form one large clique of mutually tied neighbours; this keeps their second pass off the FP64 pipe.
+constexpr int P2_RUN = 64;   // 32-entry blocks a warp takes at a time (one binary search per run)
 template <typename TQ, typename TB>
 __global__ void __launch_bounds__(256)
 p2_exact_kernel(const TQ* __restrict__ xq, int ldq, const double* __restrict__ sqn_q, const TB* __restrict__ xb, int ldb,
                 const double* __restrict__ sqn_b, int D, int64_t q_begin, const int32_t* __restrict__ wq, const int64_t* __restrict__ off,
-                unsigned int n, int64_t nblocks, const int32_t* __restrict__ cols, double* __restrict__ xs) {
+                unsigned int n, int64_t nblocks, const int32_t* __restrict__ cols, double* __restrict__ xs,
+                const double* __restrict__ uval_q, const double* __restrict__ uval_b) {
     __shared__ rw::WarpTile tiles[8];
     __shared__ double qvec[8][128];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    for (int64_t b = (int64_t)blockIdx.x * 8 + warp; b < nblocks; b += (int64_t)gridDim.x * 8) {
-        const int64_t base = b * 32;
-        // item = the last i with off[i] <= base  (off[n] = total > base)
+    const int64_t nruns = (nblocks + P2_RUN - 1) / P2_RUN;
+    for (int64_t run = (int64_t)blockIdx.x * 8 + warp; run < nruns; run += (int64_t)gridDim.x * 8) {
+        const int64_t b0 = run * P2_RUN, b1 = min(nblocks, b0 + P2_RUN);
+        // item of the first block = the last i with off[i] <= base  (off[n] = total > base)
         unsigned int lo = 0, hi = n;
-        while (lo < hi) { unsigned int m = (lo + hi + 1) >> 1; if (off[m] <= base) lo = m; else hi = m - 1; }
-        const int64_t qrow = q_begin + wq[lo];
-        rw::stage_vector<TQ>(xq, ldq, qrow, qvec[warp]);
-        const int mine = cols[base + lane];
-        rw::Walk wk = rw::walk_rows<TB, CRX_COSINE>(xb, ldb, D, mine >= 0 ? (int64_t)mine : -1, qvec[warp], tiles[warp]);
-        double sim = -INFINITY;
-        if (mine >= 0) { X87 ip = {wk.a, wk.b}; sim = cos_sim_x87(ip, sqn_b[mine], sqn_q[qrow]); }
-        xs[base + lane] = sim;
+        { const int64_t base = b0 * 32; while (lo < hi) { unsigned int m = (lo + hi + 1) >> 1; if (off[m] <= base) lo = m; else hi = m - 1; } }
+        int64_t next_off = off[lo + 1];
+        bool staged = false;
+        int64_t qrow = q_begin + wq[lo];
+        double uq = uval_q[qrow], nq = sqn_q[qrow];
+        for (int64_t b = b0; b < b1; b++) {
+            const int64_t base = b * 32;
+            if (base >= next_off) {
+                do { lo++; next_off = off[lo + 1]; } while (base >= next_off);
+                qrow = q_begin + wq[lo];
+                uq = uval_q[qrow]; nq = sqn_q[qrow];
+                staged = false;
+            }
+            const int mine = cols[base + lane];
+            double sim = -INFINITY;
+            bool walk = mine >= 0;
+            if (mine >= 0 && uq == uq) {
+                const double ub = uval_b[mine];
+                if (ub == ub) {
+                    const double pr = __dmul_rn(uq, ub);
+                    X87 ip;
+                    ip.h = __dmul_rn((double)D, pr);
+                    ip.l = __fma_rn((double)D, pr, -ip.h);
+                    sim = cos_sim_x87(ip, sqn_b[mine], nq);
+                    walk = false;
+                }
+            }
+            if (__any_sync(0xffffffffu, walk)) {
+                if (!staged) { rw::stage_vector<TQ>(xq, ldq, qrow, qvec[warp]); staged = true; }
+                rw::Walk wk = rw::walk_rows<TB, CRX_COSINE>(xb, ldb, D, walk ? (int64_t)mine : -1, qvec[warp], tiles[warp]);
+                if (walk) { X87 ip = {wk.a, wk.b}; sim = cos_sim_x87(ip, sqn_b[mine], nq); }
+            }
+            xs[base + lane] = sim;
+        }
         __syncwarp();
     }
 }
@@ -400,23 +447,29 @@ p2_resolve_kernel(const TB* __restrict__ xb, P2Resolve a) {
         if (lane == 0) p2_emit(a.next, qrel, (tries & 0xffff) > 8 ? -INFINITY : theta - lower, colx, tries + 1);
         return;
     }
-    // ---- T_P = the keep-th best similarity: sorted list of the best `keep`, one entry per lane
+    // ---- T_P = the keep-th best similarity: sorted list of the best `keep`, one entry per lane.  Long lists (a plateau of tied
+    // candidates) are read four 32-entry groups at a time so that enough loads are in flight
     double mine = -INFINITY, thr = -INFINITY;
     int filled = 0;
-    for (int base = 0; base < cnt; base += 32) {
-        const int e = base + lane;
-        const double k = e < cnt ? key[e] : -INFINITY;
-        unsigned want = __ballot_sync(0xffffffffu, e < cnt && k == k && (k > thr || filled < keep));
-        while (want) {
-            const int src = __ffs(want) - 1;
-            want &= want - 1;
-            const double x = __shfl_sync(0xffffffffu, k, src);
-            if (x > thr || filled < keep) {
-                const int pos = __popc(__ballot_sync(0xffffffffu, mine >= x));
-                const double up = __shfl_up_sync(0xffffffffu, mine, 1);
-                mine = lane < pos ? mine : (lane == pos ? x : up);
-                if (filled < keep) filled++;
-                thr = filled < keep ? -INFINITY : __shfl_sync(0xffffffffu, mine, keep - 1);
+    for (int base = 0; base < cnt; base += 128) {
+        double k4[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) { const int e = base + u * 32 + lane; k4[u] = e < cnt ? key[e] : -INFINITY; }
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const double k = k4[u];
+            unsigned want = __ballot_sync(0xffffffffu, base + u * 32 + lane < cnt && k == k && (k > thr || filled < keep));
+            while (want) {
+                const int src = __ffs(want) - 1;
+                want &= want - 1;
+                const double x = __shfl_sync(0xffffffffu, k, src);
+                if (x > thr || filled < keep) {
+                    const int pos = __popc(__ballot_sync(0xffffffffu, mine >= x));
+                    const double up = __shfl_up_sync(0xffffffffu, mine, 1);
+                    mine = lane < pos ? mine : (lane == pos ? x : up);
+                    if (filled < keep) filled++;
+                    thr = filled < keep ? -INFINITY : __shfl_sync(0xffffffffu, mine, keep - 1);
+                }
             }
         }
     }
@@ -425,31 +478,33 @@ p2_resolve_kernel(const TB* __restrict__ xb, P2Resolve a) {
         if (lane == 0) p2_emit(a.next, qrel, fmin(theta - lower, TP - 2.1 * eps), colx, tries + 1);
         return;
     }
-    // ---- H = { >= T_P }, e* = its last row
+    // ---- H = { >= T_P }, e* = its last row: read from the back (on a plateau it is found at once)
     int idx_e = -1;
-    for (int base = 0; base < cnt; base += 32) {
+    for (int base = (cnt - 1) & ~31; base >= 0 && idx_e < 0; base -= 32) {
         const int e = base + lane;
         const unsigned b = __ballot_sync(0xffffffffu, e < cnt && key[e] >= TP);
         if (b) idx_e = base + 31 - __clz(b);
     }
     const int estar = val[idx_e];
     const double s_estar = key[idx_e];
-    // ---- the tail behind e*: best known similarity and the first row that reaches it
+    // ---- the tail behind e*: best known similarity and the first row that reaches it (not needed when e* is a minimum of H)
     const bool tail_all = complete || estar >= colx;
     double tk = -INFINITY;
     int te = 0x7fffffff;
-    for (int base = (idx_e + 1) & ~31; base < cnt; base += 32) {
-        const int e = base + lane;
-        if (e > idx_e && e < cnt) {
-            const double k = key[e];
-            if ((tail_all || k > kappa) && k > tk) { tk = k; te = e; }   // ascending e per lane: the first one is kept
+    if (s_estar != TP) {
+        for (int base = (idx_e + 1) & ~31; base < cnt; base += 32) {
+            const int e = base + lane;
+            if (e > idx_e && e < cnt) {
+                const double k = key[e];
+                if ((tail_all || k > kappa) && k > tk) { tk = k; te = e; }   // ascending e per lane: the first one is kept
+            }
         }
-    }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        const double ok = __shfl_xor_sync(0xffffffffu, tk, o);
-        const int oe = __shfl_xor_sync(0xffffffffu, te, o);
-        if (ok > tk || (ok == tk && oe < te)) { tk = ok; te = oe; }
+        for (int o = 16; o > 0; o >>= 1) {
+            const double ok = __shfl_xor_sync(0xffffffffu, tk, o);
+            const int oe = __shfl_xor_sync(0xffffffffu, te, o);
+            if (ok > tk || (ok == tk && oe < te)) { tk = ok; te = oe; }
+        }
     }
     const bool found = te != 0x7fffffff;
     double tp;
@@ -473,18 +528,28 @@ p2_resolve_kernel(const TB* __restrict__ xb, P2Resolve a) {
             return;
         }
     }
-    // ---- R to the front, in row order
+    // ---- R to the front, in row order (four groups of 32 entries per step; rows are read for the members only)
     int m = 0;
-    for (int base = 0; base < rlim; base += 32) {
-        const int e = base + lane;
-        const bool in = e < rlim;
-        const double k = in ? key[e] : 0.0;
-        const int v = in ? val[e] : 0;
-        const bool g = in && (k >= tp || tp == -INFINITY);
-        const unsigned bg = __ballot_sync(0xffffffffu, g);
+    for (int base = 0; base < rlim; base += 128) {
+        double k4[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) { const int e = base + u * 32 + lane; k4[u] = e < rlim ? key[e] : -INFINITY; }
+        int v4[4];
+        bool g4[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const int e = base + u * 32 + lane;
+            g4[u] = e < rlim && (k4[u] >= tp || tp == -INFINITY);
+            v4[u] = g4[u] ? val[e] : 0;
+        }
         __syncwarp();
-        if (g) { const int dst = m + __popc(bg & lt); if (dst != e) { key[dst] = k; val[dst] = v; } }
-        m += __popc(bg);
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const int e = base + u * 32 + lane;
+            const unsigned bg = __ballot_sync(0xffffffffu, g4[u]);
+            if (g4[u]) { const int dst = m + __popc(bg & lt); if (dst != e) { key[dst] = k4[u]; val[dst] = v4[u]; } }
+            m += __popc(bg);
+        }
         __syncwarp();
     }
     warp_qs_topn_big(key, val, m, keep, posge[warp], hk[warp], hv[warp]);

@@ -481,33 +481,21 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         }
                     }
                 } else if (MODE == MODE_COLLECT) {
-                    float vm[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
-                    if (DENSE) {
-#pragma unroll
-                        for (int j = 0; j < 32; j++) vm[j & 3] = fmaxf(vm[j & 3], __uint_as_float(r[j]));
-                    } else {
-#pragma unroll
-                        for (int g = 0; g < 8; g++) {
-                            uint4 cc = st4[g];
-                            uint32_t c4[4] = {cc.x, cc.y, cc.z, cc.w};
-#pragma unroll
-                            for (int u = 0; u < 4; u++) {
-                                uint32_t x = cq ^ c4[u];
-                                uint32_t m = (x - low) & ~x & high;
-                                vm[u] = fmaxf(vm[u], m != 0u ? __uint_as_float(r[g * 4 + u]) : -INFINITY);
-                            }
-                        }
-                    }
-                    const float mx4 = fmaxf(fmaxf(vm[0], vm[1]), fmaxf(vm[2], vm[3]));
+                    // pass bits of the 32 scores, no data-dependent branch: rows of a large plateau pass a threshold in nearly
+                    // every chunk, and one such row would send its whole warp through a rare path (2 instructions per score
+                    // here).  The table mask and the column bound are applied to the set bits only.
                     uint32_t bits = 0;
-                    if (valid && (mx4 >= c_th || cbase + 31 > c_cx)) {
 #pragma unroll
-                        for (int j = 0; j < 32; j++) {
-                            const int c = cbase + j;
-                            uint32_t x = cq ^ reinterpret_cast<const uint32_t*>(st4)[j];
-                            bool pass = (__uint_as_float(r[j]) >= c_th || c > c_cx) && c < p.nb && ((x - low) & ~x & high) != 0u;
-                            bits |= pass ? (1u << j) : 0u;
-                        }
+                    for (int j = 0; j < 32; j++) bits |= __uint_as_float(r[j]) >= c_th ? (1u << j) : 0u;
+                    if (cbase + 31 > c_cx) bits |= cbase > c_cx ? 0xffffffffu : ~((2u << (c_cx - cbase)) - 1u);   // every column behind c_cx
+                    if (cbase + 32 > (int)p.nb) bits &= cbase >= (int)p.nb ? 0u : ((1u << ((int)p.nb - cbase)) - 1u);
+                    if (!valid) bits = 0u;
+                    uint32_t left = bits;
+                    while (left != 0u) {
+                        const int j = __ffs(left) - 1;
+                        left &= left - 1u;
+                        const uint32_t x = cq ^ reinterpret_cast<const uint32_t*>(st4)[j];
+                        if (((x - low) & ~x & high) == 0u) bits &= ~(1u << j);
                     }
                     mbuf[((t & 1) * 8 + half * 4 + rnd * 2 + ch) * TM + me] = bits;
                 } else if (MODE == MODE_ROWSUM) {

@@ -24,7 +24,7 @@ _BROADCAST = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ct
 class CrxComm(ctypes.Structure):
     """struct crx_comm (include/crx.h)."""
     _fields_ = [("rank", ctypes.c_int), ("world", ctypes.c_int), ("user", ctypes.c_void_p),
-                ("allreduce", _ALLREDUCE), ("allgather", _ALLGATHER), ("broadcast", _BROADCAST)]
+                ("allreduce", _ALLREDUCE), ("allgather", _ALLGATHER), ("broadcast", _BROADCAST), ("stream_ordered", ctypes.c_int)]
 
 
 _NP_DTYPES = {0: np.float32, 1: np.float64, 2: np.int32, 3: np.int64}   # CRX_F32, CRX_F64, CRX_I32, CRX_I64
@@ -51,7 +51,7 @@ class Comm:
         self.calls = {"allreduce": 0, "allgather": 0, "broadcast": 0}
         self.error = None
         self._cbs = (_ALLREDUCE(self._allreduce), _ALLGATHER(self._allgather), _BROADCAST(self._broadcast))
-        self.struct = CrxComm(self.rank, self.world, None, *self._cbs)
+        self.struct = CrxComm(self.rank, self.world, None, *self._cbs, 0)
 
     def ptr(self):
         return ctypes.byref(self.struct)
@@ -119,6 +119,53 @@ class Comm:
             back()
             self._finish(mem)
         return self._guard("broadcast", run)
+
+
+class NcclComm:
+    """crx_comm over NCCL inside libcrx.so (crx_comm_nccl_create, csrc/comm_nccl.cu): the collectives of the sharded entry
+    points are enqueued on the context's stream by the engine itself -- no Python on the data path, no host synchronisation
+    around device buffers.  torch.distributed only carries the 128-byte unique id from rank 0 to the others."""
+
+    def __init__(self, ctx, group=None):
+        import torch
+        import torch.distributed as dist
+        from . import capi
+        self.lib = capi.lib()
+        self.on = dist.is_initialized() and dist.get_world_size(group) > 1
+        self.rank = dist.get_rank(group) if self.on else 0
+        self.world = dist.get_world_size(group) if self.on else 1
+        ident = (ctypes.c_uint8 * 128)()
+        if self.rank == 0:
+            capi._check(self.lib.crx_comm_nccl_unique_id(ident))
+        if self.on:
+            t = torch.tensor(list(ident), dtype=torch.uint8)
+            if dist.get_backend(group) == "nccl":
+                t = t.cuda()
+            dist.broadcast(t, src=0 if group is None else dist.get_global_rank(group, 0), group=group)
+            ident = (ctypes.c_uint8 * 128)(*t.cpu().tolist())
+        self.h = ctypes.POINTER(CrxComm)()
+        capi._check(self.lib.crx_comm_nccl_create(ctx.h, ident, self.rank, self.world, ctypes.byref(self.h)))
+        self.ctx = ctx   # the communicator enqueues on this context's stream: keep it alive
+
+    def ptr(self):
+        return self.h
+
+    @property
+    def calls(self):
+        out = (ctypes.c_int64 * 3)()
+        self.lib.crx_comm_nccl_calls(self.h, out)
+        return {"allreduce": out[0], "allgather": out[1], "broadcast": out[2]}
+
+    def close(self):
+        if self.h:
+            self.lib.crx_comm_nccl_destroy(self.h)
+            self.h = ctypes.POINTER(CrxComm)()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 def shard_range(n, rank, world):

@@ -172,7 +172,19 @@ typedef struct crx_comm {
     int (*allreduce)(void* user, void* buf, int64_t count, int dtype, int op, int mem);                 /* in place */
     int (*allgather)(void* user, const void* send, void* recv, int64_t count_per_rank, int dtype, int mem);
     int (*broadcast)(void* user, void* buf, int64_t count, int dtype, int root, int mem);
+    int stream_ordered;   /* 1: collectives on DEVICE buffers are enqueued on the context's stream (no synchronisation on
+                           * either side; crx_comm_nccl_create); 0: the callback runs elsewhere and returns when done */
 } crx_comm;
+/* The same three collectives over NCCL inside libcrx.so (csrc/comm_nccl.cu), enqueued on the context's stream.  Rank 0 makes
+ * the 128-byte id and hands it to the other ranks through the caller's bootstrap (torch.distributed in dist.py, a file, MPI);
+ * every rank then calls crx_comm_nccl_create (collective).  NCCL is bound at run time (dlopen), preferring the copy the
+ * process already holds.  crx_comm_nccl_calls: number of all-reduce / all-gather / broadcast calls issued so far. */
+#define CRX_NCCL_ID_BYTES 128
+int crx_comm_nccl_version(void);   /* ncclGetVersion, 0 when NCCL cannot be loaded */
+int crx_comm_nccl_unique_id(uint8_t id[CRX_NCCL_ID_BYTES]);
+int crx_comm_nccl_create(crx_ctx* ctx, const uint8_t id[CRX_NCCL_ID_BYTES], int rank, int world, crx_comm** out);
+int crx_comm_nccl_calls(const crx_comm* comm, int64_t out[3]);
+int crx_comm_nccl_destroy(crx_comm* comm);
 #define CRX_ERR_COMM -5
 /* k_means_pp with the points sharded by contiguous row range: this rank holds global rows
  * [row_offset, row_offset + n_local).  Per round: all-reduce(max) of the normaliser, all-gather of the per-shard

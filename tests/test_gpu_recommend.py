@@ -89,6 +89,29 @@ def test_rec_lsh_cosine_oracle(ctx, port, dtype, n, P_, Nrec, k, L):
         assert np.array_equal(part[key], out[key][lo:hi]), key
 
 
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_rec_lsh_single_coin_users_form_a_clique(ctx, port, dtype):
+    """Users with ONE known coin have constant vectors (the unknown coins hold the mean = that rating): a clique of mutually
+    tied neighbours far larger than the 64-entry list, whose similarities 1 - ulp, 1, 1 + ulp decide the reference's order.
+    The second pass evaluates those pairs in closed form (p2_exact_kernel); everything must still be the reference's."""
+    U, unk, mean = synth.rating_users_fast(4000, 100, seed=41, min_known=1, max_known=4, dtype=dtype)
+    uniform = (U == U[:, :1]).all(axis=1)
+    assert uniform.sum() > 300, uniform.sum()
+    P = ctx.points(U, unk, mean)
+    t = capi.LshTables(ctx, P, "cosine", 4, 5, 100, 0.4, 99)
+    out = capi.recommend_lsh(ctx, t, 20, 5, want=WANT)
+    ref = port.recommend_lsh(U.astype(np.float64), unk, mean, COSINE, 4, 5, 100, 0.4, 20, 5, 99)
+    check_rec(ctx, out, ref)
+    # external queries take the same path with separate uniform flags
+    nb = 3000
+    V = ctx.points(U[:nb], unk[:nb], mean[:nb]); Q = ctx.points(U[nb:], unk[nb:], mean[nb:])
+    t2 = capi.LshTables(ctx, V, "cosine", 4, 5, 100, 0.4, 98)
+    out2 = capi.recommend_lsh(ctx, t2, 20, 5, queries=Q, want=WANT)
+    ref2 = port.recommend_lsh(U[:nb].astype(np.float64), unk[:nb], mean[:nb], COSINE, 4, 5, 100, 0.4, 20, 5, 98,
+                              Xq=U[nb:].astype(np.float64), unknown_q=unk[nb:], mean_q=mean[nb:])
+    check_rec(ctx, out2, ref2)
+
+
 def test_rec_lsh_normal_data_dense_and_table_modes(ctx, port):
     # i.i.d. normal points: ~27% of the rows are candidates (per-table passes win the cost model);
     # rating-like rows: ~95% (dense any-table scan wins).  Both must agree with the oracle.
