@@ -45,6 +45,11 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--min-warmup", type=int, default=3, help="profiling runs only: allow fewer than 3 warm-up steps")
+    ap.add_argument("--only", default="", help="comma-separated blocks to run: c2,lloyd,kmeanspp,cube_range,pam,lloyd_100m (default: all)")
+    ap.add_argument("--cube-points", type=int, default=10_000_000)
+    ap.add_argument("--pam-points", type=int, default=5_000_000)
+    ap.add_argument("--kpp-rounds", type=int, default=32)
+    ap.add_argument("--lloyd-full", type=int, default=100_000_000, help="rows of the one-GPU run of the whole C4 config (0 = skip; N = 1 only)")
     return ap.parse_args()
 
 
@@ -130,7 +135,7 @@ def cpu_reference_rate(U, unk, mean, threads, seconds, steps=1, warmup=0):
     t0 = time.perf_counter()
     h.query(0, 2, P_NEIGH, N_REC)
     per_q = max(1e-4, (time.perf_counter() - t0) / 2)
-    per = max(1, int(seconds / max(1, steps + warmup) / per_q))
+    per = max(1, min(n // (2 * threads), int(seconds / max(1, steps + warmup) / per_q)))   # the sample must fit the table
     sample = per * threads
     rates = []
     with ThreadPoolExecutor(max_workers=threads) as ex:
@@ -180,8 +185,8 @@ def run_reference(args):
     line = {
         "impl": "reference", "metric": "recs/sec (cosine LSH top-P recommendation)", "value": cb["value"], "unit": "recs/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sample / cb["value"],
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64 (x87 long double dot products)",
-        "data": "synthetic", "config": workload_config(U.shape[0], args.coins),
+        "higher_is_better": True, "scaling": "strong" if args.gpus > 1 else "weak", "vs_baseline": None, "dtype": "f64 (x87 long double dot products)",
+        "data": "synthetic", "config": workload_config(U.shape[0], args.coins, args.gpus),
         "cpu_baseline": cb, "e2e": {"value": cb["value"], "unit": "recs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0, "wall_s": wall,
     }
@@ -201,60 +206,51 @@ def dram_traffic(kernel, units):
     return None
 
 
-def workload_config(n, d):
-    return {"workload": "C2: %d users x %d coins, rating-like vectors (2-9 known coins/user), cosine LSH L=%d k=%d, top-P=%d neighbours, top-%d coins; "
-                        "step = create_LSH_hashtables + rec-A loop of main.cpp:159-170 over every user" % (n, d, L_TABLES, K_HASH, P_NEIGH, N_REC),
+def workload_config(n, d, world):
+    if world > 1:
+        par = ("queries of the ONE %d-user batch sharded over %d GPUs (tables replicated on every GPU, rank r answers users [r n/N, (r+1) n/N)), "
+               "recs all-gathered over NCCL inside the timed region" % (n, world))
+    else:
+        par = "one GPU holds the tables and answers every query"
+    return {"workload": "C2: %d users x %d coins, rating-like vectors (every coin known with probability nk/%d, nk ~ U{2..9}: 5.5%% of the users "
+                        "know ONE coin and have constant vectors = one clique of ~%dk mutually tied neighbours), cosine LSH L=%d k=%d, top-P=%d "
+                        "neighbours, top-%d coins; step = create_LSH_hashtables + rec-A loop of main.cpp:159-170 over every user"
+                        % (n, d, d, round(0.055 * n / 1e3), L_TABLES, K_HASH, P_NEIGH, N_REC),
             "users": n, "coins": d, "L": L_TABLES, "k": K_HASH, "P": P_NEIGH, "N_rec": N_REC,
             "l2": ("inputs (%.0f MB of user vectors + %.0f MB of split-fp16 operands) exceed the 126 MB L2; no explicit flush"
                    % (n * d * 4 / 1e6, n * 512 / 1e6)) if n * d * 4 > 126e6 else
-                  ("inputs (%.0f MB) FIT the 126 MB L2 at this --users: not a valid bench size, use the default" % (n * d * 4 / 1e6))}
+                  ("inputs (%.0f MB) FIT the 126 MB L2 at this --users: not a valid bench size, use the default" % (n * d * 4 / 1e6)),
+            "parallelism": par}
 
 
 # ------------------------------------------------------------------------------------------------
 # this engine
 # ------------------------------------------------------------------------------------------------
-def run_crx(args):
-    import torch
-    from crypto_recommendation_b200 import capi, synth
-    from crypto_recommendation_b200 import dist as cdist
-    rank, local_rank, world = cdist.init_process_group()
-    assert torch.cuda.is_available(), "bench.py --impl crx needs a CUDA device (there is no CPU fallback)"
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    stream = torch.cuda.Stream(dev)  # one explicit stream shared by torch (events, generators) and the engine
-    torch.cuda.set_stream(stream)
-    ctx = capi.Context(local_rank, stream.cuda_stream)
-    peaks = measured_peaks()
+class Rig:
+    """device, stream, engine context, communicator and the timing rule shared by every block"""
 
-    # ---------------- C2: recommendation ----------------
-    U, unk, mean = make_users(args.users, args.coins, SEED)  # every rank holds the replicated table
-    n, d = U.shape
-    U_pin = torch.from_numpy(U).pin_memory()
-    unk_pin = torch.from_numpy(unk).pin_memory()
-    mean_pin = torch.from_numpy(mean).pin_memory()
-    P = capi.Points(ctx, U_pin.numpy(), unk_pin.numpy(), mean_pin.numpy())
-    out_dev = {"recs": torch.empty((n, N_REC), dtype=torch.int32, device=dev), "ncand": torch.empty(n, dtype=torch.int32, device=dev)}
+    def __init__(self, args):
+        import torch
+        from crypto_recommendation_b200 import capi
+        from crypto_recommendation_b200 import dist as cdist
+        self.torch, self.capi, self.cdist, self.args = torch, capi, cdist, args
+        self.rank, self.local_rank, self.world = cdist.init_process_group()
+        assert torch.cuda.is_available(), "bench.py --impl crx needs a CUDA device (there is no CPU fallback)"
+        torch.cuda.set_device(self.local_rank)
+        self.dev = torch.device("cuda", self.local_rank)
+        self.stream = torch.cuda.Stream(self.dev)  # one explicit stream shared by torch (events, generators) and the engine
+        torch.cuda.set_stream(self.stream)
+        self.ctx = capi.Context(self.local_rank, self.stream.cuda_stream)
+        self.comm = cdist.NcclComm(self.ctx) if self.world > 1 else None   # collectives issued by libcrx.so itself
+        self.peaks = measured_peaks()
 
-    def step_resident():
-        t = capi.LshTables(ctx, P, "cosine", K_HASH, L_TABLES, LSH_BUCKET_DIV, EUCLID_W, SEED)
-        capi.recommend_lsh(ctx, t, P_NEIGH, N_REC, out=out_dev)
-        t.close()
-
-    recs_host = torch.empty((n, N_REC), dtype=torch.int32).pin_memory()
-
-    def step_e2e():
-        p = capi.Points(ctx, U_pin.numpy(), unk_pin.numpy(), mean_pin.numpy())
-        t = capi.LshTables(ctx, p, "cosine", K_HASH, L_TABLES, LSH_BUCKET_DIV, EUCLID_W, SEED)
-        capi.recommend_lsh(ctx, t, P_NEIGH, N_REC, out={"recs": recs_host.numpy()})
-        t.close()
-        p.close()
-
-    def timed(fn, steps, warmup, sample_clocks=False, profile=False):
+    def timed(self, fn, steps, warmup, sample_clocks=False, profile=False):
+        torch, ctx, cdist = self.torch, self.ctx, self.cdist
         for _ in range(warmup):
             fn()
-        sampler = ClockSampler(local_rank) if sample_clocks else None
+        sampler = ClockSampler(self.local_rank) if sample_clocks else None
         cdist.barrier()
-        torch.cuda.synchronize(dev)
+        torch.cuda.synchronize(self.dev)
         if profile:
             ctx.profile_reset(); ctx.profile(True)
             ctx.counters(reset=True)
@@ -262,11 +258,11 @@ def run_crx(args):
         if sampler:
             sampler.start()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(stream)
+        e0.record(self.stream)
         for _ in range(steps):
             fn()
-        e1.record(stream)
-        torch.cuda.synchronize(dev)
+        e1.record(self.stream)
+        torch.cuda.synchronize(self.dev)
         cdist.barrier()
         ms = e0.elapsed_time(e1)
         clocks = sampler.stop() if sampler else None
@@ -275,132 +271,374 @@ def run_crx(args):
             ctx.profile(False)
         return cdist.max_over_ranks(ms) / steps, launches, clocks
 
-    ms_step, launches, clocks = timed(step_resident, args.steps, max(args.min_warmup, args.warmup), sample_clocks=True, profile=True)
+    def kernel_ms(self, names, per):
+        return {k: round(self.ctx.kernel_time(k)[0] / per, 3) for k in names}
+
+    def gen_mixture(self, n, d, k, seed, centre_seed=None):
+        """n x d fp32 points of a mixture of k unit Gaussians (centres N(0, 4^2)), generated on the device in chunks"""
+        torch, dev = self.torch, self.dev
+        g = torch.Generator(device=dev); g.manual_seed(centre_seed if centre_seed is not None else seed)
+        c = torch.randn((k, d), generator=g, device=dev) * 4.0
+        g.manual_seed(seed + 7919)
+        X = torch.empty((n, d), dtype=torch.float32, device=dev)
+        for lo in range(0, n, 1 << 20):
+            hi = min(n, lo + (1 << 20))
+            X[lo:hi] = c[torch.randint(0, k, (hi - lo,), generator=g, device=dev)] + torch.randn((hi - lo, d), generator=g, device=dev)
+        return X, c
+
+    def release(self):
+        self.ctx.trim()
+        self.torch.cuda.empty_cache()
+
+
+P2_KERNELS = ("uniform_rows", "p2_prepare", "tc_gather", "tc_collect_scan", "p2_sizes", "p2_trim", "p2_linearize", "p2_exact", "p2_resolve",
+              "p2_collect_simt", "p2_leftover")
+
+
+def bench_c2(rig, args):
+    """BASELINE.json configs[1]: the headline.  N > 1: strong scaling -- the same 1M-user batch, queries sharded."""
+    torch, capi, cdist, ctx, dev = rig.torch, rig.capi, rig.cdist, rig.ctx, rig.dev
+    world, rank = rig.world, rig.rank
+    U, unk, mean = make_users(args.users, args.coins, SEED)  # every rank holds the replicated table
+    n, d = U.shape
+    lo, hi = cdist.shard_range(n, rank, world)
+    per = -(-n // world)     # rows per rank in the gathered buffer (the last shard may be shorter)
+    U_pin = torch.from_numpy(U).pin_memory()
+    unk_pin = torch.from_numpy(unk).pin_memory()
+    mean_pin = torch.from_numpy(mean).pin_memory()
+    P = capi.Points(ctx, U_pin.numpy(), unk_pin.numpy(), mean_pin.numpy())
+    mine = {"recs": torch.zeros((per, N_REC), dtype=torch.int32, device=dev), "ncand": torch.zeros(per, dtype=torch.int32, device=dev)}
+    gathered = torch.empty((world * per, N_REC), dtype=torch.int32, device=dev) if world > 1 else None
+
+    def answer(points, out):
+        t = capi.LshTables(ctx, points, "cosine", K_HASH, L_TABLES, LSH_BUCKET_DIV, EUCLID_W, SEED)
+        view = {k: v[:hi - lo] for k, v in out.items()}
+        capi.recommend_lsh(ctx, t, P_NEIGH, N_REC, q_begin=lo, q_end=hi, out=view)
+        t.close()
+        if world > 1:
+            rig.comm.allgather(out["recs"], gathered)
+
+    def step_resident():
+        answer(P, mine)
+
+    recs_host = torch.empty((world * per if world > 1 else n, N_REC), dtype=torch.int32).pin_memory()
+
+    def step_e2e():
+        p = capi.Points(ctx, U_pin.numpy(), unk_pin.numpy(), mean_pin.numpy())
+        answer(p, {"recs": mine["recs"]})
+        if rank == 0:   # the caller's answer: every user's coins in host memory
+            recs_host.copy_(gathered if world > 1 else mine["recs"][:n], non_blocking=True)
+        p.close()
+
+    warm = max(args.min_warmup, args.warmup)
+    ms_step, launches, clocks = rig.timed(step_resident, args.steps, warm, sample_clocks=True, profile=True)
     scan_name = "tc_topp_scan" if ctx.kernel_time("tc_topp_scan")[1] > 0 else "topp_scan"
     scan_ms, scan_launches = ctx.kernel_time(scan_name)
-    kernel_ms = {k: round(ctx.kernel_time(k)[0] / args.steps, 3) for k in (
-        "tc_topp_scan", "topp_scan", "rec_finalize", "rec_topn", "hash_rows", "tc_prep", "pack_codes", "subset_hist", "subset_count",
-        "iota", "bucket_offsets", "fill_lists", "sq_sizes")}
-    ncand_total = float(out_dev["ncand"].to(torch.float64).sum().item())
-    counters = {k: v / args.steps for k, v in ctx.counters().items()}   # per step of 1M queries (near-tie / fallback counts)
-    value = world * n / (ms_step / 1e3)
-    flops_per_launch = 2.0 * d * ncand_total * args.steps / max(1, scan_launches)
+    kernel_ms = rig.kernel_ms(("tc_topp_scan", "topp_scan", "rec_finalize", "hash_rows", "tc_prep", "pack_codes", "subset_hist", "subset_count",
+                               "bucket_offsets") + P2_KERNELS, args.steps)
+    ncand_local = float(mine["ncand"][:hi - lo].to(torch.float64).sum().item())
+    counters = {k: v / args.steps for k, v in ctx.counters().items()}   # this rank's share of the queries, per step
+    value = n / (ms_step / 1e3)
+    flops_per_launch = 2.0 * d * ncand_local * args.steps / max(1, scan_launches)
     achieved_tf = flops_per_launch / (scan_ms / max(1, scan_launches) * 1e-3) / 1e12 if scan_ms > 0 else 0.0
     tc = scan_name == "tc_topp_scan"
-    # tensor path: 3 fp16 products (hi*hi, lo*hi, hi*lo) over D rounded up to a multiple of 16 columns
-    tc_factor = 3.0 * (16 * ((d + 15) // 16)) / d
+    tc_factor = 3.0 * (16 * ((d + 15) // 16)) / d   # 3 fp16 products (hi*hi, lo*hi, hi*lo) over D rounded up to a multiple of 16
+    peak = rig.peaks["bf16_tflops_sustained"] or rig.peaks["bf16_tflops"]
     roofline = {"kernel": ("tc_scan_kernel<TOPP> (tcgen05 split-fp16 cosine scan, per-row top-64 in the epilogue)" if tc else
                            "topp_scan_kernel (FP64 SIMT masked cosine scan + per-query top-32 list)"), "bound": "tensor",
-                "achieved": achieved_tf, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s", "frac": achieved_tf / peaks["bf16_tflops"],
-                "traffic": dram_traffic("tc_topp_scan" if tc else "topp_scan", n), "peak_source": peaks["which"] + " bf16 dense GEMM (burst)",
+                "achieved": achieved_tf, "peak": peak, "unit": "TFLOP/s", "frac": achieved_tf / peak,
+                "traffic": dram_traffic("tc_topp_scan" if tc else "topp_scan", n) if world == 1 else None,
+                "peak_source": rig.peaks["which"] + " bf16 dense GEMM, sustained (the kernel is timed inside a multi-second region); burst %.1f" % rig.peaks["bf16_tflops"],
                 "pipe": ("tcgen05.mma kind::f16 M128 N256 K16, fp32 accumulate in TMEM; executed tensor flops = %.2fx algorithmic "
                          "(3 split-fp16 products, D padded to a multiple of 16)" % tc_factor) if tc else "FP64 SIMT FMA",
                 "executed_tensor_tflops": achieved_tf * tc_factor if tc else None,
-                "executed_frac_of_peak": achieved_tf * tc_factor / peaks["bf16_tflops"] if tc else None,
-                "algorithmic_flops": "2*D*sum|cand(u)|", "kernel_ms_all": kernel_ms,
-                "kernel_ms_per_step": scan_ms / args.steps, "share_of_step": scan_ms / args.steps / ms_step}
-
-    e2e_ms, _, _ = timed(step_e2e, max(1, min(2, args.steps)), 2)
+                "executed_frac_of_peak": achieved_tf * tc_factor / peak if tc else None,
+                "algorithmic_flops": "2*D*sum|cand(u)| over this rank's queries", "kernel_ms_all": kernel_ms,
+                "kernel_ms_per_step": scan_ms / args.steps, "share_of_step": scan_ms / args.steps / ms_step,
+                "second_pass_ms_per_step": round(sum(kernel_ms[k] for k in P2_KERNELS), 3)}
+    e2e_ms, _, _ = rig.timed(step_e2e, args.steps, 2)
     h2d = U_pin.numel() * 4 + unk_pin.numel() + mean_pin.numel() * 8
     d2h = recs_host.numel() * 4
-    e2e = {"value": world * n / (e2e_ms / 1e3), "unit": "recs/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-           "ms_per_step": e2e_ms}
+    e2e = {"value": n / (e2e_ms / 1e3), "unit": "recs/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_ms,
+           "note": "every rank uploads the replicated table (h2d is per rank); rank 0 reads all recs back"}
     P.close()
-
-    # ---------------- C4 shard: Lloyd assignment + k-means update ----------------
-    lloyd = None
-    if not args.no_lloyd:
-        npts, dd, kk = args.lloyd_points, args.lloyd_d, args.lloyd_k
-        g = torch.Generator(device=dev); g.manual_seed(1234)
-        centres = torch.randn((kk, dd), generator=g, device=dev) * 4.0   # ONE mixture for the whole job ...
-        g.manual_seed(1235 + rank)                                       # ... every rank draws its own shard of points from it
-        X = torch.empty((npts, dd), dtype=torch.float32, device=dev)
-        CH = 1 << 20
-        for lo in range(0, npts, CH):  # mixture of K unit Gaussians, generated on the device in chunks
-            hi = min(npts, lo + CH)
-            which = torch.randint(0, kk, (hi - lo,), generator=g, device=dev)
-            X[lo:hi] = centres[which] + torch.randn((hi - lo, dd), generator=g, device=dev)
-        Q = capi.Points(ctx, X)
-        del X
-        C = centres.to(torch.float64).contiguous()
-        if world > 1:
-            torch.distributed.broadcast(C, 0)
-        labels = torch.empty(npts, dtype=torch.int32, device=dev)
-        dists = torch.empty(npts, dtype=torch.float64, device=dev)
-        sums = torch.empty((kk, dd), dtype=torch.float64, device=dev)
-        counts = torch.empty(kk, dtype=torch.int64, device=dev)
-        newC = torch.empty_like(C)
-
-        def step_assign():
-            capi.lloyds_assignment(ctx, Q, C, None, "euclidean", labels, dists)
-
-        def step_kmeans():
-            capi.lloyds_assignment(ctx, Q, C, None, "euclidean", labels, dists)
-            capi.cluster_sums(ctx, Q, labels, kk, sums, counts)
-            cdist.allreduce_cluster_sums(sums, counts)
-            capi.k_means_finish(ctx, sums, counts, C, "euclidean", 0.05, newC)
-
-        def step_assign_labels():   # dists = NULL: what the k-means loop needs (main.cpp:96-103 never reads the stored distance)
-            capi.lloyds_assignment(ctx, Q, C, None, "euclidean", labels, want_dists=False)
-
-        def step_kmeans_labels():
-            capi.lloyds_assignment(ctx, Q, C, None, "euclidean", labels, want_dists=False)
-            capi.cluster_sums(ctx, Q, labels, kk, sums, counts)
-            cdist.allreduce_cluster_sums(sums, counts)
-            capi.k_means_finish(ctx, sums, counts, C, "euclidean", 0.05, newC)
-
-        a_ms, a_launch, _ = timed(step_assign, args.steps, args.min_warmup)
-        k_ms, _, _ = timed(step_kmeans, args.steps, 3)   # the first all-reduces set up NCCL channels
-        al_ms, _, _ = timed(step_assign_labels, args.steps, 1)
-        kl_ms, _, _ = timed(step_kmeans_labels, args.steps, 2)
-        ctx.profile_reset(); ctx.profile(True)
-        step_kmeans(); torch.cuda.synchronize(dev)
-        ctx.profile(False)
-        breakdown = {k: round(ctx.kernel_time(k)[0], 3) for k in ("tc_argmin_scan", "lloyd_refine", "lloyd_scan", "tc_prep", "maxabs", "half_norm", "chunk_sums",
-                                                                   "combine_sums", "kmeans_finish", "select_centroids", "bucket_offsets", "iota", "pad_centroids")}
-        ctx.profile_reset(); ctx.profile(True)
-        for _ in range(args.steps):
-            step_assign()
-        torch.cuda.synchronize(dev)
-        ctx.profile(False)
-        ltc = ctx.kernel_time("tc_argmin_scan")[1] > 0
-        lk_ms, lk_n = ctx.kernel_time("tc_argmin_scan" if ltc else "lloyd_scan")
-        lr_ms, _ = ctx.kernel_time("lloyd_refine")
-        lfac = 3.0 * (16 * ((dd + 15) // 16)) / dd
-        fl = 2.0 * dd * npts * kk
-        lloyd = {"metric": "Lloyd assign pts*centroids/s", "value": world * npts * kk / (a_ms / 1e3), "unit": "pts*centroids/s",
-                 "ms_per_step": a_ms, "kmeans_iteration_ms": k_ms, "kmeans_kernel_ms": breakdown, "scaling": "weak",
-                 "labels_only": {"assign_ms": al_ms, "kmeans_iteration_ms": kl_ms, "value": world * npts * kk / (al_ms / 1e3),
-                                 "note": "crx_lloyds_assignment with dists = NULL; NOT the headline (the reference stores the distance)"},
-                 "config": {"workload": "C4 shard: %d x %d fp32 points per GPU, K=%d, euclidean; bit-exact FP64 distances" % (npts, dd, kk)},
-                 "roofline": {"kernel": "tc_scan_kernel<ARGMIN> (tcgen05 split-fp16 filter) + lloyd_refine_kernel (exact FP64 distance of the winner)" if ltc else "lloyd_scan_kernel (FP64 SIMT)",
-                              "bound": "tensor", "achieved": fl / (lk_ms / max(1, lk_n) * 1e-3) / 1e12,
-                              "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
-                              "frac": fl / (lk_ms / max(1, lk_n) * 1e-3) / 1e12 / peaks["bf16_tflops"],
-                              "traffic": dram_traffic("tc_argmin_scan" if ltc else "lloyd_scan", npts),
-                              "executed_tensor_tflops": fl * lfac / (lk_ms / max(1, lk_n) * 1e-3) / 1e12 if ltc else None,
-                              "pipe": ("tcgen05.mma kind::f16, 3 split-fp16 products (%.2fx algorithmic flops), then exact FP64 refine" % lfac) if ltc
-                                      else "FP64 SIMT (sub, mul, add per element: 3 FP64 ops for the 2 algorithmic flops)",
-                              "scan_ms": lk_ms / max(1, lk_n), "refine_ms": lr_ms / max(1, lk_n),
-                              "hbm_floor_ms": npts * (4 * dd + 12) / (peaks["hbm_gbs"] * 1e6)}}
-        Q.close()
-
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu, _ = cpu_reference_rate(U, unk, mean, 1, args.cpu_seconds)
-        if lloyd is not None:
-            lloyd["cpu_baseline"] = cpu_lloyd_rate(args.lloyd_d, args.lloyd_k, min(8.0, args.cpu_seconds))
+    return {"metric": "recs/sec (cosine LSH top-P recommendation)", "value": value, "unit": "recs/s", "n_gpus": world,
+            "steps": args.steps, "warmup": warm, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong" if world > 1 else "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(n, d, world), "clocks": clocks,
+            "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
+            "mean_candidates_per_user": ncand_local / max(1, hi - lo), "exactness_counters_per_step": counters}
 
-    if rank == 0:
-        line = {"metric": "recs/sec (cosine LSH top-P recommendation)", "value": value, "unit": "recs/s", "n_gpus": world,
-                "steps": args.steps, "warmup": max(args.min_warmup, args.warmup), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
-                "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(n, d), "clocks": clocks,
-                "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "lloyd": lloyd,
-                "mean_candidates_per_user": ncand_total / n, "exactness_counters_per_step": counters}
-        line["config"]["parallelism"] = "queries: %d independent replicas of the full batch (tables replicated); Lloyd: rows sharded, NCCL all-reduce of sums" % world
+
+def bench_lloyd(rig, args, npts, tag):
+    """C4: Lloyd assignment + k-means update, rows sharded (weak: `npts` rows per GPU), NCCL all-reduce issued by libcrx.so"""
+    torch, capi, ctx, dev = rig.torch, rig.capi, rig.ctx, rig.dev
+    world, rank = rig.world, rig.rank
+    dd, kk = args.lloyd_d, args.lloyd_k
+    X, centres = rig.gen_mixture(npts, dd, kk, 1235 + rank, centre_seed=1234)   # ONE mixture, every rank its own shard of points
+    Q = capi.Points(ctx, X)
+    del X
+    torch.cuda.empty_cache()
+    C = centres.to(torch.float64).contiguous()
+    labels = torch.empty(npts, dtype=torch.int32, device=dev)
+    dists = torch.empty(npts, dtype=torch.float64, device=dev)
+
+    def step_assign():
+        capi.lloyds_assignment(ctx, Q, C, None, "euclidean", labels, dists)
+
+    def step_kmeans():
+        capi.lloyds_assignment(ctx, Q, C, None, "euclidean", labels, dists)
+        capi.k_means_sharded(ctx, Q, labels, C, "euclidean", 0.05, rig.comm)
+
+    def step_assign_labels():   # dists = NULL: what the k-means loop needs (main.cpp:96-103 never reads the stored distance)
+        capi.lloyds_assignment(ctx, Q, C, None, "euclidean", labels, want_dists=False)
+
+    a_ms, _, _ = rig.timed(step_assign, args.steps, args.min_warmup)
+    k_ms, _, _ = rig.timed(step_kmeans, args.steps, 3)   # the first all-reduces set up NCCL channels
+    al_ms, _, _ = rig.timed(step_assign_labels, args.steps, 1)
+    ctx.profile_reset(); ctx.profile(True)
+    step_kmeans(); torch.cuda.synchronize(dev)
+    ctx.profile(False)
+    breakdown = rig.kernel_ms(("tc_argmin_scan", "lloyd_refine", "lloyd_scan", "lloyd_label", "tc_prep", "maxabs", "half_norm", "chunk_sums", "combine_sums",
+                               "pack_counts", "kmeans_finish", "select_centroids", "bucket_offsets", "iota", "pad_centroids"), 1)
+    ctx.profile_reset(); ctx.profile(True)
+    for _ in range(args.steps):
+        step_assign()
+    torch.cuda.synchronize(dev)
+    ctx.profile(False)
+    ltc = ctx.kernel_time("tc_argmin_scan")[1] > 0
+    lk_ms, lk_n = ctx.kernel_time("tc_argmin_scan" if ltc else "lloyd_scan")
+    lr_ms, _ = ctx.kernel_time("lloyd_refine")
+    lfac = 3.0 * (16 * ((dd + 15) // 16)) / dd
+    fl = 2.0 * dd * npts * kk
+    peak = rig.peaks["bf16_tflops"]
+    out = {"metric": "Lloyd assign pts*centroids/s", "value": world * npts * kk / (a_ms / 1e3), "unit": "pts*centroids/s",
+           "ms_per_step": a_ms, "kmeans_iteration_ms": k_ms, "kmeans_kernel_ms": breakdown, "scaling": "weak",
+           "labels_only": {"assign_ms": al_ms, "value": world * npts * kk / (al_ms / 1e3),
+                           "note": "crx_lloyds_assignment with dists = NULL; NOT the headline (the reference stores the distance)"},
+           "config": {"workload": "%s: %d x %d fp32 points per GPU (%d in total), K=%d, euclidean; labels + bit-exact FP64 distances; k-means iteration = "
+                                  "assign + crx_k_means_sharded (one ncclAllReduce of K*D sums + K counts)" % (tag, npts, dd, world * npts, kk)},
+           "roofline": {"kernel": "tc_scan_kernel<ARGMIN> (tcgen05 split-fp16 filter) + lloyd_refine_kernel (exact FP64 distance of the winner)" if ltc else "lloyd_scan_kernel (FP64 SIMT)",
+                        "bound": "tensor", "achieved": fl / (lk_ms / max(1, lk_n) * 1e-3) / 1e12, "peak": peak, "unit": "TFLOP/s",
+                        "frac": fl / (lk_ms / max(1, lk_n) * 1e-3) / 1e12 / peak, "peak_source": rig.peaks["which"] + " bf16 dense GEMM (burst: the kernel runs for milliseconds)",
+                        "traffic": dram_traffic("tc_argmin_scan" if ltc else "lloyd_scan", npts),
+                        "executed_tensor_tflops": fl * lfac / (lk_ms / max(1, lk_n) * 1e-3) / 1e12 if ltc else None,
+                        "pipe": ("tcgen05.mma kind::f16, 3 split-fp16 products (%.2fx algorithmic flops), then exact FP64 refine" % lfac) if ltc
+                                else "FP64 SIMT (sub, mul, add per element: 3 FP64 ops for the 2 algorithmic flops)",
+                        "scan_ms": lk_ms / max(1, lk_n), "refine_ms": lr_ms / max(1, lk_n),
+                        "hbm_floor_ms": npts * (4 * dd + 12) / (rig.peaks["hbm_gbs"] * 1e6)}}
+    if rig.comm is not None:
+        out["collectives_issued"] = rig.comm.calls
+    Q.close()
+    del labels, dists
+    rig.release()
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and tag.startswith("C4 shard"):
+        out["cpu_baseline"] = cpu_lloyd_rate(dd, kk, min(8.0, args.cpu_seconds))
+    return out
+
+
+def bench_kmeanspp(rig, args):
+    """C4 initialisation: k-means++ rounds over rows sharded across the ranks (weak: --lloyd-points rows per GPU)"""
+    torch, capi, ctx = rig.torch, rig.capi, rig.ctx
+    world, rank = rig.world, rig.rank
+    npts, dd = args.lloyd_points, args.lloyd_d
+    X, _ = rig.gen_mixture(npts, dd, args.lloyd_k, 2235 + rank, centre_seed=1234)
+    Q = capi.Points(ctx, X)
+    del X
+    torch.cuda.empty_cache()
+    K0, K1 = 9, 9 + args.kpp_rounds
+
+    def run(K):
+        return lambda: capi.k_means_pp_sharded(ctx, Q, rank * npts, world * npts, K, "euclidean", 5, rig.comm)
+
+    run(K0)()
+    ms0, _, _ = rig.timed(run(K0), 1, 0)
+    ms1, _, _ = rig.timed(run(K1), 1, 0, profile=True)
+    names = ("kpp_update", "kpp_filter", "kpp_prune", "kpp_cdist", "kpp_prob", "kpp_total", "kpp_pick", "kpp_share")
+    km = rig.kernel_ms(names, K1 - 1)
+    per_round = (ms1 - ms0) / (K1 - K0)     # steady rounds: the first ones (no pruning yet) are in both runs
+    bytes_round = npts * (4 * dd + 16)
+    gbs = bytes_round / (per_round * 1e6)
+    out = {"metric": "k-means++ ms per round", "value": per_round, "unit": "ms/round", "higher_is_better": False, "scaling": "weak",
+           "rounds_timed": K1 - K0, "ms_total_K%d" % K1: ms1, "points_per_s_per_round": world * npts / (per_round * 1e-3),
+           "kernel_ms_per_round": km,
+           "config": {"workload": "C4 initialisation: k-means++ over %d x %d fp32 points per GPU (%d in total), rounds %d..%d (steady state: triangle-inequality "
+                                  "pruning + fp32 filter + exact update), draws and prefix search on the device, %s"
+                                  % (npts, dd, world * npts, K0, K1 - 1, "3 NCCL collectives per round issued by libcrx.so" if world > 1 else "no host round trip per round")},
+           "roofline": {"kernel": "kpp_prune + kpp_filter + kpp_update + kpp_prob + cub scan (one round)", "bound": "hbm", "achieved": gbs,
+                        "peak": rig.peaks["hbm_gbs"], "unit": "GB/s", "frac": gbs / rig.peaks["hbm_gbs"],
+                        "algorithmic_bytes": "(4D + 16) B per point and round (SURVEY 8d): the pruning reads fewer, so frac can exceed what a streaming pass could reach",
+                        "traffic": None}}
+    if rig.comm is not None:
+        out["collectives_issued"] = rig.comm.calls
+    Q.close()
+    rig.release()
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        from oracle import load, EUCLIDEAN
+        from crypto_recommendation_b200 import synth
+        o = load("reference") or load("port")
+        n, K = 10_000, 17
+        Xc = synth.gaussian_mixture(n, dd, 64, seed=4).astype(np.float64)
+        t0 = time.perf_counter(); o.k_means_pp(Xc, K, EUCLIDEAN, 5); dt = time.perf_counter() - t0
+        out["cpu_baseline"] = {"value": dt / (K - 1) * 1e3 * (npts / n), "unit": "ms/round (scaled linearly from N=%d to N=%d)" % (n, npts), "cores": 1, "kind": o.kind,
+                               "sample": "k_means_pp N=%d K=%d D=%d on one core: %.1f ms/round measured" % (n, K, dd, dt / (K - 1) * 1e3)}
+    return out
+
+
+def bench_cube_range(rig, args):
+    """C3: Euclidean hypercube (d'=16) build + range-search assignment with 64 probes, K=1024; N > 1: centroids split (strong)"""
+    torch, capi, ctx, dev = rig.torch, rig.capi, rig.ctx, rig.dev
+    world, rank = rig.world, rig.rank
+    n, dd, K, probes, dprime, w = args.cube_points, 128, 1024, 64, 16, 4.0
+    X, _ = rig.gen_mixture(n, dd, 1024, 3001)    # replicated: the same points on every rank
+    P = capi.Points(ctx, X)
+    del X
+    torch.cuda.empty_cache()
+    cube = [None]
+
+    def build():
+        if cube[0] is not None:
+            cube[0].close()
+        cube[0] = capi.Hypercube(ctx, P, "euclidean", dprime, w, 9)
+
+    b_ms, _, _ = rig.timed(build, args.steps, 1, profile=True)
+    hash_ms = ctx.kernel_time("hash_rows")[0] / args.steps
+    cidx = capi.rand_selection(ctx, P, K, 3)
+    outs = (torch.empty(n, dtype=torch.int32, device=dev), torch.empty(n, dtype=torch.float64, device=dev), torch.empty(n, dtype=torch.int32, device=dev))
+
+    def step():
+        capi.cube_range_assignment(ctx, P, cube[0], cidx, "euclidean", probes, comm=rig.comm, out=outs)
+
+    ms, launches, _ = rig.timed(step, args.steps, 2, profile=True)
+    km = rig.kernel_ms(("range_fire", "range_hist", "range_finalize", "tc_argmin_scan", "lloyd_refine", "lloyd_scan", "tc_prep", "gather_rows", "compact", "min_pair"), args.steps)
+    assigned = int((outs[2] >= 0).sum().item())
+    remainder = n - assigned
+    # algorithmic work (SURVEY 8d): the probes gather |bucket| rows of 4D bytes per centroid; the Lloyd pass over the remainder is 2 D K flop per point
+    fl = 2.0 * dd * remainder * K
+    tms = km["tc_argmin_scan"] if km["tc_argmin_scan"] > 0 else km["lloyd_scan"]
+    out = {"metric": "cube range-search assignment pts/s", "value": n / (ms * 1e-3), "unit": "pts/s", "ms_per_step": ms, "scaling": "strong" if world > 1 else "weak",
+           "cube_build_ms": b_ms, "cube_build_hash_ms": hash_ms, "assigned_by_range_search": assigned, "kernel_ms": km, "gpu_launches": int(launches),
+           "config": {"workload": "C3: %d x %d fp32 points (mixture of 1024 Gaussians), Euclidean hypercube d'=%d w=%.1f, K=%d random centroids, probes=%d, "
+                                  "range search + lloyds_for_remaining; results left on the device%s"
+                                  % (n, dd, dprime, w, K, probes, "; points replicated, centroids / remainder rows split over the ranks" if world > 1 else "")},
+           "roofline": {"kernel": "tc_scan_kernel<ARGMIN> over the remainder (the probes themselves take %.2f ms)" % km["range_fire"], "bound": "tensor",
+                        "achieved": fl / (tms * 1e-3) / 1e12 * (1.0 / world if world > 1 else 1.0) if tms > 0 else 0.0, "peak": rig.peaks["bf16_tflops"], "unit": "TFLOP/s",
+                        "frac": (fl / (tms * 1e-3) / 1e12 * (1.0 / world if world > 1 else 1.0) / rig.peaks["bf16_tflops"]) if tms > 0 else 0.0,
+                        "hash_pass": {"bound": "hbm", "achieved": n * (4 * dd + 4 * dprime) / (hash_ms * 1e6) if hash_ms > 0 else None, "peak": rig.peaks["hbm_gbs"], "unit": "GB/s",
+                                      "frac": n * (4 * dd + 4 * dprime) / (hash_ms * 1e6) / rig.peaks["hbm_gbs"] if hash_ms > 0 else None},
+                        "traffic": None}}
+    cube[0].close(); P.close()
+    del outs
+    rig.release()
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        from oracle import load, EUCLIDEAN
+        from crypto_recommendation_b200 import synth
+        o = load("reference") or load("port")
+        nc, Kc = 50_000, 64
+        Xc = synth.gaussian_mixture(nc, dd, 64, seed=6).astype(np.float64)
+        ci = o.rand_selection(Xc, Kc, 7)
+        t0 = time.perf_counter(); o.cube_range_assignment(Xc, ci, EUCLIDEAN, 10, 4.0, 32, 8); dt = time.perf_counter() - t0
+        out["cpu_baseline"] = {"value": nc / dt, "unit": "pts/s", "cores": 1, "kind": o.kind,
+                               "sample": "cube_range_assignment N=%d K=%d d'=10 probes=32 on one core (cost grows with K: the bench config has K=1024)" % (nc, Kc)}
+    return out
+
+
+def bench_pam(rig, args):
+    """C5: Euclidean LSH tables, LSH range-search assignment and the PAM medoid update, K=256; N > 1: work split (strong)"""
+    torch, capi, ctx, dev = rig.torch, rig.capi, rig.ctx, rig.dev
+    world, rank = rig.world, rig.rank
+    n, dd, K = args.pam_points, 100, 256
+    X, _ = rig.gen_mixture(n, dd, 256, 4001)
+    P = capi.Points(ctx, X)
+    del X
+    torch.cuda.empty_cache()
+    tab = [None]
+
+    def build():
+        if tab[0] is not None:
+            tab[0].close()
+        tab[0] = capi.LshTables(ctx, P, "euclidean", K_HASH, L_TABLES, LSH_BUCKET_DIV, EUCLID_W, 11)
+
+    b_ms, _, _ = rig.timed(build, args.steps, 1)
+    cidx = capi.rand_selection(ctx, P, K, 6)
+    outs = (torch.empty(n, dtype=torch.int32, device=dev), torch.empty(n, dtype=torch.float64, device=dev), torch.empty(n, dtype=torch.int32, device=dev))
+
+    def assign():
+        capi.lsh_range_assignment(ctx, P, tab[0], cidx, "euclidean", comm=rig.comm, out=outs)
+
+    a_ms, _, _ = rig.timed(assign, args.steps, 2)
+    labels = outs[0]
+    sizes = torch.bincount(labels.to(torch.int64), minlength=K).to(torch.float64)
+    pairs = float((sizes * sizes).sum().item())
+
+    def update():
+        capi.pam_lloyds(ctx, P, labels, cidx, "euclidean", comm=rig.comm)
+
+    ctx.counters(reset=True)
+    u_ms, launches, _ = rig.timed(update, args.steps, 2, profile=True)
+    km = rig.kernel_ms(("tc_rowsum_scan", "pam_rowsum", "tc_prep", "pam_bounds", "pam_exact", "pam_final", "bucket_offsets"), args.steps)
+    scan = km["tc_rowsum_scan"] if km["tc_rowsum_scan"] > 0 else km["pam_rowsum"]
+    fl = 2.0 * dd * pairs / world
+    fac = 3.0 * (16 * ((dd + 15) // 16)) / dd
+    out = {"metric": "PAM update pair distances/s", "value": pairs / (u_ms * 1e-3), "unit": "pair distances/s", "ms_per_step": u_ms, "scaling": "strong" if world > 1 else "weak",
+           "lsh_build_ms": b_ms, "lsh_range_assignment_ms": a_ms, "pair_distances": pairs, "kernel_ms": km, "gpu_launches": int(launches),
+           "exact_resums_per_step": ctx.counters()["pam_exact"] / args.steps,
+           "config": {"workload": "C5: %d x %d fp32 points (mixture of 256 Gaussians), Euclidean LSH L=%d k=%d w=%.1f, K=%d: table build, lsh_range_assignment, pam_lloyds "
+                                  "(medoid = member with the smallest sum of distances to its cluster)%s"
+                                  % (n, dd, L_TABLES, K_HASH, EUCLID_W, K, "; points replicated, candidate rows split over the ranks, one all-reduce of the row sums" if world > 1 else "")},
+           "roofline": {"kernel": "tc_scan_kernel<ROWSUM> (tcgen05 split-fp16 pair distances + error bars, 10-instruction epilogue per pair)", "bound": "tensor",
+                        "achieved": fl / (scan * 1e-3) / 1e12 if scan > 0 else 0.0, "peak": rig.peaks["bf16_tflops"], "unit": "TFLOP/s",
+                        "frac": fl / (scan * 1e-3) / 1e12 / rig.peaks["bf16_tflops"] if scan > 0 else 0.0,
+                        "executed_tensor_tflops": fl * fac / (scan * 1e-3) / 1e12 if scan > 0 else None,
+                        "algorithmic_flops": "2 D per ordered pair of co-members (this rank's share)", "traffic": dram_traffic("tc_rowsum_scan", n)}}
+    tab[0].close(); P.close()
+    del outs
+    rig.release()
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        from oracle import load, EUCLIDEAN
+        from crypto_recommendation_b200 import synth
+        o = load("reference") or load("port")
+        nc, Kc = 4_000, 4
+        Xc = synth.gaussian_mixture(nc, dd, Kc, seed=5).astype(np.float64)
+        ci = o.rand_selection(Xc, Kc, 6)
+        lab, _ = o.lloyds_assignment(Xc, Xc[ci], ci, EUCLIDEAN)
+        t0 = time.perf_counter(); o.pam_lloyds(Xc, lab, ci, EUCLIDEAN); dt = time.perf_counter() - t0
+        pc = float((np.bincount(lab, minlength=Kc).astype(np.float64) ** 2).sum())
+        out["cpu_baseline"] = {"value": pc / dt, "unit": "pair distances/s", "cores": 1, "kind": o.kind, "sample": "pam_lloyds N=%d K=%d D=%d on one core" % (nc, Kc, dd)}
+    return out
+
+
+def run_crx(args):
+    rig = Rig(args)
+    torch = rig.torch
+    only = set(args.only.split(",")) if args.only else None
+    want = lambda name: only is None or name in only
+
+    def guarded(name, fn):
+        if not want(name):
+            return None
+        try:
+            return fn()
+        except Exception as e:   # a secondary block must not take the headline down with it
+            rig.release()
+            return {"error": "%s: %s" % (type(e).__name__, str(e)[:300])}
+
+    line = bench_c2(rig, args) if want("c2") else {"metric": "recs/sec (cosine LSH top-P recommendation)", "value": None, "n_gpus": rig.world, "skipped": "--only"}
+    rig.release()
+    line["lloyd"] = None if args.no_lloyd else guarded("lloyd", lambda: bench_lloyd(rig, args, args.lloyd_points, "C4 shard (1/8 of the 100M config)"))
+    line["kmeanspp"] = guarded("kmeanspp", lambda: bench_kmeanspp(rig, args))
+    line["cube_range"] = guarded("cube_range", lambda: bench_cube_range(rig, args))
+    line["pam"] = guarded("pam", lambda: bench_pam(rig, args))
+    if rig.world == 1 and args.lloyd_full > 0:
+        line["lloyd_100m"] = guarded("lloyd_100m", lambda: bench_lloyd(rig, args, args.lloyd_full, "C4 whole config on ONE GPU"))
+    if rig.rank == 0:
         print(json.dumps(line))
-    ctx.close()
-    if world > 1:
+    if rig.comm is not None:
+        rig.comm.close()
+    rig.ctx.close()
+    if rig.world > 1:
         torch.distributed.destroy_process_group()
 
 

@@ -22,7 +22,7 @@ METRICS = {"euclidean": EUCLIDEAN, "cosine": COSINE, EUCLIDEAN: EUCLIDEAN, COSIN
 # every symbol include/crx.h declares (tests check the .so exports each of them)
 SYMBOLS = [
     "crx_version", "crx_last_error", "crx_ctx_create", "crx_ctx_destroy", "crx_ctx_synchronize",
-    "crx_ctx_launch_count", "crx_ctx_profile", "crx_ctx_profile_reset", "crx_ctx_kernel_time", "crx_ctx_counters",
+    "crx_ctx_launch_count", "crx_ctx_trim", "crx_ctx_profile", "crx_ctx_profile_reset", "crx_ctx_kernel_time", "crx_ctx_counters",
     "crx_points_create", "crx_points_set_ratings", "crx_points_destroy", "crx_points_n", "crx_points_d",
     "crx_pair_op", "crx_create_LSH_hashtables", "crx_lsh_destroy", "crx_lsh_bucket_ids", "crx_lsh_detailed_hashes",
     "crx_get_LSH_combined_buckets", "crx_lsh_params", "crx_create_hypercube", "crx_cube_destroy",
@@ -114,6 +114,10 @@ class Context:
 
     def launch_count(self):
         return int(lib().crx_ctx_launch_count(self.h))
+
+    def trim(self):
+        """give the memory the engine's stream-ordered pool holds back to the driver (between workloads of different shape)"""
+        _check(lib().crx_ctx_trim(self.h))
 
     def profile(self, enable=True):
         _check(lib().crx_ctx_profile(self.h, int(enable)))
@@ -439,10 +443,13 @@ def k_means(ctx, pts, labels, centroids, metric_type, min_dist):
 
 def pam_lloyds(ctx, pts, labels, centroid_rows, metric_type, comm=None):
     """comm: dist.Comm -- the candidate medoid rows are split over its ranks (points replicated)."""
-    labels = _np(labels, np.int32); cr = _np(centroid_rows, np.int32)
+    if not _is_torch(labels):
+        labels = _np(labels, np.int32)
+    cr = _np(centroid_rows, np.int32)
     new = np.zeros(len(cr), np.int32)
     sw = ctypes.c_int()
-    _check(lib().crx_pam_lloyds_sharded(ctx.h, pts.h, _ptr(labels)[0], HOST, _ptr(cr)[0], len(cr), METRICS[metric_type], _comm_ptr(comm),
+    pl, lmem = _ptr(labels)
+    _check(lib().crx_pam_lloyds_sharded(ctx.h, pts.h, pl, lmem, _ptr(cr)[0], len(cr), METRICS[metric_type], _comm_ptr(comm),
                                         _ptr(new)[0], ctypes.byref(sw)))
     return bool(sw.value), new
 

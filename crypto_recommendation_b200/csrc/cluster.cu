@@ -73,7 +73,10 @@ static int gather_rows(crx_ctx* c, const crx_points* p, const int32_t* d_rows, i
 // is lane-local across tiles and finishes with one warp-shuffle reduction per point.
 //   Euclidean: FORM_DIFF_EXACT => the sums are the reference's own values, so labels and distances
 //              are bit-exact including ties (lowest index wins, assignment.hpp:67).
-//   cosine:    FORM_DOT for the scan, winner's distance recomputed with the compensated dot product.
+//   cosine:    FORM_DOT (plain FP64 FMA chain) for the scan; it differs from the reference's x87 value by up to
+//              (D + 4) ulp, so the scan also keeps the second-best value: a row whose margin is inside that bound (equal or
+//              scalar-multiple centroids, rating-like ties) is decided again with the reference's own arithmetic over all
+//              centroids in index order, strict '<' (assignment.hpp:63-70).  The winner's distance is always the x87 one.
 // ------------------------------------------------------------------------------------------------
 template <typename T, int METRIC>
 __global__ void __launch_bounds__(pt::NT)
@@ -88,13 +91,13 @@ lloyd_scan_kernel(const T* __restrict__ x, int ld, int D, const double* __restri
     int64_t r0 = (int64_t)blockIdx.x * pt::BM;
     pt::load_a_tile<T>(As, x, ld, rowmap, r0, nrows);
 
-    double best_v[pt::RW];
+    double best_v[pt::RW], second_v[pt::RW];
     int best_i[pt::RW];
     double xn[pt::RW];
     unsigned nan0 = 0;
 #pragma unroll
     for (int r = 0; r < pt::RW; r++) {
-        best_v[r] = INFINITY; best_i[r] = INT_MAX;
+        best_v[r] = INFINITY; best_i[r] = INT_MAX; second_v[r] = INFINITY;
         int64_t pos = r0 + warp * pt::RW + r;
         xn[r] = 0.0;
         if (METRIC == CRX_COSINE && pos < nrows) xn[r] = __dsqrt_rn(sqn[rowmap ? rowmap[pos] : pos]);
@@ -120,7 +123,8 @@ lloyd_scan_kernel(const T* __restrict__ x, int ld, int D, const double* __restri
                     } else {
                         double dist = __dsub_rn(1.0, __ddiv_rn(acc[r][cc], __dmul_rn(xn[r], cn[2 * lane + cc])));
                         if (col == 0 && dist != dist) nan0 |= 1u << r;  // `min == -1` takes centroid 0 even when NaN
-                        if (pt::plain_better(dist, col, best_v[r], best_i[r])) { best_v[r] = dist; best_i[r] = col; }
+                        if (pt::plain_better(dist, col, best_v[r], best_i[r])) { second_v[r] = fmin(second_v[r], best_v[r]); best_v[r] = dist; best_i[r] = col; }
+                        else if (dist == dist) second_v[r] = fmin(second_v[r], dist);
                     }
                 }
             }
@@ -136,6 +140,10 @@ lloyd_scan_kernel(const T* __restrict__ x, int ld, int D, const double* __restri
             double ov = __shfl_xor_sync(0xffffffffu, v, off);
             int oi = __shfl_xor_sync(0xffffffffu, i, off);
             bool take = METRIC == CRX_EUCLIDEAN ? pt::euclid_better(ov, oi, v, i) : pt::plain_better(ov, oi, v, i);
+            if (METRIC == CRX_COSINE) {
+                double os = __shfl_xor_sync(0xffffffffu, second_v[r], off);
+                second_v[r] = fmin(fmin(second_v[r], os), take ? v : ov);   // the loser's best is a runner-up
+            }
             if (take) { v = ov; i = oi; }
         }
         best_v[r] = v; best_i[r] = i;
@@ -144,9 +152,9 @@ lloyd_scan_kernel(const T* __restrict__ x, int ld, int D, const double* __restri
     // lane r finishes row r
     if (lane < pt::RW) {
         int r = lane;
-        double v = 0.0; int i = 0;
+        double v = 0.0, sec = INFINITY; int i = 0;
 #pragma unroll
-        for (int rr = 0; rr < pt::RW; rr++) if (rr == r) { v = best_v[rr]; i = best_i[rr]; }
+        for (int rr = 0; rr < pt::RW; rr++) if (rr == r) { v = best_v[rr]; i = best_i[rr]; sec = second_v[rr]; }
         int64_t pos = r0 + warp * pt::RW + r;
         if (pos < nrows) {
             int64_t row = rowmap ? (int64_t)rowmap[pos] : pos;
@@ -156,7 +164,17 @@ lloyd_scan_kernel(const T* __restrict__ x, int ld, int D, const double* __restri
                 if ((nan0_all >> r) & 1u) { i = 0; dist = v = nan(""); }
                 else {
                     const double* a = As + (warp * pt::RW + r) * ld;
-                    dist = __dsub_rn(1.0, cos_sim_exact(a, cent + (size_t)i * ld, D, sqn[row], csqn[i]));
+                    if (sec - v <= (double)(D + 4) * 2.3e-16) {
+                        // near tie under the plain arithmetic: the reference's own scan (assignment.hpp:63-70)
+                        i = 0;
+                        dist = __dsub_rn(1.0, cos_sim_exact(a, cent, D, sqn[row], csqn[0]));
+                        for (int cc = 1; cc < K; cc++) {
+                            double dc = __dsub_rn(1.0, cos_sim_exact(a, cent + (size_t)cc * ld, D, sqn[row], csqn[cc]));
+                            if (dc < dist) { dist = dc; i = cc; }
+                        }
+                    } else {
+                        dist = __dsub_rn(1.0, cos_sim_exact(a, cent + (size_t)i * ld, D, sqn[row], csqn[i]));
+                    }
                 }
             }
             labels[row] = i;

@@ -141,6 +141,16 @@ int crx_ctx_synchronize(crx_ctx* c) {
 
 int64_t crx_ctx_launch_count(const crx_ctx* c) { return c ? c->launches : 0; }
 
+int crx_ctx_trim(crx_ctx* c) {
+    CRX_REQUIRE(c, "ctx is NULL");
+    CRX_CUDA(cudaSetDevice(c->device));
+    CRX_CUDA(cudaStreamSynchronize(c->stream));
+    cudaMemPool_t pool;
+    CRX_CUDA(cudaDeviceGetDefaultMemPool(&pool, c->device));
+    CRX_CUDA(cudaMemPoolTrimTo(pool, 0));
+    return CRX_OK;
+}
+
 int crx_ctx_profile(crx_ctx* c, int enable) {
     CRX_REQUIRE(c, "ctx is NULL");
     c->profiling = enable != 0;

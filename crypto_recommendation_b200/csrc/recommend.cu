@@ -858,39 +858,131 @@ static int pass2_run(crx_ctx* c, const P2Host& h, P2QueueBuf* qa, P2QueueBuf* qb
         CRX_CUDA(cudaGetLastError());
     }
     const double* d_uval_q = queries != base ? uval_q.p : uval_b.p;
+    // ---- constant query rows against the constant rows of the table (recommend_pass2.cuh, P2Uniform): answered without lists
+    static const bool uni_off = getenv("CRX_P2_UNIFORM") != nullptr && getenv("CRX_P2_UNIFORM")[0] == '0';
+    if (n > 0 && h.use_tc && !uni_off && N < (int64_t)INT_MAX) {
+        DevBuf<uint8_t> flag;
+        DevBuf<int> refuse, nsel;
+        DevBuf<int32_t> mrow;
+        CRX_TRY(flag.alloc(c, (size_t)N)); CRX_TRY(refuse.alloc(c, 1)); CRX_TRY(nsel.alloc(c, 1)); CRX_TRY(mrow.alloc(c, (size_t)N));
+        CRX_CUDA(cudaMemsetAsync(refuse.p, 0, sizeof(int), c->stream));
+        {
+            CRX_KERNEL(c, "p2u_flag");
+            if (base->x64) p2u_flag_kernel<double><<<crx_grid(N, 8), 256, 0, c->stream>>>(base->x64, base->ld, base->d, base->sqn, uval_b.p, N, flag.p, refuse.p);
+            else p2u_flag_kernel<float><<<crx_grid(N, 8), 256, 0, c->stream>>>(base->x32, base->ld, base->d, base->sqn, uval_b.p, N, flag.p, refuse.p);
+        }
+        {
+            size_t bytes = 0;
+            cub::CountingInputIterator<int32_t> rows_it(0);
+            CRX_CUDA(cub::DeviceSelect::Flagged(nullptr, bytes, rows_it, flag.p, mrow.p, nsel.p, (int)N, c->stream));
+            DevBuf<char> tmp;
+            CRX_TRY(tmp.alloc(c, bytes));
+            CRX_CUDA(cub::DeviceSelect::Flagged(tmp.p, bytes, rows_it, flag.p, mrow.p, nsel.p, (int)N, c->stream));
+        }
+        int h_info[2] = {0, 0};
+        CRX_CUDA(cudaMemcpyAsync(&h_info[0], nsel.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+        CRX_CUDA(cudaMemcpyAsync(&h_info[1], refuse.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+        CRX_CUDA(cudaStreamSynchronize(c->stream));
+        const int nm = h_info[0];
+        if (nm >= h.P && h_info[1] == 0) {
+            DevBuf<double> mval, mroot, tp;
+            DevBuf<uint32_t> mcode;
+            DevBuf<int32_t> need, rlim;
+            CRX_TRY(mval.alloc(c, nm)); CRX_TRY(mroot.alloc(c, nm)); CRX_TRY(mcode.alloc(c, nm));
+            CRX_TRY(need.alloc(c, n)); CRX_TRY(rlim.alloc(c, n)); CRX_TRY(tp.alloc(c, n));
+            { CRX_KERNEL(c, "p2u_gather"); p2u_gather_kernel<<<crx_grid(nm, 256), 256, 0, c->stream>>>(mrow.p, nm, uval_b.p, base->sqn, h.ccode, mval.p, mroot.p, mcode.p); }
+            P2Uniform u;
+            u.mrow = mrow.p; u.mval = mval.p; u.mroot = mroot.p; u.mcode = mcode.p; u.nm = nm; u.qcode = h.qcode;
+            u.low = 0; u.high = 0;
+            for (int l = 0; l < h.L; l++) { u.low |= 1u << (l * h.k); u.high |= 1u << (l * h.k + h.k - 1); }
+            u.uval_q = d_uval_q; u.sqn_q = queries->sqn;
+            P2Resolve a;
+            memset(&a, 0, sizeof(a));
+            a.unk_q = queries->unknown; a.mean_q = queries->mean; a.mean_b = base->mean;
+            a.ldb = base->ld; a.D = base->d; a.P = h.P; a.Nrec = h.Nrec; a.q_begin = h.q_begin; a.ncand = h.nc;
+            a.cur = cur->view(); a.n = n; a.eps = h.eps;
+            a.recs = h.recs; a.nbr_rows = h.rows; a.nbr_sims = h.sims; a.qstatus = h.status; a.counters = c->counters;
+#define LAUNCH_U(KERNEL, TQ, TB, xqp, xbp, ...) KERNEL<TQ, TB><<<crx_grid(n, 4), 128, 0, c->stream>>>(xqp, queries->ld, xbp, a, u, __VA_ARGS__)
+#define DISPATCH_U(KERNEL, ...)                                                                                  \
+    do {                                                                                                         \
+        if (queries->x64 && base->x64) LAUNCH_U(KERNEL, double, double, queries->x64, base->x64, __VA_ARGS__);    \
+        else if (queries->x64) LAUNCH_U(KERNEL, double, float, queries->x64, base->x32, __VA_ARGS__);             \
+        else if (base->x64) LAUNCH_U(KERNEL, float, double, queries->x32, base->x64, __VA_ARGS__);                \
+        else LAUNCH_U(KERNEL, float, float, queries->x32, base->x32, __VA_ARGS__);                                \
+    } while (0)
+            { CRX_KERNEL(c, "p2u_select"); DISPATCH_U(p2u_select_kernel, need.p, rlim.p, tp.p); }
+            CRX_CUDA(cudaGetLastError());
+            // phase B for the queries whose R mixes similarities: scratch sized by a scan of |R|
+            DevBuf<int64_t> seg, off;
+            DevBuf<char> tmp;
+            size_t tmp_bytes = 0;
+            int64_t total = 0;
+            CRX_TRY(seg.alloc(c, (size_t)n + 1)); CRX_TRY(off.alloc(c, (size_t)n + 1));
+            CRX_TRY(p2_scan_sizes(c, need.p, nullptr, n, seg, off, tmp, tmp_bytes, &total));
+            if (total > 0) {
+                DevBuf<double> keys;
+                DevBuf<int32_t> vals;
+                CRX_TRY(keys.alloc(c, (size_t)total)); CRX_TRY(vals.alloc(c, (size_t)total));
+                { CRX_KERNEL(c, "p2u_sort"); DISPATCH_U(p2u_sort_kernel, need.p, rlim.p, tp.p, off.p, keys.p, vals.p); }
+                CRX_CUDA(cudaGetLastError());
+            }
+#undef DISPATCH_U
+#undef LAUNCH_U
+            CRX_CUDA(cudaMemsetAsync(nxt->count.p, 0, sizeof(unsigned int), c->stream));
+            { CRX_KERNEL(c, "p2u_compact"); p2u_compact_kernel<<<crx_grid(n, 256), 256, 0, c->stream>>>(cur->view(), n, need.p, nxt->view()); }
+            std::swap(cur, nxt);
+            const unsigned int n_before = n;
+            CRX_CUDA(cudaMemcpyAsync(&n, cur->count.p, sizeof(n), cudaMemcpyDeviceToHost, c->stream));
+            CRX_CUDA(cudaStreamSynchronize(c->stream));
+            if (p2_debug) fprintf(stderr, "[crx pass2] constant rows: |M| = %d, %u of %u queued queries answered (%lld keys sorted in phase B)\n", nm, n_before - n, n_before, (long long)total);
+        }
+    }
     static const int max_rounds = getenv("CRX_P2_ROUNDS") ? atoi(getenv("CRX_P2_ROUNDS")) : 16;
+    DevBuf<unsigned long long> dbg;
+    if (p2_debug) { CRX_TRY(dbg.alloc(c, 4)); }
     for (int round = 0; n > 0 && round < max_rounds; round++) {
         CRX_CUDA(cudaMemsetAsync(nxt->count.p, 0, sizeof(unsigned int), c->stream));
+        if (p2_debug) CRX_CUDA(cudaMemsetAsync(dbg.p, 0, 4 * sizeof(unsigned long long), c->stream));
         size_t free_b = 0, total_b = 0;
         CRX_CUDA(cudaMemGetInfo(&free_b, &total_b));
-        DevBuf<int32_t> head, count, ovf, qrow_abs, cols, pool;
+        // budget for the collected lists: one third for the pass masks of the threshold scan (32 B per row and column tile), the
+        // rest for rows + similarities (12 B per entry).  A queue that needs more is processed in slices.
+        const int64_t budget = (int64_t)std::max<size_t>(free_b / 2, (size_t)64 << 20);
+        unsigned int slice = n;
+        if (h.use_tc) {
+            const int64_t per_row = crx_tc_collect_mask_words(128, N) / 128 * 4;
+            slice = (unsigned int)std::max<int64_t>(128, std::min<int64_t>(n, (budget / 3 / per_row) / 128 * 128));
+        }
+        int64_t collected = 0;
+        for (unsigned int s0 = 0; s0 < n; s0 += slice) {
+        const unsigned int ns = std::min(slice, n - s0);
+        DevBuf<int32_t> count, ovf, qrow_abs, cols, allf, colx_eff;
+        DevBuf<uint32_t> cmask;
         DevBuf<float> theta_f;
-        DevBuf<unsigned int> pool_next;
         DevBuf<int64_t> seg, off;
         DevBuf<char> tmp;
         DevBuf<double> xs;
         size_t tmp_bytes = 0;
         int64_t total = 0;
-        CRX_TRY(count.alloc(c, n)); CRX_TRY(ovf.alloc(c, n)); CRX_TRY(seg.alloc(c, (size_t)n + 1)); CRX_TRY(off.alloc(c, (size_t)n + 1));
-        CRX_CUDA(cudaMemsetAsync(ovf.p, 0, (size_t)n * sizeof(int32_t), c->stream));
+        CRX_TRY(count.alloc(c, ns)); CRX_TRY(ovf.alloc(c, ns)); CRX_TRY(seg.alloc(c, (size_t)ns + 1)); CRX_TRY(off.alloc(c, (size_t)ns + 1));
+        CRX_CUDA(cudaMemsetAsync(ovf.p, 0, (size_t)ns * sizeof(int32_t), c->stream));
+        CRX_CUDA(cudaMemsetAsync(count.p, 0, (size_t)ns * sizeof(int32_t), c->stream));
         P2Queue w = cur->view();
-        // budget for the collected lists (4 B per entry in the pool, then 12 B per entry as rows + similarities)
-        const int64_t budget = (int64_t)std::max<size_t>(free_b / 2, (size_t)64 << 20);
+        w.q += s0; w.theta += s0; w.colx += s0; w.tries += s0;
+        int64_t rows_pad = 0;
         if (h.use_tc) {
-            CRX_TRY(head.alloc(c, n)); CRX_TRY(qrow_abs.alloc(c, n)); CRX_TRY(theta_f.alloc(c, n)); CRX_TRY(pool_next.alloc(c, 1));
-            { CRX_KERNEL(c, "p2_prepare"); p2_prepare_kernel<<<crx_grid(n, 256), 256, 0, c->stream>>>(w, n, h.q_begin, 1.0 / h.unscale, theta_f.p, qrow_abs.p); }
+            CRX_TRY(qrow_abs.alloc(c, ns)); CRX_TRY(theta_f.alloc(c, ns)); CRX_TRY(allf.alloc(c, ns)); CRX_TRY(colx_eff.alloc(c, ns));
+            { CRX_KERNEL(c, "p2_prepare"); p2_prepare_kernel<<<crx_grid(ns, 256), 256, 0, c->stream>>>(w, ns, h.q_begin, 1.0 / h.unscale, theta_f.p, qrow_abs.p, allf.p, colx_eff.p); }
             TcOperand opA;
-            CRX_TRY(crx_tc_gather(c, *h.opQ, qrow_abs.p, n, &opA));
-            int64_t pool_bytes = std::min<int64_t>(budget / 4, (int64_t)n * (N * 4 + 4096) + ((int64_t)1 << 20));
-            unsigned int chunks = (unsigned int)std::min<int64_t>(pool_bytes / (TC_CHUNK * 4), (int64_t)0x7ffffff0);
-            CRX_TRY(pool.alloc(c, (size_t)chunks * TC_CHUNK));
-            CRX_CUDA(cudaMemsetAsync(pool_next.p, 0, sizeof(unsigned int), c->stream));
-            CRX_TRY(crx_tc_collect(c, opA, n, *h.opB, h.qcode, qrow_abs.p, h.ccode, h.k, h.L, h.dense, theta_f.p, w.colx, pool.p, pool_next.p, chunks,
-                                   head.p, count.p, ovf.p));
+            CRX_TRY(crx_tc_gather(c, *h.opQ, qrow_abs.p, ns, &opA));
+            CRX_TRY(cmask.alloc(c, (size_t)crx_tc_collect_mask_words(ns, N)));
+            rows_pad = ((int64_t)ns + 127) / 128 * 128;
+            CRX_TRY(crx_tc_collect(c, opA, ns, *h.opB, h.qcode, qrow_abs.p, h.ccode, h.k, h.L, h.dense, theta_f.p, colx_eff.p, cmask.p, count.p));
+            { CRX_KERNEL(c, "p2_all_count"); p2_all_count_kernel<<<crx_grid(ns, 256), 256, 0, c->stream>>>(allf.p, ns, w.q, h.nc, count.p, ovf.p); }
         } else {
             CRX_KERNEL(c, "p2_collect_simt");
 #define LAUNCH_S(TQ, TB, xqp, xbp, FILL)                                                                                          \
-    p2_collect_simt_kernel<TQ, TB, FILL><<<n, 256, 0, c->stream>>>(xqp, queries->ld, queries->sqn, xbp, base->ld, base->sqn, base->d, N, \
+    p2_collect_simt_kernel<TQ, TB, FILL><<<ns, 256, 0, c->stream>>>(xqp, queries->ld, queries->sqn, xbp, base->ld, base->sqn, base->d, N, \
         h.q_begin, w, h.L, h.qgid, h.qstride, h.cgid, h.cstride, count.p, ovf.p, off.p, cols.p)
             if (queries->x64 && base->x64) LAUNCH_S(double, double, queries->x64, base->x64, false);
             else if (queries->x64) LAUNCH_S(double, float, queries->x64, base->x32, false);
@@ -898,17 +990,29 @@ static int pass2_run(crx_ctx* c, const P2Host& h, P2QueueBuf* qa, P2QueueBuf* qb
             else LAUNCH_S(float, float, queries->x32, base->x32, false);
             CRX_CUDA(cudaGetLastError());
         }
-        CRX_TRY(p2_scan_sizes(c, count.p, ovf.p, n, seg, off, tmp, tmp_bytes, &total));
-        if (total * 12 > budget) {   // too many rows for this round: the queries behind the budget wait for the next one
-            { CRX_KERNEL(c, "p2_trim"); p2_trim_kernel<<<crx_grid(n, 256), 256, 0, c->stream>>>(off.p, n, budget / 12, ovf.p); }
-            CRX_TRY(p2_scan_sizes(c, count.p, ovf.p, n, seg, off, tmp, tmp_bytes, &total));
+        CRX_TRY(p2_scan_sizes(c, count.p, ovf.p, ns, seg, off, tmp, tmp_bytes, &total));
+        const int64_t list_budget = budget - (int64_t)cmask.count * 4;
+        if (total * 12 > list_budget) {   // too many rows for this round: the queries behind the budget wait for the next one
+            { CRX_KERNEL(c, "p2_trim"); p2_trim_kernel<<<crx_grid(ns, 256), 256, 0, c->stream>>>(off.p, ns, list_budget / 12, ovf.p); }
+            CRX_TRY(p2_scan_sizes(c, count.p, ovf.p, ns, seg, off, tmp, tmp_bytes, &total));
         }
+        collected += total;
         CRX_TRY(cols.alloc(c, (size_t)total)); CRX_TRY(xs.alloc(c, (size_t)total));
         if (h.use_tc) {
-            CRX_KERNEL(c, "p2_linearize");
-            p2_linearize_kernel<<<crx_grid(n, 8), 256, 0, c->stream>>>(pool.p, head.p, count.p, ovf.p, off.p, n, cols.p);
-            CRX_CUDA(cudaGetLastError());
-            pool.release();
+            {
+                CRX_KERNEL(c, "p2_expand");
+                const int tn = crx_tc_tile_cols();
+                p2_expand_kernel<<<(unsigned int)(rows_pad / 32), 256, 0, c->stream>>>(cmask.p, rows_pad, (int)((N + tn - 1) / tn), tn, allf.p, count.p, ovf.p, off.p, ns, cols.p);
+                CRX_CUDA(cudaGetLastError());
+            }
+            cmask.release();
+            {
+                uint32_t low = 0, high = 0;
+                for (int l = 0; l < h.L; l++) { low |= 1u << (l * h.k); high |= 1u << (l * h.k + h.k - 1); }
+                CRX_KERNEL(c, "p2_fill_all");
+                p2_fill_all_kernel<<<ns, 256, 0, c->stream>>>(allf.p, ovf.p, qrow_abs.p, h.qcode, h.ccode, N, low, high, off.p, cols.p);
+                CRX_CUDA(cudaGetLastError());
+            }
         } else {
             CRX_KERNEL(c, "p2_collect_simt");
             // (a trimmed query writes nothing: its segment is empty)
@@ -924,7 +1028,7 @@ static int pass2_run(crx_ctx* c, const P2Host& h, P2QueueBuf* qa, P2QueueBuf* qb
             const int64_t nblocks = total / 32;
             int grid = (int)std::min<int64_t>(((nblocks + P2_RUN - 1) / P2_RUN + 7) / 8, (int64_t)c->sm_count * 16);
 #define LAUNCH_E(TQ, TB, xqp, xbp) \
-    p2_exact_kernel<TQ, TB><<<grid, 256, 0, c->stream>>>(xqp, queries->ld, queries->sqn, xbp, base->ld, base->sqn, base->d, h.q_begin, w.q, off.p, n, nblocks, cols.p, xs.p, d_uval_q, uval_b.p)
+    p2_exact_kernel<TQ, TB><<<grid, 256, 0, c->stream>>>(xqp, queries->ld, queries->sqn, xbp, base->ld, base->sqn, base->d, h.q_begin, w.q, off.p, ns, nblocks, cols.p, xs.p, d_uval_q, uval_b.p)
             if (queries->x64 && base->x64) LAUNCH_E(double, double, queries->x64, base->x64);
             else if (queries->x64) LAUNCH_E(double, float, queries->x64, base->x32);
             else if (base->x64) LAUNCH_E(float, double, queries->x32, base->x64);
@@ -938,19 +1042,26 @@ static int pass2_run(crx_ctx* c, const P2Host& h, P2QueueBuf* qa, P2QueueBuf* qb
             memset(&a, 0, sizeof(a));
             a.unk_q = queries->unknown; a.mean_q = queries->mean; a.mean_b = base->mean;
             a.ldb = base->ld; a.D = base->d; a.P = h.P; a.Nrec = h.Nrec; a.q_begin = h.q_begin; a.ncand = h.nc;
-            a.cur = w; a.next = nxt->view(); a.n = n;
+            a.cur = w; a.next = nxt->view(); a.n = ns;
             a.off = off.p; a.count = count.p; a.ovf = ovf.p; a.cols = cols.p; a.xs = xs.p;
             a.eps = h.eps; a.blocks = h.blocks;
             a.recs = h.recs; a.nbr_rows = h.rows; a.nbr_sims = h.sims; a.qstatus = h.status; a.counters = c->counters;
-            if (base->x64) p2_resolve_kernel<double><<<crx_grid(n, 4), 128, 0, c->stream>>>(base->x64, a);
-            else p2_resolve_kernel<float><<<crx_grid(n, 4), 128, 0, c->stream>>>(base->x32, a);
+            a.dbg = p2_debug ? dbg.p : nullptr;
+            if (base->x64) p2_resolve_kernel<double><<<crx_grid(ns, 4), 128, 0, c->stream>>>(base->x64, a);
+            else p2_resolve_kernel<float><<<crx_grid(ns, 4), 128, 0, c->stream>>>(base->x32, a);
             CRX_CUDA(cudaGetLastError());
         }
+        }   // slices
         std::swap(cur, nxt);
         const unsigned int n_in = n;
         CRX_CUDA(cudaMemcpyAsync(&n, cur->count.p, sizeof(n), cudaMemcpyDeviceToHost, c->stream));
         CRX_CUDA(cudaStreamSynchronize(c->stream));
-        if (p2_debug) fprintf(stderr, "[crx pass2] round %d: %u queued, %lld collected (%.1f per query), %u left\n", round, n_in, (long long)total, (double)total / n_in, n);
+        if (p2_debug) {
+            unsigned long long hd[4];
+            CRX_CUDA(cudaMemcpy(hd, dbg.p, sizeof(hd), cudaMemcpyDeviceToHost));
+            fprintf(stderr, "[crx pass2] round %d: %u queued (slices of %u), %lld collected (%.1f per query), %u left; resolved %llu: sum |R| = %llu, their lists = %llu\n",
+                    round, n_in, slice, (long long)collected, (double)collected / n_in, n, hd[2], hd[0], hd[1]);
+        }
     }
     if (n > 0) {
         CRX_KERNEL(c, "p2_leftover");
@@ -1054,6 +1165,7 @@ static int recommend_lsh_impl(crx_ctx* c, const crx_lsh* t, const crx_points* qu
             CRX_TRY(blockmax.alloc(c, (size_t)nq * 2 * TC_NBLK));
             blk.blockmax = blockmax.p;
             blk.nblk = crx_tc_blocks(N, blk.bt);
+            blk.tile_cols = crx_tc_tile_cols();
             blk.unscale = ldexp(1.0, -20);
         }
         if (st == CRX_OK) st = crx_tc_topp(c, self ? opB : opA, q_begin, nq, opB, qcode, ccode.p, k, L, dense_cols, tl_s.p, tl_i.p, 3, blockmax.p);

@@ -37,6 +37,7 @@ __device__ __forceinline__ void p2_emit(const P2Queue& w, int q, double theta, i
 struct P2Blocks {
     const float* blockmax;   // [nq][2][TC_NBLK] filter units, or NULL
     int nblk;
+    int tile_cols;           // columns per tile of the scan that produced blockmax
     int bt[TC_NBLK + 1];
     double unscale;          // filter units -> similarity
 };
@@ -47,7 +48,7 @@ __device__ __forceinline__ double p2_tail_theta(const P2Blocks& b, int64_t qrel,
     colx = 0x7fffffff;
     double cap = fmin(TP - 2.02 * eps, theta_old);
     if (b.blockmax != nullptr) {
-        const int tile = estar / TC_TILE_COLS;
+        const int tile = estar / b.tile_cols;
         float bm = -INFINITY;
         bool any = false;
         for (int j = 1; j < b.nblk; j++)
@@ -92,17 +93,25 @@ __device__ __noinline__ void warp_qs_topn_big(double* key, int* val, int n, int 
             const int m = hi - lo;
             int cnt = 0, lastgt = -1, q1 = 0x7fffffff;
             bool alleq = true;
-            for (int base = lo; base < hi; base += 32) {
-                const int e = base + lane;
-                const bool in = e < hi;
-                const double k = in ? key[e] : 0.0;
-                const unsigned bg = __ballot_sync(0xffffffffu, in && k >= pivot);
-                const unsigned bgt = __ballot_sync(0xffffffffu, in && k > pivot);
-                const unsigned blt = __ballot_sync(0xffffffffu, in && !(k >= pivot));
-                alleq = alleq && __all_sync(0xffffffffu, !in || k == pivot);
-                cnt += __popc(bg);
-                if (bgt) lastgt = base + 31 - __clz(bgt);
-                if (blt && q1 == 0x7fffffff) q1 = base + __ffs(blt) - 1;
+            for (int base0 = lo; base0 < hi; base0 += 128) {   // four groups of 32 per step: enough loads in flight on long lists
+                double k4[4];
+#pragma unroll
+                for (int u = 0; u < 4; u++) { const int e = base0 + u * 32 + lane; k4[u] = e < hi ? key[e] : 0.0; }
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    const int base = base0 + u * 32;
+                    if (base >= hi) break;
+                    const int e = base + lane;
+                    const bool in = e < hi;
+                    const double k = k4[u];
+                    const unsigned bg = __ballot_sync(0xffffffffu, in && k >= pivot);
+                    const unsigned bgt = __ballot_sync(0xffffffffu, in && k > pivot);
+                    const unsigned blt = __ballot_sync(0xffffffffu, in && !(k >= pivot));
+                    alleq = alleq && __all_sync(0xffffffffu, !in || k == pivot);
+                    cnt += __popc(bg);
+                    if (bgt) lastgt = base + 31 - __clz(bgt);
+                    if (blt && q1 == 0x7fffffff) q1 = base + __ffs(blt) - 1;
+                }
             }
             if (alleq) break;
             if (cnt == m) { hi = lastgt; continue; }   // the pivot and its equals behind the last larger element stay
@@ -140,19 +149,25 @@ __device__ __noinline__ void warp_qs_topn_big(double* key, int* val, int n, int 
             // stable compaction of the ">=" elements to [lo, p)
             {
                 int done = 0;
-                for (int base = lo; base < hi; base += 32) {
-                    const int e = base + lane;
-                    const bool in = e < hi;
-                    const double k = in ? key[e] : 0.0;
-                    const int v = in ? val[e] : 0;
-                    const bool g = in && k >= pivot;
-                    const unsigned bg = __ballot_sync(0xffffffffu, g);
+                for (int base0 = lo; base0 < hi; base0 += 128) {
+                    double k4[4];
+                    int v4[4];
+                    bool g4[4];
+#pragma unroll
+                    for (int u = 0; u < 4; u++) { const int e = base0 + u * 32 + lane; k4[u] = e < hi ? key[e] : 0.0; g4[u] = e < hi && k4[u] >= pivot; }
+#pragma unroll
+                    for (int u = 0; u < 4; u++) { const int e = base0 + u * 32 + lane; v4[u] = g4[u] ? val[e] : 0; }
                     __syncwarp();
-                    if (g) {
-                        const int dst = lo + done + __popc(bg & lt);
-                        if (dst != e) { key[dst] = k; val[dst] = v; }
+#pragma unroll
+                    for (int u = 0; u < 4; u++) {
+                        const int e = base0 + u * 32 + lane;
+                        const unsigned bg = __ballot_sync(0xffffffffu, g4[u]);
+                        if (g4[u]) {
+                            const int dst = lo + done + __popc(bg & lt);
+                            if (dst != e) { key[dst] = k4[u]; val[dst] = v4[u]; }
+                        }
+                        done += __popc(bg);
                     }
-                    done += __popc(bg);
                     __syncwarp();
                 }
             }
@@ -234,15 +249,55 @@ __device__ __forceinline__ void predict_and_recommend(const TB* __restrict__ xb,
 // ------------------------------------------------------------------------------------------------
 constexpr int P2_KIND_SHIFT = 16;   // tries = attempts | (status the query carried out of rec_finalize << 16)
 
+// theta = -inf asks for EVERY candidate of the query ("no candidate behind e*: R = every candidate"): such a row takes no part
+// in the threshold scan (its threshold becomes +inf) -- its list is the table mask itself, written by p2_fill_all_kernel
 __global__ void p2_prepare_kernel(P2Queue w, unsigned int n, int64_t q_begin, double scale, float* __restrict__ theta_f,
-                                  int32_t* __restrict__ qrow_abs) {
+                                  int32_t* __restrict__ qrow_abs, int32_t* __restrict__ allf, int32_t* __restrict__ colx_eff) {
     unsigned int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
+    const bool all = w.theta[i] == -INFINITY;
     double th = w.theta[i] * scale;
     float f = (float)th;
     if (isfinite(f)) f = f - fabsf(f) * 1.2e-7f - 1e-30f;   // never above the double threshold
-    theta_f[i] = f;
+    theta_f[i] = all ? INFINITY : f;
+    colx_eff[i] = all ? 0x7fffffff : w.colx[i];
+    allf[i] = all;
     qrow_abs[i] = (int32_t)(q_begin + w.q[i]);
+}
+
+__global__ void p2_all_count_kernel(const int32_t* __restrict__ allf, unsigned int n, const int32_t* __restrict__ wq, const int32_t* __restrict__ ncand,
+                                    int32_t* __restrict__ count, int32_t* __restrict__ ovf) {
+    unsigned int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && allf[i]) { count[i] = ncand[wq[i]]; ovf[i] = 0; }
+}
+
+// every row that shares a bucket with the query, ascending: one block per "all" query, block-wide compaction of the table mask
+__global__ void __launch_bounds__(256)
+p2_fill_all_kernel(const int32_t* __restrict__ allf, const int32_t* __restrict__ ovf, const int32_t* __restrict__ qrow_abs, const uint32_t* __restrict__ qcode,
+                   const uint32_t* __restrict__ ccode, int64_t nb, uint32_t low, uint32_t high, const int64_t* __restrict__ off, int32_t* __restrict__ cols) {
+    const unsigned int i = blockIdx.x;
+    if (!allf[i] || ovf[i]) return;
+    __shared__ int wsum[8];
+    __shared__ int running;
+    const uint32_t cq = qcode[qrow_abs[i]];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) running = 0;
+    __syncthreads();
+    int32_t* out = cols + off[i];
+    for (int64_t c0 = 0; c0 < nb; c0 += 256) {
+        const int64_t c = c0 + threadIdx.x;
+        bool pass = false;
+        if (c < nb) { const uint32_t x = cq ^ ccode[c]; pass = ((x - low) & ~x & high) != 0u; }
+        const unsigned bm = __ballot_sync(0xffffffffu, pass);
+        if (lane == 0) wsum[warp] = __popc(bm);
+        __syncthreads();
+        int before = running;
+        for (int x = 0; x < warp; x++) before += wsum[x];
+        if (pass) out[before + __popc(bm & ((1u << lane) - 1u))] = (int32_t)c;
+        __syncthreads();
+        if (threadIdx.x == 0) { int t = 0; for (int x = 0; x < 8; x++) t += wsum[x]; running += t; }
+        __syncthreads();
+    }
 }
 
 __global__ void p2_sizes_kernel(const int32_t* __restrict__ count, const int32_t* __restrict__ ovf, unsigned int n, int64_t* __restrict__ seg) {
@@ -251,23 +306,75 @@ __global__ void p2_sizes_kernel(const int32_t* __restrict__ count, const int32_t
     seg[i] = (i < n && !(ovf && ovf[i])) ? (((int64_t)count[i] + 31) / 32) * 32 : 0;
 }
 
-__global__ void p2_linearize_kernel(const int32_t* __restrict__ pool, const int32_t* __restrict__ head, const int32_t* __restrict__ count,
-                                    const int32_t* __restrict__ ovf, const int64_t* __restrict__ off, unsigned int n, int32_t* __restrict__ cols) {
-    unsigned int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    int lane = threadIdx.x & 31;
-    if (i >= n || ovf[i]) return;
-    const int total = count[i];
-    int32_t* out = cols + off[i];
-    int c = head[i], written = 0;
-    while (c >= 0 && written < total) {
-        const int32_t* ch = pool + (size_t)c * TC_CHUNK;
-        const int next = ch[0];
-        const int m = min(TC_CHUNK - 1, total - written);
-        for (int j = lane; j < m; j += 32) out[written + j] = ch[1 + j];
-        written += m;
-        c = next;
+// pass masks of the threshold scan -> ascending column lists.  cmask[(tile * wpt + word)][rows_pad]: one block takes 32
+// consecutive rows; 128 mask words per row are staged at a time (every warp reads whole 128-byte lines of the matrix), then a
+// warp walks 4 of the rows: lane = one word of 32, prefix sum of the popcounts, the set bits written in order.
+__global__ void __launch_bounds__(256)
+p2_expand_kernel(const uint32_t* __restrict__ cmask, int64_t rows_pad, int ntiles, int tile_cols, const int32_t* __restrict__ allf,
+                 const int32_t* __restrict__ count, const int32_t* __restrict__ ovf, const int64_t* __restrict__ off, unsigned int n,
+                 int32_t* __restrict__ cols) {
+    __shared__ uint32_t sm[128][33];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const unsigned lt = (1u << lane) - 1u;
+    const int64_t row0 = (int64_t)blockIdx.x * 32;
+    const int wpt = tile_cols / 32;
+    const int64_t W = (int64_t)ntiles * wpt;
+    int run[4] = {0, 0, 0, 0};
+    bool live[4];
+#pragma unroll
+    for (int rr = 0; rr < 4; rr++) {
+        const int64_t row = row0 + warp * 4 + rr;
+        live[rr] = row < (int64_t)n && !ovf[row] && !allf[row] && count[row] > 0;
     }
-    for (int j = total + lane; j < (total + 31) / 32 * 32; j += 32) out[j] = -1;
+    const bool block_live = __syncthreads_or(live[0] || live[1] || live[2] || live[3]);
+    if (block_live) {
+        for (int64_t w0 = 0; w0 < W; w0 += 128) {
+#pragma unroll 4
+            for (int j = 0; j < 16; j++) {
+                const int64_t w = w0 + warp * 16 + j;
+                sm[warp * 16 + j][lane] = w < W ? cmask[w * rows_pad + row0 + lane] : 0u;
+            }
+            __syncthreads();
+#pragma unroll
+            for (int rr = 0; rr < 4; rr++) {
+                if (!live[rr]) continue;
+                const int r = warp * 4 + rr;
+                int32_t* out = cols + off[row0 + r];
+#pragma unroll
+                for (int sstep = 0; sstep < 4; sstep++) {
+                    uint32_t bits = sm[sstep * 32 + lane][r];
+                    const unsigned any = __ballot_sync(0xffffffffu, bits != 0u);
+                    if (!any) continue;
+                    int pc = __popc(bits), before = pc;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, before, o); if (lane >= o) before += v; }
+                    const int tot = __shfl_sync(0xffffffffu, before, 31);
+                    before -= pc;
+                    const int64_t w = w0 + sstep * 32 + lane;
+                    const int colbase = (int)(w / wpt) * tile_cols + (int)(w % wpt) * 32;
+                    int pos = run[rr] + before;
+                    while (bits != 0u) {
+                        const int j = __ffs(bits) - 1;
+                        bits &= bits - 1u;
+                        out[pos++] = colbase + j;
+                    }
+                    run[rr] += tot;
+                }
+            }
+            __syncthreads();
+        }
+    }
+    // segments are padded to multiples of 32 entries
+#pragma unroll
+    for (int rr = 0; rr < 4; rr++) {
+        const int64_t row = row0 + warp * 4 + rr;
+        if (row < (int64_t)n && !ovf[row]) {
+            const int total = count[row];
+            const int j = total + lane;
+            if (j < (total + 31) / 32 * 32) cols[off[row] + j] = -1;
+        }
+    }
+    (void)lt;
 }
 
 // plain FP64 filter for tables the tensor path does not take: one block per queued query, columns in order.
@@ -352,27 +459,41 @@ p2_exact_kernel(const TQ* __restrict__ xq, int ldq, const double* __restrict__ s
                 const double* __restrict__ uval_q, const double* __restrict__ uval_b) {
     __shared__ rw::WarpTile tiles[8];
     __shared__ double qvec[8][128];
+    __shared__ int q_ent[8][64], q_col[8][64];   // pairs that need the walk, gathered until a full warp of them is waiting
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const unsigned lt = (1u << lane) - 1u;
     const int64_t nruns = (nblocks + P2_RUN - 1) / P2_RUN;
     for (int64_t run = (int64_t)blockIdx.x * 8 + warp; run < nruns; run += (int64_t)gridDim.x * 8) {
         const int64_t b0 = run * P2_RUN, b1 = min(nblocks, b0 + P2_RUN);
+        const int64_t run_base = b0 * 32;
         // item of the first block = the last i with off[i] <= base  (off[n] = total > base)
         unsigned int lo = 0, hi = n;
-        { const int64_t base = b0 * 32; while (lo < hi) { unsigned int m = (lo + hi + 1) >> 1; if (off[m] <= base) lo = m; else hi = m - 1; } }
+        while (lo < hi) { unsigned int m = (lo + hi + 1) >> 1; if (off[m] <= run_base) lo = m; else hi = m - 1; }
         int64_t next_off = off[lo + 1];
         bool staged = false;
         int64_t qrow = q_begin + wq[lo];
         double uq = uval_q[qrow], nq = sqn_q[qrow];
+        int qn = 0;
+        // the literal walk of (up to) 32 waiting pairs of the current query: queue slots [k0, k0 + cnt)
+        auto walk_some = [&](int k0, int cnt) {
+            if (!staged) { rw::stage_vector<TQ>(xq, ldq, qrow, qvec[warp]); staged = true; }
+            const bool on = lane < cnt;
+            const int col = on ? q_col[warp][k0 + lane] : -1;
+            const int ent = on ? q_ent[warp][k0 + lane] : 0;
+            rw::Walk wk = rw::walk_rows<TB, CRX_COSINE>(xb, ldb, D, on ? (int64_t)col : -1, qvec[warp], tiles[warp]);
+            if (on) { X87 ip = {wk.a, wk.b}; xs[run_base + ent] = cos_sim_x87(ip, sqn_b[col], nq); }
+            __syncwarp();
+        };
         for (int64_t b = b0; b < b1; b++) {
             const int64_t base = b * 32;
             if (base >= next_off) {
+                if (qn > 0) { walk_some(0, qn); qn = 0; }
                 do { lo++; next_off = off[lo + 1]; } while (base >= next_off);
                 qrow = q_begin + wq[lo];
                 uq = uval_q[qrow]; nq = sqn_q[qrow];
                 staged = false;
             }
             const int mine = cols[base + lane];
-            double sim = -INFINITY;
             bool walk = mine >= 0;
             if (mine >= 0 && uq == uq) {
                 const double ub = uval_b[mine];
@@ -381,17 +502,20 @@ p2_exact_kernel(const TQ* __restrict__ xq, int ldq, const double* __restrict__ s
                     X87 ip;
                     ip.h = __dmul_rn((double)D, pr);
                     ip.l = __fma_rn((double)D, pr, -ip.h);
-                    sim = cos_sim_x87(ip, sqn_b[mine], nq);
+                    xs[base + lane] = cos_sim_x87(ip, sqn_b[mine], nq);
                     walk = false;
                 }
             }
-            if (__any_sync(0xffffffffu, walk)) {
-                if (!staged) { rw::stage_vector<TQ>(xq, ldq, qrow, qvec[warp]); staged = true; }
-                rw::Walk wk = rw::walk_rows<TB, CRX_COSINE>(xb, ldb, D, walk ? (int64_t)mine : -1, qvec[warp], tiles[warp]);
-                if (walk) { X87 ip = {wk.a, wk.b}; sim = cos_sim_x87(ip, sqn_b[mine], nq); }
+            if (mine < 0) xs[base + lane] = -INFINITY;
+            const unsigned bm = __ballot_sync(0xffffffffu, walk);
+            if (bm) {
+                if (walk) { const int pos = qn + __popc(bm & lt); q_ent[warp][pos] = (int)(base - run_base) + lane; q_col[warp][pos] = mine; }
+                qn += __popc(bm);
+                __syncwarp();
+                if (qn >= 32) { walk_some(qn - 32, 32); qn -= 32; }
             }
-            xs[base + lane] = sim;
         }
+        if (qn > 0) walk_some(0, qn);
         __syncwarp();
     }
 }
@@ -409,6 +533,7 @@ struct P2Resolve {
     P2Blocks blocks;
     int32_t* recs; int32_t* nbr_rows; double* nbr_sims; int32_t* qstatus;
     unsigned long long* counters;
+    unsigned long long* dbg;   // nullable: [0] sum of |R|, [1] sum of the list lengths of the resolved queries, [2] resolved, [3] re-queued
 };
 
 template <typename TB>
@@ -552,6 +677,7 @@ p2_resolve_kernel(const TB* __restrict__ xb, P2Resolve a) {
         }
         __syncwarp();
     }
+    if (a.dbg && lane == 0) { atomicAdd(&a.dbg[0], (unsigned long long)m); atomicAdd(&a.dbg[1], (unsigned long long)cnt); atomicAdd(&a.dbg[2], 1ull); }
     warp_qs_topn_big(key, val, m, keep, posge[warp], hk[warp], hv[warp]);
     if (lane < keep) { s_idx[warp][lane] = val[lane]; s_sim[warp][lane] = key[lane]; }
     __syncwarp();
@@ -566,6 +692,244 @@ p2_resolve_kernel(const TB* __restrict__ xb, P2Resolve a) {
         predict_and_recommend<TB>(xb, a.ldb, a.mean_b, a.unk_q + qrow * a.D, a.mean_q[qrow], a.D, s_idx[warp], s_sim[warp], keep, a.Nrec,
                                   s_pred[warp], s_coin[warp], a.recs + (size_t)qrel * a.Nrec);
     }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Constant query rows (single-coin users) against the constant rows of the table: the one LARGE class of mutually tied
+// neighbours this domain produces (5% of the users, all parallel to (1, ..., 1)).  For such a query q = c_q (1, ..., 1), c_q > 0:
+//   * the similarity to a constant row c_b (1, ..., 1), c_b > 0, has the closed form of p2_exact_kernel: 1 within a few ulp;
+//   * the similarity to ANY other row x is (sum x_k) / (sqrt(D) |x|) = alpha(x) up to rounding, the same for every such query:
+//     rows with alpha(x) < 1 - 2^-39 (computed once, plain FP64, error < 2^-44) lie below 1 - 2^-40 for all of them.
+// So when the P-th best similarity T_P over M = { constant rows with c > 0 } u { the (rare) rows with alpha >= 1 - 2^-39 } is
+// >= 1 - 2^-40, the P best and every candidate tied with them are in M; and when the last row e* among them carries T_P itself
+// ("H alone decides", recommend_pass2.cuh header), the reference's list is the literal sort of R = { members of M in front of
+// e* (e* included) with similarity >= T_P }.  One warp per queued query walks M (row order) instead of sending 50k-entry lists
+// through the collection scan; a query that does not meet the two conditions stays queued for the general rounds.
+// ------------------------------------------------------------------------------------------------
+struct P2Uniform {
+    const int32_t* mrow;     // [nm] rows of M, ascending
+    const double* mval;      // [nm] constant value of the row, NaN for a near-constant row (exact walk)
+    const double* mroot;     // [nm] sqrt of the row's sum of squares
+    const uint32_t* mcode;   // [nm] packed table code of the row
+    int nm;
+    const uint32_t* qcode;   // packed codes of the query rows
+    uint32_t low, high;
+    const double* uval_q; const double* sqn_q;
+};
+
+template <typename TQ, typename TB>
+__device__ __forceinline__ double p2u_sim(const P2Uniform& u, int j, double uq, double rq, int D, const TQ* __restrict__ xq_row,
+                                          const TB* __restrict__ xb, int ldb) {
+    const double ub = u.mval[j];
+    if (ub == ub) {
+        const double pr = __dmul_rn(uq, ub);
+        X87 ip;
+        ip.h = __dmul_rn((double)D, pr);
+        ip.l = __fma_rn((double)D, pr, -ip.h);
+        return cos_sim_x87_roots(ip, u.mroot[j], rq);
+    }
+    return cos_sim_x87_roots(dot_x87(xb + (size_t)u.mrow[j] * ldb, xq_row, D), u.mroot[j], rq);   // near-constant row: rare
+}
+
+// phase A: T_P, e*, and the answer when R is one run of equal similarities (need[i] = 0); otherwise need[i] = |R| for phase B,
+// or -1 when the query stays with the general rounds
+template <typename TQ, typename TB>
+__global__ void __launch_bounds__(128)
+p2u_select_kernel(const TQ* __restrict__ xq, int ldq, const TB* __restrict__ xb, P2Resolve a, P2Uniform u, int32_t* __restrict__ need,
+                  int32_t* __restrict__ rlim_out, double* __restrict__ tp_out) {
+    constexpr int QW = 4;
+    __shared__ int s_idx[QW][32];
+    __shared__ double s_sim[QW][32];
+    __shared__ double s_pred[QW][128];
+    __shared__ int s_coin[QW][128];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const unsigned int i = blockIdx.x * QW + warp;
+    if (i >= a.n) return;
+    const int qrel = a.cur.q[i];
+    const int64_t qrow = a.q_begin + qrel;
+    if (lane == 0) need[i] = -1;
+    const double uq = u.uval_q[qrow];
+    const int nc = a.ncand[qrel];
+    if (!(uq > 0.0) || nc < a.P) return;
+    const int keep = a.P;
+    const double rq = __dsqrt_rn(u.sqn_q[qrow]);
+    const uint32_t cq = u.qcode[qrow];
+    const TQ* xq_row = xq + (size_t)qrow * ldq;
+    const double FLOOR = 1.0 - 9.094947017729282e-13;   // 1 - 2^-40
+    // ---- T_P over the candidates in M
+    double mine = -INFINITY, thr = -INFINITY;
+    int filled = 0;
+    for (int base = 0; base < u.nm; base += 32) {
+        const int j = base + lane;
+        double k = -INFINITY;
+        bool cand = false;
+        if (j < u.nm) {
+            const uint32_t x = cq ^ u.mcode[j];
+            cand = ((x - u.low) & ~x & u.high) != 0u;
+            if (cand) k = p2u_sim<TQ, TB>(u, j, uq, rq, a.D, xq_row, xb, a.ldb);
+        }
+        unsigned want = __ballot_sync(0xffffffffu, cand && k == k && (k > thr || filled < keep));
+        while (want) {
+            const int src = __ffs(want) - 1;
+            want &= want - 1;
+            const double x = __shfl_sync(0xffffffffu, k, src);
+            if (x > thr || filled < keep) {
+                const int pos = __popc(__ballot_sync(0xffffffffu, mine >= x));
+                const double up = __shfl_up_sync(0xffffffffu, mine, 1);
+                mine = lane < pos ? mine : (lane == pos ? x : up);
+                if (filled < keep) filled++;
+                thr = filled < keep ? -INFINITY : __shfl_sync(0xffffffffu, mine, keep - 1);
+            }
+        }
+    }
+    if (filled < keep) return;
+    const double TP = __shfl_sync(0xffffffffu, mine, keep - 1);
+    const double best = __shfl_sync(0xffffffffu, mine, 0);
+    if (!(TP >= FLOOR)) return;
+    // ---- e* = the last candidate of M with similarity >= T_P (read from the back), which must carry T_P itself
+    int je = -1;
+    double se = 0.0;
+    for (int base = (u.nm - 1) & ~31; base >= 0 && je < 0; base -= 32) {
+        const int j = base + lane;
+        double k = -INFINITY;
+        if (j < u.nm) {
+            const uint32_t x = cq ^ u.mcode[j];
+            if (((x - u.low) & ~x & u.high) != 0u) k = p2u_sim<TQ, TB>(u, j, uq, rq, a.D, xq_row, xb, a.ldb);
+        }
+        const unsigned b = __ballot_sync(0xffffffffu, k >= TP);
+        if (b) { const int src = 31 - __clz(b); je = base + src; se = __shfl_sync(0xffffffffu, k, src); }
+    }
+    if (je < 0 || se != TP) return;
+    if (best != TP) {
+        // similarities above T_P among the P best: R is not one run of equal keys -- its literal sort runs in phase B
+        int m = 0;
+        for (int base = 0; base <= je; base += 32) {
+            const int j = base + lane;
+            double k = -INFINITY;
+            if (j <= je) {
+                const uint32_t x = cq ^ u.mcode[j];
+                if (((x - u.low) & ~x & u.high) != 0u) k = p2u_sim<TQ, TB>(u, j, uq, rq, a.D, xq_row, xb, a.ldb);
+            }
+            m += __popc(__ballot_sync(0xffffffffu, k >= TP));
+        }
+        if (lane == 0) { need[i] = m; rlim_out[i] = je + 1; tp_out[i] = TP; }
+        return;
+    }
+    // ---- every member of R equals T_P: the literal sort leaves it untouched, the answer is its first P rows
+    int got = 0;
+    for (int base = 0; base <= je && got < keep; base += 32) {
+        const int j = base + lane;
+        double k = -INFINITY;
+        if (j <= je) {
+            const uint32_t x = cq ^ u.mcode[j];
+            if (((x - u.low) & ~x & u.high) != 0u) k = p2u_sim<TQ, TB>(u, j, uq, rq, a.D, xq_row, xb, a.ldb);
+        }
+        const bool hit = k >= TP;
+        const unsigned b = __ballot_sync(0xffffffffu, hit);
+        if (hit) { const int pos = got + __popc(b & ((1u << lane) - 1u)); if (pos < keep) { s_idx[warp][pos] = u.mrow[j]; s_sim[warp][pos] = k; } }
+        got += __popc(b);
+    }
+    __syncwarp();
+    if (lane == 0) {
+        need[i] = 0;
+        atomicAdd(&a.counters[CRX_CNT_TOPP_PASS2], 1ull);
+        if (a.qstatus) a.qstatus[qrel] = CRX_Q_EXACT;
+    }
+    if (a.nbr_rows) for (int j = lane; j < a.P; j += 32) a.nbr_rows[(size_t)qrel * a.P + j] = s_idx[warp][j];
+    if (a.nbr_sims) for (int j = lane; j < a.P; j += 32) a.nbr_sims[(size_t)qrel * a.P + j] = s_sim[warp][j];
+    if (a.recs)
+        predict_and_recommend<TB>(xb, a.ldb, a.mean_b, a.unk_q + qrow * a.D, a.mean_q[qrow], a.D, s_idx[warp], s_sim[warp], keep, a.Nrec,
+                                  s_pred[warp], s_coin[warp], a.recs + (size_t)qrel * a.Nrec);
+}
+
+// phase B: R written out (row order), literal quicksort, answer.  off[i] .. off[i + 1]: the query's slice of the scratch
+template <typename TQ, typename TB>
+__global__ void __launch_bounds__(128)
+p2u_sort_kernel(const TQ* __restrict__ xq, int ldq, const TB* __restrict__ xb, P2Resolve a, P2Uniform u, const int32_t* __restrict__ need,
+                const int32_t* __restrict__ rlim_in, const double* __restrict__ tp_in, const int64_t* __restrict__ off,
+                double* __restrict__ keys, int32_t* __restrict__ vals) {
+    constexpr int QW = 4;
+    __shared__ int posge[QW][128];
+    __shared__ double hk[QW][128];
+    __shared__ int hv[QW][128];
+    __shared__ int s_idx[QW][32];
+    __shared__ double s_sim[QW][32];
+    __shared__ double s_pred[QW][128];
+    __shared__ int s_coin[QW][128];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const unsigned int i = blockIdx.x * QW + warp;
+    if (i >= a.n || need[i] <= 0) return;
+    const int qrel = a.cur.q[i];
+    const int64_t qrow = a.q_begin + qrel;
+    const double uq = u.uval_q[qrow], rq = __dsqrt_rn(u.sqn_q[qrow]), TP = tp_in[i];
+    const uint32_t cq = u.qcode[qrow];
+    const TQ* xq_row = xq + (size_t)qrow * ldq;
+    double* key = keys + off[i];
+    int* val = vals + off[i];
+    const int rlim = rlim_in[i], keep = a.P;
+    int m = 0;
+    for (int base = 0; base < rlim; base += 32) {
+        const int j = base + lane;
+        double k = -INFINITY;
+        if (j < rlim) {
+            const uint32_t x = cq ^ u.mcode[j];
+            if (((x - u.low) & ~x & u.high) != 0u) k = p2u_sim<TQ, TB>(u, j, uq, rq, a.D, xq_row, xb, a.ldb);
+        }
+        const bool hit = k >= TP;
+        const unsigned b = __ballot_sync(0xffffffffu, hit);
+        if (hit) { const int pos = m + __popc(b & ((1u << lane) - 1u)); key[pos] = k; val[pos] = u.mrow[j]; }
+        m += __popc(b);
+    }
+    __syncwarp();
+    warp_qs_topn_big(key, val, m, keep, posge[warp], hk[warp], hv[warp]);
+    if (lane < keep) { s_idx[warp][lane] = val[lane]; s_sim[warp][lane] = key[lane]; }
+    __syncwarp();
+    if (lane == 0) {
+        atomicAdd(&a.counters[CRX_CNT_TOPP_PASS2], 1ull);
+        if (a.qstatus) a.qstatus[qrel] = CRX_Q_EXACT;
+    }
+    if (a.nbr_rows) for (int j = lane; j < a.P; j += 32) a.nbr_rows[(size_t)qrel * a.P + j] = s_idx[warp][j];
+    if (a.nbr_sims) for (int j = lane; j < a.P; j += 32) a.nbr_sims[(size_t)qrel * a.P + j] = s_sim[warp][j];
+    if (a.recs)
+        predict_and_recommend<TB>(xb, a.ldb, a.mean_b, a.unk_q + qrow * a.D, a.mean_q[qrow], a.D, s_idx[warp], s_sim[warp], keep, a.Nrec,
+                                  s_pred[warp], s_coin[warp], a.recs + (size_t)qrel * a.Nrec);
+}
+
+// alpha(x) = (sum x_k) / (sqrt(D) |x|) of the rows that are not constant; flag[row] = 1 for the members of M
+template <typename T>
+__global__ void __launch_bounds__(256) p2u_flag_kernel(const T* __restrict__ x, int ld, int D, const double* __restrict__ sqn, const double* __restrict__ uval,
+                                                       int64_t n, uint8_t* __restrict__ flag, int* __restrict__ refuse) {
+    const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= n) return;
+    const double uv = uval[row];
+    if (uv == uv) {
+        if (lane == 0) { flag[row] = uv > 0.0; if (uv == 0.0) *refuse = 1; }   // an all-zero row has no similarity: the general rounds decide
+        return;
+    }
+    double s = 0.0;
+    for (int k = lane; k < D; k += 32) s += (double)x[row * ld + k];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    const double alpha = s / (sqrt((double)D) * sqrt(sqn[row]));
+    if (lane == 0) flag[row] = alpha >= 1.0 - 1.8189894035458565e-12;   // 1 - 2^-39 (NaN: not a member)
+}
+
+__global__ void p2u_gather_kernel(const int32_t* __restrict__ mrow, int nm, const double* __restrict__ uval, const double* __restrict__ sqn,
+                                  const uint32_t* __restrict__ ccode, double* __restrict__ mval, double* __restrict__ mroot, uint32_t* __restrict__ mcode) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= nm) return;
+    const int r = mrow[j];
+    mval[j] = uval[r];
+    mroot[j] = __dsqrt_rn(sqn[r]);
+    mcode[j] = ccode[r];
+}
+
+// queue entries that phase A / B answered leave the queue
+__global__ void p2u_compact_kernel(P2Queue cur, unsigned int n, const int32_t* __restrict__ need, P2Queue out) {
+    const unsigned int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n || need[i] >= 0) return;
+    p2_emit(out, cur.q[i], cur.theta[i], cur.colx[i], cur.tries[i]);
 }
 
 // queries still queued after the last round keep the provisional answer of rec_finalize and are counted

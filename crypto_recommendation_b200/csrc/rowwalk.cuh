@@ -23,13 +23,28 @@ __device__ __forceinline__ Walk walk_rows(const T* __restrict__ x, int ld, int d
     int lane = threadIdx.x & 31;
     double s = 0.0;
     X87 acc = {0.0, 0.0};
+    const int myrow32 = (int)myrow;   // rows are < 2^31 (crx_points_create)
     for (int c0 = 0; c0 < d; c0 += 16) {
-#pragma unroll 4
-        for (int it = 0; it < 16; it++) {
-            int r = it * 2 + (lane >> 4);
-            int64_t src = __shfl_sync(0xffffffffu, myrow, r);
-            int col = c0 + (lane & 15);
-            tile[r][lane & 15] = (src >= 0 && col < d) ? (double)x[src * ld + col] : 0.0;
+        // 16-byte pieces: one load instruction fetches 64 contiguous bytes of 8 rows (fp32) / 128 bytes of 4 rows (fp64);
+        // ld is a multiple of 4 and the padding holds zeros, so a piece that starts inside the row is readable
+        if constexpr (sizeof(T) == 4) {
+#pragma unroll
+            for (int it = 0; it < 4; it++) {
+                const int r = it * 8 + (lane >> 2), piece = (lane & 3) * 4;
+                const int src = __shfl_sync(0xffffffffu, myrow32, r);
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (src >= 0 && c0 + piece < ld) v = *reinterpret_cast<const float4*>(x + (size_t)src * ld + c0 + piece);
+                tile[r][piece] = (double)v.x; tile[r][piece + 1] = (double)v.y; tile[r][piece + 2] = (double)v.z; tile[r][piece + 3] = (double)v.w;
+            }
+        } else {
+#pragma unroll
+            for (int it = 0; it < 8; it++) {
+                const int r = it * 4 + (lane >> 3), piece = (lane & 7) * 2;
+                const int src = __shfl_sync(0xffffffffu, myrow32, r);
+                double2 v = make_double2(0.0, 0.0);
+                if (src >= 0 && c0 + piece < ld) v = *reinterpret_cast<const double2*>(x + (size_t)src * ld + c0 + piece);
+                tile[r][piece] = v.x; tile[r][piece + 1] = v.y;
+            }
         }
         __syncwarp();
         int lim = min(16, d - c0);

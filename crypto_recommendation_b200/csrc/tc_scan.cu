@@ -27,8 +27,16 @@ constexpr int TN = 256;            // columns per tile (UMMA N = 256: A 4 KB + B
 constexpr int BLK_BYTES = TM * 64 * 2;   // one 128-row x 64-col fp16 block of A = 16 KB
 constexpr int BBLK_BYTES = TN * 64 * 2;  // one 256-row x 64-col fp16 block of B = 32 KB
 constexpr int NS = 3;              // B ring stages
-constexpr uint32_t IDESC = (1u << 4) /* D = F32 */ | (0u << 7) /* A = F16 */ | (0u << 10) /* B = F16 */ |
-                           ((uint32_t)(TN >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);  // K-major A and B
+constexpr uint32_t idesc_for(int n) {   // D = F32, A = B = F16, K-major A and B, N = n, M = 128
+    return (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
+}
+// "A from tensor memory" variant of the top-P / collection scans (ATM): the 128 query rows are written ONCE into TMEM
+// columns [384, 512) (tcgen05.st, thread = row), the two accumulators shrink to 192 columns each, and every MMA reads only
+// its B operand from shared memory.  With A and B both in shared memory the operand reads (4 + 8 KB per 128-cycle MMA =
+// 96 B/clk) plus the TMA writes (35 B/clk) exceeded the 128 B/clk of the shared-memory pipe and held the tensor pipe at 73%.
+constexpr int TN_ATM = 192;
+constexpr int NS_ATM = 4;
+constexpr int ATM_COL = 2 * TN_ATM;   // first TMEM column of the A operand: 64 words of hi parts, then 64 words of lo parts
 
 // ---------------------------------------------------------------- PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -68,14 +76,25 @@ __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::
 __device__ __forceinline__ void tc_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-__device__ __forceinline__ void tc_mma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
+__device__ __forceinline__ void tc_mma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate, uint32_t idesc) {
     asm volatile(
         "{\n"
         ".reg .pred p;\n"
         "setp.ne.b32 p, %4, 0;\n"
         "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
         "}\n" ::"r"(tmem_d),
-        "l"(adesc), "l"(bdesc), "r"(IDESC), "r"(accumulate)
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// A operand in tensor memory (row = lane, two fp16 per 32-bit column), B in shared memory
+__device__ __forceinline__ void tc_mma_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t accumulate, uint32_t idesc) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d),
+        "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
 // K-major, 128-byte swizzle, rows at 128 B pitch, 8-row groups 1024 B apart (cute::UMMA::SmemDescriptor)
@@ -85,11 +104,29 @@ __device__ __forceinline__ uint64_t smem_desc(uint32_t addr) {
 }
 // up to four K=16 MMAs over one 64-column block; descriptors advance by 32 bytes (>> 4 = 2).  `steps` < 4
 // skips the all-zero padding columns of the last block (D = 100 needs 7 of the 8 K=16 slices).
-__device__ __forceinline__ void mma_block(uint32_t tmem_d, uint32_t a_addr, uint32_t b_addr, uint32_t acc_first, int steps) {
+__device__ __forceinline__ void mma_block(uint32_t tmem_d, uint32_t a_addr, uint32_t b_addr, uint32_t acc_first, int steps, uint32_t idesc) {
     uint64_t ad = smem_desc(a_addr), bd = smem_desc(b_addr);
 #pragma unroll
     for (int k = 0; k < 4; k++)
-        if (k < steps) tc_mma(tmem_d, ad + 2 * k, bd + 2 * k, k == 0 ? acc_first : 1u);
+        if (k < steps) tc_mma(tmem_d, ad + 2 * k, bd + 2 * k, k == 0 ? acc_first : 1u, idesc);
+}
+// the same with the A block in tensor memory: a K = 16 slice is 8 columns
+__device__ __forceinline__ void mma_block_ts(uint32_t tmem_d, uint32_t a_tmem, uint32_t b_addr, uint32_t acc_first, int steps, uint32_t idesc) {
+    uint64_t bd = smem_desc(b_addr);
+#pragma unroll
+    for (int k = 0; k < 4; k++)
+        if (k < steps) tc_mma_ts(tmem_d, a_tmem + 8 * k, bd + 2 * k, k == 0 ? acc_first : 1u, idesc);
+}
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+        "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]),
+        "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]),
+        "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]),
+        "r"(r[31])
+        : "memory");
 }
 __device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t (&r)[32]) {
     asm volatile(
@@ -108,6 +145,8 @@ struct TcParams {
     int64_t nb;       // valid rows of B
     int ntiles, nkb;
     int last_steps;   // K=16 slices of the last 64-column block that hold data
+    const uint32_t* a_words;   // ATM: the A operand in global memory, [rows_pad][nkb * 64] words (hi part, then lo part)
+    int64_t a_rows_pad;
     // top-P
     const uint32_t* qcode;
     const uint32_t* ccode;
@@ -131,17 +170,14 @@ struct TcParams {
     float* blockmax;       // [nq][2][TC_NBLK] or NULL
     int nblk;
     int bt[TC_NBLK + 1];
-    // threshold collection (second pass of the top-P): compact row i of A is query c_qrow[i]; every masked column with
-    // score >= c_theta[i] or column index > c_colx[i] is appended, in column order, to the row's chunk list
+    // threshold collection (second pass of the top-P): compact row i of A is query c_qrow[i]; the bit of every masked column with
+    // score >= c_theta[i] or column index > c_colx[i] is set in the row's line of the mask matrix
     const float* c_theta;
     const int32_t* c_colx;
     const int32_t* c_qrow;
-    int32_t* pool;          // [pool_chunks][TC_CHUNK]: word 0 = next chunk (-1 = none), then TC_CHUNK - 1 columns
-    unsigned int* pool_next;
-    unsigned int pool_chunks;
-    int32_t* c_head;        // [rows] first chunk (-1 = empty)
-    int32_t* c_count;       // [rows] entries (counted even when the pool ran dry)
-    int32_t* c_ovf;         // [rows] 1 = the pool ran dry: the list is incomplete
+    uint32_t* cmask;        // [ntiles][TN / 32][c_rows_pad] pass bits of every 32-column chunk (one coalesced store per warp)
+    int64_t c_rows_pad;     // rows of the mask matrix (the grid's rows, a multiple of 128)
+    int32_t* c_count;       // [rows] number of set bits, added up by the row's two epilogue threads (zeroed by the caller)
 };
 
 constexpr int MODE_TOPP = 0, MODE_ARGMIN = 1, MODE_ROWSUM = 2, MODE_COLLECT = 3;
@@ -191,21 +227,29 @@ constexpr int NTHREADS_K = 64 + NEPI * 32;    // + producer warp + MMA warp
 // DENSE (top-P only): nearly every column shares a bucket with every row (f = mean|cand|/N close to 1), so the
 // hot loop only tracks the running maximum of the raw scores (1 FMNMX per score) and the table mask is
 // evaluated in the rare path; otherwise the mask is applied before the maximum (5 instructions per score).
-template <int MODE, bool DENSE>
+template <int MODE, bool DENSE, bool ATM = false>
 __global__ void __launch_bounds__(NTHREADS_K, 1)
 tc_scan_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, TcParams p) {
+    static_assert(!ATM || MODE == MODE_TOPP || MODE == MODE_COLLECT, "A from tensor memory: top-P and collection scans only");
+    constexpr int TN = ATM ? TN_ATM : ::TN;                 // columns per tile (shadows the file-scope value)
+    constexpr int NS = ATM ? NS_ATM : ::NS;
+    constexpr int BBLK_BYTES = TN * 64 * 2;
+    constexpr int HALF = TN / 2;                            // columns of a tile per epilogue thread
+    constexpr int NCH = HALF / 32;                          // 32-column chunks per epilogue thread and tile
+    constexpr uint32_t IDESC = idesc_for(TN);
     extern __shared__ __align__(1024) uint8_t smem[];
     const int nblk = 2 * p.nkb;
     // ARGMIN is persistent: the CTA walks row tiles blockIdx.x, blockIdx.x + gridDim.x, ... with TWO A buffers, so the
     // A load, the pipeline fill and the drain of one row tile hide behind the MMAs of its neighbours (K = 1024 columns
     // are only 4 tiles per row tile).  TOPP / ROWSUM keep one row tile per CTA (their lists / long scans fill the CTA).
     constexpr int NA = MODE == MODE_ARGMIN ? 2 : 1;
+    constexpr int A_BYTES = ATM ? 0 : NA * 4 * BLK_BYTES;   // ATM: the A operand lives in tensor memory
     uint8_t* sA = smem;                                    // NA x (nblk blocks, <= 64 KB)
-    uint8_t* sB = smem + NA * 4 * BLK_BYTES;               // NS-stage ring of 32 KB blocks
-    float* ls = reinterpret_cast<float*>(smem + NA * 4 * BLK_BYTES + NS * BBLK_BYTES);   // [2 halves][HL][TM]  (top-P only)
+    uint8_t* sB = smem + A_BYTES;                          // NS-stage ring of B blocks
+    float* ls = reinterpret_cast<float*>(smem + A_BYTES + NS * BBLK_BYTES);   // [2 halves][HL][TM]  (top-P only)
     int32_t* li = reinterpret_cast<int32_t*>(ls + 2 * HL * TM);
     uint32_t* stile = MODE == MODE_TOPP ? reinterpret_cast<uint32_t*>(li + 2 * HL * TM)
-                                        : reinterpret_cast<uint32_t*>(smem + NA * 4 * BLK_BYTES + NS * BBLK_BYTES);  // [2][TN] codes / half norms
+                                        : reinterpret_cast<uint32_t*>(smem + A_BYTES + NS * BBLK_BYTES);  // [2][TN] codes / half norms
     constexpr int STW = MODE == MODE_ROWSUM ? 2 : 1;       // staged words per column (row sums: norm + error weight)
     uint64_t* bars = reinterpret_cast<uint64_t*>(stile + 2 * TN * STW);
     uint64_t* a_full = bars;            // [2]
@@ -218,13 +262,11 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // hand-over between the column halves: [TM][3] floats (argmin: aliases the staging tile, shared memory is full) or
     // [TM][2] doubles (row sums)
     float* merge = MODE == MODE_ARGMIN ? reinterpret_cast<float*>(stile) : reinterpret_cast<float*>(tmem_slot + 4);
-    // collection: pass masks of the previous tile, [tile parity][word 0..7 = half * 4 + chunk][row]
-    uint32_t* mbuf = reinterpret_cast<uint32_t*>(tmem_slot + 4);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
         if (smem_u32(smem) & 1023u) __trap();  // the 128B-swizzle atoms need a 1024-byte aligned base
-        for (int b = 0; b < 2; b++) { mbar_init(&a_full[b], 1); mbar_init(&a_empty[b], 1); }
+        for (int b = 0; b < 2; b++) { mbar_init(&a_full[b], ATM ? NEPI : 1); mbar_init(&a_empty[b], 1); }
         for (int s = 0; s < NS; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
         for (int b = 0; b < 2; b++) { mbar_init(&tfull[b], 1); mbar_init(&tempty[b], NEPI); }
         fence_barrier_init();
@@ -258,10 +300,12 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             for (int rt = blockIdx.x; rt < n_row_tiles; rt += rt_step, it++) {
                 const int ab = it & (NA - 1);
                 const uint32_t use = (uint32_t)(it / NA);
-                mbar_wait(&a_empty[ab], (use & 1u) ^ 1u);   // the MMAs of the previous row tile in this buffer are done
-                mbar_arrive_expect_tx(&a_full[ab], (uint32_t)(nblk * BLK_BYTES));
-                const int arow = MODE == MODE_ARGMIN ? (int)(p.q0 + (int64_t)rt * TM) : (int)row0;
-                for (int b = 0; b < nblk; b++) tma_load_2d(sA + ab * 4 * BLK_BYTES + b * BLK_BYTES, &tmA, b * 64, arow, &a_full[ab]);
+                if (!ATM) {
+                    mbar_wait(&a_empty[ab], (use & 1u) ^ 1u);   // the MMAs of the previous row tile in this buffer are done
+                    mbar_arrive_expect_tx(&a_full[ab], (uint32_t)(nblk * BLK_BYTES));
+                    const int arow = MODE == MODE_ARGMIN ? (int)(p.q0 + (int64_t)rt * TM) : (int)row0;
+                    for (int b = 0; b < nblk; b++) tma_load_2d(sA + ab * 4 * BLK_BYTES + b * BLK_BYTES, &tmA, b * 64, arow, &a_full[ab]);
+                }
                 for (int t = 0; t < ntiles; t++) {
                     for (int b = 0; b < nload; b++) {
                         mbar_wait(&empty[stage], phase ^ 1);
@@ -290,7 +334,7 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 const uint32_t bphase = (uint32_t)(g >> 1) & 1u;
                 mbar_wait(&tempty[buf], bphase ^ 1);
                 tc_fence_after();
-                const uint32_t d = tmem_base + (uint32_t)(buf * TN);  // 256 fp32 columns per buffer
+                const uint32_t d = tmem_base + (uint32_t)(buf * TN);  // TN fp32 columns per buffer
                 const int nload = p.nprod == 1 ? p.nkb : nblk;
                 for (int b = 0; b < nload; b++) {
                     mbar_wait(&full[stage], phase);
@@ -298,11 +342,19 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     const uint32_t bs = b_base + stage * BBLK_BYTES;
                     const int j = b < p.nkb ? b : b - p.nkb;                 // 64-column block index inside a part
                     const int steps = j == p.nkb - 1 ? p.last_steps : 4;
-                    if (b < p.nkb) {  // B.hi_j with A.hi_j and A.lo_j
-                        mma_block(d, a_base + j * BLK_BYTES, bs, b == 0 ? 0u : 1u, steps);
-                        if (p.nprod != 1) mma_block(d, a_base + (p.nkb + j) * BLK_BYTES, bs, 1u, steps);
+                    if (ATM) {        // A blocks: 32 words (64 fp16) each, hi parts at ATM_COL, lo parts 64 columns behind
+                        const uint32_t ta = tmem_base + (uint32_t)(ATM_COL + j * 32);
+                        if (b < p.nkb) {
+                            mma_block_ts(d, ta, bs, b == 0 ? 0u : 1u, steps, IDESC);
+                            if (p.nprod != 1) mma_block_ts(d, ta + 64u, bs, 1u, steps, IDESC);
+                        } else {
+                            mma_block_ts(d, ta, bs, 1u, steps, IDESC);
+                        }
+                    } else if (b < p.nkb) {  // B.hi_j with A.hi_j and A.lo_j
+                        mma_block(d, a_base + j * BLK_BYTES, bs, b == 0 ? 0u : 1u, steps, IDESC);
+                        if (p.nprod != 1) mma_block(d, a_base + (p.nkb + j) * BLK_BYTES, bs, 1u, steps, IDESC);
                     } else {          // B.lo_j with A.hi_j
-                        mma_block(d, a_base + j * BLK_BYTES, bs, 1u, steps);
+                        mma_block(d, a_base + j * BLK_BYTES, bs, 1u, steps, IDESC);
                     }
                     tc_commit(&empty[stage]);
                     if (++stage == NS) { stage = 0; phase ^= 1; }
@@ -317,7 +369,7 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int ew = warp - 2;                 // 0..7
         const int etid = threadIdx.x - 64;       // 0..255
         const int quarter = warp & 3;            // TMEM lane quarter this warp may read
-        const int half = ew >> 2;                // columns [128*half, 128*half + 128) of every tile
+        const int half = ew >> 2;                // columns [HALF*half, HALF*half + HALF) of every tile
         const int me = quarter * 32 + lane;      // row inside the tile
         int it = 0;
         for (int rt = blockIdx.x; rt < n_row_tiles; rt += rt_step, it++) {
@@ -336,42 +388,39 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             if (valid) cq = p.qcode[p.q0 + grow];
             for (int e = 0; e < HL; e++) { myls[e * TM] = -INFINITY; myli[e * TM] = -1; }
         }
+        if (ATM) {
+            // this thread's operand row (padded rows hold zeros): the half-0 warp of a lane quarter writes the hi part, the
+            // half-1 warp the lo part; a K = 16 slice is 8 consecutive columns of the row's lane
+            const int wpp = p.nkb * 32;    // words per part
+            const int64_t arow = p.q0 + (int64_t)rt * TM + me;
+            const bool arow_ok = arow < p.a_rows_pad;   // a query range that does not start on a tile boundary can reach beyond the operand
+            const uint4* src = reinterpret_cast<const uint4*>(p.a_words + (size_t)(arow_ok ? arow : 0) * (size_t)(2 * wpp) + (size_t)half * wpp);
+            const uint32_t ta = tmem_base + (uint32_t)(ATM_COL + half * 64) + ((uint32_t)(quarter * 32) << 16);
+            for (int blk = 0; blk < p.nkb; blk++) {
+                uint32_t w[32];
+#pragma unroll
+                for (int q4 = 0; q4 < 8; q4++) {
+                    const uint4 v = arow_ok ? src[blk * 8 + q4] : make_uint4(0u, 0u, 0u, 0u);
+                    w[q4 * 4 + 0] = v.x; w[q4 * 4 + 1] = v.y; w[q4 * 4 + 2] = v.z; w[q4 * 4 + 3] = v.w;
+                }
+                tmem_st32(ta + blk * 32, w);
+            }
+            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&a_full[0]);
+        }
         // top-P: running maximum of the raw scores of the current geometric column block
         float bm = -INFINITY;
         int bnext = 1;
-        // collection: threshold, "everything behind" column and the row's chunk list (appended by the half-0 thread)
+        // collection: threshold, "everything behind" column, number of bits this thread has set
         float c_th = INFINITY;
-        int c_cx = 0x7fffffff, c_cur = -1, c_fill = 0, c_total = 0, c_hd = -1, c_ov = 0;
+        int c_cx = 0x7fffffff, c_total = 0;
         if (MODE == MODE_COLLECT && valid) {
             cq = p.qcode[p.c_qrow[grow]];
             c_th = p.c_theta[grow];
             c_cx = p.c_colx[grow];
         }
-        auto c_append_tile = [&](int tprev) {
-            // the pass masks of tile `tprev` of this row (both halves), in column order
-            const uint32_t* mb = mbuf + (tprev & 1) * 8 * TM + me;
-#pragma unroll 1
-            for (int w = 0; w < 8; w++) {
-                uint32_t bits = mb[w * TM];
-                const int cb = tprev * TN + w * 32;
-                while (bits != 0u) {
-                    const int j = __ffs(bits) - 1;
-                    bits &= bits - 1u;
-                    c_total++;
-                    if (c_ov) continue;
-                    if (c_cur < 0 || c_fill == TC_CHUNK - 1) {
-                        const unsigned int nc = atomicAdd(p.pool_next, 1u);
-                        if (nc >= p.pool_chunks) { c_ov = 1; continue; }
-                        p.pool[(size_t)nc * TC_CHUNK] = -1;
-                        if (c_cur < 0) c_hd = (int)nc; else p.pool[(size_t)c_cur * TC_CHUNK] = (int)nc;
-                        c_cur = (int)nc;
-                        c_fill = 0;
-                    }
-                    p.pool[(size_t)c_cur * TC_CHUNK + 1 + c_fill] = cb + j;
-                    c_fill++;
-                }
-            }
-        };
         const uint32_t low = p.low_mask, high = p.high_mask;
         // staging value (packed code / half norm) of this thread's column of the NEXT tile, fetched one tile ahead
         auto fetch_col = [&](int t) -> uint32_t {
@@ -391,11 +440,10 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const int g = it * ntiles + t;             // running tile number (as in the MMA issuer)
             const int buf = g & 1;
             const uint32_t bphase = (uint32_t)(g >> 1) & 1u;
-            stile[buf * TN * STW + etid] = next_col;
+            if (etid < TN) stile[buf * TN * STW + etid] = next_col;
             if (MODE == MODE_ROWSUM) { stile[buf * TN * STW + TN + etid] = __float_as_uint(next_col2); next_col2 = fetch_col2(t + 1); }
             next_col = fetch_col(t + 1);
             asm volatile("bar.sync 1, 256;" ::: "memory");
-            if (MODE == MODE_COLLECT && half == 0 && t > 0 && valid) c_append_tile(t - 1);
             if (MODE == MODE_TOPP && p.blockmax != nullptr && t == p.bt[bnext]) {
                 if (valid) p.blockmax[(grow * 2 + half) * TC_NBLK + bnext - 1] = bm;
                 bm = -INFINITY;
@@ -403,14 +451,15 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
             mbar_wait(&tfull[buf], bphase);
             tc_fence_after();
-            const uint32_t taddr = tmem_base + (uint32_t)(buf * TN + half * 128) + ((uint32_t)(quarter * 32) << 16);
-            // this thread's 128 columns in two rounds of two 32-column chunks; the TMEM buffer is handed back as
+            const uint32_t taddr = tmem_base + (uint32_t)(buf * TN + half * HALF) + ((uint32_t)(quarter * 32) << 16);
+            // this thread's HALF columns in two rounds of (up to) two 32-column chunks; the TMEM buffer is handed back as
             // soon as the second round sits in registers
 #pragma unroll 1
             for (int rnd = 0; rnd < 2; rnd++) {
             uint32_t r0[32], r1[32];
+            const bool two = rnd * 2 + 1 < NCH;    // NCH = 3 (ATM): the second round holds one chunk
             tmem_ld32_nowait(taddr + rnd * 64, r0);
-            tmem_ld32_nowait(taddr + rnd * 64 + 32, r1);
+            if (two) tmem_ld32_nowait(taddr + rnd * 64 + 32, r1);
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
             if (rnd == 1) {
                 tc_fence_before();
@@ -419,9 +468,10 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
 #pragma unroll
             for (int ch = 0; ch < 2; ch++) {
+                if (rnd * 2 + ch >= NCH) continue;
                 uint32_t (&r)[32] = ch == 0 ? r0 : r1;
-                const uint4* st4 = reinterpret_cast<const uint4*>(stile + buf * TN * STW + half * 128 + rnd * 64 + ch * 32);
-                const int cbase = t * TN + half * 128 + rnd * 64 + ch * 32;
+                const uint4* st4 = reinterpret_cast<const uint4*>(stile + buf * TN * STW + half * HALF + rnd * 64 + ch * 32);
+                const int cbase = t * TN + half * HALF + rnd * 64 + ch * 32;
                 if (MODE == MODE_TOPP) {
                     // hot loop: running maximum of the (masked) scores, four independent chains
                     float vm[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
@@ -497,7 +547,9 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         const uint32_t x = cq ^ reinterpret_cast<const uint32_t*>(st4)[j];
                         if (((x - low) & ~x & high) == 0u) bits &= ~(1u << j);
                     }
-                    mbuf[((t & 1) * 8 + half * 4 + rnd * 2 + ch) * TM + me] = bits;
+                    // rows of a warp are consecutive: 128 contiguous bytes per store
+                    p.cmask[((size_t)t * (2 * NCH) + (size_t)(half * NCH + rnd * 2 + ch)) * (size_t)p.c_rows_pad + (size_t)grow] = bits;
+                    c_total += __popc(bits);
                 } else if (MODE == MODE_ROWSUM) {
                     // d = sqrt(max(0, |a|^2 + |b|^2 - 2 a.b)) and a running bound on its error.  The squared distance is
                     // off by at most E = ea + eb (error weights of the two rows: split-fp16 dot, fp32 norms, subnormal low
@@ -576,13 +628,7 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 }
             }
         } else if (MODE == MODE_COLLECT) {
-            asm volatile("bar.sync 1, 256;" ::: "memory");
-            if (half == 0 && valid) {
-                if (ntiles > 0) c_append_tile(ntiles - 1);
-                p.c_head[grow] = c_hd;
-                p.c_count[grow] = c_total;
-                p.c_ovf[grow] = c_ov;
-            }
+            if (valid && c_total) atomicAdd(&p.c_count[grow], c_total);
         } else if (MODE == MODE_ROWSUM) {
             double* dm = reinterpret_cast<double*>(merge);
             if (half == 1) { dm[me * 2 + 0] = rs_sum; dm[me * 2 + 1] = rs_err; }
@@ -678,7 +724,13 @@ int make_tensor_map(const TcOperand& op, int box_rows, CUtensorMap* tm) {
     return CRX_OK;
 }
 
-size_t smem_for(int mode) {
+size_t smem_for(int mode, bool atm = false) {
+    if (atm) {   // no A tile; 4-stage ring of 24 KB blocks
+        size_t s = (size_t)NS_ATM * TN_ATM * 128 + 2 * TN_ATM * 4 + (8 + 2 * NS_ATM) * 8 + 16;
+        if (mode == MODE_TOPP) s += (size_t)2 * HL * TM * 8;
+        else s += (size_t)2 * 6 * TM * 4;
+        return s;
+    }
     size_t s = (size_t)4 * BLK_BYTES + (size_t)NS * BBLK_BYTES + 2 * TN * 4 + (8 + 2 * NS) * 8 + 16;
     if (mode == MODE_TOPP) s += (size_t)2 * HL * TM * 8;
     else if (mode == MODE_COLLECT) s += (size_t)2 * 8 * TM * 4;
@@ -730,9 +782,19 @@ int crx_tc_prepare_matrix(crx_ctx* c, const double* m, int K, int D, int ld, dou
     return CRX_OK;
 }
 
+// columns per tile of the top-P / collection scans: 256 with both operands in shared memory (default), 192 with the A operand
+// in tensor memory (CRX_TC_ATM=1).  Measured at C2 (1M x 1M x 100): 471 ms against 586 ms -- relieving the shared-memory pipe
+// does not pay for the N = 192 MMAs (the tensor core appears to step N in units of 128); the variant stays for the record.
+bool crx_tc_atm() {
+    static const bool on = getenv("CRX_TC_ATM") != nullptr && getenv("CRX_TC_ATM")[0] == '1';
+    return on;
+}
+int crx_tc_tile_cols() { return crx_tc_atm() ? TN_ATM : TN; }
+
 // geometric column blocks: block 0 = the first half of the tiles, block 1 = the next quarter, ... , the last block = one tile
 int crx_tc_blocks(int64_t b_rows, int* bt) {
-    const int nt = (int)((b_rows + TN - 1) / TN);
+    const int tn = crx_tc_tile_cols();
+    const int nt = (int)((b_rows + tn - 1) / tn);
     int nblk = 1;
     bt[0] = 0;
     for (int j = 1; j < TC_NBLK && (nt >> j) >= 1; j++) {
@@ -770,9 +832,15 @@ int crx_tc_gather(crx_ctx* c, const TcOperand& src, const int32_t* d_rows, int64
     return CRX_OK;
 }
 
+int64_t crx_tc_collect_mask_words(int64_t nrows, int64_t b_rows) {
+    const int tn = crx_tc_tile_cols();
+    const int64_t rows_pad = (nrows + TM - 1) / TM * TM, ntiles = (b_rows + tn - 1) / tn;
+    return ntiles * (tn / 32) * rows_pad;
+}
+
 int crx_tc_collect(crx_ctx* c, const TcOperand& A, int64_t nrows, const TcOperand& B, const uint32_t* qcode, const int32_t* d_qrow,
-                   const uint32_t* ccode, int k, int L, bool dense, const float* d_theta, const int32_t* d_colx, int32_t* pool,
-                   unsigned int* pool_next, unsigned int pool_chunks, int32_t* d_head, int32_t* d_count, int32_t* d_ovf) {
+                   const uint32_t* ccode, int k, int L, bool dense, const float* d_theta, const int32_t* d_colx, uint32_t* cmask,
+                   int32_t* d_count) {
     CRX_REQUIRE(A.nkb == B.nkb, "operand widths differ");
     CRX_REQUIRE(k * L <= 32 && k >= 1, "packed codes need k*L <= 32");
     if (nrows == 0) return CRX_OK;
@@ -781,27 +849,31 @@ int crx_tc_collect(crx_ctx* c, const TcOperand& A, int64_t nrows, const TcOperan
     CRX_TRY(make_tensor_map(B, TN, &tmB));
     TcParams p;
     memset(&p, 0, sizeof(p));
-    p.q0 = 0; p.nq = nrows; p.nb = B.rows; p.ntiles = (int)((B.rows + TN - 1) / TN); p.nkb = A.nkb;
+    const bool atm = crx_tc_atm();
+    const int tn = crx_tc_tile_cols();
+    if (atm) CRX_TRY(make_tensor_map(B, tn, &tmB));
+    p.q0 = 0; p.nq = nrows; p.nb = B.rows; p.ntiles = (int)((B.rows + tn - 1) / tn); p.nkb = A.nkb;
     p.last_steps = last_steps_of(A);
     p.nprod = 3;
+    p.a_words = (const uint32_t*)A.data; p.a_rows_pad = A.rows_pad;
     p.qcode = qcode; p.ccode = ccode;
     uint32_t low = 0, high = 0;
     for (int l = 0; l < L; l++) { low |= 1u << (l * k); high |= 1u << (l * k + k - 1); }
     p.low_mask = low; p.high_mask = high;
     p.c_theta = d_theta; p.c_colx = d_colx; p.c_qrow = d_qrow;
-    p.pool = pool; p.pool_next = pool_next; p.pool_chunks = pool_chunks;
-    p.c_head = d_head; p.c_count = d_count; p.c_ovf = d_ovf;
-    size_t smem = smem_for(MODE_COLLECT);
+    p.cmask = cmask; p.c_rows_pad = (nrows + TM - 1) / TM * TM; p.c_count = d_count;
+    size_t smem = smem_for(MODE_COLLECT, atm);
     int grid = (int)((nrows + TM - 1) / TM);
     CRX_KERNEL(c, "tc_collect_scan");
-    if (dense) {
+    if (atm) {   // (the table mask is applied to the set bits only: one variant serves dense and sparse candidate sets)
+        CRX_CUDA(cudaFuncSetAttribute(tc_scan_kernel<MODE_COLLECT, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        tc_scan_kernel<MODE_COLLECT, true, true><<<grid, NTHREADS_K, smem, c->stream>>>(tmA, tmB, p);
+    } else {
         CRX_CUDA(cudaFuncSetAttribute(tc_scan_kernel<MODE_COLLECT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         tc_scan_kernel<MODE_COLLECT, true><<<grid, NTHREADS_K, smem, c->stream>>>(tmA, tmB, p);
-    } else {
-        CRX_CUDA(cudaFuncSetAttribute(tc_scan_kernel<MODE_COLLECT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        tc_scan_kernel<MODE_COLLECT, false><<<grid, NTHREADS_K, smem, c->stream>>>(tmA, tmB, p);
     }
     CRX_CUDA(cudaGetLastError());
+    (void)dense;
     return CRX_OK;
 }
 
@@ -814,9 +886,13 @@ int crx_tc_topp(crx_ctx* c, const TcOperand& A, int64_t q0, int64_t nq, const Tc
     CRX_TRY(make_tensor_map(B, TN, &tmB));
     TcParams p;
     memset(&p, 0, sizeof(p));
-    p.q0 = q0; p.nq = nq; p.nb = B.rows; p.ntiles = (int)((B.rows + TN - 1) / TN); p.nkb = A.nkb;
+    const bool atm = crx_tc_atm() && nprod != 1;
+    const int tn = atm ? TN_ATM : TN;
+    if (atm) CRX_TRY(make_tensor_map(B, tn, &tmB));
+    p.q0 = q0; p.nq = nq; p.nb = B.rows; p.ntiles = (int)((B.rows + tn - 1) / tn); p.nkb = A.nkb;
     p.last_steps = last_steps_of(A);
     p.nprod = nprod == 1 ? 1 : 3;
+    p.a_words = (const uint32_t*)A.data; p.a_rows_pad = A.rows_pad;
     p.qcode = qcode; p.ccode = ccode;
     uint32_t low = 0, high = 0;
     for (int l = 0; l < L; l++) { low |= 1u << (l * k); high |= 1u << (l * k + k - 1); }
@@ -824,10 +900,16 @@ int crx_tc_topp(crx_ctx* c, const TcOperand& A, int64_t q0, int64_t nq, const Tc
     p.list_s = list_s; p.list_i = list_i;
     p.blockmax = blockmax;
     p.nblk = crx_tc_blocks(B.rows, p.bt);
-    size_t smem = smem_for(MODE_TOPP);
+    size_t smem = smem_for(MODE_TOPP, atm);
     int grid = (int)((nq + TM - 1) / TM);
     CRX_KERNEL(c, "tc_topp_scan");
-    if (dense) {
+    if (atm && dense) {
+        CRX_CUDA(cudaFuncSetAttribute(tc_scan_kernel<MODE_TOPP, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        tc_scan_kernel<MODE_TOPP, true, true><<<grid, NTHREADS_K, smem, c->stream>>>(tmA, tmB, p);
+    } else if (atm) {
+        CRX_CUDA(cudaFuncSetAttribute(tc_scan_kernel<MODE_TOPP, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        tc_scan_kernel<MODE_TOPP, false, true><<<grid, NTHREADS_K, smem, c->stream>>>(tmA, tmB, p);
+    } else if (dense) {
         CRX_CUDA(cudaFuncSetAttribute(tc_scan_kernel<MODE_TOPP, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         tc_scan_kernel<MODE_TOPP, true><<<grid, NTHREADS_K, smem, c->stream>>>(tmA, tmB, p);
     } else {

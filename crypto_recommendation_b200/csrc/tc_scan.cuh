@@ -35,7 +35,6 @@ int crx_tc_prepare_matrix(crx_ctx* c, const double* m, int K, int D, int ld, dou
 
 constexpr int TC_LIST = 64;  // per-row candidate list of the top-P filter
 constexpr int TC_NBLK = 16;  // geometric column blocks whose score maxima the top-P filter reports (crx_tc_blocks)
-constexpr int TC_CHUNK = 256;  // words per chunk of a collected list: [next chunk | 255 columns]
 
 // top-P filter: for query rows [q0, q0+nq) of A against all rows of B, keep the TC_LIST best scores among
 // the columns whose packed code shares at least one k-bit field with the query's code.
@@ -50,17 +49,20 @@ int crx_tc_topp(crx_ctx* c, const TcOperand& A, int64_t q0, int64_t nq, const Tc
                 float* blockmax = nullptr);
 // first tile of each geometric block into bt[0..nblk], bt[nblk] = number of 256-column tiles; returns nblk <= TC_NBLK
 int crx_tc_blocks(int64_t b_rows, int* bt);
-constexpr int TC_TILE_COLS = 256;
+// columns per tile of the top-P / collection scans (256; 192 with CRX_TC_ATM=1: A operand in tensor memory)
+int crx_tc_tile_cols();
 
 // operand rows d_rows[0..n) of `src` copied into a compact operand (padded with zero rows to a multiple of 128)
 int crx_tc_gather(crx_ctx* c, const TcOperand& src, const int32_t* d_rows, int64_t n, TcOperand* out);
 
-// threshold collection (second pass of the top-P): for compact row i of A (= query row d_qrow[i], which indexes qcode) every
-// column j of B that shares a bucket with the query and has score >= d_theta[i] (filter units) or j > d_colx[i] is appended,
-// in ascending column order, to the row's chunk list in `pool` (d_head / d_count / d_ovf per row; *pool_next must start at 0)
+// threshold collection (second pass of the top-P): for compact row i of A (= query row d_qrow[i], which indexes qcode) the bit of
+// every column j of B that shares a bucket with the query and has score >= d_theta[i] (filter units) or j > d_colx[i] is set in
+// cmask[(tile * (tile_cols / 32) + word)][rows_pad] (rows_pad = nrows rounded up to 128; every word of the matrix is written);
+// d_count[i] (zeroed by the caller) receives the number of set bits.  crx_tc_collect_mask_words: size of the matrix in words.
+int64_t crx_tc_collect_mask_words(int64_t nrows, int64_t b_rows);
 int crx_tc_collect(crx_ctx* c, const TcOperand& A, int64_t nrows, const TcOperand& B, const uint32_t* qcode, const int32_t* d_qrow,
-                   const uint32_t* ccode, int k, int L, bool dense, const float* d_theta, const int32_t* d_colx, int32_t* pool,
-                   unsigned int* pool_next, unsigned int pool_chunks, int32_t* d_head, int32_t* d_count, int32_t* d_ovf);
+                   const uint32_t* ccode, int k, int L, bool dense, const float* d_theta, const int32_t* d_colx, uint32_t* cmask,
+                   int32_t* d_count);
 
 // argmin filter: for rows [r0, r0+nr) of A against the K rows of B: best / second-best of
 // half_norm[j] - dot(a, b_j) (scaled units) and the best column.

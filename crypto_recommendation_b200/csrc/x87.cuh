@@ -70,6 +70,16 @@ CRX_X87_FN void x87_add(X87& acc, double p) {   // acc = round64(acc + p)
 }
 CRX_X87_FN double x87_to_double(const X87& a) { return CRX_DADD(a.h, a.l); }
 // double(inner_product / denom), denom = sqrt(na) * sqrt(nb) in double (cust_vector.hpp:171-173)
+// the same from the square roots of the two sums of squares (callers that evaluate many pairs of the same rows)
+CRX_X87_FN double cos_sim_x87_roots(const X87& ip, double ra, double rb) {
+    double denom = CRX_DMUL(ra, rb);
+    double q1 = CRX_DDIV(ip.h, denom);
+    double r = CRX_FMA(-q1, denom, ip.h);
+    double q2 = CRX_DDIV(CRX_DADD(r, ip.l), denom);
+    double s, v;
+    two_sum(q1, q2, s, v);
+    return CRX_DADD(s, x87_round_low(s, v));
+}
 CRX_X87_FN double cos_sim_x87(const X87& ip, double na, double nb) {
     double denom = CRX_DMUL(CRX_DSQRT(na), CRX_DSQRT(nb));
     double q1 = CRX_DDIV(ip.h, denom);

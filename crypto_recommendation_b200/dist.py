@@ -150,6 +150,24 @@ class NcclComm:
     def ptr(self):
         return self.h
 
+    _CODES = {"torch.float32": 0, "torch.float64": 1, "torch.int32": 2, "torch.int64": 3}
+
+    def allgather(self, send, recv):
+        """all-gather of CUDA tensors on the context's stream (recv holds world * send.numel() elements, rank order)"""
+        assert send.is_cuda and recv.is_cuda and send.is_contiguous() and recv.is_contiguous() and recv.numel() == self.world * send.numel()
+        c = self.h.contents
+        rc = c.allgather(c.user, ctypes.c_void_p(send.data_ptr()), ctypes.c_void_p(recv.data_ptr()), send.numel(), self._CODES[str(send.dtype)], 1)
+        if rc != 0:
+            raise RuntimeError("ncclAllGather failed: %s" % self.lib.crx_last_error().decode())
+
+    def allreduce(self, t, op="sum"):
+        """in-place all-reduce of a CUDA tensor on the context's stream"""
+        assert t.is_cuda and t.is_contiguous()
+        c = self.h.contents
+        rc = c.allreduce(c.user, ctypes.c_void_p(t.data_ptr()), t.numel(), self._CODES[str(t.dtype)], {"sum": 0, "max": 1, "min": 2}[op], 1)
+        if rc != 0:
+            raise RuntimeError("ncclAllReduce failed: %s" % self.lib.crx_last_error().decode())
+
     @property
     def calls(self):
         out = (ctypes.c_int64 * 3)()

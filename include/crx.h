@@ -53,6 +53,9 @@ int crx_ctx_destroy(crx_ctx* ctx);
 int crx_ctx_synchronize(crx_ctx* ctx);
 /* number of this library's own kernels launched so far on the context */
 int64_t crx_ctx_launch_count(const crx_ctx* ctx);
+/* synchronises the stream and returns the memory held by the stream-ordered pool to the driver (freed buffers are kept by
+ * default so that rebuilding tables every step costs no driver call) */
+int crx_ctx_trim(crx_ctx* ctx);
 /* per-kernel CUDA-event timing (on the context's stream).  enable!=0 starts recording every
  * launch; crx_ctx_kernel_time sums the launches whose name starts with `prefix`. */
 int crx_ctx_profile(crx_ctx* ctx, int enable);

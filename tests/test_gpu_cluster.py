@@ -50,6 +50,26 @@ def test_golden_clustering(ctx, port, golden, metric):
     assert_float_close(capi.silhouette_cluster(ctx, P, g["cl_lloyd_lab_%s" % name], X[cidx], metric), g["cl_sil_%s" % name], 1e-10)
 
 
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_cosine_lloyd_near_ties_follow_the_reference(ctx, port, dtype):
+    """Centroids that are scalar multiples of each other (and rating-like users, whose vectors repeat directions) have
+    cosine distances that differ only through the rounding of the reference's x87 accumulation: the plain FP64 scan cannot
+    rank them, so such rows are decided again with the reference's arithmetic (lowest index wins exact ties)."""
+    U, _, _ = synth.rating_users_fast(5000, 100, seed=77, min_known=1, max_known=3, dtype=dtype)
+    X64 = U.astype(np.float64)
+    n = U.shape[0]
+    rng = np.random.default_rng(5)
+    base = X64[rng.choice(n, 12, replace=False)]
+    scales = np.array([1.0, 3.0, 0.37, 2.0, 1.0 / 3.0])
+    C = np.concatenate([base * s for s in scales])          # 60 centroids, 12 directions
+    C = C[rng.permutation(len(C))]
+    P = ctx.points(U)
+    lab, dist = capi.lloyds_assignment(ctx, P, C, None, COSINE)
+    rl, rd = port.lloyds_assignment(X64, C, None, COSINE)
+    assert np.array_equal(lab, rl), "labels differ for %d rows" % int((lab != rl).sum())
+    assert np.array_equal(dist, rd)
+
+
 @pytest.mark.parametrize("metric", METRICS)
 @pytest.mark.parametrize("dtype,n,d,k", [(np.float32, 20000, 128, 64), (np.float64, 5000, 100, 30), (np.float32, 4097, 7, 3),
                                          (np.float32, 1000, 128, 1), (np.float64, 777, 1, 5), (np.float32, 3000, 100, 129)])
