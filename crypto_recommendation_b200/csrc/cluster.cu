@@ -304,29 +304,62 @@ lloyd_refine_kernel(const T* __restrict__ x, int ld, int D, const double* __rest
     bool sure = valid && b >= 0 && b < K && margin > 2.0 * E;
     const int bsel = sure ? b : 0;
     double acc = 0.0;
-    for (int c0 = 0; c0 < D; c0 += 16) {
-        if constexpr (sizeof(T) == 4) {  // 16-byte pieces: 8 rows x 64 bytes per load instruction
+    if constexpr (sizeof(T) == 4) {
+        // software pipeline: the global loads of chunk c + 1 (point pieces from HBM, centroid pieces from L2) are in flight while
+        // chunk c is walked out of shared memory
+        float4 xv[4];
+        double2 cv[8];
+        int brow[8];
+#pragma unroll
+        for (int it = 0; it < 8; it++) brow[it] = __shfl_sync(0xffffffffu, bsel, it * 4 + (lane >> 3));
+        auto fetch = [&](int c0) {
+#pragma unroll
+            for (int it = 0; it < 4; it++) {   // 16-byte pieces: 8 rows x 64 bytes per load instruction
+                const int64_t src = row0 + it * 8 + (lane >> 2);
+                const int piece = (lane & 3) * 4;
+                xv[it] = (src < N && c0 + piece < ld) ? *reinterpret_cast<const float4*>(x + src * ld + c0 + piece) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int it = 0; it < 8; it++) {   // 8 lanes read the 128 contiguous bytes of one row's centroid (ld is a multiple of 4, padding = 0)
+                const int piece = (lane & 7) * 2;
+                cv[it] = (c0 + piece < ld) ? *reinterpret_cast<const double2*>(cent + (size_t)brow[it] * ld + c0 + piece) : make_double2(0.0, 0.0);
+            }
+        };
+        fetch(0);
+        for (int c0 = 0; c0 < D; c0 += 16) {
 #pragma unroll
             for (int it = 0; it < 4; it++) {
-                int r = it * 8 + (lane >> 2);
-                int piece = (lane & 3) * 4;
-                int64_t src = row0 + r;
-                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (src < N && c0 + piece < ld) v = *reinterpret_cast<const float4*>(x + src * ld + c0 + piece);
-                tiles[warp][r][piece] = (double)v.x; tiles[warp][r][piece + 1] = (double)v.y;
-                tiles[warp][r][piece + 2] = (double)v.z; tiles[warp][r][piece + 3] = (double)v.w;
+                const int r = it * 8 + (lane >> 2), piece = (lane & 3) * 4;
+                tiles[warp][r][piece] = (double)xv[it].x; tiles[warp][r][piece + 1] = (double)xv[it].y;
+                tiles[warp][r][piece + 2] = (double)xv[it].z; tiles[warp][r][piece + 3] = (double)xv[it].w;
             }
-        } else {
-#pragma unroll 4
-            for (int it = 0; it < 16; it++) {
-                int r = it * 2 + (lane >> 4);
-                int64_t src = row0 + r;
-                int col = c0 + (lane & 15);
-                tiles[warp][r][lane & 15] = (src < N && col < D) ? (double)x[src * ld + col] : 0.0;
+#pragma unroll
+            for (int it = 0; it < 8; it++) {
+                const int r = it * 4 + (lane >> 3), piece = (lane & 7) * 2;
+                ctiles[warp][r][piece] = cv[it].x;
+                ctiles[warp][r][piece + 1] = cv[it].y;
             }
+            __syncwarp();
+            if (c0 + 16 < D) fetch(c0 + 16);
+            const int lim = min(16, D - c0);
+#pragma unroll
+            for (int k = 0; k < 16; k++) {
+                if (k < lim) {
+                    double t = __dsub_rn(tiles[warp][lane][k], ctiles[warp][lane][k]);
+                    acc = __dadd_rn(acc, __dmul_rn(t, t));
+                }
+            }
+            __syncwarp();
         }
-        // centroid pieces are fetched cooperatively: 8 lanes read the 128 contiguous bytes of one row's centroid (4 full
-        // sectors per row instead of a 32-sector request per lane-private 16-byte load: the L1 was the limiter)
+    } else {
+    for (int c0 = 0; c0 < D; c0 += 16) {
+#pragma unroll 4
+        for (int it = 0; it < 16; it++) {
+            int r = it * 2 + (lane >> 4);
+            int64_t src = row0 + r;
+            int col = c0 + (lane & 15);
+            tiles[warp][r][lane & 15] = (src < N && col < D) ? (double)x[src * ld + col] : 0.0;
+        }
 #pragma unroll
         for (int it = 0; it < 8; it++) {  // ld is a multiple of 4 and the padding holds zeros
             int r = it * 4 + (lane >> 3);
@@ -346,6 +379,7 @@ lloyd_refine_kernel(const T* __restrict__ x, int ld, int D, const double* __rest
             }
         }
         __syncwarp();
+    }
     }
     if (sure) {
         labels[i] = b;
@@ -368,7 +402,8 @@ __global__ void lloyd_label_kernel(const double* __restrict__ sqn, int64_t row_b
     double E = scale * (6e-6 * xn * cmax + 2.5e-7 * (0.5 * cmax * cmax + xn * cmax));
     int b = bidx[i];
     double margin = (double)second[i] - (double)best[i];
-    if (b >= 0 && b < K && margin > 2.0 * E) labels[i] = b;
+    const bool sure = b >= 0 && b < K && margin > 2.0 * E;
+    if (sure) labels[i] = b;
     else amb_rows[atomicAdd(amb_count, 1)] = (int32_t)i;
 }
 
