@@ -843,6 +843,7 @@ static int pass2_run(crx_ctx* c, const P2Host& h, P2QueueBuf* qa, P2QueueBuf* qb
     CRX_CUDA(cudaMemcpyAsync(&n, cur->count.p, sizeof(n), cudaMemcpyDeviceToHost, c->stream));
     CRX_CUDA(cudaStreamSynchronize(c->stream));
     static const bool p2_debug = getenv("CRX_P2_DEBUG") != nullptr;
+    static const bool long_off = getenv("CRX_P2_LONG") != nullptr && getenv("CRX_P2_LONG")[0] == '0';   // A/B: every list on one warp
     // rows whose coordinates are all equal (single-coin users): their mutual similarities have a closed form (p2_exact_kernel)
     DevBuf<double> uval_b, uval_q;
     if (n > 0) {
@@ -939,10 +940,10 @@ static int pass2_run(crx_ctx* c, const P2Host& h, P2QueueBuf* qa, P2QueueBuf* qb
     }
     static const int max_rounds = getenv("CRX_P2_ROUNDS") ? atoi(getenv("CRX_P2_ROUNDS")) : 16;
     DevBuf<unsigned long long> dbg;
-    if (p2_debug) { CRX_TRY(dbg.alloc(c, 4)); }
+    if (p2_debug) { CRX_TRY(dbg.alloc(c, 8)); }
     for (int round = 0; n > 0 && round < max_rounds; round++) {
         CRX_CUDA(cudaMemsetAsync(nxt->count.p, 0, sizeof(unsigned int), c->stream));
-        if (p2_debug) CRX_CUDA(cudaMemsetAsync(dbg.p, 0, 4 * sizeof(unsigned long long), c->stream));
+        if (p2_debug) CRX_CUDA(cudaMemsetAsync(dbg.p, 0, 8 * sizeof(unsigned long long), c->stream));
         size_t free_b = 0, total_b = 0;
         CRX_CUDA(cudaMemGetInfo(&free_b, &total_b));
         // budget for the collected lists: one third for the pass masks of the threshold scan (32 B per row and column tile), the
@@ -1047,9 +1048,16 @@ static int pass2_run(crx_ctx* c, const P2Host& h, P2QueueBuf* qa, P2QueueBuf* qb
             a.eps = h.eps; a.blocks = h.blocks;
             a.recs = h.recs; a.nbr_rows = h.rows; a.nbr_sims = h.sims; a.qstatus = h.status; a.counters = c->counters;
             a.dbg = p2_debug ? dbg.p : nullptr;
+            a.long_min = long_off ? 0x7fffffff : P2_LONG_MIN;
             if (base->x64) p2_resolve_kernel<double><<<crx_grid(ns, 4), 128, 0, c->stream>>>(base->x64, a);
             else p2_resolve_kernel<float><<<crx_grid(ns, 4), 128, 0, c->stream>>>(base->x32, a);
             CRX_CUDA(cudaGetLastError());
+            if (!long_off) {
+                CRX_KERNEL(c, "p2_resolve_long");
+                if (base->x64) p2_resolve_long_kernel<double><<<ns, 256, 0, c->stream>>>(base->x64, a);
+                else p2_resolve_long_kernel<float><<<ns, 256, 0, c->stream>>>(base->x32, a);
+                CRX_CUDA(cudaGetLastError());
+            }
         }
         }   // slices
         std::swap(cur, nxt);
@@ -1057,10 +1065,11 @@ static int pass2_run(crx_ctx* c, const P2Host& h, P2QueueBuf* qa, P2QueueBuf* qb
         CRX_CUDA(cudaMemcpyAsync(&n, cur->count.p, sizeof(n), cudaMemcpyDeviceToHost, c->stream));
         CRX_CUDA(cudaStreamSynchronize(c->stream));
         if (p2_debug) {
-            unsigned long long hd[4];
+            unsigned long long hd[8];
             CRX_CUDA(cudaMemcpy(hd, dbg.p, sizeof(hd), cudaMemcpyDeviceToHost));
-            fprintf(stderr, "[crx pass2] round %d: %u queued (slices of %u), %lld collected (%.1f per query), %u left; resolved %llu: sum |R| = %llu, their lists = %llu\n",
-                    round, n_in, slice, (long long)collected, (double)collected / n_in, n, hd[2], hd[0], hd[1]);
+            fprintf(stderr, "[crx pass2] round %d: %u queued (slices of %u), %lld collected (%.1f per query), %u left; tie-order: %llu resolved (%llu by H alone), sum |R| = %llu, "
+                            "lists = %llu; plateau: %llu resolved (%llu by H alone), sum |R| = %llu, lists = %llu\n",
+                    round, n_in, slice, (long long)collected, (double)collected / n_in, n, hd[2], hd[3], hd[0], hd[1], hd[6], hd[7], hd[4], hd[5]);
         }
     }
     if (n > 0) {
