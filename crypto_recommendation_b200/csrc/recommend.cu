@@ -843,7 +843,6 @@ static int pass2_run(crx_ctx* c, const P2Host& h, P2QueueBuf* qa, P2QueueBuf* qb
     CRX_CUDA(cudaMemcpyAsync(&n, cur->count.p, sizeof(n), cudaMemcpyDeviceToHost, c->stream));
     CRX_CUDA(cudaStreamSynchronize(c->stream));
     static const bool p2_debug = getenv("CRX_P2_DEBUG") != nullptr;
-    static const bool long_off = getenv("CRX_P2_LONG") != nullptr && getenv("CRX_P2_LONG")[0] == '0';   // A/B: every list on one warp
     // rows whose coordinates are all equal (single-coin users): their mutual similarities have a closed form (p2_exact_kernel)
     DevBuf<double> uval_b, uval_q;
     if (n > 0) {
@@ -1048,16 +1047,9 @@ static int pass2_run(crx_ctx* c, const P2Host& h, P2QueueBuf* qa, P2QueueBuf* qb
             a.eps = h.eps; a.blocks = h.blocks;
             a.recs = h.recs; a.nbr_rows = h.rows; a.nbr_sims = h.sims; a.qstatus = h.status; a.counters = c->counters;
             a.dbg = p2_debug ? dbg.p : nullptr;
-            a.long_min = long_off ? 0x7fffffff : P2_LONG_MIN;
             if (base->x64) p2_resolve_kernel<double><<<crx_grid(ns, 4), 128, 0, c->stream>>>(base->x64, a);
             else p2_resolve_kernel<float><<<crx_grid(ns, 4), 128, 0, c->stream>>>(base->x32, a);
             CRX_CUDA(cudaGetLastError());
-            if (!long_off) {
-                CRX_KERNEL(c, "p2_resolve_long");
-                if (base->x64) p2_resolve_long_kernel<double><<<ns, 256, 0, c->stream>>>(base->x64, a);
-                else p2_resolve_long_kernel<float><<<ns, 256, 0, c->stream>>>(base->x32, a);
-                CRX_CUDA(cudaGetLastError());
-            }
         }
         }   // slices
         std::swap(cur, nxt);

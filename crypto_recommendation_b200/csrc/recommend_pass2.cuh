@@ -533,7 +533,6 @@ struct P2Resolve {
     P2Blocks blocks;
     int32_t* recs; int32_t* nbr_rows; double* nbr_sims; int32_t* qstatus;
     unsigned long long* counters;
-    int long_min;              // lists longer than this are resolved by a whole block (p2_resolve_long_kernel)
     unsigned long long* dbg;   // nullable, per kind (tie-order at [0], plateau at [4]): sum of |R|, sum of the list lengths, resolved, of which "H alone decides"
 };
 
@@ -562,7 +561,6 @@ p2_resolve_kernel(const TB* __restrict__ xb, P2Resolve a) {
         return;
     }
     const int cnt = a.count[i];
-    if (cnt > a.long_min) return;   // long lists: one block per query (p2_resolve_long_kernel)
     double* key = a.xs + a.off[i];
     int* val = a.cols + a.off[i];
     const int nc = a.ncand[qrel];
@@ -698,253 +696,6 @@ p2_resolve_kernel(const TB* __restrict__ xb, P2Resolve a) {
         predict_and_recommend<TB>(xb, a.ldb, a.mean_b, a.unk_q + qrow * a.D, a.mean_q[qrow], a.D, s_idx[warp], s_sim[warp], keep, a.Nrec,
                                   s_pred[warp], s_coin[warp], a.recs + (size_t)qrel * a.Nrec);
     }
-}
-
-// ------------------------------------------------------------------------------------------------
-// The same resolution for LONG lists (a threshold far down the ranking: tens of thousands to a million collected candidates),
-// one block of 256 threads per query: every pass of p2_resolve_kernel over the whole list -- the P-th best, e*, the tail, the
-// compaction of R, and the partitions of the quicksort while they merely drop what is below the pivot (p + 1 >= need: only the
-// ">=" side is consumed, a stable compaction) -- is a block-wide reduction / compaction; the remaining short range goes to
-// warp_qs_topn_big on warp 0.  The decisions are those of p2_resolve_kernel, line for line.
-// ------------------------------------------------------------------------------------------------
-constexpr int P2_LONG_MIN = 8192;     // shorter lists stay with the warp-per-query kernel
-constexpr int P2_LONG_SMALL = 4096;   // range at which warp 0 takes over the quicksort
-
-template <typename TB>
-__global__ void __launch_bounds__(256)
-p2_resolve_long_kernel(const TB* __restrict__ xb, P2Resolve a) {
-    __shared__ double sm_top[8][32];
-    __shared__ int red_i[8];
-    __shared__ double red_d[8];
-    __shared__ int bc_i[4];
-    __shared__ double bc_d[2];
-    __shared__ int posge[128];
-    __shared__ double hk[128];
-    __shared__ int hv[128];
-    __shared__ int s_idx[32];
-    __shared__ double s_sim[32];
-    __shared__ double s_pred[128];
-    __shared__ int s_coin[128];
-    const unsigned int i = blockIdx.x;
-    if (i >= a.n) return;
-    if (a.ovf && a.ovf[i]) return;    // re-queued by p2_resolve_kernel
-    const int cnt = a.count[i];
-    if (cnt <= a.long_min) return;
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const unsigned lt = (1u << lane) - 1u;
-    const int qrel = a.cur.q[i];
-    const double theta = a.cur.theta[i];
-    const int colx = a.cur.colx[i];
-    const int tries = a.cur.tries[i];
-    const double eps = a.eps;
-    double* key = a.xs + a.off[i];
-    int* val = a.cols + a.off[i];
-    const int nc = a.ncand[qrel];
-    const int keep = min(a.P, nc);
-    const bool complete = cnt >= nc;
-    const double kappa = theta + 1.05 * eps;
-    const double lower = ldexp(64.0 * eps, 2 * min(tries & 0xffff, 8));
-    // ---- block reductions
-    auto block_max_i = [&](int v) -> int {
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) v = max(v, __shfl_xor_sync(0xffffffffu, v, o));
-        __syncthreads();
-        if (lane == 0) red_i[warp] = v;
-        __syncthreads();
-        int r = red_i[0];
-#pragma unroll
-        for (int w = 1; w < 8; w++) r = max(r, red_i[w]);
-        return r;
-    };
-    auto block_sum_i = [&](int v) -> int {
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-        __syncthreads();
-        if (lane == 0) red_i[warp] = v;
-        __syncthreads();
-        int r = 0;
-#pragma unroll
-        for (int w = 0; w < 8; w++) r += red_i[w];
-        return r;
-    };
-    // stable in-place compaction of the entries e < limit with key >= thr (everything when thr == -inf) to the front
-    auto compact = [&](int limit, double thr) -> int {
-        int m = 0;
-        for (int base = 0; base < limit; base += 1024) {
-            const int e0 = base + tid * 4;
-            double k4[4];
-            int v4[4];
-            bool g4[4];
-            int c = 0;
-#pragma unroll
-            for (int u = 0; u < 4; u++) {
-                const int e = e0 + u;
-                k4[u] = e < limit ? key[e] : 0.0;
-                g4[u] = e < limit && (k4[u] >= thr || thr == -INFINITY);
-                c += g4[u];
-            }
-#pragma unroll
-            for (int u = 0; u < 4; u++) v4[u] = g4[u] ? val[e0 + u] : 0;
-            int incl = c;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
-            __syncthreads();   // every element of the chunk sits in registers; red_i is free
-            if (lane == 31) red_i[warp] = incl;
-            __syncthreads();
-            int before = incl - c, total = 0;
-#pragma unroll
-            for (int w = 0; w < 8; w++) { if (w < warp) before += red_i[w]; total += red_i[w]; }
-            int dst = m + before;
-#pragma unroll
-            for (int u = 0; u < 4; u++)
-                if (g4[u]) { if (dst != e0 + u) { key[dst] = k4[u]; val[dst] = v4[u]; } dst++; }
-            m += total;
-        }
-        __syncthreads();
-        return m;
-    };
-    // ---- T_P: every warp keeps the best `keep` of its share, warp 0 merges
-    double mine = -INFINITY, thr = -INFINITY;
-    int filled = 0;
-    auto offer = [&](double k, bool in) {
-        unsigned want = __ballot_sync(0xffffffffu, in && k == k && (k > thr || filled < keep));
-        while (want) {
-            const int src = __ffs(want) - 1;
-            want &= want - 1;
-            const double x = __shfl_sync(0xffffffffu, k, src);
-            if (x > thr || filled < keep) {
-                const int pos = __popc(__ballot_sync(0xffffffffu, mine >= x));
-                const double up = __shfl_up_sync(0xffffffffu, mine, 1);
-                mine = lane < pos ? mine : (lane == pos ? x : up);
-                if (filled < keep) filled++;
-                thr = filled < keep ? -INFINITY : __shfl_sync(0xffffffffu, mine, keep - 1);
-            }
-        }
-    };
-    for (int base = warp * 128; base < cnt; base += 8 * 128) {
-        double k4[4];
-#pragma unroll
-        for (int u = 0; u < 4; u++) { const int e = base + u * 32 + lane; k4[u] = e < cnt ? key[e] : -INFINITY; }
-#pragma unroll
-        for (int u = 0; u < 4; u++) offer(k4[u], base + u * 32 + lane < cnt);
-    }
-    sm_top[warp][lane] = lane < filled ? mine : -INFINITY;
-    __syncthreads();
-    if (warp == 0) {
-        for (int w = 1; w < 8; w++) {
-            const double x = sm_top[w][lane];
-            offer(x, lane < keep && x > -INFINITY);
-        }
-        const double tpw = __shfl_sync(0xffffffffu, mine, keep - 1);
-        if (lane == 0) { bc_d[0] = tpw; bc_i[0] = filled; }
-    }
-    __syncthreads();
-    const double TP = bc_d[0];
-    if (bc_i[0] < keep) {   // fewer than `keep` comparable similarities (NaN rows): as cnt < keep
-        if (tid == 0) p2_emit(a.next, qrel, (tries & 0xffff) > 8 ? -INFINITY : theta - lower, colx, tries + 1);
-        return;
-    }
-    if (!(TP > kappa) && !complete) {
-        if (tid == 0) p2_emit(a.next, qrel, fmin(theta - lower, TP - 2.1 * eps), colx, tries + 1);
-        return;
-    }
-    // ---- e* = the last entry with key >= T_P
-    int loc = -1;
-    for (int e = tid; e < cnt; e += 256) if (key[e] >= TP) loc = e;
-    const int idx_e = block_max_i(loc);
-    const int estar = val[idx_e];
-    const double s_estar = key[idx_e];
-    // ---- the tail behind e*
-    const bool tail_all = complete || estar >= colx;
-    double tk = -INFINITY;
-    int te = 0x7fffffff;
-    if (s_estar != TP) {
-        for (int e = idx_e + 1 + tid; e < cnt; e += 256) {
-            const double k = key[e];
-            if ((tail_all || k > kappa) && k > tk) { tk = k; te = e; }
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            const double ok = __shfl_xor_sync(0xffffffffu, tk, o);
-            const int oe = __shfl_xor_sync(0xffffffffu, te, o);
-            if (ok > tk || (ok == tk && oe < te)) { tk = ok; te = oe; }
-        }
-        __syncthreads();
-        if (lane == 0) { red_d[warp] = tk; red_i[warp] = te; }
-        __syncthreads();
-        tk = red_d[0]; te = red_i[0];
-#pragma unroll
-        for (int w = 1; w < 8; w++) if (red_d[w] > tk || (red_d[w] == tk && red_i[w] < te)) { tk = red_d[w]; te = red_i[w]; }
-    }
-    const bool found = te != 0x7fffffff;
-    double tp;
-    int rlim;
-    if (s_estar == TP) {
-        tp = TP; rlim = idx_e + 1;
-    } else if (!(tail_all || found)) {
-        if (tid == 0) {
-            int cx;
-            double th = p2_tail_theta(a.blocks, qrel, estar, TP, eps, theta, cx);
-            p2_emit(a.next, qrel, th, cx, tries + 1);
-        }
-        return;
-    } else if (!found) {
-        if (!complete) { if (tid == 0) p2_emit(a.next, qrel, -INFINITY, 0x7fffffff, tries + 1); return; }
-        tp = -INFINITY; rlim = cnt;
-    } else {
-        tp = tk; rlim = te;
-        if (!(tp > kappa) && !complete) {
-            if (tid == 0) p2_emit(a.next, qrel, tp - 2.1 * eps, 0x7fffffff, tries + 1);
-            return;
-        }
-    }
-    // ---- R to the front, then the partitions that only drop what is below their pivot
-    const int m = compact(rlim, tp);
-    if (a.dbg && tid == 0) {
-        const int kd = (tries >> P2_KIND_SHIFT) == CRX_Q_PLATEAU ? 4 : 0;
-        atomicAdd(&a.dbg[kd + 0], (unsigned long long)m); atomicAdd(&a.dbg[kd + 1], (unsigned long long)cnt); atomicAdd(&a.dbg[kd + 2], 1ull);
-        if (s_estar == TP) atomicAdd(&a.dbg[kd + 3], 1ull);
-    }
-    int hi = m - 1;
-    bool done_all = false;
-    while (hi + 1 > P2_LONG_SMALL) {
-        const double pivot = key[hi];
-        const int pv = val[hi];
-        int cge = 0, lgt = -1, neq = 0;
-        for (int e = tid; e < hi; e += 256) {
-            const double k = key[e];
-            cge += k >= pivot;
-            if (k > pivot) lgt = e;
-            neq += !(k == pivot);
-        }
-        const int cnt_ge = block_sum_i(cge);
-        const int lastgt = block_max_i(lgt);
-        const int noteq = block_sum_i(neq);
-        if (noteq == 0) { done_all = true; break; }          // a range of equal keys is left as it is
-        if (cnt_ge == hi) { hi = lastgt; continue; }         // the pivot and its equals behind the last larger element stay
-        const int p = cnt_ge;
-        if (p + 1 < keep) break;                             // the "<" side reaches into the consumed prefix: literal step (warp 0)
-        compact(hi, pivot);
-        if (tid == 0) { key[p] = pivot; val[p] = pv; }
-        __syncthreads();
-        hi = p - 1;
-    }
-    if (warp != 0) return;
-    if (!done_all && hi >= 1) warp_qs_topn_big(key, val, hi + 1, keep, posge, hk, hv);
-    if (lane < keep) { s_idx[lane] = val[lane]; s_sim[lane] = key[lane]; }
-    __syncwarp();
-    if (lane == 0) {
-        atomicAdd(&a.counters[CRX_CNT_TOPP_PASS2], 1ull);
-        if (a.qstatus) a.qstatus[qrel] = CRX_Q_EXACT;
-    }
-    if (a.nbr_rows) for (int j = lane; j < a.P; j += 32) a.nbr_rows[(size_t)qrel * a.P + j] = j < keep ? s_idx[j] : -1;
-    if (a.nbr_sims) for (int j = lane; j < a.P; j += 32) a.nbr_sims[(size_t)qrel * a.P + j] = j < keep ? s_sim[j] : 0.0;
-    if (a.recs) {
-        const int64_t qrow = a.q_begin + qrel;
-        predict_and_recommend<TB>(xb, a.ldb, a.mean_b, a.unk_q + qrow * a.D, a.mean_q[qrow], a.D, s_idx, s_sim, keep, a.Nrec, s_pred, s_coin,
-                                  a.recs + (size_t)qrel * a.Nrec);
-    }
-    (void)lt;
 }
 
 // ------------------------------------------------------------------------------------------------

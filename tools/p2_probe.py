@@ -19,7 +19,7 @@ capi.recommend_lsh(ctx, t, 20, 5)
 wall = time.perf_counter() - t0
 names = ["tc_topp_scan", "rec_finalize", "tc_prep", "subset_hist", "uniform_rows", "p2u_flag", "p2u_gather", "p2u_select", "p2u_sort", "p2u_compact",
          "p2_prepare", "tc_gather", "tc_collect_scan", "p2_all_count", "p2_sizes", "p2_trim", "p2_expand", "p2_fill_all",
-         "p2_exact", "p2_resolve", "p2_collect_simt", "p2_leftover"]
+         "p2_exact", "p2_resolve", "p2_collect_simt", "p2_leftover", ""]
 print("wall %.1f ms" % (wall * 1e3))
 for k in names:
     ms, cnt = ctx.kernel_time(k)
