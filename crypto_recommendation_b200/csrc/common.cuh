@@ -8,6 +8,7 @@
 #include <cstdio>
 #include <cstring>
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 #include "../../include/crx.h"
@@ -64,7 +65,49 @@ struct crx_ctx {
     std::vector<crx_prof_rec> prof;
     std::vector<cudaEvent_t> free_events;
     unsigned long long* counters = nullptr;  // device, 8 slots
+    // Large temporaries (>= CRX_BIG_BYTES: pass masks, collected lists, operands) are kept by the context between calls: the
+    // stream-ordered pool splits a freed 20 GB block for the next call's smaller buffers and then has to map fresh memory for
+    // the next 20 GB request -- hundreds of milliseconds, at random.  All work of a context is ordered on its one stream, so a
+    // block handed back here can be handed out again at once.  crx_ctx_trim / crx_ctx_destroy return them to the driver.
+    std::vector<std::pair<void*, size_t>> big_free;       // (block, capacity)
+    std::unordered_map<void*, size_t> big_live;           // blocks handed out -> capacity
 };
+constexpr size_t CRX_BIG_BYTES = (size_t)64 << 20;
+// nullptr when the request is small (the caller uses the pool) or no memory is left
+static inline void* crx_big_take(crx_ctx* c, size_t bytes, cudaError_t* err) {
+    *err = cudaSuccess;
+    if (bytes < CRX_BIG_BYTES) return nullptr;
+    size_t best = (size_t)-1, cap = 0;
+    for (size_t i = 0; i < c->big_free.size(); i++) {
+        const size_t b = c->big_free[i].second;
+        if (b >= bytes && b <= bytes + bytes / 2 + CRX_BIG_BYTES && (best == (size_t)-1 || b < cap)) { best = i; cap = b; }
+    }
+    void* p = nullptr;
+    if (best != (size_t)-1) {
+        p = c->big_free[best].first;
+        c->big_free.erase(c->big_free.begin() + best);
+    } else {
+        *err = cudaMallocAsync(&p, bytes, c->stream);
+        if (*err != cudaSuccess) {   // give the cached blocks back and try once more
+            for (auto& b : c->big_free) cudaFreeAsync(b.first, c->stream);
+            c->big_free.clear();
+            cudaGetLastError();
+            *err = cudaMallocAsync(&p, bytes, c->stream);
+            if (*err != cudaSuccess) return nullptr;
+        }
+        cap = bytes;
+    }
+    c->big_live[p] = cap;
+    return p;
+}
+// true when p was a cached block (now back in the cache)
+static inline bool crx_big_give(crx_ctx* c, void* p) {
+    auto it = c->big_live.find(p);
+    if (it == c->big_live.end()) return false;
+    c->big_free.emplace_back(p, it->second);
+    c->big_live.erase(it);
+    return true;
+}
 
 struct crx_points {
     crx_ctx* ctx = nullptr;
@@ -115,6 +158,7 @@ template <typename T>
 struct DevBuf {
     T* p = nullptr;
     cudaStream_t s = nullptr;
+    crx_ctx* ctx = nullptr;
     size_t count = 0;
     DevBuf() {}
     DevBuf(const DevBuf&) = delete;
@@ -122,9 +166,12 @@ struct DevBuf {
     int alloc(crx_ctx* c, size_t n) {
         release();
         s = c->stream;
+        ctx = c;
         count = n;
         if (n == 0) n = 1;
-        cudaError_t e = cudaMallocAsync((void**)&p, n * sizeof(T), s);
+        cudaError_t e = cudaSuccess;
+        p = (T*)crx_big_take(c, n * sizeof(T), &e);
+        if (!p && e == cudaSuccess) e = cudaMallocAsync((void**)&p, n * sizeof(T), s);
         if (e != cudaSuccess) {
             crx_set_error("cudaMallocAsync(%zu bytes) -> %s", n * sizeof(T), cudaGetErrorString(e));
             p = nullptr;
@@ -133,7 +180,7 @@ struct DevBuf {
         return CRX_OK;
     }
     void release() {
-        if (p) cudaFreeAsync(p, s);
+        if (p && !(ctx && crx_big_give(ctx, p))) cudaFreeAsync(p, s);
         p = nullptr;
     }
     ~DevBuf() { release(); }
@@ -171,7 +218,10 @@ struct IoBuf {
 // so rebuilding tables / points every step does not go back to the driver)
 template <typename T>
 static inline int crx_alloc(crx_ctx* c, T** p, size_t count) {
-    cudaError_t e = cudaMallocAsync((void**)p, (count ? count : 1) * sizeof(T), c->stream);
+    cudaError_t e = cudaSuccess;
+    *p = (T*)crx_big_take(c, (count ? count : 1) * sizeof(T), &e);
+    if (*p) return CRX_OK;
+    if (e == cudaSuccess) e = cudaMallocAsync((void**)p, (count ? count : 1) * sizeof(T), c->stream);
     if (e != cudaSuccess) {
         crx_set_error("cudaMallocAsync(%zu bytes) -> %s", count * sizeof(T), cudaGetErrorString(e));
         *p = nullptr;
@@ -180,7 +230,7 @@ static inline int crx_alloc(crx_ctx* c, T** p, size_t count) {
     return CRX_OK;
 }
 static inline void crx_free(crx_ctx* c, void* p) {
-    if (p) cudaFreeAsync(p, c->stream);
+    if (p && !crx_big_give(c, p)) cudaFreeAsync(p, c->stream);
 }
 
 static inline int crx_grid(int64_t work, int block) { return (int)((work + block - 1) / block); }

@@ -124,6 +124,8 @@ int crx_ctx_create(int device, void* cuda_stream, crx_ctx** out) {
 int crx_ctx_destroy(crx_ctx* c) {
     if (!c) return CRX_OK;
     cudaSetDevice(c->device);
+    for (auto& b : c->big_free) cudaFreeAsync(b.first, c->stream);
+    c->big_free.clear();
     cudaStreamSynchronize(c->stream);
     for (auto& r : c->prof) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
     for (auto e : c->free_events) cudaEventDestroy(e);
@@ -144,6 +146,8 @@ int64_t crx_ctx_launch_count(const crx_ctx* c) { return c ? c->launches : 0; }
 int crx_ctx_trim(crx_ctx* c) {
     CRX_REQUIRE(c, "ctx is NULL");
     CRX_CUDA(cudaSetDevice(c->device));
+    for (auto& b : c->big_free) cudaFreeAsync(b.first, c->stream);   // the context's cache of large temporaries
+    c->big_free.clear();
     CRX_CUDA(cudaStreamSynchronize(c->stream));
     cudaMemPool_t pool;
     CRX_CUDA(cudaDeviceGetDefaultMemPool(&pool, c->device));
@@ -214,7 +218,9 @@ int crx_points_create(crx_ctx* c, const void* data, int dtype, int64_t n, int32_
     const void* src = data;
     void* staged = nullptr;
     if (mem == CRX_HOST) {
-        CRX_CUDA(cudaMallocAsync(&staged, (size_t)n * d * esz, c->stream));
+        char* st8 = nullptr;
+        CRX_TRY(crx_alloc(c, &st8, (size_t)n * d * esz));   // through the context's cache of large blocks: an upload per step reuses it
+        staged = st8;
         CRX_CUDA(cudaMemcpyAsync(staged, data, (size_t)n * d * esz, cudaMemcpyHostToDevice, c->stream));
         src = staged;
     }
@@ -231,7 +237,7 @@ int crx_points_create(crx_ctx* c, const void* data, int dtype, int64_t n, int32_
         else row_sqnorm_kernel<float><<<g, 256, 0, c->stream>>>(p->x32, n, d, p->ld, p->sqn);
     }
     CRX_CUDA(cudaGetLastError());
-    if (staged) CRX_CUDA(cudaFreeAsync(staged, c->stream));
+    if (staged) crx_free(c, staged);
     if (mem == CRX_HOST) CRX_CUDA(cudaStreamSynchronize(c->stream));  // caller may reuse its buffer
     *out = p;
     return CRX_OK;

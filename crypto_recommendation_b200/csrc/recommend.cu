@@ -5,6 +5,7 @@
 //   cluster-neighbour recommendation (get_top_N_recom without similarities).
 #include <algorithm>
 #include <climits>
+#include <ctime>
 
 #include <cub/cub.cuh>
 
@@ -266,9 +267,9 @@ rec_finalize_kernel(const TQ* __restrict__ xq, int ldq, const double* __restrict
                     const double* __restrict__ mean_q, const TB* __restrict__ xb, int ldb, const double* __restrict__ sqn_b,
                     const double* __restrict__ mean_b, int D, int64_t q_begin, int64_t nq, int P, int Nrec,
                     const TS* __restrict__ list_s, const int32_t* __restrict__ list_i, const int32_t* __restrict__ ncand,
-                    double approx_scale, double approx_eps, int32_t* __restrict__ recs, int32_t* __restrict__ nbr_rows,
+                    double approx_scale, double approx_eps_all, int32_t* __restrict__ recs, int32_t* __restrict__ nbr_rows,
                     double* __restrict__ nbr_sims, unsigned long long* counters, int tie_order, int32_t* __restrict__ qstatus,
-                    int pass2, P2Queue w2, P2Blocks blk) {
+                    int pass2, P2Queue w2, P2Blocks blk, const double* __restrict__ eps_q /* per query row, or NULL */) {
     constexpr int EPL = LISTN / 32;  // list entries per lane
     constexpr int QW = 4;            // queries (warps) per block
     __shared__ int a_idx[QW][LISTN];
@@ -283,6 +284,7 @@ rec_finalize_kernel(const TQ* __restrict__ xq, int ldq, const double* __restrict
     int64_t qrel = (int64_t)blockIdx.x * QW + warp;
     if (qrel >= nq) return;
     int64_t qrow = q_begin + qrel;
+    const double approx_eps = eps_q ? eps_q[qrow] : approx_eps_all;   // the filter's error bound for this query (centred operands: per row)
     // every 32-slot group of the list is an independent "best 32 of its share of the columns" list
     // (the FP64 scan has one, the tensor-core filter one per column half): a candidate outside the lists
     // scores at most max over FULL groups of (smallest approximate score of the group)
@@ -330,14 +332,18 @@ rec_finalize_kernel(const TQ* __restrict__ xq, int ldq, const double* __restrict
             walked = count;
             one_walk = true;
             unsigned lt = (1u << lane) - 1u;
-            if (k0) a_idx[warp][__popc(b0 & lt)] = idx_e[0];
-            if (k1) a_idx[warp][__popc(b0) + __popc(b1 & lt)] = idx_e[EPL - 1];
+            if (k0) { a_idx[warp][__popc(b0 & lt)] = idx_e[0]; s_pred[warp][__popc(b0 & lt)] = val_e[0]; }
+            if (k1) { a_idx[warp][__popc(b0) + __popc(b1 & lt)] = idx_e[EPL - 1]; s_pred[warp][__popc(b0) + __popc(b1 & lt)] = val_e[EPL - 1]; }
             __syncwarp();
             int mine = lane < count ? a_idx[warp][lane] : -1;
+            const double mine_ap = lane < count ? s_pred[warp][lane] : 0.0;
             __syncwarp();
             rw::Walk w = rw::walk_rows<TB, CRX_COSINE>(xb, ldb, D, mine >= 0 ? (int64_t)mine : -1, qvec[warp], tiles[warp]);
             double mysim = -INFINITY;
             if (mine >= 0) { X87 ip = {w.a, w.b}; mysim = cos_sim_x87(ip, sqn_b[mine], nq_); }
+            // the error bound everything above rests on, checked on every evaluated candidate: a violation is counted as an
+            // uncertified query (the tests require the counter to stay 0)
+            if (mine >= 0 && fabs(mine_ap * approx_scale - mysim) > approx_eps) atomicAdd(&counters[CRX_CNT_TOPP_RESCAN], 1ull);
             a_idx[warp][lane] = mine; a_sim[warp][lane] = mysim;
             a_idx[warp][32 + lane] = -1; a_sim[warp][32 + lane] = -INFINITY;
         }
@@ -353,6 +359,7 @@ rec_finalize_kernel(const TQ* __restrict__ xq, int ldq, const double* __restrict
             if (__ballot_sync(0xffffffffu, idx >= 0)) {
                 rw::Walk w = rw::walk_rows<TB, CRX_COSINE>(xb, ldb, D, idx >= 0 ? (int64_t)idx : -1, qvec[warp], tiles[warp]);
                 if (idx >= 0) { X87 ip = {w.a, w.b}; mysim = cos_sim_x87(ip, sqn_b[idx], nq_); }
+                if (idx >= 0 && fabs(val_e[e] * approx_scale - mysim) > approx_eps) atomicAdd(&counters[CRX_CNT_TOPP_RESCAN], 1ull);
             }
             a_idx[warp][slot] = idx;
             a_sim[warp][slot] = mysim;
@@ -532,13 +539,31 @@ rec_finalize_kernel(const TQ* __restrict__ xq, int ldq, const double* __restrict
                     __syncwarp();
                 } else {
                     status = CRX_Q_TIE_ORDER;   // kept: descending similarity, ties by row (second pass: the tail behind e*)
-                    if (lane == 0) {
-                        if (pass2) {
-                            int cx;
-                            double th = p2_tail_theta(blk, qrel, estar, pth, approx_eps, INFINITY, cx);
-                            p2_emit(w2, (int)qrel, th, cx, CRX_Q_TIE_ORDER << P2_KIND_SHIFT);
-                        } else atomicAdd(&counters[CRX_CNT_TOPP_TIES], 1ull);
-                    }
+                    if (pass2) {
+                        int cx;
+                        double th = p2_tail_theta(blk, qrel, estar, pth, approx_eps, INFINITY, cx);
+                        if (cx != 0x7fffffff && blk.ccode != nullptr) {
+                            // no whole column block lies behind e*: the tail is at most a tile or two, so its best similarity
+                            // t' is looked up directly (plain FP64, certain to 1e-13) and the query needs ONE collection round
+                            // instead of two ("everything behind e*", then everything that reaches t')
+                            const uint32_t cq = blk.qcode[qrow];
+                            double tm = -INFINITY;
+                            for (int64_t r = (int64_t)estar + 1 + lane; r < blk.nb; r += 32) {
+                                const uint32_t x = cq ^ blk.ccode[r];
+                                if (((x - blk.low) & ~x & blk.high) == 0u) continue;
+                                const TB* row = xb + (size_t)r * ldb;
+                                double acc = 0.0;
+                                for (int k = 0; k < D; k++) acc = fma((double)row[k], qvec[warp][k], acc);
+                                const double sr = acc / (sqrt(sqn_b[r]) * sqrt(nq_));
+                                if (sr > tm) tm = sr;
+                            }
+#pragma unroll
+                            for (int off = 16; off > 0; off >>= 1) tm = fmax(tm, __shfl_xor_sync(0xffffffffu, tm, off));
+                            cx = 0x7fffffff;
+                            th = tm > -INFINITY ? fmin(tm - 1e-12 - 2.1 * approx_eps, pth - 2.02 * approx_eps) : -INFINITY;   // nothing behind e*: every candidate
+                        }
+                        if (lane == 0) p2_emit(w2, (int)qrel, th, cx, CRX_Q_TIE_ORDER << P2_KIND_SHIFT);
+                    } else if (lane == 0) atomicAdd(&counters[CRX_CNT_TOPP_TIES], 1ull);
                 }
             }
         }
@@ -790,6 +815,14 @@ __global__ void sq_sizes_kernel(const int32_t* __restrict__ off, int ngroups, do
 // second pass of the batched top-P: rounds of collect -> evaluate -> resolve over the queued queries
 // (recommend_pass2.cuh) until every query carries the reference's list
 // ------------------------------------------------------------------------------------------------
+// CRX_P2_DEBUG: wall-clock marks (stream synchronised) through one crx_recommend_lsh call
+struct DebugClock {
+    bool on; cudaStream_t s; double t0;
+    static double now() { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6; }
+    DebugClock(cudaStream_t st) : on(getenv("CRX_P2_DEBUG") != nullptr), s(st), t0(0) { if (on) { cudaStreamSynchronize(s); t0 = now(); } }
+    void mark(const char* what) { if (!on) return; cudaStreamSynchronize(s); double t = now(); fprintf(stderr, "[crx clock] %-28s %8.2f ms\n", what, t - t0); t0 = t; }
+};
+
 struct P2Host {
     const crx_points* base; const crx_points* queries;
     int64_t q_begin, nq;
@@ -800,6 +833,7 @@ struct P2Host {
     const uint32_t* qcode; const uint32_t* ccode; int k, L; bool dense;
     const int32_t* qgid; int64_t qstride; const int32_t* cgid; int64_t cstride;   // SIMT path: group ids
     double eps, unscale;
+    const double* eps_q;   // per query row (centred operands) or NULL
     P2Blocks blocks;
     int32_t* recs; int32_t* rows; double* sims; int32_t* status;
 };
@@ -843,6 +877,7 @@ static int pass2_run(crx_ctx* c, const P2Host& h, P2QueueBuf* qa, P2QueueBuf* qb
     CRX_CUDA(cudaMemcpyAsync(&n, cur->count.p, sizeof(n), cudaMemcpyDeviceToHost, c->stream));
     CRX_CUDA(cudaStreamSynchronize(c->stream));
     static const bool p2_debug = getenv("CRX_P2_DEBUG") != nullptr;
+    DebugClock clk(c->stream);
     // rows whose coordinates are all equal (single-coin users): their mutual similarities have a closed form (p2_exact_kernel)
     DevBuf<double> uval_b, uval_q;
     if (n > 0) {
@@ -900,7 +935,7 @@ static int pass2_run(crx_ctx* c, const P2Host& h, P2QueueBuf* qa, P2QueueBuf* qb
             memset(&a, 0, sizeof(a));
             a.unk_q = queries->unknown; a.mean_q = queries->mean; a.mean_b = base->mean;
             a.ldb = base->ld; a.D = base->d; a.P = h.P; a.Nrec = h.Nrec; a.q_begin = h.q_begin; a.ncand = h.nc;
-            a.cur = cur->view(); a.n = n; a.eps = h.eps;
+            a.cur = cur->view(); a.n = n; a.eps = h.eps; a.eps_q = h.eps_q;
             a.recs = h.recs; a.nbr_rows = h.rows; a.nbr_sims = h.sims; a.qstatus = h.status; a.counters = c->counters;
 #define LAUNCH_U(KERNEL, TQ, TB, xqp, xbp, ...) KERNEL<TQ, TB><<<crx_grid(n, 4), 128, 0, c->stream>>>(xqp, queries->ld, xbp, a, u, __VA_ARGS__)
 #define DISPATCH_U(KERNEL, ...)                                                                                  \
@@ -938,6 +973,7 @@ static int pass2_run(crx_ctx* c, const P2Host& h, P2QueueBuf* qa, P2QueueBuf* qb
         }
     }
     static const int max_rounds = getenv("CRX_P2_ROUNDS") ? atoi(getenv("CRX_P2_ROUNDS")) : 16;
+    clk.mark("  constant rows");
     DevBuf<unsigned long long> dbg;
     if (p2_debug) { CRX_TRY(dbg.alloc(c, 8)); }
     for (int round = 0; n > 0 && round < max_rounds; round++) {
@@ -945,6 +981,7 @@ static int pass2_run(crx_ctx* c, const P2Host& h, P2QueueBuf* qa, P2QueueBuf* qb
         if (p2_debug) CRX_CUDA(cudaMemsetAsync(dbg.p, 0, 8 * sizeof(unsigned long long), c->stream));
         size_t free_b = 0, total_b = 0;
         CRX_CUDA(cudaMemGetInfo(&free_b, &total_b));
+        for (auto& b : c->big_free) free_b += b.second;   // blocks the context keeps between calls are available to this round
         // budget for the collected lists: one third for the pass masks of the threshold scan (32 B per row and column tile), the
         // rest for rows + similarities (12 B per entry).  A queue that needs more is processed in slices.
         const int64_t budget = (int64_t)std::max<size_t>(free_b / 2, (size_t)64 << 20);
@@ -956,6 +993,7 @@ static int pass2_run(crx_ctx* c, const P2Host& h, P2QueueBuf* qa, P2QueueBuf* qb
         int64_t collected = 0;
         for (unsigned int s0 = 0; s0 < n; s0 += slice) {
         const unsigned int ns = std::min(slice, n - s0);
+        const bool tc_round = h.use_tc;
         DevBuf<int32_t> count, ovf, qrow_abs, cols, allf, colx_eff;
         DevBuf<uint32_t> cmask;
         DevBuf<float> theta_f;
@@ -970,7 +1008,7 @@ static int pass2_run(crx_ctx* c, const P2Host& h, P2QueueBuf* qa, P2QueueBuf* qb
         P2Queue w = cur->view();
         w.q += s0; w.theta += s0; w.colx += s0; w.tries += s0;
         int64_t rows_pad = 0;
-        if (h.use_tc) {
+        if (tc_round) {
             CRX_TRY(qrow_abs.alloc(c, ns)); CRX_TRY(theta_f.alloc(c, ns)); CRX_TRY(allf.alloc(c, ns)); CRX_TRY(colx_eff.alloc(c, ns));
             { CRX_KERNEL(c, "p2_prepare"); p2_prepare_kernel<<<crx_grid(ns, 256), 256, 0, c->stream>>>(w, ns, h.q_begin, 1.0 / h.unscale, theta_f.p, qrow_abs.p, allf.p, colx_eff.p); }
             TcOperand opA;
@@ -979,6 +1017,7 @@ static int pass2_run(crx_ctx* c, const P2Host& h, P2QueueBuf* qa, P2QueueBuf* qb
             rows_pad = ((int64_t)ns + 127) / 128 * 128;
             CRX_TRY(crx_tc_collect(c, opA, ns, *h.opB, h.qcode, qrow_abs.p, h.ccode, h.k, h.L, h.dense, theta_f.p, colx_eff.p, cmask.p, count.p));
             { CRX_KERNEL(c, "p2_all_count"); p2_all_count_kernel<<<crx_grid(ns, 256), 256, 0, c->stream>>>(allf.p, ns, w.q, h.nc, count.p, ovf.p); }
+            clk.mark("  collect");
         } else {
             CRX_KERNEL(c, "p2_collect_simt");
 #define LAUNCH_S(TQ, TB, xqp, xbp, FILL)                                                                                          \
@@ -997,8 +1036,10 @@ static int pass2_run(crx_ctx* c, const P2Host& h, P2QueueBuf* qa, P2QueueBuf* qb
             CRX_TRY(p2_scan_sizes(c, count.p, ovf.p, ns, seg, off, tmp, tmp_bytes, &total));
         }
         collected += total;
+        clk.mark("  sizes");
         CRX_TRY(cols.alloc(c, (size_t)total)); CRX_TRY(xs.alloc(c, (size_t)total));
-        if (h.use_tc) {
+        clk.mark("  alloc lists");
+        if (tc_round) {
             {
                 CRX_KERNEL(c, "p2_expand");
                 const int tn = crx_tc_tile_cols();
@@ -1023,6 +1064,7 @@ static int pass2_run(crx_ctx* c, const P2Host& h, P2QueueBuf* qa, P2QueueBuf* qb
 #undef LAUNCH_S
             CRX_CUDA(cudaGetLastError());
         }
+        clk.mark("  expand");
         if (total > 0) {
             CRX_KERNEL(c, "p2_exact");
             const int64_t nblocks = total / 32;
@@ -1036,6 +1078,7 @@ static int pass2_run(crx_ctx* c, const P2Host& h, P2QueueBuf* qa, P2QueueBuf* qb
 #undef LAUNCH_E
             CRX_CUDA(cudaGetLastError());
         }
+        clk.mark("  exact");
         {
             CRX_KERNEL(c, "p2_resolve");
             P2Resolve a;
@@ -1044,13 +1087,14 @@ static int pass2_run(crx_ctx* c, const P2Host& h, P2QueueBuf* qa, P2QueueBuf* qb
             a.ldb = base->ld; a.D = base->d; a.P = h.P; a.Nrec = h.Nrec; a.q_begin = h.q_begin; a.ncand = h.nc;
             a.cur = w; a.next = nxt->view(); a.n = ns;
             a.off = off.p; a.count = count.p; a.ovf = ovf.p; a.cols = cols.p; a.xs = xs.p;
-            a.eps = h.eps; a.blocks = h.blocks;
+            a.eps = h.eps; a.eps_q = h.eps_q; a.blocks = h.blocks;
             a.recs = h.recs; a.nbr_rows = h.rows; a.nbr_sims = h.sims; a.qstatus = h.status; a.counters = c->counters;
             a.dbg = p2_debug ? dbg.p : nullptr;
             if (base->x64) p2_resolve_kernel<double><<<crx_grid(ns, 4), 128, 0, c->stream>>>(base->x64, a);
             else p2_resolve_kernel<float><<<crx_grid(ns, 4), 128, 0, c->stream>>>(base->x32, a);
             CRX_CUDA(cudaGetLastError());
         }
+        clk.mark("  resolve");
         }   // slices
         std::swap(cur, nxt);
         const unsigned int n_in = n;
@@ -1090,6 +1134,7 @@ static int recommend_lsh_impl(crx_ctx* c, const crx_lsh* t, const crx_points* qu
     CRX_CUDA(cudaSetDevice(c->device));
     int64_t nq = q_end - q_begin;
     if (nq == 0) return CRX_OK;
+    DebugClock clk(c->stream);
     int L = t->L;
     int64_t N = base->n;
 
@@ -1112,6 +1157,8 @@ static int recommend_lsh_impl(crx_ctx* c, const crx_lsh* t, const crx_points* qu
     TcOperand opB, opA;                    // split-fp16 operands: kept until the second pass is through
     bool dense_cols = false;
     double tc_unscale = 1.0;
+    DevBuf<double> eps_b, eps_a;           // centred operands: the filter's error bound per base / query row
+    const double* eps_rows = nullptr;
     CRX_TRY(nc.alloc(c, nq));
     // second, targeted pass for the queries whose list does not decide the reference's order (recommend_pass2.cuh);
     // CRX_TOPP_EXACT=0 leaves them counted instead (counters [1] and [5])
@@ -1151,8 +1198,13 @@ static int recommend_lsh_impl(crx_ctx* c, const crx_lsh* t, const crx_points* qu
         { CRX_KERNEL(c, "subset_count"); subset_count_kernel<<<crx_grid(nq, 256), 256, 0, c->stream>>>(qcode, q_begin, nq, k, L, d_hoff.p, hist.p, nc.p); }
         CRX_CUDA(cudaGetLastError());
         // split-fp16 operands: unit rows times 2^10, so the accumulators hold 2^20 * cosine
-        int st = crx_tc_prepare(c, base, 0, 10.0, &opB);
-        if (st == CRX_OK && !self) st = crx_tc_prepare(c, queries, 0, 10.0, &opA);
+        // centred on (1,..,1)/sqrt(D) when three spare operand columns exist (tc_prep_rows_kernel): per-query error bounds
+        static const bool center_off = getenv("CRX_TC_CENTER") != nullptr && getenv("CRX_TC_CENTER")[0] == '0';
+        const bool centered = !center_off && base->d + 3 <= 128;
+        if (centered) { CRX_TRY(eps_b.alloc(c, (size_t)N)); if (!self) CRX_TRY(eps_a.alloc(c, (size_t)queries->n)); }
+        int st = crx_tc_prepare(c, base, centered ? 2 : 0, 10.0, &opB, nullptr, nullptr, nullptr, centered ? eps_b.p : nullptr);
+        if (st == CRX_OK && !self) st = crx_tc_prepare(c, queries, centered ? 2 : 0, 10.0, &opA, nullptr, nullptr, nullptr, centered ? eps_a.p : nullptr);
+        if (centered) eps_rows = self ? eps_b.p : eps_a.p;
         // candidate density decides the hot-loop variant of the filter
         DevBuf<unsigned long long> tot;
         CRX_TRY(tot.alloc(c, 1));
@@ -1167,9 +1219,13 @@ static int recommend_lsh_impl(crx_ctx* c, const crx_lsh* t, const crx_points* qu
             blk.blockmax = blockmax.p;
             blk.nblk = crx_tc_blocks(N, blk.bt);
             blk.tile_cols = crx_tc_tile_cols();
+            blk.qcode = qcode; blk.ccode = ccode.p; blk.nb = N;
+            for (int l = 0; l < L; l++) { blk.low |= 1u << (l * k); blk.high |= 1u << (l * k + k - 1); }
             blk.unscale = ldexp(1.0, -20);
         }
+        clk.mark("codes, counts, operands");
         if (st == CRX_OK) st = crx_tc_topp(c, self ? opB : opA, q_begin, nq, opB, qcode, ccode.p, k, L, dense_cols, tl_s.p, tl_i.p, 3, blockmax.p);
+        clk.mark("first-pass scan");
         tc_unscale = ldexp(1.0, -20);
         if (st != CRX_OK) return st;
     } else {
@@ -1250,10 +1306,10 @@ static int recommend_lsh_impl(crx_ctx* c, const crx_lsh* t, const crx_points* qu
     do {                                                                                                                   \
         if (use_tc)                                                                                                        \
             rec_finalize_kernel<TQ, TB, TC_LIST, float><<<g, 128, 0, c->stream>>>(xqp, queries->ld, queries->sqn, queries->unknown, queries->mean, xbp, \
-                base->ld, base->sqn, base->mean, base->d, q_begin, nq, P, Nrec, tl_s.p, tl_i.p, nc.p, tc_unscale, 8e-6, o_recs.dev, o_rows.dev, o_sims.dev, c->counters, tie_order, o_status.dev, pass2, p2a.view(), blk); \
+                base->ld, base->sqn, base->mean, base->d, q_begin, nq, P, Nrec, tl_s.p, tl_i.p, nc.p, tc_unscale, 8e-6, o_recs.dev, o_rows.dev, o_sims.dev, c->counters, tie_order, o_status.dev, pass2, p2a.view(), blk, eps_rows); \
         else                                                                                                               \
             rec_finalize_kernel<TQ, TB, LIST, double><<<g, 128, 0, c->stream>>>(xqp, queries->ld, queries->sqn, queries->unknown, queries->mean, xbp, \
-                base->ld, base->sqn, base->mean, base->d, q_begin, nq, P, Nrec, list_s.p, list_i.p, nc.p, 1.0, 1e-12, o_recs.dev, o_rows.dev, o_sims.dev, c->counters, tie_order, o_status.dev, pass2, p2a.view(), blk); \
+                base->ld, base->sqn, base->mean, base->d, q_begin, nq, P, Nrec, list_s.p, list_i.p, nc.p, 1.0, 1e-12, o_recs.dev, o_rows.dev, o_sims.dev, c->counters, tie_order, o_status.dev, pass2, p2a.view(), blk, nullptr); \
     } while (0)
         if (queries->x64 && base->x64) LAUNCH_F(double, double, queries->x64, base->x64);
         else if (queries->x64) LAUNCH_F(double, float, queries->x64, base->x32);
@@ -1262,15 +1318,17 @@ static int recommend_lsh_impl(crx_ctx* c, const crx_lsh* t, const crx_points* qu
 #undef LAUNCH_F
     }
     CRX_CUDA(cudaGetLastError());
+    clk.mark("rec_finalize");
     if (pass2) {
         P2Host h;
         memset(&h, 0, sizeof(h));
         h.base = base; h.queries = queries; h.q_begin = q_begin; h.nq = nq; h.P = P; h.Nrec = Nrec; h.nc = nc.p; h.use_tc = use_tc;
         h.opQ = self ? &opB : &opA; h.opB = &opB; h.qcode = qcode; h.ccode = ccode.p; h.k = t->k; h.L = L; h.dense = dense_cols;
         h.qgid = qgid_base; h.qstride = qstride; h.cgid = t->gid; h.cstride = N;
-        h.eps = use_tc ? 8e-6 : 1e-12; h.unscale = tc_unscale; h.blocks = blk;
+        h.eps = use_tc ? 8e-6 : 1e-12; h.eps_q = eps_rows; h.unscale = tc_unscale; h.blocks = blk;
         h.recs = o_recs.dev; h.rows = o_rows.dev; h.sims = o_sims.dev; h.status = o_status.dev;
         CRX_TRY(pass2_run(c, h, &p2a, &p2b));
+        clk.mark("second pass");
     }
     opB.free_all();
     opA.free_all();
@@ -1282,6 +1340,7 @@ static int recommend_lsh_impl(crx_ctx* c, const crx_lsh* t, const crx_points* qu
     CRX_TRY(o_sims.flush());
     CRX_TRY(o_status.flush());
     if (mem == CRX_HOST) CRX_CUDA(cudaStreamSynchronize(c->stream));
+    clk.mark("results out");
     return CRX_OK;
 }
 

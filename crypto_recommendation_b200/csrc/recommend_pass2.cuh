@@ -36,6 +36,10 @@ __device__ __forceinline__ void p2_emit(const P2Queue& w, int q, double theta, i
 
 struct P2Blocks {
     const float* blockmax;   // [nq][2][TC_NBLK] filter units, or NULL
+    const uint32_t* qcode;   // packed table codes of the query / base rows and the field masks (tail scan of rec_finalize), or NULL
+    const uint32_t* ccode;
+    uint32_t low, high;
+    int64_t nb;              // rows of the table
     int nblk;
     int tile_cols;           // columns per tile of the scan that produced blockmax
     int bt[TC_NBLK + 1];
@@ -530,6 +534,7 @@ struct P2Resolve {
     const int64_t* off; const int32_t* count; const int32_t* ovf;
     int32_t* cols; double* xs;
     double eps;
+    const double* eps_q;   // per absolute query row (centred operands), or NULL: eps for every query
     P2Blocks blocks;
     int32_t* recs; int32_t* nbr_rows; double* nbr_sims; int32_t* qstatus;
     unsigned long long* counters;
@@ -555,7 +560,7 @@ p2_resolve_kernel(const TB* __restrict__ xb, P2Resolve a) {
     const double theta = a.cur.theta[i];
     const int colx = a.cur.colx[i];
     const int tries = a.cur.tries[i];
-    const double eps = a.eps;
+    const double eps = a.eps_q ? a.eps_q[a.q_begin + qrel] : a.eps;
     if (a.ovf && a.ovf[i]) {   // the chunk pool ran dry in this round: again (the next round has fewer lists to hold)
         if (lane == 0) p2_emit(a.next, qrel, theta, colx, tries + 1);
         return;

@@ -147,6 +147,8 @@ struct TcParams {
     int last_steps;   // K=16 slices of the last 64-column block that hold data
     const uint32_t* a_words;   // ATM: the A operand in global memory, [rows_pad][nkb * 64] words (hi part, then lo part)
     int64_t a_rows_pad;
+    int lo_first;     // centred operands: the B.lo blocks go first and A.hi_last x B.hi_last is the final product of a tile, so that the
+                      // large alpha_q alpha_c term (carried by three extra columns) meets the accumulator in the LAST MMA only
     // top-P
     const uint32_t* qcode;
     const uint32_t* ccode;
@@ -177,7 +179,9 @@ struct TcParams {
     const int32_t* c_qrow;
     uint32_t* cmask;        // [ntiles][TN / 32][c_rows_pad] pass bits of every 32-column chunk (one coalesced store per warp)
     int64_t c_rows_pad;     // rows of the mask matrix (the grid's rows, a multiple of 128)
-    int32_t* c_count;       // [rows] number of set bits, added up by the row's two epilogue threads (zeroed by the caller)
+    int32_t* c_count;       // [rows] number of set bits, added up by the row's epilogue threads (zeroed by the caller)
+    int c_split;            // column tiles per CTA: blockIdx.y takes tiles [y c_split, (y + 1) c_split) -- a short queue (the later
+                            // rounds) is spread over the SMs by columns; one CTA streaming every tile is bound by its 3-stage ring
 };
 
 constexpr int MODE_TOPP = 0, MODE_ARGMIN = 1, MODE_ROWSUM = 2, MODE_COLLECT = 3;
@@ -284,6 +288,12 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     int ntiles = p.ntiles;
     const int n_row_tiles = MODE == MODE_ARGMIN ? (int)((p.nq + TM - 1) / TM) : (int)blockIdx.x + 1;
     const int rt_step = MODE == MODE_ARGMIN ? (int)gridDim.x : n_row_tiles;   // non-persistent modes: exactly one pass
+    int tile0 = 0;   // first column tile of this CTA (collection with column splits)
+    if (MODE == MODE_COLLECT) {
+        tile0 = (int)blockIdx.y * p.c_split;
+        ntiles = max(0, min(p.ntiles, tile0 + p.c_split) - tile0);
+        col0 = (int64_t)tile0 * TN;
+    }
     if (MODE == MODE_ROWSUM) {
         const int4 job = p.jobs[blockIdx.x];
         row0 = job.x; row_end = job.y; col0 = job.z; col_end = job.w;
@@ -307,7 +317,8 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     for (int b = 0; b < nblk; b++) tma_load_2d(sA + ab * 4 * BLK_BYTES + b * BLK_BYTES, &tmA, b * 64, arow, &a_full[ab]);
                 }
                 for (int t = 0; t < ntiles; t++) {
-                    for (int b = 0; b < nload; b++) {
+                    for (int sb = 0; sb < nload; sb++) {
+                        const int b = p.lo_first ? (sb < p.nkb ? p.nkb + sb : sb - p.nkb) : sb;   // lo blocks first
                         mbar_wait(&empty[stage], phase ^ 1);
                         mbar_arrive_expect_tx(&full[stage], (uint32_t)BBLK_BYTES);
                         tma_load_2d(sB + stage * BBLK_BYTES, &tmB, b * 64, (int)col0 + t * TN, &full[stage]);
@@ -336,7 +347,9 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 tc_fence_after();
                 const uint32_t d = tmem_base + (uint32_t)(buf * TN);  // TN fp32 columns per buffer
                 const int nload = p.nprod == 1 ? p.nkb : nblk;
-                for (int b = 0; b < nload; b++) {
+                uint32_t fresh = 0u;   // 0: the next MMA overwrites the accumulator (first of the tile), 1: it accumulates
+                for (int sb = 0; sb < nload; sb++) {
+                    const int b = p.lo_first ? (sb < p.nkb ? p.nkb + sb : sb - p.nkb) : sb;
                     mbar_wait(&full[stage], phase);
                     tc_fence_after();
                     const uint32_t bs = b_base + stage * BBLK_BYTES;
@@ -344,18 +357,19 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     const int steps = j == p.nkb - 1 ? p.last_steps : 4;
                     if (ATM) {        // A blocks: 32 words (64 fp16) each, hi parts at ATM_COL, lo parts 64 columns behind
                         const uint32_t ta = tmem_base + (uint32_t)(ATM_COL + j * 32);
-                        if (b < p.nkb) {
-                            mma_block_ts(d, ta, bs, b == 0 ? 0u : 1u, steps, IDESC);
-                            if (p.nprod != 1) mma_block_ts(d, ta + 64u, bs, 1u, steps, IDESC);
+                        if (b < p.nkb) {   // B.hi_j with A.lo_j and A.hi_j (the high x high product last)
+                            if (p.nprod != 1) { mma_block_ts(d, ta + 64u, bs, fresh, steps, IDESC); fresh = 1u; }
+                            mma_block_ts(d, ta, bs, fresh, steps, IDESC);
                         } else {
-                            mma_block_ts(d, ta, bs, 1u, steps, IDESC);
+                            mma_block_ts(d, ta, bs, fresh, steps, IDESC);
                         }
-                    } else if (b < p.nkb) {  // B.hi_j with A.hi_j and A.lo_j
-                        mma_block(d, a_base + j * BLK_BYTES, bs, b == 0 ? 0u : 1u, steps, IDESC);
-                        if (p.nprod != 1) mma_block(d, a_base + (p.nkb + j) * BLK_BYTES, bs, 1u, steps, IDESC);
+                    } else if (b < p.nkb) {  // B.hi_j with A.lo_j and A.hi_j (the high x high product last)
+                        if (p.nprod != 1) { mma_block(d, a_base + (p.nkb + j) * BLK_BYTES, bs, fresh, steps, IDESC); fresh = 1u; }
+                        mma_block(d, a_base + j * BLK_BYTES, bs, fresh, steps, IDESC);
                     } else {          // B.lo_j with A.hi_j
-                        mma_block(d, a_base + j * BLK_BYTES, bs, 1u, steps, IDESC);
+                        mma_block(d, a_base + j * BLK_BYTES, bs, fresh, steps, IDESC);
                     }
+                    fresh = 1u;
                     tc_commit(&empty[stage]);
                     if (++stage == NS) { stage = 0; phase ^= 1; }
                 }
@@ -471,7 +485,7 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 if (rnd * 2 + ch >= NCH) continue;
                 uint32_t (&r)[32] = ch == 0 ? r0 : r1;
                 const uint4* st4 = reinterpret_cast<const uint4*>(stile + buf * TN * STW + half * HALF + rnd * 64 + ch * 32);
-                const int cbase = t * TN + half * HALF + rnd * 64 + ch * 32;
+                const int cbase = (tile0 + t) * TN + half * HALF + rnd * 64 + ch * 32;
                 if (MODE == MODE_TOPP) {
                     // hot loop: running maximum of the (masked) scores, four independent chains
                     float vm[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
@@ -548,7 +562,7 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         if (((x - low) & ~x & high) == 0u) bits &= ~(1u << j);
                     }
                     // rows of a warp are consecutive: 128 contiguous bytes per store
-                    p.cmask[((size_t)t * (2 * NCH) + (size_t)(half * NCH + rnd * 2 + ch)) * (size_t)p.c_rows_pad + (size_t)grow] = bits;
+                    p.cmask[((size_t)(tile0 + t) * (2 * NCH) + (size_t)(half * NCH + rnd * 2 + ch)) * (size_t)p.c_rows_pad + (size_t)grow] = bits;
                     c_total += __popc(bits);
                 } else if (MODE == MODE_ROWSUM) {
                     // d = sqrt(max(0, |a|^2 + |b|^2 - 2 a.b)) and a running bound on its error.  The squared distance is
@@ -663,18 +677,37 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 }
 
 // ---------------------------------------------------------------- operand preparation
+// mode 0: unit rows times `scale`; mode 1: rows times `scale`; mode 2: CENTRED unit rows (cosine top-P scans): with
+// e = (1, ..., 1)/sqrt(D), alpha = u.e and d = u - alpha e, the operand holds d times `scale` in columns [0, D) and alpha times
+// `scale` split three ways (h + l + m, 33 bits) in three extra columns laid out as (hi block, lo block) = (m, h), (l, m), (h, l):
+// the three products the issuer forms (hi.hi + lo.hi + hi.lo) then add up to EXACTLY (h+l+m)_a (h+l+m)_b, so the accumulator
+// holds scale^2 (d_a.d_b + alpha_a alpha_b) = scale^2 cos(a, b) while the split-fp16 and fp32-accumulation errors are
+// proportional to |d_a||d_b| instead of |a||b| = 1.  Rating-like vectors are dominated by their mean fill (alpha ~ 0.98,
+// |d| ~ 0.2; single-coin users have d = 0), which is exactly where the similarities crowd: the filter resolves them 5-40x
+// finer.  eps_out[row] = the filter's error bound for a query row: 3e-7 (the alpha term meets the accumulator in the last
+// MMA of a tile: one fp32 rounding at magnitude 1, lo_first) + 8e-6 |d| (|d_c| <= 1).
 template <typename T>
 __global__ void tc_prep_rows_kernel(const T* __restrict__ x, int ld, int D, const double* __restrict__ sqn, int64_t n,
                                     int mode, double scale, int nkb, const int32_t* __restrict__ rowmap, __half* __restrict__ out,
-                                    float* __restrict__ norm_s, float* __restrict__ errw_s) {
+                                    float* __restrict__ norm_s, float* __restrict__ errw_s, double* __restrict__ eps_out) {
     int64_t orow = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     int lane = threadIdx.x & 31;
     if (orow >= n) return;
     int64_t row = rowmap ? (int64_t)rowmap[orow] : orow;  // operand row orow holds point row
-    double s = scale;
-    if (mode == 0) {
+    double s = scale, shift = 0.0, alpha = 0.0;
+    if (mode == 0 || mode == 2) {
         double nn = sqn[row];
         s = nn > 0.0 ? scale / sqrt(nn) : 0.0;
+    }
+    if (mode == 2) {
+        double sx = 0.0;
+        for (int c = lane; c < D; c += 32) sx += (double)x[row * ld + c];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) sx += __shfl_xor_sync(0xffffffffu, sx, o);
+        const double rD = sqrt((double)D);
+        alpha = sx * (s / scale) / rD;       // u . e
+        shift = alpha / rD * scale;          // alpha e_k, scaled
+        if (eps_out && lane == 0) eps_out[orow] = 3e-7 + 8e-6 * sqrt(fmax(0.0, 1.0 - alpha * alpha));
     }
     if (norm_s && lane == 0) {
         // 6.3e-6 n covers the three-product split-fp16 dot with fp32 accumulation (2 x 3e-6 |a||b| <= 3e-6 (na + nb))
@@ -686,9 +719,17 @@ __global__ void tc_prep_rows_kernel(const T* __restrict__ x, int ld, int D, cons
     int W = nkb * 64;
     __half* o = out + orow * (size_t)(2 * W);
     for (int c = lane; c < W; c += 32) {
-        double v = c < D ? (double)x[row * ld + c] * s : 0.0;
+        double v = c < D ? (double)x[row * ld + c] * s - (s != 0.0 ? shift : 0.0) : 0.0;
         __half hi = __double2half(v);
         __half lo = __double2half(v - (double)__half2float(hi));
+        if (mode == 2 && c >= D && c < D + 3 && s != 0.0) {
+            const double ap = alpha * scale;
+            const __half h = __double2half(ap);
+            const __half l = __double2half(ap - (double)__half2float(h));
+            const __half m = __double2half(ap - (double)__half2float(h) - (double)__half2float(l));
+            // the large product h_a h_b sits in the LAST of the three columns: the last K = 16 slice the issuer touches
+            if (c == D) { hi = m; lo = h; } else if (c == D + 1) { hi = l; lo = m; } else { hi = h; lo = l; }
+        }
         o[c] = hi;
         o[W + c] = lo;
     }
@@ -758,15 +799,18 @@ int alloc_operand(crx_ctx* c, int64_t rows, int D, TcOperand* out) {
 
 }  // namespace
 
-int crx_tc_prepare(crx_ctx* c, const crx_points* p, int mode, double scale_log2, TcOperand* out, const int32_t* rowmap, float* norm_s, float* errw_s) {
+int crx_tc_prepare(crx_ctx* c, const crx_points* p, int mode, double scale_log2, TcOperand* out, const int32_t* rowmap, float* norm_s, float* errw_s,
+                   double* eps_out) {
     CRX_REQUIRE(p->d <= 128, "tensor path supports D <= 128");
-    CRX_TRY(alloc_operand(c, p->n, p->d, out));
+    CRX_REQUIRE(mode != 2 || p->d + 3 <= 128, "centred operands need three spare columns (D <= 125)");
+    CRX_TRY(alloc_operand(c, p->n, mode == 2 ? p->d + 3 : p->d, out));
+    out->centered = mode == 2;
     out->scale_log2 = scale_log2;
     double scale = ldexp(1.0, (int)scale_log2);
     int g = (int)((p->n + 7) / 8);
     CRX_KERNEL(c, "tc_prep");
-    if (p->x64) tc_prep_rows_kernel<double><<<g, 256, 0, c->stream>>>(p->x64, p->ld, p->d, p->sqn, p->n, mode, scale, out->nkb, rowmap, (__half*)out->data, norm_s, errw_s);
-    else tc_prep_rows_kernel<float><<<g, 256, 0, c->stream>>>(p->x32, p->ld, p->d, p->sqn, p->n, mode, scale, out->nkb, rowmap, (__half*)out->data, norm_s, errw_s);
+    if (p->x64) tc_prep_rows_kernel<double><<<g, 256, 0, c->stream>>>(p->x64, p->ld, p->d, p->sqn, p->n, mode, scale, out->nkb, rowmap, (__half*)out->data, norm_s, errw_s, eps_out);
+    else tc_prep_rows_kernel<float><<<g, 256, 0, c->stream>>>(p->x32, p->ld, p->d, p->sqn, p->n, mode, scale, out->nkb, rowmap, (__half*)out->data, norm_s, errw_s, eps_out);
     CRX_CUDA(cudaGetLastError());
     return CRX_OK;
 }
@@ -777,7 +821,7 @@ int crx_tc_prepare_matrix(crx_ctx* c, const double* m, int K, int D, int ld, dou
     out->scale_log2 = scale_log2;
     int g = (K + 7) / 8;
     CRX_KERNEL(c, "tc_prep");
-    tc_prep_rows_kernel<double><<<g, 256, 0, c->stream>>>(m, ld, D, nullptr, K, 1, ldexp(1.0, (int)scale_log2), out->nkb, nullptr, (__half*)out->data, nullptr, nullptr);
+    tc_prep_rows_kernel<double><<<g, 256, 0, c->stream>>>(m, ld, D, nullptr, K, 1, ldexp(1.0, (int)scale_log2), out->nkb, nullptr, (__half*)out->data, nullptr, nullptr, nullptr);
     CRX_CUDA(cudaGetLastError());
     return CRX_OK;
 }
@@ -823,6 +867,7 @@ int crx_tc_gather(crx_ctx* c, const TcOperand& src, const int32_t* d_rows, int64
     out->rows_pad = (n + TM - 1) / TM * TM;
     out->nkb = src.nkb;
     out->scale_log2 = src.scale_log2;
+    out->centered = src.centered;
     out->owner = c;
     const int row_u4 = src.nkb * 2 * 64 * (int)sizeof(__half) / 16;
     CRX_TRY(crx_alloc(c, (char**)&out->data, (size_t)out->rows_pad * row_u4 * 16));
@@ -841,7 +886,7 @@ int64_t crx_tc_collect_mask_words(int64_t nrows, int64_t b_rows) {
 int crx_tc_collect(crx_ctx* c, const TcOperand& A, int64_t nrows, const TcOperand& B, const uint32_t* qcode, const int32_t* d_qrow,
                    const uint32_t* ccode, int k, int L, bool dense, const float* d_theta, const int32_t* d_colx, uint32_t* cmask,
                    int32_t* d_count) {
-    CRX_REQUIRE(A.nkb == B.nkb, "operand widths differ");
+    CRX_REQUIRE(A.nkb == B.nkb && A.centered == B.centered && A.d == B.d, "operand layouts differ");
     CRX_REQUIRE(k * L <= 32 && k >= 1, "packed codes need k*L <= 32");
     if (nrows == 0) return CRX_OK;
     CUtensorMap tmA, tmB;
@@ -856,6 +901,7 @@ int crx_tc_collect(crx_ctx* c, const TcOperand& A, int64_t nrows, const TcOperan
     p.last_steps = last_steps_of(A);
     p.nprod = 3;
     p.a_words = (const uint32_t*)A.data; p.a_rows_pad = A.rows_pad;
+    p.lo_first = A.centered ? 1 : 0;
     p.qcode = qcode; p.ccode = ccode;
     uint32_t low = 0, high = 0;
     for (int l = 0; l < L; l++) { low |= 1u << (l * k); high |= 1u << (l * k + k - 1); }
@@ -864,13 +910,19 @@ int crx_tc_collect(crx_ctx* c, const TcOperand& A, int64_t nrows, const TcOperan
     p.cmask = cmask; p.c_rows_pad = (nrows + TM - 1) / TM * TM; p.c_count = d_count;
     size_t smem = smem_for(MODE_COLLECT, atm);
     int grid = (int)((nrows + TM - 1) / TM);
+    // fewer row tiles than SMs: split the columns so that every SM has work (at least 8 tiles per CTA)
+    int splits = 1;
+    if (grid < c->sm_count) splits = std::max(1, std::min(c->sm_count / grid, p.ntiles / 8));
+    p.c_split = (p.ntiles + splits - 1) / splits;
+    splits = (p.ntiles + p.c_split - 1) / p.c_split;
+    const dim3 grid2((unsigned)grid, (unsigned)splits);
     CRX_KERNEL(c, "tc_collect_scan");
     if (atm) {   // (the table mask is applied to the set bits only: one variant serves dense and sparse candidate sets)
         CRX_CUDA(cudaFuncSetAttribute(tc_scan_kernel<MODE_COLLECT, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        tc_scan_kernel<MODE_COLLECT, true, true><<<grid, NTHREADS_K, smem, c->stream>>>(tmA, tmB, p);
+        tc_scan_kernel<MODE_COLLECT, true, true><<<grid2, NTHREADS_K, smem, c->stream>>>(tmA, tmB, p);
     } else {
         CRX_CUDA(cudaFuncSetAttribute(tc_scan_kernel<MODE_COLLECT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        tc_scan_kernel<MODE_COLLECT, true><<<grid, NTHREADS_K, smem, c->stream>>>(tmA, tmB, p);
+        tc_scan_kernel<MODE_COLLECT, true><<<grid2, NTHREADS_K, smem, c->stream>>>(tmA, tmB, p);
     }
     CRX_CUDA(cudaGetLastError());
     (void)dense;
@@ -879,7 +931,7 @@ int crx_tc_collect(crx_ctx* c, const TcOperand& A, int64_t nrows, const TcOperan
 
 int crx_tc_topp(crx_ctx* c, const TcOperand& A, int64_t q0, int64_t nq, const TcOperand& B, const uint32_t* qcode,
                 const uint32_t* ccode, int k, int L, bool dense, float* list_s, int32_t* list_i, int nprod, float* blockmax) {
-    CRX_REQUIRE(A.nkb == B.nkb, "operand widths differ");
+    CRX_REQUIRE(A.nkb == B.nkb && A.centered == B.centered && A.d == B.d, "operand layouts differ");
     CRX_REQUIRE(k * L <= 32 && k >= 1, "packed codes need k*L <= 32");
     CUtensorMap tmA, tmB;
     CRX_TRY(make_tensor_map(A, TM, &tmA));
@@ -893,6 +945,7 @@ int crx_tc_topp(crx_ctx* c, const TcOperand& A, int64_t q0, int64_t nq, const Tc
     p.last_steps = last_steps_of(A);
     p.nprod = nprod == 1 ? 1 : 3;
     p.a_words = (const uint32_t*)A.data; p.a_rows_pad = A.rows_pad;
+    p.lo_first = A.centered ? 1 : 0;
     p.qcode = qcode; p.ccode = ccode;
     uint32_t low = 0, high = 0;
     for (int l = 0; l < L; l++) { low |= 1u << (l * k); high |= 1u << (l * k + k - 1); }

@@ -17,6 +17,7 @@ struct TcOperand {
     int nkb = 0;              // 64-column blocks per part (1 for D <= 64, 2 for D <= 128)
     int d = 0;                // true number of columns
     double scale_log2 = 0;    // values were multiplied by 2^scale_log2 before the split
+    bool centered = false;    // crx_tc_prepare mode 2: rows centred on (1,..,1)/sqrt(D), alpha in three extra columns (d counts them)
     crx_ctx* owner = nullptr;
     TcOperand() {}
     TcOperand(const TcOperand&) = delete;
@@ -25,11 +26,13 @@ struct TcOperand {
     void free_all() { if (owner && data) crx_free(owner, data); data = nullptr; }
 };
 
-// mode 0: rows scaled to unit length times 2^10 (cosine);  mode 1: all rows times 2^scale_log2
+// mode 0: rows scaled to unit length times 2^scale_log2 (cosine);  mode 1: all rows times 2^scale_log2;  mode 2: unit rows
+// centred on (1,..,1)/sqrt(D) (cosine top-P scans, D <= 125: see tc_prep_rows_kernel), eps_out[row] = the filter's error
+// bound (similarity units) for that row as a query
 // rowmap (nullable): operand row i holds point rowmap[i];  norm_s / errw_s (nullable, together): scaled squared norms and
 // the row-sum error weights
 int crx_tc_prepare(crx_ctx* c, const crx_points* p, int mode, double scale_log2, TcOperand* out, const int32_t* rowmap = nullptr,
-                   float* norm_s = nullptr, float* errw_s = nullptr);
+                   float* norm_s = nullptr, float* errw_s = nullptr, double* eps_out = nullptr);
 // same for a [K][ld] double matrix (centroids)
 int crx_tc_prepare_matrix(crx_ctx* c, const double* m, int K, int D, int ld, double scale_log2, TcOperand* out);
 
