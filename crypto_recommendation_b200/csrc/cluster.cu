@@ -1704,8 +1704,9 @@ int crx_cluster_sums(crx_ctx* c, const crx_points* p, const int32_t* labels, int
     CRX_TRY(out.bind(c, sums, (size_t)K * D, mem, false));
     CRX_TRY(cnt.bind(c, (long long*)counts, K, mem, false));
     Segments seg;
+    SegmentsGuard seg_guard(seg);   // freed on every return below
     int st = crx_build_segments(c, lab.dev, N, K, &seg);
-    if (st != CRX_OK) { seg.free_all(); return st; }
+    if (st != CRX_OK) return st;
     std::vector<int32_t> off(K + 1);
     CRX_CUDA(cudaMemcpyAsync(off.data(), seg.off, (K + 1) * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
     CRX_CUDA(cudaStreamSynchronize(c->stream));
@@ -1747,7 +1748,6 @@ int crx_cluster_sums(crx_ctx* c, const crx_points* p, const int32_t* labels, int
     st = out.flush();
     if (st == CRX_OK) st = cnt.flush();
     CRX_CUDA(cudaStreamSynchronize(c->stream));
-    seg.free_all();
     return st;
 }
 

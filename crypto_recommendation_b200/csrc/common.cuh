@@ -151,7 +151,9 @@ struct crx_launch_scope {
         }
     }
 };
-#define CRX_KERNEL(ctx, name) crx_launch_scope scope__##__LINE__(ctx, name)
+#define CRX_CONCAT2(a, b) a##b
+#define CRX_CONCAT(a, b) CRX_CONCAT2(a, b)
+#define CRX_KERNEL(ctx, name) crx_launch_scope CRX_CONCAT(scope__, __LINE__)(ctx, name)
 
 // stream-ordered temporary device buffer
 template <typename T>

@@ -639,7 +639,7 @@ __global__ void __launch_bounds__(256)
 rec_cluster_kernel(const TQ* __restrict__ xq, int ldq, const double* __restrict__ sqn_q, const uint8_t* __restrict__ unk_q,
                    const double* __restrict__ mean_q, const int32_t* __restrict__ qlabels, const TB* __restrict__ xb, int ldb,
                    const double* __restrict__ sqn_b, const double* __restrict__ mean_b, const int32_t* __restrict__ perm,
-                   const int32_t* __restrict__ off, int D, int64_t nq, int Nrec, int32_t* __restrict__ recs) {
+                   const int32_t* __restrict__ off, int K, int D, int64_t nq, int Nrec, int32_t* __restrict__ recs) {
     __shared__ int s_idx[8][32];
     __shared__ double s_sim[8][32];
     __shared__ double s_pred[8][128];
@@ -648,7 +648,8 @@ rec_cluster_kernel(const TQ* __restrict__ xq, int ldq, const double* __restrict_
     int64_t qrow = (int64_t)blockIdx.x * 8 + warp;
     if (qrow >= nq) return;
     int cl = qlabels[qrow];
-    int begin = off[cl], end = off[cl + 1];
+    const bool known = cl >= 0 && cl < K;   // a label outside [0, K) has no cluster: as an empty one
+    int begin = known ? off[cl] : 0, end = known ? off[cl + 1] : 0;
     if (begin == end) {
         for (int j = lane; j < Nrec; j += 32) recs[qrow * Nrec + j] = -1;
         return;
@@ -1372,15 +1373,16 @@ int crx_recommend_cluster(crx_ctx* c, const crx_points* users, const int32_t* la
     if (!self) CRX_TRY(qlab.bind(c, qlabels, nq, lmem, true));
     CRX_TRY(out.bind(c, recs, (size_t)nq * Nrec, mem, false));
     Segments seg;
+    SegmentsGuard seg_guard(seg);   // freed on every return below
     int st = crx_build_segments(c, lab.dev, N, K, &seg);
-    if (st != CRX_OK) { seg.free_all(); return st; }
+    if (st != CRX_OK) return st;
     {
         CRX_KERNEL(c, "rec_cluster");
         int g = (int)((nq + 7) / 8);
         const int32_t* ql = self ? lab.dev : qlab.dev;
 #define LAUNCH_C(TQ, TB, xqp, xbp)                                                                                          \
     rec_cluster_kernel<TQ, TB><<<g, 256, 0, c->stream>>>(xqp, queries->ld, queries->sqn, queries->unknown, queries->mean, ql, xbp, \
-                                                          users->ld, users->sqn, users->mean, seg.perm, seg.off, users->d, nq, Nrec, out.dev)
+                                                          users->ld, users->sqn, users->mean, seg.perm, seg.off, K, users->d, nq, Nrec, out.dev)
         if (queries->x64 && users->x64) LAUNCH_C(double, double, queries->x64, users->x64);
         else if (queries->x64) LAUNCH_C(double, float, queries->x64, users->x32);
         else if (users->x64) LAUNCH_C(float, double, queries->x32, users->x64);
@@ -1390,7 +1392,6 @@ int crx_recommend_cluster(crx_ctx* c, const crx_points* users, const int32_t* la
     CRX_CUDA(cudaGetLastError());
     st = out.flush();
     CRX_CUDA(cudaStreamSynchronize(c->stream));
-    seg.free_all();
     return st;
 }
 

@@ -20,6 +20,15 @@ struct Segments {
     }
 };
 
+// frees a function-local Segments on every exit path (early error returns included); the tables keep theirs by value
+struct SegmentsGuard {
+    Segments& s;
+    explicit SegmentsGuard(Segments& seg) : s(seg) {}
+    ~SegmentsGuard() { s.free_all(); }
+    SegmentsGuard(const SegmentsGuard&) = delete;
+    SegmentsGuard& operator=(const SegmentsGuard&) = delete;
+};
+
 // keys[n] on the device, values in [0, nkeys).  Allocates the three arrays with cudaMalloc.
 int crx_build_segments(crx_ctx* c, const int32_t* keys, int64_t n, int nkeys, Segments* out);
 

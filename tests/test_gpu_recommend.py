@@ -112,6 +112,21 @@ def test_rec_lsh_single_coin_users_form_a_clique(ctx, port, dtype):
     check_rec(ctx, out2, ref2)
 
 
+@pytest.mark.parametrize("d", [5, 61, 62, 64, 100, 125, 126, 128])
+def test_rec_lsh_operand_layouts(ctx, port, d):
+    """The top-P filter runs on centred operands whose alpha term sits in three extra columns: D + 3 <= 64 keeps one 64-column
+    block per part, up to 125 two, and wider rows fall back to plain unit rows.  Every layout must give the reference's lists,
+    on rating-like rows (alpha ~ 1, constant rows included) and on sign-mixed rows (alpha ~ 0)."""
+    U, unk, mean = synth.rating_users_fast(2200, d, seed=500 + d, min_known=1, max_known=min(6, d), dtype=np.float32)
+    rng = np.random.default_rng(d)
+    for X in (U, (U * rng.choice([-1.0, 1.0], size=U.shape)).astype(np.float32)):
+        P = ctx.points(X, unk, mean)
+        t = capi.LshTables(ctx, P, "cosine", 4, 5, 100, 0.4, 77)
+        out = capi.recommend_lsh(ctx, t, 20, 5, want=WANT)
+        ref = port.recommend_lsh(X.astype(np.float64), unk, mean, COSINE, 4, 5, 100, 0.4, 20, 5, 77)
+        check_rec(ctx, out, ref)
+
+
 def test_rec_lsh_normal_data_dense_and_table_modes(ctx, port):
     # i.i.d. normal points: ~27% of the rows are candidates (per-table passes win the cost model);
     # rating-like rows: ~95% (dense any-table scan wins).  Both must agree with the oracle.
