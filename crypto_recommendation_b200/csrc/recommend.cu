@@ -274,8 +274,8 @@ rec_finalize_kernel(const TQ* __restrict__ xq, int ldq, const double* __restrict
     constexpr int QW = 4;            // queries (warps) per block
     __shared__ int a_idx[QW][LISTN];
     __shared__ double a_sim[QW][LISTN];
-    __shared__ int s_idx[QW][32];
-    __shared__ double s_sim[QW][32];
+    __shared__ int s_idx[QW][P2_MAXP];      // the P best in their final order (P <= 64 on the tensor path, <= 32 otherwise)
+    __shared__ double s_sim[QW][P2_MAXP];
     __shared__ double s_pred[QW][128];
     __shared__ int s_coin[QW][128];
     __shared__ rw::WarpTile tiles[QW];
@@ -384,7 +384,7 @@ rec_finalize_kernel(const TQ* __restrict__ xq, int ldq, const double* __restrict
                 if (oi >= 0 && (os > sim || (os == sim && oi < idx))) rank++;
                 same += oi >= 0 && os == sim;
             }
-            if (rank < 32) { s_idx[warp][rank] = idx; s_sim[warp][rank] = sim; }
+            if (rank < P2_MAXP) { s_idx[warp][rank] = idx; s_sim[warp][rank] = sim; }
             tied[e] = same > 1;
         }
     }
@@ -535,7 +535,7 @@ rec_finalize_kernel(const TQ* __restrict__ xq, int ldq, const double* __restrict
                     __syncwarp();
                     warp_lomuto_topn<EPL>(rk, rv, m, keep);
                     __syncwarp();
-                    if (lane < keep) { s_idx[warp][lane] = rv[lane]; s_sim[warp][lane] = rk[lane]; }
+                    for (int j = lane; j < keep; j += 32) { s_idx[warp][j] = rv[j]; s_sim[warp][j] = rk[j]; }
                     __syncwarp();
                 } else {
                     status = CRX_Q_TIE_ORDER;   // kept: descending similarity, ties by row (second pass: the tail behind e*)
@@ -1127,7 +1127,7 @@ static int recommend_lsh_impl(crx_ctx* c, const crx_lsh* t, const crx_points* qu
     if (!queries) queries = base;
     CRX_REQUIRE(queries->d == base->d, "query / table dimension mismatch");
     CRX_REQUIRE(q_begin >= 0 && q_begin <= q_end && q_end <= queries->n, "query range");
-    CRX_REQUIRE(P >= 1 && P <= LIST, "P must be in [1, 32] in this round");
+    CRX_REQUIRE(P >= 1 && P <= P2_MAXP, "P must be in [1, 64]");
     CRX_REQUIRE(Nrec >= 0 && Nrec <= 128, "Nrec");
     if (recs) CRX_REQUIRE(base->mean && queries->unknown && queries->mean, "ratings metadata missing (crx_points_set_ratings)");
     CRX_REQUIRE(self || t->metric == CRX_COSINE, "external queries are supported for cosine tables only in this round");
@@ -1175,6 +1175,7 @@ static int recommend_lsh_impl(crx_ctx* c, const crx_lsh* t, const crx_points* qu
     static const int tie_order = !(getenv("CRX_TIE_ORDER") != nullptr && getenv("CRX_TIE_ORDER")[0] == '0');
     const bool use_tc = !tc_off && t->metric == CRX_COSINE && t->k * L <= 32 && L <= 8 &&
                         pow(1.0 + (double)(1 << t->k), (double)L) <= (double)(1 << 24);
+    CRX_REQUIRE(use_tc || P <= LIST, "P <= 32 for tables the tensor path does not take (Euclidean tables, k*L > 32, CRX_NO_TC)");
     if (use_tc) {
         int k = t->k;
         CRX_TRY(tl_s.alloc(c, (size_t)nq * TC_LIST)); CRX_TRY(tl_i.alloc(c, (size_t)nq * TC_LIST));

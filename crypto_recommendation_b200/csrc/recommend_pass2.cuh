@@ -34,6 +34,43 @@ __device__ __forceinline__ void p2_emit(const P2Queue& w, int q, double theta, i
     w.q[i] = q; w.theta[i] = theta; w.colx[i] = colx; w.tries[i] = tries;
 }
 
+constexpr int P2_MAXP = 64;   // neighbours per query the batched path can return
+
+// The `keep` (<= 64) largest values seen so far, sorted descending over the warp: slot s lives in lane s (lo) for s < 32 and
+// in lane s - 32 (hi) beyond.  thr = the keep-th largest once `keep` values are in (else -inf).
+struct WarpTop {
+    double lo = -INFINITY, hi = -INFINITY, thr = -INFINITY;
+    int filled = 0;
+    __device__ __forceinline__ double slot(int s) const {   // every lane receives the value of slot s
+        const double a = __shfl_sync(0xffffffffu, lo, s & 31), b = __shfl_sync(0xffffffffu, hi, s & 31);
+        return s < 32 ? a : b;
+    }
+    // every lane offers k (taken when `in`); all 32 lanes call together
+    __device__ __forceinline__ void offer(double k, bool in, int keep) {
+        const int lane = threadIdx.x & 31;
+        unsigned want = __ballot_sync(0xffffffffu, in && k == k && (k > thr || filled < keep));
+        while (want) {
+            const int src = __ffs(want) - 1;
+            want &= want - 1;
+            const double x = __shfl_sync(0xffffffffu, k, src);
+            if (x > thr || filled < keep) {
+                const int pos = __popc(__ballot_sync(0xffffffffu, lo >= x)) + __popc(__ballot_sync(0xffffffffu, hi >= x));
+                const double up_lo = __shfl_up_sync(0xffffffffu, lo, 1), up_hi = __shfl_up_sync(0xffffffffu, hi, 1);
+                const double carry = __shfl_sync(0xffffffffu, lo, 31);   // old slot 31 moves to slot 32 when the shift crosses it
+                if (pos < 32) {
+                    lo = lane < pos ? lo : (lane == pos ? x : up_lo);
+                    hi = lane == 0 ? carry : up_hi;
+                } else {
+                    const int ph = pos - 32;
+                    hi = lane < ph ? hi : (lane == ph ? x : up_hi);
+                }
+                if (filled < keep) filled++;
+                thr = filled < keep ? -INFINITY : slot(keep - 1);
+            }
+        }
+    }
+};
+
 struct P2Blocks {
     const float* blockmax;   // [nq][2][TC_NBLK] filter units, or NULL
     const uint32_t* qcode;   // packed table codes of the query / base rows and the field masks (tail scan of rec_finalize), or NULL
@@ -548,8 +585,8 @@ p2_resolve_kernel(const TB* __restrict__ xb, P2Resolve a) {
     __shared__ int posge[QW][128];
     __shared__ double hk[QW][128];
     __shared__ int hv[QW][128];
-    __shared__ int s_idx[QW][32];
-    __shared__ double s_sim[QW][32];
+    __shared__ int s_idx[QW][P2_MAXP];
+    __shared__ double s_sim[QW][P2_MAXP];
     __shared__ double s_pred[QW][128];
     __shared__ int s_coin[QW][128];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -577,33 +614,17 @@ p2_resolve_kernel(const TB* __restrict__ xb, P2Resolve a) {
         if (lane == 0) p2_emit(a.next, qrel, (tries & 0xffff) > 8 ? -INFINITY : theta - lower, colx, tries + 1);
         return;
     }
-    // ---- T_P = the keep-th best similarity: sorted list of the best `keep`, one entry per lane.  Long lists (a plateau of tied
+    // ---- T_P = the keep-th best similarity (WarpTop: the best `keep` sorted over the warp).  Long lists (a plateau of tied
     // candidates) are read four 32-entry groups at a time so that enough loads are in flight
-    double mine = -INFINITY, thr = -INFINITY;
-    int filled = 0;
+    WarpTop top;
     for (int base = 0; base < cnt; base += 128) {
         double k4[4];
 #pragma unroll
         for (int u = 0; u < 4; u++) { const int e = base + u * 32 + lane; k4[u] = e < cnt ? key[e] : -INFINITY; }
 #pragma unroll
-        for (int u = 0; u < 4; u++) {
-            const double k = k4[u];
-            unsigned want = __ballot_sync(0xffffffffu, base + u * 32 + lane < cnt && k == k && (k > thr || filled < keep));
-            while (want) {
-                const int src = __ffs(want) - 1;
-                want &= want - 1;
-                const double x = __shfl_sync(0xffffffffu, k, src);
-                if (x > thr || filled < keep) {
-                    const int pos = __popc(__ballot_sync(0xffffffffu, mine >= x));
-                    const double up = __shfl_up_sync(0xffffffffu, mine, 1);
-                    mine = lane < pos ? mine : (lane == pos ? x : up);
-                    if (filled < keep) filled++;
-                    thr = filled < keep ? -INFINITY : __shfl_sync(0xffffffffu, mine, keep - 1);
-                }
-            }
-        }
+        for (int u = 0; u < 4; u++) top.offer(k4[u], base + u * 32 + lane < cnt, keep);
     }
-    const double TP = __shfl_sync(0xffffffffu, mine, keep - 1);
+    const double TP = top.slot(keep - 1);
     if (!(TP > kappa) && !complete) {   // the P best are not all known yet
         if (lane == 0) p2_emit(a.next, qrel, fmin(theta - lower, TP - 2.1 * eps), colx, tries + 1);
         return;
@@ -688,7 +709,7 @@ p2_resolve_kernel(const TB* __restrict__ xb, P2Resolve a) {
         if (s_estar == TP) atomicAdd(&a.dbg[kd + 3], 1ull);
     }
     warp_qs_topn_big(key, val, m, keep, posge[warp], hk[warp], hv[warp]);
-    if (lane < keep) { s_idx[warp][lane] = val[lane]; s_sim[warp][lane] = key[lane]; }
+    for (int j = lane; j < keep; j += 32) { s_idx[warp][j] = val[j]; s_sim[warp][j] = key[j]; }
     __syncwarp();
     if (lane == 0) {
         atomicAdd(&a.counters[CRX_CNT_TOPP_PASS2], 1ull);
@@ -747,8 +768,8 @@ __global__ void __launch_bounds__(128)
 p2u_select_kernel(const TQ* __restrict__ xq, int ldq, const TB* __restrict__ xb, P2Resolve a, P2Uniform u, int32_t* __restrict__ need,
                   int32_t* __restrict__ rlim_out, double* __restrict__ tp_out) {
     constexpr int QW = 4;
-    __shared__ int s_idx[QW][32];
-    __shared__ double s_sim[QW][32];
+    __shared__ int s_idx[QW][P2_MAXP];
+    __shared__ double s_sim[QW][P2_MAXP];
     __shared__ double s_pred[QW][128];
     __shared__ int s_coin[QW][128];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -766,8 +787,7 @@ p2u_select_kernel(const TQ* __restrict__ xq, int ldq, const TB* __restrict__ xb,
     const TQ* xq_row = xq + (size_t)qrow * ldq;
     const double FLOOR = 1.0 - 9.094947017729282e-13;   // 1 - 2^-40
     // ---- T_P over the candidates in M
-    double mine = -INFINITY, thr = -INFINITY;
-    int filled = 0;
+    WarpTop top;
     for (int base = 0; base < u.nm; base += 32) {
         const int j = base + lane;
         double k = -INFINITY;
@@ -777,23 +797,11 @@ p2u_select_kernel(const TQ* __restrict__ xq, int ldq, const TB* __restrict__ xb,
             cand = ((x - u.low) & ~x & u.high) != 0u;
             if (cand) k = p2u_sim<TQ, TB>(u, j, uq, rq, a.D, xq_row, xb, a.ldb);
         }
-        unsigned want = __ballot_sync(0xffffffffu, cand && k == k && (k > thr || filled < keep));
-        while (want) {
-            const int src = __ffs(want) - 1;
-            want &= want - 1;
-            const double x = __shfl_sync(0xffffffffu, k, src);
-            if (x > thr || filled < keep) {
-                const int pos = __popc(__ballot_sync(0xffffffffu, mine >= x));
-                const double up = __shfl_up_sync(0xffffffffu, mine, 1);
-                mine = lane < pos ? mine : (lane == pos ? x : up);
-                if (filled < keep) filled++;
-                thr = filled < keep ? -INFINITY : __shfl_sync(0xffffffffu, mine, keep - 1);
-            }
-        }
+        top.offer(k, cand, keep);
     }
-    if (filled < keep) return;
-    const double TP = __shfl_sync(0xffffffffu, mine, keep - 1);
-    const double best = __shfl_sync(0xffffffffu, mine, 0);
+    if (top.filled < keep) return;
+    const double TP = top.slot(keep - 1);
+    const double best = top.slot(0);
     if (!(TP >= FLOOR)) return;
     // ---- e* = the last candidate of M with similarity >= T_P (read from the back), which must carry T_P itself
     int je = -1;
@@ -861,8 +869,8 @@ p2u_sort_kernel(const TQ* __restrict__ xq, int ldq, const TB* __restrict__ xb, P
     __shared__ int posge[QW][128];
     __shared__ double hk[QW][128];
     __shared__ int hv[QW][128];
-    __shared__ int s_idx[QW][32];
-    __shared__ double s_sim[QW][32];
+    __shared__ int s_idx[QW][P2_MAXP];
+    __shared__ double s_sim[QW][P2_MAXP];
     __shared__ double s_pred[QW][128];
     __shared__ int s_coin[QW][128];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -891,7 +899,7 @@ p2u_sort_kernel(const TQ* __restrict__ xq, int ldq, const TB* __restrict__ xb, P
     }
     __syncwarp();
     warp_qs_topn_big(key, val, m, keep, posge[warp], hk[warp], hv[warp]);
-    if (lane < keep) { s_idx[warp][lane] = val[lane]; s_sim[warp][lane] = key[lane]; }
+    for (int j = lane; j < keep; j += 32) { s_idx[warp][j] = val[j]; s_sim[warp][j] = key[j]; }
     __syncwarp();
     if (lane == 0) {
         atomicAdd(&a.counters[CRX_CNT_TOPP_PASS2], 1ull);

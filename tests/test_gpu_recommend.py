@@ -73,7 +73,7 @@ def test_golden_rec_cluster(ctx, golden):
 
 
 @pytest.mark.parametrize("dtype", [np.float64, np.float32])
-@pytest.mark.parametrize("n,P_,Nrec,k,L", [(3000, 20, 5, 4, 5), (1200, 5, 2, 2, 3), (700, 32, 7, 6, 2), (65, 20, 5, 4, 5)])
+@pytest.mark.parametrize("n,P_,Nrec,k,L", [(3000, 20, 5, 4, 5), (1200, 5, 2, 2, 3), (700, 32, 7, 6, 2), (65, 20, 5, 4, 5), (1500, 50, 5, 4, 5), (900, 64, 3, 3, 4)])
 def test_rec_lsh_cosine_oracle(ctx, port, dtype, n, P_, Nrec, k, L):
     U, unk, mean = synth.rating_users(n, 100, seed=300 + n, dtype=dtype)
     P = ctx.points(U, unk, mean)
