@@ -786,6 +786,27 @@ __global__ void __launch_bounds__(32) warp_qs_kernel(double* sims, int32_t* ids,
     warp_qs_topn_big(sims, ids, n, need, posge, hk, hv);
 }
 
+// group id of an external query in one Euclidean table: the stored rows of its bucket are walked in insertion order; the
+// first one with the query's k-tuple of h values gives its group; `none` (= the number of groups: a key no stored row has, and
+// still a valid sort key) when no stored row shares the tuple
+__global__ void query_groups_kernel(const int32_t* __restrict__ qh, const int32_t* __restrict__ qb, int64_t nq, int k,
+                                    const int32_t* __restrict__ hvals, const int32_t* __restrict__ gid, const int32_t* __restrict__ perm,
+                                    const int32_t* __restrict__ off, int nbuckets, int none, int32_t* __restrict__ qgid) {
+    const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= nq) return;
+    const int b = qb[q];
+    int g = none;
+    if (b >= 0 && b < nbuckets) {
+        for (int pos = off[b]; pos < off[b + 1] && g == none; pos++) {
+            const int r = perm[pos];
+            bool same = true;
+            for (int j = 0; j < k; j++) same = same && hvals[(size_t)r * k + j] == qh[(size_t)q * k + j];
+            if (same) g = gid[r];
+        }
+    }
+    qgid[q] = g;
+}
+
 __global__ void fill_lists_kernel(double* s, int32_t* i, int32_t* nc, int64_t nq) {
     int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t < nq * LIST) { s[t] = -INFINITY; i[t] = -1; }
@@ -1130,7 +1151,6 @@ static int recommend_lsh_impl(crx_ctx* c, const crx_lsh* t, const crx_points* qu
     CRX_REQUIRE(P >= 1 && P <= P2_MAXP, "P must be in [1, 64]");
     CRX_REQUIRE(Nrec >= 0 && Nrec <= 128, "Nrec");
     if (recs) CRX_REQUIRE(base->mean && queries->unknown && queries->mean, "ratings metadata missing (crx_points_set_ratings)");
-    CRX_REQUIRE(self || t->metric == CRX_COSINE, "external queries are supported for cosine tables only in this round");
     CRX_NARROW(queries);
     CRX_CUDA(cudaSetDevice(c->device));
     int64_t nq = q_end - q_begin;
@@ -1145,7 +1165,22 @@ static int recommend_lsh_impl(crx_ctx* c, const crx_lsh* t, const crx_points* qu
     int64_t qstride = N;
     if (!self) {
         CRX_TRY(qgid_buf.alloc(c, (size_t)L * queries->n));
-        CRX_TRY(crx_hash_rows(c, queries, t->metric, t->k, L, t->d_proj, t->ldp, t->d_pnorm, t->d_t, t->d_r, t->w, t->nbuckets, nullptr, qgid_buf.p));
+        if (t->metric == CRX_COSINE) {
+            CRX_TRY(crx_hash_rows(c, queries, t->metric, t->k, L, t->d_proj, t->ldp, t->d_pnorm, t->d_t, t->d_r, t->w, t->nbuckets, nullptr, qgid_buf.p));
+        } else {
+            // Euclidean tables filter a bucket by the k-tuple of h values (cust_hashtable.hpp:81-97): an external query takes the
+            // group of any stored row of its bucket that has its tuple, or none
+            DevBuf<int32_t> qh, qb;
+            CRX_TRY(qh.alloc(c, (size_t)L * queries->n * t->k)); CRX_TRY(qb.alloc(c, (size_t)L * queries->n));
+            CRX_TRY(crx_hash_rows(c, queries, t->metric, t->k, L, t->d_proj, t->ldp, t->d_pnorm, t->d_t, t->d_r, t->w, t->nbuckets, qh.p, qb.p));
+            for (int l = 0; l < L; l++) {
+                CRX_KERNEL(c, "query_groups");
+                query_groups_kernel<<<crx_grid(queries->n, 128), 128, 0, c->stream>>>(qh.p + (size_t)l * queries->n * t->k, qb.p + (size_t)l * queries->n, queries->n, t->k,
+                    t->hvals + (size_t)l * N * t->k, t->gid + (size_t)l * N, t->by_bucket[l].perm, t->by_bucket[l].off, t->nbuckets, t->ngroups[l], qgid_buf.p + (size_t)l * queries->n);
+            }
+            CRX_CUDA(cudaGetLastError());
+            CRX_CUDA(cudaStreamSynchronize(c->stream));   // qh / qb are released on leaving this scope
+        }
         qgid_base = qgid_buf.p;
         qstride = queries->n;
     }
@@ -1286,7 +1321,7 @@ static int recommend_lsh_impl(crx_ctx* c, const crx_lsh* t, const crx_points* qu
             for (int l = 0; l < L; l++) {
                 // queries of the batch ordered by their group in table l
                 Segments qs;
-                int st = crx_build_segments(c, a.qgid[l] + q_begin, nq, std::max(1, t->ngroups[l]), &qs);
+                int st = crx_build_segments(c, a.qgid[l] + q_begin, nq, t->ngroups[l] + 1, &qs);   // + the "no group" key of external queries
                 if (st != CRX_OK) { qs.free_all(); return st; }
                 { CRX_KERNEL(c, "add_off"); add_off_kernel<<<crx_grid(nq, 256), 256, 0, c->stream>>>(qs.perm, nq, (int32_t)q_begin); }
                 a.pass = l; a.qperm = qs.perm; a.cperm = t->by_group[l].perm; a.csorted = t->by_group[l].sorted; a.load_state = l > 0;

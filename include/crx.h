@@ -221,7 +221,9 @@ int crx_cube_range_assignment_sharded(crx_ctx* ctx, const crx_points* input_vect
  *   neighbours = get_LSH_filtered_combined_buckets; sims = get_P_closest(neighbours, user, P);
  *   recs = get_top_N_recom(neighbours, user, Nrec, sims).
  * Outputs (rows relative to q_begin; any may be NULL): recs[nq][Nrec] (-1 when the reference prints
- * nothing), nbr_rows[nq][P] (-1 padded), nbr_sims[nq][P], ncand[nq]. */
+ * nothing), nbr_rows[nq][P] (-1 padded), nbr_sims[nq][P], ncand[nq].  P <= 64 for cosine tables whose L k-bit bucket
+ * ids pack into 32 bits (the tensor path), P <= 32 otherwise; every query carries the reference's own list (rows, order
+ * among equal similarities, similarity doubles). */
 int crx_recommend_lsh(crx_ctx* ctx, const crx_lsh* lsh_hashtables, const crx_points* queries, int64_t q_begin,
                       int64_t q_end, int P, int Nrec, int32_t* recs, int32_t* nbr_rows, double* nbr_sims,
                       int32_t* ncand, int mem);

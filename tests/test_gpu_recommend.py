@@ -164,6 +164,20 @@ def test_rec_B_external_queries(ctx, port):
     check_rec(ctx, out, ref)
 
 
+@pytest.mark.parametrize("k,L,div,w", [(4, 5, 100, 0.4), (2, 3, 10, 1.0)])
+def test_rec_B_external_queries_euclidean_tables(ctx, port, k, L, div, w):
+    """Users that are not stored in the tables against EUCLIDEAN tables: a query's candidates are the stored rows of its bucket
+    that share its k-tuple of h values (cust_hashtable.hpp:81-97); a tuple no stored row has gives no candidate."""
+    U, unk, mean = synth.rating_users(2200, 100, seed=21)
+    nb = 1400
+    V = ctx.points(U[:nb], unk[:nb], mean[:nb])
+    Q = ctx.points(U[nb:], unk[nb:], mean[nb:])
+    t = capi.LshTables(ctx, V, "euclidean", k, L, div, w, 909)
+    out = capi.recommend_lsh(ctx, t, 20, 3, queries=Q, want=WANT)
+    ref = port.recommend_lsh(U[:nb], unk[:nb], mean[:nb], EUCLIDEAN, k, L, div, w, 20, 3, 909, Xq=U[nb:], unknown_q=unk[nb:], mean_q=mean[nb:])
+    check_rec(ctx, out, ref)
+
+
 def test_rec_cluster_oracle(ctx, port):
     U, unk, mean = synth.rating_users(2000, 100, seed=13)
     P = ctx.points(U, unk, mean)
