@@ -45,7 +45,8 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--min-warmup", type=int, default=3, help="profiling runs only: allow fewer than 3 warm-up steps")
-    ap.add_argument("--only", default="", help="comma-separated blocks to run: c2,c2_normal,lloyd,kmeanspp,cube_range,pam,lloyd_100m (default: all)")
+    ap.add_argument("--only", default="", help="comma-separated blocks to run: c2,c2_normal,lloyd,kmeanspp,cube_range,pam,c1_main,lloyd_100m (default: all)")
+    ap.add_argument("--c1-users", type=int, default=6000, help="tweeting users of the c1_main block (the reference's own scale)")
     ap.add_argument("--cube-points", type=int, default=10_000_000)
     ap.add_argument("--pam-points", type=int, default=5_000_000)
     ap.add_argument("--kpp-k", type=int, default=1024, help="centroids drawn by the k-means++ block (C4: 1024)")
@@ -700,6 +701,44 @@ def bench_pam(rig, args):
     return out
 
 
+def bench_c1_main(rig, args):
+    """BASELINE config 1 (the reference's own run): the reference's UNCHANGED main.cpp, built once over its own headers
+    (oracle/_ref/recommendation_ref, CPU) and once over the drop-in headers + libcrx.so (oracle/_ref/recommendation_crx), on the
+    same synthetic input files (tools/make_main_inputs.py, 6000 tweeting users -> ~4.4k kept).  Stage times are the ones
+    main.cpp prints itself (main.cpp:181,227,271,375); the outputs must be identical."""
+    import shutil
+    import subprocess
+    import tempfile
+    ref_bin = os.path.join(ROOT, "oracle", "_ref", "recommendation_ref")
+    crx_bin = os.path.join(ROOT, "oracle", "_ref", "recommendation_crx")
+    if not (os.path.exists(ref_bin) and os.path.exists(crx_bin)):
+        return {"skipped": "oracle/_ref/recommendation_{ref,crx} not built (tools/build_main_dropin.sh needs the reference sources)"}
+    work = tempfile.mkdtemp(prefix="crx_c1_")
+    try:
+        subprocess.run([sys.executable, os.path.join(ROOT, "tools", "make_main_inputs.py"), work, "--users", str(args.c1_users)],
+                       check=True, stdout=subprocess.DEVNULL)
+        out = {"workload": "C1: main.cpp end to end, %d tweeting users x 100 coins, P=20, cosine LSH L=5 k=4 + two clustering stages" % args.c1_users,
+               "stages": ["cosine LSH real users (main.cpp:146-186)", "cosine LSH cluster users (:196-232)",
+                          "clustering recommendation A (:242-275)", "clustering recommendation B (:344-380)"]}
+        texts = {}
+        for tag, exe in (("reference_cpu", ref_bin), ("dropin_gpu", crx_bin)):
+            env = dict(os.environ, CRX_FAKE_SEED="5", CRX_DEVICE=str(rig.local_rank))
+            t0 = time.perf_counter()
+            subprocess.run([exe, "-d", "./tweets.tsv", "-o", "./out_%s.txt" % tag], cwd=work, env=env, check=True,
+                           stdout=subprocess.DEVNULL, timeout=900)
+            wall = time.perf_counter() - t0
+            lines = open(os.path.join(work, "out_%s.txt" % tag)).read().splitlines()
+            stage_ms = [int(l.split(":")[1]) for l in lines if l.startswith("Execution Time:")]
+            texts[tag] = [l for l in lines if not l.startswith("Execution Time:")]
+            out[tag] = {"stage_ms": stage_ms, "stages_total_ms": sum(stage_ms), "process_wall_ms": round(wall * 1e3)}
+        out["output_lines"] = len(texts["reference_cpu"])
+        out["outputs_identical"] = texts["reference_cpu"] == texts["dropin_gpu"]
+        out["speedup_stages_total"] = round(out["reference_cpu"]["stages_total_ms"] / max(1, out["dropin_gpu"]["stages_total_ms"]), 2)
+        return out
+    finally:
+        shutil.rmtree(work, ignore_errors=True)
+
+
 def run_crx(args):
     rig = Rig(args)
     torch = rig.torch
@@ -722,6 +761,8 @@ def run_crx(args):
     line["kmeanspp"] = guarded("kmeanspp", lambda: bench_kmeanspp(rig, args))
     line["cube_range"] = guarded("cube_range", lambda: bench_cube_range(rig, args))
     line["pam"] = guarded("pam", lambda: bench_pam(rig, args))
+    if rig.world == 1:
+        line["c1_main"] = guarded("c1_main", lambda: bench_c1_main(rig, args))
     if rig.world == 1 and args.lloyd_full > 0:
         line["lloyd_100m"] = guarded("lloyd_100m", lambda: bench_lloyd(rig, args, args.lloyd_full, "C4 whole config on ONE GPU"))
     if rig.rank == 0:

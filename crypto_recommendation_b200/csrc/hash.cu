@@ -660,6 +660,16 @@ __global__ void cube_vertex_kernel(const int32_t* __restrict__ hv, int64_t N, in
 // ------------------------------------------------------------------------------------------------
 // C ABI
 // ------------------------------------------------------------------------------------------------
+// bucket (or h-tuple group) of one stored row in every table and the extent [begin, end) of that bucket's member list
+struct BucketMeta { const int32_t* ids[16]; const int32_t* off[16]; int L; };
+__global__ void bucket_meta_kernel(BucketMeta m, int32_t* __restrict__ ext) {
+    int l = threadIdx.x;
+    if (l >= m.L) return;
+    int g = *m.ids[l];
+    ext[2 * l] = m.off[l][g];
+    ext[2 * l + 1] = m.off[l][g + 1];
+}
+
 extern "C" {
 
 int crx_get_num_hamming_dist_from(int num, int dist, int min_bit, int bits, int32_t* out, int cap) {
@@ -805,21 +815,33 @@ int crx_get_LSH_combined_buckets(const crx_lsh* t, int64_t q, int filtered, int3
     CRX_REQUIRE(q >= 0 && q < t->N, "query_row out of range");
     crx_ctx* c = t->ctx;
     CRX_CUDA(cudaSetDevice(c->device));
-    std::vector<int32_t> all;
+    // one kernel reads the query's bucket (or h-tuple group) of every table and that bucket's extent; one sync; then the L
+    // member lists come back in one more sync
+    BucketMeta m;
+    m.L = t->L;
+    for (int l = 0; l < t->L; l++) {
+        m.ids[l] = (filtered ? t->gid : t->bucket) + (size_t)l * t->N + q;
+        m.off[l] = (filtered ? t->by_group[l] : t->by_bucket[l]).off;
+    }
+    int32_t* d_ext = nullptr;
+    CRX_TRY(crx_alloc(c, &d_ext, 32));
+    bucket_meta_kernel<<<1, 32, 0, c->stream>>>(m, d_ext);
+    int32_t ext[32];
+    cudaError_t e = cudaMemcpyAsync(ext, d_ext, 2 * t->L * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    crx_free(c, d_ext);
+    CRX_CUDA(e);
+    size_t total = 0;
+    for (int l = 0; l < t->L; l++) total += (size_t)(ext[2 * l + 1] - ext[2 * l]);
+    std::vector<int32_t> all(total);
+    size_t base = 0;
     for (int l = 0; l < t->L; l++) {
         const Segments& s = filtered ? t->by_group[l] : t->by_bucket[l];
-        const int32_t* ids = (filtered ? t->gid : t->bucket) + (size_t)l * t->N;
-        int32_t g, off[2];
-        CRX_CUDA(cudaMemcpyAsync(&g, ids + q, sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
-        CRX_CUDA(cudaStreamSynchronize(c->stream));
-        CRX_CUDA(cudaMemcpyAsync(off, s.off + g, 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
-        CRX_CUDA(cudaStreamSynchronize(c->stream));
-        size_t base = all.size();
-        all.resize(base + (off[1] - off[0]));
-        if (off[1] > off[0])
-            CRX_CUDA(cudaMemcpyAsync(all.data() + base, s.perm + off[0], (size_t)(off[1] - off[0]) * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
-        CRX_CUDA(cudaStreamSynchronize(c->stream));
+        size_t len = (size_t)(ext[2 * l + 1] - ext[2 * l]);
+        if (len) CRX_CUDA(cudaMemcpyAsync(all.data() + base, s.perm + ext[2 * l], len * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+        base += len;
     }
+    CRX_CUDA(cudaStreamSynchronize(c->stream));
     std::sort(all.begin(), all.end());  // std::set<CustVector*> order = row order (lsh_cube.hpp:96,104)
     all.erase(std::unique(all.begin(), all.end()), all.end());
     *count = (int64_t)all.size();

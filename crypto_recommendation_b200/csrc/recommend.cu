@@ -700,7 +700,7 @@ rec_cluster_kernel(const TQ* __restrict__ xq, int ldq, const double* __restrict_
 // neighbour list (rows of `xb`, in the given order).  sims == NULL: similarities to all neighbours are computed
 // first (crypto_rec.hpp:331-333).  One warp.
 template <typename TQ, typename TB>
-__global__ void rec_list_kernel(const TQ* __restrict__ q, int D, double sqn_q, const uint8_t* __restrict__ unk_q, double mean_q,
+__global__ void rec_list_kernel(const TQ* __restrict__ q, int D, const double* __restrict__ sqn_q_p, const uint8_t* __restrict__ unk_q, const double* __restrict__ mean_q_p,
                                 const TB* __restrict__ xb, int ldb, const double* __restrict__ sqn_b, const double* __restrict__ mean_b,
                                 const int32_t* __restrict__ nbr, const double* __restrict__ sims_in, int n, int Nrec,
                                 double* __restrict__ predicted /* [D] or NULL */, int32_t* __restrict__ recs /* [Nrec] or NULL */) {
@@ -709,6 +709,7 @@ __global__ void rec_list_kernel(const TQ* __restrict__ q, int D, double sqn_q, c
     __shared__ double s_pred[128];
     __shared__ int s_coin[128];
     int lane = threadIdx.x & 31;
+    const double sqn_q = *sqn_q_p, mean_q = *mean_q_p;
     double main_sum[4] = {0, 0, 0, 0}, abs_sum = 0.0;
     for (int base = 0; base < n; base += 32) {
         int p = base + lane;
@@ -768,6 +769,17 @@ quicksort_kernel(double* sims, int32_t* ids, int n, int need, int in_smem) {
         lomuto_desc(sims, ids, n, need);
     }
 }
+// similarity of every listed neighbour to one user (crypto_rec.hpp:219-220): neighbors[i]->cosineSimilarity(&user), i.e. the
+// neighbour is the left operand of cust_vector.hpp:160-174
+template <typename TQ, typename TB>
+__global__ void list_sims_kernel(const TQ* __restrict__ q, const double* __restrict__ sqn_q, const TB* __restrict__ xb, int ldb,
+                                 const double* __restrict__ sqn_b, const int32_t* __restrict__ nbr, int64_t n, int D, double* __restrict__ sims) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int32_t r = nbr[i];
+    sims[i] = cos_sim_exact(xb + (int64_t)r * ldb, q, D, sqn_b[r], *sqn_q);
+}
+
 static int launch_quicksort(crx_ctx* c, double* d_sims, int32_t* d_ids, int n, int need) {
     size_t smem = (size_t)n * (sizeof(double) + sizeof(int32_t));
     int in_smem = smem <= 200 * 1024;
@@ -1438,21 +1450,30 @@ int crx_get_P_closest(crx_ctx* c, const crx_points* users, int32_t* neighbor_row
     CRX_REQUIRE(query_row >= 0 && query_row < query_set->n && n >= 0 && P >= 0, "argument range");
     *kept = std::min<int64_t>(n, P);
     if (n == 0) return CRX_OK;
-    std::vector<int32_t> qrows((size_t)n, (int32_t)query_row);
-    std::vector<double> sims((size_t)n);
-    // similarities (crypto_rec.hpp:219-220), then the literal co-sort (:223) on the device
-    CRX_TRY(crx_pair_op(c, users, neighbor_rows, query_set, qrows.data(), n, 3, sims.data()));
-    {   // only the first min(n, P) positions are consumed (crypto_rec.hpp:225-228): ranges beyond them are left unrefined
-        IoBuf<double> sb;
-        IoBuf<int32_t> ib;
-        CRX_TRY(sb.bind(c, sims.data(), (size_t)n, CRX_HOST, true));
-        CRX_TRY(ib.bind(c, neighbor_rows, (size_t)n, CRX_HOST, true));
-        CRX_TRY(launch_quicksort(c, sb.dev, ib.dev, (int)n, (int)*kept));
-        CRX_TRY(sb.flush());
-        CRX_TRY(ib.flush());
+    CRX_CUDA(cudaSetDevice(c->device));
+    // similarities (crypto_rec.hpp:219-220), then the literal co-sort (:223): both on the device, one upload of the rows, one
+    // download of the reordered rows and of the kept similarities, one synchronisation
+    IoBuf<int32_t> ib;
+    DevBuf<double> sims;
+    CRX_TRY(ib.bind(c, neighbor_rows, (size_t)n, CRX_HOST, true));
+    CRX_TRY(sims.alloc(c, (size_t)n));
+    {
+        CRX_KERNEL(c, "list_sims");
+        int grid = crx_grid(n, 128);
+#define LAUNCH_S(TQ, TB, xqp, xbp) \
+    list_sims_kernel<TQ, TB><<<grid, 128, 0, c->stream>>>(xqp + (size_t)query_row * query_set->ld, query_set->sqn + query_row, xbp, users->ld, \
+                                                          users->sqn, ib.dev, n, users->d, sims.p)
+        if (query_set->x64 && users->x64) LAUNCH_S(double, double, query_set->x64, users->x64);
+        else if (query_set->x64) LAUNCH_S(double, float, query_set->x64, users->x32);
+        else if (users->x64) LAUNCH_S(float, double, query_set->x32, users->x64);
+        else LAUNCH_S(float, float, query_set->x32, users->x32);
+#undef LAUNCH_S
+        CRX_CUDA(cudaGetLastError());
     }
-    for (int64_t i = 0; i < *kept; i++) similarities[i] = sims[i];
-    return CRX_OK;
+    // only the first min(n, P) positions are consumed (crypto_rec.hpp:225-228): ranges beyond them are left unrefined
+    CRX_TRY(launch_quicksort(c, sims.p, ib.dev, (int)n, (int)*kept));
+    if (*kept > 0) CRX_CUDA(cudaMemcpyAsync(similarities, sims.p, (size_t)*kept * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    return ib.flush();
 }
 
 int crx_get_top_N_recom(crx_ctx* c, const crx_points* users, const int32_t* neighbor_rows, const double* similarities,
@@ -1469,15 +1490,11 @@ int crx_get_top_N_recom(crx_ctx* c, const crx_points* users, const int32_t* neig
     CRX_TRY(sm.bind(c, similarities, (size_t)n, CRX_HOST, true));
     CRX_TRY(pr.bind(c, predicted, (size_t)D, CRX_HOST, false));
     CRX_TRY(out.bind(c, recs, (size_t)N, CRX_HOST, false));
-    double h_sq, h_mean;
-    CRX_CUDA(cudaMemcpyAsync(&h_sq, query_set->sqn + query_row, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
-    CRX_CUDA(cudaMemcpyAsync(&h_mean, query_set->mean + query_row, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
-    CRX_CUDA(cudaStreamSynchronize(c->stream));
     {
         CRX_KERNEL(c, "rec_list");
         const uint8_t* unk = query_set->unknown + (size_t)query_row * D;
 #define LAUNCH_L(TQ, TB, xqp, xbp) \
-    rec_list_kernel<TQ, TB><<<1, 32, 0, c->stream>>>(xqp + (size_t)query_row * query_set->ld, D, h_sq, unk, h_mean, xbp, users->ld, users->sqn, \
+    rec_list_kernel<TQ, TB><<<1, 32, 0, c->stream>>>(xqp + (size_t)query_row * query_set->ld, D, query_set->sqn + query_row, unk, query_set->mean + query_row, xbp, users->ld, users->sqn, \
                                                       users->mean, nb.dev, sm.dev, (int)n, N, pr.dev, out.dev)
         if (query_set->x64 && users->x64) LAUNCH_L(double, double, query_set->x64, users->x64);
         else if (query_set->x64) LAUNCH_L(double, float, query_set->x64, users->x32);
@@ -1486,8 +1503,8 @@ int crx_get_top_N_recom(crx_ctx* c, const crx_points* users, const int32_t* neig
 #undef LAUNCH_L
     }
     CRX_CUDA(cudaGetLastError());
-    CRX_TRY(pr.flush());
-    CRX_TRY(out.flush());
+    if (predicted) CRX_CUDA(cudaMemcpyAsync(predicted, pr.dev, (size_t)D * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    if (recs && N > 0) CRX_CUDA(cudaMemcpyAsync(recs, out.dev, (size_t)N * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
     CRX_CUDA(cudaStreamSynchronize(c->stream));
     return CRX_OK;
 }

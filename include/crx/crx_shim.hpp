@@ -49,6 +49,36 @@ inline uint64_t next_seed() {
     return (uint64_t)std::chrono::system_clock::now().time_since_epoch().count();
 }
 
+// CRX_SHIM_PROFILE=1: wall time and call count of each drop-in function, printed to stderr at exit (how
+// tools/time_main.sh explains where an unchanged main.cpp spends its time).
+struct ProfRow { const char* name; double ms; long calls; };
+inline std::vector<ProfRow>& prof_rows() { static std::vector<ProfRow>* r = new std::vector<ProfRow>(); return *r; }   // read by an atexit handler: never destroyed
+inline bool prof_on() {
+    static int on = -1;
+    if (on < 0) {
+        const char* e = std::getenv("CRX_SHIM_PROFILE");
+        on = e && e[0] == '1';
+        if (on) std::atexit([] { for (const ProfRow& r : prof_rows()) std::fprintf(stderr, "crx shim: %-34s %9.1f ms %8ld calls\n", r.name, r.ms, r.calls); });
+    }
+    return on == 1;
+}
+struct Timed {
+    const char* name;
+    std::chrono::steady_clock::time_point t0;
+    explicit Timed(const char* n) : name(prof_on() ? n : nullptr) { if (name) t0 = std::chrono::steady_clock::now(); }
+    ~Timed() {
+        if (!name) return;
+        double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+        for (ProfRow& r : prof_rows()) if (r.name == name) { r.ms += ms; r.calls++; return; }
+        prof_rows().push_back(ProfRow{name, ms, 1});
+    }
+};
+
+// Bumped by every CustVector member that can change (or hand out a way to change) the image the engine sees:
+// constructors, assignment, destructor, setters, getDimensions().  A cached result that was verified against the
+// content of its inputs stays valid while the counter has not moved and the same objects are passed again.
+inline unsigned long& content_epoch() { static unsigned long e = 1; return e; }
+
 inline int metric_code(const std::string& m) {
     if (m == "euclidean") return CRX_EUCLIDEAN;
     if (m == "cosine") return CRX_COSINE;
@@ -115,10 +145,15 @@ struct Registered {
     const char* end;
     size_t stride;
     crx_points* pts;   // built with the rating metadata
+    void* table_set;   // the crx::TableSet<T> that owns the registration (T: the element type `stride` belongs to)
 };
 inline std::vector<Registered>& registry() { static std::vector<Registered> r; return r; }
-inline void register_points(const void* base, size_t n, size_t stride, crx_points* pts) {
-    registry().push_back(Registered{(const char*)base, (const char*)base + n * stride, stride, pts});
+inline void register_points(const void* base, size_t n, size_t stride, crx_points* pts, void* table_set = nullptr) {
+    registry().push_back(Registered{(const char*)base, (const char*)base + n * stride, stride, pts, table_set});
+}
+inline void* table_set_of(const crx_points* pts) {
+    for (const Registered& reg : registry()) if (reg.pts == pts) return reg.table_set;
+    return nullptr;
 }
 inline void unregister_points(crx_points* pts) {
     auto& r = registry();

@@ -18,7 +18,7 @@ void pack_centroids(std::vector<CustVector<T> >& vecs, std::vector<CustVector<T>
     C.resize((size_t)K * D);
     rows.resize(K);
     for (int c = 0; c < K; c++) {
-        const std::vector<T>& d = *centroids[c]->getDimensions();
+        const std::vector<T>& d = centroids[c]->crxDimsRef();
         for (int j = 0; j < D; j++) C[(size_t)c * D + j] = (double)d[j];
         rows[c] = row_of(vecs, centroids[c]);
     }

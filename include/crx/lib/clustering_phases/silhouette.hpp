@@ -21,7 +21,7 @@ std::vector<double> silhouette_cluster(std::vector<std::vector<CustVector<vector
     int D = K ? (int)centroids[0]->getDimNumber() : 0;
     std::vector<double> C((size_t)K * D), sils((size_t)K + 1);
     for (int c = 0; c < K; c++) {
-        const std::vector<vector_type>& d = *centroids[c]->getDimensions();
+        const std::vector<vector_type>& d = centroids[c]->crxDimsRef();
         for (int j = 0; j < D; j++) C[(size_t)c * D + j] = (double)d[j];
     }
     crx::check(crx_silhouette_cluster(crx::context(), P.pts, labels.data(), CRX_HOST, C.data(), CRX_HOST, K, crx::metric_code(metric_type), sils.data()),

@@ -20,7 +20,7 @@ bool k_means(std::vector<CustVector<vector_type> >& input_vectors, std::vector<C
     for (size_t i = 0; i < input_vectors.size(); i++) labels[i] = input_vectors[i].getCluster();
     std::vector<double> oldc((size_t)K * D), newc((size_t)K * D);
     for (int c = 0; c < K; c++) {
-        const std::vector<vector_type>& d = *centers[c]->getDimensions();
+        const std::vector<vector_type>& d = centers[c]->crxDimsRef();
         for (int j = 0; j < D; j++) oldc[(size_t)c * D + j] = (double)d[j];
     }
     int cont = 0;

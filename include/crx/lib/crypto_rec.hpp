@@ -24,33 +24,77 @@
 #include "lsh_cube.hpp"
 
 namespace crx {
-// The neighbours and the user as rows of device point sets.  Fast path: the neighbours point into a vector a table set
-// has registered (create_LSH_hashtables) -- nothing but row numbers travels; the user is a row of the same set or a
-// one-row set of its own.  Otherwise neighbours + user are packed into one fresh set (rows 0..n-1, user = row n).
+// Device copies the per-user calls would otherwise upload again and again: the user as a one-row set with its rating
+// metadata (get_P_closest and get_top_N_recom are called one after the other for the same user), and a neighbour list
+// that is not part of a registered vector (the members of one cluster, main.cpp:367-372, passed once per user).  A copy
+// is reused only for the same objects and while crx::content_epoch() has not moved since it was packed, i.e. no
+// CustVector has been created, destroyed or written in between.
+template <typename T>
+struct DeviceCopies {
+    struct Entry {
+        std::vector<const void*> who;
+        unsigned long epoch = 0, stamp = 0;
+        Packed<T>* set = nullptr;
+    };
+    std::vector<Entry> entries;
+    unsigned long clock_ = 0;
+    explicit DeviceCopies(size_t slots) : entries(slots) {}
+    crx_points* get(CustVector<T>* const* ptrs, size_t n) {
+        Entry* victim = &entries[0];
+        for (Entry& e : entries) {
+            if (e.set && e.who.size() == n && std::memcmp(e.who.data(), ptrs, n * sizeof(void*)) == 0) {
+                if (e.epoch == content_epoch()) { e.stamp = ++clock_; return e.set->pts; }
+                victim = &e;   // same objects, possibly new content: packed again below
+                break;
+            }
+            if (e.stamp < victim->stamp) victim = &e;
+        }
+        delete victim->set;
+        victim->set = new Packed<T>();
+        victim->set->build((int64_t)n, [&](int64_t i) { return ptrs[i]; }, true);
+        victim->who.assign((const void* const*)ptrs, (const void* const*)ptrs + n);
+        victim->epoch = content_epoch();
+        victim->stamp = ++clock_;
+        return victim->set->pts;
+    }
+};
+template <typename T>
+inline DeviceCopies<T>& user_copies() { static DeviceCopies<T> c(8); return c; }
+template <typename T>
+inline DeviceCopies<T>& list_copies() { static DeviceCopies<T> c(32); return c; }
+
+// The neighbours and the user as rows of device point sets.  The neighbours point into a vector a table set has
+// registered (create_LSH_hashtables) -- nothing but row numbers travels -- or are a list kept by list_copies(); the
+// user is a row of the same registered set or a one-row set of its own.
 template <typename T>
 struct Resolved {
-    Packed<T> own;            // owns whatever had to be packed for this call
     crx_points* users = nullptr;
     crx_points* query_set = nullptr;
     int64_t query_row = 0;
+    bool packed = false;      // rows[] are positions in `neighbors`, not rows of a registered vector
     std::vector<int32_t> rows;
     Resolved(std::vector<CustVector<T>*>& neighbors, CustVector<T>& user) {
+        std::vector<CustVector<T>*> one(1, &user);
         users = registered_rows(neighbors, rows);
         if (users) {
-            std::vector<CustVector<T>*> one(1, &user);
             std::vector<int32_t> ur;
-            if (registered_rows(one, ur) == users) { query_set = users; query_row = ur[0]; }
-            else { own.from_pointers(one, true); query_set = own.pts; query_row = 0; }
-            return;
+            if (registered_rows(one, ur) == users) { query_set = users; query_row = ur[0]; return; }
+        } else {
+            packed = true;
+            if ((size_t)neighbors.size() * user.getDimNumber() <= ((size_t)1 << 22)) {
+                users = list_copies<T>().get(neighbors.data(), neighbors.size());
+            } else {   // too large to keep around: packed for this call only
+                big.from_pointers(neighbors, true);
+                users = big.pts;
+            }
+            rows.resize(neighbors.size());
+            for (size_t i = 0; i < rows.size(); i++) rows[i] = (int32_t)i;
         }
-        std::vector<CustVector<T>*> all(neighbors.begin(), neighbors.end());
-        all.push_back(&user);
-        own.from_pointers(all, true);
-        users = query_set = own.pts;
-        query_row = (int64_t)neighbors.size();
-        rows.resize(neighbors.size());
-        for (size_t i = 0; i < rows.size(); i++) rows[i] = (int32_t)i;
+        query_set = user_copies<T>().get(one.data(), 1);
+        query_row = 0;
     }
+private:
+    Packed<T> big;
 };
 }  // namespace crx
 
@@ -69,11 +113,45 @@ void parallel_quickSort(std::vector<dim_type>& sim, std::vector<type>& neighbors
     for (int i = 0; i < n; i++) { sim[low + i] = s2[i]; neighbors[low + i] = n2[i]; }
 }
 
+namespace crx {
+// The table set whose batched result (TableSet::batch_for) can answer a call about `user`: the user is a stored row of a
+// registered vector that a set of LSH tables was built over.  row receives its row number.
+template <typename T>
+inline TableSet<T>* batch_owner(CustVector<T>& user, int32_t& row) {
+    const char* q = (const char*)&user;
+    for (const Registered& reg : registry()) {
+        if (q < reg.begin || q >= reg.end || reg.stride != sizeof(CustVector<T>) || !reg.table_set) continue;
+        row = (int32_t)((q - reg.begin) / (ptrdiff_t)reg.stride);
+        return (TableSet<T>*)reg.table_set;
+    }
+    return nullptr;
+}
+}  // namespace crx
+
 // crypto_rec.hpp:214-231: sorts and truncates `neighbors`, returns the parallel similarities
 template <typename dim_type>
 std::vector<double> get_P_closest(std::vector<CustVector<dim_type>*>& neighbors, CustVector<dim_type>& user, int P) {
     int64_t n = (int64_t)neighbors.size();
     if (n == 0) return std::vector<double>();
+    crx::Timed timed("get_P_closest");
+    {
+        // the candidate list get_LSH_filtered_combined_buckets has just returned for this stored row: the batched call
+        // over all stored rows holds the answer (see TableSet)
+        int32_t row = -1;
+        crx::TableSet<dim_type>* set = crx::batch_owner(user, row);
+        if (set && set->last_row == row && (int64_t)set->last_list.size() == n && set->base && !set->base->empty()) {
+            CustVector<dim_type>* base = &(*set->base)[0];
+            bool same = true;
+            for (int64_t i = 0; i < n && same; i++) same = neighbors[i] == base + set->last_list[i];
+            if (same && set->batch_for(P) && set->b_ncand[row] == n) {
+                int64_t kept = std::min<int64_t>(n, P);
+                std::vector<CustVector<dim_type>*> sorted((size_t)kept);
+                for (int64_t i = 0; i < kept; i++) sorted[i] = base + set->b_rows[(size_t)row * P + i];
+                neighbors.swap(sorted);
+                return std::vector<double>(set->b_sims.begin() + (size_t)row * P, set->b_sims.begin() + (size_t)row * P + kept);
+            }
+        }
+    }
     crx::Resolved<dim_type> R(neighbors, user);
     // position -> neighbour, carried through the co-sort as the payload
     std::vector<int32_t> order(R.rows);
@@ -82,7 +160,7 @@ std::vector<double> get_P_closest(std::vector<CustVector<dim_type>*>& neighbors,
     crx::check(crx_get_P_closest(crx::context(), R.users, order.data(), n, R.query_set, R.query_row, P, buf.data(), &kept), "crx_get_P_closest");
     // rows -> pointers: rows are unique inside one call (a neighbour list holds every vector once)
     std::vector<CustVector<dim_type>*> sorted((size_t)kept);
-    if (R.own.pts == R.users) {
+    if (R.packed) {
         for (int64_t i = 0; i < kept; i++) sorted[i] = neighbors[order[i]];
     } else {
         const char* base = nullptr;
@@ -111,6 +189,22 @@ std::vector<dim_type> get_predicted_user_sim(std::vector<CustVector<dim_type>*>&
 // crypto_rec.hpp:310-324
 template <typename dim_type>
 std::vector<int> get_top_N_recom(std::vector<CustVector<dim_type>*>& neighbors, CustVector<dim_type>& user, int N, std::vector<double> similarities) {
+    crx::Timed timed("get_top_N_recom (similarities)");
+    {
+        // neighbours and similarities are the ones the batched call produced for this stored row: its coin order is the
+        // literal sort of the same predicted ratings, so the first N entries are this call's answer
+        int32_t row = -1;
+        crx::TableSet<dim_type>* set = crx::batch_owner(user, row);
+        int64_t n = (int64_t)neighbors.size();
+        if (set && set->batch_state == 1 && N >= 0 && N <= set->batch_nrec && n > 0 && n <= set->batch_P && (int64_t)similarities.size() == n &&
+            n == std::min<int64_t>(set->b_ncand[row], set->batch_P)) {
+            int P = set->batch_P;
+            CustVector<dim_type>* base = &(*set->base)[0];
+            bool same = std::memcmp(similarities.data(), &set->b_sims[(size_t)row * P], (size_t)n * sizeof(double)) == 0;
+            for (int64_t i = 0; i < n && same; i++) same = neighbors[i] == base + set->b_rows[(size_t)row * P + i];
+            if (same) return std::vector<int>(set->b_recs.begin() + (size_t)row * set->batch_nrec, set->b_recs.begin() + (size_t)row * set->batch_nrec + N);
+        }
+    }
     crx::Resolved<dim_type> R(neighbors, user);
     int64_t n = (int64_t)neighbors.size();
     std::vector<int32_t> recs(N);
@@ -133,6 +227,8 @@ struct ClusterRecs {
     std::vector<uint8_t> unk;
     std::vector<int32_t> recs;   // [n][N]
     unsigned long stamp = 0;
+    std::vector<const void*> who;   // the objects the image was last compared with ...
+    unsigned long epoch = 0;        // ... and crx::content_epoch() at that moment
 };
 inline uint64_t image_hash(const void* p, size_t bytes, uint64_t h) {
     const unsigned char* b = (const unsigned char*)p;
@@ -150,6 +246,15 @@ inline bool cached_cluster_recs(std::vector<CustVector<T>*>& neighbors, CustVect
     if (me < 0) return false;
     static std::vector<ClusterRecs> cache(64);
     static unsigned long clock_ = 0;
+    // the same objects as at the last full comparison and no CustVector has been created, destroyed or written since
+    // (crx::content_epoch): the image is what it was -- no need to pack and compare it again
+    for (ClusterRecs& e : cache) {
+        if (e.n != n || e.N != N || e.epoch != content_epoch() || e.who.size() != (size_t)n) continue;
+        if (std::memcmp(e.who.data(), neighbors.data(), (size_t)n * sizeof(void*)) != 0) continue;
+        e.stamp = ++clock_;
+        out.assign(e.recs.begin() + (size_t)me * N, e.recs.begin() + (size_t)(me + 1) * N);
+        return true;
+    }
     ClusterRecs probe;
     probe.n = n; probe.N = N;
     Packed<T>::pack_host(n, [&](int64_t i) { return neighbors[i]; }, true, probe.d, probe.buf, probe.unk, probe.mean);
@@ -160,6 +265,7 @@ inline bool cached_cluster_recs(std::vector<CustVector<T>*>& neighbors, CustVect
     for (ClusterRecs& e : cache) {
         if (e.n == n && e.N == N && e.d == probe.d && e.hash == probe.hash && e.buf == probe.buf && e.unk == probe.unk && e.mean == probe.mean) {
             e.stamp = ++clock_;
+            e.who.assign(neighbors.begin(), neighbors.end()); e.epoch = content_epoch();
             out.assign(e.recs.begin() + (size_t)me * N, e.recs.begin() + (size_t)(me + 1) * N);
             return true;
         }
@@ -171,6 +277,7 @@ inline bool cached_cluster_recs(std::vector<CustVector<T>*>& neighbors, CustVect
     probe.recs.assign((size_t)n * N, 0);
     check(crx_recommend_cluster(context(), set.pts, labels.data(), CRX_HOST, 1, nullptr, nullptr, N, probe.recs.data(), CRX_HOST), "crx_recommend_cluster");
     probe.stamp = ++clock_;
+    probe.who.assign(neighbors.begin(), neighbors.end()); probe.epoch = content_epoch();
     out.assign(probe.recs.begin() + (size_t)me * N, probe.recs.begin() + (size_t)(me + 1) * N);
     *victim = std::move(probe);
     return true;
@@ -180,6 +287,7 @@ inline bool cached_cluster_recs(std::vector<CustVector<T>*>& neighbors, CustVect
 // crypto_rec.hpp:328-345: similarities to ALL neighbours are computed first, no top-P cut
 template <typename dim_type>
 std::vector<int> get_top_N_recom(std::vector<CustVector<dim_type>*>& neighbors, CustVector<dim_type>& user, int N) {
+    crx::Timed timed("get_top_N_recom (no similarities)");
     {
         std::vector<int> cached;
         if (crx::cached_cluster_recs(neighbors, user, N, cached)) return cached;

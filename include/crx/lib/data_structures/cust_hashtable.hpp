@@ -22,6 +22,58 @@ struct TableSet {
     std::vector<int32_t> ids;   // [L][N] bucket / vertex of every stored row (lazily downloaded)
     std::vector<int32_t> det;   // [L][N][k] euclidean h tuples
     std::vector<std::vector<std::vector<int32_t> > > members;  // [L][bucket] rows in insertion order
+
+    // rows stored in bucket b[l] of every table l (euclidean tables with `tuples`: only those stored with the same k-tuple
+    // of h values, cust_hashtable.hpp:81-97), each once, ascending: the std::set<CustVector*> order of lsh_cube.hpp:96,104
+    std::vector<uint64_t> seen_bits;
+    void union_rows(const int32_t* b, const int32_t* tuples, std::vector<int32_t>& rows) {
+        load();
+        int64_t N = n();
+        seen_bits.assign((size_t)(N + 63) / 64, 0);
+        for (int l = 0; l < L; l++) {
+            if (b[l] < 0 || b[l] >= (int32_t)members[l].size()) continue;
+            for (int32_t r : members[l][b[l]]) {
+                if (tuples) {
+                    const int32_t* t = &det[((size_t)l * N + r) * k];
+                    bool same = true;
+                    for (int j = 0; j < k; j++) if (t[j] != tuples[(size_t)l * k + j]) { same = false; break; }
+                    if (!same) continue;
+                }
+                seen_bits[(size_t)r >> 6] |= 1ull << (r & 63);
+            }
+        }
+        rows.clear();
+        for (size_t w = 0; w < seen_bits.size(); w++)
+            for (uint64_t m = seen_bits[w]; m; m &= m - 1) rows.push_back((int32_t)(w * 64 + (size_t)__builtin_ctzll(m)));
+    }
+
+    // ---- the recommendation loop over the stored rows (main.cpp:159-170), answered from ONE batched engine call ----
+    // get_LSH_filtered_combined_buckets remembers the candidate list it returned for a stored row; when get_P_closest is
+    // then called with exactly that list, that row as the user and the second such call has been seen, crx_recommend_lsh
+    // is run once for every stored row (neighbour rows, similarities, the full literal order of the predicted coins) and
+    // this and the following calls are answered from its output.  The engine sees the rows as they were when the tables
+    // were built -- the same snapshot the per-user calls on registered rows use.
+    int32_t last_row = -1;               // stored row of the last combined-bucket query (filtered, all tables)
+    std::vector<int32_t> last_list;      // the rows it returned
+    int batch_P = -1, batch_nrec = 0, batch_state = 0;   // 0 not built, 1 ready, -1 not available for this table set / P
+    int batch_wanted = 0;                // qualifying get_P_closest calls seen so far
+    std::vector<int32_t> b_rows, b_recs, b_ncand;   // [n][P], [n][nrec], [n]
+    std::vector<double> b_sims;                      // [n][P]
+    bool batch_for(int P) {
+        if (batch_state == 1 && batch_P == P) return true;
+        if (batch_state == -1 && batch_P == P) return false;
+        if (!lsh || ++batch_wanted < 2) return false;
+        Timed timed("batched crx_recommend_lsh");
+        int64_t N = n();
+        int nrec = std::min(pts.d, 128);
+        // a few hundred MB of host results at most; larger tables keep the per-user calls
+        if (P <= 0 || N <= 0 || (double)N * (P * 12.0 + nrec * 4.0) > 512e6) { batch_state = -1; batch_P = P; return false; }
+        b_rows.assign((size_t)N * P, -1); b_sims.assign((size_t)N * P, 0.0); b_recs.assign((size_t)N * nrec, 0); b_ncand.assign((size_t)N, 0);
+        int st = crx_recommend_lsh(context(), lsh, nullptr, 0, N, P, nrec, b_recs.data(), b_rows.data(), b_sims.data(), b_ncand.data(), CRX_HOST);
+        batch_P = P; batch_nrec = nrec;
+        batch_state = st == CRX_OK ? 1 : -1;   // outside the batched call's limits (P, D): the per-user calls answer
+        return batch_state == 1;
+    }
     ~TableSet() {
         if (pts.pts) unregister_points(pts.pts);
         if (lsh) crx_lsh_destroy(lsh);
@@ -81,7 +133,7 @@ public:
             std::fprintf(stderr, "crx: hypercube queries must be stored rows (the reference's EuclideanFGen draws from a dead engine otherwise)\n");
             std::abort();
         }
-        std::vector<double> x(q->getDimensions()->begin(), q->getDimensions()->end());
+        std::vector<double> x(q->crxDimsRef().begin(), q->crxDimsRef().end());
         std::vector<int32_t> b(set->L), d((size_t)set->L * set->k);
         crx::check(crx_lsh_hash_vector(set->lsh, x.data(), b.data(), set->metric == CRX_EUCLIDEAN ? d.data() : nullptr), "crx_lsh_hash_vector");
         *bucket = b[table];

@@ -37,6 +37,64 @@ inline crx_points* one_row_points(const void* key, const std::vector<double>& di
     victim->key = key; victim->dims = dims; victim->stamp = ++clock_;
     return victim->pts;
 }
+
+// The same loops call ONE left operand against a recurring family of right operands (a user against every centroid).
+// The right operands seen lately are kept as rows of one device set; when a new left operand meets one of them, the
+// operation is evaluated against the whole family in one engine call (crx_pair_op with m pairs; every pair is computed
+// exactly as a single-pair call computes it) and the following calls of that left operand are answered from the result.
+// An answer is handed out only after the coordinates of both operands were compared with what it was computed from.
+struct PairFan {
+    static const int MAXB = 256;
+    struct B { const void* key; std::vector<double> dims; unsigned long stamp; };
+    std::vector<B> family;            // right operands, most of them recurring
+    bool family_dirty = true;         // device set out of date
+    crx_points* family_pts = nullptr;
+    int family_d = 0;
+    unsigned long clock_ = 0;
+    // the last fan-out
+    const void* a_key = nullptr;
+    std::vector<double> a_dims;
+    int op = -1;
+    std::vector<double> out;          // [family.size()] at the time of the call
+    bool valid = false;
+
+    int find(const void* key, const std::vector<double>& dims) {
+        for (size_t i = 0; i < family.size(); i++) if (family[i].key == key && family[i].dims == dims) return (int)i;
+        return -1;
+    }
+    void remember(const void* key, const std::vector<double>& dims) {
+        for (B& b : family) if (b.key == key) { b.dims = dims; b.stamp = ++clock_; family_dirty = true; valid = false; return; }
+        if ((int)family.size() < MAXB) family.push_back(B{key, dims, ++clock_});
+        else {
+            B* victim = &family[0];
+            for (B& b : family) if (b.stamp < victim->stamp) victim = &b;
+            *victim = B{key, dims, ++clock_};
+        }
+        family_dirty = true; valid = false;
+    }
+    // distances of `a` to every family member of its dimension; false when there is nothing to fan out to
+    bool fan(const void* key, const std::vector<double>& a, int which_op) {
+        int d = (int)a.size();
+        std::vector<int32_t> rows_b;
+        for (size_t i = 0; i < family.size(); i++) if ((int)family[i].dims.size() == d) rows_b.push_back((int32_t)i);
+        if (rows_b.size() < 2 || rows_b.size() != family.size()) return false;
+        if (family_dirty || family_d != d) {
+            if (family_pts) crx_points_destroy(family_pts);
+            family_pts = nullptr;
+            std::vector<double> buf(family.size() * (size_t)d);
+            for (size_t i = 0; i < family.size(); i++) std::copy(family[i].dims.begin(), family[i].dims.end(), buf.begin() + i * (size_t)d);
+            check(crx_points_create(context(), buf.data(), CRX_F64, (int64_t)family.size(), d, CRX_HOST, &family_pts), "crx_points_create");
+            family_dirty = false; family_d = d;
+        }
+        crx_points* pa = one_row_points(key, a);
+        std::vector<int32_t> rows_a(rows_b.size(), 0);
+        out.assign(rows_b.size(), 0.0);
+        check(crx_pair_op(context(), pa, rows_a.data(), family_pts, rows_b.data(), (int64_t)rows_b.size(), which_op, out.data()), "crx_pair_op");
+        a_key = key; a_dims = a; op = which_op; valid = true;
+        return true;
+    }
+};
+inline PairFan& pair_fan() { static PairFan f; return f; }
 }  // namespace crx
 
 template <typename dim_type>
@@ -51,10 +109,22 @@ private:
 
     template <typename in_dim_type>
     double pair_op(CustVector<in_dim_type>* other, int op) {
-        std::vector<in_dim_type>* od = other->getDimensions();
+        const std::vector<in_dim_type>* od = &other->crxDimsRef();
         int d = (int)dimensions.size();
         std::vector<double> a(dimensions.begin(), dimensions.end()), b(od->begin(), od->end());
         (void)d;
+        crx::Timed timed("CustVector pair operation");
+        if (a.size() == b.size()) {
+            crx::PairFan& f = crx::pair_fan();
+            int at = f.find(other, b);
+            if (at >= 0) {
+                f.family[at].stamp = ++f.clock_;
+                if (!(f.valid && f.a_key == (const void*)this && f.op == op && f.a_dims == a)) f.fan(this, a, op);
+                if (f.valid && f.a_key == (const void*)this && f.op == op && f.a_dims == a) return f.out[at];
+            } else {
+                f.remember(other, b);
+            }
+        }
         crx_points* pa = crx::one_row_points(this, a);
         crx_points* pb = crx::one_row_points(other, b);   // (both stay valid: the cache holds 64 entries)
         int32_t zero = 0;
@@ -64,20 +134,36 @@ private:
     }
 
 public:
+    // every member that creates, destroys or can alter the coordinates / unknown set / mean moves crx::content_epoch()
     CustVector(std::string in_id, std::vector<dim_type> dim_vector)
-        : id(std::move(in_id)), dimensions(std::move(dim_vector)), known_mean(0), cluster_i(-1), dist_from_centroid(0) {}
+        : id(std::move(in_id)), dimensions(std::move(dim_vector)), known_mean(0), cluster_i(-1), dist_from_centroid(0) { crx::content_epoch()++; }
     CustVector(std::string in_id, std::vector<dim_type> dim_vector, std::set<int> indexes, double mean)
         : id(std::move(in_id)), dimensions(std::move(dim_vector)), unknown_indexes(std::move(indexes)), known_mean(mean),
-          cluster_i(-1), dist_from_centroid(0) {}
+          cluster_i(-1), dist_from_centroid(0) { crx::content_epoch()++; }
     CustVector(std::string in_id, std::vector<dim_type> dim_vector, int cluster, double distance)
-        : id(std::move(in_id)), dimensions(std::move(dim_vector)), known_mean(0), cluster_i(cluster), dist_from_centroid(distance) {}
-    CustVector(const CustVector& o) = default;
-    CustVector& operator=(const CustVector& o) = default;
+        : id(std::move(in_id)), dimensions(std::move(dim_vector)), known_mean(0), cluster_i(cluster), dist_from_centroid(distance) { crx::content_epoch()++; }
+    CustVector(const CustVector& o)
+        : id(o.id), dimensions(o.dimensions), unknown_indexes(o.unknown_indexes), known_mean(o.known_mean), cluster_i(o.cluster_i),
+          dist_from_centroid(o.dist_from_centroid) { crx::content_epoch()++; }
+    CustVector(CustVector&& o) noexcept
+        : id(std::move(o.id)), dimensions(std::move(o.dimensions)), unknown_indexes(std::move(o.unknown_indexes)), known_mean(o.known_mean),
+          cluster_i(o.cluster_i), dist_from_centroid(o.dist_from_centroid) { crx::content_epoch()++; }
+    CustVector& operator=(const CustVector& o) {
+        id = o.id; dimensions = o.dimensions; unknown_indexes = o.unknown_indexes; known_mean = o.known_mean; cluster_i = o.cluster_i;
+        dist_from_centroid = o.dist_from_centroid; crx::content_epoch()++;
+        return *this;
+    }
+    CustVector& operator=(CustVector&& o) noexcept {
+        id = std::move(o.id); dimensions = std::move(o.dimensions); unknown_indexes = std::move(o.unknown_indexes); known_mean = o.known_mean;
+        cluster_i = o.cluster_i; dist_from_centroid = o.dist_from_centroid; crx::content_epoch()++;
+        return *this;
+    }
+    ~CustVector() { crx::content_epoch()++; }
 
     // cust_vector.hpp:107-121.  Dimension mismatch prints and returns -1 like the reference.
     template <typename in_dim_type>
     long double inner_product(CustVector<in_dim_type>* inVector, long double strt) {
-        if (dimensions.size() != inVector->getDimensions()->size()) {
+        if (dimensions.size() != inVector->crxDimsRef().size()) {
             std::cerr << id << " : Error in inner product with " << inVector->getId() << ". Different number of dimensions" << std::endl;
             return -1;
         }
@@ -93,21 +179,23 @@ public:
     // container updates (cust_vector.hpp:179-194); the engine computes cluster means itself (crx_k_means)
     template <typename in_dim_type>
     void addVectorToThis(CustVector<in_dim_type>* inVector) {
-        std::vector<in_dim_type>& in = *inVector->getDimensions();
+        crx::content_epoch()++;
+        const std::vector<in_dim_type>& in = inVector->crxDimsRef();
         for (size_t i = 0; i < dimensions.size(); i++) dimensions[i] = dimensions[i] + in[i];
     }
     void divDimensionsByD(double div_const) {
+        crx::content_epoch()++;
         if (div_const != 0)
             for (size_t i = 0; i < dimensions.size(); i++) dimensions[i] = dimensions[i] / div_const;
     }
 
     void setCluster(int index, double dist) { cluster_i = index; dist_from_centroid = dist; }
     void resetCluster() { cluster_i = -1; dist_from_centroid = 0; }
-    void setKnownMean(double in_mean) { known_mean = in_mean; }
-    void setUnknownIndexes(std::set<int> in_indexes) { unknown_indexes = std::move(in_indexes); }
+    void setKnownMean(double in_mean) { known_mean = in_mean; crx::content_epoch()++; }
+    void setUnknownIndexes(std::set<int> in_indexes) { unknown_indexes = std::move(in_indexes); crx::content_epoch()++; }
 
     std::string getId() { return id; }
-    std::vector<dim_type>* getDimensions() { return &dimensions; }
+    std::vector<dim_type>* getDimensions() { crx::content_epoch()++; return &dimensions; }   // hands out write access
     std::vector<int> getUnknownIndexes() { return std::vector<int>(unknown_indexes.begin(), unknown_indexes.end()); }
     std::set<int> getUnknownIndexesSet() { return unknown_indexes; }
     // not in the reference: read-only views for the packing code of the drop-in headers (the getters above copy, as the

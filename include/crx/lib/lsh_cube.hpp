@@ -21,7 +21,7 @@ std::vector<CustHashtable<vector_type>*> create_LSH_hashtables(std::vector<CustV
     set->k = k;
     set->L = L;
     set->pts.from_vector(input_vectors, true);   // with the rating metadata: the recommendation calls reuse these rows
-    if (!input_vectors.empty()) crx::register_points(&input_vectors[0], input_vectors.size(), sizeof(CustVector<vector_type>), set->pts.pts);
+    if (!input_vectors.empty()) crx::register_points(&input_vectors[0], input_vectors.size(), sizeof(CustVector<vector_type>), set->pts.pts, set.get());
     crx::check(crx_create_LSH_hashtables(crx::context(), set->pts.pts, set->metric, k, L, lsh_bucket_div, euclidean_h_w, crx::next_seed(), &set->lsh),
                "crx_create_LSH_hashtables");
     std::vector<CustHashtable<vector_type>*> tables;
@@ -37,26 +37,33 @@ std::vector<CustVector<T>*> combined(std::vector<CustHashtable<T>*>& tables, Cus
     if (tables.empty()) return out;
     auto& set = tables[0]->set;
     int32_t row = row_of(*set->base, q);
-    if (row >= 0 && (int)tables.size() == set->L) {  // stored query, all tables: one engine call
-        std::vector<int32_t> rows((size_t)set->n());
-        int64_t count = 0;
-        check(crx_get_LSH_combined_buckets(set->lsh, row, filtered ? 1 : 0, rows.data(), (int64_t)rows.size(), &count), "crx_get_LSH_combined_buckets");
-        for (int64_t i = 0; i < count; i++) out.push_back(&(*set->base)[rows[i]]);
+    if ((int)tables.size() == set->L && set->lsh && set->base && !set->base->empty()) {
+        // all tables of the set.  The bucket ids (and h tuples) of the stored rows were computed by the engine when the tables
+        // were built and are mirrored on the host once (TableSet::load); a vector that is not stored is hashed for every
+        // table in ONE engine call.  What is left is the reference's own bookkeeping: the union of L member lists.
+        Timed timed(row >= 0 ? "combined buckets (stored row)" : "combined buckets (other vector)");
+        set->load();
+        int64_t N = set->n();
+        const bool tuples = filtered && set->metric == CRX_EUCLIDEAN;
+        std::vector<int32_t> b(set->L), d(tuples || row < 0 ? (size_t)set->L * set->k : 0);
+        if (row >= 0) {
+            for (int l = 0; l < set->L; l++) {
+                b[l] = set->ids[(size_t)l * N + row];
+                if (tuples) std::copy(&set->det[((size_t)l * N + row) * set->k], &set->det[((size_t)l * N + row) * set->k] + set->k, d.begin() + (size_t)l * set->k);
+            }
+        } else {
+            std::vector<double> x(q->crxDimsRef().begin(), q->crxDimsRef().end());
+            check(crx_lsh_hash_vector(set->lsh, x.data(), b.data(), set->metric == CRX_EUCLIDEAN ? d.data() : nullptr), "crx_lsh_hash_vector");
+        }
+        std::vector<int32_t> rows;
+        set->union_rows(b.data(), tuples ? d.data() : nullptr, rows);
+        CustVector<T>* base = &(*set->base)[0];
+        out.reserve(rows.size());
+        for (int32_t r : rows) out.push_back(base + r);
+        if (filtered && row >= 0) { set->last_row = row; set->last_list.swap(rows); }
         return out;
     }
     std::set<CustVector<T>*> u;  // pointer order == row order (lsh_cube.hpp:96,104)
-    if (row < 0 && set->lsh) {
-        // a vector that is not stored: ONE engine call hashes it for every table of the set
-        set->load();
-        std::vector<double> x(q->getDimensions()->begin(), q->getDimensions()->end());
-        std::vector<int32_t> b(set->L), d((size_t)set->L * set->k);
-        check(crx_lsh_hash_vector(set->lsh, x.data(), b.data(), set->metric == CRX_EUCLIDEAN ? d.data() : nullptr), "crx_lsh_hash_vector");
-        for (auto t : tables) {
-            std::vector<CustVector<T>*> m = t->membersOf(b[t->table], filtered && set->metric == CRX_EUCLIDEAN ? &d[(size_t)t->table * set->k] : nullptr);
-            u.insert(m.begin(), m.end());
-        }
-        return std::vector<CustVector<T>*>(u.begin(), u.end());
-    }
     for (auto t : tables) {
         std::vector<CustVector<T>*> b = filtered ? t->getFilteredBucketFor(q) : t->getBucketFor(q);
         u.insert(b.begin(), b.end());
