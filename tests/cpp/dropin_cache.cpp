@@ -1,0 +1,162 @@
+// dropin_cache.cpp -- the drop-in headers remember results behind the reference's per-user signatures:
+// the batched answer of the stored-user loop, the fan-out of one user's distances over recurring centroids, device copies
+// of users and explicit neighbour lists.  Every remembered answer must be the one a cold call gives, and a change of an
+// input (through a setter, getDimensions(), a new object at an old address) must be seen.  Prints "OK" or the first mismatch.
+#include <cstdio>
+#include <cstdlib>
+#include <random>
+#include <set>
+#include <string>
+#include <vector>
+
+#include "lib/data_structures/cust_vector.hpp"
+#include "lib/data_structures/cust_hashtable.hpp"
+#include "lib/lsh_cube.hpp"
+#include "lib/crypto_rec.hpp"
+
+typedef CustVector<double> Vec;
+
+static int g_bad = 0;
+#define EXPECT(cond, ...) do { if (!(cond)) { if (!g_bad) { std::printf("MISMATCH %s:%d: ", __FILE__, __LINE__); std::printf(__VA_ARGS__); std::printf("\n"); } g_bad++; } } while (0)
+
+// rating-like users: a few known coins with small integer scores, the rest = mean (ties and equal similarities abound)
+static std::vector<Vec> make_users(int n, int d, unsigned seed) {
+    std::mt19937 g(seed);
+    std::vector<Vec> out;
+    for (int u = 0; u < n; u++) {
+        std::vector<double> x(d, 0.0);
+        std::set<int> unknown;
+        int known = 1 + (int)(g() % 6);
+        std::set<int> kn;
+        while ((int)kn.size() < known) kn.insert((int)(g() % d));
+        double total = 0;
+        for (int c : kn) { x[c] = (double)((int)(g() % 9) - 3) * 0.5 + 0.25 * (double)(g() % 3); total += x[c]; }
+        double mean = total / known;
+        bool all_zero = true;
+        for (int c : kn) if (x[c] != 0) all_zero = false;
+        if (all_zero) { x[*kn.begin()] = 1.0; mean = 1.0 / known; }
+        for (int c = 0; c < d; c++) if (!kn.count(c)) { x[c] = mean; unknown.insert(c); }
+        out.emplace_back(Vec(std::to_string(u), x, unknown, mean));
+    }
+    return out;
+}
+
+// a copy of every argument at fresh addresses: nothing the headers remembered can apply to it
+struct Cold {
+    std::vector<Vec> store;
+    std::vector<Vec*> ptrs;
+    Vec user;
+    Cold(const std::vector<Vec*>& neighbors, Vec& u) : user(u) {
+        store.reserve(neighbors.size());
+        for (Vec* v : neighbors) store.emplace_back(*v);
+        for (Vec& v : store) ptrs.push_back(&v);
+    }
+};
+
+int main() {
+    crx::set_seed(12345);
+    const int D = 40;
+
+    // ---- 1. one user against recurring centroids (main.cpp:353-366) ----
+    {
+        std::vector<Vec> users = make_users(6, D, 1), cents = make_users(11, D, 2);
+        std::vector<std::vector<double> > first(users.size(), std::vector<double>(cents.size()));
+        for (size_t u = 0; u < users.size(); u++)
+            for (size_t c = 0; c < cents.size(); c++) first[u][c] = users[u].euclideanDistance(&cents[c]);   // user 0: single calls; later users: fan-out
+        for (size_t u = 0; u < users.size(); u++)
+            for (size_t c = 0; c < cents.size(); c++) {
+                Vec a(users[u]), b(cents[c]);   // fresh addresses: cold single-pair call
+                double cold = a.euclideanDistance(&b);
+                EXPECT(cold == first[u][c], "fan-out distance user %zu centroid %zu: %.17g vs cold %.17g", u, c, first[u][c], cold);
+                EXPECT(users[u].cosineSimilarity(&cents[c]) == a.cosineSimilarity(&b), "cosine similarity user %zu centroid %zu", u, c);
+            }
+        // a centroid changes through getDimensions(): the next loop must see it
+        (*cents[3].getDimensions())[5] += 2.5;
+        for (size_t u = 0; u < users.size(); u++)
+            for (size_t c = 0; c < cents.size(); c++) {
+                double warm = users[u].euclideanDistance(&cents[c]);
+                Vec a(users[u]), b(cents[c]);
+                EXPECT(warm == a.euclideanDistance(&b), "after an edit: user %zu centroid %zu", u, c);
+                if (c == 3) EXPECT(warm != first[u][c], "edit of centroid 3 not seen by user %zu", u);
+            }
+        // a user changes between two of its own calls
+        double before = users[2].euclideanDistance(&cents[0]);
+        (*users[2].getDimensions())[0] += 1.0;
+        double after = users[2].euclideanDistance(&cents[0]);
+        Vec a(users[2]), b(cents[0]);
+        EXPECT(after == a.euclideanDistance(&b) && after != before, "edit of the left operand not seen");
+    }
+
+    // ---- 2. explicit neighbour lists (main.cpp:260-269, 367-372) ----
+    {
+        std::vector<Vec> members = make_users(60, D, 3), outsiders = make_users(5, D, 4);
+        std::vector<Vec*> list;
+        for (Vec& v : members) list.push_back(&v);
+        for (int round = 0; round < 2; round++) {
+            for (Vec& u : outsiders) {   // not a member: per-user call against the remembered device copy of the list
+                std::vector<int> warm = get_top_N_recom(list, u, 5);
+                Cold cold(list, u);
+                EXPECT(warm == get_top_N_recom(cold.ptrs, cold.user, 5), "outsider %s round %d", u.getId().c_str(), round);
+            }
+            for (Vec& u : members) {     // a member: answered from one call for the whole list
+                std::vector<int> warm = get_top_N_recom(list, u, 5);
+                Cold cold(list, u);
+                std::vector<Vec*> one_by_one(cold.ptrs);
+                EXPECT(warm == get_top_N_recom(one_by_one, cold.user, 5), "member %s round %d", u.getId().c_str(), round);
+            }
+            // between the rounds one neighbour's mean and one coordinate change
+            members[7].setKnownMean(members[7].getKnownMean() + 0.75);
+            (*members[11].getDimensions())[3] -= 1.25;
+        }
+    }
+
+    // ---- 3. the stored-user loop (main.cpp:159-170): batched answer == per-user answer ----
+    {
+        const int P = 20;
+        std::vector<Vec> users = make_users(700, D, 5);
+        std::vector<CustHashtable<double>*> tables = create_LSH_hashtables<double>(users, "cosine", 3, 4, 100, 0.4);
+        struct Ans { std::vector<std::string> ids; std::vector<double> sims; std::vector<int> recs; };
+        std::vector<Ans> per_user(users.size()), batched(users.size());
+        // per-user path: the list is passed as a copy at the time another row was the last combined-bucket query
+        for (size_t u = 0; u < users.size(); u++) {
+            std::vector<Vec*> nb = get_LSH_filtered_combined_buckets(tables, &users[u]);
+            get_LSH_filtered_combined_buckets(tables, &users[(u + 1) % users.size()]);
+            if (nb.empty()) continue;
+            per_user[u].sims = get_P_closest(nb, users[u], P);
+            for (Vec* v : nb) per_user[u].ids.push_back(v->getId());
+            per_user[u].recs = get_top_N_recom(nb, users[u], 2, per_user[u].sims);
+        }
+        for (size_t u = 0; u < users.size(); u++) {   // main.cpp's own order of calls: the second user triggers the batch
+            std::vector<Vec*> nb = get_LSH_filtered_combined_buckets(tables, &users[u]);
+            if (nb.empty()) continue;
+            batched[u].sims = get_P_closest(nb, users[u], P);
+            for (Vec* v : nb) batched[u].ids.push_back(v->getId());
+            batched[u].recs = get_top_N_recom(nb, users[u], 2, batched[u].sims);
+        }
+        EXPECT(tables[0]->set->batch_state == 1, "the batched call did not run (state %d)", tables[0]->set->batch_state);
+        for (size_t u = 0; u < users.size(); u++) {
+            EXPECT(per_user[u].ids == batched[u].ids, "neighbours of user %zu", u);
+            EXPECT(per_user[u].sims == batched[u].sims, "similarities of user %zu", u);
+            EXPECT(per_user[u].recs == batched[u].recs, "coins of user %zu", u);
+        }
+        // a user that is not a table row, twice in a row and after an edit (main.cpp:205-216)
+        std::vector<Vec> others = make_users(8, D, 6);
+        for (int round = 0; round < 2; round++) {
+            for (Vec& u : others) {
+                std::vector<Vec*> nb = get_LSH_filtered_combined_buckets(tables, &u);
+                if (nb.empty()) continue;
+                std::vector<Vec*> nb2(nb);
+                Vec copy(u);
+                std::vector<double> s1 = get_P_closest(nb, u, P), s2 = get_P_closest(nb2, copy, P);
+                EXPECT(s1 == s2 && nb == nb2, "external user %s round %d", u.getId().c_str(), round);
+                EXPECT(get_top_N_recom(nb, u, 2, s1) == get_top_N_recom(nb2, copy, 2, s2), "coins of external user %s round %d", u.getId().c_str(), round);
+            }
+            others[1].setKnownMean(others[1].getKnownMean() - 0.5);
+            (*others[2].getDimensions())[1] += 3.0;
+        }
+        for (auto t : tables) delete t;
+    }
+    if (!g_bad) std::printf("OK\n");
+    else std::printf("%d mismatches\n", g_bad);
+    return g_bad ? 1 : 0;
+}
