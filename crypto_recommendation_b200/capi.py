@@ -28,7 +28,7 @@ SYMBOLS = [
     "crx_get_LSH_combined_buckets", "crx_lsh_params", "crx_create_hypercube", "crx_cube_destroy",
     "crx_cube_vertex_ids", "crx_get_hypercube_combined_buckets", "crx_get_num_hamming_dist_from",
     "crx_rand_selection", "crx_k_means_pp", "crx_lloyds_assignment", "crx_lloyds_for_remaining",
-    "crx_lsh_range_assignment", "crx_cube_range_assignment", "crx_cluster_sums", "crx_k_means_finish",
+    "crx_lsh_range_assignment", "crx_lsh_range_assignment_vectors", "crx_cube_range_assignment", "crx_cluster_sums", "crx_k_means_finish",
     "crx_k_means", "crx_pam_lloyds", "crx_silhouette_cluster", "crx_recommend_lsh", "crx_recommend_lsh_status", "crx_recommend_cluster",
     "crx_parallel_quickSort", "crx_parallel_quickSort_topn", "crx_get_P_closest", "crx_get_top_N_recom", "crx_lsh_hash_vector",
     "crx_user_vectors_build",
@@ -398,6 +398,18 @@ def lsh_range_assignment(ctx, pts, tables, centroid_rows, metric_type, comm=None
     pl, mem = _ptr(labels)
     _check(lib().crx_lsh_range_assignment_sharded(ctx.h, pts.h, tables.h, _ptr(cr)[0], len(cr), METRICS[metric_type], _comm_ptr(comm),
                                                   pl, _ptr(dists)[0], mem, _ptr(before)[0]))
+    return labels, dists, before
+
+
+def lsh_range_assignment_vectors(ctx, pts, tables, centroids, metric_type, shared_ids=False, centroid_rows=None, out=None):
+    """lsh_range_assignment for centroids that are any vectors (the k_means centres of the second and later iterations):
+    centroids [K][D] float64 on the host.  shared_ids: all centroid ids equal ("k_means_center")."""
+    C = np.ascontiguousarray(centroids, np.float64)
+    cr = None if centroid_rows is None else _np(centroid_rows, np.int32)
+    labels, dists, before = _range_outputs(pts, out)
+    pl, mem = _ptr(labels)
+    _check(lib().crx_lsh_range_assignment_vectors(ctx.h, pts.h, tables.h, _ptr(C)[0], None if cr is None else _ptr(cr)[0], C.shape[0],
+                                                  METRICS[metric_type], int(bool(shared_ids)), pl, _ptr(dists)[0], mem, _ptr(before)[0]))
     return labels, dists, before
 
 

@@ -859,7 +859,10 @@ __host__ __device__ __forceinline__ int annulus_index(double d, double r0) {
 
 template <typename T, int METRIC>
 __global__ void __launch_bounds__(256)
-range_fire_kernel(const T* __restrict__ x, int ld, int D, const double* __restrict__ sqn, int K, const int32_t* __restrict__ crow,
+range_fire_kernel(const T* __restrict__ x, int ld, int D, const double* __restrict__ sqn, int K,
+                  const double* __restrict__ cvec,            // [K][ld] centroid coordinates (stored rows gathered, or any vectors)
+                  const double* __restrict__ csqn,            // [K] their sums of squares
+                  const int32_t* __restrict__ cbucket,        // [L][K] bucket of every centroid in every table (LSH) or NULL
                   double r0, int nseg,                        // segments per centroid
                   const int32_t* __restrict__ seg_begin,      // [K*nseg] start position in seg_perm space
                   const int32_t* __restrict__ seg_end,        // [K*nseg]
@@ -874,17 +877,16 @@ range_fire_kernel(const T* __restrict__ x, int ld, int D, const double* __restri
     int end = min(seg_end[cs], begin + chunk);
     if (begin >= end) return;
     int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    int cr = crow[c];
-    for (int k = threadIdx.x; k < ld; k += blockDim.x) vec[k] = (double)x[(size_t)cr * ld + k];
+    for (int k = threadIdx.x; k < ld; k += blockDim.x) vec[k] = cvec[(size_t)c * ld + k];
     __syncthreads();
     const int32_t* perm = seg_perm[bucket ? sgi : 0];
-    double ncr = sqn[cr];
+    double ncr = csqn[c];
     for (int base = begin + warp * 32; base < end; base += 256) {
         int pos = base + lane;
         int64_t row = pos < end ? (int64_t)perm[pos] : -1;
         if (row >= 0 && bucket) {  // union of the L buckets: count a vector in the first table that holds it
             for (int l = 0; l < sgi; l++)
-                if (bucket[(size_t)l * N + row] == bucket[(size_t)l * N + cr]) { row = -1; break; }
+                if (bucket[(size_t)l * N + row] == cbucket[(size_t)l * K + c]) { row = -1; break; }
         }
         double d = rw::dist_rows<T, METRIC>(x, ld, D, row, vec, row >= 0 ? sqn[row] : 1.0, ncr, tiles[warp]);
         if (row >= 0) {
@@ -892,6 +894,42 @@ range_fire_kernel(const T* __restrict__ x, int ld, int D, const double* __restri
             if (a >= 0 && a % K == c) atomicMin(&key[row], a);
         }
     }
+}
+
+// Shared-id mode: the reference caches distances under the key "<centroid id>to<vector id>"
+// (assignment.hpp:183-194) and k_means names every new centre "k_means_center" (update.hpp:48), so from the second
+// iteration of {range assignment, k_means} all centroids share one cache entry per vector: the distance every centroid
+// uses for vector v is d0(v) = d(c0(v), v), c0(v) = the lowest centroid whose bucket list holds v (the first to evaluate it;
+// an assigned vector is never evaluated again before that, see above).  v is then assigned at step a(d0) to centroid
+// a(d0) mod K -- if that centroid's list holds v -- with distance d0.
+__global__ void __launch_bounds__(256)
+range_first_kernel(int nseg, const int32_t* __restrict__ seg_begin, const int32_t* __restrict__ seg_end,
+                   const int32_t* const* __restrict__ seg_perm, int per_table, int chunk, int* __restrict__ first) {
+    int cs = blockIdx.x;
+    int c = cs / nseg, sgi = cs - c * nseg;
+    int begin = seg_begin[cs] + blockIdx.y * chunk;
+    int end = min(seg_end[cs], begin + chunk);
+    const int32_t* perm = seg_perm[per_table ? sgi : 0];
+    for (int pos = begin + threadIdx.x; pos < end; pos += blockDim.x) atomicMin(&first[perm[pos]], c);
+}
+
+template <typename T, int METRIC>
+__global__ void range_shared_kernel(const T* __restrict__ x, int ld, int D, const double* __restrict__ sqn, int64_t N, int K, int L,
+                                    const double* __restrict__ cvec, const double* __restrict__ csqn, const int32_t* __restrict__ bucket,
+                                    const int32_t* __restrict__ cbucket, double r0, const int* __restrict__ first,
+                                    int* __restrict__ key, double* __restrict__ d0) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    int c0 = first[i];
+    if (c0 == INT_MAX) return;
+    double d = metric_dist_exact(METRIC, cvec + (size_t)c0 * ld, x + (size_t)i * ld, D, csqn[c0], sqn[i]);
+    d0[i] = d;
+    int a = annulus_index(d, r0);
+    if (a < 0) return;
+    int c = a % K;
+    bool member = false;
+    for (int l = 0; l < L; l++) member |= bucket[(size_t)l * N + i] == cbucket[(size_t)l * K + c];
+    if (member) key[i] = a;
 }
 
 __global__ void range_hist_kernel(const int* __restrict__ key, int64_t N, int K, int* __restrict__ hist, int nh) {
@@ -904,18 +942,17 @@ __global__ void range_hist_kernel(const int* __restrict__ key, int64_t N, int K,
 template <typename T, int METRIC>
 __global__ void __launch_bounds__(256)
 range_finalize_kernel(const T* __restrict__ x, int ld, int D, const double* __restrict__ sqn, int64_t N, int K,
-                      const int32_t* __restrict__ crow, const int* __restrict__ key, int sweep_limit,
+                      const double* __restrict__ cvec, const double* __restrict__ csqn, const int* __restrict__ key, int sweep_limit,
+                      const double* __restrict__ shared_d0,   // shared-id mode: the one distance every centroid used for row i
                       int32_t* __restrict__ labels, double* __restrict__ dists) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= N) return;
     int a = key[i];
     if (a != INT_MAX && a / K < sweep_limit) {
         int c = a % K;
-        int cr = crow[c];
         const T* xi = x + (size_t)i * ld;
-        const T* xc = x + (size_t)cr * ld;
         labels[i] = c;
-        dists[i] = metric_dist_exact(METRIC, xc, xi, D, sqn[cr], sqn[i]);
+        dists[i] = shared_d0 ? shared_d0[i] : metric_dist_exact(METRIC, cvec + (size_t)c * ld, xi, D, csqn[c], sqn[i]);
     } else {
         labels[i] = -1;
         dists[i] = 0.0;
@@ -927,7 +964,7 @@ range_finalize_kernel(const T* __restrict__ x, int ld, int D, const double* __re
 // atomicMin on their bit patterns; the host applies the `-1` sentinel rule.
 template <typename T>
 __global__ void min_pair_kernel(const T* __restrict__ x, int ld, int D, const double* __restrict__ sqn,
-                                const int32_t* __restrict__ crow, int K, int metric, unsigned long long* __restrict__ minbits,
+                                int K, int metric, unsigned long long* __restrict__ minbits,
                                 int* __restrict__ any_negative_or_nan) {
     long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     long long npairs = (long long)K * (K - 1) / 2;
@@ -937,7 +974,7 @@ __global__ void min_pair_kernel(const T* __restrict__ x, int ld, int D, const do
     while ((long long)a * (2 * K - a - 1) / 2 > t) a--;
     while ((long long)(a + 1) * (2 * K - a - 2) / 2 <= t) a++;
     int b = (int)(t - (long long)a * (2 * K - a - 1) / 2) + a + 1;
-    double d = metric_dist_exact(metric, x + (size_t)crow[a] * ld, x + (size_t)crow[b] * ld, D, sqn[crow[a]], sqn[crow[b]]);
+    double d = metric_dist_exact(metric, x + (size_t)a * ld, x + (size_t)b * ld, D, sqn[a], sqn[b]);
     if (d >= 0.0) atomicMin(minbits, (unsigned long long)__double_as_longlong(d));
     else atomicExch(any_negative_or_nan, 1);
 }
@@ -946,12 +983,12 @@ __global__ void min_pair_kernel(const T* __restrict__ x, int ld, int D, const do
 // `min == -1 || d < min` rule is order dependent
 template <typename T>
 __global__ void min_pair_seq_kernel(const T* __restrict__ x, int ld, int D, const double* __restrict__ sqn,
-                                    const int32_t* __restrict__ crow, int K, int metric, double* __restrict__ out) {
+                                    int K, int metric, double* __restrict__ out) {
     if (blockIdx.x != 0 || threadIdx.x != 0) return;
     double m = -1;
     for (int a = 0; a < K; a++)
         for (int b = a + 1; b < K; b++) {
-            double d = metric_dist_exact(metric, x + (size_t)crow[a] * ld, x + (size_t)crow[b] * ld, D, sqn[crow[a]], sqn[crow[b]]);
+            double d = metric_dist_exact(metric, x + (size_t)a * ld, x + (size_t)b * ld, D, sqn[a], sqn[b]);
             if (m == -1 || d < m) m = d;
         }
     *out = m;
@@ -1166,6 +1203,11 @@ __global__ void merge_remaining_kernel(const int32_t* __restrict__ tl, const dou
     if (i < n && labels[i] == -1) { labels[i] = tl[i]; dists[i] = td[i]; }
 }
 
+__global__ void range_iota_kernel(int32_t* p, int n) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = i;
+}
+
 __global__ void fill_int_kernel(int* p, int64_t n, int v) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) p[i] = v;
@@ -1201,13 +1243,19 @@ static int comm_allgather(crx_ctx* c, const crx_comm* cm, const void* send, void
     if (mem == CRX_DEVICE && !cm->stream_ordered) CRX_CUDA(cudaStreamSynchronize(c->stream));
     return comm_done(cm->allgather(cm->user, send, recv, n, dtype, mem), "allgather");
 }
-static int range_assign_common(crx_ctx* c, const crx_points* p, const int32_t* h_crow, int K, int metric, int nseg,
+// cp: the K centroids as an FP64 point set of their own (stored rows gathered, or the caller's vectors); h_crow[c] = the stored
+// row centroid c aliases (it is assigned to its own cluster at the end, assignment.hpp:126-128) or -1; d_cbucket: [L][K]
+// bucket of every centroid in every table (LSH) or NULL (hypercube); shared_ids: SURVEY App. A-2, see range_first_kernel
+static int range_assign_common(crx_ctx* c, const crx_points* p, const int32_t* h_crow, const crx_points* cp, const int32_t* d_cbucket,
+                               bool shared_ids, int K, int metric, int nseg,
                                const std::vector<int32_t>& h_begin, const std::vector<int32_t>& h_end,
                                const std::vector<const int32_t*>& h_perm, const int32_t* d_bucket, int32_t* labels,
                                double* dists, int mem, int32_t* before, const crx_comm* comm) {
     const int world = comm_world(comm), me = comm_rank(comm);
     int64_t N = p->n;
     int D = p->d, ld = p->ld;
+    CRX_REQUIRE(cp && cp->x64 && cp->n == K && cp->d == D && cp->ld == ld, "centroid set");
+    CRX_REQUIRE(!shared_ids || (d_bucket && d_cbucket), "the shared-id mode needs LSH tables");
     IoBuf<int32_t> lab, bef;
     IoBuf<double> dis;
     CRX_TRY(lab.bind(c, labels, N, mem, false));
@@ -1233,8 +1281,7 @@ static int range_assign_common(crx_ctx* c, const crx_points* p, const int32_t* h
     if (npairs > 0) {
         CRX_KERNEL(c, "min_pair");
         int g = crx_grid(npairs, 128);
-        if (p->x64) min_pair_kernel<double><<<g, 128, 0, c->stream>>>(p->x64, ld, D, p->sqn, d_crow.p, K, metric, minbits.p, oddflag.p);
-        else min_pair_kernel<float><<<g, 128, 0, c->stream>>>(p->x32, ld, D, p->sqn, d_crow.p, K, metric, minbits.p, oddflag.p);
+        min_pair_kernel<double><<<g, 128, 0, c->stream>>>(cp->x64, ld, D, cp->sqn, K, metric, minbits.p, oddflag.p);
     }
     unsigned long long h_minbits = ~0ull;
     int h_odd = 0;
@@ -1247,8 +1294,7 @@ static int range_assign_common(crx_ctx* c, const crx_points* p, const int32_t* h
         DevBuf<double> seq;
         CRX_TRY(seq.alloc(c, 1));
         CRX_KERNEL(c, "min_pair_seq");
-        if (p->x64) min_pair_seq_kernel<double><<<1, 32, 0, c->stream>>>(p->x64, ld, D, p->sqn, d_crow.p, K, metric, seq.p);
-        else min_pair_seq_kernel<float><<<1, 32, 0, c->stream>>>(p->x32, ld, D, p->sqn, d_crow.p, K, metric, seq.p);
+        min_pair_seq_kernel<double><<<1, 32, 0, c->stream>>>(cp->x64, ld, D, cp->sqn, K, metric, seq.p);
         CRX_CUDA(cudaMemcpyAsync(&mn, seq.p, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
         CRX_CUDA(cudaStreamSynchronize(c->stream));
     }
@@ -1272,18 +1318,42 @@ static int range_assign_common(crx_ctx* c, const crx_points* p, const int32_t* h
             else if (a_max < K) c_limit = a_max + 1;
         }
     }
+    DevBuf<double> d0;
+    const int chunk = 8192;
+    if (shared_ids) {
+        // every rank walks every bucket list (the lists are short next to the Lloyd pass that follows); c0(v) needs all K
+        // centroids, whatever their annuli
+        DevBuf<int> first;
+        CRX_TRY(first.alloc(c, N)); CRX_TRY(d0.alloc(c, N));
+        { CRX_KERNEL(c, "fill_key"); fill_int_kernel<<<crx_grid(N, 256), 256, 0, c->stream>>>(first.p, N, INT_MAX); }
+        int maxlen = 0;
+        for (size_t i = 0; i < (size_t)K * nseg; i++) maxlen = std::max(maxlen, h_end[i] - h_begin[i]);
+        if (maxlen > 0) {
+            CRX_KERNEL(c, "range_first");
+            dim3 grid((unsigned)(K * nseg), (unsigned)((maxlen + chunk - 1) / chunk));
+            range_first_kernel<<<grid, 256, 0, c->stream>>>(nseg, d_begin.p, d_end.p, d_perm.p, 1, chunk, first.p);
+        }
+        {
+            CRX_KERNEL(c, "range_shared");
+#define LAUNCH_S(T, M, xptr) range_shared_kernel<T, M><<<crx_grid(N, 256), 256, 0, c->stream>>>(xptr, ld, D, p->sqn, N, K, nseg, cp->x64, cp->sqn, d_bucket, d_cbucket, r0, first.p, key.p, d0.p)
+            if (p->x64) { if (metric == CRX_EUCLIDEAN) LAUNCH_S(double, CRX_EUCLIDEAN, p->x64); else LAUNCH_S(double, CRX_COSINE, p->x64); }
+            else { if (metric == CRX_EUCLIDEAN) LAUNCH_S(float, CRX_EUCLIDEAN, p->x32); else LAUNCH_S(float, CRX_COSINE, p->x32); }
+#undef LAUNCH_S
+        }
+        CRX_CUDA(cudaGetLastError());
+    } else {
     // this rank probes the buckets of its share of those centroids; the firing steps are combined with a min
     const int c_lo = (int)((int64_t)c_limit * me / world), c_hi = (int)((int64_t)c_limit * (me + 1) / world);
     int maxlen = 0;
     for (size_t i = (size_t)c_lo * nseg; i < (size_t)c_hi * nseg; i++) maxlen = std::max(maxlen, h_end[i] - h_begin[i]);
-    const int chunk = 8192;
     dim3 grid((unsigned)std::max(1, (c_hi - c_lo) * nseg), (unsigned)std::max(1, (maxlen + chunk - 1) / chunk));
     if (maxlen > 0) {
         CRX_KERNEL(c, "range_fire");
-#define LAUNCH_R(T, M, xptr) range_fire_kernel<T, M><<<grid, 256, 0, c->stream>>>(xptr, ld, D, p->sqn, K, d_crow.p, r0, nseg, d_begin.p, d_end.p, d_perm.p, d_bucket, N, chunk, c_lo * nseg, key.p)
+#define LAUNCH_R(T, M, xptr) range_fire_kernel<T, M><<<grid, 256, 0, c->stream>>>(xptr, ld, D, p->sqn, K, cp->x64, cp->sqn, d_cbucket, r0, nseg, d_begin.p, d_end.p, d_perm.p, d_bucket, N, chunk, c_lo * nseg, key.p)
         if (p->x64) { if (metric == CRX_EUCLIDEAN) LAUNCH_R(double, CRX_EUCLIDEAN, p->x64); else LAUNCH_R(double, CRX_COSINE, p->x64); }
         else { if (metric == CRX_EUCLIDEAN) LAUNCH_R(float, CRX_EUCLIDEAN, p->x32); else LAUNCH_R(float, CRX_COSINE, p->x32); }
 #undef LAUNCH_R
+    }
     }
     CRX_TRY(comm_allreduce(c, comm, key.p, N, CRX_I32, CRX_MIN, CRX_DEVICE));
     { CRX_KERNEL(c, "range_hist"); range_hist_kernel<<<crx_grid(N, 256), 256, 0, c->stream>>>(key.p, N, K, hist.p, NH); }
@@ -1294,7 +1364,7 @@ static int range_assign_common(crx_ctx* c, const crx_points* p, const int32_t* h
     while (limit < NH && h_hist[limit] > 0) limit++;
     {
         CRX_KERNEL(c, "range_finalize");
-#define LAUNCH_F(T, M, xptr) range_finalize_kernel<T, M><<<crx_grid(N, 256), 256, 0, c->stream>>>(xptr, ld, D, p->sqn, N, K, d_crow.p, key.p, limit, lab.dev, dis.dev)
+#define LAUNCH_F(T, M, xptr) range_finalize_kernel<T, M><<<crx_grid(N, 256), 256, 0, c->stream>>>(xptr, ld, D, p->sqn, N, K, cp->x64, cp->sqn, key.p, limit, shared_ids ? d0.p : nullptr, lab.dev, dis.dev)
         if (p->x64) { if (metric == CRX_EUCLIDEAN) LAUNCH_F(double, CRX_EUCLIDEAN, p->x64); else LAUNCH_F(double, CRX_COSINE, p->x64); }
         else { if (metric == CRX_EUCLIDEAN) LAUNCH_F(float, CRX_EUCLIDEAN, p->x32); else LAUNCH_F(float, CRX_COSINE, p->x32); }
 #undef LAUNCH_F
@@ -1313,7 +1383,12 @@ static int range_assign_common(crx_ctx* c, const crx_points* p, const int32_t* h
     { CRX_KERNEL(c, "compact_unassigned"); compact_unassigned_kernel<<<crx_grid(N, 256), 256, 0, c->stream>>>(lab.dev, N, rows.p, cnt.p); }
     int h_cnt = 0;
     CRX_CUDA(cudaMemcpyAsync(&h_cnt, cnt.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-    CRX_TRY(gather_rows(c, p, d_crow.p, K, cmat.p));
+    {   // the centroid coordinates as a compact [K][D] matrix for the Lloyd pass
+        DevBuf<int32_t> iota;
+        CRX_TRY(iota.alloc(c, K));
+        { CRX_KERNEL(c, "iota"); range_iota_kernel<<<crx_grid(K, 128), 128, 0, c->stream>>>(iota.p, K); }
+        CRX_TRY(gather_rows(c, cp, iota.p, K, cmat.p));
+    }
     Centroids cen;
     CRX_TRY(cen.stage(c, cmat.p, CRX_DEVICE, K, D, ld));
     CRX_CUDA(cudaStreamSynchronize(c->stream));
@@ -1618,25 +1693,25 @@ int crx_lloyds_for_remaining(crx_ctx* c, const crx_points* p, const double* cent
     return CRX_OK;
 }
 
-int crx_lsh_range_assignment_sharded(crx_ctx* c, const crx_points* p, const crx_lsh* t, const int32_t* crow, int K, int metric,
-                                     const crx_comm* comm, int32_t* labels, double* dists, int mem, int32_t* before) {
-    CRX_REQUIRE(c && p && t && crow && labels && dists, "NULL argument");
-    CRX_REQUIRE(t->pts == p, "the tables were built over a different point set");
-    CRX_REQUIRE(K >= 1, "K");
-    for (int i = 0; i < K; i++) CRX_REQUIRE(crow[i] >= 0 && crow[i] < p->n, "centroid_rows must be stored rows");
-    CRX_CUDA(cudaSetDevice(c->device));
+// the K stored rows `d_crow` as an FP64 point set of their own
+static int centroid_set_from_rows(crx_ctx* c, const crx_points* p, const int32_t* d_crow, int K, crx_points** out) {
+    DevBuf<double> cm;
+    CRX_TRY(cm.alloc(c, (size_t)K * p->d));
+    CRX_TRY(gather_rows(c, p, d_crow, K, cm.p));
+    return crx_points_create(c, cm.p, CRX_F64, K, p->d, CRX_DEVICE, out);
+}
+struct PointsGuard {
+    crx_points* p = nullptr;
+    ~PointsGuard() { if (p) crx_points_destroy(p); }
+};
+
+// d_cb: [L][K] bucket of every centroid in every table (get_LSH_combined_buckets -> getBucketFor, unfiltered)
+static int lsh_range_with_buckets(crx_ctx* c, const crx_points* p, const crx_lsh* t, const int32_t* h_crow, const crx_points* cp,
+                                  const int32_t* d_cb, bool shared_ids, int K, int metric, const crx_comm* comm, int32_t* labels,
+                                  double* dists, int mem, int32_t* before) {
     int L = t->L;
-    int64_t N = p->n;
-    // bucket of every centroid in every table (get_LSH_combined_buckets -> getBucketFor, unfiltered)
-    DevBuf<int32_t> d_crow, d_cb;
-    CRX_TRY(d_crow.alloc(c, K)); CRX_TRY(d_cb.alloc(c, (size_t)K * L));
-    CRX_CUDA(cudaMemcpyAsync(d_crow.p, crow, K * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
-    for (int l = 0; l < L; l++) {
-        CRX_KERNEL(c, "gather_int");
-        gather_int_kernel<<<crx_grid(K, 128), 128, 0, c->stream>>>(t->bucket + (size_t)l * N, d_crow.p, K, d_cb.p + (size_t)l * K);
-    }
     std::vector<int32_t> cb((size_t)K * L);
-    CRX_CUDA(cudaMemcpyAsync(cb.data(), d_cb.p, cb.size() * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+    CRX_CUDA(cudaMemcpyAsync(cb.data(), d_cb, cb.size() * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
     std::vector<std::vector<int32_t>> offs(L);
     for (int l = 0; l < L; l++) {
         offs[l].resize((size_t)t->nbuckets + 1);
@@ -1652,12 +1727,50 @@ int crx_lsh_range_assignment_sharded(crx_ctx* c, const crx_points* p, const crx_
             hb[(size_t)cc * L + l] = offs[l][b];
             he[(size_t)cc * L + l] = offs[l][b + 1];
         }
-    return range_assign_common(c, p, crow, K, metric, L, hb, he, perms, t->bucket, labels, dists, mem, before, comm);
+    return range_assign_common(c, p, h_crow, cp, d_cb, shared_ids, K, metric, L, hb, he, perms, t->bucket, labels, dists, mem, before, comm);
+}
+
+int crx_lsh_range_assignment_sharded(crx_ctx* c, const crx_points* p, const crx_lsh* t, const int32_t* crow, int K, int metric,
+                                     const crx_comm* comm, int32_t* labels, double* dists, int mem, int32_t* before) {
+    CRX_REQUIRE(c && p && t && crow && labels && dists, "NULL argument");
+    CRX_REQUIRE(t->pts == p, "the tables were built over a different point set");
+    CRX_REQUIRE(K >= 1, "K");
+    for (int i = 0; i < K; i++) CRX_REQUIRE(crow[i] >= 0 && crow[i] < p->n, "centroid_rows must be stored rows");
+    CRX_CUDA(cudaSetDevice(c->device));
+    int L = t->L;
+    int64_t N = p->n;
+    DevBuf<int32_t> d_crow, d_cb;
+    CRX_TRY(d_crow.alloc(c, K)); CRX_TRY(d_cb.alloc(c, (size_t)K * L));
+    CRX_CUDA(cudaMemcpyAsync(d_crow.p, crow, K * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+    for (int l = 0; l < L; l++) {
+        CRX_KERNEL(c, "gather_int");
+        gather_int_kernel<<<crx_grid(K, 128), 128, 0, c->stream>>>(t->bucket + (size_t)l * N, d_crow.p, K, d_cb.p + (size_t)l * K);
+    }
+    PointsGuard cp;
+    CRX_TRY(centroid_set_from_rows(c, p, d_crow.p, K, &cp.p));
+    return lsh_range_with_buckets(c, p, t, crow, cp.p, d_cb.p, false, K, metric, comm, labels, dists, mem, before);
 }
 
 int crx_lsh_range_assignment(crx_ctx* c, const crx_points* p, const crx_lsh* t, const int32_t* crow, int K, int metric,
                              int32_t* labels, double* dists, int mem, int32_t* before) {
     return crx_lsh_range_assignment_sharded(c, p, t, crow, K, metric, nullptr, labels, dists, mem, before);
+}
+
+int crx_lsh_range_assignment_vectors(crx_ctx* c, const crx_points* p, const crx_lsh* t, const double* centroids, const int32_t* crow,
+                                     int K, int metric, int shared_ids, int32_t* labels, double* dists, int mem, int32_t* before) {
+    CRX_REQUIRE(c && p && t && centroids && labels && dists, "NULL argument");
+    CRX_REQUIRE(t->pts == p, "the tables were built over a different point set");
+    CRX_REQUIRE(K >= 1, "K");
+    std::vector<int32_t> rows((size_t)K, -1);
+    if (crow) for (int i = 0; i < K; i++) { CRX_REQUIRE(crow[i] >= -1 && crow[i] < p->n, "centroid_rows out of range"); rows[i] = crow[i]; }
+    CRX_CUDA(cudaSetDevice(c->device));
+    PointsGuard cp;
+    CRX_TRY(crx_points_create(c, centroids, CRX_F64, K, p->d, CRX_HOST, &cp.p));
+    // CustHashtable::getHash of every centroid vector (cust_hashtable.hpp:123), all tables in one pass
+    DevBuf<int32_t> d_cb;
+    CRX_TRY(d_cb.alloc(c, (size_t)K * t->L));
+    CRX_TRY(crx_hash_rows(c, cp.p, t->metric, t->k, t->L, t->d_proj, t->ldp, t->d_pnorm, t->d_t, t->d_r, t->w, t->nbuckets, nullptr, d_cb.p));
+    return lsh_range_with_buckets(c, p, t, rows.data(), cp.p, d_cb.p, shared_ids != 0, K, metric, nullptr, labels, dists, mem, before);
 }
 
 int crx_cube_range_assignment_sharded(crx_ctx* c, const crx_points* p, const crx_cube* cu, const int32_t* crow, int K, int metric,
@@ -1683,7 +1796,9 @@ int crx_cube_range_assignment_sharded(crx_ctx* c, const crx_points* p, const crx
     for (int cc = 0; cc < K; cc++)
         for (size_t s = 0; s < seqs[cc].size(); s++) { hb[cc * nseg + s] = off[seqs[cc][s]]; he[cc * nseg + s] = off[seqs[cc][s] + 1]; }
     std::vector<const int32_t*> perms(1, cu->by_vertex.perm);
-    return range_assign_common(c, p, crow, K, metric, (int)nseg, hb, he, perms, nullptr, labels, dists, mem, before, comm);
+    PointsGuard cp;
+    CRX_TRY(centroid_set_from_rows(c, p, d_crow.p, K, &cp.p));
+    return range_assign_common(c, p, crow, cp.p, nullptr, false, K, metric, (int)nseg, hb, he, perms, nullptr, labels, dists, mem, before, comm);
 }
 
 int crx_cube_range_assignment(crx_ctx* c, const crx_points* p, const crx_cube* cu, const int32_t* crow, int K, int metric,

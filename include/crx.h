@@ -137,6 +137,16 @@ int crx_lloyds_for_remaining(crx_ctx* ctx, const crx_points* input_vectors, cons
 int crx_lsh_range_assignment(crx_ctx* ctx, const crx_points* input_vectors, const crx_lsh* lsh_hashtables,
                              const int32_t* centroid_rows, int K, int metric, int32_t* labels, double* dists, int mem,
                              int32_t* labels_before_lloyd);
+/* lsh_range_assignment (assignment.hpp:109-129) for centroids that are ANY vectors -- the heap centres k_means leaves behind
+ * (update.hpp:48) from the second iteration of {range assignment, k_means} on: centroids[K][D] doubles on the host, hashed
+ * like a query (cust_hashtable.hpp:123); centroid_rows (nullable) = the stored row a centroid aliases, or -1.
+ * shared_ids != 0 reproduces SURVEY App. A-2: the reference keys its distance cache by "<centroid id>to<vector id>"
+ * (assignment.hpp:183-194) and every k_means centre is called "k_means_center", so all centroids share ONE cached distance
+ * per vector -- the one of the lowest centroid whose bucket list holds it.  Pass it when all K centroid ids are equal
+ * (the drop-in header does, from the ids themselves); with unique ids (shared_ids = 0) the cache is value-transparent. */
+int crx_lsh_range_assignment_vectors(crx_ctx* ctx, const crx_points* input_vectors, const crx_lsh* lsh_hashtables,
+                                     const double* centroids /* host [K][D] */, const int32_t* centroid_rows, int K, int metric,
+                                     int shared_ids, int32_t* labels, double* dists, int mem, int32_t* labels_before_lloyd);
 int crx_cube_range_assignment(crx_ctx* ctx, const crx_points* input_vectors, const crx_cube* hypercube,
                               const int32_t* centroid_rows, int K, int metric, int probes, int32_t* labels,
                               double* dists, int mem, int32_t* labels_before_lloyd);

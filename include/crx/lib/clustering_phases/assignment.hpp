@@ -2,6 +2,7 @@
 #ifndef CLUSTER_ASSIGNMENT_H
 #define CLUSTER_ASSIGNMENT_H
 
+#include <set>
 #include <string>
 #include <vector>
 
@@ -74,16 +75,38 @@ std::vector<int32_t> stored_rows(std::vector<CustVector<T> >& vecs, std::vector<
 }
 }  // namespace crx
 
-// assignment.hpp:109-129
+// assignment.hpp:109-129.  Centroids that are stored input vectors (after rand_selection / k_means_pp / pam_lloyds) go by row
+// number; any other centroid -- the heap centres k_means leaves behind -- is shipped as a vector and hashed like a query.
+// The reference keys its distance cache by "<centroid id>to<vector id>" (assignment.hpp:183-194): with unique centroid ids
+// the cache changes nothing; when all centroids carry the same id (k_means names every centre "k_means_center",
+// update.hpp:48) they share one cached distance per vector, and that is reproduced (crx_lsh_range_assignment_vectors).
 template <typename vector_type>
 void lsh_range_assignment(std::vector<CustVector<vector_type> >& input_vectors, std::vector<CustHashtable<vector_type>*>& lsh_hashtables,
                           std::vector<CustVector<vector_type>*>& centroids, std::string metric_type) {
     auto& set = lsh_hashtables.at(0)->set;
-    std::vector<int32_t> rows = crx::stored_rows(input_vectors, centroids, "lsh_range_assignment"), labels(input_vectors.size());
+    std::vector<int32_t> labels(input_vectors.size());
     std::vector<double> dists(input_vectors.size());
-    crx::check(crx_lsh_range_assignment(crx::context(), set->pts.pts, set->lsh, rows.data(), (int)rows.size(), crx::metric_code(metric_type), labels.data(),
-                                        dists.data(), CRX_HOST, nullptr), "crx_lsh_range_assignment");
+    std::vector<double> C;
+    std::vector<int32_t> rows;
+    crx::pack_centroids(input_vectors, centroids, C, rows);
+    bool all_stored = true;
+    for (int32_t r : rows) all_stored = all_stored && r >= 0;
+    if (all_stored) {
+        crx::check(crx_lsh_range_assignment(crx::context(), set->pts.pts, set->lsh, rows.data(), (int)rows.size(), crx::metric_code(metric_type), labels.data(),
+                                            dists.data(), CRX_HOST, nullptr), "crx_lsh_range_assignment");
+    } else {
+        std::set<std::string> ids;
+        for (auto c : centroids) ids.insert(c->getId());
+        if (ids.size() != centroids.size() && ids.size() != 1) {
+            std::fprintf(stderr, "crx: lsh_range_assignment: centroid ids must be all different or all equal (%zu distinct among %zu)\n", ids.size(), centroids.size());
+            std::abort();
+        }
+        int shared = centroids.size() > 1 && ids.size() == 1;
+        crx::check(crx_lsh_range_assignment_vectors(crx::context(), set->pts.pts, set->lsh, C.data(), rows.data(), (int)rows.size(), crx::metric_code(metric_type),
+                                                    shared, labels.data(), dists.data(), CRX_HOST, nullptr), "crx_lsh_range_assignment_vectors");
+    }
     crx::write_back(input_vectors, labels, dists);
+    for (size_t c = 0; c < centroids.size(); c++) centroids[c]->setCluster((int)c, 0);  // assignment.hpp:126-128, heap centres included
 }
 
 // assignment.hpp:132-152

@@ -150,6 +150,14 @@ class Oracle:
                                           ctypes.c_double(w), ctypes.c_uint64(seed), _p(labels), _p(dists), _p(before))
         return labels, dists, before
 
+    def lsh_range_assignment_vectors(self, X, C, cidx, shared_ids, metric, k, L, div, w, seed):
+        X = _f64(X); C = _f64(C); N, D = X.shape; K = C.shape[0]
+        cidx = _i32(cidx) if cidx is not None else None
+        labels = np.zeros(N, np.int32); dists = np.zeros(N); before = np.zeros(N, np.int32)
+        self.lib.orc_lsh_range_assignment_vectors(_p(X), ctypes.c_int64(N), D, _p(C), _p(cidx), K, int(bool(shared_ids)), metric, k, L, div,
+                                                  ctypes.c_double(w), ctypes.c_uint64(seed), _p(labels), _p(dists), _p(before))
+        return labels, dists, before
+
     def cube_range_assignment(self, X, cidx, metric, k, w, probes, seed):
         X = _f64(X); N, D = X.shape; cidx = _i32(cidx); K = len(cidx)
         labels = np.zeros(N, np.int32); dists = np.zeros(N); before = np.zeros(N, np.int32)

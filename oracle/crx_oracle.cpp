@@ -359,6 +359,40 @@ void range_assign(const double* X, int D, const int32_t* cidx, int K, int metric
     } while (assigned > 0);
 }
 
+/* assignment.hpp:156-217 as written, for centroids that are any vectors: the distance cache keyed by
+ * "<centroid id>to<vector id>" (:183-194) is kept; idgroup[c] stands for the id string of centroid c (equal numbers =
+ * equal strings, e.g. every k_means centre is "k_means_center", update.hpp:48) */
+void range_assign_cached(const double* X, int64_t N, int D, const double* C, const int* idgroup, int K, int metric,
+                         const std::vector<std::vector<int32_t>>& comb, int32_t* labels, double* dists) {
+    std::vector<int32_t> iota(K);
+    for (int c = 0; c < K; c++) iota[c] = c;
+    double radius = min_pair_distance(C, D, iota.data(), K, metric) / 2;
+    double min_radius = 0;
+    std::unordered_map<uint64_t, double> cache;
+    int assigned;
+    do {
+        assigned = 0;
+        for (int c = 0; c < K; c++) {
+            const double* cv = C + (size_t)c * D;
+            for (int32_t v : comb[c]) {
+                if (labels[v] == -1 || dists[v] >= min_radius) {
+                    uint64_t key = (uint64_t)idgroup[c] * (uint64_t)N + (uint64_t)v;
+                    double d;
+                    auto it = cache.find(key);
+                    if (it != cache.end()) d = it->second;
+                    else { d = metric_dist(metric, cv, X + (size_t)v * D, D); cache[key] = d; }
+                    if (d >= min_radius && d < radius) {
+                        if (labels[v] == -1) { labels[v] = c; dists[v] = d; assigned++; }
+                        else if (dists[v] > d) { labels[v] = c; dists[v] = d; assigned++; }
+                    }
+                }
+            }
+            min_radius = radius;
+            radius = radius * 2;
+        }
+    } while (assigned > 0);
+}
+
 /* assignment.hpp:84-105 */
 void lloyd_remaining(const double* X, int64_t N, int D, const double* C, int K, int metric, bool only_unassigned,
                      int32_t* labels, double* dists) {
@@ -568,6 +602,30 @@ int orc_lsh_range_assignment(const double* X, int64_t N, int D, const int32_t* c
     std::vector<double> C = gather_rows(X, D, cidx, K);
     lloyd_remaining(X, N, D, C.data(), K, metric, true, labels, dists);
     for (int c = 0; c < K; c++) { labels[cidx[c]] = c; dists[cidx[c]] = 0; }
+    return 0;
+}
+
+/* assignment.hpp:109-129 with heap centroids (the second and later iterations of {range assignment, k_means}) */
+int orc_lsh_range_assignment_vectors(const double* X, int64_t N, int D, const double* C, const int32_t* cidx, int K, int shared_ids,
+                                     int metric, int k, int L, int div, double w, uint64_t seed, int32_t* labels, double* dists,
+                                     int32_t* before) {
+    Lsh lsh;
+    lsh.build(X, N, D, metric, k, L, div, w, seed);
+    for (int64_t i = 0; i < N; i++) { labels[i] = -1; dists[i] = 0; }
+    std::vector<double> Cm((size_t)K * D);
+    std::vector<int> group(K);
+    for (int c = 0; c < K; c++) {
+        bool stored = cidx && cidx[c] >= 0;
+        std::memcpy(&Cm[(size_t)c * D], stored ? X + (size_t)cidx[c] * D : C + (size_t)c * D, sizeof(double) * D);
+        group[c] = stored ? 1 + cidx[c] : (shared_ids ? 0 : (int)N + 1 + c);   /* stored rows keep their own unique ids */
+    }
+    std::vector<std::vector<int32_t>> comb(K);
+    for (int c = 0; c < K; c++) lsh.candidates(&Cm[(size_t)c * D], 0, comb[c]);
+    range_assign_cached(X, N + K + 2, D, Cm.data(), group.data(), K, metric, comb, labels, dists);
+    if (before) std::memcpy(before, labels, sizeof(int32_t) * N);
+    lloyd_remaining(X, N, D, Cm.data(), K, metric, true, labels, dists);
+    for (int c = 0; c < K; c++)
+        if (cidx && cidx[c] >= 0) { labels[cidx[c]] = c; dists[cidx[c]] = 0; }
     return 0;
 }
 

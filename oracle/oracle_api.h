@@ -66,6 +66,12 @@ int orc_lloyds_assignment(const double* X, int64_t N, int D, const double* C, in
 int orc_lsh_range_assignment(const double* X, int64_t N, int D, const int32_t* cidx, int K, int metric, int k, int L,
                              int lsh_bucket_div, double w, uint64_t seed, int32_t* labels, double* dists,
                              int32_t* labels_before_lloyd);
+/* lsh_range_assignment with centroids that are any vectors: C[K][D]; cidx[c] = the stored row centroid c IS (the pointer
+ * aliases it and keeps that vector's id), or -1 = a heap vector called "k_means_center" (update.hpp:48) when shared_ids,
+ * "center_<c>" otherwise */
+int orc_lsh_range_assignment_vectors(const double* X, int64_t N, int D, const double* C, const int32_t* cidx, int K, int shared_ids,
+                                     int metric, int k, int L, int lsh_bucket_div, double w, uint64_t seed, int32_t* labels,
+                                     double* dists, int32_t* labels_before_lloyd);
 int orc_cube_range_assignment(const double* X, int64_t N, int D, const int32_t* cidx, int K, int metric, int k, double w,
                               int probes, uint64_t seed, int32_t* labels, double* dists, int32_t* labels_before_lloyd);
 /* returns the bool of k_means (update.hpp:38); newC receives the computed means either way */

@@ -278,6 +278,36 @@ int orc_lsh_range_assignment(const double* X, int64_t N, int D, const int32_t* c
     return 0;
 }
 
+int orc_lsh_range_assignment_vectors(const double* X, int64_t N, int D, const double* C, const int32_t* cidx, int K, int shared_ids,
+                                     int metric, int k, int L, int div, double w, uint64_t seed, int32_t* labels, double* dists,
+                                     int32_t* before) {
+    g_seed = seed;
+    vector<CV> vecs = make_vectors(X, N, D);
+    vector<CustHashtable<double>*> tabs = create_LSH_hashtables<double>(vecs, metric_name(metric), k, L, div, w);
+    vector<CV*> cent(K);
+    for (int i = 0; i < K; i++) {
+        if (cidx && cidx[i] >= 0) cent[i] = &vecs[cidx[i]];
+        else cent[i] = new CV(shared_ids ? std::string("k_means_center") : "center_" + std::to_string(i),
+                              vector<double>(C + (size_t)i * D, C + (size_t)(i + 1) * D));
+    }
+    if (before) {
+        remove_clustering(vecs);
+        vector<vector<CV*>> comb(K);
+        for (int c = 0; c < K; c++) comb[c] = get_LSH_combined_buckets<double>(tabs, cent[c]);
+        range_assignment(comb, cent, metric_name(metric));
+        for (int64_t i = 0; i < N; i++) before[i] = vecs[i].getCluster();
+    }
+    lsh_range_assignment(vecs, tabs, cent, metric_name(metric));
+    for (int64_t i = 0; i < N; i++) {
+        labels[i] = vecs[i].getCluster();
+        dists[i] = vecs[i].getDistFromCentroid();
+    }
+    for (int i = 0; i < K; i++)
+        if (!(cidx && cidx[i] >= 0)) delete cent[i];
+    for (auto t : tabs) delete t;
+    return 0;
+}
+
 int orc_cube_range_assignment(const double* X, int64_t N, int D, const int32_t* cidx, int K, int metric, int k, double w,
                               int probes, uint64_t seed, int32_t* labels, double* dists, int32_t* before) {
     g_seed = seed;

@@ -166,6 +166,26 @@ int main(int argc, char** argv) {
         for (auto t : tabs) delete t;
         delete cube;
     }
+    // ---- {lsh_range_assignment, k_means} iterated (assignment.hpp:109-129 + update.hpp:38-86): from the second iteration the
+    // centroids are heap vectors that all carry the id "k_means_center"
+    for (int m = 0; m < 2; m++) {
+        string metric_type = m == 0 ? "euclidean" : "cosine";
+        set_seed_all(1010 + m);
+        vector<CustVector<double>*> centroids = rand_selection(users, 5);
+        vector<CustHashtable<double>*> tabs = create_LSH_hashtables<double>(users, metric_type, 3, 4, 10, 2.0);
+        bool cont = true;
+        int it = 0;
+        while (cont && it < 3) {
+            lsh_range_assignment(users, tabs, centroids, metric_type);
+            fprintf(o, "rangeloop%d_%d", m, it);
+            for (auto& u : users) fprintf(o, " %d", u.getCluster());
+            fprintf(o, "\n");
+            cont = k_means(users, centroids, metric_type, 0.0);
+            it++;
+        }
+        for (auto c : centroids) if (c->getId() == "k_means_center") delete c;
+        for (auto t : tabs) delete t;
+    }
     fclose(o);
     return 0;
 }

@@ -165,6 +165,77 @@ def test_range_assignment_oracle(ctx, port, metric, dtype):
 
 @pytest.mark.parametrize("metric", METRICS)
 @pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_range_assignment_with_heap_centroids(ctx, port, metric, dtype):
+    """lsh_range_assignment with centroids that are not stored rows (the centres k_means leaves behind), with unique ids and
+    with the shared "k_means_center" id whose distance-cache collisions the reference has from the second iteration on
+    (SURVEY App. A-2): labels before and after the Lloyd pass and distances bit-exact."""
+    X = synth.gaussian_mixture(6000, 32, 10, seed=52, dtype=dtype)
+    X64 = X.astype(np.float64)
+    P = ctx.points(X)
+    rng = np.random.default_rng(9)
+    cidx = port.k_means_pp(X64, 12, metric, 111)
+    lab, _ = port.lloyds_assignment(X64, X64[cidx], cidx, metric)
+    _, C = port.k_means(X64, lab, X64[cidx], metric, 0.0)          # real k-means centres
+    C2 = np.stack([X64[rng.choice(len(X64), 30)].mean(0) for _ in range(12)])   # and centres of random subsets
+    assigned = 0
+    differs = 0
+    for (k, L, div, w) in [(4, 5, 100, 0.4), (3, 4, 50, 6.0)]:
+        t = capi.LshTables(ctx, P, metric, k, L, div, w, 112)
+        for cen in (C, C2):
+            per_mode = []
+            for shared in (False, True):
+                l, d, b = capi.lsh_range_assignment_vectors(ctx, P, t, cen, metric, shared_ids=shared)
+                rl, rd, rb = port.lsh_range_assignment_vectors(X64, cen, None, shared, metric, k, L, div, w, 112)
+                assert np.array_equal(b, rb), (shared, int(np.sum(b != rb)), int((rb >= 0).sum()))
+                assert np.array_equal(l, rl) and np.array_equal(d, rd)
+                assigned += int((rb >= 0).sum())
+                per_mode.append(rb)
+            differs += int(np.sum(per_mode[0] != per_mode[1]))
+        # some centroids are stored rows (their own unique ids, assigned to their own cluster at the end)
+        rows = np.full(12, -1, np.int32)
+        rows[[2, 7]] = cidx[[2, 7]]
+        cen = C.copy()
+        cen[[2, 7]] = X64[cidx[[2, 7]]]
+        l, d, b = capi.lsh_range_assignment_vectors(ctx, P, t, cen, metric, shared_ids=False, centroid_rows=rows)
+        rl, rd, rb = port.lsh_range_assignment_vectors(X64, cen, rows, 0, metric, k, L, div, w, 112)
+        assert np.array_equal(b, rb) and np.array_equal(l, rl) and np.array_equal(d, rd)
+        t.close()
+    assert assigned > 0 and differs > 0   # the range search assigned rows, and the id collision changed some of them
+
+
+@pytest.mark.parametrize("metric", METRICS)
+def test_iterated_range_assignment_and_k_means(ctx, port, metric):
+    """The loop the reference's library allows (and round 1 aborted in): {lsh_range_assignment, k_means} repeated; from the
+    second iteration the centroids are heap vectors that all carry the id "k_means_center"."""
+    X = synth.gaussian_mixture(5000, 24, 8, seed=53, dtype=np.float64)
+    P = ctx.points(X)
+    k, L, div, w = 4, 4, 50, 2.0
+    t = capi.LshTables(ctx, P, metric, k, L, div, w, 77)
+    cidx = port.k_means_pp(X, 9, metric, 78)
+    lab, dist, _ = capi.lsh_range_assignment(ctx, P, t, cidx, metric)
+    rlab, rdist, _ = port.lsh_range_assignment(X, cidx, metric, k, L, div, w, 77)
+    assert np.array_equal(lab, rlab) and np.array_equal(dist, rdist)
+    C = X[cidx]
+    for it in range(3):
+        cont, C_new = capi.k_means(ctx, P, lab, C, metric, 0.0)
+        rcont, rC = port.k_means(X, rlab, C, metric, 0.0)
+        assert cont == rcont
+        if not rcont:
+            break
+        assert_float_close(C_new, rC, 1e-12)
+        C = rC   # both sides continue from the oracle's centres (the engine's sums may differ in the last bits)
+        lab, dist, bef = capi.lsh_range_assignment_vectors(ctx, P, t, C, metric, shared_ids=True)
+        rlab, rdist, rbef = port.lsh_range_assignment_vectors(X, C, None, 1, metric, k, L, div, w, 77)
+        assert np.array_equal(bef, rbef), (it, int(np.sum(bef != rbef)))
+        # (an emptied cluster leaves a zero centre: cosine distances to it are NaN on both sides)
+        assert np.array_equal(lab, rlab) and np.array_equal(dist, rdist, equal_nan=True), it
+        if it == 0:
+            assert len(set(rlab.tolist())) > 1
+    t.close()
+
+
+@pytest.mark.parametrize("metric", METRICS)
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
 def test_pam_silhouette_oracle(ctx, port, metric, dtype):
     X = synth.gaussian_mixture(2500, 24, 6, seed=61, dtype=dtype)
     X64 = X.astype(np.float64)

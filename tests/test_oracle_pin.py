@@ -137,6 +137,16 @@ def test_live_clustering(both, metric):
         assert same(a, b)
     for a, b in zip(ref.cube_range_assignment(X, cidx, metric, 6, 0.4, 10, 56), port.cube_range_assignment(X, cidx, metric, 6, 0.4, 10, 56)):
         assert same(a, b)
+    # heap centroids (k_means centres): unique ids, and the shared "k_means_center" id of SURVEY App. A-2 -- the port keeps
+    # the reference's string-keyed distance cache literally
+    rng = np.random.default_rng(3)
+    Cm = np.stack([X[rng.choice(len(X), 40)].mean(0) for _ in range(9)])
+    mixed = np.array([-1, int(cidx[1]), -1, -1, int(cidx[4]), -1, -1, -1, -1], np.int32)
+    for shared, rows in ((0, None), (1, None), (0, mixed), (1, mixed)):
+        ra = ref.lsh_range_assignment_vectors(X, Cm, rows, shared, metric, 4, 5, 100, 0.4, 55)
+        pa = port.lsh_range_assignment_vectors(X, Cm, rows, shared, metric, 4, 5, 100, 0.4, 55)
+        for a, b in zip(ra, pa):
+            assert same(a, b)
     Xs = X[:500]
     cs = ref.rand_selection(Xs, 6, 9); ls, _ = ref.lloyds_assignment(Xs, Xs[cs], cs, metric)
     a, b = ref.pam_lloyds(Xs, ls, cs, metric), port.pam_lloyds(Xs, ls, cs, metric)
