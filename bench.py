@@ -721,18 +721,28 @@ def bench_c1_main(rig, args):
                "stages": ["cosine LSH real users (main.cpp:146-186)", "cosine LSH cluster users (:196-232)",
                           "clustering recommendation A (:242-275)", "clustering recommendation B (:344-380)"]}
         texts = {}
-        for tag, exe in (("reference_cpu", ref_bin), ("dropin_gpu", crx_bin)):
-            env = dict(os.environ, CRX_FAKE_SEED="5", CRX_DEVICE=str(rig.local_rank))
+        for tag, exe in (("reference_cpu", ref_bin), ("dropin_gpu", crx_bin), ("dropin_gpu_columnar_input", crx_bin)):
+            if tag == "dropin_gpu_columnar_input":   # row f-4: the tweet-vector file converted once to the binary columnar form
+                sys.path.insert(0, os.path.join(ROOT, "tools"))
+                import csv_to_columnar
+                src = os.path.join(work, "proj2_input.csv")
+                csv_to_columnar.convert(src, src + ".crxcol")
+            env = dict(os.environ, CRX_FAKE_SEED="5", CRX_DEVICE=str(rig.local_rank), CRX_SHIM_PROFILE="1")
             t0 = time.perf_counter()
-            subprocess.run([exe, "-d", "./tweets.tsv", "-o", "./out_%s.txt" % tag], cwd=work, env=env, check=True,
-                           stdout=subprocess.DEVNULL, timeout=900)
+            run = subprocess.run([exe, "-d", "./tweets.tsv", "-o", "./out_%s.txt" % tag], cwd=work, env=env, check=True,
+                                 stdout=subprocess.DEVNULL, stderr=subprocess.PIPE, timeout=900)
             wall = time.perf_counter() - t0
             lines = open(os.path.join(work, "out_%s.txt" % tag)).read().splitlines()
             stage_ms = [int(l.split(":")[1]) for l in lines if l.startswith("Execution Time:")]
             texts[tag] = [l for l in lines if not l.startswith("Execution Time:")]
             out[tag] = {"stage_ms": stage_ms, "stages_total_ms": sum(stage_ms), "process_wall_ms": round(wall * 1e3)}
+            for l in run.stderr.decode().splitlines():   # the drop-in headers' own clock (CRX_SHIM_PROFILE)
+                if "VectorReader::read" in l:
+                    out[tag]["tweet_vectors_read_ms"] = float(l.split(")")[1].split("ms")[0])
+                elif "CUDA start-up" in l:
+                    out[tag]["cuda_startup_ms"] = float(l.split(")")[1].split("ms")[0])
         out["output_lines"] = len(texts["reference_cpu"])
-        out["outputs_identical"] = texts["reference_cpu"] == texts["dropin_gpu"]
+        out["outputs_identical"] = texts["reference_cpu"] == texts["dropin_gpu"] == texts["dropin_gpu_columnar_input"]
         out["speedup_stages_total"] = round(out["reference_cpu"]["stages_total_ms"] / max(1, out["dropin_gpu"]["stages_total_ms"]), 2)
         return out
     finally:

@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJDIR = os.path.join(HERE, "_obj")
 LIB = os.path.join(HERE, "libcrx.so")
-SOURCES = ["core.cu", "hash.cu", "cluster.cu", "recommend.cu", "tc_scan.cu", "uservec.cu", "comm_nccl.cu"]
+SOURCES = ["core.cu", "hash.cu", "cluster.cu", "recommend.cu", "tc_scan.cu", "uservec.cu", "comm_nccl.cu", "ingest.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
          "-Xcompiler", "-fPIC", "-Xcompiler", "-fno-strict-aliasing", "--expt-relaxed-constexpr",

@@ -28,6 +28,8 @@ SYMBOLS = [
     "crx_get_LSH_combined_buckets", "crx_lsh_params", "crx_create_hypercube", "crx_cube_destroy",
     "crx_cube_vertex_ids", "crx_get_hypercube_combined_buckets", "crx_get_num_hamming_dist_from",
     "crx_rand_selection", "crx_k_means_pp", "crx_lloyds_assignment", "crx_lloyds_for_remaining",
+    "crx_columnar_write", "crx_columnar_open", "crx_columnar_n", "crx_columnar_d", "crx_columnar_id", "crx_columnar_points",
+    "crx_columnar_rows", "crx_columnar_close",
     "crx_lsh_range_assignment", "crx_lsh_range_assignment_vectors", "crx_cube_range_assignment", "crx_cluster_sums", "crx_k_means_finish",
     "crx_k_means", "crx_pam_lloyds", "crx_silhouette_cluster", "crx_recommend_lsh", "crx_recommend_lsh_status", "crx_recommend_cluster",
     "crx_parallel_quickSort", "crx_parallel_quickSort_topn", "crx_get_P_closest", "crx_get_top_N_recom", "crx_lsh_hash_vector",
@@ -195,6 +197,51 @@ class Points:
     def close(self):
         if self.h:
             lib().crx_points_destroy(self.h)
+            self.h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Columnar:
+    """A binary columnar vector file (include/crx.h, "input ingest"): ids + float64 columns, opened with mmap."""
+
+    def __init__(self, path):
+        L = lib()
+        L.crx_columnar_n.restype = ctypes.c_int64
+        L.crx_columnar_id.restype = ctypes.c_char_p
+        self.h = ctypes.c_void_p()
+        _check(L.crx_columnar_open(os.fsencode(path), ctypes.byref(self.h)))
+        self.n, self.d = int(L.crx_columnar_n(self.h)), int(L.crx_columnar_d(self.h))
+
+    @staticmethod
+    def write(path, ids, rows):
+        rows = np.ascontiguousarray(rows, np.float64)
+        arr = (ctypes.c_char_p * len(ids))(*[str(i).encode() for i in ids])
+        _check(lib().crx_columnar_write(os.fsencode(path), arr, _ptr(rows)[0], ctypes.c_int64(rows.shape[0]), int(rows.shape[1])))
+
+    def ids(self):
+        return [lib().crx_columnar_id(self.h, ctypes.c_int64(i)).decode() for i in range(self.n)]
+
+    def points(self, ctx):
+        """The vectors as a point set on the GPU (upload of the columns + transpose kernel)."""
+        P = Points.__new__(Points)
+        P.ctx, P.h, P.n, P.d = ctx, ctypes.c_void_p(), self.n, self.d
+        _check(lib().crx_columnar_points(ctx.h, self.h, ctypes.byref(P.h)))
+        ctx._children.add(P)
+        return P
+
+    def rows(self, ctx):
+        out = np.zeros((self.n, self.d))
+        _check(lib().crx_columnar_rows(ctx.h, self.h, _ptr(out)[0]))
+        return out
+
+    def close(self):
+        if self.h:
+            lib().crx_columnar_close(self.h)
             self.h = ctypes.c_void_p()
 
     def __del__(self):

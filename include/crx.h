@@ -267,6 +267,24 @@ int crx_parallel_quickSort(crx_ctx* ctx, double* sims /* host, in/out */, int32_
  * of any size.  The first min(n, need) entries of sims / ids are the literal sort's; the rest is unspecified. */
 int crx_parallel_quickSort_topn(crx_ctx* ctx, double* sims /* host, in/out */, int32_t* ids /* host, in/out */, int n, int need);
 
+/* ---- input ingest (vector_reader.hpp:55-85): binary columnar files in place of line-by-line getline + stod -----------
+ * A file converted once (crx_columnar_write, tools/csv_to_columnar.py; values = strtod of every token = what the
+ * reference's stod lambda returns, main.cpp:82) holds the ids and the coordinates as float64 columns:
+ *   "CRXCOL1\0" | int64 n | int32 d | int32 0 | int64 ids_bytes | n NUL-terminated ids | zero padding to 8 bytes |
+ *   float64 [d][n]
+ * Loading = one mapped read, one upload, one transpose on the GPU into the engine's row-major layout. */
+typedef struct crx_columnar crx_columnar;
+int crx_columnar_write(const char* path, const char* const* ids, const double* rows /* host [n][d] */, int64_t n, int d);
+int crx_columnar_open(const char* path, crx_columnar** out);
+int64_t crx_columnar_n(const crx_columnar* f);
+int32_t crx_columnar_d(const crx_columnar* f);
+const char* crx_columnar_id(const crx_columnar* f, int64_t i);   /* valid until crx_columnar_close */
+/* the vectors as a point set on the GPU (VectorReader::read + the packing every clustering call would do) */
+int crx_columnar_points(crx_ctx* ctx, const crx_columnar* f, crx_points** out);
+/* the same rows on the host, [n][d] doubles, transposed by the GPU (for callers that keep CustVector objects) */
+int crx_columnar_rows(crx_ctx* ctx, const crx_columnar* f, double* rows /* host */);
+int crx_columnar_close(crx_columnar* f);
+
 /* ---- the step in front of the path: user rating vectors from tweet mentions ------------------------------
  * tweets_to_user_vectors (crypto_rec.hpp:79-140) and clusters_to_user_vectors (:143-210) after the strings are
  * resolved to indices: mention i says "tweet with sentiment mention_score[i] names coin mention_coin[i], posted

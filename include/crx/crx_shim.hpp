@@ -33,7 +33,11 @@ inline crx_ctx* context() {
     static crx_ctx* ctx = nullptr;
     if (!ctx) {
         const char* dev = std::getenv("CRX_DEVICE");
+        auto t0 = std::chrono::steady_clock::now();
         check(crx_ctx_create(dev ? std::atoi(dev) : 0, nullptr, &ctx), "crx_ctx_create");
+        if (std::getenv("CRX_SHIM_PROFILE"))
+            std::fprintf(stderr, "crx shim: %-34s %9.1f ms\n", "crx_ctx_create (CUDA start-up)",
+                         std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
     }
     return ctx;
 }

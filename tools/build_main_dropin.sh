@@ -3,7 +3,7 @@
 #   oracle/_ref/recommendation_ref  = main.cpp + the reference's own headers            (the checker)
 #   oracle/_ref/recommendation_crx  = main.cpp + include/crx/lib drop-in headers + libcrx.so (the product behind main.cpp)
 # main.cpp includes "./lib/..." relative to itself, so the drop-in build compiles it from a scratch tree of symlinks:
-# main.cpp and the non-hot-path files (arg_parser, vector_reader, tweet) point at the reference, the hot-path headers at
+# main.cpp and the non-hot-path files (arg_parser, tweet) point at the reference, the hot-path headers at
 # include/crx/lib.  Nothing is copied; only the two binaries are kept.
 set -euo pipefail
 REPO="$(cd "$(dirname "$0")/.." && pwd)"
@@ -25,7 +25,7 @@ ln -s "$REPO/include/crx/crx_shim.hpp" "$T/w/crx_shim.hpp"
 ln -s "$REPO/oracle/main_ref_wrap.cpp" "$T/w/wrap.cpp"
 cp -rs "$REPO/include/crx/lib/." "$T/w/lib/"
 mkdir -p "$T/w/lib/in_out"
-for f in in_out/arg_parser.cpp in_out/arg_parser.h in_out/vector_reader.hpp data_structures/tweet.h data_structures/tweet.cpp; do
+for f in in_out/arg_parser.cpp in_out/arg_parser.h data_structures/tweet.h data_structures/tweet.cpp; do
     ln -sf "$REF/lib/$f" "$T/w/lib/$f"
 done
 (cd "$T/w" && g++ $FLAGS -DCRX_DROPIN_BUILD wrap.cpp lib/in_out/arg_parser.cpp lib/data_structures/tweet.cpp \
