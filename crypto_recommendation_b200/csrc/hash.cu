@@ -173,31 +173,46 @@ hash_rows32_kernel(const float* __restrict__ x, int ld, const double* __restrict
                    int32_t* __restrict__ hvals, int32_t* __restrict__ bucket, int32_t* __restrict__ rowlist, int* __restrict__ nlist) {
     extern __shared__ float sp32[];          // [H][ldp] projections, then the row tile
     const int H = L * k;
-    float* tile = sp32 + H * ldp;             // [256 rows][17]: 16 coordinates of the block's 256 rows, conflict-free
+    float* tile = sp32 + H * ldp;             // 2 x [256 rows][20]: 16 coordinates of the block's 256 rows; the 80-byte row pitch keeps
+                                              // the 128-bit reads of a quarter warp (8 rows) on 8 different bank groups
     for (int e = threadIdx.x; e < H * ldp; e += blockDim.x) sp32[e] = (float)proj[e];
-    // thread t owns rows base + t and base + 128 + t; the global reads are cooperative and coalesced (64-byte pieces)
-    const int64_t base = (int64_t)blockIdx.x * 256;
+    // thread t owns rows base + t and base + 128 + t; the global reads are cooperative and coalesced (64-byte pieces).
+    // A block walks groups of 256 rows (grid = a few blocks per SM): the projections are staged once per block, not per group.
     const int t = threadIdx.x;
+    for (int64_t base = (int64_t)blockIdx.x * 256; base < N; base += (int64_t)gridDim.x * 256) {
     int64_t i0 = base + t, i1 = base + 128 + t;
     bool v0 = i0 < N, v1 = i1 < N;
     float a0[KH], a1[KH];
 #pragma unroll
     for (int h = 0; h < KH; h++) { a0[h] = 0.f; a1[h] = 0.f; }
-    for (int c0 = 0; c0 < ld; c0 += 16) {
-        __syncthreads();   // previous tile consumed (and, first time, the projections staged)
+    // two tiles: the 16-byte asynchronous copies of chunk c+1 are in flight while chunk c is multiplied (the kernel was bound by
+    // the exposed latency of its global loads at 16 warps per SM, not by HBM or the FMA pipe)
+    auto fetch = [&](int c0, float* dst_tile) {
 #pragma unroll
         for (int it = 0; it < 8; it++) {
             int idx = it * 128 + t;
             int row = idx >> 2, piece = (idx & 3) * 4;
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (base + row < N && c0 + piece < ld) v = *reinterpret_cast<const float4*>(x + (base + row) * ld + c0 + piece);
-            float* dst = tile + row * 17 + piece;
-            dst[0] = v.x; dst[1] = v.y; dst[2] = v.z; dst[3] = v.w;
+            const bool in = base + row < N && c0 + piece < ld;
+            const float* src = in ? x + (base + row) * ld + c0 + piece : x;
+            unsigned dst = (unsigned)__cvta_generic_to_shared(dst_tile + row * 20 + piece);
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(in ? 16 : 0) : "memory");   // src-size 0: zero fill
         }
-        __syncthreads();
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    fetch(0, tile);
+    int buf = 0;
+    for (int c0 = 0; c0 < ld; c0 += 16, buf ^= 1) {
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncthreads();   // chunk c0 landed for every thread; the other tile is no longer read (and, first time, the projections are staged)
+        const float* cur = tile + buf * (256 * 20);
         float p0[16], p1[16];
 #pragma unroll
-        for (int i = 0; i < 16; i++) { p0[i] = tile[t * 17 + i]; p1[i] = tile[(128 + t) * 17 + i]; }
+        for (int i = 0; i < 4; i++) {
+            float4 u0 = *reinterpret_cast<const float4*>(cur + t * 20 + 4 * i), u1 = *reinterpret_cast<const float4*>(cur + (128 + t) * 20 + 4 * i);
+            p0[4 * i] = u0.x; p0[4 * i + 1] = u0.y; p0[4 * i + 2] = u0.z; p0[4 * i + 3] = u0.w;
+            p1[4 * i] = u1.x; p1[4 * i + 1] = u1.y; p1[4 * i + 2] = u1.z; p1[4 * i + 3] = u1.w;
+        }
+        if (c0 + 16 < ld) fetch(c0 + 16, tile + (buf ^ 1) * (256 * 20));
         if (c0 + 16 <= ld) {
 #pragma unroll
             for (int h = 0; h < KH; h++) {
@@ -232,7 +247,9 @@ hash_rows32_kernel(const float* __restrict__ x, int ld, const double* __restrict
     }
     const double cb = (double)(3 * D + 8) * 5.9604644775390625e-8 * 1.001;
     const double nx0 = v0 ? sqrt(sqn[i0]) : 0.0, nx1 = v1 ? sqrt(sqn[i1]) : 0.0;
-    const double dw = (double)w;
+    // y = (v.x + t) / w is formed as (v.x + t) * (1 / w): two roundings instead of one, both inside the bound Ey that a
+    // decision has to clear (a double division costs ~30 instructions and there are 4 per row and projection otherwise)
+    const double inv_w = 1.0 / (double)w;
     bool unsure0 = false, unsure1 = false;
     for (int l = 0; l < L; l++) {
         int g0 = 0, g1 = 0;
@@ -253,14 +270,14 @@ hash_rows32_kernel(const float* __restrict__ x, int ld, const double* __restrict
                 } else {
                     double t = (double)tt[h];
                     {
-                        double sv = (double)a0[h] + t, y = sv / dw, f = floor(y), fr = y - f;
-                        double Ey = (E0 + fabs(sv) * 2.3e-16) / dw + fabs(y) * 2.3e-16;
+                        double sv = (double)a0[h] + t, y = sv * inv_w, f = floor(y), fr = y - f;
+                        double Ey = (E0 + fabs(sv) * 2.3e-16) * (inv_w * 1.000001) + fabs(y) * 4.6e-16;
                         unsure0 |= !(fmin(fr, 1.0 - fr) > Ey);
                         r0 = f2i_x87(f);
                     }
                     {
-                        double sv = (double)a1[h] + t, y = sv / dw, f = floor(y), fr = y - f;
-                        double Ey = (E1 + fabs(sv) * 2.3e-16) / dw + fabs(y) * 2.3e-16;
+                        double sv = (double)a1[h] + t, y = sv * inv_w, f = floor(y), fr = y - f;
+                        double Ey = (E1 + fabs(sv) * 2.3e-16) * (inv_w * 1.000001) + fabs(y) * 4.6e-16;
                         unsure1 |= !(fmin(fr, 1.0 - fr) > Ey);
                         r1 = f2i_x87(f);
                     }
@@ -292,6 +309,8 @@ hash_rows32_kernel(const float* __restrict__ x, int ld, const double* __restrict
     }
     if (v0 && unsure0) rowlist[atomicAdd(nlist, 1)] = (int32_t)i0;
     if (v1 && unsure1) rowlist[atomicAdd(nlist, 1)] = (int32_t)i1;
+    __syncthreads();   // the tiles are free for the next group
+    }
 }
 
 template <typename T>
@@ -335,8 +354,8 @@ int crx_hash_rows(crx_ctx* c, const crx_points* pts, int metric, int k, int L, c
         int64_t N = pts->n;
         CRX_TRY(list.alloc(c, N)); CRX_TRY(count.alloc(c, 1));
         CRX_CUDA(cudaMemsetAsync(count.p, 0, sizeof(int), c->stream));
-        int grid = (int)((N + 255) / 256);
-        size_t smem = ((size_t)H * ldp + 256 * 17) * sizeof(float);
+        int grid = (int)std::min<int64_t>((N + 255) / 256, (int64_t)c->sm_count * 4);
+        size_t smem = ((size_t)H * ldp + 2 * 256 * 20) * sizeof(float);
         {
             CRX_KERNEL(c, "hash_rows32");
 #define LAUNCH_F(KH)                                                                                                       \
