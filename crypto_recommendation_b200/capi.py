@@ -32,7 +32,7 @@ SYMBOLS = [
     "crx_columnar_rows", "crx_columnar_close",
     "crx_lsh_range_assignment", "crx_lsh_range_assignment_vectors", "crx_cube_range_assignment", "crx_cluster_sums", "crx_k_means_finish",
     "crx_k_means", "crx_pam_lloyds", "crx_silhouette_cluster", "crx_recommend_lsh", "crx_recommend_lsh_status", "crx_recommend_cluster",
-    "crx_parallel_quickSort", "crx_parallel_quickSort_topn", "crx_get_P_closest", "crx_get_top_N_recom", "crx_lsh_hash_vector",
+    "crx_parallel_quickSort", "crx_parallel_quickSort_topn", "crx_get_P_closest", "crx_get_top_N_recom", "crx_lsh_hash_vector", "crx_lsh_hash_points",
     "crx_user_vectors_build",
     "crx_k_means_pp_sharded", "crx_k_means_sharded", "crx_pam_lloyds_sharded", "crx_silhouette_cluster_sharded",
     "crx_lsh_range_assignment_sharded", "crx_cube_range_assignment_sharded",
@@ -303,6 +303,13 @@ class LshTables:
         ids = np.zeros(self.L, np.int32)
         det = np.zeros((self.L, self.k), np.int32) if self.metric == EUCLIDEAN else None
         _check(lib().crx_lsh_hash_vector(self.h, _ptr(x)[0], _ptr(ids)[0], _ptr(det)[0]))
+        return ids, det
+
+    def hash_points(self, pts):
+        """getHash of every row of another point set: (bucket_ids[L][n], detailed[L][n][k] or None)."""
+        ids = np.zeros((self.L, pts.n), np.int32)
+        det = np.zeros((self.L, pts.n, self.k), np.int32) if self.metric == EUCLIDEAN else None
+        _check(lib().crx_lsh_hash_points(self.h, pts.h, _ptr(ids)[0], None if det is None else _ptr(det)[0], HOST))
         return ids, det
 
     def params(self):

@@ -820,6 +820,20 @@ int crx_lsh_hash_vector(const crx_lsh* t, const double* x, int32_t* bucket_ids, 
     return st;
 }
 
+int crx_lsh_hash_points(const crx_lsh* t, const crx_points* q, int32_t* bucket_ids, int32_t* detailed, int mem) {
+    CRX_REQUIRE(t && q && bucket_ids, "NULL argument");
+    CRX_REQUIRE(q->d == t->D, "dimension mismatch");
+    crx_ctx* c = t->ctx;
+    CRX_CUDA(cudaSetDevice(c->device));
+    const bool det = detailed && t->metric == CRX_EUCLIDEAN;
+    IoBuf<int32_t> b, h;
+    CRX_TRY(b.bind(c, bucket_ids, (size_t)t->L * q->n, mem, false));
+    if (det) CRX_TRY(h.bind(c, detailed, (size_t)t->L * q->n * t->k, mem, false));
+    CRX_TRY(crx_hash_rows(c, q, t->metric, t->k, t->L, t->d_proj, t->ldp, t->d_pnorm, t->d_t, t->d_r, t->w, t->nbuckets, det ? h.dev : nullptr, b.dev));
+    if (det) CRX_TRY(h.flush());
+    return b.flush();
+}
+
 int crx_lsh_params(const crx_lsh* t, double* cos_r, float* euc_v, float* euc_t, int32_t* euc_r) {
     CRX_REQUIRE(t, "NULL argument");
     if (cos_r && !t->cos_r.empty()) memcpy(cos_r, t->cos_r.data(), t->cos_r.size() * sizeof(double));

@@ -101,6 +101,9 @@ int crx_get_LSH_combined_buckets(const crx_lsh* t, int64_t query_row, int filter
 /* CustHashtable::getHash of a vector that is NOT stored in the tables (e.g. a query user, main.cpp:207):
  * bucket_ids[L]; detailed[L][k] (euclidean, may be NULL).  x[D] doubles on the host. */
 int crx_lsh_hash_vector(const crx_lsh* t, const double* x, int32_t* bucket_ids, int32_t* detailed);
+/* The same for every row of a point set that is not the stored one (all the query users of main.cpp:205-216 at once):
+ * bucket_ids[L][n]; detailed[L][n][k] (euclidean, may be NULL); buffers in `mem`. */
+int crx_lsh_hash_points(const crx_lsh* t, const crx_points* queries, int32_t* bucket_ids, int32_t* detailed, int mem);
 /* hash parameters actually drawn (for inspection / parity): cosine r[L][k][D] doubles,
  * euclidean v[L][k][D] floats, t[L][k] floats, r_i[L][k] ints.  Any pointer may be NULL.  Host. */
 int crx_lsh_params(const crx_lsh* t, double* cos_r, float* euc_v, float* euc_t, int32_t* euc_r);

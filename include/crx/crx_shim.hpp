@@ -78,11 +78,6 @@ struct Timed {
     }
 };
 
-// Bumped by every CustVector member that can change (or hand out a way to change) the image the engine sees:
-// constructors, assignment, destructor, setters, getDimensions().  A cached result that was verified against the
-// content of its inputs stays valid while the counter has not moved and the same objects are passed again.
-inline unsigned long& content_epoch() { static unsigned long e = 1; return e; }
-
 inline int metric_code(const std::string& m) {
     if (m == "euclidean") return CRX_EUCLIDEAN;
     if (m == "cosine") return CRX_COSINE;
@@ -144,24 +139,65 @@ struct Packed {
 // the reference's tables do, lsh_cube.hpp:70) for exactly its own lifetime.  Functions that receive pointers into such
 // a vector (the neighbour lists of the recommendation loop) then pass row numbers instead of packing and uploading the
 // neighbours again on every call.
+//
+// When its tables are deleted a registration is RETIRED, not dropped: the device copy stays for as long as no CustVector
+// inside the range has been created, destroyed or written since the copy was packed (crx::touched) -- every object of the
+// range is then still alive and still equal to its row.  A later loop over the same vector
+// (main.cpp:205-216 and :353-373 walk user_vectors again, against other tables and against centroids) finds its users
+// there (home_of) and is answered from ONE engine call over all rows instead of one per user.
 struct Registered {
     const char* begin;
     const char* end;
     size_t stride;
-    crx_points* pts;   // built with the rating metadata
-    void* table_set;   // the crx::TableSet<T> that owns the registration (T: the element type `stride` belongs to)
+    crx_points* pts;       // built with the rating metadata
+    void* table_set;       // the crx::TableSet<T> that owns the registration (NULL once retired)
+    unsigned long gen;     // identifies this packing of the range (never reused)
+    int64_t n;
+    bool dirty;            // a CustVector inside the range was created, destroyed or written since pts was packed
 };
-inline std::vector<Registered>& registry() { static std::vector<Registered> r; return r; }
-inline void register_points(const void* base, size_t n, size_t stride, crx_points* pts, void* table_set = nullptr) {
-    registry().push_back(Registered{(const char*)base, (const char*)base + n * stride, stride, pts, table_set});
+inline std::vector<Registered>& registry() { static std::vector<Registered>* r = new std::vector<Registered>(); return *r; }
+inline void register_points(const void* base, size_t n, size_t stride, crx_points* pts, void* table_set) {
+    static unsigned long generation = 0;
+    registry().push_back(Registered{(const char*)base, (const char*)base + n * stride, stride, pts, table_set, ++generation, (int64_t)n, false});
+}
+// Called by every CustVector member that creates, destroys or can alter (or hands out a way to alter) the image the engine
+// sees -- coordinates, unknown set, known mean: constructors, assignment, destructor, setters, getDimensions().
+// content_epoch() moves (remembered results that were verified against the content of objects outside any registered range
+// stay valid only while it stands), and a registered range that holds the object is marked dirty: its device copy is no
+// longer known to be current.
+inline unsigned long& content_epoch() { static unsigned long e = 1; return e; }
+inline void touched(const void* self) {
+    content_epoch()++;
+    const char* q = (const char*)self;
+    for (Registered& reg : registry()) if (q >= reg.begin && q < reg.end) reg.dirty = true;
 }
 inline void* table_set_of(const crx_points* pts) {
     for (const Registered& reg : registry()) if (reg.pts == pts) return reg.table_set;
     return nullptr;
 }
-inline void unregister_points(crx_points* pts) {
+// the tables over `pts` are gone.  Returns true when the registry took the device copy over (the caller must not destroy it).
+inline bool retire_points(crx_points* pts) {
     auto& r = registry();
-    for (size_t i = 0; i < r.size(); i++) if (r[i].pts == pts) { r.erase(r.begin() + i); return; }
+    // retired copies that can never be valid again go; besides the new one at most one older retired copy stays
+    int retired = 0;
+    for (size_t i = r.size(); i-- > 0;) {
+        if (r[i].table_set || r[i].pts == pts) continue;
+        if (r[i].dirty || ++retired > 1) { crx_points_destroy(r[i].pts); r.erase(r.begin() + i); }
+    }
+    for (size_t i = 0; i < r.size(); i++) {
+        if (r[i].pts != pts) continue;
+        if (!r[i].dirty) { r[i].table_set = nullptr; return true; }
+        r.erase(r.begin() + i);
+        return false;
+    }
+    return false;
+}
+// the registration (live or retired) whose range holds `p` and whose device copy is provably current, or NULL
+inline const Registered* home_of(const void* p, size_t stride) {
+    const char* q = (const char*)p;
+    for (const Registered& reg : registry())
+        if (q >= reg.begin && q < reg.end && reg.stride == stride && !reg.dirty && (size_t)(q - reg.begin) % stride == 0) return &reg;
+    return nullptr;
 }
 // the registered set that holds ALL of `ptrs` (rows[] receives their row numbers), or NULL
 template <typename T>
@@ -169,7 +205,7 @@ inline crx_points* registered_rows(const std::vector<CustVector<T>*>& ptrs, std:
     if (ptrs.empty()) return nullptr;
     for (const Registered& reg : registry()) {
         const char* p0 = (const char*)ptrs[0];
-        if (p0 < reg.begin || p0 >= reg.end || reg.stride != sizeof(CustVector<T>)) continue;
+        if (!reg.table_set || p0 < reg.begin || p0 >= reg.end || reg.stride != sizeof(CustVector<T>)) continue;
         rows.resize(ptrs.size());
         for (size_t i = 0; i < ptrs.size(); i++) {
             const char* q = (const char*)ptrs[i];

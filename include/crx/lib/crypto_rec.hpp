@@ -114,15 +114,28 @@ void parallel_quickSort(std::vector<dim_type>& sim, std::vector<type>& neighbors
 }
 
 namespace crx {
-// The table set whose batched result (TableSet::batch_for) can answer a call about `user`: the user is a stored row of a
-// registered vector that a set of LSH tables was built over.  row receives its row number.
+// The batch (TableSet::Batch) that can answer a call about `user` and the row of the user in it: the user is a stored row
+// of the tables the neighbours point into (own), or a row of another vector with a current device copy (ext).
 template <typename T>
-inline TableSet<T>* batch_owner(CustVector<T>& user, int32_t& row) {
+inline typename TableSet<T>::Batch* batch_of(std::vector<CustVector<T>*>& neighbors, CustVector<T>& user, TableSet<T>*& set, int64_t& row, int64_t& nq) {
+    if (neighbors.empty()) return nullptr;
+    const char* p0 = (const char*)neighbors[0];
+    set = nullptr;
+    for (const Registered& reg : registry())
+        if (reg.table_set && p0 >= reg.begin && p0 < reg.end && reg.stride == sizeof(CustVector<T>)) { set = (TableSet<T>*)reg.table_set; break; }
+    if (!set || !set->base || set->base->empty()) return nullptr;
     const char* q = (const char*)&user;
-    for (const Registered& reg : registry()) {
-        if (q < reg.begin || q >= reg.end || reg.stride != sizeof(CustVector<T>) || !reg.table_set) continue;
-        row = (int32_t)((q - reg.begin) / (ptrdiff_t)reg.stride);
-        return (TableSet<T>*)reg.table_set;
+    const char* b0 = (const char*)&(*set->base)[0];
+    if (q >= b0 && q < b0 + set->base->size() * sizeof(CustVector<T>)) {
+        row = (int64_t)((q - b0) / (ptrdiff_t)sizeof(CustVector<T>));
+        nq = set->n();
+        return &set->own;
+    }
+    const Registered* home = home_of(&user, sizeof(CustVector<T>));
+    if (home && set->ext.queries == home->pts && set->ext.epoch == home->gen) {
+        row = (int64_t)((q - home->begin) / (ptrdiff_t)home->stride);
+        nq = home->n;
+        return &set->ext;
     }
     return nullptr;
 }
@@ -135,20 +148,21 @@ std::vector<double> get_P_closest(std::vector<CustVector<dim_type>*>& neighbors,
     if (n == 0) return std::vector<double>();
     crx::Timed timed("get_P_closest");
     {
-        // the candidate list get_LSH_filtered_combined_buckets has just returned for this stored row: the batched call
-        // over all stored rows holds the answer (see TableSet)
-        int32_t row = -1;
-        crx::TableSet<dim_type>* set = crx::batch_owner(user, row);
-        if (set && set->last_row == row && (int64_t)set->last_list.size() == n && set->base && !set->base->empty()) {
+        // the candidate list get_LSH_filtered_combined_buckets has just returned for this user: the batched call over all
+        // users holds the answer (see TableSet::Batch)
+        crx::TableSet<dim_type>* set = nullptr;
+        int64_t row = -1, nq = 0;
+        typename crx::TableSet<dim_type>::Batch* bt = crx::batch_of(neighbors, user, set, row, nq);
+        if (bt && bt->last_row == row && (int64_t)bt->last_list.size() == n) {
             CustVector<dim_type>* base = &(*set->base)[0];
             bool same = true;
-            for (int64_t i = 0; i < n && same; i++) same = neighbors[i] == base + set->last_list[i];
-            if (same && set->batch_for(P) && set->b_ncand[row] == n) {
+            for (int64_t i = 0; i < n && same; i++) same = neighbors[i] == base + bt->last_list[i];
+            if (same && set->batch_for(*bt, P, nq) && bt->ncand[row] == n) {
                 int64_t kept = std::min<int64_t>(n, P);
                 std::vector<CustVector<dim_type>*> sorted((size_t)kept);
-                for (int64_t i = 0; i < kept; i++) sorted[i] = base + set->b_rows[(size_t)row * P + i];
+                for (int64_t i = 0; i < kept; i++) sorted[i] = base + bt->rows[(size_t)row * P + i];
                 neighbors.swap(sorted);
-                return std::vector<double>(set->b_sims.begin() + (size_t)row * P, set->b_sims.begin() + (size_t)row * P + kept);
+                return std::vector<double>(bt->sims.begin() + (size_t)row * P, bt->sims.begin() + (size_t)row * P + kept);
             }
         }
     }
@@ -191,18 +205,19 @@ template <typename dim_type>
 std::vector<int> get_top_N_recom(std::vector<CustVector<dim_type>*>& neighbors, CustVector<dim_type>& user, int N, std::vector<double> similarities) {
     crx::Timed timed("get_top_N_recom (similarities)");
     {
-        // neighbours and similarities are the ones the batched call produced for this stored row: its coin order is the
-        // literal sort of the same predicted ratings, so the first N entries are this call's answer
-        int32_t row = -1;
-        crx::TableSet<dim_type>* set = crx::batch_owner(user, row);
+        // neighbours and similarities are the ones the batched call produced for this user: its coin order is the literal sort
+        // of the same predicted ratings, so the first N entries are this call's answer
+        crx::TableSet<dim_type>* set = nullptr;
+        int64_t row = -1, nq = 0;
+        typename crx::TableSet<dim_type>::Batch* bt = crx::batch_of(neighbors, user, set, row, nq);
         int64_t n = (int64_t)neighbors.size();
-        if (set && set->batch_state == 1 && N >= 0 && N <= set->batch_nrec && n > 0 && n <= set->batch_P && (int64_t)similarities.size() == n &&
-            n == std::min<int64_t>(set->b_ncand[row], set->batch_P)) {
-            int P = set->batch_P;
+        if (bt && bt->state == 1 && N >= 0 && N <= bt->nrec && n > 0 && n <= bt->P && (int64_t)similarities.size() == n &&
+            n == std::min<int64_t>(bt->ncand[row], bt->P)) {
+            int P = bt->P;
             CustVector<dim_type>* base = &(*set->base)[0];
-            bool same = std::memcmp(similarities.data(), &set->b_sims[(size_t)row * P], (size_t)n * sizeof(double)) == 0;
-            for (int64_t i = 0; i < n && same; i++) same = neighbors[i] == base + set->b_rows[(size_t)row * P + i];
-            if (same) return std::vector<int>(set->b_recs.begin() + (size_t)row * set->batch_nrec, set->b_recs.begin() + (size_t)row * set->batch_nrec + N);
+            bool same = std::memcmp(similarities.data(), &bt->sims[(size_t)row * P], (size_t)n * sizeof(double)) == 0;
+            for (int64_t i = 0; i < n && same; i++) same = neighbors[i] == base + bt->rows[(size_t)row * P + i];
+            if (same) return std::vector<int>(bt->recs.begin() + (size_t)row * bt->nrec, bt->recs.begin() + (size_t)row * bt->nrec + N);
         }
     }
     crx::Resolved<dim_type> R(neighbors, user);
@@ -284,6 +299,54 @@ inline bool cached_cluster_recs(std::vector<CustVector<T>*>& neighbors, CustVect
 }
 }  // namespace crx
 
+namespace crx {
+// main.cpp:367-372: every user of a vector gets the recommendations of ONE of a few explicit neighbour lists (the members
+// of its nearest cluster).  When the user's vector has a current device copy (home_of), the second call with a given list
+// computes that list's recommendations for ALL rows of the vector in one engine call (crx_recommend_cluster with the
+// vector as the query set); later calls with the same list objects are answered from it while content_epoch() stands.
+template <typename T>
+inline bool home_list_recs(std::vector<CustVector<T>*>& neighbors, CustVector<T>& user, int N, std::vector<int>& out) {
+    size_t n = neighbors.size();
+    if (n < 1 || N <= 0 || N > 128 || n * user.getDimNumber() > ((size_t)1 << 22)) return false;
+    const Registered* home = home_of(&user, sizeof(CustVector<T>));
+    if (!home || (double)home->n * N > 64e6 || crx_points_d(home->pts) != (int32_t)user.getDimNumber()) return false;
+    int64_t hrow = (int64_t)(((const char*)&user - home->begin) / (ptrdiff_t)home->stride);
+    struct Entry {
+        std::vector<const void*> who;
+        unsigned long epoch = 0, stamp = 0;
+        const crx_points* home = nullptr;
+        int N = 0, calls = 0;
+        std::vector<int32_t> recs;   // [home rows][N]
+    };
+    static std::vector<Entry> cache(32);
+    static unsigned long clock_ = 0;
+    Entry* victim = &cache[0];
+    Entry* hit = nullptr;
+    for (Entry& e : cache) {
+        if (e.home == home->pts && e.epoch == content_epoch() && e.N == N && e.who.size() == n &&
+            std::memcmp(e.who.data(), neighbors.data(), n * sizeof(void*)) == 0) { hit = &e; break; }
+        if (e.stamp < victim->stamp) victim = &e;
+    }
+    if (!hit) {
+        *victim = Entry();
+        victim->who.assign(neighbors.begin(), neighbors.end());
+        victim->epoch = content_epoch(); victim->home = home->pts; victim->N = N; victim->calls = 1; victim->stamp = ++clock_;
+        return false;
+    }
+    hit->stamp = ++clock_;
+    if (hit->recs.empty()) {
+        if (++hit->calls < 2) return false;
+        Timed timed("crx_recommend_cluster, whole vector x list");
+        crx_points* users = list_copies<T>().get(neighbors.data(), n);
+        std::vector<int32_t> labels(n, 0), qlabels((size_t)home->n, 0);
+        hit->recs.assign((size_t)home->n * N, 0);
+        check(crx_recommend_cluster(context(), users, labels.data(), CRX_HOST, 1, home->pts, qlabels.data(), N, hit->recs.data(), CRX_HOST), "crx_recommend_cluster");
+    }
+    out.assign(hit->recs.begin() + (size_t)hrow * N, hit->recs.begin() + (size_t)(hrow + 1) * N);
+    return true;
+}
+}  // namespace crx
+
 // crypto_rec.hpp:328-345: similarities to ALL neighbours are computed first, no top-P cut
 template <typename dim_type>
 std::vector<int> get_top_N_recom(std::vector<CustVector<dim_type>*>& neighbors, CustVector<dim_type>& user, int N) {
@@ -291,6 +354,7 @@ std::vector<int> get_top_N_recom(std::vector<CustVector<dim_type>*>& neighbors, 
     {
         std::vector<int> cached;
         if (crx::cached_cluster_recs(neighbors, user, N, cached)) return cached;
+        if (crx::home_list_recs(neighbors, user, N, cached)) return cached;
     }
     crx::Resolved<dim_type> R(neighbors, user);
     int64_t n = (int64_t)neighbors.size();

@@ -47,35 +47,59 @@ struct TableSet {
             for (uint64_t m = seen_bits[w]; m; m &= m - 1) rows.push_back((int32_t)(w * 64 + (size_t)__builtin_ctzll(m)));
     }
 
-    // ---- the recommendation loop over the stored rows (main.cpp:159-170), answered from ONE batched engine call ----
-    // get_LSH_filtered_combined_buckets remembers the candidate list it returned for a stored row; when get_P_closest is
-    // then called with exactly that list, that row as the user and the second such call has been seen, crx_recommend_lsh
-    // is run once for every stored row (neighbour rows, similarities, the full literal order of the predicted coins) and
-    // this and the following calls are answered from its output.  The engine sees the rows as they were when the tables
-    // were built -- the same snapshot the per-user calls on registered rows use.
-    int32_t last_row = -1;               // stored row of the last combined-bucket query (filtered, all tables)
-    std::vector<int32_t> last_list;      // the rows it returned
-    int batch_P = -1, batch_nrec = 0, batch_state = 0;   // 0 not built, 1 ready, -1 not available for this table set / P
-    int batch_wanted = 0;                // qualifying get_P_closest calls seen so far
-    std::vector<int32_t> b_rows, b_recs, b_ncand;   // [n][P], [n][nrec], [n]
-    std::vector<double> b_sims;                      // [n][P]
-    bool batch_for(int P) {
-        if (batch_state == 1 && batch_P == P) return true;
-        if (batch_state == -1 && batch_P == P) return false;
-        if (!lsh || ++batch_wanted < 2) return false;
+    // ---- the recommendation loops (main.cpp:159-170 over the stored rows, :205-216 over another vector of users), answered
+    // from ONE batched engine call ----
+    // get_LSH_filtered_combined_buckets remembers the candidate list it returned for a user; when get_P_closest is then
+    // called with exactly that list and that user, and it is the second such call, crx_recommend_lsh is run once for all
+    // users (neighbour rows, similarities, the full literal order of the predicted coins) and this and the following calls
+    // are answered from its output.  "All users" = the stored rows (the engine sees them as they were when the tables were
+    // built -- the snapshot the per-user calls on registered rows use), or the rows of the vector the user lives in when
+    // that vector has a provably current device copy (crx::home_of).
+    struct Batch {
+        const crx_points* queries = nullptr;  // NULL: the stored rows
+        unsigned long epoch = 0;              // of the home registration (external queries)
+        int P = -1, nrec = 0, state = 0;      // state: 0 not built, 1 ready, -1 not available for this P
+        int wanted = 0;                       // qualifying get_P_closest calls seen so far
+        int64_t last_row = -1;                // row of the last combined-bucket query (filtered, all tables) ...
+        std::vector<int32_t> last_list;       // ... and the rows it returned
+        std::vector<int32_t> rows, recs, ncand;   // [n][P], [n][nrec], [n]
+        std::vector<double> sims;                  // [n][P]
+        void reset(const crx_points* q, unsigned long e) { *this = Batch(); queries = q; epoch = e; }
+    };
+    Batch own, ext;
+    // bucket ids (and h tuples) of every row of the external home vector, hashed in one engine call
+    std::vector<int32_t> ext_ids, ext_det;
+    const crx_points* ext_hashed = nullptr;
+    unsigned long ext_hashed_epoch = 0;
+    int ext_hash_wanted = 0;
+
+    bool batch_for(Batch& b, int P, int64_t nq) {
+        if (b.state == 1 && b.P == P) return true;
+        if (b.state == -1 && b.P == P) return false;
+        if (!lsh || ++b.wanted < 2) return false;
         Timed timed("batched crx_recommend_lsh");
-        int64_t N = n();
         int nrec = std::min(pts.d, 128);
         // a few hundred MB of host results at most; larger tables keep the per-user calls
-        if (P <= 0 || N <= 0 || (double)N * (P * 12.0 + nrec * 4.0) > 512e6) { batch_state = -1; batch_P = P; return false; }
-        b_rows.assign((size_t)N * P, -1); b_sims.assign((size_t)N * P, 0.0); b_recs.assign((size_t)N * nrec, 0); b_ncand.assign((size_t)N, 0);
-        int st = crx_recommend_lsh(context(), lsh, nullptr, 0, N, P, nrec, b_recs.data(), b_rows.data(), b_sims.data(), b_ncand.data(), CRX_HOST);
-        batch_P = P; batch_nrec = nrec;
-        batch_state = st == CRX_OK ? 1 : -1;   // outside the batched call's limits (P, D): the per-user calls answer
-        return batch_state == 1;
+        if (P <= 0 || nq <= 0 || (double)nq * (P * 12.0 + nrec * 4.0) > 512e6) { b.state = -1; b.P = P; return false; }
+        b.rows.assign((size_t)nq * P, -1); b.sims.assign((size_t)nq * P, 0.0); b.recs.assign((size_t)nq * nrec, 0); b.ncand.assign((size_t)nq, 0);
+        int st = crx_recommend_lsh(context(), lsh, b.queries, 0, nq, P, nrec, b.recs.data(), b.rows.data(), b.sims.data(), b.ncand.data(), CRX_HOST);
+        b.P = P; b.nrec = nrec;
+        b.state = st == CRX_OK ? 1 : -1;   // outside the batched call's limits (P, D): the per-user calls answer
+        return b.state == 1;
+    }
+    // all rows of the home vector hashed for every table (second qualifying call on)
+    bool ext_hash_for(const Registered* home) {
+        if (ext_hashed == home->pts && ext_hashed_epoch == home->gen) return true;
+        if (!lsh || crx_points_d(home->pts) != pts.d || ++ext_hash_wanted < 2 || (double)home->n * L * (k + 1) * 4.0 > 512e6) return false;
+        Timed timed("batched crx_lsh_hash_points");
+        ext_ids.assign((size_t)L * home->n, 0);
+        ext_det.assign(metric == CRX_EUCLIDEAN ? (size_t)L * home->n * k : 0, 0);
+        check(crx_lsh_hash_points(lsh, home->pts, ext_ids.data(), metric == CRX_EUCLIDEAN ? ext_det.data() : nullptr, CRX_HOST), "crx_lsh_hash_points");
+        ext_hashed = home->pts; ext_hashed_epoch = home->gen;
+        return true;
     }
     ~TableSet() {
-        if (pts.pts) unregister_points(pts.pts);
+        if (pts.pts && retire_points(pts.pts)) pts.pts = nullptr;   // the registry keeps the device copy (crx_shim.hpp)
         if (lsh) crx_lsh_destroy(lsh);
         if (cube) crx_cube_destroy(cube);
     }

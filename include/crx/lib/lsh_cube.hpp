@@ -46,21 +46,40 @@ std::vector<CustVector<T>*> combined(std::vector<CustHashtable<T>*>& tables, Cus
         int64_t N = set->n();
         const bool tuples = filtered && set->metric == CRX_EUCLIDEAN;
         std::vector<int32_t> b(set->L), d(tuples || row < 0 ? (size_t)set->L * set->k : 0);
+        const Registered* ext_home = nullptr;
+        int64_t ext_row = -1;
         if (row >= 0) {
             for (int l = 0; l < set->L; l++) {
                 b[l] = set->ids[(size_t)l * N + row];
                 if (tuples) std::copy(&set->det[((size_t)l * N + row) * set->k], &set->det[((size_t)l * N + row) * set->k] + set->k, d.begin() + (size_t)l * set->k);
             }
         } else {
-            std::vector<double> x(q->crxDimsRef().begin(), q->crxDimsRef().end());
-            check(crx_lsh_hash_vector(set->lsh, x.data(), b.data(), set->metric == CRX_EUCLIDEAN ? d.data() : nullptr), "crx_lsh_hash_vector");
+            // a user of another vector: when that vector has a provably current device copy, all its rows are hashed in one call
+            const Registered* home = home_of(q, sizeof(CustVector<T>));
+            if (home && set->ext_hash_for(home)) {
+                ext_row = (int64_t)(((const char*)q - home->begin) / (ptrdiff_t)home->stride);
+                ext_home = home;
+                for (int l = 0; l < set->L; l++) {
+                    b[l] = set->ext_ids[(size_t)l * home->n + ext_row];
+                    if (set->metric == CRX_EUCLIDEAN)
+                        std::copy(&set->ext_det[((size_t)l * home->n + ext_row) * set->k], &set->ext_det[((size_t)l * home->n + ext_row) * set->k] + set->k, d.begin() + (size_t)l * set->k);
+                }
+            } else {
+                std::vector<double> x(q->crxDimsRef().begin(), q->crxDimsRef().end());
+                check(crx_lsh_hash_vector(set->lsh, x.data(), b.data(), set->metric == CRX_EUCLIDEAN ? d.data() : nullptr), "crx_lsh_hash_vector");
+                if (home) { ext_row = (int64_t)(((const char*)q - home->begin) / (ptrdiff_t)home->stride); ext_home = home; }
+            }
         }
         std::vector<int32_t> rows;
         set->union_rows(b.data(), tuples ? d.data() : nullptr, rows);
         CustVector<T>* base = &(*set->base)[0];
         out.reserve(rows.size());
         for (int32_t r : rows) out.push_back(base + r);
-        if (filtered && row >= 0) { set->last_row = row; set->last_list.swap(rows); }
+        if (filtered && row >= 0) { set->own.last_row = row; set->own.last_list.swap(rows); }
+        else if (filtered && ext_home) {
+            if (set->ext.queries != ext_home->pts || set->ext.epoch != ext_home->gen) set->ext.reset(ext_home->pts, ext_home->gen);
+            set->ext.last_row = ext_row; set->ext.last_list.swap(rows);
+        }
         return out;
     }
     std::set<CustVector<T>*> u;  // pointer order == row order (lsh_cube.hpp:96,104)

@@ -133,7 +133,7 @@ int main() {
             for (Vec* v : nb) batched[u].ids.push_back(v->getId());
             batched[u].recs = get_top_N_recom(nb, users[u], 2, batched[u].sims);
         }
-        EXPECT(tables[0]->set->batch_state == 1, "the batched call did not run (state %d)", tables[0]->set->batch_state);
+        EXPECT(tables[0]->set->own.state == 1, "the batched call did not run (state %d)", tables[0]->set->own.state);
         for (size_t u = 0; u < users.size(); u++) {
             EXPECT(per_user[u].ids == batched[u].ids, "neighbours of user %zu", u);
             EXPECT(per_user[u].sims == batched[u].sims, "similarities of user %zu", u);
@@ -155,6 +155,74 @@ int main() {
             (*others[2].getDimensions())[1] += 3.0;
         }
         for (auto t : tables) delete t;
+    }
+    // ---- 4. users of ANOTHER vector against the tables (main.cpp:205-216), and against centroids and explicit lists
+    // (main.cpp:353-373): the vector has a device copy from tables of its own that were deleted (as user_vectors has after
+    // main.cpp:175-176); while no CustVector is created, destroyed or written, all its rows are answered from single calls
+    {
+        const int P = 20;
+        std::vector<Vec> tableUsers = make_users(600, D, 7), queryUsers = make_users(300, D, 8), cents = make_users(12, D, 9), members = make_users(120, D, 10);
+        auto give_home = [&]() { auto t0 = create_LSH_hashtables<double>(queryUsers, "cosine", 3, 4, 100, 0.4); for (auto t : t0) delete t; };
+        std::vector<CustHashtable<double>*> tabs = create_LSH_hashtables<double>(tableUsers, "cosine", 3, 4, 100, 0.4);
+        struct Ans { std::vector<std::string> ids; std::vector<double> sims; std::vector<int> recs; };
+        auto lsh_loop = [&](std::vector<Vec>& qs, std::vector<Ans>& ans) {
+            ans.assign(qs.size(), Ans());
+            for (size_t u = 0; u < qs.size(); u++) {
+                std::vector<Vec*> nb = get_LSH_filtered_combined_buckets(tabs, &qs[u]);
+                if (nb.empty()) continue;
+                ans[u].sims = get_P_closest(nb, qs[u], P);
+                for (Vec* v : nb) ans[u].ids.push_back(v->getId());
+                ans[u].recs = get_top_N_recom(nb, qs[u], 2, ans[u].sims);
+            }
+        };
+        for (int round = 0; round < 2; round++) {
+            give_home();
+            std::vector<Ans> warm, cold;
+            lsh_loop(queryUsers, warm);
+            EXPECT(tabs[0]->set->ext.state == 1 && tabs[0]->set->ext_hashed != nullptr, "round %d: the whole-vector calls did not run (state %d)", round, tabs[0]->set->ext.state);
+            std::vector<Vec> copies(queryUsers);       // fresh addresses (and the epoch moves: no home any more)
+            lsh_loop(copies, cold);
+            for (size_t u = 0; u < queryUsers.size(); u++)
+                EXPECT(warm[u].ids == cold[u].ids && warm[u].sims == cold[u].sims && warm[u].recs == cold[u].recs, "round %d: external user %zu", round, u);
+            // an edit between the rounds; then one more edit AFTER the home was given: the per-user path must see it
+            queryUsers[5].setKnownMean(queryUsers[5].getKnownMean() + 0.5);
+            (*queryUsers[9].getDimensions())[2] += 1.0;
+        }
+        give_home();
+        (*queryUsers[11].getDimensions())[4] -= 2.0;
+        {
+            std::vector<Ans> warm, cold;
+            lsh_loop(queryUsers, warm);
+            std::vector<Vec> copies(queryUsers);
+            lsh_loop(copies, cold);
+            for (size_t u = 0; u < queryUsers.size(); u++)
+                EXPECT(warm[u].ids == cold[u].ids && warm[u].sims == cold[u].sims && warm[u].recs == cold[u].recs, "after a late edit: external user %zu", u);
+        }
+        // nearest centroid + the recommendations of that cluster's list
+        std::vector<std::vector<Vec*> > lists(3);
+        for (size_t i = 0; i < members.size(); i++) lists[i % 3].push_back(&members[i]);
+        auto centroid_loop = [&](std::vector<Vec>& qs, std::vector<std::vector<double> >& dist, std::vector<std::vector<int> >& recs) {
+            dist.assign(qs.size(), std::vector<double>());
+            recs.assign(qs.size(), std::vector<int>());
+            for (size_t u = 0; u < qs.size(); u++) {
+                for (size_t c = 0; c < cents.size(); c++) dist[u].push_back(qs[u].euclideanDistance(&cents[c]));
+                recs[u] = get_top_N_recom(lists[u % 3], qs[u], 2);
+            }
+        };
+        for (int round = 0; round < 2; round++) {
+            give_home();
+            std::vector<std::vector<double> > wd, cd;
+            std::vector<std::vector<int> > wr, cr;
+            centroid_loop(queryUsers, wd, wr);
+            EXPECT(crx::pair_fan().m_home != nullptr, "round %d: the whole-vector pair call did not run", round);
+            std::vector<Vec> copies(queryUsers);
+            centroid_loop(copies, cd, cr);
+            for (size_t u = 0; u < queryUsers.size(); u++) EXPECT(wd[u] == cd[u] && wr[u] == cr[u], "round %d: centroid loop, user %zu", round, u);
+            (*cents[3].getDimensions())[1] += 0.75;
+            members[4].setKnownMean(members[4].getKnownMean() - 0.25);
+            (*queryUsers[7].getDimensions())[0] += 1.5;
+        }
+        for (auto t : tabs) delete t;
     }
     if (!g_bad) std::printf("OK\n");
     else std::printf("%d mismatches\n", g_bad);

@@ -84,6 +84,16 @@ def test_lsh_tables_oracle(ctx, port, dtype, case):
     for q in (0, 1500, 3000):
         for filt in (0, 1):
             assert np.array_equal(t.combined_buckets(q, filt), port.lsh_candidates(X64, metric, k, L, div, w, 555, q, filt))
+    # a whole point set hashed like queries (crx_lsh_hash_points): the stored rows get their stored ids, other vectors
+    # what the one-vector call gives
+    hb, hd = t.hash_points(P)
+    assert np.array_equal(hb, ids) and (metric != EUCLIDEAN or np.array_equal(hd, det))
+    Y = X64[::-1][:40] * 1.25 + 0.5
+    Q = ctx.points(Y)
+    hb, hd = t.hash_points(Q)
+    for i in (0, 7, 39):
+        b1, d1 = t.hash_vector(Y[i])
+        assert np.array_equal(hb[:, i], b1) and (metric != EUCLIDEAN or np.array_equal(hd[:, i], d1))
 
 
 @pytest.mark.parametrize("dtype", [np.float64, np.float32])
