@@ -33,6 +33,7 @@ void write_back(std::vector<CustVector<T> >& vecs, const std::vector<int32_t>& l
 // assignment.hpp:55-80 (centroids that alias input vectors get setCluster(c, 0) through centroid_rows)
 template <typename vector_type>
 void lloyds_assignment(std::vector<CustVector<vector_type> >& input_vectors, std::vector<CustVector<vector_type>*>& centroids, std::string metric_type) {
+    crx::Timed timed("lloyds_assignment");
     crx::Packed<vector_type> P;
     P.from_vector(input_vectors);
     std::vector<double> C;

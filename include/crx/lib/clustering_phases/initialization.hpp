@@ -22,6 +22,7 @@ std::vector<CustVector<vector_type>*> rand_selection(std::vector<CustVector<vect
 // initialization.hpp:72-156
 template <typename vector_type>
 std::vector<CustVector<vector_type>*> k_means_pp(std::vector<CustVector<vector_type> >& input_vectors, int cluster_num, std::string metric_type) {
+    crx::Timed timed("k_means_pp");
     crx::Packed<vector_type> P;
     P.from_vector(input_vectors);
     std::vector<int32_t> rows(cluster_num);

@@ -12,6 +12,7 @@
 // of that name are deleted); on `false` the centres are left untouched.
 template <typename vector_type>
 bool k_means(std::vector<CustVector<vector_type> >& input_vectors, std::vector<CustVector<vector_type>*>& centers, std::string metric_type, double min_dist) {
+    crx::Timed timed("k_means");
     int K = (int)centers.size();
     int D = K ? (int)centers[0]->getDimNumber() : 0;
     crx::Packed<vector_type> P;
