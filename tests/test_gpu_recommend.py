@@ -1,4 +1,6 @@
 """GPU parity (through the C ABI): cosine top-P neighbours, rating prediction, top-N coins."""
+import os
+
 import numpy as np
 import pytest
 
@@ -7,6 +9,8 @@ from crypto_recommendation_b200 import capi, synth
 from helpers import assert_float_close, topp_compare
 
 pytestmark = pytest.mark.gpu
+# CRX_NO_TC=1 keeps everything on the FP64 scan, whose candidate list holds 32 entries
+NO_TC = os.environ.get("CRX_NO_TC") == "1"
 WANT = ("recs", "nbr_rows", "nbr_sims", "ncand", "status")
 
 
@@ -78,6 +82,10 @@ def test_rec_lsh_cosine_oracle(ctx, port, dtype, n, P_, Nrec, k, L):
     U, unk, mean = synth.rating_users(n, 100, seed=300 + n, dtype=dtype)
     P = ctx.points(U, unk, mean)
     t = capi.LshTables(ctx, P, "cosine", k, L, 100, 0.4, 31337)
+    if NO_TC and P_ > 32:   # outside the FP64 scan's limit: refused, never answered approximately
+        with pytest.raises(capi.CrxError):
+            capi.recommend_lsh(ctx, t, P_, Nrec, want=WANT)
+        return
     out = capi.recommend_lsh(ctx, t, P_, Nrec, want=WANT)
     ref = port.recommend_lsh(U.astype(np.float64), unk, mean, COSINE, k, L, 100, 0.4, P_, Nrec, 31337)
     check_rec(ctx, out, ref)
