@@ -849,12 +849,15 @@ __global__ void sq_sizes_kernel(const int32_t* __restrict__ off, int ngroups, do
 // second pass of the batched top-P: rounds of collect -> evaluate -> resolve over the queued queries
 // (recommend_pass2.cuh) until every query carries the reference's list
 // ------------------------------------------------------------------------------------------------
-// CRX_P2_DEBUG: wall-clock marks (stream synchronised) through one crx_recommend_lsh call
+// CRX_P2_DEBUG: wall-clock marks (stream synchronised) through one crx_recommend_lsh call; CRX_P2_DEBUG=host: the same marks
+// without the extra synchronisations, i.e. where the HOST spends its time (its own waits included)
 struct DebugClock {
-    bool on; cudaStream_t s; double t0;
+    bool on, sync; cudaStream_t s; double t0;
     static double now() { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6; }
-    DebugClock(cudaStream_t st) : on(getenv("CRX_P2_DEBUG") != nullptr), s(st), t0(0) { if (on) { cudaStreamSynchronize(s); t0 = now(); } }
-    void mark(const char* what) { if (!on) return; cudaStreamSynchronize(s); double t = now(); fprintf(stderr, "[crx clock] %-28s %8.2f ms\n", what, t - t0); t0 = t; }
+    DebugClock(cudaStream_t st) : on(getenv("CRX_P2_DEBUG") != nullptr), sync(on && strcmp(getenv("CRX_P2_DEBUG"), "host") != 0), s(st), t0(0) {
+        if (on) { if (sync) cudaStreamSynchronize(s); t0 = now(); }
+    }
+    void mark(const char* what) { if (!on) return; if (sync) cudaStreamSynchronize(s); double t = now(); fprintf(stderr, "[crx clock] %-28s %8.2f ms\n", what, t - t0); t0 = t; }
 };
 
 struct P2Host {
@@ -868,6 +871,7 @@ struct P2Host {
     const int32_t* qgid; int64_t qstride; const int32_t* cgid; int64_t cstride;   // SIMT path: group ids
     double eps, unscale;
     const double* eps_q;   // per query row (centred operands) or NULL
+    size_t free_bytes;     // device memory that was free when the first pass had been enqueued
     P2Blocks blocks;
     int32_t* recs; int32_t* rows; double* sims; int32_t* status;
 };
@@ -1013,8 +1017,9 @@ static int pass2_run(crx_ctx* c, const P2Host& h, P2QueueBuf* qa, P2QueueBuf* qb
     for (int round = 0; n > 0 && round < max_rounds; round++) {
         CRX_CUDA(cudaMemsetAsync(nxt->count.p, 0, sizeof(unsigned int), c->stream));
         if (p2_debug) CRX_CUDA(cudaMemsetAsync(dbg.p, 0, 8 * sizeof(unsigned long long), c->stream));
-        size_t free_b = 0, total_b = 0;
-        CRX_CUDA(cudaMemGetInfo(&free_b, &total_b));
+        // (cudaMemGetInfo costs 15-50 ms of host time per call with a populated memory pool -- and the GPU idles meanwhile: the
+        // query is made once, while the first pass runs, see recommend_lsh_impl; a round frees what it allocates)
+        size_t free_b = h.free_bytes;
         for (auto& b : c->big_free) free_b += b.second;   // blocks the context keeps between calls are available to this round
         // budget for the collected lists: one third for the pass masks of the threshold scan (32 B per row and column tile), the
         // rest for rows + similarities (12 B per entry).  A queue that needs more is processed in slices.
@@ -1046,8 +1051,11 @@ static int pass2_run(crx_ctx* c, const P2Host& h, P2QueueBuf* qa, P2QueueBuf* qb
             CRX_TRY(qrow_abs.alloc(c, ns)); CRX_TRY(theta_f.alloc(c, ns)); CRX_TRY(allf.alloc(c, ns)); CRX_TRY(colx_eff.alloc(c, ns));
             { CRX_KERNEL(c, "p2_prepare"); p2_prepare_kernel<<<crx_grid(ns, 256), 256, 0, c->stream>>>(w, ns, h.q_begin, 1.0 / h.unscale, theta_f.p, qrow_abs.p, allf.p, colx_eff.p); }
             TcOperand opA;
+            clk.mark("  round buffers");
             CRX_TRY(crx_tc_gather(c, *h.opQ, qrow_abs.p, ns, &opA));
+            clk.mark("  gather operand");
             CRX_TRY(cmask.alloc(c, (size_t)crx_tc_collect_mask_words(ns, N)));
+            clk.mark("  mask alloc");
             rows_pad = ((int64_t)ns + 127) / 128 * 128;
             CRX_TRY(crx_tc_collect(c, opA, ns, *h.opB, h.qcode, qrow_abs.p, h.ccode, h.k, h.L, h.dense, theta_f.p, colx_eff.p, cmask.p, count.p));
             { CRX_KERNEL(c, "p2_all_count"); p2_all_count_kernel<<<crx_grid(ns, 256), 256, 0, c->stream>>>(allf.p, ns, w.q, h.nc, count.p, ovf.p); }
@@ -1370,10 +1378,13 @@ static int recommend_lsh_impl(crx_ctx* c, const crx_lsh* t, const crx_points* qu
 #undef LAUNCH_F
     }
     CRX_CUDA(cudaGetLastError());
+    size_t free_now = 0, total_now = 0;
+    if (pass2) CRX_CUDA(cudaMemGetInfo(&free_now, &total_now));   // slow call: made here, behind the work enqueued above
     clk.mark("rec_finalize");
     if (pass2) {
         P2Host h;
         memset(&h, 0, sizeof(h));
+        h.free_bytes = free_now;
         h.base = base; h.queries = queries; h.q_begin = q_begin; h.nq = nq; h.P = P; h.Nrec = Nrec; h.nc = nc.p; h.use_tc = use_tc;
         h.opQ = self ? &opB : &opA; h.opB = &opB; h.qcode = qcode; h.ccode = ccode.p; h.k = t->k; h.L = L; h.dense = dense_cols;
         h.qgid = qgid_base; h.qstride = qstride; h.cgid = t->gid; h.cstride = N;
