@@ -205,7 +205,9 @@ inline crx_points* registered_rows(const std::vector<CustVector<T>*>& ptrs, std:
     if (ptrs.empty()) return nullptr;
     for (const Registered& reg : registry()) {
         const char* p0 = (const char*)ptrs[0];
-        if (!reg.table_set || p0 < reg.begin || p0 >= reg.end || reg.stride != sizeof(CustVector<T>)) continue;
+        // (a dirty registration -- some vector of the range was written after the device copy was packed -- is not used: the
+        // caller packs the live values instead, as the reference's tables, which hold live pointers, would see them)
+        if (!reg.table_set || reg.dirty || p0 < reg.begin || p0 >= reg.end || reg.stride != sizeof(CustVector<T>)) continue;
         rows.resize(ptrs.size());
         for (size_t i = 0; i < ptrs.size(); i++) {
             const char* q = (const char*)ptrs[i];

@@ -122,7 +122,7 @@ inline typename TableSet<T>::Batch* batch_of(std::vector<CustVector<T>*>& neighb
     const char* p0 = (const char*)neighbors[0];
     set = nullptr;
     for (const Registered& reg : registry())
-        if (reg.table_set && p0 >= reg.begin && p0 < reg.end && reg.stride == sizeof(CustVector<T>)) { set = (TableSet<T>*)reg.table_set; break; }
+        if (reg.table_set && !reg.dirty && p0 >= reg.begin && p0 < reg.end && reg.stride == sizeof(CustVector<T>)) { set = (TableSet<T>*)reg.table_set; break; }
     if (!set || !set->base || set->base->empty()) return nullptr;
     const char* q = (const char*)&user;
     const char* b0 = (const char*)&(*set->base)[0];

@@ -154,6 +154,24 @@ int main() {
             others[1].setKnownMean(others[1].getKnownMean() - 0.5);
             (*others[2].getDimensions())[1] += 3.0;
         }
+        // a stored vector is edited while its tables live: the bucket placement stays (as in the reference), the values are live
+        users[3].setKnownMean(users[3].getKnownMean() + 1.0);
+        (*users[10].getDimensions())[7] += 0.5;
+        {
+            std::vector<Vec> copies(users);   // same contents at fresh addresses; candidates by row number
+            for (size_t u : {(size_t)3, (size_t)10, (size_t)11, (size_t)400}) {
+                std::vector<Vec*> nb = get_LSH_filtered_combined_buckets(tables, &users[u]);
+                if (nb.empty()) continue;
+                std::vector<Vec*> nbc;
+                for (Vec* v : nb) nbc.push_back(&copies[(size_t)(v - &users[0])]);
+                std::vector<double> s1 = get_P_closest(nb, users[u], P), s2 = get_P_closest(nbc, copies[u], P);
+                EXPECT(s1 == s2, "similarities of stored user %zu after an edit of stored vectors", u);
+                bool same = nb.size() == nbc.size();
+                for (size_t i = 0; same && i < nb.size(); i++) same = (nb[i] - &users[0]) == (nbc[i] - &copies[0]);
+                EXPECT(same, "neighbours of stored user %zu after an edit of stored vectors", u);
+                EXPECT(get_top_N_recom(nb, users[u], 2, s1) == get_top_N_recom(nbc, copies[u], 2, s2), "coins of stored user %zu after an edit", u);
+            }
+        }
         for (auto t : tables) delete t;
     }
     // ---- 4. users of ANOTHER vector against the tables (main.cpp:205-216), and against centroids and explicit lists
