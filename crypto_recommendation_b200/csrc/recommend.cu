@@ -795,7 +795,10 @@ __global__ void __launch_bounds__(32) warp_qs_kernel(double* sims, int32_t* ids,
     __shared__ int posge[128];
     __shared__ double hk[128];
     __shared__ int hv[128];
-    warp_qs_topn_big(sims, ids, n, need, posge, hk, hv);
+    __shared__ double sk[128];
+    __shared__ int sv[128];
+    __shared__ int gp[128];
+    warp_qs_topn_big(sims, ids, n, need, QsScratch{posge, hk, hv, sk, sv, gp});
 }
 
 // group id of an external query in one Euclidean table: the stored rows of its bucket are walked in insertion order; the

@@ -120,9 +120,23 @@ __device__ __forceinline__ double p2_tail_theta(const P2Blocks& b, int64_t qrel,
 //   * a pivot that is a minimum of its range stays in place together with all equal elements behind the last larger one.
 // `need` <= 126.  posge / hk / hv: per-warp scratch of 128 entries each.
 // ------------------------------------------------------------------------------------------------
-__device__ __noinline__ void warp_qs_topn_big(double* key, int* val, int n, int need, int* posge, double* hk, int* hv) {
+// A warp that walks a list of 10^5..10^6 entries alone is bound by the latency of its loads (the lists of one round are GBs:
+// every step misses L2).  Once per 128-entry step the lanes ask for the lines eight steps ahead: 32 x 128 B of keys (four
+// steps' worth) and 32 x 128 B of rows (eight steps' worth) on their way to L2.
+__device__ __forceinline__ void p2_prefetch_ahead(const double* key, const int* val, int base0, int end, int lane) {
+    const int ek = base0 + 1024 + lane * 16, ev = base0 + 1024 + lane * 32;
+    if (ek < end) asm volatile("prefetch.global.L2 [%0];" ::"l"(key + ek));
+    if (val && ev < end) asm volatile("prefetch.global.L2 [%0];" ::"l"(val + ev));
+}
+
+// per-warp scratch of warp_qs_topn_big (shared memory): posge/hk/hv [128] for the literal steps, sk/sv [128] = the head of the
+// range as it was before a partition step, gp [128] = where the first 128 ">=" elements of the step came from
+struct QsScratch { int* posge; double* hk; int* hv; double* sk; int* sv; int* gp; };
+
+__device__ __noinline__ void warp_qs_topn_big(double* key, int* val, int n, int need, const QsScratch S) {
     const int lane = threadIdx.x & 31;
     const unsigned lt = (1u << lane) - 1u;
+    int* posge = S.posge; double* hk = S.hk; int* hv = S.hv;
     int st_lo[128], st_hi[128];
     int sp = 1;
     st_lo[0] = 0; st_hi[0] = n - 1;
@@ -131,13 +145,27 @@ __device__ __noinline__ void warp_qs_topn_big(double* key, int* val, int n, int 
         int lo = st_lo[sp], hi = st_hi[sp];
         while (lo < hi && lo < need) {
             const double pivot = key[hi];
+            const int pv = val[hi];
             const int m = hi - lo;
+            // ONE pass per partition step: the ">=" elements are counted AND moved to the front as they come (stable, in place: a
+            // destination is never behind its source, and a step of 128 entries is in registers before anything is written).
+            // Nothing moves when every element is ">=" (the two cases that end or shorten the range without a partition).  A
+            // step that turns out to be literal needs the "<" elements the compaction has overwritten: they lie in the head of
+            // the range (fewer than `need` <= 126 elements moved), which is saved first.
+            for (int j = lane; j < min(m, 128); j += 32) { S.sk[j] = key[lo + j]; S.sv[j] = val[lo + j]; }
+            __syncwarp();
             int cnt = 0, lastgt = -1, q1 = 0x7fffffff;
             bool alleq = true;
             for (int base0 = lo; base0 < hi; base0 += 128) {   // four groups of 32 per step: enough loads in flight on long lists
                 double k4[4];
+                int v4[4];
+                bool g4[4];
+                p2_prefetch_ahead(key, val, base0, hi, lane);
 #pragma unroll
-                for (int u = 0; u < 4; u++) { const int e = base0 + u * 32 + lane; k4[u] = e < hi ? key[e] : 0.0; }
+                for (int u = 0; u < 4; u++) { const int e = base0 + u * 32 + lane; k4[u] = e < hi ? key[e] : 0.0; g4[u] = e < hi && k4[u] >= pivot; }
+#pragma unroll
+                for (int u = 0; u < 4; u++) { const int e = base0 + u * 32 + lane; v4[u] = g4[u] ? val[e] : 0; }
+                __syncwarp();
 #pragma unroll
                 for (int u = 0; u < 4; u++) {
                     const int base = base0 + u * 32;
@@ -145,40 +173,39 @@ __device__ __noinline__ void warp_qs_topn_big(double* key, int* val, int n, int 
                     const int e = base + lane;
                     const bool in = e < hi;
                     const double k = k4[u];
-                    const unsigned bg = __ballot_sync(0xffffffffu, in && k >= pivot);
+                    const unsigned bg = __ballot_sync(0xffffffffu, g4[u]);
                     const unsigned bgt = __ballot_sync(0xffffffffu, in && k > pivot);
                     const unsigned blt = __ballot_sync(0xffffffffu, in && !(k >= pivot));
                     alleq = alleq && __all_sync(0xffffffffu, !in || k == pivot);
+                    if (g4[u]) {
+                        const int r = cnt + __popc(bg & lt);
+                        if (r < 128) S.gp[r] = e;
+                        if (lo + r != e) { key[lo + r] = k; val[lo + r] = v4[u]; }
+                    }
                     cnt += __popc(bg);
                     if (bgt) lastgt = base + 31 - __clz(bgt);
                     if (blt && q1 == 0x7fffffff) q1 = base + __ffs(blt) - 1;
                 }
+                __syncwarp();
             }
             if (alleq) break;
             if (cnt == m) { hi = lastgt; continue; }   // the pivot and its equals behind the last larger element stay
             const int p = lo + cnt;
-            const int pv = val[hi];
             const bool literal = p + 1 < need && p < hi;
             int rho = 0;
             if (literal) {
-                // ranks of the ">=" elements behind q1
-                int seen = 0;
-                for (int base = q1 + 1; base < hi; base += 32) {
-                    const int e = base + lane;
-                    const bool g = e < hi && key[e] >= pivot;
-                    const unsigned bg = __ballot_sync(0xffffffffu, g);
-                    if (g) { int r = seen + __popc(bg & lt) + 1; if (r < 127) posge[r] = e; }
-                    seen += __popc(bg);
-                }
-                rho = seen + 1;
+                // the ">=" elements behind q1 (the first q1 - lo elements of the range are ">=" and did not move), by rank
+                const int lead = q1 - lo;
+                rho = cnt - lead + 1;
+                for (int r = 1 + lane; r < rho; r += 32) posge[r] = S.gp[lead + r - 1];
                 if (lane == 0) posge[rho] = hi;
                 __syncwarp();
-                if (lane == 0) {
+                if (lane == 0) {   // the elements the literal algorithm leaves at those places (read from the saved head)
                     int pp = 1;
                     for (int r = 1; r <= rho; r++) {
                         const int src = q1 + r - 1;
-                        const double ks = key[src];
-                        if (!(ks >= pivot)) { hk[r] = ks; hv[r] = val[src]; }
+                        const double ks = S.sk[src - lo];
+                        if (!(ks >= pivot)) { hk[r] = ks; hv[r] = S.sv[src - lo]; }
                         else {
                             while (posge[pp] < src) pp++;
                             hk[r] = hk[pp]; hv[r] = hv[pp];
@@ -186,31 +213,6 @@ __device__ __noinline__ void warp_qs_topn_big(double* key, int* val, int n, int 
                     }
                 }
                 __syncwarp();
-            }
-            // stable compaction of the ">=" elements to [lo, p)
-            {
-                int done = 0;
-                for (int base0 = lo; base0 < hi; base0 += 128) {
-                    double k4[4];
-                    int v4[4];
-                    bool g4[4];
-#pragma unroll
-                    for (int u = 0; u < 4; u++) { const int e = base0 + u * 32 + lane; k4[u] = e < hi ? key[e] : 0.0; g4[u] = e < hi && k4[u] >= pivot; }
-#pragma unroll
-                    for (int u = 0; u < 4; u++) { const int e = base0 + u * 32 + lane; v4[u] = g4[u] ? val[e] : 0; }
-                    __syncwarp();
-#pragma unroll
-                    for (int u = 0; u < 4; u++) {
-                        const int e = base0 + u * 32 + lane;
-                        const unsigned bg = __ballot_sync(0xffffffffu, g4[u]);
-                        if (g4[u]) {
-                            const int dst = lo + done + __popc(bg & lt);
-                            if (dst != e) { key[dst] = k4[u]; val[dst] = v4[u]; }
-                        }
-                        done += __popc(bg);
-                    }
-                    __syncwarp();
-                }
             }
             if (lane == 0) { key[p] = pivot; val[p] = pv; }
             if (literal) {
@@ -585,6 +587,9 @@ p2_resolve_kernel(const TB* __restrict__ xb, P2Resolve a) {
     __shared__ int posge[QW][128];
     __shared__ double hk[QW][128];
     __shared__ int hv[QW][128];
+    __shared__ double qs_sk[QW][128];
+    __shared__ int qs_sv[QW][128];
+    __shared__ int qs_gp[QW][128];
     __shared__ int s_idx[QW][P2_MAXP];
     __shared__ double s_sim[QW][P2_MAXP];
     __shared__ double s_pred[QW][128];
@@ -619,6 +624,7 @@ p2_resolve_kernel(const TB* __restrict__ xb, P2Resolve a) {
     WarpTop top;
     for (int base = 0; base < cnt; base += 128) {
         double k4[4];
+        p2_prefetch_ahead(key, nullptr, base, cnt, lane);
 #pragma unroll
         for (int u = 0; u < 4; u++) { const int e = base + u * 32 + lane; k4[u] = e < cnt ? key[e] : -INFINITY; }
 #pragma unroll
@@ -681,6 +687,8 @@ p2_resolve_kernel(const TB* __restrict__ xb, P2Resolve a) {
     }
     // ---- R to the front, in row order (four groups of 32 entries per step; rows are read for the members only)
     int m = 0;
+    if (tp == -INFINITY && rlim == cnt) m = cnt;   // R = every candidate: the list is R already
+    else
     for (int base = 0; base < rlim; base += 128) {
         double k4[4];
 #pragma unroll
@@ -708,7 +716,7 @@ p2_resolve_kernel(const TB* __restrict__ xb, P2Resolve a) {
         atomicAdd(&a.dbg[kd + 0], (unsigned long long)m); atomicAdd(&a.dbg[kd + 1], (unsigned long long)cnt); atomicAdd(&a.dbg[kd + 2], 1ull);
         if (s_estar == TP) atomicAdd(&a.dbg[kd + 3], 1ull);
     }
-    warp_qs_topn_big(key, val, m, keep, posge[warp], hk[warp], hv[warp]);
+    warp_qs_topn_big(key, val, m, keep, QsScratch{posge[warp], hk[warp], hv[warp], qs_sk[warp], qs_sv[warp], qs_gp[warp]});
     for (int j = lane; j < keep; j += 32) { s_idx[warp][j] = val[j]; s_sim[warp][j] = key[j]; }
     __syncwarp();
     if (lane == 0) {
@@ -869,6 +877,9 @@ p2u_sort_kernel(const TQ* __restrict__ xq, int ldq, const TB* __restrict__ xb, P
     __shared__ int posge[QW][128];
     __shared__ double hk[QW][128];
     __shared__ int hv[QW][128];
+    __shared__ double qs_sk[QW][128];
+    __shared__ int qs_sv[QW][128];
+    __shared__ int qs_gp[QW][128];
     __shared__ int s_idx[QW][P2_MAXP];
     __shared__ double s_sim[QW][P2_MAXP];
     __shared__ double s_pred[QW][128];
@@ -898,7 +909,7 @@ p2u_sort_kernel(const TQ* __restrict__ xq, int ldq, const TB* __restrict__ xb, P
         m += __popc(b);
     }
     __syncwarp();
-    warp_qs_topn_big(key, val, m, keep, posge[warp], hk[warp], hv[warp]);
+    warp_qs_topn_big(key, val, m, keep, QsScratch{posge[warp], hk[warp], hv[warp], qs_sk[warp], qs_sv[warp], qs_gp[warp]});
     for (int j = lane; j < keep; j += 32) { s_idx[warp][j] = val[j]; s_sim[warp][j] = key[j]; }
     __syncwarp();
     if (lane == 0) {
