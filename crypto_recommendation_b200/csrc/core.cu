@@ -216,13 +216,17 @@ int crx_points_create(crx_ctx* c, const void* data, int dtype, int64_t n, int32_
     }
     size_t esz = dtype == CRX_F32 ? 4 : 8;
     const void* src = data;
-    void* staged = nullptr;
+    // released on every early return below (CRX_TRY / CRX_CUDA): the half-built object and the staged copy of the caller's rows
+    struct Guard {
+        crx_ctx* c; crx_points* p; void* staged;
+        ~Guard() { if (staged) crx_free(c, staged); if (p) crx_points_destroy(p); }
+    } guard{c, p, nullptr};
     if (mem == CRX_HOST) {
         char* st8 = nullptr;
         CRX_TRY(crx_alloc(c, &st8, (size_t)n * d * esz));   // through the context's cache of large blocks: an upload per step reuses it
-        staged = st8;
-        CRX_CUDA(cudaMemcpyAsync(staged, data, (size_t)n * d * esz, cudaMemcpyHostToDevice, c->stream));
-        src = staged;
+        guard.staged = st8;
+        CRX_CUDA(cudaMemcpyAsync(st8, data, (size_t)n * d * esz, cudaMemcpyHostToDevice, c->stream));
+        src = st8;
     }
     int grid = (int)std::min<int64_t>((int64_t)c->sm_count * 16, (int64_t)((elems + 255) / 256));
     {
@@ -237,8 +241,8 @@ int crx_points_create(crx_ctx* c, const void* data, int dtype, int64_t n, int32_
         else row_sqnorm_kernel<float><<<g, 256, 0, c->stream>>>(p->x32, n, d, p->ld, p->sqn);
     }
     CRX_CUDA(cudaGetLastError());
-    if (staged) crx_free(c, staged);
     if (mem == CRX_HOST) CRX_CUDA(cudaStreamSynchronize(c->stream));  // caller may reuse its buffer
+    guard.p = nullptr;   // built: the caller owns it (the staged copy is still released by the guard, stream-ordered)
     *out = p;
     return CRX_OK;
 }
