@@ -44,6 +44,30 @@ def test_converter_and_abi_writer_agree(tmp_path):
     f.close()
 
 
+def test_converter_follows_the_readers_line_rules(tmp_path):
+    # vector_reader.hpp:67-80: metadata lines in front are skipped, '\r' dropped, the id is the text before the first delimiter,
+    # a trailing delimiter adds no coordinate (getline-based split), any one-character delimiter
+    p = str(tmp_path / "t.tsv")
+    with open(p, "w", newline="") as f:
+        f.write("meta line one\nmeta line two\n")
+        f.write("a\t1.5\t-2e-3\t7\t\r\n")
+        f.write("id with spaces\t0.1\t0.2\t1e308\n")
+        f.write("c\t4.9e-324\t-0.0\t3\t\n")
+    out = str(tmp_path / "t.crxcol")
+    assert csv_to_columnar.convert(p, out, delimiter="\t", skip_lines=2) == (3, 3)
+    f = capi.Columnar(out)
+    assert f.ids() == ["a", "id with spaces", "c"] and (f.n, f.d) == (3, 3)
+    f.close()
+    want = np.array([[1.5, -2e-3, 7.0], [0.1, 0.2, 1e308], [4.9e-324, -0.0, 3.0]])
+    blob = open(out, "rb").read()
+    cols = np.frombuffer(blob[-3 * 3 * 8:], np.float64).reshape(3, 3)
+    assert np.array_equal(cols.T.view(np.uint64), want.view(np.uint64))     # bit for bit, -0.0 and the subnormal included
+    ragged = str(tmp_path / "r.csv")
+    open(ragged, "w").write("a,1,2\nb,1\n")
+    with pytest.raises(SystemExit):
+        csv_to_columnar.convert(ragged, str(tmp_path / "r.crxcol"))
+
+
 def test_damaged_files_are_refused(tmp_path):
     ids, X = sample(40, 5)
     good = str(tmp_path / "g.crxcol")
