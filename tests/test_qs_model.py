@@ -14,7 +14,10 @@ import numpy as np
 import pytest
 
 
-def model(keys, need, passes=None):
+def model(keys, need, passes=None, prefix_min_jump=False):
+    """prefix_min_jump: the remedy DESIGN.md section 9 proposes for lists with long non-increasing tails (NOT in the kernel yet):
+    when every element of the range is >= the pivot, jump straight to the last element that is not a minimum of what precedes
+    it -- one walk instead of one walk per trailing minimum."""
     key = list(keys); val = list(range(len(keys))); n = len(key)
     stack = [(0, n - 1)]
     touched = 0
@@ -28,6 +31,17 @@ def model(keys, need, passes=None):
             if all(key[j] == pivot for j in rng):
                 break
             if cnt == m:
+                if prefix_min_jump:
+                    touched += m
+                    run_min, last = key[lo], None
+                    for j in range(lo + 1, hi):
+                        if key[j] > run_min:
+                            last = j
+                        run_min = min(run_min, key[j])
+                    if last is None:
+                        break          # non-increasing: every remaining step leaves everything where it is
+                    hi = last
+                    continue
                 hi = max(j for j in rng if key[j] > pivot)
                 continue
             p = lo + cnt
@@ -80,6 +94,27 @@ def test_closed_form_partition_matches_literal_quicksort(which, port, ref):
         _, full = oracle.quicksort(s, np.arange(n, dtype=np.int32))
         for need in (int(rng.integers(1, 33)), n):
             assert model(s.tolist(), need) == full[:min(need, n)].tolist(), (n, need)
+
+
+def test_prefix_minimum_jump_gives_the_same_order_and_is_linear_on_descending_tails(port):
+    """The literal quicksort (and the kernel's closed form) walks a descending list once per element; with the jump over
+    trailing prefix minima the same prefix of the order comes out of a few walks.  Specification of the next kernel step."""
+    rng = np.random.default_rng(6)
+    for s in sequences(rng, 1500, 200):
+        n = len(s)
+        if rng.random() < 0.5:   # a non-increasing tail behind a random head
+            s = np.r_[s, np.sort(rng.integers(0, 6, int(rng.integers(1, 80))) / 5.0)[::-1]]
+            n = len(s)
+        _, full = port.quicksort(s, np.arange(n, dtype=np.int32))
+        for need in (int(rng.integers(1, 33)), n):
+            assert model(s.tolist(), need, prefix_min_jump=True) == full[:min(need, n)].tolist(), (n, need)
+    n = 3000
+    s = np.arange(n, 0, -1, dtype=np.float64)
+    _, full = port.quicksort(s, np.arange(n, dtype=np.int32))
+    slow, fast = [], []
+    assert model(s.tolist(), 20, slow) == full[:20].tolist()
+    assert model(s.tolist(), 20, fast, prefix_min_jump=True) == full[:20].tolist()
+    assert slow[0] > n * n // 4 and fast[0] <= 3 * n, (slow, fast)
 
 
 def test_plateau_costs_a_few_passes(port):
